@@ -1,0 +1,178 @@
+"""Generate tests/golden/*.npz by IMPORTING AND RUNNING the reference (`/root/reference`).
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python oracle/make_golden.py
+
+TEST INFRASTRUCTURE ONLY.  Nothing from the reference is copied: its functions are executed and their
+inputs/outputs recorded as small fixtures.
+
+Fixtures
+--------
+res_shift.npz     ``get_res_shifting_latents`` (src/adapters/res_srdiff.py:7-25) on seeded inputs, scalar
+                  and per-sample timesteps.
+log_validation.npz ``log_validation`` (src/adapters/res_srdiff.py:35-105) driven end-to-end with stub
+                  unet / controlnet / vae objects (deterministic closed-form functions) and injected
+                  noise; records every latent the loop handed to the UNet, the timesteps, and the
+                  returned image.  N = 6 and N = 50 steps.
+adapter_xl_*.npz  ``Adapter_XL`` (src/adapters/modules.py:114-157) outputs for small channel configs,
+                  with the module's own initialised weights stored alongside.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = os.environ.get("MRISR_REFERENCE", "/root/reference")
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+sys.path.insert(0, REF)
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from oracle import sched_oracle as so  # noqa: E402
+
+
+class StubScheduler:
+    """Duck-typed stand-in for diffusers DDPMScheduler (absent here): only the attributes the
+    reference reads (res_srdiff.py:13,53-54,60)."""
+
+    def __init__(self):
+        self.alphas_cumprod = so.alphas_cumprod(so.make_betas())
+        self.timesteps = None
+
+    def set_timesteps(self, n, device=None):
+        self.timesteps = torch.from_numpy(so.timesteps(n, 1000, "trailing"))
+
+
+from oracle.make_golden_stub import stub_eps  # noqa: E402  closed-form 'UNet' stand-in
+
+
+def gen_res_shift():
+    from src.adapters.res_srdiff import get_res_shifting_latents
+
+    g = torch.Generator().manual_seed(11)
+    hr = torch.randn(3, 4, 8, 8, generator=g)
+    lr = torch.randn(3, 4, 8, 8, generator=g)
+    noise = torch.randn(3, 4, 8, 8, generator=g)
+    sch = StubScheduler()
+    t_scalar = torch.tensor(979)
+    t_vec = torch.tensor([999, 500, 19])
+    out_scalar = get_res_shifting_latents(hr, lr, t_scalar, sch, noise)
+    out_vec = get_res_shifting_latents(hr, lr, t_vec, sch, noise)
+    np.savez_compressed(os.path.join(OUT, "res_shift.npz"), hr=hr.numpy(), lr=lr.numpy(), noise=noise.numpy(),
+                        t_scalar=t_scalar.numpy(), t_vec=t_vec.numpy(), out_scalar=out_scalar.numpy(),
+                        out_vec=out_vec.numpy(), alphas_cumprod=sch.alphas_cumprod.numpy())
+
+
+def gen_log_validation():
+    import src.adapters.res_srdiff as ref
+
+    out = {}
+    for n_steps in (6, 50):
+        g = torch.Generator().manual_seed(100 + n_steps)
+        lr_img = torch.rand(2, 1, 64, 64, generator=g) * 2 - 1
+        hr_img = torch.rand(2, 1, 64, 64, generator=g) * 2 - 1
+        noises = [torch.randn(1, 4, 8, 8, generator=g) for _ in range(n_steps + 1)]
+        queue = list(noises)
+        rec = {"lat_in": [], "t": [], "ctrl_calls": 0}
+
+        class VAE:
+            config = types.SimpleNamespace(scaling_factor=0.18215)
+
+            def encode(self, x):  # [1,3,64,64] -> latent [1,4,8,8], deterministic
+                lat = torch.nn.functional.avg_pool2d(x, 8)
+                lat = torch.cat([lat, lat[:, :1] * 0.5], dim=1)
+                return types.SimpleNamespace(latent_dist=types.SimpleNamespace(sample=lambda: lat))
+
+            def decode(self, z):
+                img = torch.nn.functional.interpolate(z[:, :1], scale_factor=8, mode="nearest")
+                return types.SimpleNamespace(sample=img)
+
+        class UNet:
+            def eval(self):
+                return self
+
+            def __call__(self, latents, t, encoder_hidden_states=None, down_block_additional_residuals=None,
+                         mid_block_additional_residual=None):
+                rec["lat_in"].append(latents.clone())
+                rec["t"].append(int(t))
+                return types.SimpleNamespace(sample=stub_eps(latents, t))
+
+        class ControlNet:
+            def eval(self):
+                return self
+
+            def __call__(self, latents, t, encoder_hidden_states=None, controlnet_cond=None, return_dict=False):
+                rec["ctrl_calls"] += 1
+                assert tuple(controlnet_cond.shape) == (1, 3, 512, 512)
+                return None, None
+
+        orig = torch.randn_like
+        torch.randn_like = lambda x, *a, **k: queue.pop(0).to(x.dtype)
+        try:
+            img = ref.log_validation(UNet(), ControlNet(), VAE(), [{"hr": hr_img, "lr": lr_img}], StubScheduler(),
+                                     torch.float32, types.SimpleNamespace(device=torch.device("cpu")),
+                                     torch.zeros(1, 77, 768), num_inference_steps=n_steps)
+        finally:
+            torch.randn_like = orig
+        out[f"n{n_steps}_lr_img"] = lr_img.numpy()
+        out[f"n{n_steps}_hr_img"] = hr_img.numpy()
+        out[f"n{n_steps}_noises"] = torch.stack(noises).numpy()
+        out[f"n{n_steps}_noises_left"] = np.int64(len(queue))
+        out[f"n{n_steps}_lat_in"] = torch.stack(rec["lat_in"]).numpy()
+        out[f"n{n_steps}_t"] = np.asarray(rec["t"], dtype=np.int64)
+        out[f"n{n_steps}_image"] = np.asarray(img)
+    np.savez_compressed(os.path.join(OUT, "log_validation.npz"), **out)
+
+
+def gen_prepare_condition():
+    from src.adapters.res_srdiff import prepare_condition_image
+
+    g = torch.Generator().manual_seed(5)
+    a = torch.rand(2, 1, 16, 16, generator=g)
+    out_a = prepare_condition_image(a, target_size=(32, 32))
+    b = torch.rand(1, 3, 32, 32, generator=g)
+    out_b = prepare_condition_image(b, target_size=(32, 32))
+    np.savez_compressed(os.path.join(OUT, "prepare_condition.npz"), a=a.numpy(), out_a=out_a.numpy(), b=b.numpy(),
+                        out_b=out_b.numpy())
+
+
+def gen_adapter():
+    from src.adapters.modules import Adapter_XL
+
+    for tag, kw in (("k3", dict(channels=[8, 16, 32, 32], nums_rb=2, cin=192, ksize=3, sk=True, use_conv=True)),
+                    ("k1", dict(channels=[8, 16, 16, 32], nums_rb=2, cin=192, ksize=1, sk=True, use_conv=True)),
+                    ("pool", dict(channels=[16, 16, 16, 16], nums_rb=1, cin=192, ksize=3, sk=False, use_conv=False))):
+        torch.manual_seed(7)
+        m = Adapter_XL(**kw).eval()
+        x = torch.rand(2, 3, 64, 64) * 2 - 1
+        with torch.no_grad():
+            feats = m(x)
+        d = {f"w::{k}": v.numpy() for k, v in m.state_dict().items()}
+        d["x"] = x.numpy()
+        for i, f in enumerate(feats):
+            d[f"feat{i}"] = f.numpy()
+        d["channels"] = np.asarray(kw["channels"])
+        d["nums_rb"] = np.int64(kw["nums_rb"])
+        d["ksize"] = np.int64(kw["ksize"])
+        d["sk"] = np.int64(kw["sk"])
+        d["use_conv"] = np.int64(kw["use_conv"])
+        np.savez_compressed(os.path.join(OUT, f"adapter_xl_{tag}.npz"), **d)
+    # known answer for the production config (params only)
+    m = Adapter_XL(sk=True)
+    n = sum(p.numel() for p in m.parameters())
+    np.savez_compressed(os.path.join(OUT, "adapter_xl_known.npz"), n_params_sk_true=np.int64(n),
+                        keys=np.asarray(sorted(m.state_dict().keys())))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    gen_res_shift()
+    gen_log_validation()
+    gen_prepare_condition()
+    gen_adapter()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
