@@ -1,0 +1,137 @@
+/* mrisr_b200.h -- C ABI of the B200-native denoising-loop hot path (libmrisr_b200.so).
+ *
+ * The reference (Bernat-C/MRI-Diffusion-SuperResolution) is pure Python and has NO FFI/plugin boundary of
+ * its own: its hot path is `log_validation` (src/adapters/res_srdiff.py:35-105) calling, per step, a
+ * diffusers `UNet2DConditionModel` (call site :73-78) and a hand-written reverse step (:84-96), plus the
+ * T2I-Adapter extractor `Adapter_XL` (src/adapters/modules.py:114-157).  This header therefore declares the
+ * operator-level entry points those Python call sites decompose into; the Python package
+ * `mri_diffusion_superresolution_b200` binds them with ctypes and re-exposes the reference's own function /
+ * class signatures on top.  Each declaration cites the reference code it replaces.
+ *
+ * Conventions: every pointer is a DEVICE pointer unless stated otherwise; the caller owns all buffers
+ * (kernels never allocate); `stream` is a cudaStream_t passed as void*; all functions are asynchronous on
+ * that stream, re-entrant, capturable into a CUDA graph, and return 0 on success or a negative MRISR_E_*
+ * code (mrisr_last_error() gives a thread-local message).  No exceptions cross this boundary.
+ * Activations are bf16, channels-last (NHWC == [tokens, channels]); reductions and the scheduler state are fp32.
+ */
+#ifndef MRISR_B200_H_
+#define MRISR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRISR_ABI_VERSION 1
+
+#define MRISR_OK 0
+#define MRISR_E_INVALID (-1)     /* bad argument (null pointer, misaligned, negative size) */
+#define MRISR_E_UNSUPPORTED (-2) /* shape outside what the sm_100a kernels handle            */
+#define MRISR_E_CUDA (-3)        /* CUDA runtime / driver error                              */
+
+#define MRISR_ACT_NONE 0
+#define MRISR_ACT_RELU 1
+#define MRISR_ACT_SILU 2
+#define MRISR_ACT_GEGLU 3 /* out[:, j] = a_j * gelu_erf(g_j); weight rows interleaved per mrisr_gemm_block_n */
+
+int mrisr_abi_version(void);
+const char* mrisr_last_error(void);
+/* Number of SMs / compute capability (major*10+minor) of the current device; negative error code otherwise. */
+int mrisr_device_info(int* sm_count, int* cc);
+
+/* --- scheduler ------------------------------------------------------------------------------------------
+ * Replaces the ~12 eager elementwise ops of the manual Res-SRDiff reverse step, src/adapters/res_srdiff.py:85-96
+ * (and, with c3 = c4 = 0, diffusers DDIMScheduler.step as used by BASELINE configs 2-3):
+ *     out = c1*x + c2*eps + c3*lr + c4*z,   coef = {c1,c2,c3,c4} (DEVICE fp32[4]; host precomputes the table)
+ * x/eps/lr/z/out: fp32 [n]; lr and z may be NULL; out may alias x.  n % 4 == 0. */
+int mrisr_sched_step(const float* x, const float* eps, const float* lr, const float* z, float* out, int64_t n,
+                     const float* coef, void* stream);
+
+/* Replaces get_res_shifting_latents, src/adapters/res_srdiff.py:7-25:
+ *     out[b] = sa[b]*hr[b] + (1-sa[b])*lr[b] + s1[b]*noise[b],  coef = DEVICE fp32 [batch][2] = {sqrt(abar_t), sqrt(1-abar_t)} */
+int mrisr_res_shift(const float* hr, const float* lr, const float* noise, float* out, int64_t n_per_sample, int batch,
+                    const float* coef, void* stream);
+
+/* Selects row *idx of a device table (per-step time-embedding projections / step coefficients) and advances the
+ * device-side step counter -- lets one captured CUDA graph replay all N steps of the loop (res_srdiff.py:63). */
+int mrisr_select_row(const float* table, const int* idx, int64_t stride, float* dst, int n, void* stream);
+int mrisr_advance_index(int* idx, void* stream);
+
+/* --- UNet building blocks (diffusers UNet2DConditionModel.forward; call site src/adapters/res_srdiff.py:73-78) */
+
+/* diffusers get_timestep_embedding(flip_sin_to_cos=True, downscale_freq_shift=0): t fp32[batch] -> bf16 [batch, dim] = [cos|sin]. */
+int mrisr_timestep_embedding(const float* t, void* out_bf16, int batch, int dim, void* stream);
+
+/* GroupNorm (+ optional SiLU) over NHWC bf16 whose channels are the concat of x1 [B,HW,c1] (pixel stride ld1) and
+ * optional x2 [B,HW,c2] (UNet skip concat, diffusers `torch.cat([h, skip], 1)`), writing dense bf16 [B,HW,c1+c2].
+ * workspace: fp32, at least mrisr_groupnorm_workspace_floats(batch, groups). c1, c2 % 8 == 0; groups <= 64. */
+int64_t mrisr_groupnorm_workspace_floats(int batch, int groups);
+int mrisr_groupnorm(const void* x1, int64_t ld1, int c1, const void* x2, int64_t ld2, int c2, int batch, int hw,
+                    int groups, const float* gamma, const float* beta, float eps, int silu, void* out,
+                    float* workspace, void* stream);
+
+/* LayerNorm over the last dim: bf16 [rows, C] (row stride ldx) -> bf16 [rows, C] (row stride ldo). C % 8 == 0, C <= 2048. */
+int mrisr_layernorm(const void* x, int64_t ldx, const float* gamma, const float* beta, float eps, void* out,
+                    int64_t ldo, int rows, int C, void* stream);
+
+/* Tensor-core GEMM / implicit-GEMM conv (tcgen05 + TMEM + TMA):
+ *     out[M, n_store] = act( concat_K(A1, A2) (*) W^T + bias + rowvec[batch(m)] ) + res1 + res2
+ * taps == 1: A1 [M, k1] (row stride lda1), A2 [M, k2] optional -- Linear layers, 1x1 convs, LoRA rank extension.
+ * taps == 9: A1/A2 are NHWC [B, H, W, k] activations (pixel strides lda1/lda2); 3x3, stride 1, pad 1 convolution;
+ *            M = B*H*W; W and H powers of two, W <= 128 (the TMA box is {64ch, W, 128/W rows}).
+ * W: bf16 [N, taps*(k1+k2)] K-major, k index = tap*(k1+k2) + channel.  N % mrisr_gemm_block_n(N, act) == 0.
+ * k1, k2 % 64 == 0.  bias fp32 [N] or NULL.  rowvec fp32: added before act, row m uses
+ * rowvec[(m / rows_per_batch) * rowvec_stride + n] (time-embedding projection; NULL = none).
+ * res1/res2: bf16 [M, *] row strides ldr1/ldr2, added after act (NULL = none).
+ * out: bf16 (out_fp32 = 0) or fp32, row stride ldo; only columns < n_store are written (GEGLU: n_store <= N/2). */
+typedef struct mrisr_gemm_args {
+  int32_t M, N, n_store;
+  int32_t k1, k2, taps;
+  int32_t H, W;
+  const void* a1;
+  int64_t lda1;
+  const void* a2;
+  int64_t lda2;
+  const void* w;
+  const float* bias;
+  const float* rowvec;
+  int64_t rowvec_stride;
+  int32_t rows_per_batch;
+  int32_t act;
+  const void* res1;
+  int64_t ldr1;
+  const void* res2;
+  int64_t ldr2;
+  void* out;
+  int64_t ldo;
+  int32_t out_fp32;
+  int32_t reserved;
+} mrisr_gemm_args;
+int mrisr_gemm(const mrisr_gemm_args* args, void* stream);
+/* N-tile the kernel will use for (N, act); GEGLU callers interleave weight/bias rows in blocks of this size:
+ * rows [t*BN, t*BN+BN/2) = value half, rows [t*BN+BN/2, (t+1)*BN) = gate half of output columns [t*BN/2, (t+1)*BN/2). */
+int mrisr_gemm_block_n(int N, int act);
+
+/* Fused softmax(Q K^T / sqrt(d)) V (diffusers Attention -> F.scaled_dot_product_attention), all heads.
+ * q: bf16 rows [batch*nq], row stride ldq, head h at columns [h*d, (h+1)*d); k, v likewise with nk rows per batch
+ * (kv_broadcast != 0: one [nk, .] context shared by every batch element -- the fixed prompt, res_srdiff.py:67,75).
+ * o: bf16 [batch*nq, heads*d] (row stride ldo). d in {8,16,32,40,64,80,160}. */
+int mrisr_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                    int64_t ldo, int batch, int nq, int nk, int heads, int d, int kv_broadcast, void* stream);
+
+/* Layout / resampling helpers around the tensor-core kernels (all NHWC bf16 unless stated). */
+int mrisr_upsample2x(const void* in, void* out, int B, int H, int W, int C, void* stream);          /* diffusers Upsample2D (nearest) */
+int mrisr_im2col3x3s2(const void* in, void* out, int B, int H, int W, int C, void* stream);         /* diffusers Downsample2D / modules.py:52-76 */
+int mrisr_im2col_first(const float* in_nchw, void* out, int B, int Cin, int H, int W, int kpad, void* stream); /* UNet conv_in */
+int mrisr_pixel_unshuffle_nhwc(const float* in_nchw, void* out, int B, int C, int Hin, int Win, int r, void* stream); /* modules.py:148 */
+int mrisr_avgpool2(const void* in, void* out, int B, int H, int W, int C, void* stream);            /* modules.py:70-72 */
+int mrisr_add(const void* a, const void* b, void* out, int64_t n, void* stream);                    /* skips += residual (res_srdiff.py:76-77) */
+/* [B, R, Cc] -> [B, Cc, R].  dtype codes: 0 = fp32, 1 = bf16.  NCHW->NHWC: R = C, Cc = H*W.  NHWC->NCHW: R = H*W, Cc = C. */
+int mrisr_transpose(const void* src, int src_dtype, void* dst, int dst_dtype, int B, int R, int Cc, void* stream);
+int mrisr_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRISR_B200_H_ */

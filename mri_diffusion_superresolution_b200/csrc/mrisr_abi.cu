@@ -1,0 +1,477 @@
+// C-ABI entry points of libmrisr_b200.so (declared in include/mrisr_b200.h).  Host-side only: argument
+// validation, TMA descriptor encoding, launch configuration.  No torch types, no allocation, no CPU compute path.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/mrisr_b200.h"
+#include "attention.cuh"
+#include "gemm_tcgen05.cuh"
+#include "pointwise.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define MRISR_CHECK_CUDA(expr)                                                              \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) return fail(MRISR_E_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define MRISR_REQUIRE(cond, ...) \
+  do {                           \
+    if (!(cond)) return fail(MRISR_E_INVALID, __VA_ARGS__); \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
+
+int g_sm_count = 0;
+int sm_count() {
+  if (g_sm_count == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+    g_sm_count = n;
+  }
+  return g_sm_count;
+}
+
+inline int grid_for(long long work_items, int threads, int per_sm = 8) {
+  long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = static_cast<long long>(sm_count()) * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+// ---- TMA descriptor encoding through the driver entry point (no link-time libcuda dependency)
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+int load_encode() {
+  if (g_encode != nullptr) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || fn == nullptr)
+    return fail(MRISR_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e));
+  g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  return 0;
+}
+
+// bf16 tensor, `rank` dims (innermost first), byte strides for dims 1..rank-1, 128B swizzle, zero OOB fill.
+int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+               const cuuint32_t* box) {
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(ptr), dims,
+                        strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MRISR_E_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", static_cast<int>(r));
+  return 0;
+}
+
+template <int BN>
+int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const mrisr::GemmKernelParams& p,
+                cudaStream_t st) {
+  using Cfg = mrisr::GemmCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    MRISR_CHECK_CUDA(cudaFuncSetAttribute(mrisr::gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  mrisr::gemm_tcgen05_kernel<BN><<<grid, mrisr::kGemmThreads, Cfg::kSmemBytes, st>>>(a1, a2, b, p);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int D>
+int launch_attention(const mrisr::AttnArgs& a, cudaStream_t st) {
+  using Cfg = mrisr::AttnCfg<D>;
+  static bool configured = false;
+  if (!configured) {
+    MRISR_CHECK_CUDA(cudaFuncSetAttribute(mrisr::attention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          Cfg::kSmemBytes));
+    configured = true;
+  }
+  dim3 grid((a.nq + mrisr::kAttnBM - 1) / mrisr::kAttnBM, a.heads, a.batch);
+  mrisr::attention_kernel<D><<<grid, mrisr::kAttnThreads, Cfg::kSmemBytes, st>>>(a);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int VPL>
+int launch_layernorm(const void* x, int64_t ldx, const float* g, const float* b, float eps, void* out, int64_t ldo, int rows,
+                     int C, cudaStream_t st) {
+  const int wpb = 8;
+  mrisr::layernorm_kernel<VPL><<<(rows + wpb - 1) / wpb, wpb * 32, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(x), ldx, g, b, eps, static_cast<__nv_bfloat16*>(out), ldo, rows, C);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+constexpr int kGnMaxSlabs = 64;
+
+}  // namespace
+
+extern "C" {
+
+int mrisr_abi_version(void) { return MRISR_ABI_VERSION; }
+const char* mrisr_last_error(void) { return g_err; }
+
+int mrisr_device_info(int* sms, int* cc) {
+  int dev = 0, major = 0, minor = 0, n = 0;
+  MRISR_CHECK_CUDA(cudaGetDevice(&dev));
+  MRISR_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  MRISR_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  MRISR_CHECK_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (sms) *sms = n;
+  if (cc) *cc = major * 10 + minor;
+  return 0;
+}
+
+int mrisr_sched_step(const float* x, const float* eps, const float* lr, const float* z, float* out, int64_t n,
+                     const float* coef, void* stream) {
+  MRISR_REQUIRE(x && eps && out && coef, "sched_step: null pointer");
+  MRISR_REQUIRE(n >= 0 && n % 4 == 0, "sched_step: n (%lld) must be a non-negative multiple of 4", (long long)n);
+  MRISR_REQUIRE(aligned16(x) && aligned16(eps) && aligned16(out) && (!lr || aligned16(lr)) && (!z || aligned16(z)),
+                "sched_step: pointers must be 16-byte aligned");
+  if (n == 0) return 0;
+  const long long n4 = n / 4;
+  mrisr::sched_step_kernel<<<grid_for(n4, 256, 8), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(eps), reinterpret_cast<const float4*>(lr),
+      reinterpret_cast<const float4*>(z), reinterpret_cast<float4*>(out), n4, coef);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mrisr_res_shift(const float* hr, const float* lr, const float* noise, float* out, int64_t n_per_sample, int batch,
+                    const float* coef, void* stream) {
+  MRISR_REQUIRE(hr && lr && noise && out && coef, "res_shift: null pointer");
+  MRISR_REQUIRE(batch >= 0 && n_per_sample >= 0 && n_per_sample % 4 == 0, "res_shift: bad sizes");
+  MRISR_REQUIRE(aligned16(hr) && aligned16(lr) && aligned16(noise) && aligned16(out), "res_shift: misaligned pointer");
+  if (batch == 0 || n_per_sample == 0) return 0;
+  const long long n4 = n_per_sample / 4;
+  mrisr::res_shift_kernel<<<grid_for(n4 * batch, 256, 8), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(hr), reinterpret_cast<const float4*>(lr), reinterpret_cast<const float4*>(noise),
+      reinterpret_cast<float4*>(out), n4, batch, coef);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mrisr_select_row(const float* table, const int* idx, int64_t stride, float* dst, int n, void* stream) {
+  MRISR_REQUIRE(table && idx && dst && n >= 0, "select_row: bad argument");
+  if (n == 0) return 0;
+  mrisr::select_row_kernel<<<grid_for(n, 256, 2), 256, 0, as_stream(stream)>>>(table, idx, stride, dst, n);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mrisr_advance_index(int* idx, void* stream) {
+  MRISR_REQUIRE(idx, "advance_index: null pointer");
+  mrisr::advance_index_kernel<<<1, 32, 0, as_stream(stream)>>>(idx);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mrisr_timestep_embedding(const float* t, void* out, int batch, int dim, void* stream) {
+  MRISR_REQUIRE(t && out && batch > 0 && dim > 0 && dim % 2 == 0, "timestep_embedding: bad argument");
+  const int n = batch * (dim / 2);
+  mrisr::timestep_embedding_kernel<<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(
+      t, static_cast<__nv_bfloat16*>(out), batch, dim);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int64_t mrisr_groupnorm_workspace_floats(int batch, int groups) {
+  return static_cast<int64_t>(batch) * kGnMaxSlabs * groups * 2;
+}
+
+int mrisr_groupnorm(const void* x1, int64_t ld1, int c1, const void* x2, int64_t ld2, int c2, int batch, int hw, int groups,
+                    const float* gamma, const float* beta, float eps, int silu, void* out, float* workspace,
+                    void* stream) {
+  MRISR_REQUIRE(x1 && gamma && beta && out && workspace, "groupnorm: null pointer");
+  MRISR_REQUIRE(batch > 0 && hw > 0 && c1 > 0 && c2 >= 0, "groupnorm: bad sizes");
+  if (c2 == 0) { x2 = nullptr; ld2 = 0; }
+  MRISR_REQUIRE(c2 == 0 || x2, "groupnorm: c2 > 0 but x2 is null");
+  const int C = c1 + c2;
+  MRISR_REQUIRE(c1 % 8 == 0 && c2 % 8 == 0 && ld1 % 8 == 0 && ld2 % 8 == 0, "groupnorm: channels/strides must be multiples of 8");
+  MRISR_REQUIRE(groups > 0 && groups <= 64 && C % groups == 0, "groupnorm: groups must divide C and be <= 64");
+  MRISR_REQUIRE(aligned16(x1) && aligned16(out) && (!x2 || aligned16(x2)), "groupnorm: misaligned pointer");
+  const int nvec = C / 8;
+  if (nvec > 1024) return fail(MRISR_E_UNSUPPORTED, "groupnorm: C = %d > 8192 unsupported", C);
+  int R = 256 / nvec;
+  if (R < 1) R = 1;
+  if (R > hw) R = hw;
+  int want = (296 + batch - 1) / batch;
+  int max_slabs = (hw + 4 * R - 1) / (4 * R);
+  int nslab = want < max_slabs ? want : max_slabs;
+  if (nslab > kGnMaxSlabs) nslab = kGnMaxSlabs;
+  if (nslab < 1) nslab = 1;
+  const int pps = (hw + nslab - 1) / nslab;
+  nslab = (hw + pps - 1) / pps;
+  mrisr::GnArgs a;
+  a.x1 = static_cast<const __nv_bfloat16*>(x1);
+  a.x2 = static_cast<const __nv_bfloat16*>(x2);
+  a.ld1 = ld1; a.ld2 = ld2; a.c1 = c1; a.c2 = c2; a.hw = hw; a.batch = batch; a.groups = groups;
+  a.nslab = nslab; a.pix_per_slab = pps;
+  dim3 block(nvec, R), grid(nslab, batch);
+  cudaStream_t st = as_stream(stream);
+  mrisr::groupnorm_stats_kernel<<<grid, block, 0, st>>>(a, reinterpret_cast<float2*>(workspace));
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  mrisr::groupnorm_apply_kernel<<<grid, block, 2 * C * sizeof(float), st>>>(
+      a, reinterpret_cast<const float2*>(workspace), gamma, beta, eps, silu, static_cast<__nv_bfloat16*>(out), nslab);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mrisr_layernorm(const void* x, int64_t ldx, const float* gamma, const float* beta, float eps, void* out, int64_t ldo,
+                    int rows, int C, void* stream) {
+  MRISR_REQUIRE(x && gamma && beta && out, "layernorm: null pointer");
+  MRISR_REQUIRE(rows >= 0 && C > 0 && C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0, "layernorm: C and strides must be multiples of 8");
+  MRISR_REQUIRE(aligned16(x) && aligned16(out) && aligned16(gamma) && aligned16(beta), "layernorm: misaligned pointer");
+  if (rows == 0) return 0;
+  const int vpl = (C / 8 + 31) / 32;
+  cudaStream_t st = as_stream(stream);
+  switch (vpl) {
+    case 1: return launch_layernorm<1>(x, ldx, gamma, beta, eps, out, ldo, rows, C, st);
+    case 2: return launch_layernorm<2>(x, ldx, gamma, beta, eps, out, ldo, rows, C, st);
+    case 3: return launch_layernorm<3>(x, ldx, gamma, beta, eps, out, ldo, rows, C, st);
+    case 4: return launch_layernorm<4>(x, ldx, gamma, beta, eps, out, ldo, rows, C, st);
+    case 5: return launch_layernorm<5>(x, ldx, gamma, beta, eps, out, ldo, rows, C, st);
+    case 6: case 7: case 8: return launch_layernorm<8>(x, ldx, gamma, beta, eps, out, ldo, rows, C, st);
+    default: return fail(MRISR_E_UNSUPPORTED, "layernorm: C = %d > 2048 unsupported", C);
+  }
+}
+
+int mrisr_gemm_block_n(int N, int act) {
+  if (N <= 0) return 0;
+  if (act == MRISR_ACT_GEGLU) {
+    if (N % 256 == 0) return 256;
+    if (N % 128 == 0) return 128;
+    if (N % 64 == 0) return 64;
+    return 0;
+  }
+  if (N % 256 == 0) return 256;
+  if (N % 160 == 0) return 160;
+  if (N % 128 == 0) return 128;
+  if (N % 64 == 0) return 64;
+  return 0;
+}
+
+int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
+  MRISR_REQUIRE(g != nullptr, "gemm: null args");
+  MRISR_REQUIRE(g->a1 && g->w && g->out, "gemm: null a1/w/out");
+  MRISR_REQUIRE(g->M > 0 && g->N > 0 && g->n_store > 0, "gemm: M, N, n_store must be positive");
+  MRISR_REQUIRE(g->taps == 1 || g->taps == 9, "gemm: taps must be 1 or 9");
+  MRISR_REQUIRE(g->k1 > 0 && g->k1 % 64 == 0 && g->k2 >= 0 && g->k2 % 64 == 0, "gemm: k1 (%d) / k2 (%d) must be multiples of 64", g->k1, g->k2);
+  MRISR_REQUIRE(g->k2 == 0 || g->a2, "gemm: k2 > 0 but a2 is null");
+  MRISR_REQUIRE(g->act >= 0 && g->act <= 3, "gemm: bad act");
+  const int BN = mrisr_gemm_block_n(g->N, g->act);
+  if (BN == 0) return fail(MRISR_E_UNSUPPORTED, "gemm: N = %d is not a multiple of 64", g->N);
+  const int out_cols = g->act == MRISR_ACT_GEGLU ? g->N / 2 : g->N;
+  MRISR_REQUIRE(g->n_store <= out_cols, "gemm: n_store (%d) > produced columns (%d)", g->n_store, out_cols);
+  MRISR_REQUIRE(aligned16(g->a1) && aligned16(g->w) && (!g->a2 || aligned16(g->a2)), "gemm: a1/a2/w must be 16-byte aligned");
+  MRISR_REQUIRE(g->lda1 % 8 == 0 && g->lda1 >= g->k1 && (g->k2 == 0 || (g->lda2 % 8 == 0 && g->lda2 >= g->k2)), "gemm: lda must be a multiple of 8 and >= k");
+  const int esz = g->out_fp32 ? 4 : 2;
+  MRISR_REQUIRE(aligned16(g->out) && (g->ldo * esz) % 16 == 0, "gemm: out must be 16-byte aligned with 16-byte row pitch");
+  MRISR_REQUIRE((!g->res1 || (aligned16(g->res1) && g->ldr1 % 8 == 0)) && (!g->res2 || (aligned16(g->res2) && g->ldr2 % 8 == 0)), "gemm: residuals must be 16-byte aligned");
+  MRISR_REQUIRE(!g->rowvec || g->rows_per_batch > 0, "gemm: rowvec needs rows_per_batch > 0");
+  MRISR_REQUIRE(!(g->act == MRISR_ACT_GEGLU && g->rowvec), "gemm: rowvec unsupported with GEGLU");
+  if (int e = load_encode()) return e;
+
+  const int ktot = g->taps * (g->k1 + g->k2);
+  CUtensorMap ma1, ma2, mb;
+  {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(ktot), static_cast<cuuint64_t>(g->N)};
+    cuuint64_t str[1] = {static_cast<cuuint64_t>(ktot) * 2};
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(BN)};
+    if (int e = encode_map(&mb, g->w, 2, dims, str, box)) return e;
+  }
+  if (g->taps == 1) {
+    cuuint32_t box[2] = {64, 128};
+    {
+      cuuint64_t dims[2] = {static_cast<cuuint64_t>(g->k1), static_cast<cuuint64_t>(g->M)};
+      cuuint64_t str[1] = {static_cast<cuuint64_t>(g->lda1) * 2};
+      if (int e = encode_map(&ma1, g->a1, 2, dims, str, box)) return e;
+    }
+    if (g->k2 > 0) {
+      cuuint64_t dims[2] = {static_cast<cuuint64_t>(g->k2), static_cast<cuuint64_t>(g->M)};
+      cuuint64_t str[1] = {static_cast<cuuint64_t>(g->lda2) * 2};
+      if (int e = encode_map(&ma2, g->a2, 2, dims, str, box)) return e;
+    } else {
+      ma2 = ma1;
+    }
+  } else {
+    const int H = g->H, W = g->W;
+    if (!is_pow2(H) || !is_pow2(W) || W > 128)
+      return fail(MRISR_E_UNSUPPORTED, "gemm(conv3x3): H (%d) and W (%d) must be powers of two, W <= 128", H, W);
+    MRISR_REQUIRE(g->M % (H * W) == 0, "gemm(conv3x3): M must be batch*H*W");
+    const int B = g->M / (H * W);
+    const int TH = (128 / W) < H ? (128 / W) : H;
+    const int TB = 128 / (W * TH);
+    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(W), static_cast<cuuint32_t>(TH), static_cast<cuuint32_t>(TB)};
+    {
+      cuuint64_t dims[4] = {static_cast<cuuint64_t>(g->k1), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(B)};
+      cuuint64_t str[3] = {static_cast<cuuint64_t>(g->lda1) * 2, static_cast<cuuint64_t>(g->lda1) * 2 * W, static_cast<cuuint64_t>(g->lda1) * 2 * W * H};
+      if (int e = encode_map(&ma1, g->a1, 4, dims, str, box)) return e;
+    }
+    if (g->k2 > 0) {
+      cuuint64_t dims[4] = {static_cast<cuuint64_t>(g->k2), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(B)};
+      cuuint64_t str[3] = {static_cast<cuuint64_t>(g->lda2) * 2, static_cast<cuuint64_t>(g->lda2) * 2 * W, static_cast<cuuint64_t>(g->lda2) * 2 * W * H};
+      if (int e = encode_map(&ma2, g->a2, 4, dims, str, box)) return e;
+    } else {
+      ma2 = ma1;
+    }
+  }
+
+  mrisr::GemmKernelParams p;
+  p.M = g->M; p.N = g->N; p.n_store = g->n_store;
+  p.kc1 = g->k1 / 64; p.kc2 = g->k2 / 64; p.taps = g->taps; p.conv = g->taps == 9 ? 1 : 0;
+  p.H = g->H; p.W = g->W;
+  p.m_tiles = (g->M + 127) / 128; p.n_tiles = g->N / BN;
+  p.bias = g->bias; p.rowvec = g->rowvec; p.rowvec_stride = g->rowvec_stride;
+  p.rows_per_batch = g->rows_per_batch > 0 ? g->rows_per_batch : 1;
+  p.act = g->act;
+  p.res1 = static_cast<const __nv_bfloat16*>(g->res1); p.ldr1 = g->ldr1;
+  p.res2 = static_cast<const __nv_bfloat16*>(g->res2); p.ldr2 = g->ldr2;
+  p.out = g->out; p.ldo = g->ldo; p.out_fp32 = g->out_fp32;
+  cudaStream_t st = as_stream(stream);
+  switch (BN) {
+    case 256: return launch_gemm<256>(ma1, ma2, mb, p, st);
+    case 160: return launch_gemm<160>(ma1, ma2, mb, p, st);
+    case 128: return launch_gemm<128>(ma1, ma2, mb, p, st);
+    default: return launch_gemm<64>(ma1, ma2, mb, p, st);
+  }
+}
+
+int mrisr_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
+                    int batch, int nq, int nk, int heads, int d, int kv_broadcast, void* stream) {
+  MRISR_REQUIRE(q && k && v && o, "attention: null pointer");
+  MRISR_REQUIRE(batch > 0 && nq > 0 && nk > 0 && heads > 0, "attention: bad sizes");
+  MRISR_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o), "attention: misaligned pointer");
+  MRISR_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 2 == 0, "attention: row strides must be multiples of 8");
+  mrisr::AttnArgs a;
+  a.q = static_cast<const __nv_bfloat16*>(q); a.ldq = ldq; a.q_batch_rows = nq;
+  a.k = static_cast<const __nv_bfloat16*>(k); a.ldk = ldk;
+  a.v = static_cast<const __nv_bfloat16*>(v); a.ldv = ldv; a.kv_batch_rows = kv_broadcast ? 0 : nk;
+  a.o = static_cast<__nv_bfloat16*>(o); a.ldo = ldo;
+  a.nq = nq; a.nk = nk; a.heads = heads; a.batch = batch;
+  a.scale_log2 = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(d)));
+  cudaStream_t st = as_stream(stream);
+  switch (d) {
+    case 8: return launch_attention<8>(a, st);
+    case 16: return launch_attention<16>(a, st);
+    case 32: return launch_attention<32>(a, st);
+    case 40: return launch_attention<40>(a, st);
+    case 64: return launch_attention<64>(a, st);
+    case 80: return launch_attention<80>(a, st);
+    case 160: return launch_attention<160>(a, st);
+    default: return fail(MRISR_E_UNSUPPORTED, "attention: head dim %d unsupported (8,16,32,40,64,80,160)", d);
+  }
+}
+
+int mrisr_upsample2x(const void* in, void* out, int B, int H, int W, int C, void* stream) {
+  MRISR_REQUIRE(in && out && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "upsample2x: bad argument");
+  MRISR_REQUIRE(aligned16(in) && aligned16(out), "upsample2x: misaligned pointer");
+  const long long n = static_cast<long long>(B) * H * W * (C / 8);
+  mrisr::upsample2x_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(
+      static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H, W, C / 8);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mrisr_im2col3x3s2(const void* in, void* out, int B, int H, int W, int C, void* stream) {
+  MRISR_REQUIRE(in && out && B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 8 == 0, "im2col3x3s2: bad argument");
+  MRISR_REQUIRE(aligned16(in) && aligned16(out), "im2col3x3s2: misaligned pointer");
+  const long long n = static_cast<long long>(B) * (H / 2) * (W / 2) * 9 * (C / 8);
+  mrisr::im2col3x3s2_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(
+      static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H, W, C / 8);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mrisr_im2col_first(const float* in, void* out, int B, int Cin, int H, int W, int kpad, void* stream) {
+  MRISR_REQUIRE(in && out && B > 0 && Cin > 0 && H > 0 && W > 0 && kpad >= 9 * Cin && kpad % 64 == 0, "im2col_first: bad argument");
+  const long long n = static_cast<long long>(B) * H * W * kpad;
+  mrisr::im2col_first_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(in, static_cast<__nv_bfloat16*>(out), B, Cin, H, W, kpad);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mrisr_pixel_unshuffle_nhwc(const float* in, void* out, int B, int C, int Hin, int Win, int r, void* stream) {
+  MRISR_REQUIRE(in && out && B > 0 && C > 0 && r > 0 && Hin % r == 0 && Win % r == 0, "pixel_unshuffle: bad argument");
+  const long long n = static_cast<long long>(B) * C * Hin * Win;
+  mrisr::pixel_unshuffle_nhwc_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(in, static_cast<__nv_bfloat16*>(out), B, C, Hin, Win, r);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mrisr_avgpool2(const void* in, void* out, int B, int H, int W, int C, void* stream) {
+  MRISR_REQUIRE(in && out && B > 0 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 8 == 0, "avgpool2: bad argument");
+  MRISR_REQUIRE(aligned16(in) && aligned16(out), "avgpool2: misaligned pointer");
+  const long long n = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 8);
+  mrisr::avgpool2_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H, W, C / 8);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mrisr_add(const void* a, const void* b, void* out, int64_t n, void* stream) {
+  MRISR_REQUIRE(a && b && out && n >= 0 && n % 8 == 0, "add: bad argument");
+  MRISR_REQUIRE(aligned16(a) && aligned16(b) && aligned16(out), "add: misaligned pointer");
+  if (n == 0) return 0;
+  mrisr::add_bf16_kernel<<<grid_for(n / 8, 256, 8), 256, 0, as_stream(stream)>>>(
+      static_cast<const uint4*>(a), static_cast<const uint4*>(b), static_cast<uint4*>(out), n / 8);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mrisr_transpose(const void* src, int sdt, void* dst, int ddt, int B, int R, int Cc, void* stream) {
+  MRISR_REQUIRE(src && dst && B > 0 && R > 0 && Cc > 0, "transpose: bad argument");
+  MRISR_REQUIRE((sdt == 0 || sdt == 1) && (ddt == 0 || ddt == 1), "transpose: dtype codes are 0 (fp32) / 1 (bf16)");
+  dim3 block(32, 8), grid((Cc + 31) / 32, (R + 31) / 32, B);
+  cudaStream_t st = as_stream(stream);
+  if (sdt == 0 && ddt == 0)
+    mrisr::transpose_kernel<float, float><<<grid, block, 0, st>>>(static_cast<const float*>(src), static_cast<float*>(dst), R, Cc);
+  else if (sdt == 0 && ddt == 1)
+    mrisr::transpose_kernel<float, __nv_bfloat16><<<grid, block, 0, st>>>(static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst), R, Cc);
+  else if (sdt == 1 && ddt == 0)
+    mrisr::transpose_kernel<__nv_bfloat16, float><<<grid, block, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<float*>(dst), R, Cc);
+  else
+    mrisr::transpose_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, block, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), R, Cc);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mrisr_cast(const void* src, int sdt, void* dst, int ddt, int64_t n, void* stream) {
+  MRISR_REQUIRE(src && dst && n >= 0, "cast: bad argument");
+  if (n == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  if (sdt == 0 && ddt == 1)
+    mrisr::cast_f32_bf16_kernel<<<grid_for(n, 256, 8), 256, 0, st>>>(static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst), n);
+  else if (sdt == 1 && ddt == 0)
+    mrisr::cast_bf16_f32_kernel<<<grid_for(n, 256, 8), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<float*>(dst), n);
+  else
+    return fail(MRISR_E_INVALID, "cast: only fp32<->bf16 supported");
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

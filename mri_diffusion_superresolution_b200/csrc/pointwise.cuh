@@ -1,0 +1,386 @@
+// HBM-bound kernels of the denoising loop: scheduler step, forward shifting, GroupNorm (NHWC, two-source
+// concat), LayerNorm, timestep sinusoid, nearest-2x upsample, stride-2 im2col, layout conversion.
+// All are 128-bit vectorised, coalesced along the channel (innermost) dimension, fp32 math.
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "ptx.cuh"
+
+namespace mrisr {
+
+__device__ __forceinline__ void unpack8(const uint4& x, float (&f)[8]) {
+  f[0] = bf16_lo(x.x); f[1] = bf16_hi(x.x); f[2] = bf16_lo(x.y); f[3] = bf16_hi(x.y);
+  f[4] = bf16_lo(x.z); f[5] = bf16_hi(x.z); f[6] = bf16_lo(x.w); f[7] = bf16_hi(x.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Scheduler step (reference src/adapters/res_srdiff.py:84-96):
+//   x' = c1*x + c2*eps + c3*lr + c4*z      coef = {c1,c2,c3,c4} read from device memory (graph-replayable)
+// lr / z may be null (DDIM: c3 = c4 = 0).  fp32 state, in-place allowed.  n4 = n / 4.
+__global__ void sched_step_kernel(const float4* __restrict__ x, const float4* __restrict__ eps,
+                                  const float4* __restrict__ lr, const float4* __restrict__ z, float4* out,
+                                  long long n4, const float* __restrict__ coef) {
+  const float c1 = __ldg(coef), c2 = __ldg(coef + 1), c3 = __ldg(coef + 2), c4 = __ldg(coef + 3);
+  const bool use_lr = lr != nullptr && c3 != 0.f;
+  const bool use_z = z != nullptr && c4 != 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = x[i], e = __ldg(eps + i);
+    float4 r = make_float4(c1 * a.x + c2 * e.x, c1 * a.y + c2 * e.y, c1 * a.z + c2 * e.z, c1 * a.w + c2 * e.w);
+    if (use_lr) {
+      const float4 l = __ldg(lr + i);
+      r.x += c3 * l.x; r.y += c3 * l.y; r.z += c3 * l.z; r.w += c3 * l.w;
+    }
+    if (use_z) {
+      const float4 q = __ldg(z + i);
+      r.x += c4 * q.x; r.y += c4 * q.y; r.z += c4 * q.z; r.w += c4 * q.w;
+    }
+    out[i] = r;
+  }
+}
+
+// Forward shifting (row F; reference src/adapters/res_srdiff.py:7-25):
+//   x_t = sa[b]*hr + (1 - sa[b])*lr + s1[b]*noise, coef[b] = {sqrt(abar_t), sqrt(1-abar_t)} per sample.
+__global__ void res_shift_kernel(const float4* __restrict__ hr, const float4* __restrict__ lr,
+                                 const float4* __restrict__ noise, float4* __restrict__ out, long long n4_per_sample,
+                                 int batch, const float* __restrict__ coef) {
+  const long long total = n4_per_sample * batch;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = static_cast<int>(i / n4_per_sample);
+    const float sa = __ldg(coef + 2 * b), s1 = __ldg(coef + 2 * b + 1);
+    const float4 h = __ldg(hr + i), l = __ldg(lr + i), q = __ldg(noise + i);
+    const float ia = 1.f - sa;
+    out[i] = make_float4(sa * h.x + ia * l.x + s1 * q.x, sa * h.y + ia * l.y + s1 * q.y,
+                         sa * h.z + ia * l.z + s1 * q.z, sa * h.w + ia * l.w + s1 * q.w);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Sinusoidal timestep embedding, diffusers convention (flip_sin_to_cos, shift 0): [cos | sin], bf16 out.
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ out, int batch,
+                                          int dim) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch * half) return;
+  const int b = i / half, j = i % half;
+  const float freq = expf(-9.210340371976184f * static_cast<float>(j) / static_cast<float>(half));
+  const float ang = __ldg(t + b) * freq;
+  out[(long long)b * dim + j] = __float2bfloat16(cosf(ang));
+  out[(long long)b * dim + half + j] = __float2bfloat16(sinf(ang));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// GroupNorm over NHWC bf16, input = channel concat of up to two tensors ([B,HW,c1] ++ [B,HW,c2]).
+// Pass 1: per-(batch, slab, group) partial sums.  Pass 2: combine in fp64, normalise, optional SiLU, store bf16.
+// Thread (vx, ry): vx indexes an 8-channel vector of the concatenated row (coalesced), ry strides pixels.
+struct GnArgs {
+  const __nv_bfloat16* x1;
+  const __nv_bfloat16* x2;
+  long long ld1, ld2;  // pixel strides (elements)
+  int c1, c2;          // channels from each source (multiples of 8)
+  int hw, batch, groups;
+  int nslab, pix_per_slab;
+};
+
+__device__ __forceinline__ uint4 gn_load(const GnArgs& a, int b, int pix, int vx) {
+  const int nv1 = a.c1 >> 3;
+  const long long p = static_cast<long long>(b) * a.hw + pix;
+  if (vx < nv1) return __ldg(reinterpret_cast<const uint4*>(a.x1 + p * a.ld1) + vx);
+  return __ldg(reinterpret_cast<const uint4*>(a.x2 + p * a.ld2) + (vx - nv1));
+}
+
+__global__ void groupnorm_stats_kernel(GnArgs a, float2* __restrict__ partial /*[B, nslab, groups]*/) {
+  __shared__ float s_sum[64], s_ss[64];
+  const int vx = threadIdx.x, ry = threadIdx.y, R = blockDim.y;
+  const int b = blockIdx.y, slab = blockIdx.x;
+  const int tid = ry * blockDim.x + vx;
+  if (tid < 64) { s_sum[tid] = 0.f; s_ss[tid] = 0.f; }
+  __syncthreads();
+  float s[8], ss[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; ss[j] = 0.f; }
+  const int p0 = slab * a.pix_per_slab;
+  const int p1 = min(a.hw, p0 + a.pix_per_slab);
+  for (int pix = p0 + ry; pix < p1; pix += R) {
+    float f[8];
+    unpack8(gn_load(a, b, pix, vx), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
+  }
+  const int cpg = (a.c1 + a.c2) / a.groups;
+  int g_cur = (vx * 8) / cpg;
+  float acc_s = 0.f, acc_ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (vx * 8 + j) / cpg;
+    if (g != g_cur) {
+      atomicAdd(&s_sum[g_cur], acc_s); atomicAdd(&s_ss[g_cur], acc_ss);
+      acc_s = 0.f; acc_ss = 0.f; g_cur = g;
+    }
+    acc_s += s[j]; acc_ss += ss[j];
+  }
+  atomicAdd(&s_sum[g_cur], acc_s); atomicAdd(&s_ss[g_cur], acc_ss);
+  __syncthreads();
+  if (tid < a.groups)
+    partial[(static_cast<long long>(b) * a.nslab + slab) * a.groups + tid] = make_float2(s_sum[tid], s_ss[tid]);
+}
+
+__global__ void groupnorm_apply_kernel(GnArgs a, const float2* __restrict__ partial, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, float eps, int silu,
+                                       __nv_bfloat16* __restrict__ out /*[B,HW,c1+c2] dense*/, int stats_nslab) {
+  extern __shared__ float s_aff[];  // scale[C], shift[C]
+  __shared__ float s_mean[64], s_rstd[64];
+  const int C = a.c1 + a.c2;
+  const int vx = threadIdx.x, ry = threadIdx.y, R = blockDim.y;
+  const int b = blockIdx.y, slab = blockIdx.x;
+  const int tid = ry * blockDim.x + vx, nthr = blockDim.x * blockDim.y;
+  const int cpg = C / a.groups;
+  if (tid < a.groups) {
+    double su = 0.0, sq = 0.0;
+    for (int k = 0; k < stats_nslab; ++k) {
+      const float2 v = __ldg(partial + (static_cast<long long>(b) * stats_nslab + k) * a.groups + tid);
+      su += v.x; sq += v.y;
+    }
+    const double n = static_cast<double>(a.hw) * cpg;
+    const double mean = su / n;
+    double var = sq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[tid] = static_cast<float>(mean);
+    s_rstd[tid] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += nthr) {
+    const int g = c / cpg;
+    const float sc = s_rstd[g] * __ldg(gamma + c);
+    s_aff[c] = sc;
+    s_aff[C + c] = __ldg(beta + c) - s_mean[g] * sc;
+  }
+  __syncthreads();
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = s_aff[vx * 8 + j]; sh[j] = s_aff[C + vx * 8 + j]; }
+  const int p0 = slab * a.pix_per_slab;
+  const int p1 = min(a.hw, p0 + a.pix_per_slab);
+  for (int pix = p0 + ry; pix < p1; pix += R) {
+    float f[8];
+    unpack8(gn_load(a, b, pix, vx), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float y = f[j] * sc[j] + sh[j];
+      if (silu) y = y / (1.f + __expf(-y));
+      f[j] = y;
+    }
+    reinterpret_cast<uint4*>(out + (static_cast<long long>(b) * a.hw + pix) * C)[vx] = pack8(f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// LayerNorm over the last dim of a bf16 [rows, C] matrix, one warp per row, row held in registers.
+template <int VPL>  // 8-element vectors per lane (C <= 256 * VPL)
+__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ out,
+                                 long long ldo, int rows, int C) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int nvec = C >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<long long>(warp) * ldx);
+  float f[VPL][8];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int v = lane + 32 * k;
+    if (v < nvec) {
+      unpack8(__ldg(xr + v), f[k]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += f[k][j];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / static_cast<float>(C);
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int v = lane + 32 * k;
+    if (v < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = f[k][j] - mean; q += d * d; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / static_cast<float>(C) + eps);
+  uint4* orow = reinterpret_cast<uint4*>(out + static_cast<long long>(warp) * ldo);
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int v = lane + 32 * k;
+    if (v < nvec) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v);
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * v);
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * v + 1);
+      float y[8];
+      y[0] = (f[k][0] - mean) * rstd * g0.x + b0.x; y[1] = (f[k][1] - mean) * rstd * g0.y + b0.y;
+      y[2] = (f[k][2] - mean) * rstd * g0.z + b0.z; y[3] = (f[k][3] - mean) * rstd * g0.w + b0.w;
+      y[4] = (f[k][4] - mean) * rstd * g1.x + b1.x; y[5] = (f[k][5] - mean) * rstd * g1.y + b1.y;
+      y[6] = (f[k][6] - mean) * rstd * g1.z + b1.z; y[7] = (f[k][7] - mean) * rstd * g1.w + b1.w;
+      orow[v] = pack8(y);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Nearest 2x upsample, NHWC bf16: out[b, 2h+i, 2w+j, :] = in[b, h, w, :].
+__global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int nvec) {
+  const long long total = static_cast<long long>(B) * H * W * nvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = static_cast<int>(i % nvec);
+    long long p = i / nvec;
+    const int w = static_cast<int>(p % W); p /= W;
+    const int h = static_cast<int>(p % H);
+    const int b = static_cast<int>(p / H);
+    const uint4 x = __ldg(in + i);
+    const long long o = ((static_cast<long long>(b) * 2 * H + 2 * h) * 2 * W + 2 * w) * nvec + v;
+    out[o] = x;
+    out[o + nvec] = x;
+    out[o + 2LL * W * nvec] = x;
+    out[o + 2LL * W * nvec + nvec] = x;
+  }
+}
+
+// 3x3 / stride 2 / pad 1 im2col, NHWC bf16 [B,H,W,C] -> [B*Ho*Wo, 9*C] with k = tap*C + c (tap = r*3 + s).
+__global__ void im2col3x3s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int nvec) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = static_cast<long long>(B) * Ho * Wo * 9 * nvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = static_cast<int>(i % nvec);
+    long long p = i / nvec;
+    const int tap = static_cast<int>(p % 9); p /= 9;
+    const int wo = static_cast<int>(p % Wo); p /= Wo;
+    const int ho = static_cast<int>(p % Ho);
+    const int b = static_cast<int>(p / Ho);
+    const int h = 2 * ho + tap / 3 - 1, w = 2 * wo + tap % 3 - 1;
+    uint4 x = make_uint4(0, 0, 0, 0);
+    if (h >= 0 && h < H && w >= 0 && w < W) x = __ldg(in + ((static_cast<long long>(b) * H + h) * W + w) * nvec + v);
+    out[i] = x;
+  }
+}
+
+// conv_in im2col: NCHW fp32 [B,Cin,H,W] -> bf16 [B*H*W, kpad], k = tap*Cin + c (3x3, stride 1, pad 1), zero padded.
+__global__ void im2col_first_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int Cin, int H,
+                                    int W, int kpad) {
+  const long long total = static_cast<long long>(B) * H * W * kpad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = static_cast<int>(i % kpad);
+    long long p = i / kpad;
+    const int w = static_cast<int>(p % W); p /= W;
+    const int h = static_cast<int>(p % H);
+    const int b = static_cast<int>(p / H);
+    float val = 0.f;
+    if (k < 9 * Cin) {
+      const int tap = k / Cin, c = k % Cin;
+      const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W) val = __ldg(in + ((static_cast<long long>(b) * Cin + c) * H + hh) * W + ww);
+    }
+    out[i] = __float2bfloat16(val);
+  }
+}
+
+// PixelUnshuffle(r) + NCHW fp32 -> NHWC bf16: out[b, h, w, c*r*r + i*r + j] = in[b, c, h*r+i, w*r+j].
+__global__ void pixel_unshuffle_nhwc_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int C,
+                                            int Hin, int Win, int r) {
+  const int Ho = Hin / r, Wo = Win / r, Co = C * r * r;
+  const long long total = static_cast<long long>(B) * Ho * Wo * Co;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    // iterate in INPUT-friendly order: (b, c, h, i, w, j) so reads are contiguous along w*r+j
+    long long p = i;
+    const int j = static_cast<int>(p % r); p /= r;
+    const int w = static_cast<int>(p % Wo); p /= Wo;
+    const int ii = static_cast<int>(p % r); p /= r;
+    const int h = static_cast<int>(p % Ho); p /= Ho;
+    const int c = static_cast<int>(p % C);
+    const int b = static_cast<int>(p / C);
+    const float v = __ldg(in + ((static_cast<long long>(b) * C + c) * Hin + h * r + ii) * Win + w * r + j);
+    out[((static_cast<long long>(b) * Ho + h) * Wo + w) * Co + c * r * r + ii * r + j] = __float2bfloat16(v);
+  }
+}
+
+// Tiled transpose between NCHW (fp32 or bf16) and NHWC (fp32 or bf16).  src viewed as [B, R, Cc] -> dst [B, Cc, R].
+template <typename TI, typename TO>
+__global__ void transpose_kernel(const TI* __restrict__ src, TO* __restrict__ dst, int R, int Cc) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const TI* s = src + static_cast<long long>(b) * R * Cc;
+  TO* d = dst + static_cast<long long>(b) * R * Cc;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < R && c < Cc) tile[i][threadIdx.x] = static_cast<float>(s[static_cast<long long>(r) * Cc + c]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < Cc) d[static_cast<long long>(c) * R + r] = static_cast<TO>(tile[threadIdx.x][i]);
+  }
+}
+
+// out = a + b (bf16, 8-wide); used for ControlNet-style additional residuals on stored skips.
+__global__ void add_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out, long long nvec) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float x[8], y[8];
+    unpack8(__ldg(a + i), x);
+    unpack8(__ldg(b + i), y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] += y[j];
+    out[i] = pack8(x);
+  }
+}
+
+// 2x2 average pool, NHWC bf16 (Adapter_XL use_conv=False path, reference modules.py:70-72).
+__global__ void avgpool2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int nvec) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = static_cast<long long>(B) * Ho * Wo * nvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = static_cast<int>(i % nvec);
+    long long p = i / nvec;
+    const int wo = static_cast<int>(p % Wo); p /= Wo;
+    const int ho = static_cast<int>(p % Ho);
+    const int b = static_cast<int>(p / Ho);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float f[8];
+      unpack8(__ldg(in + ((static_cast<long long>(b) * H + 2 * ho + (t >> 1)) * W + 2 * wo + (t & 1)) * nvec + v), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= 0.25f;
+    out[i] = pack8(acc);
+  }
+}
+
+// fp32 <-> bf16 casts.
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16(__ldg(in + i));
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __bfloat162float(in[i]);
+}
+
+// dst[0:n] = table[(*idx) * stride : ... + n]  -- selects the per-step row (time-embedding projections, step
+// coefficients) inside a replayed CUDA graph without host involvement; idx lives in device memory.
+__global__ void select_row_kernel(const float* __restrict__ table, const int* __restrict__ idx, long long stride,
+                                  float* __restrict__ dst, int n) {
+  const float* src = table + static_cast<long long>(__ldg(idx)) * stride;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = __ldg(src + i);
+}
+__global__ void advance_index_kernel(int* idx) { if (threadIdx.x == 0 && blockIdx.x == 0) *idx += 1; }
+
+}  // namespace mrisr

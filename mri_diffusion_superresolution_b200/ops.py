@@ -1,0 +1,307 @@
+"""Tensor-level wrappers over the C ABI (include/mrisr_b200.h).
+
+PyTorch is used here for device memory (``torch.empty``) and the current CUDA stream only; every wrapper hands raw
+device pointers to ``libmrisr_b200.so``.  All tensors must live on a CUDA device: there is no CPU implementation.
+Layout convention: activations are bf16 channels-last -- a conv activation is ``[B, H, W, C]`` and the same memory
+viewed as ``[B*H*W, C]`` is the token matrix of the transformer blocks.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GEGLU, ACT_NONE, ACT_RELU, ACT_SILU, GemmArgs  # noqa: F401
+
+Tensor = torch.Tensor
+_DT = {torch.float32: 0, torch.bfloat16: 1}
+
+
+def _stream(t: Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _cuda(t: Tensor, name: str, dtype=None) -> Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (this package has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    return t
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _rows(t: Tensor, name: str) -> int:
+    """Row stride (elements) of a 2-D row-major view whose last dim is contiguous."""
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"{name}: expected a 2-D tensor with contiguous last dim, got shape {tuple(t.shape)} strides {t.stride()}")
+    return t.stride(0)
+
+
+def gemm_block_n(n: int, act: int = ACT_NONE) -> int:
+    return _lib.load().mrisr_gemm_block_n(n, act)
+
+
+def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[Tensor] = None,
+         rowvec: Optional[Tensor] = None, rowvec_stride: int = 0, rows_per_batch: int = 0, act: int = ACT_NONE,
+         res1: Optional[Tensor] = None, res2: Optional[Tensor] = None, n_store: Optional[int] = None,
+         out_fp32: bool = False, conv: bool = False, out: Optional[Tensor] = None) -> Tensor:
+    """``act(concat_K(a1, a2) @ w.T + bias + rowvec[batch]) + res1 + res2`` on the tcgen05 kernel.
+
+    GEMM mode: a1 ``[M, k1]`` (+ a2 ``[M, k2]``).  ``conv=True``: a1/a2 are NHWC ``[B, H, W, k]`` and ``w`` is
+    ``[N, 9*(k1+k2)]`` (3x3, stride 1, pad 1).  Returns ``[M, n_store]`` (bf16, or fp32 if ``out_fp32``)."""
+    lib = _lib.load()
+    _cuda(a1, "gemm.a1", torch.bfloat16)
+    _cuda(w, "gemm.w", torch.bfloat16)
+    g = GemmArgs()
+    if conv:
+        if a1.dim() != 4 or a1.stride(3) != 1:
+            raise ValueError("gemm(conv): a1 must be NHWC [B,H,W,k] with contiguous channels")
+        B, H, W, k1 = a1.shape
+        lda1 = a1.stride(2)
+        if a1.stride(1) != W * lda1 or a1.stride(0) != H * W * lda1:
+            raise ValueError("gemm(conv): a1 must be dense in B,H,W (channel-slice views allowed)")
+        M, taps = B * H * W, 9
+        k2, lda2 = 0, 0
+        if a2 is not None:
+            _cuda(a2, "gemm.a2", torch.bfloat16)
+            if a2.dim() != 4 or tuple(a2.shape[:3]) != (B, H, W) or a2.stride(3) != 1:
+                raise ValueError("gemm(conv): a2 must be NHWC with the same B,H,W as a1")
+            k2, lda2 = a2.shape[3], a2.stride(2)
+        g.H, g.W = H, W
+    else:
+        lda1 = _rows(a1, "gemm.a1")
+        M, k1 = a1.shape
+        taps, k2, lda2 = 1, 0, 0
+        if a2 is not None:
+            _cuda(a2, "gemm.a2", torch.bfloat16)
+            lda2 = _rows(a2, "gemm.a2")
+            if a2.shape[0] != M:
+                raise ValueError("gemm: a1 and a2 must have the same number of rows")
+            k2 = a2.shape[1]
+    if w.dim() != 2 or not w.is_contiguous() or w.shape[1] != taps * (k1 + k2):
+        raise ValueError(f"gemm: weight must be contiguous [N, {taps * (k1 + k2)}], got {tuple(w.shape)}")
+    N = w.shape[0]
+    prod = N // 2 if act == ACT_GEGLU else N
+    n_store = prod if n_store is None else n_store
+    if out is None:
+        out = torch.empty((M, n_store), device=a1.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    else:
+        _cuda(out, "gemm.out", torch.float32 if out_fp32 else torch.bfloat16)
+        if out.shape[0] != M or out.shape[1] < n_store:
+            raise ValueError("gemm: out has the wrong shape")
+    g.M, g.N, g.n_store = M, N, n_store
+    g.k1, g.k2, g.taps = k1, k2, taps
+    g.a1, g.lda1 = a1.data_ptr(), lda1
+    g.a2, g.lda2 = _ptr(a2), lda2
+    g.w = w.data_ptr()
+    if bias is not None:
+        _cuda(bias, "gemm.bias", torch.float32)
+        if bias.numel() != N:
+            raise ValueError("gemm: bias must have N elements")
+    g.bias = _ptr(bias)
+    if rowvec is not None:
+        _cuda(rowvec, "gemm.rowvec", torch.float32)
+    g.rowvec, g.rowvec_stride, g.rows_per_batch = _ptr(rowvec), rowvec_stride, rows_per_batch
+    g.act = act
+    for name, r in (("res1", res1), ("res2", res2)):
+        if r is not None:
+            _cuda(r, f"gemm.{name}", torch.bfloat16)
+            if r.shape[0] != M or r.shape[1] < n_store:
+                raise ValueError(f"gemm: {name} has the wrong shape")
+    g.res1, g.ldr1 = _ptr(res1), (_rows(res1, "gemm.res1") if res1 is not None else 0)
+    g.res2, g.ldr2 = _ptr(res2), (_rows(res2, "gemm.res2") if res2 is not None else 0)
+    g.out, g.ldo, g.out_fp32 = out.data_ptr(), _rows(out, "gemm.out"), int(out_fp32)
+    _lib.check(lib.mrisr_gemm(C.byref(g), _stream(a1)), "mrisr_gemm")
+    return out
+
+
+def attention(q: Tensor, k: Tensor, v: Tensor, batch: int, heads: int, kv_broadcast: bool = False) -> Tensor:
+    """softmax(QK^T/sqrt(d))V.  q ``[batch*nq, heads*d]``, k/v ``[batch*nk, heads*d]`` (or ``[nk, .]`` when
+    broadcast); all may be column-slice views of wider projection outputs."""
+    lib = _lib.load()
+    for n, t in (("q", q), ("k", k), ("v", v)):
+        _cuda(t, f"attention.{n}", torch.bfloat16)
+    c = q.shape[1]
+    d = c // heads
+    nq = q.shape[0] // batch
+    nk = k.shape[0] if kv_broadcast else k.shape[0] // batch
+    o = torch.empty((q.shape[0], c), device=q.device, dtype=torch.bfloat16)
+    _lib.check(lib.mrisr_attention(q.data_ptr(), _rows(q, "q"), k.data_ptr(), _rows(k, "k"), v.data_ptr(), _rows(v, "v"),
+                                   o.data_ptr(), c, batch, nq, nk, heads, d, int(kv_broadcast), _stream(q)),
+               "mrisr_attention")
+    return o
+
+
+def groupnorm(x1: Tensor, gamma: Tensor, beta: Tensor, groups: int, eps: float, silu: bool,
+              x2: Optional[Tensor] = None) -> Tensor:
+    """GroupNorm(+SiLU) of the channel concat [x1 | x2]; x*: NHWC ``[B, H, W, c]`` (channel-slice views allowed)."""
+    lib = _lib.load()
+    _cuda(x1, "groupnorm.x1", torch.bfloat16)
+    B, H, W, c1 = x1.shape
+    c2, ld2 = 0, 0
+    if x2 is not None:
+        _cuda(x2, "groupnorm.x2", torch.bfloat16)
+        c2, ld2 = x2.shape[3], x2.stride(2)
+    out = torch.empty((B, H, W, c1 + c2), device=x1.device, dtype=torch.bfloat16)
+    ws = torch.empty((lib.mrisr_groupnorm_workspace_floats(B, groups),), device=x1.device, dtype=torch.float32)
+    _lib.check(lib.mrisr_groupnorm(x1.data_ptr(), x1.stride(2), c1, _ptr(x2), ld2, c2, B, H * W, groups,
+                                   _cuda(gamma, "gamma", torch.float32).data_ptr(),
+                                   _cuda(beta, "beta", torch.float32).data_ptr(), float(eps), int(silu),
+                                   out.data_ptr(), ws.data_ptr(), _stream(x1)), "mrisr_groupnorm")
+    return out
+
+
+def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5) -> Tensor:
+    lib = _lib.load()
+    _cuda(x, "layernorm.x", torch.bfloat16)
+    rows, c = x.shape
+    out = torch.empty((rows, c), device=x.device, dtype=torch.bfloat16)
+    _lib.check(lib.mrisr_layernorm(x.data_ptr(), _rows(x, "x"), gamma.data_ptr(), beta.data_ptr(), float(eps),
+                                   out.data_ptr(), c, rows, c, _stream(x)), "mrisr_layernorm")
+    return out
+
+
+def timestep_embedding(t: Tensor, dim: int) -> Tensor:
+    lib = _lib.load()
+    _cuda(t, "timestep_embedding.t", torch.float32)
+    out = torch.empty((t.numel(), dim), device=t.device, dtype=torch.bfloat16)
+    _lib.check(lib.mrisr_timestep_embedding(t.data_ptr(), out.data_ptr(), t.numel(), dim, _stream(t)),
+               "mrisr_timestep_embedding")
+    return out
+
+
+def sched_step(x: Tensor, eps: Tensor, coef: Tensor, lr: Optional[Tensor] = None, z: Optional[Tensor] = None,
+               out: Optional[Tensor] = None) -> Tensor:
+    """x' = c1*x + c2*eps + c3*lr + c4*z with coef = device fp32[4] (reference res_srdiff.py:85-96 in closed form)."""
+    lib = _lib.load()
+    for n, t in (("x", x), ("eps", eps), ("coef", coef)):
+        _cuda(t, f"sched_step.{n}", torch.float32)
+    out = torch.empty_like(x) if out is None else out
+    _lib.check(lib.mrisr_sched_step(x.data_ptr(), eps.data_ptr(), _ptr(lr), _ptr(z), out.data_ptr(), x.numel(),
+                                    coef.data_ptr(), _stream(x)), "mrisr_sched_step")
+    return out
+
+
+def res_shift(hr: Tensor, lr: Tensor, noise: Tensor, coef: Tensor) -> Tensor:
+    """coef: device fp32 [B, 2] = {sqrt(abar_t), sqrt(1 - abar_t)}."""
+    lib = _lib.load()
+    for n, t in (("hr", hr), ("lr", lr), ("noise", noise), ("coef", coef)):
+        _cuda(t, f"res_shift.{n}", torch.float32)
+    out = torch.empty_like(hr)
+    b = hr.shape[0]
+    _lib.check(lib.mrisr_res_shift(hr.data_ptr(), lr.data_ptr(), noise.data_ptr(), out.data_ptr(), hr.numel() // b, b,
+                                   coef.data_ptr(), _stream(hr)), "mrisr_res_shift")
+    return out
+
+
+def select_row(table: Tensor, idx: Tensor, dst: Tensor) -> Tensor:
+    lib = _lib.load()
+    _cuda(table, "select_row.table", torch.float32)
+    _cuda(idx, "select_row.idx", torch.int32)
+    _lib.check(lib.mrisr_select_row(table.data_ptr(), idx.data_ptr(), table.stride(0), dst.data_ptr(), dst.numel(),
+                                    _stream(table)), "mrisr_select_row")
+    return dst
+
+
+def advance_index(idx: Tensor) -> None:
+    _lib.check(_lib.load().mrisr_advance_index(_cuda(idx, "idx", torch.int32).data_ptr(), _stream(idx)),
+               "mrisr_advance_index")
+
+
+def upsample2x(x: Tensor) -> Tensor:
+    lib = _lib.load()
+    _cuda(x, "upsample2x.x", torch.bfloat16)
+    B, H, W, c = x.shape
+    out = torch.empty((B, 2 * H, 2 * W, c), device=x.device, dtype=torch.bfloat16)
+    _lib.check(lib.mrisr_upsample2x(x.data_ptr(), out.data_ptr(), B, H, W, c, _stream(x)), "mrisr_upsample2x")
+    return out
+
+
+def im2col3x3s2(x: Tensor) -> Tensor:
+    lib = _lib.load()
+    _cuda(x, "im2col3x3s2.x", torch.bfloat16)
+    B, H, W, c = x.shape
+    out = torch.empty((B * (H // 2) * (W // 2), 9 * c), device=x.device, dtype=torch.bfloat16)
+    _lib.check(lib.mrisr_im2col3x3s2(x.data_ptr(), out.data_ptr(), B, H, W, c, _stream(x)), "mrisr_im2col3x3s2")
+    return out
+
+
+def im2col_first(x_nchw: Tensor, kpad: int) -> Tensor:
+    lib = _lib.load()
+    _cuda(x_nchw, "im2col_first.x", torch.float32)
+    B, cin, H, W = x_nchw.shape
+    out = torch.empty((B * H * W, kpad), device=x_nchw.device, dtype=torch.bfloat16)
+    _lib.check(lib.mrisr_im2col_first(x_nchw.data_ptr(), out.data_ptr(), B, cin, H, W, kpad, _stream(x_nchw)),
+               "mrisr_im2col_first")
+    return out
+
+
+def pixel_unshuffle_nhwc(x_nchw: Tensor, r: int) -> Tensor:
+    lib = _lib.load()
+    _cuda(x_nchw, "pixel_unshuffle.x", torch.float32)
+    B, c, H, W = x_nchw.shape
+    out = torch.empty((B, H // r, W // r, c * r * r), device=x_nchw.device, dtype=torch.bfloat16)
+    _lib.check(lib.mrisr_pixel_unshuffle_nhwc(x_nchw.data_ptr(), out.data_ptr(), B, c, H, W, r, _stream(x_nchw)),
+               "mrisr_pixel_unshuffle_nhwc")
+    return out
+
+
+def avgpool2(x: Tensor) -> Tensor:
+    lib = _lib.load()
+    _cuda(x, "avgpool2.x", torch.bfloat16)
+    B, H, W, c = x.shape
+    out = torch.empty((B, H // 2, W // 2, c), device=x.device, dtype=torch.bfloat16)
+    _lib.check(lib.mrisr_avgpool2(x.data_ptr(), out.data_ptr(), B, H, W, c, _stream(x)), "mrisr_avgpool2")
+    return out
+
+
+def add(a: Tensor, b: Tensor) -> Tensor:
+    lib = _lib.load()
+    _cuda(a, "add.a", torch.bfloat16)
+    _cuda(b, "add.b", torch.bfloat16)
+    out = torch.empty_like(a)
+    _lib.check(lib.mrisr_add(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), _stream(a)), "mrisr_add")
+    return out
+
+
+def nchw_to_nhwc(x: Tensor, dtype=torch.bfloat16) -> Tensor:
+    """[B, C, H, W] (fp32|bf16) -> [B, H, W, C] (fp32|bf16)."""
+    lib = _lib.load()
+    _cuda(x, "nchw_to_nhwc.x")
+    B, c, H, W = x.shape
+    out = torch.empty((B, H, W, c), device=x.device, dtype=dtype)
+    _lib.check(lib.mrisr_transpose(x.data_ptr(), _DT[x.dtype], out.data_ptr(), _DT[dtype], B, c, H * W, _stream(x)),
+               "mrisr_transpose")
+    return out
+
+
+def nhwc_to_nchw(x: Tensor, dtype=torch.float32) -> Tensor:
+    """[B, H, W, C] -> [B, C, H, W]."""
+    lib = _lib.load()
+    _cuda(x, "nhwc_to_nchw.x")
+    B, H, W, c = x.shape
+    out = torch.empty((B, c, H, W), device=x.device, dtype=dtype)
+    _lib.check(lib.mrisr_transpose(x.data_ptr(), _DT[x.dtype], out.data_ptr(), _DT[dtype], B, H * W, c, _stream(x)),
+               "mrisr_transpose")
+    return out
+
+
+def cast(x: Tensor, dtype) -> Tensor:
+    lib = _lib.load()
+    _cuda(x, "cast.x")
+    if x.dtype == dtype:
+        return x
+    out = torch.empty(x.shape, device=x.device, dtype=dtype)
+    _lib.check(lib.mrisr_cast(x.data_ptr(), _DT[x.dtype], out.data_ptr(), _DT[dtype], x.numel(), _stream(x)), "mrisr_cast")
+    return out
+
+
+def device_info() -> Tuple[int, int]:
+    sms, cc = C.c_int(0), C.c_int(0)
+    _lib.check(_lib.load().mrisr_device_info(C.byref(sms), C.byref(cc)), "mrisr_device_info")
+    return sms.value, cc.value
