@@ -49,9 +49,18 @@ int mrisr_sched_step(const float* x, const float* eps, const float* lr, const fl
                      const float* coef, void* stream);
 
 /* Replaces get_res_shifting_latents, src/adapters/res_srdiff.py:7-25:
- *     out[b] = sa[b]*hr[b] + (1-sa[b])*lr[b] + s1[b]*noise[b],  coef = DEVICE fp32 [batch][2] = {sqrt(abar_t), sqrt(1-abar_t)} */
+ *     a = abar[timesteps[b]];  out[b] = sqrt(a)*hr[b] + (1-sqrt(a))*lr[b] + sqrt(1-a)*noise[b]
+ * sqrt_table: DEVICE fp32 [T][2] = {sqrt(abar_t), sqrt(1-abar_t)} (host-precomputed from the scheduler's fp32
+ * alphas_cumprod, :13); timesteps: DEVICE int64 [t_count], t_count == 1 broadcasts a scalar timestep (:14), else
+ * t_count == batch.  Indices outside [0, T) make the kernel trap.  hr/lr/noise/out fp32. */
 int mrisr_res_shift(const float* hr, const float* lr, const float* noise, float* out, int64_t n_per_sample, int batch,
-                    const float* coef, void* stream);
+                    const float* sqrt_table, int table_len, const int64_t* timesteps, int t_count, void* stream);
+
+/* Graph-replayable form of mrisr_sched_step: step i = *idx (DEVICE int32) selects coef_table[i][0..3] and the
+ * noise slab z_table + i*z_stride (z_table may be NULL), so ONE captured step serves all N iterations of the loop
+ * (res_srdiff.py:63) with no host sync (the reference syncs on `prev_t > 0`, :92; here c4 == 0 encodes it). */
+int mrisr_sched_step_indexed(const float* x, const float* eps, const float* lr, const float* z_table, int64_t z_stride,
+                             float* out, int64_t n, const float* coef_table, const int* idx, void* stream);
 
 /* Selects row *idx of a device table (per-step time-embedding projections / step coefficients) and advances the
  * device-side step counter -- lets one captured CUDA graph replay all N steps of the loop (res_srdiff.py:63). */
@@ -130,6 +139,14 @@ int mrisr_add(const void* a, const void* b, void* out, int64_t n, void* stream);
 /* [B, R, Cc] -> [B, Cc, R].  dtype codes: 0 = fp32, 1 = bf16.  NCHW->NHWC: R = C, Cc = H*W.  NHWC->NCHW: R = H*W, Cc = C. */
 int mrisr_transpose(const void* src, int src_dtype, void* dst, int dst_dtype, int B, int R, int Cc, void* stream);
 int mrisr_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+
+/* prepare_condition_image, src/adapters/res_srdiff.py:27-33: bilinear resize (align_corners=False, no antialias),
+ * fp32 NCHW [planes, Hin, Win] -> [planes, Hout, Wout]. */
+int mrisr_bilinear_resize(const float* in, float* out, int planes, int Hin, int Win, int Hout, int Wout, void* stream);
+
+/* decode_to_vis, src/adapters/res_srdiff.py:115-122: fp32 CHW image (first batch element) -> uint8 [H, W, 3]:
+ * floor(clamp(x/2 + 0.5, 0, 1) * 255), grayscale (C == 1) replicated to 3 channels.  C in {1, 3}. */
+int mrisr_to_uint8_vis(const float* chw, uint8_t* out_hw3, int C, int H, int W, void* stream);
 
 #ifdef __cplusplus
 }

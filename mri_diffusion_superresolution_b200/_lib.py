@@ -40,7 +40,8 @@ PROTOTYPES = {
     "mrisr_last_error": (C.c_char_p, []),
     "mrisr_device_info": (_I, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "mrisr_sched_step": (_I, [_P, _P, _P, _P, _P, _L, _P, _P]),
-    "mrisr_res_shift": (_I, [_P, _P, _P, _P, _L, _I, _P, _P]),
+    "mrisr_res_shift": (_I, [_P, _P, _P, _P, _L, _I, _P, _I, _P, _I, _P]),
+    "mrisr_sched_step_indexed": (_I, [_P, _P, _P, _P, _L, _P, _L, _P, _P, _P]),
     "mrisr_select_row": (_I, [_P, _P, _L, _P, _I, _P]),
     "mrisr_advance_index": (_I, [_P, _P]),
     "mrisr_timestep_embedding": (_I, [_P, _P, _I, _I, _P]),
@@ -58,6 +59,8 @@ PROTOTYPES = {
     "mrisr_add": (_I, [_P, _P, _P, _L, _P]),
     "mrisr_transpose": (_I, [_P, _I, _P, _I, _I, _I, _I, _P]),
     "mrisr_cast": (_I, [_P, _I, _P, _I, _L, _P]),
+    "mrisr_bilinear_resize": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "mrisr_to_uint8_vis": (_I, [_P, _P, _I, _I, _I, _P]),
 }
 
 _lib = None
@@ -82,10 +85,15 @@ def load() -> C.CDLL:
     return _lib
 
 
-def check(code: int, what: str) -> None:
+# number of CUDA kernels launched through the C ABI by this process (bench.py reports it as gpu_launches)
+LAUNCHES = [0]
+
+
+def check(code: int, what: str, kernels: int = 1) -> None:
     """Map a negative ABI return code to the Python exceptions the reference's callers would see
     (ValueError for bad arguments, cf. src/adapters/modules.py:16,29; RuntimeError otherwise)."""
     if code == 0:
+        LAUNCHES[0] += kernels
         return
     msg = load().mrisr_last_error().decode("utf-8", "replace")
     if code in (E_INVALID, E_UNSUPPORTED):

@@ -163,15 +163,32 @@ int mrisr_sched_step(const float* x, const float* eps, const float* lr, const fl
 }
 
 int mrisr_res_shift(const float* hr, const float* lr, const float* noise, float* out, int64_t n_per_sample, int batch,
-                    const float* coef, void* stream) {
-  MRISR_REQUIRE(hr && lr && noise && out && coef, "res_shift: null pointer");
-  MRISR_REQUIRE(batch >= 0 && n_per_sample >= 0 && n_per_sample % 4 == 0, "res_shift: bad sizes");
+                    const float* sqrt_table, int table_len, const int64_t* timesteps, int t_count, void* stream) {
+  MRISR_REQUIRE(hr && lr && noise && out && sqrt_table && timesteps, "res_shift: null pointer");
+  MRISR_REQUIRE(batch >= 0 && n_per_sample >= 0 && n_per_sample % 4 == 0 && table_len > 0, "res_shift: bad sizes");
+  MRISR_REQUIRE(t_count == 1 || t_count == batch, "res_shift: timesteps must hold 1 or batch (%d) entries, got %d", batch, t_count);
   MRISR_REQUIRE(aligned16(hr) && aligned16(lr) && aligned16(noise) && aligned16(out), "res_shift: misaligned pointer");
   if (batch == 0 || n_per_sample == 0) return 0;
   const long long n4 = n_per_sample / 4;
   mrisr::res_shift_kernel<<<grid_for(n4 * batch, 256, 8), 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(hr), reinterpret_cast<const float4*>(lr), reinterpret_cast<const float4*>(noise),
-      reinterpret_cast<float4*>(out), n4, batch, coef);
+      reinterpret_cast<float4*>(out), n4, batch, sqrt_table, table_len, reinterpret_cast<const long long*>(timesteps),
+      t_count);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mrisr_sched_step_indexed(const float* x, const float* eps, const float* lr, const float* z_table, int64_t z_stride,
+                             float* out, int64_t n, const float* coef_table, const int* idx, void* stream) {
+  MRISR_REQUIRE(x && eps && out && coef_table && idx, "sched_step_indexed: null pointer");
+  MRISR_REQUIRE(n >= 0 && n % 4 == 0 && z_stride % 4 == 0, "sched_step_indexed: n and z_stride must be multiples of 4");
+  MRISR_REQUIRE(aligned16(x) && aligned16(eps) && aligned16(out) && (!lr || aligned16(lr)) && (!z_table || aligned16(z_table)),
+                "sched_step_indexed: pointers must be 16-byte aligned");
+  if (n == 0) return 0;
+  const long long n4 = n / 4;
+  mrisr::sched_step_indexed_kernel<<<grid_for(n4, 256, 8), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(eps), reinterpret_cast<const float4*>(lr),
+      reinterpret_cast<const float4*>(z_table), z_stride / 4, reinterpret_cast<float4*>(out), n4, coef_table, idx);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -216,7 +233,7 @@ int mrisr_groupnorm(const void* x1, int64_t ld1, int c1, const void* x2, int64_t
   MRISR_REQUIRE(groups > 0 && groups <= 64 && C % groups == 0, "groupnorm: groups must divide C and be <= 64");
   MRISR_REQUIRE(aligned16(x1) && aligned16(out) && (!x2 || aligned16(x2)), "groupnorm: misaligned pointer");
   const int nvec = C / 8;
-  if (nvec > 1024) return fail(MRISR_E_UNSUPPORTED, "groupnorm: C = %d > 8192 unsupported", C);
+  if (nvec > 512) return fail(MRISR_E_UNSUPPORTED, "groupnorm: C = %d > 4096 unsupported", C);
   int R = 256 / nvec;
   if (R < 1) R = 1;
   if (R > hw) R = hw;
@@ -234,7 +251,7 @@ int mrisr_groupnorm(const void* x1, int64_t ld1, int c1, const void* x2, int64_t
   a.nslab = nslab; a.pix_per_slab = pps;
   dim3 block(nvec, R), grid(nslab, batch);
   cudaStream_t st = as_stream(stream);
-  mrisr::groupnorm_stats_kernel<<<grid, block, 0, st>>>(a, reinterpret_cast<float2*>(workspace));
+  mrisr::groupnorm_stats_kernel<<<grid, block, 2 * R * C * sizeof(float), st>>>(a, reinterpret_cast<float2*>(workspace));
   MRISR_CHECK_CUDA(cudaGetLastError());
   mrisr::groupnorm_apply_kernel<<<grid, block, 2 * C * sizeof(float), st>>>(
       a, reinterpret_cast<const float2*>(workspace), gamma, beta, eps, silu, static_cast<__nv_bfloat16*>(out), nslab);
@@ -470,6 +487,21 @@ int mrisr_cast(const void* src, int sdt, void* dst, int ddt, int64_t n, void* st
     mrisr::cast_bf16_f32_kernel<<<grid_for(n, 256, 8), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<float*>(dst), n);
   else
     return fail(MRISR_E_INVALID, "cast: only fp32<->bf16 supported");
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mrisr_bilinear_resize(const float* in, float* out, int planes, int Hin, int Win, int Hout, int Wout, void* stream) {
+  MRISR_REQUIRE(in && out && planes > 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0, "bilinear_resize: bad argument");
+  const long long n = static_cast<long long>(planes) * Hout * Wout;
+  mrisr::bilinear_resize_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(in, out, planes, Hin, Win, Hout, Wout);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mrisr_to_uint8_vis(const float* chw, uint8_t* out, int C, int H, int W, void* stream) {
+  MRISR_REQUIRE(chw && out && (C == 1 || C == 3) && H > 0 && W > 0, "to_uint8_vis: C must be 1 or 3");
+  mrisr::to_uint8_vis_kernel<<<grid_for(static_cast<long long>(H) * W * 3, 256, 8), 256, 0, as_stream(stream)>>>(chw, out, C, H, W);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -42,19 +42,88 @@ __global__ void sched_step_kernel(const float4* __restrict__ x, const float4* __
   }
 }
 
+// Graph-replayable variant: the step index lives in device memory and selects the coefficient row and noise slab.
+__global__ void sched_step_indexed_kernel(const float4* __restrict__ x, const float4* __restrict__ eps,
+                                          const float4* __restrict__ lr, const float4* __restrict__ z_table,
+                                          long long z_stride4, float4* out, long long n4,
+                                          const float* __restrict__ coef_table, const int* __restrict__ idx) {
+  const int step = __ldg(idx);
+  const float* coef = coef_table + 4 * step;
+  const float c1 = __ldg(coef), c2 = __ldg(coef + 1), c3 = __ldg(coef + 2), c4 = __ldg(coef + 3);
+  const bool use_lr = lr != nullptr && c3 != 0.f;
+  const bool use_z = z_table != nullptr && c4 != 0.f;
+  const float4* z = z_table != nullptr ? z_table + static_cast<long long>(step) * z_stride4 : nullptr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = x[i], e = __ldg(eps + i);
+    float4 r = make_float4(c1 * a.x + c2 * e.x, c1 * a.y + c2 * e.y, c1 * a.z + c2 * e.z, c1 * a.w + c2 * e.w);
+    if (use_lr) {
+      const float4 l = __ldg(lr + i);
+      r.x += c3 * l.x; r.y += c3 * l.y; r.z += c3 * l.z; r.w += c3 * l.w;
+    }
+    if (use_z) {
+      const float4 q = __ldg(z + i);
+      r.x += c4 * q.x; r.y += c4 * q.y; r.z += c4 * q.z; r.w += c4 * q.w;
+    }
+    out[i] = r;
+  }
+}
+
 // Forward shifting (row F; reference src/adapters/res_srdiff.py:7-25):
-//   x_t = sa[b]*hr + (1 - sa[b])*lr + s1[b]*noise, coef[b] = {sqrt(abar_t), sqrt(1-abar_t)} per sample.
+//   x_t = sa*hr + (1 - sa)*lr + s1*noise with {sa, s1} = sqrt_table[timesteps[b]] = {sqrt(abar_t), sqrt(1-abar_t)}.
+// Written with explicitly rounded mul/add (no FMA contraction) in the reference's operation order, so that with
+// the same fp32 table the result is bit-identical to the eager PyTorch expression.
+__device__ __forceinline__ float res_shift_one(float sa, float ia, float s1, float h, float l, float q) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(sa, h), __fmul_rn(ia, l)), __fmul_rn(s1, q));
+}
 __global__ void res_shift_kernel(const float4* __restrict__ hr, const float4* __restrict__ lr,
                                  const float4* __restrict__ noise, float4* __restrict__ out, long long n4_per_sample,
-                                 int batch, const float* __restrict__ coef) {
+                                 int batch, const float* __restrict__ sqrt_table, int table_len,
+                                 const long long* __restrict__ timesteps, int t_count) {
   const long long total = n4_per_sample * batch;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int b = static_cast<int>(i / n4_per_sample);
-    const float sa = __ldg(coef + 2 * b), s1 = __ldg(coef + 2 * b + 1);
+    const long long t = timesteps[t_count == 1 ? 0 : b];
+    if (t < 0 || t >= table_len) __trap();
+    const float sa = __ldg(sqrt_table + 2 * t), s1 = __ldg(sqrt_table + 2 * t + 1);
+    const float ia = __fsub_rn(1.f, sa);
     const float4 h = __ldg(hr + i), l = __ldg(lr + i), q = __ldg(noise + i);
-    const float ia = 1.f - sa;
-    out[i] = make_float4(sa * h.x + ia * l.x + s1 * q.x, sa * h.y + ia * l.y + s1 * q.y,
-                         sa * h.z + ia * l.z + s1 * q.z, sa * h.w + ia * l.w + s1 * q.w);
+    out[i] = make_float4(res_shift_one(sa, ia, s1, h.x, l.x, q.x), res_shift_one(sa, ia, s1, h.y, l.y, q.y),
+                         res_shift_one(sa, ia, s1, h.z, l.z, q.z), res_shift_one(sa, ia, s1, h.w, l.w, q.w));
+  }
+}
+
+// Bilinear resize, align_corners=False, no antialias (F.interpolate semantics; reference res_srdiff.py:31-32).
+__global__ void bilinear_resize_kernel(const float* __restrict__ in, float* __restrict__ out, int planes, int Hin, int Win,
+                                       int Hout, int Wout) {
+  const float sh = static_cast<float>(Hin) / static_cast<float>(Hout);
+  const float sw = static_cast<float>(Win) / static_cast<float>(Wout);
+  const long long total = static_cast<long long>(planes) * Hout * Wout;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = static_cast<int>(i % Wout);
+    const int oy = static_cast<int>((i / Wout) % Hout);
+    const long long pl = i / (static_cast<long long>(Wout) * Hout);
+    float fy = fmaxf(__fsub_rn(__fmul_rn(static_cast<float>(oy) + 0.5f, sh), 0.5f), 0.f);
+    float fx = fmaxf(__fsub_rn(__fmul_rn(static_cast<float>(ox) + 0.5f, sw), 0.5f), 0.f);
+    const int y0 = min(static_cast<int>(fy), Hin - 1), x0 = min(static_cast<int>(fx), Win - 1);
+    const int y1 = min(y0 + 1, Hin - 1), x1 = min(x0 + 1, Win - 1);
+    const float ly = fy - static_cast<float>(y0), lx = fx - static_cast<float>(x0);
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const float* p = in + pl * Hin * Win;
+    const float v00 = __ldg(p + y0 * Win + x0), v01 = __ldg(p + y0 * Win + x1);
+    const float v10 = __ldg(p + y1 * Win + x0), v11 = __ldg(p + y1 * Win + x1);
+    out[i] = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+  }
+}
+
+// decode_to_vis (reference res_srdiff.py:115-122): uint8(trunc(clamp(x/2 + 0.5, 0, 1) * 255)), CHW -> HW3.
+__global__ void to_uint8_vis_kernel(const float* __restrict__ chw, uint8_t* __restrict__ out, int C, int H, int W) {
+  const int total = H * W * 3;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % 3, p = i / 3;
+    const float x = __ldg(chw + (C == 1 ? 0 : c) * H * W + p);
+    float v = __fadd_rn(__fmul_rn(x, 0.5f), 0.5f);
+    v = fminf(fmaxf(v, 0.f), 1.f);
+    out[i] = static_cast<uint8_t>(static_cast<int>(__fmul_rn(v, 255.f)));
   }
 }
 
@@ -93,12 +162,11 @@ __device__ __forceinline__ uint4 gn_load(const GnArgs& a, int b, int pix, int vx
 }
 
 __global__ void groupnorm_stats_kernel(GnArgs a, float2* __restrict__ partial /*[B, nslab, groups]*/) {
-  __shared__ float s_sum[64], s_ss[64];
+  extern __shared__ float gn_sh[];  // [2][R][C]: per-thread per-channel partial sums, reduced in a FIXED order below
   const int vx = threadIdx.x, ry = threadIdx.y, R = blockDim.y;
   const int b = blockIdx.y, slab = blockIdx.x;
   const int tid = ry * blockDim.x + vx;
-  if (tid < 64) { s_sum[tid] = 0.f; s_ss[tid] = 0.f; }
-  __syncthreads();
+  const int C = a.c1 + a.c2;
   float s[8], ss[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s[j] = 0.f; ss[j] = 0.f; }
@@ -110,22 +178,24 @@ __global__ void groupnorm_stats_kernel(GnArgs a, float2* __restrict__ partial /*
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
   }
-  const int cpg = (a.c1 + a.c2) / a.groups;
-  int g_cur = (vx * 8) / cpg;
-  float acc_s = 0.f, acc_ss = 0.f;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int g = (vx * 8 + j) / cpg;
-    if (g != g_cur) {
-      atomicAdd(&s_sum[g_cur], acc_s); atomicAdd(&s_ss[g_cur], acc_ss);
-      acc_s = 0.f; acc_ss = 0.f; g_cur = g;
-    }
-    acc_s += s[j]; acc_ss += ss[j];
-  }
-  atomicAdd(&s_sum[g_cur], acc_s); atomicAdd(&s_ss[g_cur], acc_ss);
+  float* sh_s = gn_sh + ry * C + vx * 8;
+  float* sh_q = gn_sh + R * C + ry * C + vx * 8;
+  *reinterpret_cast<float4*>(sh_s) = make_float4(s[0], s[1], s[2], s[3]);
+  *reinterpret_cast<float4*>(sh_s + 4) = make_float4(s[4], s[5], s[6], s[7]);
+  *reinterpret_cast<float4*>(sh_q) = make_float4(ss[0], ss[1], ss[2], ss[3]);
+  *reinterpret_cast<float4*>(sh_q + 4) = make_float4(ss[4], ss[5], ss[6], ss[7]);
   __syncthreads();
-  if (tid < a.groups)
-    partial[(static_cast<long long>(b) * a.nslab + slab) * a.groups + tid] = make_float2(s_sum[tid], s_ss[tid]);
+  // deterministic (atomic-free) group reduction: bitwise-reproducible statistics run to run, eager or graph
+  if (tid < a.groups) {
+    const int cpg = C / a.groups;
+    float su = 0.f, sq = 0.f;
+    for (int r = 0; r < R; ++r) {
+      const float* ps = gn_sh + r * C + tid * cpg;
+      const float* pq = gn_sh + R * C + r * C + tid * cpg;
+      for (int c = 0; c < cpg; ++c) { su += ps[c]; sq += pq[c]; }
+    }
+    partial[(static_cast<long long>(b) * a.nslab + slab) * a.groups + tid] = make_float2(su, sq);
+  }
 }
 
 __global__ void groupnorm_apply_kernel(GnArgs a, const float2* __restrict__ partial, const float* __restrict__ gamma,

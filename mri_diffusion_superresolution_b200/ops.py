@@ -16,6 +16,8 @@ from . import _lib
 from ._lib import ACT_GEGLU, ACT_NONE, ACT_RELU, ACT_SILU, GemmArgs  # noqa: F401
 
 Tensor = torch.Tensor
+# bench.py sets this to a list to time every tensor-core kernel launch with CUDA events (executed flops, taps, ev0, ev1)
+GEMM_PROFILE = None
 _DT = {torch.float32: 0, torch.bfloat16: 1}
 
 
@@ -116,6 +118,13 @@ def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[T
     g.res1, g.ldr1 = _ptr(res1), (_rows(res1, "gemm.res1") if res1 is not None else 0)
     g.res2, g.ldr2 = _ptr(res2), (_rows(res2, "gemm.res2") if res2 is not None else 0)
     g.out, g.ldo, g.out_fp32 = out.data_ptr(), _rows(out, "gemm.out"), int(out_fp32)
+    if GEMM_PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream(a1.device))
+        _lib.check(lib.mrisr_gemm(C.byref(g), _stream(a1)), "mrisr_gemm")
+        e1.record(torch.cuda.current_stream(a1.device))
+        GEMM_PROFILE.append((2.0 * M * N * taps * (k1 + k2), taps, e0, e1))
+        return out
     _lib.check(lib.mrisr_gemm(C.byref(g), _stream(a1)), "mrisr_gemm")
     return out
 
@@ -152,7 +161,7 @@ def groupnorm(x1: Tensor, gamma: Tensor, beta: Tensor, groups: int, eps: float, 
     _lib.check(lib.mrisr_groupnorm(x1.data_ptr(), x1.stride(2), c1, _ptr(x2), ld2, c2, B, H * W, groups,
                                    _cuda(gamma, "gamma", torch.float32).data_ptr(),
                                    _cuda(beta, "beta", torch.float32).data_ptr(), float(eps), int(silu),
-                                   out.data_ptr(), ws.data_ptr(), _stream(x1)), "mrisr_groupnorm")
+                                   out.data_ptr(), ws.data_ptr(), _stream(x1)), "mrisr_groupnorm", kernels=2)
     return out
 
 
@@ -187,15 +196,57 @@ def sched_step(x: Tensor, eps: Tensor, coef: Tensor, lr: Optional[Tensor] = None
     return out
 
 
-def res_shift(hr: Tensor, lr: Tensor, noise: Tensor, coef: Tensor) -> Tensor:
-    """coef: device fp32 [B, 2] = {sqrt(abar_t), sqrt(1 - abar_t)}."""
+def sched_step_indexed(x: Tensor, eps: Tensor, coef_table: Tensor, idx: Tensor, lr: Optional[Tensor] = None,
+                       z_table: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
+    """Step ``*idx`` of the loop: coefficients ``coef_table[idx]`` (fp32 [N,4]) and noise ``z_table[idx]`` are picked
+    on the device, so one captured CUDA graph replays all N steps."""
     lib = _lib.load()
-    for n, t in (("hr", hr), ("lr", lr), ("noise", noise), ("coef", coef)):
+    for n, t in (("x", x), ("eps", eps), ("coef_table", coef_table)):
+        _cuda(t, f"sched_step_indexed.{n}", torch.float32)
+    _cuda(idx, "sched_step_indexed.idx", torch.int32)
+    out = torch.empty_like(x) if out is None else out
+    zs = 0
+    if z_table is not None:
+        _cuda(z_table, "sched_step_indexed.z_table", torch.float32)
+        zs = z_table.stride(0)
+    _lib.check(lib.mrisr_sched_step_indexed(x.data_ptr(), eps.data_ptr(), _ptr(lr), _ptr(z_table), zs, out.data_ptr(),
+                                            x.numel(), coef_table.data_ptr(), idx.data_ptr(), _stream(x)),
+               "mrisr_sched_step_indexed")
+    return out
+
+
+def res_shift(hr: Tensor, lr: Tensor, noise: Tensor, sqrt_table: Tensor, timesteps: Tensor) -> Tensor:
+    """sqrt_table: device fp32 [T, 2] = {sqrt(abar), sqrt(1 - abar)}; timesteps: device int64 [1] or [B]."""
+    lib = _lib.load()
+    for n, t in (("hr", hr), ("lr", lr), ("noise", noise), ("sqrt_table", sqrt_table)):
         _cuda(t, f"res_shift.{n}", torch.float32)
+    _cuda(timesteps, "res_shift.timesteps", torch.int64)
     out = torch.empty_like(hr)
     b = hr.shape[0]
-    _lib.check(lib.mrisr_res_shift(hr.data_ptr(), lr.data_ptr(), noise.data_ptr(), out.data_ptr(), hr.numel() // b, b,
-                                   coef.data_ptr(), _stream(hr)), "mrisr_res_shift")
+    _lib.check(lib.mrisr_res_shift(hr.data_ptr(), lr.data_ptr(), noise.data_ptr(), out.data_ptr(), hr.numel() // max(b, 1), b,
+                                   sqrt_table.data_ptr(), sqrt_table.shape[0], timesteps.data_ptr(), timesteps.numel(),
+                                   _stream(hr)), "mrisr_res_shift")
+    return out
+
+
+def bilinear_resize(x: Tensor, size: Tuple[int, int]) -> Tensor:
+    """fp32 NCHW bilinear resize (align_corners=False), reference res_srdiff.py:31-32."""
+    lib = _lib.load()
+    _cuda(x, "bilinear_resize.x", torch.float32)
+    B, c, H, W = x.shape
+    out = torch.empty((B, c, size[0], size[1]), device=x.device, dtype=torch.float32)
+    _lib.check(lib.mrisr_bilinear_resize(x.contiguous().data_ptr(), out.data_ptr(), B * c, H, W, size[0], size[1], _stream(x)),
+               "mrisr_bilinear_resize")
+    return out
+
+
+def to_uint8_vis(chw: Tensor) -> Tensor:
+    """fp32 [C, H, W] (C in {1,3}) -> uint8 [H, W, 3], reference res_srdiff.py:115-122."""
+    lib = _lib.load()
+    _cuda(chw, "to_uint8_vis.chw", torch.float32)
+    c, H, W = chw.shape
+    out = torch.empty((H, W, 3), device=chw.device, dtype=torch.uint8)
+    _lib.check(lib.mrisr_to_uint8_vis(chw.contiguous().data_ptr(), out.data_ptr(), c, H, W, _stream(chw)), "mrisr_to_uint8_vis")
     return out
 
 

@@ -161,6 +161,27 @@ def gen_adapter():
         d["sk"] = np.int64(kw["sk"])
         d["use_conv"] = np.int64(kw["use_conv"])
         np.savez_compressed(os.path.join(OUT, f"adapter_xl_{tag}.npz"), **d)
+    # tensor-core-sized configs (channels % 64 == 0) for the CUDA Adapter_XL parity test; weights and input are rounded
+    # to bf16-representable values BEFORE the reference runs, so the fixture isolates activation rounding.
+    for tag, kw, px in (("g64", dict(channels=[64, 64, 64, 128], nums_rb=1, cin=192, ksize=3, sk=True, use_conv=True), 128),
+                        ("g64k1", dict(channels=[64, 64, 64, 64], nums_rb=2, cin=192, ksize=1, sk=False, use_conv=False), 64)):
+        torch.manual_seed(8)
+        m = Adapter_XL(**kw).eval()
+        sd = {k: (v.to(torch.bfloat16).float() if v.dim() > 1 else v) for k, v in m.state_dict().items()}
+        m.load_state_dict(sd)
+        x = (torch.rand(2, 3, px, px) * 2 - 1).to(torch.bfloat16).float()
+        with torch.no_grad():
+            feats = m(x)
+        d = {f"w::{k}": v.numpy() for k, v in sd.items()}
+        d["x"] = x.numpy()
+        for i, f in enumerate(feats):
+            d[f"feat{i}"] = f.numpy().astype(np.float16 if f.abs().max() < 6e4 else np.float32)
+        d["channels"] = np.asarray(kw["channels"])
+        d["nums_rb"] = np.int64(kw["nums_rb"])
+        d["ksize"] = np.int64(kw["ksize"])
+        d["sk"] = np.int64(kw["sk"])
+        d["use_conv"] = np.int64(kw["use_conv"])
+        np.savez_compressed(os.path.join(OUT, f"adapter_xl_{tag}.npz"), **d)
     # known answer for the production config (params only)
     m = Adapter_XL(sk=True)
     n = sum(p.numel() for p in m.parameters())

@@ -1,0 +1,290 @@
+"""Kernel-level parity of every C-ABI entry point against a plain PyTorch fp32 reference of the same op.
+
+All inputs are bf16-representable so the only differences are accumulation order (fp32 in both) and the final bf16
+rounding of the output; tolerances are written per test.  Runs on the GPU box only (``-m gpu``).
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from mri_diffusion_superresolution_b200 import ops as _ops
+    sms, cc = _ops.device_info()
+    assert cc >= 100, f"needs sm_100a, got cc {cc}"
+    return _ops
+
+
+def _bf(shape, seed, scale=1.0, device="cuda"):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(torch.bfloat16).to(device)
+
+
+def _f32(shape, seed, scale=1.0, device="cuda"):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(device)
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (256, 128, 128), (4096, 320, 320), (1000, 640, 1280), (77, 1280, 768),
+                                   (64, 256, 2560), (8192, 2560, 320), (300, 20160, 1280)])
+def test_gemm_plain(ops, M, N, K):
+    a = _bf((M, K), 1)
+    w = _bf((N, K), 2, 1.0 / math.sqrt(K))
+    bias = _f32((N,), 3)
+    out = ops.gemm(a, w, bias=bias)
+    ref = a.float() @ w.float().t() + bias
+    assert out.shape == (M, N) and out.dtype == torch.bfloat16
+    assert _rel(out, ref) < 4e-3
+    assert (out.float() - ref).abs().max().item() < 0.06
+
+
+def test_gemm_fp32_out_and_ragged_store(ops):
+    M, K = 4096, 320
+    a = _bf((M, K), 4)
+    w = torch.zeros((64, K), dtype=torch.bfloat16, device="cuda")
+    w[:4] = _bf((4, K), 5, 1.0 / math.sqrt(K))
+    bias = torch.zeros(64, device="cuda")
+    bias[:4] = _f32((4,), 6)
+    out = ops.gemm(a, w, bias=bias, n_store=4, out_fp32=True)
+    ref = a.float() @ w[:4].float().t() + bias[:4]
+    assert out.shape == (M, 4) and out.dtype == torch.float32
+    assert _rel(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("act", ["relu", "silu"])
+def test_gemm_epilogue_act_rowvec_residuals(ops, act):
+    B, HW, K, N = 3, 256, 128, 320
+    M = B * HW
+    a = _bf((M, K), 7)
+    w = _bf((N, K), 8, 1.0 / math.sqrt(K))
+    bias = _f32((N,), 9)
+    rowvec = _f32((B, N + 64), 10)  # strided table
+    r1 = _bf((M, N), 11)
+    r2full = _bf((M, N + 32), 12)
+    r2 = r2full[:, :N]
+    out = ops.gemm(a, w, bias=bias, rowvec=rowvec, rowvec_stride=N + 64, rows_per_batch=HW,
+                   act=ops.ACT_RELU if act == "relu" else ops.ACT_SILU, res1=r1, res2=r2)
+    pre = a.float() @ w.float().t() + bias + rowvec[:, :N].repeat_interleave(HW, 0)
+    ref = (F.relu(pre) if act == "relu" else F.silu(pre)) + r1.float() + r2.float()
+    assert _rel(out, ref) < 4e-3
+
+
+@pytest.mark.parametrize("N2", [256, 2560, 640])
+def test_gemm_geglu(ops, N2):
+    from mri_diffusion_superresolution_b200.packing import pack_geglu
+    M, K = 512, 320
+    a = _bf((M, K), 13)
+    w = _bf((N2, K), 14, 1.0 / math.sqrt(K))
+    b = _f32((N2,), 15)
+    bn = ops.gemm_block_n(N2, ops.ACT_GEGLU)
+    wi, bi = pack_geglu(w, b, bn)
+    out = ops.gemm(a, wi, bias=bi, act=ops.ACT_GEGLU)
+    y = a.float() @ w.float().t() + b
+    val, gate = y.chunk(2, -1)
+    ref = val * F.gelu(gate)
+    assert out.shape == (M, N2 // 2)
+    assert _rel(out, ref) < 5e-3
+
+
+def test_gemm_k_concat(ops):
+    M, K1, K2, N = 640, 320, 64, 960
+    a1full = _bf((M, K1 + 64), 16)
+    a1 = a1full[:, :K1]  # strided view
+    a2 = _bf((M, K2), 17)
+    w = _bf((N, K1 + K2), 18, 1.0 / math.sqrt(K1 + K2))
+    out = ops.gemm(a1, w, a2=a2)
+    ref = torch.cat([a1.float(), a2.float()], 1) @ w.float().t()
+    assert _rel(out, ref) < 4e-3
+
+
+def test_gemm_rejects_bad_shapes(ops):
+    a = _bf((128, 72), 19)
+    w = _bf((64, 72), 20)
+    with pytest.raises(ValueError):
+        ops.gemm(a, w)  # K not a multiple of 64
+    with pytest.raises(RuntimeError):
+        ops.gemm(a.cpu(), w.cpu())  # no CPU path
+
+
+# ------------------------------------------------------------------------------------------------ conv
+@pytest.mark.parametrize("B,H,W,C1,C2,N", [(2, 16, 16, 64, 0, 64), (1, 64, 64, 320, 0, 320), (2, 32, 32, 640, 320, 640),
+                                             (3, 8, 8, 128, 0, 128), (1, 8, 8, 1280, 1280, 1280), (2, 64, 64, 64, 0, 64)])
+def test_conv3x3(ops, B, H, W, C1, C2, N):
+    from mri_diffusion_superresolution_b200.packing import pack_conv3x3
+    x1 = _bf((B, H, W, C1), 21)
+    x2 = _bf((B, H, W, C2), 22) if C2 else None
+    cin = C1 + C2
+    w = _bf((N, cin, 3, 3), 23, 1.0 / math.sqrt(9 * cin))
+    bias = _f32((N,), 24)
+    res = _bf((B * H * W, N), 25)
+    out = ops.gemm(x1, pack_conv3x3(w), a2=x2, bias=bias, res1=res, conv=True)
+    xin = x1 if x2 is None else torch.cat([x1, x2], -1)
+    ref = F.conv2d(xin.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(B * H * W, N)
+    ref = ref + res.float()
+    assert _rel(out, ref) < 4e-3
+
+
+def test_conv3x3_stride2_via_im2col(ops):
+    from mri_diffusion_superresolution_b200.packing import pack_conv3x3
+    B, H, W, C = 2, 32, 32, 320
+    x = _bf((B, H, W, C), 26)
+    w = _bf((C, C, 3, 3), 27, 1.0 / math.sqrt(9 * C))
+    bias = _f32((C,), 28)
+    cols = ops.im2col3x3s2(x)
+    out = ops.gemm(cols, pack_conv3x3(w), bias=bias)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, stride=2, padding=1).permute(0, 2, 3, 1).reshape(-1, C)
+    assert _rel(out, ref) < 4e-3
+
+
+def test_conv_in_via_im2col_first(ops):
+    from mri_diffusion_superresolution_b200.packing import pack_conv3x3, pad_cols
+    B, Cin, H, W, N = 2, 4, 64, 64, 320
+    x = _bf((B, Cin, H, W), 29).float()
+    w = _bf((N, Cin, 3, 3), 30, 1.0 / 6)
+    cols = ops.im2col_first(x, 64)
+    out = ops.gemm(cols, pad_cols(pack_conv3x3(w), 64))
+    ref = F.conv2d(x, w.float(), None, padding=1).permute(0, 2, 3, 1).reshape(-1, N)
+    assert _rel(out, ref) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("B,heads,d,nq,nk,bcast", [(2, 8, 40, 1024, 1024, False), (1, 8, 40, 4096, 4096, False),
+                                                    (2, 8, 80, 256, 256, False), (2, 8, 160, 64, 64, False),
+                                                    (2, 8, 40, 1024, 77, True), (3, 8, 160, 64, 77, True),
+                                                    (2, 2, 64, 100, 50, False), (1, 4, 8, 16, 16, False)])
+def test_attention(ops, B, heads, d, nq, nk, bcast):
+    c = heads * d
+    qkv = _bf((B * nq, 3 * c), 31)
+    q = qkv[:, :c]
+    if nk == nq and not bcast:
+        k, v = qkv[:, c:2 * c], qkv[:, 2 * c:]
+    else:
+        kv = _bf(((1 if bcast else B) * nk, 2 * c), 32)
+        k, v = kv[:, :c], kv[:, c:]
+    out = ops.attention(q, k, v, B, heads, kv_broadcast=bcast)
+    qh = q.float().reshape(B, nq, heads, d).transpose(1, 2)
+    kb = k.float().reshape(-1, nk, heads, d).transpose(1, 2)
+    vb = v.float().reshape(-1, nk, heads, d).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(qh, kb.expand(B, -1, -1, -1), vb.expand(B, -1, -1, -1))
+    ref = ref.transpose(1, 2).reshape(B * nq, c)
+    assert _rel(out, ref) < 1e-2
+
+
+# ------------------------------------------------------------------------------------------------ norms
+@pytest.mark.parametrize("B,HW,C1,C2,silu,eps", [(2, 4096, 320, 0, True, 1e-5), (2, 1024, 640, 320, True, 1e-5),
+                                                  (1, 64, 1280, 1280, True, 1e-5), (3, 256, 1280, 0, False, 1e-6),
+                                                  (2, 64, 64, 0, True, 1e-5)])
+def test_groupnorm(ops, B, HW, C1, C2, silu, eps):
+    h = int(math.isqrt(HW))
+    x1 = _bf((B, h, h, C1), 33) + 0.5
+    x2 = _bf((B, h, h, C2), 34) * 2 if C2 else None
+    C = C1 + C2
+    gamma, beta = _f32((C,), 35) * 0.1 + 1, _f32((C,), 36) * 0.1
+    out = ops.groupnorm(x1, gamma, beta, 32, eps, silu, x2=x2)
+    xin = x1 if x2 is None else torch.cat([x1, x2], -1)
+    ref = F.group_norm(xin.float().permute(0, 3, 1, 2), 32, gamma, beta, eps)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 3, 1)
+    assert (out.float() - ref).abs().max().item() < 0.03
+    assert _rel(out, ref) < 4e-3
+
+
+@pytest.mark.parametrize("rows,C", [(4096, 320), (1000, 640), (77, 1280), (5, 64)])
+def test_layernorm(ops, rows, C):
+    x = _bf((rows, C), 37) * 3 + 1
+    gamma, beta = _f32((C,), 38) * 0.1 + 1, _f32((C,), 39) * 0.1
+    out = ops.layernorm(x, gamma, beta, 1e-5)
+    ref = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
+    assert _rel(out, ref) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------ scheduler + helpers
+def test_sched_step_and_res_shift(ops):
+    n = (5, 4, 64, 64)
+    x, eps, lr, z = (_f32(n, s) for s in (40, 41, 42, 43))
+    coef = torch.tensor([1.01, -0.2, 0.003, 0.05], device="cuda")
+    out = ops.sched_step(x, eps, coef, lr=lr, z=z)
+    ref = coef[0] * x + coef[1] * eps + coef[2] * lr + coef[3] * z
+    assert torch.allclose(out, ref, rtol=1e-6, atol=1e-6)
+    out2 = ops.sched_step(x, eps, torch.tensor([1.01, -0.2, 0.0, 0.0], device="cuda"))
+    assert torch.allclose(out2, 1.01 * x - 0.2 * eps, rtol=1e-6, atol=1e-6)
+    table = torch.tensor([[0.9, 0.3], [0.5, 0.7], [0.1, 0.99], [1.0, 0.0], [0.3, 0.2]], device="cuda")
+    tsv = torch.tensor([4, 0, 2, 2, 1], device="cuda")
+    o3 = ops.res_shift(x, lr, z, table, tsv)
+    sa, s1 = table[tsv, 0].view(-1, 1, 1, 1), table[tsv, 1].view(-1, 1, 1, 1)
+    assert torch.equal(o3, sa * x + (1 - sa) * lr + s1 * z)  # bit-exact: same op order, no FMA contraction
+    o4 = ops.res_shift(x, lr, z, table, tsv[2:3])
+    assert torch.equal(o4, 0.1 * x + (1 - table[2, 0]) * lr + 0.99 * z)
+    idx = torch.tensor([3], dtype=torch.int32, device="cuda")
+    ctab = torch.arange(24, dtype=torch.float32, device="cuda").view(6, 4) * 0.01
+    ztab = _f32((6,) + n, 50)
+    o5 = ops.sched_step_indexed(x, eps, ctab, idx, lr=lr, z_table=ztab)
+    c = ctab[3]
+    assert torch.allclose(o5, c[0] * x + c[1] * eps + c[2] * lr + c[3] * ztab[3], rtol=1e-6, atol=1e-6)
+    with pytest.raises(ValueError):
+        ops.res_shift(x, lr, z, table, tsv[:2])
+
+
+def test_bilinear_and_uint8_vis(ops):
+    x = _f32((2, 3, 16, 24), 51)
+    out = ops.bilinear_resize(x, (32, 40))
+    ref = F.interpolate(x, size=(32, 40), mode="bilinear", align_corners=False)
+    assert torch.allclose(out, ref, rtol=1e-5, atol=1e-6)
+    down = ops.bilinear_resize(x, (8, 12))
+    assert torch.allclose(down, F.interpolate(x, size=(8, 12), mode="bilinear", align_corners=False), rtol=1e-5, atol=1e-6)
+    img = _f32((1, 64, 48), 52)
+    u8 = ops.to_uint8_vis(img)
+    ref8 = ((img / 2 + 0.5).clamp(0, 1).cpu().permute(1, 2, 0).numpy() * 255).astype("uint8")
+    assert (u8.cpu().numpy() == ref8.repeat(3, axis=-1)).all()
+    img3 = _f32((3, 32, 32), 53)
+    ref83 = ((img3 / 2 + 0.5).clamp(0, 1).cpu().permute(1, 2, 0).numpy() * 255).astype("uint8")
+    assert (ops.to_uint8_vis(img3).cpu().numpy() == ref83).all()
+
+
+def test_timestep_embedding(ops):
+    t = torch.tensor([999.0, 19.0, 0.0, 500.0], device="cuda")
+    out = ops.timestep_embedding(t, 320)
+    half = 160
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device="cuda") / half)
+    ang = t[:, None] * freqs[None]
+    ref = torch.cat([ang.cos(), ang.sin()], -1)
+    assert (out.float() - ref).abs().max().item() < 8e-3  # bf16 output rounding (|x| <= 1 -> ulp 2^-8)
+
+
+def test_layout_helpers(ops):
+    x = _bf((2, 8, 8, 64), 44)
+    up = ops.upsample2x(x)
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(up.float(), ref)
+    xn = _f32((2, 5, 16, 16), 45)
+    nhwc = ops.nchw_to_nhwc(xn, torch.float32)
+    assert torch.equal(nhwc, xn.permute(0, 2, 3, 1).contiguous())
+    back = ops.nhwc_to_nchw(nhwc, torch.float32)
+    assert torch.equal(back, xn)
+    pu = ops.pixel_unshuffle_nhwc(_f32((2, 3, 64, 64), 46), 8)
+    refpu = F.pixel_unshuffle(_f32((2, 3, 64, 64), 46), 8).permute(0, 2, 3, 1).to(torch.bfloat16)
+    assert torch.equal(pu, refpu)
+    a, b = _bf((4, 64), 47), _bf((4, 64), 48)
+    assert torch.equal(ops.add(a, b), (a.float() + b.float()).to(torch.bfloat16))
+    ap = ops.avgpool2(x)
+    refap = F.avg_pool2d(x.float().permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+    assert (ap.float() - refap).abs().max().item() < 0.02
+    idx = torch.zeros(1, dtype=torch.int32, device="cuda")
+    table = _f32((6, 40), 49)
+    dst = torch.empty(40, device="cuda")
+    ops.advance_index(idx)
+    ops.advance_index(idx)
+    ops.select_row(table, idx, dst)
+    assert torch.equal(dst, table[2])
