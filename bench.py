@@ -153,6 +153,7 @@ def main():
     import torch.distributed as dist
     from mri_diffusion_superresolution_b200 import _lib, ops
     from mri_diffusion_superresolution_b200.adapter import Adapter_XL
+    from mri_diffusion_superresolution_b200.parallel import gather_slices
     from mri_diffusion_superresolution_b200.sampler import SliceSampler
     from mri_diffusion_superresolution_b200.scheduler import ResShiftScheduler
     from mri_diffusion_superresolution_b200.synthetic import init_unet_params, phantom_volume
@@ -192,12 +193,11 @@ def main():
     lr_lat = torch.randn((B, 4, 64, 64), generator=g, device=dev)
     ehs = torch.randn((1, 77, 768), generator=torch.Generator(device=dev).manual_seed(1236), device=dev)
     noises = torch.randn((NI + 1, B, 4, 64, 64), generator=torch.Generator(device=dev).manual_seed(4321 + rank), device=dev)
-    gather = [torch.empty((B, 4, 64, 64), device=dev) for _ in range(world)] if world > 1 else None
 
     def step_device():
         out = sampler.sample(lr_lat, ehs, cond_image=slices, noises=noises)
         if world > 1:
-            dist.all_gather(gather, out)
+            out = gather_slices(out, B * world)      # the path's one collective: NCCL all_gather over NVLink
         return out
 
     def barrier():
@@ -243,7 +243,7 @@ def main():
             d_lat = h_lat.to(dev, non_blocking=True)
             o = sampler.sample(d_lat, ehs, cond_image=d_sl, generator=gen)
             if world > 1:
-                dist.all_gather(gather, o)
+                o = gather_slices(o, B * world)[rank * B:(rank + 1) * B]
             h_out.copy_(o, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             return float(h_out[0, 0, 0, 0])

@@ -1,0 +1,175 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol the header declares, host bookkeeping is
+bit-exact against the oracle, weight re-layouts are exact, the product refuses CPU tensors, and the multi-GPU slice
+sharding works under a 2-rank gloo group."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_library_exports_every_declared_symbol():
+    from mri_diffusion_superresolution_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "mrisr_b200.h")).read()
+    declared = set(re.findall(r"\b(mrisr_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"mrisr_gemm_args"}
+    assert len(declared) >= 25
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.mrisr_abi_version() == 1
+    assert lib.mrisr_gemm_block_n(320, 0) == 160 and lib.mrisr_gemm_block_n(2560, 3) == 256 and lib.mrisr_gemm_block_n(100, 0) == 0
+
+
+def test_no_cpu_path():
+    from mri_diffusion_superresolution_b200 import ops, res_srdiff
+    from mri_diffusion_superresolution_b200.adapter import Adapter_XL
+    from mri_diffusion_superresolution_b200.scheduler import ResShiftScheduler
+    x = torch.zeros(1, 4, 8, 8)
+    with pytest.raises(RuntimeError):
+        ops.sched_step(x, x, torch.zeros(4))
+    with pytest.raises(RuntimeError):
+        res_srdiff.get_res_shifting_latents(x, x, torch.tensor(5), ResShiftScheduler(), x)
+    with pytest.raises(RuntimeError):
+        Adapter_XL(channels=[64, 64, 64, 64], nums_rb=1, sk=True, device="cpu")(torch.zeros(1, 3, 64, 64))
+    with pytest.raises(ValueError):
+        Adapter_XL(channels=[8, 16, 32, 32])  # channel counts the tensor-core kernels cannot take
+
+
+def test_scheduler_matches_oracle_bit_exact():
+    from oracle import sched_oracle as so
+    from mri_diffusion_superresolution_b200.scheduler import ResShiftScheduler
+    ab = so.alphas_cumprod(so.make_betas())
+    for spacing, off in (("trailing", 0), ("leading", 1), ("linspace", 0)):
+        for n in (1, 6, 20, 50, 1000):
+            s = ResShiftScheduler(timestep_spacing=spacing, steps_offset=off)
+            assert torch.equal(s.alphas_cumprod, ab)
+            s.set_timesteps(n)
+            ts = so.timesteps(n, spacing=spacing, steps_offset=off)
+            assert s.timesteps.dtype == torch.int64 and s.timesteps.tolist() == ts.tolist()
+            if spacing == "linspace" or (n == 1000 and spacing == "leading"):
+                continue
+            for kind in ("res_srdiff", "ddim"):
+                if kind == "ddim" and spacing == "trailing" and n in (1,):
+                    pass
+                c, book = s.step_table(kind)
+                co, booko = so.step_coefficients(kind, ab, ts)
+                assert book == booko
+                np.testing.assert_array_equal(c, co)
+    z = ResShiftScheduler(rescale_betas_zero_snr=True)
+    assert abs(float(z.alphas_cumprod[-1])) < 1e-9
+    lin = ResShiftScheduler(beta_schedule="linear", beta_start=1e-4, beta_end=0.02)   # MNIST notebook schedule (:121-125)
+    assert torch.equal(lin.alphas_cumprod, so.alphas_cumprod(so.make_betas(1000, 1e-4, 0.02, "linear")))
+    with pytest.raises(ValueError):
+        ResShiftScheduler(prediction_type="v_prediction")
+
+
+def test_ddpm_table_matches_diffusers_formula():
+    from mri_diffusion_superresolution_b200.scheduler import ResShiftScheduler
+    s = ResShiftScheduler()
+    s.set_timesteps(10)
+    coef, book = s.step_table("ddpm")
+    ab = s.alphas_cumprod.double()
+    g = torch.Generator().manual_seed(0)
+    x, e, z = (torch.randn(2, 4, 8, 8, generator=g, dtype=torch.float64) for _ in range(3))
+    ts = s.timesteps.tolist()
+    for i, t in enumerate(ts):
+        p = ts[i + 1] if i + 1 < len(ts) else -1
+        a_t, a_p = ab[t], (ab[p] if p >= 0 else torch.tensor(1.0, dtype=torch.float64))
+        cur_a = a_t / a_p
+        x0 = (x - (1 - a_t) ** 0.5 * e) / a_t ** 0.5
+        prev = (a_p ** 0.5 * (1 - cur_a)) / (1 - a_t) * x0 + cur_a ** 0.5 * (1 - a_p) / (1 - a_t) * x
+        if t > 0:
+            prev = prev + torch.clamp((1 - a_p) / (1 - a_t) * (1 - cur_a), min=1e-20) ** 0.5 * z
+        c = coef[i]
+        got = c[0] * x + c[1] * e + c[3] * z
+        assert book[i] == (t, p, t > 0)
+        torch.testing.assert_close(got, prev, rtol=1e-10, atol=1e-10)
+
+
+def test_weight_packing_is_exact():
+    from mri_diffusion_superresolution_b200 import packing as pk
+    g = torch.Generator().manual_seed(1)
+    w = torch.randn(6, 5, 3, 3, generator=g)
+    x = torch.randn(2, 5, 7, 7, generator=g)
+    cols = torch.nn.functional.unfold(x, 3, padding=1)                       # [B, Cin*9, L], k = c*9 + tap
+    cols = cols.view(2, 5, 9, -1).permute(0, 3, 2, 1).reshape(2 * 49, 45)    # -> k = tap*Cin + c
+    ref = torch.nn.functional.conv2d(x, w, padding=1).permute(0, 2, 3, 1).reshape(-1, 6)
+    torch.testing.assert_close(cols @ pk.pack_conv3x3(w).t(), ref, rtol=1e-5, atol=1e-5)
+    # GEGLU interleave
+    wg, bg = torch.randn(512, 16, generator=g), torch.randn(512, generator=g)
+    wi, bi = pk.pack_geglu(wg, bg, 128)
+    y = torch.randn(3, 16, generator=g)
+    full = y @ wi.t() + bi
+    tiles = full.view(3, 4, 2, 64)
+    val, gate = (y @ wg.t() + bg).chunk(2, -1)
+    torch.testing.assert_close(tiles[:, :, 0].reshape(3, 256), val)
+    torch.testing.assert_close(tiles[:, :, 1].reshape(3, 256), gate)
+    # LoRA rank extension == W x + s * B (A x)
+    ws = [torch.randn(8, 16, generator=g) for _ in range(3)]
+    As = [torch.randn(4, 16, generator=g) for _ in range(3)]
+    Bs = [torch.randn(8, 4, generator=g) for _ in range(3)]
+    t = y @ pk.pack_lora_down(As).t()
+    out = torch.cat([y, t], 1) @ pk.pack_lora_up(ws, Bs, 0.5).t()
+    ref = torch.cat([y @ w_.t() + 0.5 * (y @ a.t()) @ b.t() for w_, a, b in zip(ws, As, Bs)], 1)
+    torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_state_dict_key_normalisation_and_param_shapes():
+    from oracle import unet_oracle as uo
+    from mri_diffusion_superresolution_b200.synthetic import unet_param_shapes
+    from mri_diffusion_superresolution_b200.unet import UNetConfig, normalize_state_dict_keys
+    cfg = UNetConfig(lora_rank=16, lora_alpha=16.0)
+    assert unet_param_shapes(cfg) == uo.param_shapes(uo.UNetConfig(lora_rank=16, lora_alpha=16.0))
+    assert sum(int(np.prod(s)) for k, s in unet_param_shapes(UNetConfig()).items()) == 859_520_964
+    k = normalize_state_dict_keys({
+        "unet.down_blocks.0.attentions.0.transformer_blocks.0.attn1.to_q.lora_A.weight": 1,
+        "base_model.model.mid_block.attentions.0.transformer_blocks.0.attn2.to_out.0.lora_B.default.weight": 2,
+        "base_model.model.mid_block.attentions.0.transformer_blocks.0.attn2.to_k.base_layer.weight": 3,
+        "conv_in.weight": 4})
+    assert set(k) == {"down_blocks.0.attentions.0.transformer_blocks.0.attn1.to_q.lora_A.weight",
+                      "mid_block.attentions.0.transformer_blocks.0.attn2.to_out.0.lora_B.weight",
+                      "mid_block.attentions.0.transformer_blocks.0.attn2.to_k.weight", "conv_in.weight"}
+
+
+def test_phantom_slices_follow_the_slice_contract():
+    from mri_diffusion_superresolution_b200.synthetic import phantom_volume
+    v = phantom_volume(3, size=(64, 64, 8))
+    assert v.shape == (8, 1, 64, 64) and v.dtype == torch.float32
+    assert float(v.min()) >= -1.0 and float(v.max()) <= 1.0
+    assert torch.equal(v, phantom_volume(3, size=(64, 64, 8)))
+
+
+def _gloo_worker(rank, world, port, n_slices, q):
+    import torch.distributed as dist
+    from mri_diffusion_superresolution_b200.parallel import gather_slices, shard_range
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lo, hi = shard_range(n_slices, rank, world)
+    full = torch.arange(n_slices * 4 * 2 * 2, dtype=torch.float32).view(n_slices, 4, 2, 2)
+    out = gather_slices(full[lo:hi] * 2.0, n_slices)          # each rank "processes" its own slices
+    q.put((rank, bool(torch.equal(out, full * 2.0)), (lo, hi)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_slices", [8, 7, 1])
+def test_slice_sharding_two_ranks_gloo(n_slices):
+    import torch.multiprocessing as mp
+    from mri_diffusion_superresolution_b200.parallel import shard_range
+    assert [shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + n_slices
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, n_slices, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res)
+    assert res[0][2][0] == 0 and res[1][2][1] == n_slices and res[0][2][1] == res[1][2][0]
