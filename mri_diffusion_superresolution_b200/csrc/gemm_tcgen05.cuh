@@ -41,25 +41,193 @@ struct GemmKernelParams {
   void* out;
   long long ldo;
   int out_fp32;
+  int dbg;  // timing experiments only: bit0 = skip TMA issue, bit1 = skip MMA issue (results are garbage)
 };
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;  // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: epilogue (2 per TMEM lane quarter)
+constexpr int kEpilogueThreads = 256;
 
 template <int BN>
 struct GemmCfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 160) ? 5 : (BN == 128) ? 6 : 8;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN >= 160) ? 5 : (BN == 128) ? 6 : 8;
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024: manual alignment slack
+  static constexpr int kBiasBytes = 2 * BN * 4;  // epilogue-staged bias, one slab per accumulator stage
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kBiasBytes + 1024;  // +1024: manual alignment slack
 };
 
 __device__ __forceinline__ float act_silu(float x) { return x / (1.f + __expf(-x)); }
-__device__ __forceinline__ float act_gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// Exact-erf GELU (diffusers GEGLU, F.gelu default) with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far
+// below the bf16 output rounding): 2 MUFU + ~12 FMA-class instructions instead of libdevice erff's branchy ~40.
+__device__ __forceinline__ float act_gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = 1.f - poly * t * __expf(-z * z);  // erf(|x|/sqrt2)
+  return 0.5f * x * (1.f + copysignf(e, x));
+}
+
+// Epilogue of one accumulator tile for ONE output row per thread: thread (lane quarter q, lane) owns TMEM lane
+// q*32+lane == output row m and walks the 32-column chunks [c_begin, c_end) of the tile (two warps share a lane
+// quarter and split the chunks).  TMEM loads are software-pipelined one chunk ahead; bias / time-embedding rows are
+// fetched as 128-bit broadcast loads.
+__device__ __forceinline__ void add_vec32(float (&f)[32], const float* __restrict__ src) {
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const float4 b = __ldg(s4 + u);
+    f[4 * u] += b.x; f[4 * u + 1] += b.y; f[4 * u + 2] += b.z; f[4 * u + 3] += b.w;
+  }
+}
+__device__ __forceinline__ void add_res32(float (&f)[32], const __nv_bfloat16* __restrict__ src) {
+  const uint4* r = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const uint4 x = __ldg(r + u);
+    f[u * 8 + 0] += bf16_lo(x.x); f[u * 8 + 1] += bf16_hi(x.x);
+    f[u * 8 + 2] += bf16_lo(x.y); f[u * 8 + 3] += bf16_hi(x.y);
+    f[u * 8 + 4] += bf16_lo(x.z); f[u * 8 + 5] += bf16_hi(x.z);
+    f[u * 8 + 6] += bf16_lo(x.w); f[u * 8 + 7] += bf16_hi(x.w);
+  }
+}
+
+__device__ __forceinline__ void ld_res32(uint4 (&r)[4], const __nv_bfloat16* __restrict__ src) {
+  const uint4* p4 = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) r[u] = __ldg(p4 + u);
+}
+__device__ __forceinline__ void add_res32r(float (&f)[32], const uint4 (&r)[4]) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    f[u * 8 + 0] += bf16_lo(r[u].x); f[u * 8 + 1] += bf16_hi(r[u].x);
+    f[u * 8 + 2] += bf16_lo(r[u].y); f[u * 8 + 3] += bf16_hi(r[u].y);
+    f[u * 8 + 4] += bf16_lo(r[u].z); f[u * 8 + 5] += bf16_hi(r[u].z);
+    f[u * 8 + 6] += bf16_lo(r[u].w); f[u * 8 + 7] += bf16_hi(r[u].w);
+  }
+}
+__device__ __forceinline__ void add_smem32(float (&f)[32], const float* s) {
+  const float4* s4 = reinterpret_cast<const float4*>(s);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const float4 b = s4[u];
+    f[4 * u] += b.x; f[4 * u + 1] += b.y; f[4 * u + 2] += b.z; f[4 * u + 3] += b.w;
+  }
+}
+
+// Stage this tile's bias slab (BN floats; zeros when there is no bias) in shared memory.  Called by all 256 epilogue
+// threads BEFORE they wait for the accumulator, so the global loads overlap the tile's MMAs.
+template <int BN>
+__device__ __forceinline__ void gemm_stage_bias(const GemmKernelParams& p, float* sbias, int n_blk, int et) {
+  if (et < BN) sbias[et] = p.bias != nullptr ? __ldg(p.bias + n_blk * BN + et) : 0.f;
+  asm volatile("bar.sync 1, 256;" ::: "memory");  // epilogue warps only (named barrier 1)
+}
+
+template <int BN>
+__device__ __forceinline__ void gemm_epilogue_rows(const GemmKernelParams& p, uint32_t t_row, int m, int n_blk, int half,
+                                                   const float* sbias) {
+  const bool row_ok = m < p.M;
+  const bool geglu = p.act == ACT_GEGLU;
+  const int out_cols = geglu ? BN / 2 : BN;
+  const int nchunks = out_cols / 32;
+  const int c_begin = half == 0 ? 0 : (nchunks + 1) / 2;
+  const int c_end = half == 0 ? (nchunks + 1) / 2 : nchunks;
+  if (c_begin >= c_end) return;
+  const int n_w0 = n_blk * BN;        // first weight row of this tile
+  const int n_o0 = n_blk * out_cols;  // first output column of this tile
+  const float* rv = nullptr;
+  if (p.rowvec != nullptr && row_ok) rv = p.rowvec + static_cast<long long>(m / p.rows_per_batch) * p.rowvec_stride;
+  const __nv_bfloat16* r1p = (p.res1 != nullptr && row_ok) ? p.res1 + static_cast<long long>(m) * p.ldr1 + n_o0 : nullptr;
+  const __nv_bfloat16* r2p = (p.res2 != nullptr && row_ok) ? p.res2 + static_cast<long long>(m) * p.ldr2 + n_o0 : nullptr;
+  uint32_t v[32], g[32];
+  uint4 rn1[4], rn2[4];  // residuals of the NEXT chunk (prefetched one chunk ahead, like the TMEM loads)
+  tmem_ld_32x32(t_row + c_begin * 32, v);
+  if (geglu) tmem_ld_32x32(t_row + out_cols + c_begin * 32, g);
+  const bool full0 = n_o0 + c_begin * 32 + 32 <= p.n_store;
+  if (r1p != nullptr && full0) ld_res32(rn1, r1p + c_begin * 32);
+  if (r2p != nullptr && full0) ld_res32(rn2, r2p + c_begin * 32);
+  for (int c = c_begin; c < c_end; ++c) {
+    float f[32];
+    const bool next = c + 1 < c_end;
+    const bool fulln = next && (n_o0 + (c + 1) * 32 + 32 <= p.n_store);
+    tmem_ld_wait();
+    if (geglu) {
+      float gg[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { f[j] = __uint_as_float(v[j]); gg[j] = __uint_as_float(g[j]); }
+      if (next) {  // prefetch the next chunk while this one is processed
+        tmem_ld_32x32(t_row + (c + 1) * 32, v);
+        tmem_ld_32x32(t_row + out_cols + (c + 1) * 32, g);
+      }
+      add_smem32(f, sbias + c * 32);
+      add_smem32(gg, sbias + out_cols + c * 32);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] *= act_gelu_erf(gg[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      if (next) tmem_ld_32x32(t_row + (c + 1) * 32, v);
+      add_smem32(f, sbias + c * 32);
+      if (rv != nullptr) add_vec32(f, rv + n_w0 + c * 32);
+      if (p.act == ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+      } else if (p.act == ACT_SILU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = act_silu(f[j]);
+      }
+    }
+    const int n = n_o0 + c * 32;
+    if (row_ok && n < p.n_store) {
+      if (n + 32 <= p.n_store) {
+        if (geglu) {  // (GEGLU + residual is not used by the UNet; keep it correct, unpipelined)
+          if (r1p != nullptr) add_res32(f, r1p + c * 32);
+          if (r2p != nullptr) add_res32(f, r2p + c * 32);
+        } else {
+          if (r1p != nullptr) add_res32r(f, rn1);
+          if (r2p != nullptr) add_res32r(f, rn2);
+          // refill for the next chunk right after use: the loads fly during this chunk's stores and the next
+          // chunk's TMEM wait / bias / activation work
+          if (r1p != nullptr && fulln) ld_res32(rn1, r1p + (c + 1) * 32);
+          if (r2p != nullptr && fulln) ld_res32(rn2, r2p + (c + 1) * 32);
+        }
+        if (p.out_fp32) {
+          float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<long long>(m) * p.ldo + n);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) o[u] = make_float4(f[4 * u], f[4 * u + 1], f[4 * u + 2], f[4 * u + 3]);
+        } else {
+          uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(m) * p.ldo + n);
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            o[u] = make_uint4(pack_bf16(f[8 * u], f[8 * u + 1]), pack_bf16(f[8 * u + 2], f[8 * u + 3]),
+                              pack_bf16(f[8 * u + 4], f[8 * u + 5]), pack_bf16(f[8 * u + 6], f[8 * u + 7]));
+        }
+      } else {
+        // ragged last chunk (e.g. conv_out, 4 real columns): predicated scalar path (fully unrolled so f[] stays in registers)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (n + j < p.n_store) {
+            float x = f[j];
+            if (p.res1 != nullptr) x += __bfloat162float(p.res1[static_cast<long long>(m) * p.ldr1 + n + j]);
+            if (p.res2 != nullptr) x += __bfloat162float(p.res2[static_cast<long long>(m) * p.ldr2 + n + j]);
+            if (p.out_fp32)
+              static_cast<float*>(p.out)[static_cast<long long>(m) * p.ldo + n + j] = x;
+            else
+              static_cast<__nv_bfloat16*>(p.out)[static_cast<long long>(m) * p.ldo + n + j] = __float2bfloat16(x);
+          }
+        }
+      }
+    }
+  }
+}
 
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -75,6 +243,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  float* sbias_base = reinterpret_cast<float*>(smem_raw + (bar_base + Cfg::kBarBytes - smem_u32(smem_raw)));
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -93,7 +262,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 128);
+      mbar_init(tempty_bar(s), kEpilogueThreads);
     }
     fence_mbar_init();
   }
@@ -107,9 +276,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
   const int kchunks = p.kc1 + p.kc2;
   const int kiters = p.taps * kchunks;
 
+  // warps 0-3 (one warpgroup) need few registers; each role branch re-balances so the 8 epilogue warps get 200
   if (warp == 0) {
-    if (lane == 0) {
+    reg_dealloc<72>();
+    {
       // ===================== TMA producer =====================
+      // The whole warp walks the loop (warp-uniform control flow keeps descriptors / coordinates in uniform registers:
+      // a single divergent thread makes ptxas wrap every UTMALDG / UTCHMMA in an ELECT + R2UR waterfall loop);
+      // one elected lane issues.
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -128,23 +302,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
             const uint32_t sb = sa + Cfg::kABytes;
-            mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-            const bool first = kc < p.kc1;
-            const CUtensorMap* ma = first ? &tmA1 : &tmA2;
-            const int c0 = (first ? kc : kc - p.kc1) * kBlockK;
-            if (p.conv)
-              tma_load_4d(sa, ma, full_bar(stage), c0, ds, h0 + dr, b0);
-            else
-              tma_load_2d(sa, ma, full_bar(stage), c0, m0);
-            tma_load_2d(sb, &tmB, full_bar(stage), (tap * kchunks + kc) * kBlockK, n0);
+            if (elect_one()) {
+              if (p.dbg & 1) {
+                mbar_arrive(full_bar(stage));
+              } else {
+                mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+                const bool first = kc < p.kc1;
+                const CUtensorMap* ma = first ? &tmA1 : &tmA2;
+                const int c0 = (first ? kc : kc - p.kc1) * kBlockK;
+                if (p.conv)
+                  tma_load_4d(sa, ma, full_bar(stage), c0, ds, h0 + dr, b0);
+                else
+                  tma_load_2d(sa, ma, full_bar(stage), c0, m0);
+                tma_load_2d(sb, &tmB, full_bar(stage), (tap * kchunks + kc) * kBlockK, n0);
+              }
+            }
+            __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
+    reg_dealloc<72>();
+    {
+      // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
       constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -160,125 +342,36 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint64_t adesc = umma_smem_desc(sa, 1024, kLayoutSW128);
           const uint64_t bdesc = umma_smem_desc(sa + Cfg::kABytes, 1024, kLayoutSW128);
+          if (elect_one()) {
+            if (!(p.dbg & 2)) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
-          umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+              for (int k = 0; k < kBlockK / 16; ++k)
+                umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+            if (ki == kiters - 1) umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+          }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 4) {
+    reg_dealloc<72>();
+  } else {
+    reg_alloc<216>();
     // ===================== epilogue (TMEM -> regs -> global) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     uint32_t it = 0;
-    constexpr int kOutCols = BN;  // per tile, halved for GEGLU
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
       const int n_blk = tile % p.n_tiles;
       const int m = (tile / p.n_tiles) * kBlockM + q * 32 + lane;
-      const bool row_ok = m < p.M;
+      float* sbias = sbias_base + as * BN;
+      gemm_stage_bias<BN>(p, sbias, n_blk, static_cast<int>(threadIdx.x) - 128);
       mbar_wait(tfull_bar(as), aph);
       tcgen05_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-      const bool geglu = p.act == ACT_GEGLU;
-      const int out_cols = geglu ? kOutCols / 2 : kOutCols;
-      const int n_w0 = n_blk * BN;           // first weight row (bias index) of this tile
-      const int n_o0 = n_blk * out_cols;     // first output column of this tile
-      const float* rv = nullptr;
-      if (p.rowvec != nullptr && row_ok) rv = p.rowvec + static_cast<long long>(m / p.rows_per_batch) * p.rowvec_stride;
-      for (int c = 0; c < out_cols / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_row + c * 32, v);
-        float f[32];
-        if (geglu) {
-          uint32_t g[32];
-          tmem_ld_32x32(t_row + out_cols + c * 32, g);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float a = __uint_as_float(v[j]), gg = __uint_as_float(g[j]);
-            if (p.bias != nullptr) {
-              a += __ldg(p.bias + n_w0 + c * 32 + j);
-              gg += __ldg(p.bias + n_w0 + out_cols + c * 32 + j);
-            }
-            f[j] = a * act_gelu_erf(gg);
-          }
-        } else {
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float a = __uint_as_float(v[j]);
-            if (p.bias != nullptr) a += __ldg(p.bias + n_w0 + c * 32 + j);
-            f[j] = a;
-          }
-          if (rv != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] += __ldg(rv + n_w0 + c * 32 + j);
-          }
-          if (p.act == ACT_RELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-          } else if (p.act == ACT_SILU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = act_silu(f[j]);
-          }
-        }
-        const int n = n_o0 + c * 32;
-        if (row_ok && n < p.n_store) {
-          const bool full = n + 32 <= p.n_store;
-          if (full) {
-            if (p.res1 != nullptr) {
-              const uint4* r = reinterpret_cast<const uint4*>(p.res1 + static_cast<long long>(m) * p.ldr1 + n);
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const uint4 x = __ldg(r + u);
-                f[u * 8 + 0] += bf16_lo(x.x); f[u * 8 + 1] += bf16_hi(x.x);
-                f[u * 8 + 2] += bf16_lo(x.y); f[u * 8 + 3] += bf16_hi(x.y);
-                f[u * 8 + 4] += bf16_lo(x.z); f[u * 8 + 5] += bf16_hi(x.z);
-                f[u * 8 + 6] += bf16_lo(x.w); f[u * 8 + 7] += bf16_hi(x.w);
-              }
-            }
-            if (p.res2 != nullptr) {
-              const uint4* r = reinterpret_cast<const uint4*>(p.res2 + static_cast<long long>(m) * p.ldr2 + n);
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const uint4 x = __ldg(r + u);
-                f[u * 8 + 0] += bf16_lo(x.x); f[u * 8 + 1] += bf16_hi(x.x);
-                f[u * 8 + 2] += bf16_lo(x.y); f[u * 8 + 3] += bf16_hi(x.y);
-                f[u * 8 + 4] += bf16_lo(x.z); f[u * 8 + 5] += bf16_hi(x.z);
-                f[u * 8 + 6] += bf16_lo(x.w); f[u * 8 + 7] += bf16_hi(x.w);
-              }
-            }
-            if (p.out_fp32) {
-              float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<long long>(m) * p.ldo + n);
-#pragma unroll
-              for (int u = 0; u < 8; ++u) o[u] = make_float4(f[4 * u], f[4 * u + 1], f[4 * u + 2], f[4 * u + 3]);
-            } else {
-              uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(m) * p.ldo + n);
-#pragma unroll
-              for (int u = 0; u < 4; ++u)
-                o[u] = make_uint4(pack_bf16(f[8 * u], f[8 * u + 1]), pack_bf16(f[8 * u + 2], f[8 * u + 3]),
-                                  pack_bf16(f[8 * u + 4], f[8 * u + 5]), pack_bf16(f[8 * u + 6], f[8 * u + 7]));
-            }
-          } else {
-            // ragged last chunk (e.g. conv_out, 4 real columns): predicated scalar path (fully unrolled so f[] stays in registers)
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (n + j < p.n_store) {
-                float x = f[j];
-                if (p.res1 != nullptr) x += __bfloat162float(p.res1[static_cast<long long>(m) * p.ldr1 + n + j]);
-                if (p.res2 != nullptr) x += __bfloat162float(p.res2[static_cast<long long>(m) * p.ldr2 + n + j]);
-                if (p.out_fp32)
-                  static_cast<float*>(p.out)[static_cast<long long>(m) * p.ldo + n + j] = x;
-                else
-                  static_cast<__nv_bfloat16*>(p.out)[static_cast<long long>(m) * p.ldo + n + j] = __float2bfloat16(x);
-              }
-            }
-          }
-        }
-      }
+      gemm_epilogue_rows<BN>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN, m, n_blk, (warp - 4) >> 2, sbias);
       tcgen05_fence_before();
       mbar_arrive(tempty_bar(as));
     }
@@ -289,6 +382,182 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
   if (warp == 2) {
     tcgen05_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ======================================================================================================================
+// CTA-pair variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x BN tile.  Each CTA stages its own
+// 128 rows of A and HALF of the W tile (BN/2 rows); one tcgen05.mma (M=256) issued by the leader reads both CTAs' shared
+// memory, so every SM pulls 16 KB + BN*64 B per k-chunk from L2 instead of 16 KB + BN*128 B -- the round-1 profile
+// showed the single-CTA kernel bound by L2->SM operand delivery (71 FLOP/B), this tile is at 100 (BN=160) / 131 (BN=256).
+// Both CTAs' TMA loads complete on the LEADER's full barrier; the leader's commits are multicast to both CTAs' empty /
+// accumulator-full barriers; both CTAs' epilogue warps arrive on the leader's accumulator-empty barrier.
+template <int BN>
+struct GemmPairCfg {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = (BN / 2) * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 6 : (BN == 192) ? 7 : 8;
+  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
+  static constexpr int kBiasBytes = 2 * BN * 4;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kBiasBytes + 1024;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                         const __grid_constant__ CUtensorMap tmB, const GemmKernelParams p) {
+  using Cfg = GemmPairCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  float* sbias_base = reinterpret_cast<float*>(smem_raw + (bar_base + Cfg::kBarBytes - smem_u32(smem_raw)));
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair_id = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmA2);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);   // leader: one arrive.expect_tx covering both CTAs' bytes
+      mbar_init(empty_bar(s), 1);  // one multicast commit per phase
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 2 * kEpilogueThreads);  // 8 epilogue warps x 2 CTAs (only the leader's copy is used)
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int m_tiles = (p.M + 2 * kBlockM - 1) / (2 * kBlockM);
+  const int total_tiles = m_tiles * p.n_tiles;
+  const int kchunks = p.kc1 + p.kc2;
+  const int kiters = p.taps * kchunks;
+
+  if (warp == 0) {
+    reg_dealloc<72>();
+    {
+      // ===================== TMA producer (both CTAs; whole warp loops, one elected lane issues) =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair_id; tile < total_tiles; tile += num_pairs) {
+        const int n0 = (tile % p.n_tiles) * BN + static_cast<int>(rank) * (BN / 2);
+        const int m0 = (tile / p.n_tiles) * (2 * kBlockM) + static_cast<int>(rank) * kBlockM;
+        int b0 = 0, h0 = 0;
+        if (p.conv) {
+          const int hw = p.H * p.W;
+          b0 = m0 / hw;
+          h0 = (m0 - b0 * hw) / p.W;
+        }
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int dr = (p.taps == 9) ? tap / 3 - 1 : 0;
+          const int ds = (p.taps == 9) ? tap % 3 - 1 : 0;
+          for (int kc = 0; kc < kchunks; ++kc) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+            const uint32_t sb = sa + Cfg::kABytes;
+            if (elect_one()) {
+              if (p.dbg & 1) {
+                if (leader) mbar_arrive(full_bar(stage));
+              } else {
+                if (leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+                const bool first = kc < p.kc1;
+                const CUtensorMap* ma = first ? &tmA1 : &tmA2;
+                const int c0 = (first ? kc : kc - p.kc1) * kBlockK;
+                if (p.conv)
+                  tma_load_4d_pair(sa, ma, full_bar(stage), c0, ds, h0 + dr, b0);
+                else
+                  tma_load_2d_pair(sa, ma, full_bar(stage), c0, m0);
+                tma_load_2d_pair(sb, &tmB, full_bar(stage), (tap * kchunks + kc) * kBlockK, n0);
+              }
+            }
+            __syncwarp();
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    reg_dealloc<72>();
+    if (leader) {
+      // ===================== MMA issuer (leader CTA only; whole warp loops, one elected lane issues) =====================
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * kBlockM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;
+      for (int tile = pair_id; tile < total_tiles; tile += num_pairs, ++it) {
+        const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
+        mbar_wait(tempty_bar(as), aph ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int ki = 0; ki < kiters; ++ki) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint64_t adesc = umma_smem_desc(sa, 1024, kLayoutSW128);
+          const uint64_t bdesc = umma_smem_desc(sa + Cfg::kABytes, 1024, kLayoutSW128);
+          if (elect_one()) {
+            if (!(p.dbg & 2)) {
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k)
+                umma_bf16_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit_pair(empty_bar(stage));  // frees this smem slot in BOTH CTAs
+            if (ki == kiters - 1) umma_commit_pair(tfull_bar(as));  // accumulator complete -> both CTAs' epilogues
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp < 4) {
+    reg_dealloc<72>();
+  } else {
+    reg_alloc<216>();
+    // ===================== epilogue (both CTAs; each drains its own 128 TMEM lanes) =====================
+    const int q = warp & 3;
+    uint32_t it = 0;
+    for (int tile = pair_id; tile < total_tiles; tile += num_pairs, ++it) {
+      const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
+      const int n_blk = tile % p.n_tiles;
+      const int m = (tile / p.n_tiles) * (2 * kBlockM) + static_cast<int>(rank) * kBlockM + q * 32 + lane;
+      float* sbias = sbias_base + as * BN;
+      gemm_stage_bias<BN>(p, sbias, n_blk, static_cast<int>(threadIdx.x) - 128);
+      mbar_wait(tfull_bar(as), aph);
+      tcgen05_fence_after();
+      gemm_epilogue_rows<BN>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN, m, n_blk, (warp - 4) >> 2, sbias);
+      tcgen05_fence_before();
+      mbar_arrive_leader(tempty_bar(as));
+    }
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer can still touch its smem / barriers
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
   }
 }
 

@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "../../include/mrisr_b200.h"
 #include "attention.cuh"
@@ -100,6 +101,45 @@ int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap&
   mrisr::gemm_tcgen05_kernel<BN><<<grid, mrisr::kGemmThreads, Cfg::kSmemBytes, st>>>(a1, a2, b, p);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <int BN>
+int launch_gemm_pair(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const mrisr::GemmKernelParams& p,
+                     cudaStream_t st) {
+  using Cfg = mrisr::GemmPairCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    MRISR_CHECK_CUDA(cudaFuncSetAttribute(mrisr::gemm_tcgen05_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int tiles = ((p.M + 255) / 256) * p.n_tiles;
+  const int max_pairs = sm_count() / 2;
+  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(mrisr::kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MRISR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mrisr::gemm_tcgen05_pair_kernel<BN>, a1, a2, b, p));
+  return 0;
+}
+
+// MRISR_GEMM_SINGLE_CTA=1 selects the round-1 single-CTA kernel (A/B measurements only; same results)
+bool use_pair_kernel() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MRISR_GEMM_SINGLE_CTA");
+    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 template <int D>
@@ -280,6 +320,10 @@ int mrisr_layernorm(const void* x, int64_t ldx, const float* gamma, const float*
 
 int mrisr_gemm_block_n(int N, int act) {
   if (N <= 0) return 0;
+  if (const char* e = getenv("MRISR_GEMM_BN")) {  // tile-shape experiments only
+    const int bn = atoi(e);
+    if ((bn == 64 || bn == 128 || bn == 160 || bn == 192 || bn == 256) && N % bn == 0) return bn;
+  }
   if (act == MRISR_ACT_GEGLU) {
     if (N % 256 == 0) return 256;
     if (N % 128 == 0) return 128;
@@ -311,15 +355,18 @@ int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
   MRISR_REQUIRE(aligned16(g->out) && (g->ldo * esz) % 16 == 0, "gemm: out must be 16-byte aligned with 16-byte row pitch");
   MRISR_REQUIRE((!g->res1 || (aligned16(g->res1) && g->ldr1 % 8 == 0)) && (!g->res2 || (aligned16(g->res2) && g->ldr2 % 8 == 0)), "gemm: residuals must be 16-byte aligned");
   MRISR_REQUIRE(!g->rowvec || g->rows_per_batch > 0, "gemm: rowvec needs rows_per_batch > 0");
+  MRISR_REQUIRE((!g->bias || aligned16(g->bias)) && (!g->rowvec || (aligned16(g->rowvec) && g->rowvec_stride % 4 == 0)),
+                "gemm: bias / rowvec must be 16-byte aligned (rowvec_stride a multiple of 4)");
   MRISR_REQUIRE(!(g->act == MRISR_ACT_GEGLU && g->rowvec), "gemm: rowvec unsupported with GEGLU");
   if (int e = load_encode()) return e;
 
   const int ktot = g->taps * (g->k1 + g->k2);
+  const bool pair = use_pair_kernel();
   CUtensorMap ma1, ma2, mb;
   {
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(ktot), static_cast<cuuint64_t>(g->N)};
     cuuint64_t str[1] = {static_cast<cuuint64_t>(ktot) * 2};
-    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(BN)};
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(pair ? BN / 2 : BN)};
     if (int e = encode_map(&mb, g->w, 2, dims, str, box)) return e;
   }
   if (g->taps == 1) {
@@ -370,9 +417,20 @@ int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
   p.res1 = static_cast<const __nv_bfloat16*>(g->res1); p.ldr1 = g->ldr1;
   p.res2 = static_cast<const __nv_bfloat16*>(g->res2); p.ldr2 = g->ldr2;
   p.out = g->out; p.ldo = g->ldo; p.out_fp32 = g->out_fp32;
+  p.dbg = g->reserved;
   cudaStream_t st = as_stream(stream);
+  if (pair) {
+    switch (BN) {
+      case 256: return launch_gemm_pair<256>(ma1, ma2, mb, p, st);
+      case 192: return launch_gemm_pair<192>(ma1, ma2, mb, p, st);
+      case 160: return launch_gemm_pair<160>(ma1, ma2, mb, p, st);
+      case 128: return launch_gemm_pair<128>(ma1, ma2, mb, p, st);
+      default: return launch_gemm_pair<64>(ma1, ma2, mb, p, st);
+    }
+  }
   switch (BN) {
     case 256: return launch_gemm<256>(ma1, ma2, mb, p, st);
+    case 192: return launch_gemm<192>(ma1, ma2, mb, p, st);
     case 160: return launch_gemm<160>(ma1, ma2, mb, p, st);
     case 128: return launch_gemm<128>(ma1, ma2, mb, p, st);
     default: return launch_gemm<64>(ma1, ma2, mb, p, st);

@@ -51,7 +51,7 @@ def gemm_block_n(n: int, act: int = ACT_NONE) -> int:
 def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[Tensor] = None,
          rowvec: Optional[Tensor] = None, rowvec_stride: int = 0, rows_per_batch: int = 0, act: int = ACT_NONE,
          res1: Optional[Tensor] = None, res2: Optional[Tensor] = None, n_store: Optional[int] = None,
-         out_fp32: bool = False, conv: bool = False, out: Optional[Tensor] = None) -> Tensor:
+         out_fp32: bool = False, conv: bool = False, out: Optional[Tensor] = None, _dbg: int = 0) -> Tensor:
     """``act(concat_K(a1, a2) @ w.T + bias + rowvec[batch]) + res1 + res2`` on the tcgen05 kernel.
 
     GEMM mode: a1 ``[M, k1]`` (+ a2 ``[M, k2]``).  ``conv=True``: a1/a2 are NHWC ``[B, H, W, k]`` and ``w`` is
@@ -118,6 +118,7 @@ def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[T
     g.res1, g.ldr1 = _ptr(res1), (_rows(res1, "gemm.res1") if res1 is not None else 0)
     g.res2, g.ldr2 = _ptr(res2), (_rows(res2, "gemm.res2") if res2 is not None else 0)
     g.out, g.ldo, g.out_fp32 = out.data_ptr(), _rows(out, "gemm.out"), int(out_fp32)
+    g.reserved = _dbg
     if GEMM_PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(torch.cuda.current_stream(a1.device))
