@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmrisr_b200.so")
 SOURCES = ["mrisr_abi.cu"]
-DEPS = ["mrisr_abi.cu", "ptx.cuh", "gemm_tcgen05.cuh", "attention.cuh", "pointwise.cuh",
+DEPS = ["mrisr_abi.cu", "ptx.cuh", "gemm_tcgen05.cuh", "attention.cuh", "attention_tcgen05.cuh", "pointwise.cuh",
         os.path.join("..", "..", "include", "mrisr_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -26,7 +26,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, *SOURCES]
+    cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("MRISR_NVCC_EXTRA", "").split(), "-o", LIB, *SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)

@@ -12,6 +12,7 @@
 
 #include "../../include/mrisr_b200.h"
 #include "attention.cuh"
+#include "attention_tcgen05.cuh"
 #include "gemm_tcgen05.cuh"
 #include "pointwise.cuh"
 
@@ -155,6 +156,51 @@ int launch_attention(const mrisr::AttnArgs& a, cudaStream_t st) {
   mrisr::attention_kernel<D><<<grid, mrisr::kAttnThreads, Cfg::kSmemBytes, st>>>(a);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+// tcgen05 / TMEM attention (head dims 40, 80).  K and V are addressed through TMA maps over [rows, heads*d] views.
+template <int D>
+int launch_attention_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                        int64_t ldo, int batch, int nq, int nk, int heads, int kv_broadcast, cudaStream_t st) {
+  using Cfg = mrisr::AttnTcCfg<D>;
+  if (int e = load_encode()) return e;
+  static bool configured = false;
+  if (!configured) {
+    MRISR_CHECK_CUDA(cudaFuncSetAttribute(mrisr::attention_tcgen05_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          Cfg::kSmemBytes));
+    configured = true;
+  }
+  CUtensorMap mk, mv;
+  const cuuint64_t rows = static_cast<cuuint64_t>(kv_broadcast ? 1 : batch) * nk;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(heads) * D, rows};
+  cuuint32_t box[2] = {64, 128};
+  {
+    cuuint64_t str[1] = {static_cast<cuuint64_t>(ldk) * 2};
+    if (int e = encode_map(&mk, k, 2, dims, str, box)) return e;
+  }
+  {
+    cuuint64_t str[1] = {static_cast<cuuint64_t>(ldv) * 2};
+    if (int e = encode_map(&mv, v, 2, dims, str, box)) return e;
+  }
+  mrisr::AttnTcArgs a;
+  a.q = static_cast<const __nv_bfloat16*>(q); a.ldq = ldq;
+  a.o = static_cast<__nv_bfloat16*>(o); a.ldo = ldo;
+  a.nq = nq; a.nk = nk; a.heads = heads; a.batch = batch;
+  a.kv_rows_per_batch = kv_broadcast ? 0 : nk;
+  a.scale_log2 = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(D)));
+  dim3 grid((nq + mrisr::kAtcBQ - 1) / mrisr::kAtcBQ, heads, batch);
+  mrisr::attention_tcgen05_kernel<D><<<grid, mrisr::kAtcThreads, Cfg::kSmemBytes, st>>>(mk, mv, a);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+bool use_tc_attention() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MRISR_ATTN_LEGACY");  // =1: round-1 mma.sync kernel for every head dim (A/B measurements)
+    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 template <int VPL>
@@ -451,6 +497,11 @@ int mrisr_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   a.nq = nq; a.nk = nk; a.heads = heads; a.batch = batch;
   a.scale_log2 = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(d)));
   cudaStream_t st = as_stream(stream);
+  // tensor-core (tcgen05) path: needs 16-byte aligned, 16-byte-pitched K / V views for TMA and 16-byte aligned O rows
+  if (use_tc_attention() && (d == 40 || d == 80) && nk >= 128 && ldo % 8 == 0) {
+    if (d == 40) return launch_attention_tc<40>(q, ldq, k, ldk, v, ldv, o, ldo, batch, nq, nk, heads, kv_broadcast, st);
+    return launch_attention_tc<80>(q, ldq, k, ldk, v, ldv, o, ldo, batch, nq, nk, heads, kv_broadcast, st);
+  }
   switch (d) {
     case 8: return launch_attention<8>(a, st);
     case 16: return launch_attention<16>(a, st);
