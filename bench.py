@@ -277,8 +277,8 @@ def main():
         s1.record()
         torch.cuda.synchronize(dev)
         prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
-        gemm_ms = sum(a.elapsed_time(b) for _, _, a, b in prof)
-        conv_ms = sum(a.elapsed_time(b) for _, taps, a, b in prof if taps == 9)
+        gemm_ms = sum(a.elapsed_time(b) for _, _, a, b, _ in prof)
+        conv_ms = sum(a.elapsed_time(b) for _, taps, a, b, _ in prof if taps == 9)
         step_ms = s0.elapsed_time(s1)
         algo_tflop = B * (GFLOP_UNET_STEP - GFLOP_SDPA_STEP) / 1e3
         achieved = algo_tflop / (gemm_ms / 1e3)

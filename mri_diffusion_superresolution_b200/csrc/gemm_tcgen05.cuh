@@ -58,7 +58,8 @@ struct GemmCfg {
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
   static constexpr int kBiasBytes = 2 * BN * 4;  // epilogue-staged bias, one slab per accumulator stage
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kBiasBytes + 1024;  // +1024: manual alignment slack
+  static constexpr int kEpiBytes = 8 * 2048;     // per-epilogue-warp 32x32 bf16 transpose buffer (coalesced stores)
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kBiasBytes + kEpiBytes + 1024;  // +1024: manual alignment slack
 };
 
 __device__ __forceinline__ float act_silu(float x) { return x / (1.f + __expf(-x)); }
@@ -133,7 +134,8 @@ __device__ __forceinline__ void gemm_stage_bias(const GemmKernelParams& p, float
 
 template <int BN>
 __device__ __forceinline__ void gemm_epilogue_rows(const GemmKernelParams& p, uint32_t t_row, int m, int n_blk, int half,
-                                                   const float* sbias) {
+                                                   const float* sbias, uint8_t* stage_buf) {
+  const int lane_id = threadIdx.x & 31;
   const bool row_ok = m < p.M;
   const bool geglu = p.act == ACT_GEGLU;
   const int out_cols = geglu ? BN / 2 : BN;
@@ -186,8 +188,9 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmKernelParams& p, ui
       }
     }
     const int n = n_o0 + c * 32;
+    const bool chunk_full = n + 32 <= p.n_store;  // warp-uniform
     if (row_ok && n < p.n_store) {
-      if (n + 32 <= p.n_store) {
+      if (chunk_full) {
         if (geglu) {  // (GEGLU + residual is not used by the UNet; keep it correct, unpipelined)
           if (r1p != nullptr) add_res32(f, r1p + c * 32);
           if (r2p != nullptr) add_res32(f, r2p + c * 32);
@@ -203,12 +206,6 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmKernelParams& p, ui
           float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<long long>(m) * p.ldo + n);
 #pragma unroll
           for (int u = 0; u < 8; ++u) o[u] = make_float4(f[4 * u], f[4 * u + 1], f[4 * u + 2], f[4 * u + 3]);
-        } else {
-          uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(m) * p.ldo + n);
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            o[u] = make_uint4(pack_bf16(f[8 * u], f[8 * u + 1]), pack_bf16(f[8 * u + 2], f[8 * u + 3]),
-                              pack_bf16(f[8 * u + 4], f[8 * u + 5]), pack_bf16(f[8 * u + 6], f[8 * u + 7]));
         }
       } else {
         // ragged last chunk (e.g. conv_out, 4 real columns): predicated scalar path (fully unrolled so f[] stays in registers)
@@ -225,6 +222,28 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmKernelParams& p, ui
           }
         }
       }
+    }
+    if (chunk_full && !p.out_fp32) {
+      // bf16 store, coalesced: the warp's 32 rows x 64 B go through a swizzled shared-memory transpose so that every
+      // store instruction writes 8 rows x 64 contiguous bytes (full 32 B sectors) instead of 32 rows x 16 B.
+      {
+        const int sw = (lane_id >> 1) & 3;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          *reinterpret_cast<uint4*>(stage_buf + lane_id * 64 + ((u ^ sw) << 4)) =
+              make_uint4(pack_bf16(f[8 * u], f[8 * u + 1]), pack_bf16(f[8 * u + 2], f[8 * u + 3]),
+                         pack_bf16(f[8 * u + 4], f[8 * u + 5]), pack_bf16(f[8 * u + 6], f[8 * u + 7]));
+      }
+      __syncwarp();
+      const int m_base = m - lane_id;  // first row of this warp
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = (lane_id >> 2) + 8 * i, u = lane_id & 3;
+        const uint4 val = *reinterpret_cast<const uint4*>(stage_buf + r * 64 + ((u ^ ((r >> 1) & 3)) << 4));
+        if (m_base + r < p.M)
+          *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(m_base + r) * p.ldo + n + u * 8) = val;
+      }
+      __syncwarp();
     }
   }
 }
@@ -244,6 +263,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
   float* sbias_base = reinterpret_cast<float*>(smem_raw + (bar_base + Cfg::kBarBytes - smem_u32(smem_raw)));
+  uint8_t* sepi_base = reinterpret_cast<uint8_t*>(sbias_base) + Cfg::kBiasBytes;
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -371,7 +391,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
       gemm_stage_bias<BN>(p, sbias, n_blk, static_cast<int>(threadIdx.x) - 128);
       mbar_wait(tfull_bar(as), aph);
       tcgen05_fence_after();
-      gemm_epilogue_rows<BN>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN, m, n_blk, (warp - 4) >> 2, sbias);
+      gemm_epilogue_rows<BN>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN, m, n_blk, (warp - 4) >> 2, sbias, sepi_base + (warp - 4) * 2048);
       tcgen05_fence_before();
       mbar_arrive(tempty_bar(as));
     }
@@ -397,11 +417,12 @@ struct GemmPairCfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = (BN / 2) * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 6 : (BN == 192) ? 7 : 8;
+  static constexpr int kStages = (BN == 256) ? 6 : 7;
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
   static constexpr int kBiasBytes = 2 * BN * 4;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kBiasBytes + 1024;
+  static constexpr int kEpiBytes = 8 * 2048;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kBiasBytes + kEpiBytes + 1024;
 };
 
 template <int BN>
@@ -419,6 +440,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
   float* sbias_base = reinterpret_cast<float*>(smem_raw + (bar_base + Cfg::kBarBytes - smem_u32(smem_raw)));
+  uint8_t* sepi_base = reinterpret_cast<uint8_t*>(sbias_base) + Cfg::kBiasBytes;
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -547,7 +569,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
       gemm_stage_bias<BN>(p, sbias, n_blk, static_cast<int>(threadIdx.x) - 128);
       mbar_wait(tfull_bar(as), aph);
       tcgen05_fence_after();
-      gemm_epilogue_rows<BN>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN, m, n_blk, (warp - 4) >> 2, sbias);
+      gemm_epilogue_rows<BN>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN, m, n_blk, (warp - 4) >> 2, sbias, sepi_base + (warp - 4) * 2048);
       tcgen05_fence_before();
       mbar_arrive_leader(tempty_bar(as));
     }

@@ -323,7 +323,7 @@ int mrisr_groupnorm(const void* x1, int64_t ld1, int c1, const void* x2, int64_t
   int R = 256 / nvec;
   if (R < 1) R = 1;
   if (R > hw) R = hw;
-  int want = (296 + batch - 1) / batch;
+  int want = (148 * 8 + batch - 1) / batch;  // >= 8 CTAs per SM chip-wide: these kernels are latency-bound below that
   int max_slabs = (hw + 4 * R - 1) / (4 * R);
   int nslab = want < max_slabs ? want : max_slabs;
   if (nslab > kGnMaxSlabs) nslab = kGnMaxSlabs;

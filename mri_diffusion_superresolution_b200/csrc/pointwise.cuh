@@ -172,7 +172,20 @@ __global__ void groupnorm_stats_kernel(GnArgs a, float2* __restrict__ partial /*
   for (int j = 0; j < 8; ++j) { s[j] = 0.f; ss[j] = 0.f; }
   const int p0 = slab * a.pix_per_slab;
   const int p1 = min(a.hw, p0 + a.pix_per_slab);
-  for (int pix = p0 + ry; pix < p1; pix += R) {
+  int pix = p0 + ry;
+  for (; pix + 3 * R < p1; pix += 4 * R) {  // 4 independent 16-byte loads in flight per thread
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = gn_load(a, b, pix + u * R, vx);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      unpack8(v[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
+    }
+  }
+  for (; pix < p1; pix += R) {
     float f[8];
     unpack8(gn_load(a, b, pix, vx), f);
 #pragma unroll
@@ -234,17 +247,26 @@ __global__ void groupnorm_apply_kernel(GnArgs a, const float2* __restrict__ part
   for (int j = 0; j < 8; ++j) { sc[j] = s_aff[vx * 8 + j]; sh[j] = s_aff[C + vx * 8 + j]; }
   const int p0 = slab * a.pix_per_slab;
   const int p1 = min(a.hw, p0 + a.pix_per_slab);
-  for (int pix = p0 + ry; pix < p1; pix += R) {
+  auto emit = [&](int pix, const uint4& v) {
     float f[8];
-    unpack8(gn_load(a, b, pix, vx), f);
+    unpack8(v, f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float y = f[j] * sc[j] + sh[j];
-      if (silu) y = y / (1.f + __expf(-y));
+      if (silu) y = __fdividef(y, 1.f + __expf(-y));
       f[j] = y;
     }
     reinterpret_cast<uint4*>(out + (static_cast<long long>(b) * a.hw + pix) * C)[vx] = pack8(f);
+  };
+  int pix = p0 + ry;
+  for (; pix + 3 * R < p1; pix += 4 * R) {  // 4 independent 16-byte loads in flight per thread
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = gn_load(a, b, pix + u * R, vx);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) emit(pix + u * R, v[u]);
   }
+  for (; pix < p1; pix += R) emit(pix, gn_load(a, b, pix, vx));
 }
 
 // ---------------------------------------------------------------------------------------------------

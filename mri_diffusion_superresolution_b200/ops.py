@@ -124,7 +124,7 @@ def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[T
         e0.record(torch.cuda.current_stream(a1.device))
         _lib.check(lib.mrisr_gemm(C.byref(g), _stream(a1)), "mrisr_gemm")
         e1.record(torch.cuda.current_stream(a1.device))
-        GEMM_PROFILE.append((2.0 * M * N * taps * (k1 + k2), taps, e0, e1))
+        GEMM_PROFILE.append((2.0 * M * N * taps * (k1 + k2), taps, e0, e1, (M, N, taps * (k1 + k2), act, res1 is not None)))
         return out
     _lib.check(lib.mrisr_gemm(C.byref(g), _stream(a1)), "mrisr_gemm")
     return out
