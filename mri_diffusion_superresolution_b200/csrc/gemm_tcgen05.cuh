@@ -57,7 +57,7 @@ struct GemmCfg {
   static constexpr int kStages = (BN == 256) ? 4 : (BN >= 160) ? 5 : (BN == 128) ? 6 : 8;
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kBiasBytes = 2 * BN * 4;  // epilogue-staged bias, one slab per accumulator stage
+  static constexpr int kBiasBytes = 8 * BN * 4;  // epilogue-staged bias, one slab per epilogue warp
   static constexpr int kEpiBytes = 8 * 2048;     // per-epilogue-warp 32x32 bf16 transpose buffer (coalesced stores)
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kBiasBytes + kEpiBytes + 1024;  // +1024: manual alignment slack
 };
@@ -124,12 +124,17 @@ __device__ __forceinline__ void add_smem32(float (&f)[32], const float* s) {
   }
 }
 
-// Stage this tile's bias slab (BN floats; zeros when there is no bias) in shared memory.  Called by all 256 epilogue
-// threads BEFORE they wait for the accumulator, so the global loads overlap the tile's MMAs.
+// Stage this tile's bias slab (BN floats; zeros when there is no bias) in a PER-WARP shared-memory slot.  Called by every
+// epilogue warp BEFORE it waits for the accumulator, so the global loads overlap the tile's MMAs; only a __syncwarp is
+// needed (a CTA-wide named barrier here made the 8 epilogue warps run in lock-step).
 template <int BN>
-__device__ __forceinline__ void gemm_stage_bias(const GemmKernelParams& p, float* sbias, int n_blk, int et) {
-  if (et < BN) sbias[et] = p.bias != nullptr ? __ldg(p.bias + n_blk * BN + et) : 0.f;
-  asm volatile("bar.sync 1, 256;" ::: "memory");  // epilogue warps only (named barrier 1)
+__device__ __forceinline__ void gemm_stage_bias(const GemmKernelParams& p, float* sbias_warp, int n_blk, int lane) {
+#pragma unroll
+  for (int i = 0; i < (BN + 31) / 32; ++i) {
+    const int c = lane + 32 * i;
+    if (c < BN) sbias_warp[c] = p.bias != nullptr ? __ldg(p.bias + n_blk * BN + c) : 0.f;
+  }
+  __syncwarp();
 }
 
 template <int BN>
@@ -387,8 +392,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
       const int n_blk = tile % p.n_tiles;
       const int m = (tile / p.n_tiles) * kBlockM + q * 32 + lane;
-      float* sbias = sbias_base + as * BN;
-      gemm_stage_bias<BN>(p, sbias, n_blk, static_cast<int>(threadIdx.x) - 128);
+      float* sbias = sbias_base + (warp - 4) * BN;
+      __syncwarp();  // every lane finished reading the previous tile's slab
+      gemm_stage_bias<BN>(p, sbias, n_blk, lane);
       mbar_wait(tfull_bar(as), aph);
       tcgen05_fence_after();
       gemm_epilogue_rows<BN>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN, m, n_blk, (warp - 4) >> 2, sbias, sepi_base + (warp - 4) * 2048);
@@ -420,7 +426,7 @@ struct GemmPairCfg {
   static constexpr int kStages = (BN == 256) ? 6 : 7;
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kBiasBytes = 2 * BN * 4;
+  static constexpr int kBiasBytes = 8 * BN * 4;
   static constexpr int kEpiBytes = 8 * 2048;
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kBiasBytes + kEpiBytes + 1024;
 };
@@ -565,8 +571,9 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
       const int n_blk = tile % p.n_tiles;
       const int m = (tile / p.n_tiles) * (2 * kBlockM) + static_cast<int>(rank) * kBlockM + q * 32 + lane;
-      float* sbias = sbias_base + as * BN;
-      gemm_stage_bias<BN>(p, sbias, n_blk, static_cast<int>(threadIdx.x) - 128);
+      float* sbias = sbias_base + (warp - 4) * BN;
+      __syncwarp();  // every lane finished reading the previous tile's slab
+      gemm_stage_bias<BN>(p, sbias, n_blk, lane);
       mbar_wait(tfull_bar(as), aph);
       tcgen05_fence_after();
       gemm_epilogue_rows<BN>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN, m, n_blk, (warp - 4) >> 2, sbias, sepi_base + (warp - 4) * 2048);
