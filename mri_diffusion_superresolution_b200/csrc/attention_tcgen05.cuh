@@ -94,6 +94,22 @@ __device__ __forceinline__ uint64_t umma_smem_desc_mn(uint32_t saddr, uint32_t l
   d |= static_cast<uint64_t>(kLayoutSW128) << 61;
   return d;
 }
+// 2^x for two values per MUFU op (half the XU-pipe time of two fp32 ex2): inputs rounded to f16 (ulp <= 2^-7 for
+// |x| <= 16), result = packed f16 pair {lo = 2^x0, hi = 2^x1} with subnormals kept, then widened and re-packed to bf16
+// (tcgen05 kind::f16 requires A and B of the same 16-bit type and V is bf16; f16 A with bf16 B faults).
+__device__ __forceinline__ uint32_t ex2_pair_bf16(float x0, float x1) {
+  uint32_t h, r;
+  float lo, hi;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(h));
+  asm("{\n\t.reg .b16 l, u;\n\tmov.b32 {l, u}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, u;\n\t}" : "=f"(lo), "=f"(hi) : "r"(r));
+  return pack_bf16(lo, hi);
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -319,6 +335,283 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_c
         *reinterpret_cast<uint4*>(og + c * 8) =
             make_uint4(pack_bf16(o_acc[c * 8] * inv, o_acc[c * 8 + 1] * inv), pack_bf16(o_acc[c * 8 + 2] * inv, o_acc[c * 8 + 3] * inv),
                        pack_bf16(o_acc[c * 8 + 4] * inv, o_acc[c * 8 + 5] * inv), pack_bf16(o_acc[c * 8 + 6] * inv, o_acc[c * 8 + 7] * inv));
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ======================================================================================================================
+// Split-row variant (d = 40): TWO threads per query row, each owning 64 of the tile's 128 keys and half of the output
+// columns -> 16 softmax warps = 4 per scheduler instead of 2 (the single-thread-per-row kernel is latency-bound:
+// XU pipe 53 %, issue slots 45 % busy).  The two threads of a row exchange their partial row maxima through shared
+// memory (one named barrier per query tile per key tile); the row sum comes from the tensor core (Lt = P * 1 with a
+// constant all-ones B tile), so it is the sum of the ROUNDED probabilities that the P V product actually used.
+constexpr int kAtsThreads = 640;
+
+template <int D>
+struct AttnSplitCfg {
+  static constexpr int kKSteps = (D + 15) / 16;
+  static constexpr int kDO = (D + 15) / 16 * 16;
+  static constexpr int kHalfCols = kDO / 2;                 // output columns folded / stored per thread
+  static_assert(D <= 64 && kHalfCols % 8 == 0, "split-row attention: one 64-column atom, 8-column store granularity");
+  static constexpr int kAtomBytes = 128 * 128;
+  static constexpr int kQBytes = 2 * kAtomBytes;
+  static constexpr int kKVBytes = 2 * kAtomBytes;
+  static constexpr int kStages = 4;
+  static constexpr int kBarBytes = 1024;                    // 16 mbarriers + TMEM slot, padded to the ones tile alignment
+  static constexpr int kOnesBytes = 2048;
+  static constexpr int kMaxBytes = 2 * 2 * 128 * 2 * 4;     // [tile parity][query tile][row][half] partial maxima
+  static constexpr int kSmemBytes = kQBytes + kStages * kKVBytes + kBarBytes + kOnesBytes + kMaxBytes + 1024;
+};
+
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x1(uint32_t taddr, uint32_t& v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+}
+// spin without the printf of mbar_wait (keeps the 24-register control warps free of call overhead); traps on a hang
+__device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kAtsThreads, 1)
+attention_tcgen05_split_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                               const AttnTcArgs a) {
+  using Cfg = AttnSplitCfg<D>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int DO = Cfg::kDO;
+  constexpr int HC = Cfg::kHalfCols;
+  constexpr int BK = 128;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t sQ = smem_base;
+  const uint32_t sKV = smem_base + Cfg::kQBytes;
+  const uint32_t bar_base = sKV + kStages * Cfg::kKVBytes;
+  const uint32_t sOnes = bar_base + Cfg::kBarBytes;
+  float* smax = reinterpret_cast<float*>(smem_al + Cfg::kQBytes + kStages * Cfg::kKVBytes + Cfg::kBarBytes + Cfg::kOnesBytes);
+  auto kv_full = [&](int st) { return bar_base + 8u * st; };
+  auto kv_empty = [&](int st) { return bar_base + 8u * (4 + st); };
+  auto s_full = [&](int g) { return bar_base + 8u * (8 + g); };
+  auto p_full = [&](int g) { return bar_base + 8u * (10 + g); };
+  auto o_full = [&](int g) { return bar_base + 8u * (12 + g); };
+  auto o_free = [&](int g) { return bar_base + 8u * (14 + g); };
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + Cfg::kQBytes + kStages * Cfg::kKVBytes + 128);
+  const uint32_t tmem_slot = bar_base + 128;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kAtcBQ, head = blockIdx.y, b = blockIdx.z;
+  const int ntiles = (a.nk + BK - 1) / BK;
+  const int kv_row0 = b * a.kv_rows_per_batch;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int st = 0; st < kStages; ++st) { mbar_init(kv_full(st), 1); mbar_init(kv_empty(st), 1); }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(s_full(g), 1); mbar_init(o_full(g), 1);
+      mbar_init(p_full(g), 256); mbar_init(o_free(g), 256);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  {  // stage both query tiles (zero-padded, hand-swizzled) and the all-ones tile
+    const __nv_bfloat16* qg = a.q + (static_cast<long long>(b) * a.nq) * a.ldq + head * D;
+    for (int i = threadIdx.x; i < kAtcBQ * 8; i += kAtsThreads) {
+      const int r = i >> 3, c = i & 7;
+      const int g = r >> 7, rr = r & 127;
+      uint4 val = make_uint4(0, 0, 0, 0);
+      if (q0 + r < a.nq && c * 8 < D) val = __ldg(reinterpret_cast<const uint4*>(qg + static_cast<long long>(q0 + r) * a.ldq + c * 8));
+      *reinterpret_cast<uint4*>(smem_al + g * Cfg::kAtomBytes + rr * 128 + ((c ^ (rr & 7)) << 4)) = val;
+    }
+    for (int i = threadIdx.x; i < Cfg::kOnesBytes / 16; i += kAtsThreads)
+      *reinterpret_cast<uint4*>(smem_al + Cfg::kQBytes + kStages * Cfg::kKVBytes + Cfg::kBarBytes + i * 16) =
+          make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async_smem();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  // TMEM columns of query tile g (base g*256): S [0,128), P [128,192), Ot [192, 192+DO), Lt [192+DO, +16).
+  // P does NOT alias S: the next tile's Q K^T is issued before this tile's P V, so a query tile's softmax threads get
+  // their next S ~400 cycles after they publish P instead of ~800.
+  static_assert(192 + DO + 16 <= 256, "TMEM budget");
+
+  if (warp == 0) {
+    reg_dealloc<24>();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < ntiles; ++j) {
+      mbar_wait_lean(kv_empty(stage), phase ^ 1u);
+      if (elect_one()) {
+        const uint32_t sk = sKV + stage * Cfg::kKVBytes;
+        mbar_expect_tx(kv_full(stage), Cfg::kKVBytes);
+        tma_load_2d(sk, &tmK, kv_full(stage), head * D, kv_row0 + j * BK);
+        tma_load_2d(sk + Cfg::kAtomBytes, &tmV, kv_full(stage), head * D, kv_row0 + j * BK);
+      }
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp == 1) {
+    reg_dealloc<24>();
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, BK);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, DO) | (1u << 16);
+    constexpr uint32_t idesc_l = umma_idesc_bf16(128, 16);
+    auto issue_s = [&](int g, int stage) {
+      const uint32_t sk = sKV + stage * Cfg::kKVBytes;
+#pragma unroll
+      for (int k = 0; k < Cfg::kKSteps; ++k)
+        umma_bf16(tmem_base + g * 256, umma_smem_desc(sQ + g * Cfg::kAtomBytes + k * 32, 1024, kLayoutSW128),
+                  umma_smem_desc(sk + k * 32, 1024, kLayoutSW128), idesc_s, k > 0 ? 1u : 0u);
+      umma_commit(s_full(g));
+    };
+    int stage = 0;
+    uint32_t phase = 0;
+    mbar_wait_lean(kv_full(0), 0);
+    tcgen05_fence_after();
+    if (elect_one()) { issue_s(0, 0); issue_s(1, 0); }
+    __syncwarp();
+    for (int j = 0; j < ntiles; ++j) {
+      const int nstage = (stage + 1 == kStages) ? 0 : stage + 1;
+      const uint32_t nphase = (stage + 1 == kStages) ? phase ^ 1u : phase;
+      for (int g = 0; g < 2; ++g) {
+        mbar_wait_lean(p_full(g), j & 1);                  // softmax read S_g(j) completely and wrote P_g(j)
+        if (j + 1 < ntiles) {
+          if (g == 0) mbar_wait_lean(kv_full(nstage), nphase);
+          tcgen05_fence_after();
+          if (elect_one()) issue_s(g, nstage);             // S_g(j+1) first: it is what the softmax threads wait for
+          __syncwarp();
+        }
+        if (j > 0) mbar_wait_lean(o_free(g), (j - 1) & 1);  // Ot_g(j-1) folded
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t sv = sKV + stage * Cfg::kKVBytes + Cfg::kAtomBytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16_ts(tmem_base + g * 256 + 192, tmem_base + g * 256 + 128 + k * 8,
+                         umma_smem_desc_mn(sv + k * 2048, Cfg::kAtomBytes, 1024), idesc_o, k > 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16_ts(tmem_base + g * 256 + 192 + DO, tmem_base + g * 256 + 128 + k * 8,
+                         umma_smem_desc(sOnes, 1024, kLayoutSW128), idesc_l, k > 0 ? 1u : 0u);
+          umma_commit(o_full(g));
+          if (g == 1) umma_commit(kv_empty(stage));
+        }
+        __syncwarp();
+      }
+      stage = nstage; phase = nphase;
+    }
+  } else if (warp < 4) {
+    reg_dealloc<24>();
+  } else {
+    reg_alloc<112>();  // pool = 640 * 96; 128 * 24 + 512 * 112 fits exactly
+    const int i16 = warp - 4;
+    const int g = i16 >> 3, half = (i16 >> 2) & 1, qrt = warp & 3;
+    const int rloc = qrt * 32 + lane;                 // row within the query tile
+    const int row = q0 + g * 128 + rloc;
+    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(qrt * 32) << 16) + g * 256;
+    const uint32_t t_p = t_s + 128;
+    const uint32_t t_o = t_s + 192;
+    float o_acc[HC];
+#pragma unroll
+    for (int i = 0; i < HC; ++i) o_acc[i] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    const float sc = a.scale_log2;
+    auto add_ot = [&]() {
+      uint32_t lt;
+      tmem_ld_32x1(t_o + DO, lt);
+#pragma unroll
+      for (int c = 0; c < HC / 8; ++c) {
+        uint32_t t[8];
+        tmem_ld_32x8(t_o + half * HC + c * 8, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o_acc[c * 8 + i] += __uint_as_float(t[i]);
+      }
+      l += __uint_as_float(lt);
+    };
+    for (int j = 0; j < ntiles; ++j) {
+      mbar_wait_lean(s_full(g), j & 1);
+      tcgen05_fence_after();
+      uint32_t s[64];
+      tmem_ld_32x32(t_s + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+      tmem_ld_32x32(t_s + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+      tmem_ld_wait();
+      const int kbase = j * BK + half * 64;
+      if (kbase + 64 > a.nk) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (kbase + i >= a.nk) s[i] = 0xff800000u;
+      }
+      // row max with the 3-input max instruction, 4 independent chains (half the issue slots of 2-input FMNMX)
+      float mx4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mx4[i] = max3(__uint_as_float(s[i]), __uint_as_float(s[4 + i]), __uint_as_float(s[8 + i]));
+#pragma unroll
+      for (int i = 12; i + 8 <= 64; i += 8) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) mx4[c] = max3(mx4[c], __uint_as_float(s[i + c]), __uint_as_float(s[i + 4 + c]));
+      }
+      float raw = max3(max3(mx4[0], mx4[1], mx4[2]), mx4[3], fmaxf(fmaxf(__uint_as_float(s[60]), __uint_as_float(s[61])), fmaxf(__uint_as_float(s[62]), __uint_as_float(s[63]))));
+      // exchange the partial maximum with the thread that owns the other 64 keys of this row; the barrier also
+      // guarantees that BOTH threads finished reading S before either overwrites it with P
+      float* mslot = smax + (((j & 1) * 2 + g) * 128 + rloc) * 2;
+      mslot[half] = raw;
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
+      raw = fmaxf(raw, mslot[half ^ 1]);
+      const float mx = fmaxf(m, raw * sc);
+      const float alpha = ex2_approx(m - mx);
+      uint32_t pk[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        pk[i] = pack_bf16(ex2_approx(fmaf(__uint_as_float(s[2 * i]), sc, -mx)), ex2_approx(fmaf(__uint_as_float(s[2 * i + 1]), sc, -mx)));
+      if (j > 0) {  // P V of the previous tile: done long ago; fold it (o_acc is still held against the previous max),
+                    // which also proves that the tensor core finished reading the previous P before it is overwritten
+        mbar_wait_lean(o_full(g), (j - 1) & 1);
+        tcgen05_fence_after();
+        add_ot();
+        tcgen05_fence_before();
+        mbar_arrive(o_free(g));
+      }
+      tmem_st_32x32(t_p + half * 32, pk);
+      tmem_st_wait();
+      tcgen05_fence_before();
+      mbar_arrive(p_full(g));
+      l *= alpha;
+#pragma unroll
+      for (int i = 0; i < HC; ++i) o_acc[i] *= alpha;
+      m = mx;
+    }
+    mbar_wait_lean(o_full(g), (ntiles - 1) & 1);
+    tcgen05_fence_after();
+    add_ot();
+    if (row < a.nq) {
+      const float inv = 1.f / l;
+      __nv_bfloat16* og = a.o + (static_cast<long long>(b) * a.nq + row) * a.ldo + head * D + half * HC;
+#pragma unroll
+      for (int c = 0; c < HC / 8; ++c) {
+        if (half * HC + c * 8 < D)
+          *reinterpret_cast<uint4*>(og + c * 8) =
+              make_uint4(pack_bf16(o_acc[c * 8] * inv, o_acc[c * 8 + 1] * inv), pack_bf16(o_acc[c * 8 + 2] * inv, o_acc[c * 8 + 3] * inv),
+                         pack_bf16(o_acc[c * 8 + 4] * inv, o_acc[c * 8 + 5] * inv), pack_bf16(o_acc[c * 8 + 6] * inv, o_acc[c * 8 + 7] * inv));
       }
     }
   }

@@ -189,6 +189,22 @@ int launch_attention_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, 
   a.kv_rows_per_batch = kv_broadcast ? 0 : nk;
   a.scale_log2 = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(D)));
   dim3 grid((nq + mrisr::kAtcBQ - 1) / mrisr::kAtcBQ, heads, batch);
+  if constexpr (D == 40) {
+    // two threads per query row (16 softmax warps): see attention_tcgen05_split_kernel
+    static const bool split = !(getenv("MRISR_ATTN_NOSPLIT") != nullptr && getenv("MRISR_ATTN_NOSPLIT")[0] == '1');
+    if (split) {
+      using SCfg = mrisr::AttnSplitCfg<D>;
+      static bool configured2 = false;
+      if (!configured2) {
+        MRISR_CHECK_CUDA(cudaFuncSetAttribute(mrisr::attention_tcgen05_split_kernel<D>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, SCfg::kSmemBytes));
+        configured2 = true;
+      }
+      mrisr::attention_tcgen05_split_kernel<D><<<grid, mrisr::kAtsThreads, SCfg::kSmemBytes, st>>>(mk, mv, a);
+      MRISR_CHECK_CUDA(cudaGetLastError());
+      return 0;
+    }
+  }
   mrisr::attention_tcgen05_kernel<D><<<grid, mrisr::kAtcThreads, Cfg::kSmemBytes, st>>>(mk, mv, a);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
