@@ -63,18 +63,17 @@ struct GemmCfg {
 };
 
 __device__ __forceinline__ float act_silu(float x) { return x / (1.f + __expf(-x)); }
-// Exact-erf GELU (diffusers GEGLU, F.gelu default) with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far
-// below the bf16 output rounding): 2 MUFU + ~12 FMA-class instructions instead of libdevice erff's branchy ~40.
+// Exact-erf GELU (diffusers GEGLU, F.gelu default): erf(z) = tanh(z (c1 + c2 z^2 + c3 z^4)) fitted on [0, 5]
+// (max |erf error| 4.1e-5 -> |gelu error| <= 5e-5, 80x below the bf16 rounding of the output), evaluated with ONE
+// MUFU.TANH + 6 FMA-class instructions; libdevice erff costs ~40 branchy instructions, the A&S form 2 MUFU + 12.
 __device__ __forceinline__ float act_gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
+  const float z = x * 0.70710678118654752f;
+  const float z2 = z * z;
+  const float poly = fmaf(z2, fmaf(z2, -0.0018136252868498051f, 0.10414107035307328f), 1.1281242310939545f);
   float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float e = 1.f - poly * t * __expf(-z * z);  // erf(|x|/sqrt2)
-  return 0.5f * x * (1.f + copysignf(e, x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(z * poly));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
 
 // Epilogue of one accumulator tile for ONE output row per thread: thread (lane quarter q, lane) owns TMEM lane
@@ -147,7 +146,7 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmKernelParams& p, ui
   const int nchunks = out_cols / 32;
   const int c_begin = half == 0 ? 0 : (nchunks + 1) / 2;
   const int c_end = half == 0 ? (nchunks + 1) / 2 : nchunks;
-  if (c_begin >= c_end) return;
+  if (c_begin >= c_end || (p.dbg & 16)) return;
   const int n_w0 = n_blk * BN;        // first weight row of this tile
   const int n_o0 = n_blk * out_cols;  // first output column of this tile
   const float* rv = nullptr;
@@ -156,6 +155,10 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmKernelParams& p, ui
   const __nv_bfloat16* r2p = (p.res2 != nullptr && row_ok) ? p.res2 + static_cast<long long>(m) * p.ldr2 + n_o0 : nullptr;
   uint32_t v[32], g[32];
   uint4 rn1[4], rn2[4];  // residuals of the NEXT chunk (prefetched one chunk ahead, like the TMEM loads)
+  if (p.dbg & 8) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = 0;
+  } else
   tmem_ld_32x32(t_row + c_begin * 32, v);
   if (geglu) tmem_ld_32x32(t_row + out_cols + c_begin * 32, g);
   const bool full0 = n_o0 + c_begin * 32 + 32 <= p.n_store;
@@ -181,7 +184,7 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmKernelParams& p, ui
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-      if (next) tmem_ld_32x32(t_row + (c + 1) * 32, v);
+      if (next && !(p.dbg & 8)) tmem_ld_32x32(t_row + (c + 1) * 32, v);
       add_smem32(f, sbias + c * 32);
       if (rv != nullptr) add_vec32(f, rv + n_w0 + c * 32);
       if (p.act == ACT_RELU) {
@@ -228,7 +231,7 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmKernelParams& p, ui
         }
       }
     }
-    if (chunk_full && !p.out_fp32) {
+    if (chunk_full && !p.out_fp32 && !(p.dbg & 4)) {
       // bf16 store, coalesced: the warp's 32 rows x 64 B go through a swizzled shared-memory transpose so that every
       // store instruction writes 8 rows x 64 contiguous bytes (full 32 B sectors) instead of 32 rows x 16 B.
       {
