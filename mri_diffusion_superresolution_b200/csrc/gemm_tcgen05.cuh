@@ -136,6 +136,87 @@ __device__ __forceinline__ void gemm_stage_bias(const GemmKernelParams& p, float
   __syncwarp();
 }
 
+// Fast epilogue for the common case (bf16 output, every chunk inside n_store, no GEGLU): ALL of this warp's TMEM loads
+// are issued up front and waited for once, values are processed in place (no per-chunk tcgen05.wait / register copy),
+// and the per-row global pointers of the transposed store are computed once per tile.
+template <int BN>
+__device__ __forceinline__ void gemm_epilogue_fast(const GemmKernelParams& p, uint32_t t_row, int m, int n_blk, int half,
+                                                   const float* sbias, uint8_t* stage_buf) {
+  constexpr int kChunks = BN / 32;
+  constexpr int kMaxC = (kChunks + 1) / 2;
+  const int lane_id = threadIdx.x & 31;
+  const int c_begin = half == 0 ? 0 : kMaxC;
+  const int nc = half == 0 ? kMaxC : kChunks - kMaxC;
+  if (nc <= 0) return;
+  const bool row_ok = m < p.M;
+  const int n_w0 = n_blk * BN;
+  uint32_t v[kMaxC][32];
+#pragma unroll
+  for (int ci = 0; ci < kMaxC; ++ci)
+    if (ci < nc) tmem_ld_32x32(t_row + (c_begin + ci) * 32, v[ci]);
+  const float* rv = nullptr;
+  if (p.rowvec != nullptr && row_ok) rv = p.rowvec + static_cast<long long>(m / p.rows_per_batch) * p.rowvec_stride + n_w0;
+  const __nv_bfloat16* r1p = (p.res1 != nullptr && row_ok) ? p.res1 + static_cast<long long>(m) * p.ldr1 + n_w0 : nullptr;
+  const __nv_bfloat16* r2p = (p.res2 != nullptr && row_ok) ? p.res2 + static_cast<long long>(m) * p.ldr2 + n_w0 : nullptr;
+  uint4 rn1[4];
+  if (r1p != nullptr) ld_res32(rn1, r1p + c_begin * 32);
+  // transposed-store geometry: lane handles row (lane >> 2) + 8 i, 16-byte chunk (lane & 3)
+  const int m_base = m - lane_id;
+  __nv_bfloat16* orow[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = (lane_id >> 2) + 8 * i;
+    orow[i] = (m_base + r < p.M) ? static_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(m_base + r) * p.ldo + n_w0 + (lane_id & 3) * 8
+                                 : nullptr;
+  }
+  const int sw = (lane_id >> 1) & 3;
+  uint8_t* st_dst = stage_buf + lane_id * 64;
+  const uint8_t* ld_src[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = (lane_id >> 2) + 8 * i;
+    ld_src[i] = stage_buf + r * 64 + (((lane_id & 3) ^ ((r >> 1) & 3)) << 4);
+  }
+  tmem_ld_wait();
+#pragma unroll
+  for (int ci = 0; ci < kMaxC; ++ci) {
+    if (ci < nc) {
+      const int c = c_begin + ci;
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[ci][j]);
+      add_smem32(f, sbias + c * 32);
+      if (rv != nullptr) add_vec32(f, rv + c * 32);
+      if (p.act == ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+      } else if (p.act == ACT_SILU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = act_silu(f[j]);
+      }
+      if (r1p != nullptr) {
+        add_res32r(f, rn1);
+        if (ci + 1 < nc) ld_res32(rn1, r1p + (c + 1) * 32);
+      }
+      if (r2p != nullptr) add_res32(f, r2p + c * 32);
+      if (!(p.dbg & 4)) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          *reinterpret_cast<uint4*>(st_dst + ((u ^ sw) << 4)) =
+              make_uint4(pack_bf16(f[8 * u], f[8 * u + 1]), pack_bf16(f[8 * u + 2], f[8 * u + 3]),
+                         pack_bf16(f[8 * u + 4], f[8 * u + 5]), pack_bf16(f[8 * u + 6], f[8 * u + 7]));
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 val = *reinterpret_cast<const uint4*>(ld_src[i]);
+          if (orow[i] != nullptr) *reinterpret_cast<uint4*>(orow[i] + c * 32) = val;
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
 template <int BN>
 __device__ __forceinline__ void gemm_epilogue_rows(const GemmKernelParams& p, uint32_t t_row, int m, int n_blk, int half,
                                                    const float* sbias, uint8_t* stage_buf) {
@@ -400,7 +481,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
       gemm_stage_bias<BN>(p, sbias, n_blk, lane);
       mbar_wait(tfull_bar(as), aph);
       tcgen05_fence_after();
-      gemm_epilogue_rows<BN>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN, m, n_blk, (warp - 4) >> 2, sbias, sepi_base + (warp - 4) * 2048);
+      if (BN <= 192 && !p.out_fp32 && p.act != ACT_GEGLU && (n_blk + 1) * BN <= p.n_store && !(p.dbg & 24))
+        gemm_epilogue_fast<(BN <= 192 ? BN : 64)>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN, m, n_blk, (warp - 4) >> 2, sbias, sepi_base + (warp - 4) * 2048);
+      else
+        gemm_epilogue_rows<BN>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN, m, n_blk, (warp - 4) >> 2, sbias, sepi_base + (warp - 4) * 2048);
       tcgen05_fence_before();
       mbar_arrive(tempty_bar(as));
     }
@@ -579,7 +663,10 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
       gemm_stage_bias<BN>(p, sbias, n_blk, lane);
       mbar_wait(tfull_bar(as), aph);
       tcgen05_fence_after();
-      gemm_epilogue_rows<BN>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN, m, n_blk, (warp - 4) >> 2, sbias, sepi_base + (warp - 4) * 2048);
+      if (BN <= 192 && !p.out_fp32 && p.act != ACT_GEGLU && (n_blk + 1) * BN <= p.n_store && !(p.dbg & 24))
+        gemm_epilogue_fast<(BN <= 192 ? BN : 64)>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN, m, n_blk, (warp - 4) >> 2, sbias, sepi_base + (warp - 4) * 2048);
+      else
+        gemm_epilogue_rows<BN>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN, m, n_blk, (warp - 4) >> 2, sbias, sepi_base + (warp - 4) * 2048);
       tcgen05_fence_before();
       mbar_arrive_leader(tempty_bar(as));
     }
