@@ -10,9 +10,12 @@
 //   LoRA rank extension) is consumed as two K ranges without materialising the concatenation.
 // * W tiles (BN rows x 64 k) arrive by TMA from a [N, taps*(k1+k2)] K-major matrix.
 // * One elected thread issues tcgen05.mma (M=128, N=BN, K=16) into one of two TMEM accumulator stages;
-//   four epilogue warps drain the other stage concurrently (tcgen05.ld 32x32b), apply
-//   bias / per-batch row vector (time embedding) / ReLU / SiLU / GEGLU / up to two residual tensors, and
-//   store bf16 (or fp32) rows straight to global memory, 64 contiguous bytes per thread per chunk.
+//   eight epilogue warps drain the other stage concurrently (tcgen05.ld 32x32b), apply
+//   bias / per-batch row vector (time embedding) / ReLU / SiLU / GEGLU, and hand 32x32 bf16 chunks to the TMA
+//   store unit through a 64B-swizzled per-warp staging buffer (fp32 / ragged outputs take a plain-store path).
+// * Residual tensors of activation-free GEMMs never touch the epilogue: R[M, N] is consumed as one more A operand
+//   against a 0/1 identity weight tile (BN/64 extra k-chunks per tile), i.e. it rides the same deep TMA pipeline as
+//   the operands and is added exactly (bf16 x 1.0) in the fp32 accumulator.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -22,6 +25,13 @@ namespace mrisr {
 
 enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2, ACT_GEGLU = 3 };
 
+struct GemmMaps {
+  CUtensorMap a1, a2, b;  // operands
+  CUtensorMap r1, r2;     // residuals as [M, N] A operands (res_mma > 0)
+  CUtensorMap ident;      // 256 x 256 identity weight tile
+  CUtensorMap out;        // bf16 output, 32 x 32 boxes, 64B swizzle (tma_store)
+};
+
 struct GemmKernelParams {
   int M, N, n_store;
   int kc1, kc2;  // 64-wide K chunks per tap taken from A1 / A2
@@ -29,6 +39,8 @@ struct GemmKernelParams {
   int conv;      // 0: A is [M, k]; 1: A is NHWC [B, H, W, k]
   int H, W;
   int m_tiles, n_tiles;
+  int res_mma;    // residual operands folded into the MMA K loop (0, 1 or 2)
+  int tma_store;  // bf16 output written by TMA from the swizzled staging buffers
   const float* bias;
   const float* rowvec;
   long long rowvec_stride;
@@ -49,17 +61,25 @@ constexpr int kBlockK = 64;
 constexpr int kGemmThreads = 384;  // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: epilogue (2 per TMEM lane quarter)
 constexpr int kEpilogueThreads = 256;
 
-template <int BN>
+// kPair: a cluster of two CTAs on one TPC computes a 256 x BN tile with cta_group::2 MMAs; each CTA stages its own 128
+// rows of A and HALF of the W tile, so every SM pulls 16 KB + BN*64 B per k-chunk from L2 instead of 16 KB + BN*128 B
+// (the round-1 profile showed the single-CTA kernel bound by L2->SM operand delivery).
+template <int BN, bool kPair>
 struct GemmCfg {
+  static constexpr int kTileM = kPair ? 2 * kBlockM : kBlockM;
+  static constexpr int kBRows = kPair ? BN / 2 : BN;
   static constexpr int kABytes = kBlockM * kBlockK * 2;
-  static constexpr int kBBytes = BN * kBlockK * 2;
+  static constexpr int kBBytes = kBRows * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN >= 160) ? 5 : (BN == 128) ? 6 : 8;
-  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
+  static constexpr int kEpiBytes = 8 * 4096;     // per-epilogue-warp: two 32x32 bf16 staging buffers (TMA store double buffer)
   static constexpr int kBiasBytes = 8 * BN * 4;  // epilogue-staged bias, one slab per epilogue warp
-  static constexpr int kEpiBytes = 8 * 2048;     // per-epilogue-warp 32x32 bf16 transpose buffer (coalesced stores)
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kBiasBytes + kEpiBytes + 1024;  // +1024: manual alignment slack
+  static constexpr int kBarBytes = 256;          // <= 2*8+4 mbarriers + the TMEM base slot
+  static constexpr int kFixedBytes = kEpiBytes + kBiasBytes + kBarBytes + 1024;  // +1024: manual alignment slack
+  static constexpr int kFit = (232448 - kFixedBytes) / kStageBytes;
+  static constexpr int kStages = kFit > 8 ? 8 : kFit;
+  static_assert(kStages >= 3, "shared-memory budget");
+  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kFixedBytes;
 };
 
 __device__ __forceinline__ float act_silu(float x) { return x / (1.f + __expf(-x)); }
@@ -136,48 +156,41 @@ __device__ __forceinline__ void gemm_stage_bias(const GemmKernelParams& p, float
   __syncwarp();
 }
 
-// Fast epilogue for the common case (bf16 output, every chunk inside n_store, no GEGLU): ALL of this warp's TMEM loads
-// are issued up front and waited for once, values are processed in place (no per-chunk tcgen05.wait / register copy),
-// and the per-row global pointers of the transposed store are computed once per tile.
-template <int BN>
-__device__ __forceinline__ void gemm_epilogue_fast(const GemmKernelParams& p, uint32_t t_row, int m, int n_blk, int half,
-                                                   const float* sbias, uint8_t* stage_buf) {
-  constexpr int kChunks = BN / 32;
+// TMA-store epilogue (bf16 output, every chunk of the tile inside n_store, no residual left for the epilogue).
+// Thread (lane quarter q, lane) owns TMEM lane q*32+lane == output row m; two warps share a lane quarter and split the
+// 32-column chunks.  ALL of the warp's TMEM loads are issued up front and waited for once, then `release()` hands the
+// accumulator stage back to the MMA warp BEFORE any arithmetic or store.  Each chunk is packed to bf16, written to one of
+// the warp's two 2 KB staging buffers in the TMA 64B-swizzle pattern (16-byte slot ^= (row >> 1) & 3: conflict-free
+// 128-bit writes) and stored by ONE cp.async.bulk.tensor issued by lane 0 -- ~4x fewer instructions per chunk than
+// transposing through shared memory and storing with per-row pointers, and rows >= M are clipped by the TMA unit.
+template <int BN, bool kGeglu, typename Release>
+__device__ __forceinline__ void gemm_epilogue_tma(const GemmKernelParams& p, const CUtensorMap* tm_out, uint32_t t_row, int m,
+                                                  int n_blk, int half, const float* sbias, uint8_t* stage_buf,
+                                                  uint32_t& buf_sel, Release release) {
+  constexpr int kOutCols = kGeglu ? BN / 2 : BN;
+  constexpr int kChunks = kOutCols / 32;
   constexpr int kMaxC = (kChunks + 1) / 2;
   const int lane_id = threadIdx.x & 31;
   const int c_begin = half == 0 ? 0 : kMaxC;
   const int nc = half == 0 ? kMaxC : kChunks - kMaxC;
-  if (nc <= 0) return;
-  const bool row_ok = m < p.M;
-  const int n_w0 = n_blk * BN;
   uint32_t v[kMaxC][32];
+  uint32_t g[kGeglu ? kMaxC : 1][32];
 #pragma unroll
-  for (int ci = 0; ci < kMaxC; ++ci)
-    if (ci < nc) tmem_ld_32x32(t_row + (c_begin + ci) * 32, v[ci]);
+  for (int ci = 0; ci < kMaxC; ++ci) {
+    if (ci < nc) {
+      tmem_ld_32x32(t_row + (c_begin + ci) * 32, v[ci]);
+      if (kGeglu) tmem_ld_32x32(t_row + kOutCols + (c_begin + ci) * 32, g[ci]);
+    }
+  }
+  const bool row_ok = m < p.M;
   const float* rv = nullptr;
-  if (p.rowvec != nullptr && row_ok) rv = p.rowvec + static_cast<long long>(m / p.rows_per_batch) * p.rowvec_stride + n_w0;
-  const __nv_bfloat16* r1p = (p.res1 != nullptr && row_ok) ? p.res1 + static_cast<long long>(m) * p.ldr1 + n_w0 : nullptr;
-  const __nv_bfloat16* r2p = (p.res2 != nullptr && row_ok) ? p.res2 + static_cast<long long>(m) * p.ldr2 + n_w0 : nullptr;
-  uint4 rn1[4];
-  if (r1p != nullptr) ld_res32(rn1, r1p + c_begin * 32);
-  // transposed-store geometry: lane handles row (lane >> 2) + 8 i, 16-byte chunk (lane & 3)
-  const int m_base = m - lane_id;
-  __nv_bfloat16* orow[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = (lane_id >> 2) + 8 * i;
-    orow[i] = (m_base + r < p.M) ? static_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(m_base + r) * p.ldo + n_w0 + (lane_id & 3) * 8
-                                 : nullptr;
-  }
+  if (!kGeglu && p.rowvec != nullptr && row_ok)
+    rv = p.rowvec + static_cast<long long>(m / p.rows_per_batch) * p.rowvec_stride + n_blk * BN;
+  const int m_warp0 = m - lane_id;
+  const int n_o0 = n_blk * kOutCols;
   const int sw = (lane_id >> 1) & 3;
-  uint8_t* st_dst = stage_buf + lane_id * 64;
-  const uint8_t* ld_src[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = (lane_id >> 2) + 8 * i;
-    ld_src[i] = stage_buf + r * 64 + (((lane_id & 3) ^ ((r >> 1) & 3)) << 4);
-  }
   tmem_ld_wait();
+  release();
 #pragma unroll
   for (int ci = 0; ci < kMaxC; ++ci) {
     if (ci < nc) {
@@ -186,37 +199,48 @@ __device__ __forceinline__ void gemm_epilogue_fast(const GemmKernelParams& p, ui
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[ci][j]);
       add_smem32(f, sbias + c * 32);
-      if (rv != nullptr) add_vec32(f, rv + c * 32);
-      if (p.act == ACT_RELU) {
+      if (kGeglu) {
+        float gg[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-      } else if (p.act == ACT_SILU) {
+        for (int j = 0; j < 32; ++j) gg[j] = __uint_as_float(g[ci][j]);
+        add_smem32(gg, sbias + kOutCols + c * 32);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = act_silu(f[j]);
+        for (int j = 0; j < 32; ++j) f[j] *= act_gelu_erf(gg[j]);
+      } else {
+        if (rv != nullptr) add_vec32(f, rv + c * 32);
+        if (p.act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        } else if (p.act == ACT_SILU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = act_silu(f[j]);
+        }
       }
-      if (r1p != nullptr) {
-        add_res32r(f, rn1);
-        if (ci + 1 < nc) ld_res32(rn1, r1p + (c + 1) * 32);
-      }
-      if (r2p != nullptr) add_res32(f, r2p + c * 32);
       if (!(p.dbg & 4)) {
+        uint8_t* buf = stage_buf + (buf_sel & 1u) * 2048;
+        buf_sel ^= 1u;
+        if (lane_id == 0) bulk_wait_group_read<1>();  // the store that last read THIS buffer has drained it
+        __syncwarp();
+        uint8_t* dst = buf + lane_id * 64;
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-          *reinterpret_cast<uint4*>(st_dst + ((u ^ sw) << 4)) =
+          *reinterpret_cast<uint4*>(dst + ((u ^ sw) << 4)) =
               make_uint4(pack_bf16(f[8 * u], f[8 * u + 1]), pack_bf16(f[8 * u + 2], f[8 * u + 3]),
                          pack_bf16(f[8 * u + 4], f[8 * u + 5]), pack_bf16(f[8 * u + 6], f[8 * u + 7]));
+        fence_proxy_async_smem();
         __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint4 val = *reinterpret_cast<const uint4*>(ld_src[i]);
-          if (orow[i] != nullptr) *reinterpret_cast<uint4*>(orow[i] + c * 32) = val;
+        if (lane_id == 0 && m_warp0 < p.M) {
+          tma_store_2d(tm_out, smem_u32(buf), n_o0 + c * 32, m_warp0);
+          bulk_commit_group();
         }
-        __syncwarp();
       }
     }
   }
 }
 
+// Generic epilogue: fp32 output, ragged n_store (e.g. conv_out, 4 real columns), residuals combined with an activation.
+// One output row per thread, TMEM loads and residual loads software-pipelined one chunk ahead, bf16 rows stored through
+// a swizzled shared-memory transpose (8 rows x 64 contiguous bytes per store instruction).
 template <int BN>
 __device__ __forceinline__ void gemm_epilogue_rows(const GemmKernelParams& p, uint32_t t_row, int m, int n_blk, int half,
                                                    const float* sbias, uint8_t* stage_buf) {
@@ -235,20 +259,11 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmKernelParams& p, ui
   const __nv_bfloat16* r1p = (p.res1 != nullptr && row_ok) ? p.res1 + static_cast<long long>(m) * p.ldr1 + n_o0 : nullptr;
   const __nv_bfloat16* r2p = (p.res2 != nullptr && row_ok) ? p.res2 + static_cast<long long>(m) * p.ldr2 + n_o0 : nullptr;
   uint32_t v[32], g[32];
-  uint4 rn1[4], rn2[4];  // residuals of the NEXT chunk (prefetched one chunk ahead, like the TMEM loads)
-  if (p.dbg & 8) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = 0;
-  } else
   tmem_ld_32x32(t_row + c_begin * 32, v);
   if (geglu) tmem_ld_32x32(t_row + out_cols + c_begin * 32, g);
-  const bool full0 = n_o0 + c_begin * 32 + 32 <= p.n_store;
-  if (r1p != nullptr && full0) ld_res32(rn1, r1p + c_begin * 32);
-  if (r2p != nullptr && full0) ld_res32(rn2, r2p + c_begin * 32);
   for (int c = c_begin; c < c_end; ++c) {
     float f[32];
     const bool next = c + 1 < c_end;
-    const bool fulln = next && (n_o0 + (c + 1) * 32 + 32 <= p.n_store);
     tmem_ld_wait();
     if (geglu) {
       float gg[32];
@@ -265,7 +280,7 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmKernelParams& p, ui
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-      if (next && !(p.dbg & 8)) tmem_ld_32x32(t_row + (c + 1) * 32, v);
+      if (next) tmem_ld_32x32(t_row + (c + 1) * 32, v);
       add_smem32(f, sbias + c * 32);
       if (rv != nullptr) add_vec32(f, rv + n_w0 + c * 32);
       if (p.act == ACT_RELU) {
@@ -280,24 +295,15 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmKernelParams& p, ui
     const bool chunk_full = n + 32 <= p.n_store;  // warp-uniform
     if (row_ok && n < p.n_store) {
       if (chunk_full) {
-        if (geglu) {  // (GEGLU + residual is not used by the UNet; keep it correct, unpipelined)
-          if (r1p != nullptr) add_res32(f, r1p + c * 32);
-          if (r2p != nullptr) add_res32(f, r2p + c * 32);
-        } else {
-          if (r1p != nullptr) add_res32r(f, rn1);
-          if (r2p != nullptr) add_res32r(f, rn2);
-          // refill for the next chunk right after use: the loads fly during this chunk's stores and the next
-          // chunk's TMEM wait / bias / activation work
-          if (r1p != nullptr && fulln) ld_res32(rn1, r1p + (c + 1) * 32);
-          if (r2p != nullptr && fulln) ld_res32(rn2, r2p + (c + 1) * 32);
-        }
+        if (r1p != nullptr) add_res32(f, r1p + c * 32);
+        if (r2p != nullptr) add_res32(f, r2p + c * 32);
         if (p.out_fp32) {
           float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<long long>(m) * p.ldo + n);
 #pragma unroll
           for (int u = 0; u < 8; ++u) o[u] = make_float4(f[4 * u], f[4 * u + 1], f[4 * u + 2], f[4 * u + 3]);
         }
       } else {
-        // ragged last chunk (e.g. conv_out, 4 real columns): predicated scalar path (fully unrolled so f[] stays in registers)
+        // ragged last chunk: predicated scalar path (fully unrolled so f[] stays in registers)
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           if (n + j < p.n_store) {
@@ -313,16 +319,12 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmKernelParams& p, ui
       }
     }
     if (chunk_full && !p.out_fp32 && !(p.dbg & 4)) {
-      // bf16 store, coalesced: the warp's 32 rows x 64 B go through a swizzled shared-memory transpose so that every
-      // store instruction writes 8 rows x 64 contiguous bytes (full 32 B sectors) instead of 32 rows x 16 B.
-      {
-        const int sw = (lane_id >> 1) & 3;
+      const int sw = (lane_id >> 1) & 3;
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          *reinterpret_cast<uint4*>(stage_buf + lane_id * 64 + ((u ^ sw) << 4)) =
-              make_uint4(pack_bf16(f[8 * u], f[8 * u + 1]), pack_bf16(f[8 * u + 2], f[8 * u + 3]),
-                         pack_bf16(f[8 * u + 4], f[8 * u + 5]), pack_bf16(f[8 * u + 6], f[8 * u + 7]));
-      }
+      for (int u = 0; u < 4; ++u)
+        *reinterpret_cast<uint4*>(stage_buf + lane_id * 64 + ((u ^ sw) << 4)) =
+            make_uint4(pack_bf16(f[8 * u], f[8 * u + 1]), pack_bf16(f[8 * u + 2], f[8 * u + 3]),
+                       pack_bf16(f[8 * u + 4], f[8 * u + 5]), pack_bf16(f[8 * u + 6], f[8 * u + 7]));
       __syncwarp();
       const int m_base = m - lane_id;  // first row of this warp
 #pragma unroll
@@ -337,293 +339,138 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmKernelParams& p, ui
   }
 }
 
-template <int BN>
+// Persistent kernel: grid = #SMs (pairs: clusters of 2).  Pair protocol: both CTAs' TMA loads complete on the LEADER's
+// full barrier; the leader's commits are multicast to both CTAs' empty / accumulator-full barriers; both CTAs' epilogue
+// warps arrive on the leader's accumulator-empty barrier.
+template <int BN, bool kPair>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-                    const __grid_constant__ CUtensorMap tmB, const GemmKernelParams p) {
-  using Cfg = GemmCfg<BN>;
+gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParams p) {
+  using Cfg = GemmCfg<BN, kPair>;
   constexpr int kStages = Cfg::kStages;
+  constexpr int kTileM = Cfg::kTileM;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint8_t* sepi_base = smem_al + kStages * Cfg::kStageBytes;  // 1024-aligned: the TMA swizzle pattern is address-based
+  float* sbias_base = reinterpret_cast<float*>(sepi_base + Cfg::kEpiBytes);
+  const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes + Cfg::kEpiBytes + Cfg::kBiasBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
-  float* sbias_base = reinterpret_cast<float*>(smem_raw + (bar_base + Cfg::kBarBytes - smem_u32(smem_raw)));
-  uint8_t* sepi_base = reinterpret_cast<uint8_t*>(sbias_base) + Cfg::kBiasBytes;
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA1);
-    tma_prefetch_desc(&tmA2);
-    tma_prefetch_desc(&tmB);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), kEpilogueThreads);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-
-  const int total_tiles = p.m_tiles * p.n_tiles;
-  const int kchunks = p.kc1 + p.kc2;
-  const int kiters = p.taps * kchunks;
-
-  // warps 0-3 (one warpgroup) need few registers; each role branch re-balances so the 8 epilogue warps get 200
-  if (warp == 0) {
-    reg_dealloc<72>();
-    {
-      // ===================== TMA producer =====================
-      // The whole warp walks the loop (warp-uniform control flow keeps descriptors / coordinates in uniform registers:
-      // a single divergent thread makes ptxas wrap every UTMALDG / UTCHMMA in an ELECT + R2UR waterfall loop);
-      // one elected lane issues.
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n0 = (tile % p.n_tiles) * BN;
-        const int m0 = (tile / p.n_tiles) * kBlockM;
-        int b0 = 0, h0 = 0;
-        if (p.conv) {
-          const int hw = p.H * p.W;
-          b0 = m0 / hw;
-          h0 = (m0 - b0 * hw) / p.W;
-        }
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int dr = (p.taps == 9) ? tap / 3 - 1 : 0;
-          const int ds = (p.taps == 9) ? tap % 3 - 1 : 0;
-          for (int kc = 0; kc < kchunks; ++kc) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-            const uint32_t sb = sa + Cfg::kABytes;
-            if (elect_one()) {
-              if (p.dbg & 1) {
-                mbar_arrive(full_bar(stage));
-              } else {
-                mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-                const bool first = kc < p.kc1;
-                const CUtensorMap* ma = first ? &tmA1 : &tmA2;
-                const int c0 = (first ? kc : kc - p.kc1) * kBlockK;
-                if (p.conv)
-                  tma_load_4d(sa, ma, full_bar(stage), c0, ds, h0 + dr, b0);
-                else
-                  tma_load_2d(sa, ma, full_bar(stage), c0, m0);
-                tma_load_2d(sb, &tmB, full_bar(stage), (tap * kchunks + kc) * kBlockK, n0);
-              }
-            }
-            __syncwarp();
-            if (++stage == kStages) { stage = 0; phase ^= 1u; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    reg_dealloc<72>();
-    {
-      // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
-      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
-        mbar_wait(tempty_bar(as), aph ^ 1u);
-        tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
-        for (int ki = 0; ki < kiters; ++ki) {
-          mbar_wait(full_bar(stage), phase);
-          tcgen05_fence_after();
-          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-          const uint64_t adesc = umma_smem_desc(sa, 1024, kLayoutSW128);
-          const uint64_t bdesc = umma_smem_desc(sa + Cfg::kABytes, 1024, kLayoutSW128);
-          if (elect_one()) {
-            if (!(p.dbg & 2)) {
-#pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k)
-                umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
-            }
-            umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
-            if (ki == kiters - 1) umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
-          }
-          __syncwarp();
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
-        }
-      }
-    }
-  } else if (warp < 4) {
-    reg_dealloc<72>();
-  } else {
-    reg_alloc<216>();
-    // ===================== epilogue (TMEM -> regs -> global) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
-      const int n_blk = tile % p.n_tiles;
-      const int m = (tile / p.n_tiles) * kBlockM + q * 32 + lane;
-      float* sbias = sbias_base + (warp - 4) * BN;
-      __syncwarp();  // every lane finished reading the previous tile's slab
-      gemm_stage_bias<BN>(p, sbias, n_blk, lane);
-      mbar_wait(tfull_bar(as), aph);
-      tcgen05_fence_after();
-      if (BN <= 192 && !p.out_fp32 && p.act != ACT_GEGLU && (n_blk + 1) * BN <= p.n_store && !(p.dbg & 24))
-        gemm_epilogue_fast<(BN <= 192 ? BN : 64)>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN, m, n_blk, (warp - 4) >> 2, sbias, sepi_base + (warp - 4) * 2048);
-      else
-        gemm_epilogue_rows<BN>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN, m, n_blk, (warp - 4) >> 2, sbias, sepi_base + (warp - 4) * 2048);
-      tcgen05_fence_before();
-      mbar_arrive(tempty_bar(as));
-    }
-  }
-
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tcgen05_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
-  }
-}
-
-// ======================================================================================================================
-// CTA-pair variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x BN tile.  Each CTA stages its own
-// 128 rows of A and HALF of the W tile (BN/2 rows); one tcgen05.mma (M=256) issued by the leader reads both CTAs' shared
-// memory, so every SM pulls 16 KB + BN*64 B per k-chunk from L2 instead of 16 KB + BN*128 B -- the round-1 profile
-// showed the single-CTA kernel bound by L2->SM operand delivery (71 FLOP/B), this tile is at 100 (BN=160) / 131 (BN=256).
-// Both CTAs' TMA loads complete on the LEADER's full barrier; the leader's commits are multicast to both CTAs' empty /
-// accumulator-full barriers; both CTAs' epilogue warps arrive on the leader's accumulator-empty barrier.
-template <int BN>
-struct GemmPairCfg {
-  static constexpr int kABytes = kBlockM * kBlockK * 2;
-  static constexpr int kBBytes = (BN / 2) * kBlockK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 6 : 7;
-  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kBiasBytes = 8 * BN * 4;
-  static constexpr int kEpiBytes = 8 * 2048;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kBiasBytes + kEpiBytes + 1024;
-};
-
-template <int BN>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-                         const __grid_constant__ CUtensorMap tmB, const GemmKernelParams p) {
-  using Cfg = GemmPairCfg<BN>;
-  constexpr int kStages = Cfg::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
-  float* sbias_base = reinterpret_cast<float*>(smem_raw + (bar_base + Cfg::kBarBytes - smem_u32(smem_raw)));
-  uint8_t* sepi_base = reinterpret_cast<uint8_t*>(sbias_base) + Cfg::kBiasBytes;
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const int rank = kPair ? static_cast<int>(cluster_ctarank()) : 0;
   const bool leader = rank == 0;
-  const int pair_id = blockIdx.x >> 1;
-  const int num_pairs = gridDim.x >> 1;
+  const int worker = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int num_workers = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA1);
-    tma_prefetch_desc(&tmA2);
-    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&maps.a1);
+    tma_prefetch_desc(&maps.a2);
+    tma_prefetch_desc(&maps.b);
+    if (p.res_mma > 0) {
+      tma_prefetch_desc(&maps.r1);
+      tma_prefetch_desc(&maps.ident);
+    }
+    if (p.tma_store) tma_prefetch_desc(&maps.out);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(full_bar(s), 1);   // leader: one arrive.expect_tx covering both CTAs' bytes
-      mbar_init(empty_bar(s), 1);  // one multicast commit per phase
+      mbar_init(full_bar(s), 1);   // (pair: leader's copy) one arrive.expect_tx covering every CTA's bytes
+      mbar_init(empty_bar(s), 1);  // one (multicast) commit per phase
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 2 * kEpilogueThreads);  // 8 epilogue warps x 2 CTAs (only the leader's copy is used)
+      mbar_init(tempty_bar(s), (kPair ? 2 : 1) * kEpilogueThreads);
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
+  if (warp == 2) {
+    if (kPair) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot); else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
   tcgen05_fence_before();
-  cluster_sync_all();
+  if (kPair) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int m_tiles = (p.M + 2 * kBlockM - 1) / (2 * kBlockM);
+  const int m_tiles = (p.M + kTileM - 1) / kTileM;
   const int total_tiles = m_tiles * p.n_tiles;
   const int kchunks = p.kc1 + p.kc2;
-  const int kiters = p.taps * kchunks;
+  const int kmain = p.taps * kchunks;
+  // residual-as-operand: the k-chunks of R that intersect this tile's columns [n_blk*BN, n_blk*BN + BN)
+  auto res_first = [&](int n_blk) { return (n_blk * BN) >> 6; };
+  auto res_count = [&](int n_blk) { return p.res_mma > 0 ? ((n_blk * BN + BN + 63) >> 6) - ((n_blk * BN) >> 6) : 0; };
 
+  // warps 0-3 (one warpgroup) need few registers; each role branch re-balances so the 8 epilogue warps get 216
   if (warp == 0) {
     reg_dealloc<72>();
-    {
-      // ===================== TMA producer (both CTAs; whole warp loops, one elected lane issues) =====================
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = pair_id; tile < total_tiles; tile += num_pairs) {
-        const int n0 = (tile % p.n_tiles) * BN + static_cast<int>(rank) * (BN / 2);
-        const int m0 = (tile / p.n_tiles) * (2 * kBlockM) + static_cast<int>(rank) * kBlockM;
-        int b0 = 0, h0 = 0;
-        if (p.conv) {
-          const int hw = p.H * p.W;
-          b0 = m0 / hw;
-          h0 = (m0 - b0 * hw) / p.W;
+    // ===================== TMA producer =====================
+    // The whole warp walks the loop (warp-uniform control flow keeps descriptors / coordinates in uniform registers: a
+    // single divergent thread makes ptxas wrap every UTMALDG / UTCHMMA in an ELECT + R2UR waterfall loop); one elected
+    // lane issues.
+    int stage = 0;
+    uint32_t phase = 0;
+    auto load = [&](const CUtensorMap* ma, bool conv, int c0, int ds, int hh, int bb, int m0, const CUtensorMap* mb, int kb, int nb) {
+      mbar_wait(empty_bar(stage), phase ^ 1u);
+      const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+      const uint32_t sb = sa + Cfg::kABytes;
+      if (elect_one()) {
+        if (p.dbg & 1) {
+          if (leader) mbar_arrive(full_bar(stage));
+        } else if (kPair) {
+          if (leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+          if (conv) tma_load_4d_pair(sa, ma, full_bar(stage), c0, ds, hh, bb); else tma_load_2d_pair(sa, ma, full_bar(stage), c0, m0);
+          tma_load_2d_pair(sb, mb, full_bar(stage), kb, nb);
+        } else {
+          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          if (conv) tma_load_4d(sa, ma, full_bar(stage), c0, ds, hh, bb); else tma_load_2d(sa, ma, full_bar(stage), c0, m0);
+          tma_load_2d(sb, mb, full_bar(stage), kb, nb);
         }
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int dr = (p.taps == 9) ? tap / 3 - 1 : 0;
-          const int ds = (p.taps == 9) ? tap % 3 - 1 : 0;
-          for (int kc = 0; kc < kchunks; ++kc) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-            const uint32_t sb = sa + Cfg::kABytes;
-            if (elect_one()) {
-              if (p.dbg & 1) {
-                if (leader) mbar_arrive(full_bar(stage));
-              } else {
-                if (leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
-                const bool first = kc < p.kc1;
-                const CUtensorMap* ma = first ? &tmA1 : &tmA2;
-                const int c0 = (first ? kc : kc - p.kc1) * kBlockK;
-                if (p.conv)
-                  tma_load_4d_pair(sa, ma, full_bar(stage), c0, ds, h0 + dr, b0);
-                else
-                  tma_load_2d_pair(sa, ma, full_bar(stage), c0, m0);
-                tma_load_2d_pair(sb, &tmB, full_bar(stage), (tap * kchunks + kc) * kBlockK, n0);
-              }
-            }
-            __syncwarp();
-            if (++stage == kStages) { stage = 0; phase ^= 1u; }
-          }
+      }
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1u; }
+    };
+    for (int tile = worker; tile < total_tiles; tile += num_workers) {
+      const int n_blk = tile % p.n_tiles;
+      const int n0 = n_blk * BN + rank * Cfg::kBRows;
+      const int m0 = (tile / p.n_tiles) * kTileM + rank * kBlockM;
+      int b0 = 0, h0 = 0;
+      if (p.conv) {
+        const int hw = p.H * p.W;
+        b0 = m0 / hw;
+        h0 = (m0 - b0 * hw) / p.W;
+      }
+      for (int tap = 0; tap < p.taps; ++tap) {
+        const int dr = (p.taps == 9) ? tap / 3 - 1 : 0;
+        const int ds = (p.taps == 9) ? tap % 3 - 1 : 0;
+        for (int kc = 0; kc < kchunks; ++kc) {
+          const bool first = kc < p.kc1;
+          load(first ? &maps.a1 : &maps.a2, p.conv != 0, (first ? kc : kc - p.kc1) * kBlockK, ds, h0 + dr, b0, m0, &maps.b,
+               (tap * kchunks + kc) * kBlockK, n0);
         }
+      }
+      if (p.res_mma > 0) {
+        const int rk0 = res_first(n_blk), rkn = res_count(n_blk);
+        for (int r = 0; r < p.res_mma; ++r)
+          for (int j = 0; j < rkn; ++j)
+            load(r == 0 ? &maps.r1 : &maps.r2, false, (rk0 + j) * kBlockK, 0, 0, 0, m0, &maps.ident, j * kBlockK, n0 - rk0 * kBlockK);
       }
     }
   } else if (warp == 1) {
     reg_dealloc<72>();
     if (leader) {
-      // ===================== MMA issuer (leader CTA only; whole warp loops, one elected lane issues) =====================
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * kBlockM, BN);
+      // ===================== MMA issuer (leader CTA; whole warp loops, one elected lane issues) =====================
+      constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
-      for (int tile = pair_id; tile < total_tiles; tile += num_pairs, ++it) {
+      for (int tile = worker; tile < total_tiles; tile += num_workers, ++it) {
         const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
+        const int kiters = kmain + p.res_mma * res_count(tile % p.n_tiles);
         mbar_wait(tempty_bar(as), aph ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -636,11 +483,19 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
           if (elect_one()) {
             if (!(p.dbg & 2)) {
 #pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k)
-                umma_bf16_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                if (kPair) umma_bf16_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+                else umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+              }
             }
-            umma_commit_pair(empty_bar(stage));  // frees this smem slot in BOTH CTAs
-            if (ki == kiters - 1) umma_commit_pair(tfull_bar(as));  // accumulator complete -> both CTAs' epilogues
+            // free the smem slot once these MMAs retire; the last k-chunk also publishes the accumulator
+            if (kPair) {
+              umma_commit_pair(empty_bar(stage));
+              if (ki == kiters - 1) umma_commit_pair(tfull_bar(as));
+            } else {
+              umma_commit(empty_bar(stage));
+              if (ki == kiters - 1) umma_commit(tfull_bar(as));
+            }
           }
           __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -651,32 +506,48 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_
     reg_dealloc<72>();
   } else {
     reg_alloc<216>();
-    // ===================== epilogue (both CTAs; each drains its own 128 TMEM lanes) =====================
-    const int q = warp & 3;
+    // ===================== epilogue (every CTA drains its own 128 TMEM lanes) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int half = (warp - 4) >> 2;
+    float* sbias = sbias_base + (warp - 4) * BN;
+    uint8_t* stage_buf = sepi_base + (warp - 4) * 4096;
+    uint32_t buf_sel = 0;
     uint32_t it = 0;
-    for (int tile = pair_id; tile < total_tiles; tile += num_pairs, ++it) {
+    for (int tile = worker; tile < total_tiles; tile += num_workers, ++it) {
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
       const int n_blk = tile % p.n_tiles;
-      const int m = (tile / p.n_tiles) * (2 * kBlockM) + static_cast<int>(rank) * kBlockM + q * 32 + lane;
-      float* sbias = sbias_base + (warp - 4) * BN;
+      const int m = (tile / p.n_tiles) * kTileM + rank * kBlockM + q * 32 + lane;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
       __syncwarp();  // every lane finished reading the previous tile's slab
       gemm_stage_bias<BN>(p, sbias, n_blk, lane);
       mbar_wait(tfull_bar(as), aph);
       tcgen05_fence_after();
-      if (BN <= 192 && !p.out_fp32 && p.act != ACT_GEGLU && (n_blk + 1) * BN <= p.n_store && !(p.dbg & 24))
-        gemm_epilogue_fast<(BN <= 192 ? BN : 64)>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN, m, n_blk, (warp - 4) >> 2, sbias, sepi_base + (warp - 4) * 2048);
-      else
-        gemm_epilogue_rows<BN>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN, m, n_blk, (warp - 4) >> 2, sbias, sepi_base + (warp - 4) * 2048);
-      tcgen05_fence_before();
-      mbar_arrive_leader(tempty_bar(as));
+      auto release = [&]() {
+        tcgen05_fence_before();
+        if (kPair) mbar_arrive_leader(tempty_bar(as)); else mbar_arrive(tempty_bar(as));
+      };
+      const int out_cols = p.act == ACT_GEGLU ? BN / 2 : BN;
+      if (p.tma_store && (n_blk + 1) * out_cols <= p.n_store && (BN % 64 == 0 || p.act != ACT_GEGLU)) {
+        if (p.act == ACT_GEGLU) {
+          if constexpr (BN % 64 == 0)
+            gemm_epilogue_tma<BN, true>(p, &maps.out, t_row, m, n_blk, half, sbias, stage_buf, buf_sel, release);
+        } else {
+          gemm_epilogue_tma<BN, false>(p, &maps.out, t_row, m, n_blk, half, sbias, stage_buf, buf_sel, release);
+        }
+      } else {
+        gemm_epilogue_rows<BN>(p, t_row, m, n_blk, half, sbias, stage_buf);
+        release();
+      }
     }
+    if (lane == 0) bulk_wait_group_read<0>();  // staging buffers must outlive the last TMA store's reads
   }
 
   tcgen05_fence_before();
-  cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer can still touch its smem / barriers
+  // (pair) neither CTA may exit or free TMEM while its peer can still touch its smem / barriers
+  if (kPair) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
-    tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+    if (kPair) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base); else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 

@@ -78,59 +78,63 @@ int load_encode() {
 
 // bf16 tensor, `rank` dims (innermost first), byte strides for dims 1..rank-1, 128B swizzle, zero OOB fill.
 int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-               const cuuint32_t* box) {
+               const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(ptr), dims,
-                        strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(MRISR_E_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", static_cast<int>(r));
   return 0;
 }
 
-template <int BN>
-int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const mrisr::GemmKernelParams& p,
-                cudaStream_t st) {
-  using Cfg = mrisr::GemmCfg<BN>;
-  static bool configured = false;
-  if (!configured) {
-    MRISR_CHECK_CUDA(cudaFuncSetAttribute(mrisr::gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          Cfg::kSmemBytes));
-    configured = true;
+// 256 x 256 bf16 identity: the weight tile against which residual tensors are consumed as extra A operands (I[n, k]
+// depends only on n - k, so one tile shifted by the tile's first k-chunk serves every N).  Constant-initialised device
+// data: no allocation, no init kernel, safe under CUDA-graph capture.
+struct IdentityTile {
+  uint16_t v[256 * 256];
+  constexpr IdentityTile() : v() {
+    for (int i = 0; i < 256; ++i) v[i * 256 + i] = 0x3F80;  // bf16 1.0
   }
-  const int tiles = p.m_tiles * p.n_tiles;
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  mrisr::gemm_tcgen05_kernel<BN><<<grid, mrisr::kGemmThreads, Cfg::kSmemBytes, st>>>(a1, a2, b, p);
-  MRISR_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
+};
+__device__ const IdentityTile g_identity_tile = IdentityTile();
 
-template <int BN>
-int launch_gemm_pair(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const mrisr::GemmKernelParams& p,
-                     cudaStream_t st) {
-  using Cfg = mrisr::GemmPairCfg<BN>;
+template <int BN, bool kPair>
+int launch_gemm(const mrisr::GemmMaps& maps, const mrisr::GemmKernelParams& p, cudaStream_t st) {
+  using Cfg = mrisr::GemmCfg<BN, kPair>;
   static bool configured = false;
   if (!configured) {
-    MRISR_CHECK_CUDA(cudaFuncSetAttribute(mrisr::gemm_tcgen05_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MRISR_CHECK_CUDA(cudaFuncSetAttribute(mrisr::gemm_tcgen05_kernel<BN, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           Cfg::kSmemBytes));
     configured = true;
   }
-  const int tiles = ((p.M + 255) / 256) * p.n_tiles;
-  const int max_pairs = sm_count() / 2;
-  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  const int tiles = ((p.M + Cfg::kTileM - 1) / Cfg::kTileM) * p.n_tiles;
+  const int max_workers = kPair ? sm_count() / 2 : sm_count();
+  const int workers = tiles < max_workers ? tiles : max_workers;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * pairs);
+  cfg.gridDim = dim3(kPair ? 2 * workers : workers);
   cfg.blockDim = dim3(mrisr::kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.x = kPair ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MRISR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mrisr::gemm_tcgen05_pair_kernel<BN>, a1, a2, b, p));
+  MRISR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mrisr::gemm_tcgen05_kernel<BN, kPair>, maps, p));
   return 0;
+}
+
+template <bool kPair>
+int dispatch_gemm(int BN, const mrisr::GemmMaps& maps, const mrisr::GemmKernelParams& p, cudaStream_t st) {
+  switch (BN) {
+    case 256: return launch_gemm<256, kPair>(maps, p, st);
+    case 192: return launch_gemm<192, kPair>(maps, p, st);
+    case 160: return launch_gemm<160, kPair>(maps, p, st);
+    case 128: return launch_gemm<128, kPair>(maps, p, st);
+    default: return launch_gemm<64, kPair>(maps, p, st);
+  }
 }
 
 // MRISR_GEMM_SINGLE_CTA=1 selects the round-1 single-CTA kernel (A/B measurements only; same results)
@@ -399,6 +403,28 @@ int mrisr_gemm_block_n(int N, int act) {
   return 0;
 }
 
+// N-tile for a given problem: GEGLU weights are interleaved per tile at load time, so their BN depends on N only; every
+// other GEMM picks, per call, the tile width that minimises waves x (BN + fixed per-tile cost) on the 74 CTA pairs --
+// at batch 32 the 16x16 level (M = 8192, N = 1280) is 3 waves of BN=256 tiles but 4 waves of the 37 % narrower BN=160.
+static int pick_block_n(int M, int N, int act) {
+  const int fixed = mrisr_gemm_block_n(N, act);
+  if (act == MRISR_ACT_GEGLU || fixed == 0 || getenv("MRISR_GEMM_BN") != nullptr) return fixed;
+  const int pairs = sm_count() / 2 > 0 ? sm_count() / 2 : 1;
+  const int m_tiles = (M + 255) / 256;
+  static const int cand[5] = {256, 192, 160, 128, 64};
+  int best = fixed;
+  long long best_cost = -1;
+  for (int i = 0; i < 5; ++i) {
+    const int bn = cand[i];
+    if (N % bn != 0) continue;
+    const long long tiles = static_cast<long long>(m_tiles) * (N / bn);
+    const long long waves = (tiles + pairs - 1) / pairs;
+    const long long cost = waves * (bn + 40);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
 int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
   MRISR_REQUIRE(g != nullptr, "gemm: null args");
   MRISR_REQUIRE(g->a1 && g->w && g->out, "gemm: null a1/w/out");
@@ -407,7 +433,7 @@ int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
   MRISR_REQUIRE(g->k1 > 0 && g->k1 % 64 == 0 && g->k2 >= 0 && g->k2 % 64 == 0, "gemm: k1 (%d) / k2 (%d) must be multiples of 64", g->k1, g->k2);
   MRISR_REQUIRE(g->k2 == 0 || g->a2, "gemm: k2 > 0 but a2 is null");
   MRISR_REQUIRE(g->act >= 0 && g->act <= 3, "gemm: bad act");
-  const int BN = mrisr_gemm_block_n(g->N, g->act);
+  const int BN = pick_block_n(g->M, g->N, g->act);
   if (BN == 0) return fail(MRISR_E_UNSUPPORTED, "gemm: N = %d is not a multiple of 64", g->N);
   const int out_cols = g->act == MRISR_ACT_GEGLU ? g->N / 2 : g->N;
   MRISR_REQUIRE(g->n_store <= out_cols, "gemm: n_store (%d) > produced columns (%d)", g->n_store, out_cols);
@@ -424,12 +450,14 @@ int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
 
   const int ktot = g->taps * (g->k1 + g->k2);
   const bool pair = use_pair_kernel();
-  CUtensorMap ma1, ma2, mb;
+  mrisr::GemmMaps maps;
+  CUtensorMap& ma1 = maps.a1;
+  CUtensorMap& ma2 = maps.a2;
   {
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(ktot), static_cast<cuuint64_t>(g->N)};
     cuuint64_t str[1] = {static_cast<cuuint64_t>(ktot) * 2};
     cuuint32_t box[2] = {64, static_cast<cuuint32_t>(pair ? BN / 2 : BN)};
-    if (int e = encode_map(&mb, g->w, 2, dims, str, box)) return e;
+    if (int e = encode_map(&maps.b, g->w, 2, dims, str, box)) return e;
   }
   if (g->taps == 1) {
     cuuint32_t box[2] = {64, 128};
@@ -480,23 +508,50 @@ int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
   p.res2 = static_cast<const __nv_bfloat16*>(g->res2); p.ldr2 = g->ldr2;
   p.out = g->out; p.ldo = g->ldo; p.out_fp32 = g->out_fp32;
   p.dbg = g->reserved;
-  cudaStream_t st = as_stream(stream);
-  if (pair) {
-    switch (BN) {
-      case 256: return launch_gemm_pair<256>(ma1, ma2, mb, p, st);
-      case 192: return launch_gemm_pair<192>(ma1, ma2, mb, p, st);
-      case 160: return launch_gemm_pair<160>(ma1, ma2, mb, p, st);
-      case 128: return launch_gemm_pair<128>(ma1, ma2, mb, p, st);
-      default: return launch_gemm_pair<64>(ma1, ma2, mb, p, st);
+  p.res_mma = 0;
+  p.tma_store = 0;
+  maps.r1 = ma1; maps.r2 = ma1; maps.ident = ma1; maps.out = ma1;
+
+  // Residuals of activation-free GEMMs become extra A operands against the identity tile (see gemm_tcgen05.cuh): the
+  // epilogue then has no residual traffic at all.  MRISR_GEMM_RES_EPILOGUE=1 keeps them in the epilogue (A/B runs).
+  static const bool res_in_epilogue = getenv("MRISR_GEMM_RES_EPILOGUE") != nullptr;
+  if (g->act == MRISR_ACT_NONE && (g->res1 || g->res2) && !res_in_epilogue) {
+    static const void* ident = nullptr;
+    if (ident == nullptr) {
+      void* sym = nullptr;
+      MRISR_CHECK_CUDA(cudaGetSymbolAddress(&sym, g_identity_tile));
+      ident = sym;
     }
+    {
+      cuuint64_t dims[2] = {256, 256};
+      cuuint64_t str[1] = {512};
+      cuuint32_t box[2] = {64, static_cast<cuuint32_t>(pair ? BN / 2 : BN)};
+      if (int e = encode_map(&maps.ident, ident, 2, dims, str, box)) return e;
+    }
+    const void* rp[2] = {g->res1 ? g->res1 : g->res2, g->res1 ? g->res2 : nullptr};
+    const long long rl[2] = {g->res1 ? g->ldr1 : g->ldr2, g->ldr2};
+    CUtensorMap* rm[2] = {&maps.r1, &maps.r2};
+    for (int i = 0; i < 2 && rp[i] != nullptr; ++i) {
+      // columns >= n_store are never stored: clip them (TMA zero-fills), so R only needs n_store readable columns
+      cuuint64_t dims[2] = {static_cast<cuuint64_t>(g->n_store), static_cast<cuuint64_t>(g->M)};
+      cuuint64_t str[1] = {static_cast<cuuint64_t>(rl[i]) * 2};
+      cuuint32_t box[2] = {64, 128};
+      if (int e = encode_map(rm[i], rp[i], 2, dims, str, box)) return e;
+      ++p.res_mma;
+    }
+    p.res1 = nullptr;
+    p.res2 = nullptr;
   }
-  switch (BN) {
-    case 256: return launch_gemm<256>(ma1, ma2, mb, p, st);
-    case 192: return launch_gemm<192>(ma1, ma2, mb, p, st);
-    case 160: return launch_gemm<160>(ma1, ma2, mb, p, st);
-    case 128: return launch_gemm<128>(ma1, ma2, mb, p, st);
-    default: return launch_gemm<64>(ma1, ma2, mb, p, st);
+  // bf16 outputs whose residuals (if any) are out of the epilogue go through the TMA-store epilogue
+  if (!g->out_fp32 && p.res1 == nullptr && p.res2 == nullptr && g->n_store >= 32) {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(g->n_store), static_cast<cuuint64_t>(g->M)};
+    cuuint64_t str[1] = {static_cast<cuuint64_t>(g->ldo) * 2};
+    cuuint32_t box[2] = {32, 32};
+    if (int e = encode_map(&maps.out, g->out, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
+    p.tma_store = 1;
   }
+  cudaStream_t st = as_stream(stream);
+  return pair ? dispatch_gemm<true>(BN, maps, p, st) : dispatch_gemm<false>(BN, maps, p, st);
 }
 
 int mrisr_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,

@@ -84,6 +84,24 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, 
       : "memory");
 }
 
+// Asynchronous L2 prefetch of a contiguous global range (16-byte aligned address, size a multiple of 16).
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gptr)), "r"(bytes) : "memory");
+}
+
+// ------------------------------------------------------------------ TMA stores (tile mode, bulk async-groups)
+// smem -> global; the issuing thread owns the bulk group.  Generic-proxy writes to the source buffer must be followed by
+// fence.proxy.async (every writing thread) and a barrier before the issue.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still READ their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
 // ------------------------------------------------------------------ TMEM allocation
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {

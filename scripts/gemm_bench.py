@@ -44,6 +44,12 @@ for hw, K, N, act in [(4096, 320, 320, 0), (4096, 384, 960, 0), (4096, 320, 2560
     a = bf(B * hw, K); w = bf(N, K); bias = torch.zeros(N, device=dev)
     ms = timeit(lambda: ops.gemm(a, w, bias=bias, act=act))
     rows.append((f"linear M={B*hw} K={K} N={N} act={act}", ms, 2.0 * B * hw * K * N))
+# linear + residual (attention to_out / FF2 at batch-32 sizes)
+for M_, K, N in [(131072, 384, 320), (131072, 320, 320), (131072, 1280, 320), (32768, 704, 640), (8192, 1344, 1280)]:
+    M_ = M_ * B // 32
+    a = bf(M_, K); w = bf(N, K); bias = torch.zeros(N, device=dev); r = bf(M_, N)
+    ms = timeit(lambda: ops.gemm(a, w, bias=bias, res1=r))
+    rows.append((f"linear+res M={M_} K={K} N={N}", ms, 2.0 * M_ * K * N))
 tot_ms = tot_fl = 0
 for name, ms, fl in rows:
     print(f"{name:44s} {ms*1e3:9.1f} us  {fl/ms/1e9:8.1f} TFLOP/s")
