@@ -227,4 +227,170 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const AttnAr
   }
 }
 
+// ----------------------------------------------------------------------------------------------------------------------
+// Short-context variant (Nk <= 128: cross-attention on the 77 prompt tokens, self-attention of the 8x8 mid block).
+// The generic kernel above spends its time in per-CTA latency there (2 CTAs of 256 threads per SM, each: load ->
+// barrier -> ~1 us of math -> store; 28 waves at the 64x64 level = 146 us for 168 MB of traffic).  Here a CTA is 4 warps
+// x 16 queries, the WHOLE key/value context sits in shared memory (NKP = Nk padded to 16: one pass, no online-softmax
+// rescaling, 80 instead of 128 padded keys for the prompt), 4-8 CTAs are resident per SM so loads, math and stores of
+// different CTAs overlap, and O leaves through shared memory as full 16-byte chunks per row.
+constexpr int kCtxBM = 64;
+constexpr int kCtxThreads = 128;
+
+template <int D, int NKP>
+struct AttnCtxCfg {
+  static constexpr int DP = (D + 15) / 16 * 16;
+  static constexpr int LDS = DP + 8;
+  static constexpr int kSmemBytes = (2 * kCtxBM + 2 * NKP) * LDS * 2;
+};
+
+template <int D, int NKP>
+__global__ void __launch_bounds__(kCtxThreads, (D <= 80 && NKP <= 80) ? 4 : 2) attention_ctx_kernel(const AttnArgs a, int q_tiles) {
+  using Cfg = AttnCtxCfg<D, NKP>;
+  constexpr int DP = Cfg::DP, LDS = Cfg::LDS;
+  constexpr int KQ = DP / 16;   // k16 steps of Q K^T
+  constexpr int NS = NKP / 8;   // n8 tiles of S
+  constexpr int KP = NKP / 16;  // k16 steps of P V
+  constexpr int NT = D / 8;     // n8 tiles of O
+  constexpr int CPR = DP / 8;   // 16-byte chunks per staged row
+  constexpr int kQBuf = kCtxBM * LDS * 2;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const uint32_t sQ = smem_u32(smem);
+  const uint32_t sK = sQ + 2 * kQBuf;
+  const uint32_t sV = sK + NKP * LDS * 2;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int qbase = blockIdx.x * q_tiles * kCtxBM;
+  const int ntiles = min(q_tiles, (a.nq - qbase + kCtxBM - 1) / kCtxBM);
+  const __nv_bfloat16* qg = a.q + (static_cast<long long>(b) * a.q_batch_rows) * a.ldq + head * D;
+  const __nv_bfloat16* kg = a.k + (static_cast<long long>(b) * a.kv_batch_rows) * a.ldk + head * D;
+  const __nv_bfloat16* vg = a.v + (static_cast<long long>(b) * a.kv_batch_rows) * a.ldv + head * D;
+  __nv_bfloat16* og = a.o + (static_cast<long long>(b) * a.q_batch_rows) * a.ldo + head * D;
+
+  auto load_rows = [&](uint32_t sdst, const __nv_bfloat16* g, long long ld, int row0, int rows, int nrows) {
+    for (int i = tid; i < rows * CPR; i += kCtxThreads) {
+      const int r = i / CPR, c = i % CPR;
+      const uint32_t dst = sdst + (r * LDS + c * 8) * 2;
+      if (row0 + r < nrows && c * 8 < D) cp_async16(dst, g + static_cast<long long>(row0 + r) * ld + c * 8);
+      else asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(dst), "r"(0) : "memory");
+    }
+  };
+  // the context is staged once per CTA and reused by all of its query tiles; Q tiles are double-buffered
+  load_rows(sQ, qg, a.ldq, qbase, kCtxBM, a.nq);
+  load_rows(sK, kg, a.ldk, 0, NKP, a.nk);
+  load_rows(sV, vg, a.ldv, 0, NKP, a.nk);
+  cp_async_commit();
+
+  for (int t = 0; t < ntiles; ++t) {
+    const int q0 = qbase + t * kCtxBM;
+    const uint32_t sQt = sQ + (t & 1) * kQBuf;
+    uint8_t* sQt_ptr = smem + (t & 1) * kQBuf;
+    cp_async_wait<0>();
+    __syncthreads();  // tile t (and the context) visible; every warp is done with the other Q buffer (tile t-1)
+    if (t + 1 < ntiles) load_rows(sQ + ((t + 1) & 1) * kQBuf, qg, a.ldq, q0 + kCtxBM, kCtxBM, a.nq);
+    cp_async_commit();
+
+    uint32_t qf[KQ][4];
+#pragma unroll
+    for (int kk = 0; kk < KQ; ++kk)
+      ldsm_x4(sQt + ((warp * 16 + (lane & 15)) * LDS + kk * 16 + (lane >> 4) * 8) * 2, qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3]);
+
+    // ---- S = Q K^T (16 x NKP per warp)
+    float s[NS][4];
+#pragma unroll
+    for (int j = 0; j < NS; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < KQ; ++kk) {
+#pragma unroll
+      for (int jp = 0; jp < NS / 2; ++jp) {
+        const int mi = lane >> 3;
+        const int key = jp * 16 + (mi >> 1) * 8 + (lane & 7);
+        const int dc = kk * 16 + (mi & 1) * 8;
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(sK + (key * LDS + dc) * 2, b0, b1, b2, b3);
+        mma_bf16_16816(s[2 * jp], qf[kk], b0, b1);
+        mma_bf16_16816(s[2 * jp + 1], qf[kk], b2, b3);
+      }
+    }
+    if (NKP > a.nk) {
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        const int key = j * 8 + (lane & 3) * 2;
+        if (key >= a.nk) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+        if (key + 1 >= a.nk) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+      }
+    }
+    // ---- softmax over the whole context (rows g = lane/4 and g+8)
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float ms0 = mx0 * a.scale_log2, ms1 = mx1 * a.scale_log2;
+    float l0 = 0.f, l1 = 0.f;
+    uint32_t pf[KP][4];
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      const float p0 = fast_exp2(s[j][0] * a.scale_log2 - ms0);
+      const float p1 = fast_exp2(s[j][1] * a.scale_log2 - ms0);
+      const float p2 = fast_exp2(s[j][2] * a.scale_log2 - ms1);
+      const float p3 = fast_exp2(s[j][3] * a.scale_log2 - ms1);
+      l0 += p0 + p1; l1 += p2 + p3;
+      pf[j >> 1][(j & 1) * 2] = pack_bf16(p0, p1);
+      pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2, p3);
+    }
+    // ---- O = P V
+    float o[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < KP; ++kk) {
+#pragma unroll
+      for (int jp = 0; jp < NT / 2; ++jp) {
+        const int mi = lane >> 3;
+        const int key = kk * 16 + (mi & 1) * 8 + (lane & 7);
+        const int dc = jp * 16 + (mi >> 1) * 8;
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t(sV + (key * LDS + dc) * 2, b0, b1, b2, b3);
+        mma_bf16_16816(o[2 * jp], pf[kk], b0, b1);
+        mma_bf16_16816(o[2 * jp + 1], pf[kk], b2, b3);
+      }
+      if (NT & 1) {
+        const int key = kk * 16 + (lane & 15);
+        uint32_t b0, b1;
+        ldsm_x2_t(sV + (key * LDS + (NT - 1) * 8) * 2, b0, b1);
+        mma_bf16_16816(o[NT - 1], pf[kk], b0, b1);
+      }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    // ---- O -> this warp's 16 rows of the (now free) Q buffer -> 16-byte row chunks in global memory
+    __syncwarp();  // every lane's ldmatrix of Q has completed (only this warp ever touches these rows)
+    {
+      const int r0 = warp * 16 + (lane >> 2);
+      uint8_t* base = sQt_ptr + (r0 * LDS + (lane & 3) * 2) * 2;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        *reinterpret_cast<uint32_t*>(base + j * 16) = pack_bf16(o[j][0] * i0, o[j][1] * i0);
+        *reinterpret_cast<uint32_t*>(base + 8 * LDS * 2 + j * 16) = pack_bf16(o[j][2] * i1, o[j][3] * i1);
+      }
+    }
+    __syncwarp();
+    for (int i = lane; i < 16 * NT; i += 32) {
+      const int r = i / NT, c = i % NT;
+      const int row = q0 + warp * 16 + r;
+      if (row < a.nq)
+        *reinterpret_cast<uint4*>(og + static_cast<long long>(row) * a.ldo + c * 8) =
+            *reinterpret_cast<const uint4*>(sQt_ptr + ((warp * 16 + r) * LDS + c * 8) * 2);
+    }
+  }
+  cp_async_wait<0>();
+}
+
 }  // namespace mrisr

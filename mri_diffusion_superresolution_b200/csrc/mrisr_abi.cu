@@ -162,6 +162,31 @@ int launch_attention(const mrisr::AttnArgs& a, cudaStream_t st) {
   return 0;
 }
 
+template <int D, int NKP>
+int launch_attention_ctx(const mrisr::AttnArgs& a, cudaStream_t st) {
+  using Cfg = mrisr::AttnCtxCfg<D, NKP>;
+  static bool configured = false;
+  if (!configured) {
+    MRISR_CHECK_CUDA(cudaFuncSetAttribute(mrisr::attention_ctx_kernel<D, NKP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          Cfg::kSmemBytes));
+    configured = true;
+  }
+  // query tiles per CTA: the context is staged once per CTA, so long query ranges amortise it (and overlap the next
+  // tile's Q load with the current tile's math) as long as the grid still fills the SMs several times over
+  const int q_tiles = a.nq >= 2048 ? 4 : a.nq >= 512 ? 2 : 1;
+  const int rows_per_cta = mrisr::kCtxBM * q_tiles;
+  dim3 grid((a.nq + rows_per_cta - 1) / rows_per_cta, a.heads, a.batch);
+  mrisr::attention_ctx_kernel<D, NKP><<<grid, mrisr::kCtxThreads, Cfg::kSmemBytes, st>>>(a, q_tiles);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+template <int D>
+int dispatch_attention_ctx(const mrisr::AttnArgs& a, cudaStream_t st) {
+  if (a.nk <= 64) return launch_attention_ctx<D, 64>(a, st);
+  if (a.nk <= 80) return launch_attention_ctx<D, 80>(a, st);
+  return launch_attention_ctx<D, 128>(a, st);
+}
+
 // tcgen05 / TMEM attention (head dims 40, 80).  K and V are addressed through TMA maps over [rows, heads*d] views.
 template <int D>
 int launch_attention_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
@@ -572,6 +597,13 @@ int mrisr_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   if (use_tc_attention() && (d == 40 || d == 80) && nk >= 128 && ldo % 8 == 0) {
     if (d == 40) return launch_attention_tc<40>(q, ldq, k, ldk, v, ldv, o, ldo, batch, nq, nk, heads, kv_broadcast, st);
     return launch_attention_tc<80>(q, ldq, k, ldk, v, ldv, o, ldo, batch, nq, nk, heads, kv_broadcast, st);
+  }
+  // short contexts (cross-attention on the prompt, 8x8 self-attention): whole K/V in shared memory, small CTAs
+  static const bool no_ctx = getenv("MRISR_ATTN_NO_CTX") != nullptr;
+  if (nk <= 128 && ldo % 8 == 0 && !no_ctx) {
+    if (d == 40) return dispatch_attention_ctx<40>(a, st);
+    if (d == 80) return dispatch_attention_ctx<80>(a, st);
+    if (d == 160) return dispatch_attention_ctx<160>(a, st);
   }
   switch (d) {
     case 8: return launch_attention<8>(a, st);

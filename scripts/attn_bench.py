@@ -12,7 +12,7 @@ def graph_ms(fn, reps=4):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); g.replay(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1) / reps)
     return sorted(ts)[2]
-for heads, d, nq, nk, bc in [(8, 40, 4096, 4096, False), (8, 80, 1024, 1024, False), (8, 160, 256, 256, False), (8, 40, 4096, 77, True), (8, 80, 1024, 77, True)]:
+for heads, d, nq, nk, bc in [(8, 40, 4096, 4096, False), (8, 80, 1024, 1024, False), (8, 160, 256, 256, False), (8, 40, 4096, 77, True), (8, 80, 1024, 77, True), (8, 160, 256, 77, True), (8, 160, 64, 64, False), (8, 160, 64, 77, True)]:
     c = heads * d
     qkv = torch.randn(B * nq, 3 * c, device="cuda").to(torch.bfloat16)
     q = qkv[:, :c]

@@ -161,7 +161,8 @@ def test_conv_in_via_im2col_first(ops):
 # ------------------------------------------------------------------------------------------------ attention
 @pytest.mark.parametrize("B,heads,d,nq,nk,bcast", [(2, 8, 40, 1024, 1024, False), (1, 8, 40, 4096, 4096, False),
                                                     (2, 8, 80, 256, 256, False), (2, 8, 160, 64, 64, False),
-                                                    (2, 8, 40, 1024, 77, True), (3, 8, 160, 64, 77, True),
+                                                    (2, 8, 40, 1024, 77, True), (3, 8, 160, 64, 77, True), (2, 8, 80, 200, 77, False), (2, 8, 40, 100, 128, False),
+                                                    (1, 8, 80, 64, 33, True),
                                                     (2, 2, 64, 100, 50, False), (1, 4, 8, 16, 16, False)])
 def test_attention(ops, B, heads, d, nq, nk, bcast):
     c = heads * d
