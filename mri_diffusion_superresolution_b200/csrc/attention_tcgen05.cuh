@@ -353,6 +353,13 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_c
 // XU pipe 53 %, issue slots 45 % busy).  The two threads of a row exchange their partial row maxima through shared
 // memory (one named barrier per query tile per key tile); the row sum comes from the tensor core (Lt = P * 1 with a
 // constant all-ones B tile), so it is the sum of the ROUNDED probabilities that the P V product actually used.
+// O and the row sum ACCUMULATE IN TMEM across key tiles (PV issued with accumulate = 1); the online-softmax rescale is
+// lazy: probabilities are taken against a stale maximum m_used and O / l are only rescaled (TMEM load-multiply-store by
+// the row's own two threads, before they publish P) when a tile raises the row maximum by more than 8 in the log2
+// domain (P <= 256, exact in fp32 accumulation) -- after the first tiles this almost never happens, so the per-tile
+// softmax path has no TMEM read-back and no accumulator rescaling at all.  kPolyPairs of every 8 element pairs take the
+// FMA-pipe exponential (exp2_poly_pair) instead of MUFU.EX2.  The next tile's Q K^T is issued as soon as every softmax
+// thread has LOADED the current S (s_free), so it runs under the current tile's exponentials.
 constexpr int kAtsThreads = 640;
 
 template <int D>
@@ -379,6 +386,30 @@ __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
 __device__ __forceinline__ void tmem_ld_32x1(uint32_t taddr, uint32_t& v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x1(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
+// 2^x for a PAIR of arguments on the FMA pipe (no MUFU): Cody-Waite split x = n + f with the 1.5*2^23 magic-number
+// rounding (f in [-0.5, 0.5]), degree-3 minimax polynomial for 2^f (max relative error 7.5e-5, 26x below the bf16
+// rounding of P), exponent inserted with one integer shift-add.  Packed f32x2 instructions (FADD2 / FFMA2) process both
+// values per issue slot.  The softmax is bound by the 16/clk/SM MUFU.EX2 rate (scripts/micro/mufu_bench.cu), so a fixed
+// fraction of every row's exponentials is moved here.
+__device__ __forceinline__ void exp2_poly_pair(float x0, float x1, float& p0, float& p1) {
+  const float kMagic = 12582912.f;  // 1.5 * 2^23
+  const float2 x = make_float2(fmaxf(x0, -120.f), fmaxf(x1, -120.f));
+  const float2 t = __fadd2_rn(x, make_float2(kMagic, kMagic));
+  const float2 n = __fadd2_rn(t, make_float2(-kMagic, -kMagic));
+  const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), x);
+  float2 p = __ffma2_rn(f, make_float2(0.0551716685295105f, 0.0551716685295105f), make_float2(0.2426111251115799f, 0.2426111251115799f));
+  p = __ffma2_rn(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+  p = __ffma2_rn(p, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
+  p0 = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  p1 = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+}
 // spin without the printf of mbar_wait (keeps the 24-register control warps free of call overhead); traps on a hang
 __device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
@@ -388,7 +419,7 @@ __device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
   }
 }
 
-template <int D>
+template <int D, int kPolyPairs>
 __global__ void __launch_bounds__(kAtsThreads, 1)
 attention_tcgen05_split_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                                const AttnTcArgs a) {
@@ -410,7 +441,7 @@ attention_tcgen05_split_kernel(const __grid_constant__ CUtensorMap tmK, const __
   auto s_full = [&](int g) { return bar_base + 8u * (8 + g); };
   auto p_full = [&](int g) { return bar_base + 8u * (10 + g); };
   auto o_full = [&](int g) { return bar_base + 8u * (12 + g); };
-  auto o_free = [&](int g) { return bar_base + 8u * (14 + g); };
+  auto s_free = [&](int g) { return bar_base + 8u * (14 + g); };
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + Cfg::kQBytes + kStages * Cfg::kKVBytes + 128);
   const uint32_t tmem_slot = bar_base + 128;
 
@@ -427,7 +458,7 @@ attention_tcgen05_split_kernel(const __grid_constant__ CUtensorMap tmK, const __
     for (int st = 0; st < kStages; ++st) { mbar_init(kv_full(st), 1); mbar_init(kv_empty(st), 1); }
     for (int g = 0; g < 2; ++g) {
       mbar_init(s_full(g), 1); mbar_init(o_full(g), 1);
-      mbar_init(p_full(g), 256); mbar_init(o_free(g), 256);
+      mbar_init(p_full(g), 256); mbar_init(s_free(g), 1);
     }
     fence_mbar_init();
   }
@@ -451,8 +482,8 @@ attention_tcgen05_split_kernel(const __grid_constant__ CUtensorMap tmK, const __
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   // TMEM columns of query tile g (base g*256): S [0,128), P [128,192), Ot [192, 192+DO), Lt [192+DO, +16).
-  // P does NOT alias S: the next tile's Q K^T is issued before this tile's P V, so a query tile's softmax threads get
-  // their next S ~400 cycles after they publish P instead of ~800.
+  // P does NOT alias S: the next tile's Q K^T is issued as soon as the softmax threads have loaded S (s_free), long
+  // before this tile's P V.
   static_assert(192 + DO + 16 <= 256, "TMEM budget");
 
   if (warp == 0) {
@@ -492,26 +523,31 @@ attention_tcgen05_split_kernel(const __grid_constant__ CUtensorMap tmK, const __
     for (int j = 0; j < ntiles; ++j) {
       const int nstage = (stage + 1 == kStages) ? 0 : stage + 1;
       const uint32_t nphase = (stage + 1 == kStages) ? phase ^ 1u : phase;
-      for (int g = 0; g < 2; ++g) {
-        mbar_wait_lean(p_full(g), j & 1);                  // softmax read S_g(j) completely and wrote P_g(j)
-        if (j + 1 < ntiles) {
-          if (g == 0) mbar_wait_lean(kv_full(nstage), nphase);
+      if (j + 1 < ntiles) {
+        // S_g(j+1) as soon as every softmax thread of g has LOADED S_g(j) (s_free: signalled right after the
+        // max-exchange barrier) -- P does not alias S, so the next Q K^T overlaps this tile's exponentials
+        mbar_wait_lean(kv_full(nstage), nphase);
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait_lean(s_free(g), j & 1);
           tcgen05_fence_after();
-          if (elect_one()) issue_s(g, nstage);             // S_g(j+1) first: it is what the softmax threads wait for
+          if (elect_one()) issue_s(g, nstage);
           __syncwarp();
         }
-        if (j > 0) mbar_wait_lean(o_free(g), (j - 1) & 1);  // Ot_g(j-1) folded
+      }
+      for (int g = 0; g < 2; ++g) {
+        mbar_wait_lean(p_full(g), j & 1);                  // P_g(j) written
         tcgen05_fence_after();
         if (elect_one()) {
           const uint32_t sv = sKV + stage * Cfg::kKVBytes + Cfg::kAtomBytes;
+          const uint32_t acc0 = j > 0 ? 1u : 0u;  // O and the row sum accumulate in TMEM across key tiles
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             umma_bf16_ts(tmem_base + g * 256 + 192, tmem_base + g * 256 + 128 + k * 8,
-                         umma_smem_desc_mn(sv + k * 2048, Cfg::kAtomBytes, 1024), idesc_o, k > 0 ? 1u : 0u);
+                         umma_smem_desc_mn(sv + k * 2048, Cfg::kAtomBytes, 1024), idesc_o, k > 0 ? 1u : acc0);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             umma_bf16_ts(tmem_base + g * 256 + 192 + DO, tmem_base + g * 256 + 128 + k * 8,
-                         umma_smem_desc(sOnes, 1024, kLayoutSW128), idesc_l, k > 0 ? 1u : 0u);
+                         umma_smem_desc(sOnes, 1024, kLayoutSW128), idesc_l, k > 0 ? 1u : acc0);
           umma_commit(o_full(g));
           if (g == 1) umma_commit(kv_empty(stage));
         }
@@ -530,31 +566,25 @@ attention_tcgen05_split_kernel(const __grid_constant__ CUtensorMap tmK, const __
     const uint32_t t_s = tmem_base + (static_cast<uint32_t>(qrt * 32) << 16) + g * 256;
     const uint32_t t_p = t_s + 128;
     const uint32_t t_o = t_s + 192;
-    float o_acc[HC];
-#pragma unroll
-    for (int i = 0; i < HC; ++i) o_acc[i] = 0.f;
-    float m = -INFINITY, l = 0.f;
+    float m_used = -INFINITY;  // the maximum (log2 domain) that P, O and l are currently expressed against
     const float sc = a.scale_log2;
-    auto add_ot = [&]() {
-      uint32_t lt;
-      tmem_ld_32x1(t_o + DO, lt);
-#pragma unroll
-      for (int c = 0; c < HC / 8; ++c) {
-        uint32_t t[8];
-        tmem_ld_32x8(t_o + half * HC + c * 8, t);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o_acc[c * 8 + i] += __uint_as_float(t[i]);
-      }
-      l += __uint_as_float(lt);
-    };
+#ifdef MRISR_ATTN_TIMELINE
+    long long tl[4][7];
+    const bool tl_on = blockIdx.x == 3 && blockIdx.y == 2 && blockIdx.z == 0 && lane == 0 && (warp == 4 || warp == 9 || warp == 12 || warp == 19);
+#define TL(k) do { if (j >= 8 && j < 12) tl[j - 8][k] = clock64(); } while (0)
+#else
+#define TL(k) do { } while (0)
+#endif
     for (int j = 0; j < ntiles; ++j) {
+      TL(0);
       mbar_wait_lean(s_full(g), j & 1);
       tcgen05_fence_after();
+      TL(1);
       uint32_t s[64];
       tmem_ld_32x32(t_s + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
       tmem_ld_32x32(t_s + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
       tmem_ld_wait();
+      tcgen05_fence_before();  // this thread's reads of S_g(j) are ordered before the barrier below (-> s_free)
       const int kbase = j * BK + half * 64;
       if (kbase + 64 > a.nk) {
 #pragma unroll
@@ -571,47 +601,102 @@ attention_tcgen05_split_kernel(const __grid_constant__ CUtensorMap tmK, const __
         for (int c = 0; c < 4; ++c) mx4[c] = max3(mx4[c], __uint_as_float(s[i + c]), __uint_as_float(s[i + 4 + c]));
       }
       float raw = max3(max3(mx4[0], mx4[1], mx4[2]), mx4[3], fmaxf(fmaxf(__uint_as_float(s[60]), __uint_as_float(s[61])), fmaxf(__uint_as_float(s[62]), __uint_as_float(s[63]))));
-      // exchange the partial maximum with the thread that owns the other 64 keys of this row; the barrier also
-      // guarantees that BOTH threads finished reading S before either overwrites it with P
+      // exchange the partial maximum with the thread that owns the other 64 keys of this row.  Every thread of the
+      // query tile passes this barrier only after its S loads completed, so right after it one thread hands the S
+      // columns back to the MMA warp (s_free): the next tile's Q K^T runs under this tile's exponentials.
       float* mslot = smax + (((j & 1) * 2 + g) * 128 + rloc) * 2;
       mslot[half] = raw;
+      TL(2);
       asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
+      TL(3);
+      if ((i16 & 7) == 0 && lane == 0) mbar_arrive(s_free(g));
       raw = fmaxf(raw, mslot[half ^ 1]);
-      const float mx = fmaxf(m, raw * sc);
-      const float alpha = ex2_approx(m - mx);
+      const float mnew = raw * sc;  // identical in both threads of the row, so both take the same decisions below
+      bool o_done = j == 0;         // PV(j-1) known complete (nothing to wait for on the first tile)
+      if (j == 0) {
+        m_used = mnew;
+      } else {
+        const bool need = mnew > m_used + 8.f;
+        if (__any_sync(0xffffffffu, need)) {
+          // rare: rescale this row's O columns (and, by the half-0 thread, its row sum) in TMEM
+          mbar_wait_lean(o_full(g), (j - 1) & 1);
+          tcgen05_fence_after();
+          o_done = true;
+          const float fac = need ? ex2_approx(m_used - mnew) : 1.f;
+          if (need) m_used = mnew;
+#pragma unroll
+          for (int c = 0; c < HC / 8; ++c) {
+            uint32_t t[8];
+            tmem_ld_32x8(t_o + half * HC + c * 8, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * fac);
+            tmem_st_32x8(t_o + half * HC + c * 8, t);
+          }
+          if (half == 0) {
+            uint32_t lt;
+            tmem_ld_32x1(t_o + DO, lt);
+            tmem_ld_wait();
+            tmem_st_32x1(t_o + DO, __float_as_uint(__uint_as_float(lt) * fac));
+          }
+          tmem_st_wait();
+        }
+      }
+      const float neg_m = -m_used;
+      TL(6);
+      const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(neg_m, neg_m);
       uint32_t pk[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        pk[i] = pack_bf16(ex2_approx(fmaf(__uint_as_float(s[2 * i]), sc, -mx)), ex2_approx(fmaf(__uint_as_float(s[2 * i + 1]), sc, -mx)));
-      if (j > 0) {  // P V of the previous tile: done long ago; fold it (o_acc is still held against the previous max),
-                    // which also proves that the tensor core finished reading the previous P before it is overwritten
+      for (int i = 0; i < 32; ++i) {
+        const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), sc2, nm2);
+        float p0, p1;
+        if ((i & 7) < kPolyPairs) {
+          exp2_poly_pair(x.x, x.y, p0, p1);
+        } else {
+          p0 = ex2_approx(x.x);
+          p1 = ex2_approx(x.y);
+        }
+        pk[i] = pack_bf16(p0, p1);
+      }
+      TL(4);
+      if (!o_done) {  // the tensor core must have finished reading the previous P before it is overwritten
         mbar_wait_lean(o_full(g), (j - 1) & 1);
         tcgen05_fence_after();
-        add_ot();
-        tcgen05_fence_before();
-        mbar_arrive(o_free(g));
       }
       tmem_st_32x32(t_p + half * 32, pk);
       tmem_st_wait();
       tcgen05_fence_before();
       mbar_arrive(p_full(g));
-      l *= alpha;
-#pragma unroll
-      for (int i = 0; i < HC; ++i) o_acc[i] *= alpha;
-      m = mx;
+      TL(5);
     }
+#ifdef MRISR_ATTN_TIMELINE
+    if (tl_on && ntiles >= 12) {
+      for (int t = 0; t < 4; ++t)
+        printf("TL warp %2d tile %2d: start %8lld | s_full +%5lld | ld+max +%5lld | bar +%5lld | token +%5lld | exp +%5lld | st/arrive +%5lld\n", warp, t + 8,
+               tl[t][0] % 100000000, tl[t][1] - tl[t][0], tl[t][2] - tl[t][1], tl[t][3] - tl[t][2], tl[t][6] - tl[t][3], tl[t][4] - tl[t][6], tl[t][5] - tl[t][4]);
+    }
+#endif
     mbar_wait_lean(o_full(g), (ntiles - 1) & 1);
     tcgen05_fence_after();
-    add_ot();
-    if (row < a.nq) {
-      const float inv = 1.f / l;
-      __nv_bfloat16* og = a.o + (static_cast<long long>(b) * a.nq + row) * a.ldo + head * D + half * HC;
+    {
+      uint32_t lt;
+      uint32_t ob[HC];
+      tmem_ld_32x1(t_o + DO, lt);
 #pragma unroll
-      for (int c = 0; c < HC / 8; ++c) {
-        if (half * HC + c * 8 < D)
-          *reinterpret_cast<uint4*>(og + c * 8) =
-              make_uint4(pack_bf16(o_acc[c * 8] * inv, o_acc[c * 8 + 1] * inv), pack_bf16(o_acc[c * 8 + 2] * inv, o_acc[c * 8 + 3] * inv),
-                         pack_bf16(o_acc[c * 8 + 4] * inv, o_acc[c * 8 + 5] * inv), pack_bf16(o_acc[c * 8 + 6] * inv, o_acc[c * 8 + 7] * inv));
+      for (int c = 0; c < HC / 8; ++c) tmem_ld_32x8(t_o + half * HC + c * 8, *reinterpret_cast<uint32_t(*)[8]>(&ob[c * 8]));
+      tmem_ld_wait();
+      if (row < a.nq) {
+        const float inv = 1.f / __uint_as_float(lt);
+        __nv_bfloat16* og = a.o + (static_cast<long long>(b) * a.nq + row) * a.ldo + head * D + half * HC;
+#pragma unroll
+        for (int c = 0; c < HC / 8; ++c) {
+          if (half * HC + c * 8 < D) {
+            const uint32_t* t = &ob[c * 8];
+            *reinterpret_cast<uint4*>(og + c * 8) =
+                make_uint4(pack_bf16(__uint_as_float(t[0]) * inv, __uint_as_float(t[1]) * inv), pack_bf16(__uint_as_float(t[2]) * inv, __uint_as_float(t[3]) * inv),
+                           pack_bf16(__uint_as_float(t[4]) * inv, __uint_as_float(t[5]) * inv), pack_bf16(__uint_as_float(t[6]) * inv, __uint_as_float(t[7]) * inv));
+          }
+        }
       }
     }
   }

@@ -223,15 +223,26 @@ int launch_attention_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, 
     static const bool split = !(getenv("MRISR_ATTN_NOSPLIT") != nullptr && getenv("MRISR_ATTN_NOSPLIT")[0] == '1');
     if (split) {
       using SCfg = mrisr::AttnSplitCfg<D>;
-      static bool configured2 = false;
-      if (!configured2) {
-        MRISR_CHECK_CUDA(cudaFuncSetAttribute(mrisr::attention_tcgen05_split_kernel<D>,
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, SCfg::kSmemBytes));
-        configured2 = true;
+      // MRISR_ATTN_POLY = number of every 8 element pairs whose 2^x runs on the FMA pipe (tuning runs; default 3)
+      static const int poly = getenv("MRISR_ATTN_POLY") ? atoi(getenv("MRISR_ATTN_POLY")) : 3;
+      static bool configured2[8] = {false, false, false, false, false, false, false, false};
+      auto launch = [&](auto kern) -> int {
+        if (!configured2[poly & 7]) {
+          MRISR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SCfg::kSmemBytes));
+          configured2[poly & 7] = true;
+        }
+        kern<<<grid, mrisr::kAtsThreads, SCfg::kSmemBytes, st>>>(mk, mv, a);
+        MRISR_CHECK_CUDA(cudaGetLastError());
+        return 0;
+      };
+      switch (poly) {
+        case 0: return launch(mrisr::attention_tcgen05_split_kernel<D, 0>);
+        case 1: return launch(mrisr::attention_tcgen05_split_kernel<D, 1>);
+        case 2: return launch(mrisr::attention_tcgen05_split_kernel<D, 2>);
+        case 4: return launch(mrisr::attention_tcgen05_split_kernel<D, 4>);
+        case 5: return launch(mrisr::attention_tcgen05_split_kernel<D, 5>);
+        default: return launch(mrisr::attention_tcgen05_split_kernel<D, 3>);
       }
-      mrisr::attention_tcgen05_split_kernel<D><<<grid, mrisr::kAtsThreads, SCfg::kSmemBytes, st>>>(mk, mv, a);
-      MRISR_CHECK_CUDA(cudaGetLastError());
-      return 0;
     }
   }
   mrisr::attention_tcgen05_kernel<D><<<grid, mrisr::kAtcThreads, Cfg::kSmemBytes, st>>>(mk, mv, a);
