@@ -87,6 +87,8 @@ __device__ __forceinline__ void attn_load_tile(uint32_t sdst, const __nv_bfloat1
 
 template <int D>
 __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const AttnArgs a) {
+  grid_dep_launch();
+  grid_dep_wait();
   using Cfg = AttnCfg<D>;
   constexpr int DP = Cfg::DP, LDS = Cfg::LDS;
   constexpr int KQ = DP / 16;  // k16 steps of Q K^T
@@ -246,6 +248,8 @@ struct AttnCtxCfg {
 
 template <int D, int NKP>
 __global__ void __launch_bounds__(kCtxThreads, (D <= 80 && NKP <= 80) ? 4 : 2) attention_ctx_kernel(const AttnArgs a, int q_tiles) {
+  grid_dep_launch();
+  grid_dep_wait();
   using Cfg = AttnCtxCfg<D, NKP>;
   constexpr int DP = Cfg::DP, LDS = Cfg::LDS;
   constexpr int KQ = DP / 16;   // k16 steps of Q K^T

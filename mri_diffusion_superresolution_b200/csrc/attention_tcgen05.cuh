@@ -157,6 +157,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_c
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
+  grid_dep_launch();
+  grid_dep_wait();  // Q / K / V are the previous kernel's output
 
   // ---- stage both query tiles: [256 rows x D] -> swizzled atoms, zero-padded (rows >= nq, columns >= D)
   {
@@ -463,6 +465,8 @@ attention_tcgen05_split_kernel(const __grid_constant__ CUtensorMap tmK, const __
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
+  grid_dep_launch();
+  grid_dep_wait();  // Q / K / V are the previous kernel's output
   {  // stage both query tiles (zero-padded, hand-swizzled) and the all-ones tile
     const __nv_bfloat16* qg = a.q + (static_cast<long long>(b) * a.nq) * a.ldq + head * D;
     for (int i = threadIdx.x; i < kAtcBQ * 8; i += kAtsThreads) {

@@ -368,6 +368,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
   const int worker = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int num_workers = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
+  grid_dep_launch();  // PDL: the next kernel may start its prologue while this grid drains
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.a1);
     tma_prefetch_desc(&maps.a2);
@@ -412,6 +413,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
     // The whole warp walks the loop (warp-uniform control flow keeps descriptors / coordinates in uniform registers: a
     // single divergent thread makes ptxas wrap every UTMALDG / UTCHMMA in an ELECT + R2UR waterfall loop); one elected
     // lane issues.
+    grid_dep_wait();  // operands may be the previous kernel's output
     int stage = 0;
     uint32_t phase = 0;
     auto load = [&](const CUtensorMap* ma, bool conv, int c0, int ds, int hh, int bb, int m0, const CUtensorMap* mb, int kb, int nb) {
@@ -513,6 +515,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
     uint8_t* stage_buf = sepi_base + (warp - 4) * 4096;
     uint32_t buf_sel = 0;
     uint32_t it = 0;
+    grid_dep_wait();  // the previous kernel may still read the buffer this one overwrites
     for (int tile = worker; tile < total_tiles; tile += num_workers, ++it) {
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
       const int n_blk = tile % p.n_tiles;

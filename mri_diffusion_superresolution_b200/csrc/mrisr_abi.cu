@@ -63,6 +63,30 @@ inline int grid_for(long long work_items, int threads, int per_sm = 8) {
   return static_cast<int>(blocks);
 }
 
+// ---- Every kernel is launched with programmatic dependent launch (PDL): it may become resident while its predecessor in
+// the stream (or captured graph) is still draining, runs its prologue (barrier init, TMEM allocation, descriptor
+// prefetch), and executes griddepcontrol.wait before its first global-memory access.  MRISR_NO_PDL=1 turns the
+// attribute off (A/B runs); griddepcontrol.* are then no-ops.
+bool use_pdl() {
+  static int v = -1;
+  if (v < 0) v = getenv("MRISR_NO_PDL") != nullptr ? 0 : 1;
+  return v == 1;
+}
+template <typename... KArgs, typename... Args>
+void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);  // errors surface through cudaGetLastError at the call site
+}
+
 // ---- TMA descriptor encoding through the driver entry point (no link-time libcuda dependency)
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 int load_encode() {
@@ -115,13 +139,15 @@ int launch_gemm(const mrisr::GemmMaps& maps, const mrisr::GemmKernelParams& p, c
   cfg.blockDim = dim3(mrisr::kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kPair ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = use_pdl() ? 2 : 1;
   MRISR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mrisr::gemm_tcgen05_kernel<BN, kPair>, maps, p));
   return 0;
 }
@@ -157,7 +183,7 @@ int launch_attention(const mrisr::AttnArgs& a, cudaStream_t st) {
     configured = true;
   }
   dim3 grid((a.nq + mrisr::kAttnBM - 1) / mrisr::kAttnBM, a.heads, a.batch);
-  mrisr::attention_kernel<D><<<grid, mrisr::kAttnThreads, Cfg::kSmemBytes, st>>>(a);
+  launch_k(mrisr::attention_kernel<D>, dim3(grid), dim3(mrisr::kAttnThreads), Cfg::kSmemBytes, st, a);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -176,7 +202,7 @@ int launch_attention_ctx(const mrisr::AttnArgs& a, cudaStream_t st) {
   const int q_tiles = a.nq >= 2048 ? 4 : a.nq >= 512 ? 2 : 1;
   const int rows_per_cta = mrisr::kCtxBM * q_tiles;
   dim3 grid((a.nq + rows_per_cta - 1) / rows_per_cta, a.heads, a.batch);
-  mrisr::attention_ctx_kernel<D, NKP><<<grid, mrisr::kCtxThreads, Cfg::kSmemBytes, st>>>(a, q_tiles);
+  launch_k(mrisr::attention_ctx_kernel<D, NKP>, dim3(grid), dim3(mrisr::kCtxThreads), Cfg::kSmemBytes, st, a, q_tiles);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -231,7 +257,7 @@ int launch_attention_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, 
           MRISR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SCfg::kSmemBytes));
           configured2[poly & 7] = true;
         }
-        kern<<<grid, mrisr::kAtsThreads, SCfg::kSmemBytes, st>>>(mk, mv, a);
+        launch_k(kern, dim3(grid), dim3(mrisr::kAtsThreads), SCfg::kSmemBytes, st, mk, mv, a);
         MRISR_CHECK_CUDA(cudaGetLastError());
         return 0;
       };
@@ -245,7 +271,7 @@ int launch_attention_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, 
       }
     }
   }
-  mrisr::attention_tcgen05_kernel<D><<<grid, mrisr::kAtcThreads, Cfg::kSmemBytes, st>>>(mk, mv, a);
+  launch_k(mrisr::attention_tcgen05_kernel<D>, dim3(grid), dim3(mrisr::kAtcThreads), Cfg::kSmemBytes, st, mk, mv, a);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -263,8 +289,7 @@ template <int VPL>
 int launch_layernorm(const void* x, int64_t ldx, const float* g, const float* b, float eps, void* out, int64_t ldo, int rows,
                      int C, cudaStream_t st) {
   const int wpb = 8;
-  mrisr::layernorm_kernel<VPL><<<(rows + wpb - 1) / wpb, wpb * 32, 0, st>>>(
-      static_cast<const __nv_bfloat16*>(x), ldx, g, b, eps, static_cast<__nv_bfloat16*>(out), ldo, rows, C);
+  launch_k(mrisr::layernorm_kernel<VPL>, dim3((rows + wpb - 1) / wpb), dim3(wpb * 32), 0, st, static_cast<const __nv_bfloat16*>(x), ldx, g, b, eps, static_cast<__nv_bfloat16*>(out), ldo, rows, C);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -297,8 +322,7 @@ int mrisr_sched_step(const float* x, const float* eps, const float* lr, const fl
                 "sched_step: pointers must be 16-byte aligned");
   if (n == 0) return 0;
   const long long n4 = n / 4;
-  mrisr::sched_step_kernel<<<grid_for(n4, 256, 8), 256, 0, as_stream(stream)>>>(
-      reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(eps), reinterpret_cast<const float4*>(lr),
+  launch_k(mrisr::sched_step_kernel, dim3(grid_for(n4, 256, 8)), dim3(256), 0, as_stream(stream), reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(eps), reinterpret_cast<const float4*>(lr),
       reinterpret_cast<const float4*>(z), reinterpret_cast<float4*>(out), n4, coef);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -312,8 +336,7 @@ int mrisr_res_shift(const float* hr, const float* lr, const float* noise, float*
   MRISR_REQUIRE(aligned16(hr) && aligned16(lr) && aligned16(noise) && aligned16(out), "res_shift: misaligned pointer");
   if (batch == 0 || n_per_sample == 0) return 0;
   const long long n4 = n_per_sample / 4;
-  mrisr::res_shift_kernel<<<grid_for(n4 * batch, 256, 8), 256, 0, as_stream(stream)>>>(
-      reinterpret_cast<const float4*>(hr), reinterpret_cast<const float4*>(lr), reinterpret_cast<const float4*>(noise),
+  launch_k(mrisr::res_shift_kernel, dim3(grid_for(n4 * batch, 256, 8)), dim3(256), 0, as_stream(stream), reinterpret_cast<const float4*>(hr), reinterpret_cast<const float4*>(lr), reinterpret_cast<const float4*>(noise),
       reinterpret_cast<float4*>(out), n4, batch, sqrt_table, table_len, reinterpret_cast<const long long*>(timesteps),
       t_count);
   MRISR_CHECK_CUDA(cudaGetLastError());
@@ -328,8 +351,7 @@ int mrisr_sched_step_indexed(const float* x, const float* eps, const float* lr, 
                 "sched_step_indexed: pointers must be 16-byte aligned");
   if (n == 0) return 0;
   const long long n4 = n / 4;
-  mrisr::sched_step_indexed_kernel<<<grid_for(n4, 256, 8), 256, 0, as_stream(stream)>>>(
-      reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(eps), reinterpret_cast<const float4*>(lr),
+  launch_k(mrisr::sched_step_indexed_kernel, dim3(grid_for(n4, 256, 8)), dim3(256), 0, as_stream(stream), reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(eps), reinterpret_cast<const float4*>(lr),
       reinterpret_cast<const float4*>(z_table), z_stride / 4, reinterpret_cast<float4*>(out), n4, coef_table, idx);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -338,14 +360,14 @@ int mrisr_sched_step_indexed(const float* x, const float* eps, const float* lr, 
 int mrisr_select_row(const float* table, const int* idx, int64_t stride, float* dst, int n, void* stream) {
   MRISR_REQUIRE(table && idx && dst && n >= 0, "select_row: bad argument");
   if (n == 0) return 0;
-  mrisr::select_row_kernel<<<grid_for(n, 256, 2), 256, 0, as_stream(stream)>>>(table, idx, stride, dst, n);
+  launch_k(mrisr::select_row_kernel, dim3(grid_for(n, 256, 2)), dim3(256), 0, as_stream(stream), table, idx, stride, dst, n);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int mrisr_advance_index(int* idx, void* stream) {
   MRISR_REQUIRE(idx, "advance_index: null pointer");
-  mrisr::advance_index_kernel<<<1, 32, 0, as_stream(stream)>>>(idx);
+  launch_k(mrisr::advance_index_kernel, dim3(1), dim3(32), 0, as_stream(stream), idx);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -353,8 +375,7 @@ int mrisr_advance_index(int* idx, void* stream) {
 int mrisr_timestep_embedding(const float* t, void* out, int batch, int dim, void* stream) {
   MRISR_REQUIRE(t && out && batch > 0 && dim > 0 && dim % 2 == 0, "timestep_embedding: bad argument");
   const int n = batch * (dim / 2);
-  mrisr::timestep_embedding_kernel<<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(
-      t, static_cast<__nv_bfloat16*>(out), batch, dim);
+  launch_k(mrisr::timestep_embedding_kernel, dim3((n + 127) / 128), dim3(128), 0, as_stream(stream), t, static_cast<__nv_bfloat16*>(out), batch, dim);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -393,10 +414,9 @@ int mrisr_groupnorm(const void* x1, int64_t ld1, int c1, const void* x2, int64_t
   a.nslab = nslab; a.pix_per_slab = pps;
   dim3 block(nvec, R), grid(nslab, batch);
   cudaStream_t st = as_stream(stream);
-  mrisr::groupnorm_stats_kernel<<<grid, block, 2 * R * C * sizeof(float), st>>>(a, reinterpret_cast<float2*>(workspace));
+  launch_k(mrisr::groupnorm_stats_kernel, dim3(grid), dim3(block), 2 * R * C * sizeof(float), st, a, reinterpret_cast<float2*>(workspace));
   MRISR_CHECK_CUDA(cudaGetLastError());
-  mrisr::groupnorm_apply_kernel<<<grid, block, 2 * C * sizeof(float), st>>>(
-      a, reinterpret_cast<const float2*>(workspace), gamma, beta, eps, silu, static_cast<__nv_bfloat16*>(out), nslab);
+  launch_k(mrisr::groupnorm_apply_kernel, dim3(grid), dim3(block), 2 * C * sizeof(float), st, a, reinterpret_cast<const float2*>(workspace), gamma, beta, eps, silu, static_cast<__nv_bfloat16*>(out), nslab);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -632,8 +652,7 @@ int mrisr_upsample2x(const void* in, void* out, int B, int H, int W, int C, void
   MRISR_REQUIRE(in && out && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "upsample2x: bad argument");
   MRISR_REQUIRE(aligned16(in) && aligned16(out), "upsample2x: misaligned pointer");
   const long long n = static_cast<long long>(B) * H * W * (C / 8);
-  mrisr::upsample2x_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(
-      static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H, W, C / 8);
+  launch_k(mrisr::upsample2x_kernel, dim3(grid_for(n, 256, 8)), dim3(256), 0, as_stream(stream), static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H, W, C / 8);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -642,8 +661,7 @@ int mrisr_im2col3x3s2(const void* in, void* out, int B, int H, int W, int C, voi
   MRISR_REQUIRE(in && out && B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 8 == 0, "im2col3x3s2: bad argument");
   MRISR_REQUIRE(aligned16(in) && aligned16(out), "im2col3x3s2: misaligned pointer");
   const long long n = static_cast<long long>(B) * (H / 2) * (W / 2) * 9 * (C / 8);
-  mrisr::im2col3x3s2_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(
-      static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H, W, C / 8);
+  launch_k(mrisr::im2col3x3s2_kernel, dim3(grid_for(n, 256, 8)), dim3(256), 0, as_stream(stream), static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H, W, C / 8);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -651,7 +669,7 @@ int mrisr_im2col3x3s2(const void* in, void* out, int B, int H, int W, int C, voi
 int mrisr_im2col_first(const float* in, void* out, int B, int Cin, int H, int W, int kpad, void* stream) {
   MRISR_REQUIRE(in && out && B > 0 && Cin > 0 && H > 0 && W > 0 && kpad >= 9 * Cin && kpad % 64 == 0, "im2col_first: bad argument");
   const long long n = static_cast<long long>(B) * H * W * kpad;
-  mrisr::im2col_first_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(in, static_cast<__nv_bfloat16*>(out), B, Cin, H, W, kpad);
+  launch_k(mrisr::im2col_first_kernel, dim3(grid_for(n, 256, 8)), dim3(256), 0, as_stream(stream), in, static_cast<__nv_bfloat16*>(out), B, Cin, H, W, kpad);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -659,7 +677,7 @@ int mrisr_im2col_first(const float* in, void* out, int B, int Cin, int H, int W,
 int mrisr_pixel_unshuffle_nhwc(const float* in, void* out, int B, int C, int Hin, int Win, int r, void* stream) {
   MRISR_REQUIRE(in && out && B > 0 && C > 0 && r > 0 && Hin % r == 0 && Win % r == 0, "pixel_unshuffle: bad argument");
   const long long n = static_cast<long long>(B) * C * Hin * Win;
-  mrisr::pixel_unshuffle_nhwc_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(in, static_cast<__nv_bfloat16*>(out), B, C, Hin, Win, r);
+  launch_k(mrisr::pixel_unshuffle_nhwc_kernel, dim3(grid_for(n, 256, 8)), dim3(256), 0, as_stream(stream), in, static_cast<__nv_bfloat16*>(out), B, C, Hin, Win, r);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -668,7 +686,7 @@ int mrisr_avgpool2(const void* in, void* out, int B, int H, int W, int C, void* 
   MRISR_REQUIRE(in && out && B > 0 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 8 == 0, "avgpool2: bad argument");
   MRISR_REQUIRE(aligned16(in) && aligned16(out), "avgpool2: misaligned pointer");
   const long long n = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 8);
-  mrisr::avgpool2_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H, W, C / 8);
+  launch_k(mrisr::avgpool2_kernel, dim3(grid_for(n, 256, 8)), dim3(256), 0, as_stream(stream), static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H, W, C / 8);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -677,8 +695,7 @@ int mrisr_add(const void* a, const void* b, void* out, int64_t n, void* stream) 
   MRISR_REQUIRE(a && b && out && n >= 0 && n % 8 == 0, "add: bad argument");
   MRISR_REQUIRE(aligned16(a) && aligned16(b) && aligned16(out), "add: misaligned pointer");
   if (n == 0) return 0;
-  mrisr::add_bf16_kernel<<<grid_for(n / 8, 256, 8), 256, 0, as_stream(stream)>>>(
-      static_cast<const uint4*>(a), static_cast<const uint4*>(b), static_cast<uint4*>(out), n / 8);
+  launch_k(mrisr::add_bf16_kernel, dim3(grid_for(n / 8, 256, 8)), dim3(256), 0, as_stream(stream), static_cast<const uint4*>(a), static_cast<const uint4*>(b), static_cast<uint4*>(out), n / 8);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -689,13 +706,13 @@ int mrisr_transpose(const void* src, int sdt, void* dst, int ddt, int B, int R, 
   dim3 block(32, 8), grid((Cc + 31) / 32, (R + 31) / 32, B);
   cudaStream_t st = as_stream(stream);
   if (sdt == 0 && ddt == 0)
-    mrisr::transpose_kernel<float, float><<<grid, block, 0, st>>>(static_cast<const float*>(src), static_cast<float*>(dst), R, Cc);
+    launch_k(mrisr::transpose_kernel<float, float>, dim3(grid), dim3(block), 0, st, static_cast<const float*>(src), static_cast<float*>(dst), R, Cc);
   else if (sdt == 0 && ddt == 1)
-    mrisr::transpose_kernel<float, __nv_bfloat16><<<grid, block, 0, st>>>(static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst), R, Cc);
+    launch_k(mrisr::transpose_kernel<float, __nv_bfloat16>, dim3(grid), dim3(block), 0, st, static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst), R, Cc);
   else if (sdt == 1 && ddt == 0)
-    mrisr::transpose_kernel<__nv_bfloat16, float><<<grid, block, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<float*>(dst), R, Cc);
+    launch_k(mrisr::transpose_kernel<__nv_bfloat16, float>, dim3(grid), dim3(block), 0, st, static_cast<const __nv_bfloat16*>(src), static_cast<float*>(dst), R, Cc);
   else
-    mrisr::transpose_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, block, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), R, Cc);
+    launch_k(mrisr::transpose_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(grid), dim3(block), 0, st, static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), R, Cc);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -705,9 +722,9 @@ int mrisr_cast(const void* src, int sdt, void* dst, int ddt, int64_t n, void* st
   if (n == 0) return 0;
   cudaStream_t st = as_stream(stream);
   if (sdt == 0 && ddt == 1)
-    mrisr::cast_f32_bf16_kernel<<<grid_for(n, 256, 8), 256, 0, st>>>(static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst), n);
+    launch_k(mrisr::cast_f32_bf16_kernel, dim3(grid_for(n, 256, 8)), dim3(256), 0, st, static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst), n);
   else if (sdt == 1 && ddt == 0)
-    mrisr::cast_bf16_f32_kernel<<<grid_for(n, 256, 8), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<float*>(dst), n);
+    launch_k(mrisr::cast_bf16_f32_kernel, dim3(grid_for(n, 256, 8)), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(src), static_cast<float*>(dst), n);
   else
     return fail(MRISR_E_INVALID, "cast: only fp32<->bf16 supported");
   MRISR_CHECK_CUDA(cudaGetLastError());
@@ -717,14 +734,14 @@ int mrisr_cast(const void* src, int sdt, void* dst, int ddt, int64_t n, void* st
 int mrisr_bilinear_resize(const float* in, float* out, int planes, int Hin, int Win, int Hout, int Wout, void* stream) {
   MRISR_REQUIRE(in && out && planes > 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0, "bilinear_resize: bad argument");
   const long long n = static_cast<long long>(planes) * Hout * Wout;
-  mrisr::bilinear_resize_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(in, out, planes, Hin, Win, Hout, Wout);
+  launch_k(mrisr::bilinear_resize_kernel, dim3(grid_for(n, 256, 8)), dim3(256), 0, as_stream(stream), in, out, planes, Hin, Win, Hout, Wout);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int mrisr_to_uint8_vis(const float* chw, uint8_t* out, int C, int H, int W, void* stream) {
   MRISR_REQUIRE(chw && out && (C == 1 || C == 3) && H > 0 && W > 0, "to_uint8_vis: C must be 1 or 3");
-  mrisr::to_uint8_vis_kernel<<<grid_for(static_cast<long long>(H) * W * 3, 256, 8), 256, 0, as_stream(stream)>>>(chw, out, C, H, W);
+  launch_k(mrisr::to_uint8_vis_kernel, dim3(grid_for(static_cast<long long>(H) * W * 3, 256, 8)), dim3(256), 0, as_stream(stream), chw, out, C, H, W);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

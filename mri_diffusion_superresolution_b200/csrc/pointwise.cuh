@@ -24,6 +24,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 __global__ void sched_step_kernel(const float4* __restrict__ x, const float4* __restrict__ eps,
                                   const float4* __restrict__ lr, const float4* __restrict__ z, float4* out,
                                   long long n4, const float* __restrict__ coef) {
+  grid_dep_launch();
+  grid_dep_wait();
   const float c1 = __ldg(coef), c2 = __ldg(coef + 1), c3 = __ldg(coef + 2), c4 = __ldg(coef + 3);
   const bool use_lr = lr != nullptr && c3 != 0.f;
   const bool use_z = z != nullptr && c4 != 0.f;
@@ -47,6 +49,8 @@ __global__ void sched_step_indexed_kernel(const float4* __restrict__ x, const fl
                                           const float4* __restrict__ lr, const float4* __restrict__ z_table,
                                           long long z_stride4, float4* out, long long n4,
                                           const float* __restrict__ coef_table, const int* __restrict__ idx) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int step = __ldg(idx);
   const float* coef = coef_table + 4 * step;
   const float c1 = __ldg(coef), c2 = __ldg(coef + 1), c3 = __ldg(coef + 2), c4 = __ldg(coef + 3);
@@ -79,6 +83,8 @@ __global__ void res_shift_kernel(const float4* __restrict__ hr, const float4* __
                                  const float4* __restrict__ noise, float4* __restrict__ out, long long n4_per_sample,
                                  int batch, const float* __restrict__ sqrt_table, int table_len,
                                  const long long* __restrict__ timesteps, int t_count) {
+  grid_dep_launch();
+  grid_dep_wait();
   const long long total = n4_per_sample * batch;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int b = static_cast<int>(i / n4_per_sample);
@@ -95,6 +101,8 @@ __global__ void res_shift_kernel(const float4* __restrict__ hr, const float4* __
 // Bilinear resize, align_corners=False, no antialias (F.interpolate semantics; reference res_srdiff.py:31-32).
 __global__ void bilinear_resize_kernel(const float* __restrict__ in, float* __restrict__ out, int planes, int Hin, int Win,
                                        int Hout, int Wout) {
+  grid_dep_launch();
+  grid_dep_wait();
   const float sh = static_cast<float>(Hin) / static_cast<float>(Hout);
   const float sw = static_cast<float>(Win) / static_cast<float>(Wout);
   const long long total = static_cast<long long>(planes) * Hout * Wout;
@@ -117,6 +125,8 @@ __global__ void bilinear_resize_kernel(const float* __restrict__ in, float* __re
 
 // decode_to_vis (reference res_srdiff.py:115-122): uint8(trunc(clamp(x/2 + 0.5, 0, 1) * 255)), CHW -> HW3.
 __global__ void to_uint8_vis_kernel(const float* __restrict__ chw, uint8_t* __restrict__ out, int C, int H, int W) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int total = H * W * 3;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int c = i % 3, p = i / 3;
@@ -131,6 +141,8 @@ __global__ void to_uint8_vis_kernel(const float* __restrict__ chw, uint8_t* __re
 // Sinusoidal timestep embedding, diffusers convention (flip_sin_to_cos, shift 0): [cos | sin], bf16 out.
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ out, int batch,
                                           int dim) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= batch * half) return;
@@ -162,6 +174,8 @@ __device__ __forceinline__ uint4 gn_load(const GnArgs& a, int b, int pix, int vx
 }
 
 __global__ void groupnorm_stats_kernel(GnArgs a, float2* __restrict__ partial /*[B, nslab, groups]*/) {
+  grid_dep_launch();
+  grid_dep_wait();
   extern __shared__ float gn_sh[];  // [2][R][C]: per-thread per-channel partial sums, reduced in a FIXED order below
   const int vx = threadIdx.x, ry = threadIdx.y, R = blockDim.y;
   const int b = blockIdx.y, slab = blockIdx.x;
@@ -214,6 +228,8 @@ __global__ void groupnorm_stats_kernel(GnArgs a, float2* __restrict__ partial /*
 __global__ void groupnorm_apply_kernel(GnArgs a, const float2* __restrict__ partial, const float* __restrict__ gamma,
                                        const float* __restrict__ beta, float eps, int silu,
                                        __nv_bfloat16* __restrict__ out /*[B,HW,c1+c2] dense*/, int stats_nslab) {
+  grid_dep_launch();
+  grid_dep_wait();
   extern __shared__ float s_aff[];  // scale[C], shift[C]
   __shared__ float s_mean[64], s_rstd[64];
   const int C = a.c1 + a.c2;
@@ -275,6 +291,8 @@ template <int VPL>  // 8-element vectors per lane (C <= 256 * VPL)
 __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ out,
                                  long long ldo, int rows, int C) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -328,6 +346,8 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long 
 // ---------------------------------------------------------------------------------------------------
 // Nearest 2x upsample, NHWC bf16: out[b, 2h+i, 2w+j, :] = in[b, h, w, :].
 __global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int nvec) {
+  grid_dep_launch();
+  grid_dep_wait();
   const long long total = static_cast<long long>(B) * H * W * nvec;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int v = static_cast<int>(i % nvec);
@@ -346,6 +366,8 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restric
 
 // 3x3 / stride 2 / pad 1 im2col, NHWC bf16 [B,H,W,C] -> [B*Ho*Wo, 9*C] with k = tap*C + c (tap = r*3 + s).
 __global__ void im2col3x3s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int nvec) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int Ho = H / 2, Wo = W / 2;
   const long long total = static_cast<long long>(B) * Ho * Wo * 9 * nvec;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -365,6 +387,8 @@ __global__ void im2col3x3s2_kernel(const uint4* __restrict__ in, uint4* __restri
 // conv_in im2col: NCHW fp32 [B,Cin,H,W] -> bf16 [B*H*W, kpad], k = tap*Cin + c (3x3, stride 1, pad 1), zero padded.
 __global__ void im2col_first_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int Cin, int H,
                                     int W, int kpad) {
+  grid_dep_launch();
+  grid_dep_wait();
   const long long total = static_cast<long long>(B) * H * W * kpad;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int k = static_cast<int>(i % kpad);
@@ -385,6 +409,8 @@ __global__ void im2col_first_kernel(const float* __restrict__ in, __nv_bfloat16*
 // PixelUnshuffle(r) + NCHW fp32 -> NHWC bf16: out[b, h, w, c*r*r + i*r + j] = in[b, c, h*r+i, w*r+j].
 __global__ void pixel_unshuffle_nhwc_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int C,
                                             int Hin, int Win, int r) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int Ho = Hin / r, Wo = Win / r, Co = C * r * r;
   const long long total = static_cast<long long>(B) * Ho * Wo * Co;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -404,6 +430,8 @@ __global__ void pixel_unshuffle_nhwc_kernel(const float* __restrict__ in, __nv_b
 // Tiled transpose between NCHW (fp32 or bf16) and NHWC (fp32 or bf16).  src viewed as [B, R, Cc] -> dst [B, Cc, R].
 template <typename TI, typename TO>
 __global__ void transpose_kernel(const TI* __restrict__ src, TO* __restrict__ dst, int R, int Cc) {
+  grid_dep_launch();
+  grid_dep_wait();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -422,6 +450,8 @@ __global__ void transpose_kernel(const TI* __restrict__ src, TO* __restrict__ ds
 
 // out = a + b (bf16, 8-wide); used for ControlNet-style additional residuals on stored skips.
 __global__ void add_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out, long long nvec) {
+  grid_dep_launch();
+  grid_dep_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     float x[8], y[8];
     unpack8(__ldg(a + i), x);
@@ -434,6 +464,8 @@ __global__ void add_bf16_kernel(const uint4* __restrict__ a, const uint4* __rest
 
 // 2x2 average pool, NHWC bf16 (Adapter_XL use_conv=False path, reference modules.py:70-72).
 __global__ void avgpool2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int nvec) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int Ho = H / 2, Wo = W / 2;
   const long long total = static_cast<long long>(B) * Ho * Wo * nvec;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -458,10 +490,14 @@ __global__ void avgpool2_kernel(const uint4* __restrict__ in, uint4* __restrict_
 
 // fp32 <-> bf16 casts.
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  grid_dep_launch();
+  grid_dep_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = __float2bfloat16(__ldg(in + i));
 }
 __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long n) {
+  grid_dep_launch();
+  grid_dep_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = __bfloat162float(in[i]);
 }
@@ -470,9 +506,13 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, float
 // coefficients) inside a replayed CUDA graph without host involvement; idx lives in device memory.
 __global__ void select_row_kernel(const float* __restrict__ table, const int* __restrict__ idx, long long stride,
                                   float* __restrict__ dst, int n) {
+  grid_dep_launch();
+  grid_dep_wait();
   const float* src = table + static_cast<long long>(__ldg(idx)) * stride;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = __ldg(src + i);
 }
-__global__ void advance_index_kernel(int* idx) { if (threadIdx.x == 0 && blockIdx.x == 0) *idx += 1; }
+__global__ void advance_index_kernel(int* idx) {
+  grid_dep_launch();
+  grid_dep_wait(); if (threadIdx.x == 0 && blockIdx.x == 0) *idx += 1; }
 
 }  // namespace mrisr

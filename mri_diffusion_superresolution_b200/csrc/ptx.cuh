@@ -22,6 +22,13 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// launch_dependents: the next kernel in the stream may start becoming resident (it still waits for THIS grid to complete
+// at its own grid_dep_wait).  grid_dep_wait: all prerequisite grids completed and their memory is visible; must precede
+// the first global-memory access of the executing thread.  Both are no-ops without the launch attribute.
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
