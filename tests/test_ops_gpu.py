@@ -108,6 +108,38 @@ def test_gemm_k_concat(ops):
     assert _rel(out, ref) < 4e-3
 
 
+@pytest.mark.parametrize("M,N,K,K2,two", [(4096, 320, 384, 0, False), (1000, 640, 640, 64, True), (300, 1280, 1280, 64, False),
+                                          (256, 64, 64, 0, True), (513, 960, 320, 0, False), (2048, 192, 128, 0, True),
+                                          (131, 2560, 192, 0, False)])
+def test_gemm_residual_as_operand(ops, M, N, K, K2, two):
+    """Activation-free GEMMs take their residuals as extra A operands against the identity weight tile (no epilogue
+    traffic): every N-tile width (64 / 128 / 160 / 192 / 256), tile origins that are not multiples of 64 (BN = 160),
+    ragged M, a strided residual view and the LoRA K-extension combined with two residuals."""
+    a = _bf((M, K), 40)
+    a2 = _bf((M, K2), 41) if K2 else None
+    w = _bf((N, K + K2), 42, 1.0 / math.sqrt(K + K2))
+    bias = _f32((N,), 43)
+    r1full = _bf((M, N + 64), 44)
+    r1 = r1full[:, :N]  # row pitch != N
+    r2 = _bf((M, N), 45) if two else None
+    out = ops.gemm(a, w, a2=a2, bias=bias, res1=r1, res2=r2)
+    x = a.float() if a2 is None else torch.cat([a.float(), a2.float()], 1)
+    ref = x @ w.float().t() + bias + r1.float() + (r2.float() if two else 0)
+    assert out.shape == (M, N)
+    assert _rel(out, ref) < 4e-3
+    only2 = ops.gemm(a, w, a2=a2, bias=bias, res2=r1)  # a lone res2 takes the first residual slot
+    assert torch.equal(only2, ops.gemm(a, w, a2=a2, bias=bias, res1=r1))
+
+
+def test_gemm_residual_is_exact(ops):
+    """The identity K-chunks add the bf16 residual exactly: with zero operands the output IS the residual, bit for bit."""
+    M, N, K = 1024, 320, 64
+    a = torch.zeros((M, K), dtype=torch.bfloat16, device="cuda")
+    w = _bf((N, K), 46)
+    r = _bf((M, N), 47, 50.0)
+    assert torch.equal(ops.gemm(a, w, res1=r), r)
+
+
 def test_gemm_rejects_bad_shapes(ops):
     a = _bf((128, 72), 19)
     w = _bf((64, 72), 20)
