@@ -288,8 +288,38 @@ bool use_tc_attention() {
 template <int VPL>
 int launch_layernorm(const void* x, int64_t ldx, const float* g, const float* b, float eps, void* out, int64_t ldo, int rows,
                      int C, cudaStream_t st) {
+  constexpr int kRows = VPL <= 2 ? 4 : 2;  // rows in flight per warp (register budget: ROWS * VPL uint4 + one unpacked row)
   const int wpb = 8;
-  launch_k(mrisr::layernorm_kernel<VPL>, dim3((rows + wpb - 1) / wpb), dim3(wpb * 32), 0, st, static_cast<const __nv_bfloat16*>(x), ldx, g, b, eps, static_cast<__nv_bfloat16*>(out), ldo, rows, C);
+  const long long need = (static_cast<long long>(rows) + wpb * kRows - 1) / (wpb * kRows);
+  static int per_sm = 0;  // persistent grid = what is actually resident (registers decide: 2-8 CTAs of 256 threads)
+  if (per_sm == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mrisr::layernorm_kernel<VPL, kRows>, wpb * 32, 2048 * 8) != cudaSuccess || n < 1) n = 2;
+    per_sm = n;
+  }
+  const long long cap = static_cast<long long>(sm_count()) * per_sm;
+  const int grid = static_cast<int>(need < cap ? (need > 0 ? need : 1) : cap);
+  launch_k(mrisr::layernorm_kernel<VPL, kRows>, dim3(grid), dim3(wpb * 32), static_cast<size_t>(C) * 8, st,
+           static_cast<const __nv_bfloat16*>(x), ldx, g, b, eps, static_cast<__nv_bfloat16*>(out), ldo, rows, C);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int LPR, int VPL>
+int launch_layernorm_group(const void* x, int64_t ldx, const float* g, const float* b, float eps, void* out, int64_t ldo,
+                           int rows, cudaStream_t st) {
+  constexpr int kRowsPerCta = 8 * (32 / LPR) * 2;
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mrisr::layernorm_group_kernel<LPR, VPL>, 256, LPR * VPL * 64) != cudaSuccess || n < 1) n = 2;
+    per_sm = n;
+  }
+  const long long need = (static_cast<long long>(rows) + kRowsPerCta - 1) / kRowsPerCta;
+  const long long cap = static_cast<long long>(sm_count()) * per_sm;
+  const int grid = static_cast<int>(need < cap ? (need > 0 ? need : 1) : cap);
+  launch_k(mrisr::layernorm_group_kernel<LPR, VPL>, dim3(grid), dim3(256), static_cast<size_t>(LPR * VPL) * 64, st,
+           static_cast<const __nv_bfloat16*>(x), ldx, g, b, eps, static_cast<__nv_bfloat16*>(out), ldo, rows);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -429,6 +459,10 @@ int mrisr_layernorm(const void* x, int64_t ldx, const float* gamma, const float*
   if (rows == 0) return 0;
   const int vpl = (C / 8 + 31) / 32;
   cudaStream_t st = as_stream(stream);
+  // the UNet's widths map exactly onto lane groups (every lane busy, 5 vectors each)
+  if (C == 320) return launch_layernorm_group<8, 5>(x, ldx, gamma, beta, eps, out, ldo, rows, st);
+  if (C == 640) return launch_layernorm_group<16, 5>(x, ldx, gamma, beta, eps, out, ldo, rows, st);
+  if (C == 1280) return launch_layernorm_group<32, 5>(x, ldx, gamma, beta, eps, out, ldo, rows, st);
   switch (vpl) {
     case 1: return launch_layernorm<1>(x, ldx, gamma, beta, eps, out, ldo, rows, C, st);
     case 2: return launch_layernorm<2>(x, ldx, gamma, beta, eps, out, ldo, rows, C, st);

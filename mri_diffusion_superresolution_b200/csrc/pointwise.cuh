@@ -17,6 +17,25 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
 }
 
+// packed-pair variants (Blackwell f32x2 arithmetic: one issue slot per two elements).  At 6.5 TB/s a bf16 stream delivers
+// ~11 elements per clock per SM against 128 thread-instruction issue slots: elementwise kernels that spend more than
+// ~11 instructions per element are ISSUE-bound, not HBM-bound, so the norm kernels count instructions.
+__device__ __forceinline__ void unpack8p(const uint4& x, float2 (&f)[4]) {
+  f[0] = make_float2(bf16_lo(x.x), bf16_hi(x.x)); f[1] = make_float2(bf16_lo(x.y), bf16_hi(x.y));
+  f[2] = make_float2(bf16_lo(x.z), bf16_hi(x.z)); f[3] = make_float2(bf16_lo(x.w), bf16_hi(x.w));
+}
+__device__ __forceinline__ uint4 pack8p(const float2 (&f)[4]) {
+  return make_uint4(pack_bf16(f[0].x, f[0].y), pack_bf16(f[1].x, f[1].y), pack_bf16(f[2].x, f[2].y), pack_bf16(f[3].x, f[3].y));
+}
+// SiLU with ONE MUFU op: y * sigmoid(y) = h + h * tanh(h), h = y / 2 (exp + reciprocal would be two MUFU ops per element,
+// i.e. 23 per clock per SM at the HBM rate against the 16 the XU pipe delivers).  tanh.approx: |rel err| ~ 2^-11.
+__device__ __forceinline__ float silu_tanh(float y) {
+  const float h = 0.5f * y;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Scheduler step (reference src/adapters/res_srdiff.py:84-96):
 //   x' = c1*x + c2*eps + c3*lr + c4*z      coef = {c1,c2,c3,c4} read from device memory (graph-replayable)
@@ -237,18 +256,31 @@ __global__ void groupnorm_apply_kernel(GnArgs a, const float2* __restrict__ part
   const int b = blockIdx.y, slab = blockIdx.x;
   const int tid = ry * blockDim.x + vx, nthr = blockDim.x * blockDim.y;
   const int cpg = C / a.groups;
-  if (tid < a.groups) {
+  // combine the per-slab partials: (group, part) pairs spread over the CTA, each sums every 8th slab, then one thread
+  // per group adds the 8 parts -- all in a fixed order (deterministic); a single thread per group walking all slabs
+  // serially cost ~2 us per CTA
+  __shared__ double s_part[64 * 8 * 2];
+  for (int idx = tid; idx < a.groups * 8; idx += nthr) {
+    const int g = idx >> 3, part = idx & 7;
     double su = 0.0, sq = 0.0;
-    for (int k = 0; k < stats_nslab; ++k) {
-      const float2 v = __ldg(partial + (static_cast<long long>(b) * stats_nslab + k) * a.groups + tid);
+    for (int k = part; k < stats_nslab; k += 8) {
+      const float2 v = __ldg(partial + (static_cast<long long>(b) * stats_nslab + k) * a.groups + g);
       su += v.x; sq += v.y;
     }
+    s_part[idx * 2] = su;
+    s_part[idx * 2 + 1] = sq;
+  }
+  __syncthreads();
+  for (int g = tid; g < a.groups; g += nthr) {
+    double su = 0.0, sq = 0.0;
+#pragma unroll
+    for (int part = 0; part < 8; ++part) { su += s_part[(g * 8 + part) * 2]; sq += s_part[(g * 8 + part) * 2 + 1]; }
     const double n = static_cast<double>(a.hw) * cpg;
     const double mean = su / n;
     double var = sq / n - mean * mean;
     if (var < 0.0) var = 0.0;
-    s_mean[tid] = static_cast<float>(mean);
-    s_rstd[tid] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    s_mean[g] = static_cast<float>(mean);
+    s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
   }
   __syncthreads();
   for (int c = tid; c < C; c += nthr) {
@@ -258,21 +290,23 @@ __global__ void groupnorm_apply_kernel(GnArgs a, const float2* __restrict__ part
     s_aff[C + c] = __ldg(beta + c) - s_mean[g] * sc;
   }
   __syncthreads();
-  float sc[8], sh[8];
+  float2 sc[4], sh[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { sc[j] = s_aff[vx * 8 + j]; sh[j] = s_aff[C + vx * 8 + j]; }
+  for (int j = 0; j < 4; ++j) {
+    sc[j] = make_float2(s_aff[vx * 8 + 2 * j], s_aff[vx * 8 + 2 * j + 1]);
+    sh[j] = make_float2(s_aff[C + vx * 8 + 2 * j], s_aff[C + vx * 8 + 2 * j + 1]);
+  }
   const int p0 = slab * a.pix_per_slab;
   const int p1 = min(a.hw, p0 + a.pix_per_slab);
   auto emit = [&](int pix, const uint4& v) {
-    float f[8];
-    unpack8(v, f);
+    float2 f[4];
+    unpack8p(v, f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float y = f[j] * sc[j] + sh[j];
-      if (silu) y = __fdividef(y, 1.f + __expf(-y));
-      f[j] = y;
+    for (int j = 0; j < 4; ++j) {
+      f[j] = __ffma2_rn(f[j], sc[j], sh[j]);
+      if (silu) { f[j].x = silu_tanh(f[j].x); f[j].y = silu_tanh(f[j].y); }
     }
-    reinterpret_cast<uint4*>(out + (static_cast<long long>(b) * a.hw + pix) * C)[vx] = pack8(f);
+    reinterpret_cast<uint4*>(out + (static_cast<long long>(b) * a.hw + pix) * C)[vx] = pack8p(f);
   };
   int pix = p0 + ry;
   for (; pix + 3 * R < p1; pix += 4 * R) {  // 4 independent 16-byte loads in flight per thread
@@ -286,59 +320,170 @@ __global__ void groupnorm_apply_kernel(GnArgs a, const float2* __restrict__ part
 }
 
 // ---------------------------------------------------------------------------------------------------
-// LayerNorm over the last dim of a bf16 [rows, C] matrix, one warp per row, row held in registers.
-template <int VPL>  // 8-element vectors per lane (C <= 256 * VPL)
-__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ out,
-                                 long long ldo, int rows, int C) {
+// LayerNorm over the last dim of a bf16 [rows, C] matrix.  Persistent CTAs (grid ~ resident capacity), one warp per
+// row, kLnRows rows of a warp IN FLIGHT at once (all their 16-byte loads are issued before the first reduction: a
+// single 640-byte row per warp left ~40 KB per SM in flight and the kernel at half the HBM rate), gamma / beta staged
+// in shared memory once per CTA as float4 pairs.  Two-pass (mean, then centred second moment) on the registers.
+template <int VPL, int ROWS>  // 8-element vectors per lane (C <= 256 * VPL), rows in flight per warp
+__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        float eps, __nv_bfloat16* __restrict__ out, long long ldo, int rows,
+                                                        int C) {
+  extern __shared__ float4 ln_sh[];  // [2 * nvec] gamma pairs, then [2 * nvec] beta pairs
   grid_dep_launch();
-  grid_dep_wait();
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= rows) return;
   const int nvec = C >> 3;
-  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<long long>(warp) * ldx);
-  float f[VPL][8];
-  float s = 0.f;
+  for (int i = threadIdx.x; i < 2 * nvec; i += blockDim.x) {  // parameters: not produced by the previous kernel
+    ln_sh[i] = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+    ln_sh[2 * nvec + i] = __ldg(reinterpret_cast<const float4*>(beta) + i);
+  }
+  __syncthreads();
+  grid_dep_wait();
+  const int lane = threadIdx.x & 31;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const float inv_c = 1.f / static_cast<float>(C);
+  for (int base = warp0; base < rows; base += warps_total * ROWS) {
+    uint4 raw[ROWS][VPL];
 #pragma unroll
-  for (int k = 0; k < VPL; ++k) {
-    const int v = lane + 32 * k;
-    if (v < nvec) {
-      unpack8(__ldg(xr + v), f[k]);
+    for (int r = 0; r < ROWS; ++r) {
+      const int row = base + r * warps_total;
+      const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<long long>(row) * ldx);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s += f[k][j];
+      for (int k = 0; k < VPL; ++k) {
+        const int v = lane + 32 * k;
+        raw[r][k] = (row < rows && v < nvec) ? __ldg(xr + v) : make_uint4(0, 0, 0, 0);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const int row = base + r * warps_total;
+      if (row >= rows) break;  // warp-uniform
+      float2 f[VPL][4];
+      float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        unpack8p(raw[r][k], f[k]);  // lanes beyond nvec hold zeros: they add nothing to the sum
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s2 = __fadd2_rn(s2, f[k][j]);
+      }
+      float s = s2.x + s2.y;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s * inv_c;
+      const float2 nmean = make_float2(-mean, -mean);
+      float2 q2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        if (lane + 32 * k < nvec) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            f[k][j] = __fadd2_rn(f[k][j], nmean);  // centred values are kept for the normalisation
+            q2 = __ffma2_rn(f[k][j], f[k][j], q2);
+          }
+        }
+      }
+      float q = q2.x + q2.y;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = rsqrtf(q * inv_c + eps);
+      const float2 rstd2 = make_float2(rstd, rstd);
+      uint4* orow = reinterpret_cast<uint4*>(out + static_cast<long long>(row) * ldo);
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int v = lane + 32 * k;
+        if (v < nvec) {
+          const float4 g0 = ln_sh[2 * v], g1 = ln_sh[2 * v + 1];
+          const float4 b0 = ln_sh[2 * nvec + 2 * v], b1 = ln_sh[2 * nvec + 2 * v + 1];
+          float2 y[4];
+          y[0] = __ffma2_rn(f[k][0], __fmul2_rn(rstd2, make_float2(g0.x, g0.y)), make_float2(b0.x, b0.y));
+          y[1] = __ffma2_rn(f[k][1], __fmul2_rn(rstd2, make_float2(g0.z, g0.w)), make_float2(b0.z, b0.w));
+          y[2] = __ffma2_rn(f[k][2], __fmul2_rn(rstd2, make_float2(g1.x, g1.y)), make_float2(b1.x, b1.y));
+          y[3] = __ffma2_rn(f[k][3], __fmul2_rn(rstd2, make_float2(g1.z, g1.w)), make_float2(b1.z, b1.w));
+          orow[v] = pack8p(y);
+        }
+      }
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / static_cast<float>(C);
-  float q = 0.f;
-#pragma unroll
-  for (int k = 0; k < VPL; ++k) {
-    const int v = lane + 32 * k;
-    if (v < nvec) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { const float d = f[k][j] - mean; q += d * d; }
-    }
+}
+
+// Lane-group variant for C = 8 * LPR * VPL: LPR lanes own one row (VPL 16-byte vectors per lane, every lane busy: the
+// warp-per-row mapping leaves 24 of 32 lanes idle on the second vector of a 320-channel row), so a warp normalises 32 / LPR
+// rows at once with log2(LPR) shuffle steps, and two such row groups are in flight per warp.
+template <int LPR, int VPL>
+__global__ void __launch_bounds__(256) layernorm_group_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              float eps, __nv_bfloat16* __restrict__ out, long long ldo,
+                                                              int rows) {
+  constexpr int RPW = 32 / LPR;     // rows per warp per pass
+  constexpr int NVEC = LPR * VPL;   // 16-byte vectors per row
+  constexpr int UNROLL = 2;
+  extern __shared__ float4 ln_sh[];  // [2 * NVEC] gamma pairs, then [2 * NVEC] beta pairs
+  grid_dep_launch();
+  for (int i = threadIdx.x; i < 2 * NVEC; i += blockDim.x) {
+    ln_sh[i] = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+    ln_sh[2 * NVEC + i] = __ldg(reinterpret_cast<const float4*>(beta) + i);
   }
+  __syncthreads();
+  grid_dep_wait();
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, j0 = lane % LPR;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  constexpr float inv_c = 1.f / static_cast<float>(NVEC * 8);
+  for (long long base = static_cast<long long>(warp0) * RPW; base < rows; base += static_cast<long long>(warps_total) * RPW * UNROLL) {
+    uint4 raw[UNROLL][VPL];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q / static_cast<float>(C) + eps);
-  uint4* orow = reinterpret_cast<uint4*>(out + static_cast<long long>(warp) * ldo);
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long row = base + static_cast<long long>(u) * warps_total * RPW + sub;
+      const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
 #pragma unroll
-  for (int k = 0; k < VPL; ++k) {
-    const int v = lane + 32 * k;
-    if (v < nvec) {
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v);
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v + 1);
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * v);
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * v + 1);
-      float y[8];
-      y[0] = (f[k][0] - mean) * rstd * g0.x + b0.x; y[1] = (f[k][1] - mean) * rstd * g0.y + b0.y;
-      y[2] = (f[k][2] - mean) * rstd * g0.z + b0.z; y[3] = (f[k][3] - mean) * rstd * g0.w + b0.w;
-      y[4] = (f[k][4] - mean) * rstd * g1.x + b1.x; y[5] = (f[k][5] - mean) * rstd * g1.y + b1.y;
-      y[6] = (f[k][6] - mean) * rstd * g1.z + b1.z; y[7] = (f[k][7] - mean) * rstd * g1.w + b1.w;
-      orow[v] = pack8(y);
+      for (int k = 0; k < VPL; ++k) raw[u][k] = row < rows ? __ldg(xr + j0 + k * LPR) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long row = base + static_cast<long long>(u) * warps_total * RPW + sub;
+      float2 f[VPL][4];
+      float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        unpack8p(raw[u][k], f[k]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s2 = __fadd2_rn(s2, f[k][j]);
+      }
+      float s = s2.x + s2.y;
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s * inv_c;
+      const float2 nmean = make_float2(-mean, -mean);
+      float2 q2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          f[k][j] = __fadd2_rn(f[k][j], nmean);
+          q2 = __ffma2_rn(f[k][j], f[k][j], q2);
+        }
+      }
+      float q = q2.x + q2.y;
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = rsqrtf(q * inv_c + eps);
+      const float2 rstd2 = make_float2(rstd, rstd);
+      if (row < rows) {
+        uint4* orow = reinterpret_cast<uint4*>(out + row * ldo);
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          const int v = j0 + k * LPR;
+          const float4 g0 = ln_sh[2 * v], g1 = ln_sh[2 * v + 1];
+          const float4 b0 = ln_sh[2 * NVEC + 2 * v], b1 = ln_sh[2 * NVEC + 2 * v + 1];
+          float2 y[4];
+          y[0] = __ffma2_rn(f[k][0], __fmul2_rn(rstd2, make_float2(g0.x, g0.y)), make_float2(b0.x, b0.y));
+          y[1] = __ffma2_rn(f[k][1], __fmul2_rn(rstd2, make_float2(g0.z, g0.w)), make_float2(b0.z, b0.w));
+          y[2] = __ffma2_rn(f[k][2], __fmul2_rn(rstd2, make_float2(g1.x, g1.y)), make_float2(b1.x, b1.y));
+          y[3] = __ffma2_rn(f[k][3], __fmul2_rn(rstd2, make_float2(g1.z, g1.w)), make_float2(b1.z, b1.w));
+          orow[v] = pack8p(y);
+        }
+      }
     }
   }
 }
