@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MRISR_ABI_VERSION 1
+#define MRISR_ABI_VERSION 2
 
 #define MRISR_OK 0
 #define MRISR_E_INVALID (-1)     /* bad argument (null pointer, misaligned, negative size) */
@@ -87,8 +87,9 @@ int mrisr_layernorm(const void* x, int64_t ldx, const float* gamma, const float*
 /* Tensor-core GEMM / implicit-GEMM conv (tcgen05 + TMEM + TMA):
  *     out[M, n_store] = act( concat_K(A1, A2) (*) W^T + bias + rowvec[batch(m)] ) + res1 + res2
  * taps == 1: A1 [M, k1] (row stride lda1), A2 [M, k2] optional -- Linear layers, 1x1 convs, LoRA rank extension.
- * taps == 9: A1/A2 are NHWC [B, H, W, k] activations (pixel strides lda1/lda2); 3x3, stride 1, pad 1 convolution;
- *            M = B*H*W; W and H powers of two, W <= 128 (the TMA box is {64ch, W, 128/W rows}).
+ * taps == 9: A1/A2 are NHWC [B, H, W, k] activations (pixel strides lda1/lda2); 3x3, pad 1 convolution, stride
+ *            conv_stride (1 or 2); M = B*Ho*Wo; Wo and Ho powers of two, Wo <= 128 (the TMA box is {64ch, Wo, 128/Wo rows},
+ *            traversed with element stride conv_stride).
  * W: bf16 [N, taps*(k1+k2)] K-major, k index = tap*(k1+k2) + channel.  N % mrisr_gemm_block_n(N, act) == 0.
  * k1, k2 % 64 == 0.  bias fp32 [N] or NULL.  rowvec fp32: added before act, row m uses
  * rowvec[(m / rows_per_batch) * rowvec_stride + n] (time-embedding projection; NULL = none).
@@ -116,6 +117,9 @@ typedef struct mrisr_gemm_args {
   int64_t ldo;
   int32_t out_fp32;
   int32_t reserved;
+  int32_t conv_stride; /* taps == 9 only: 1 (or 0) = stride 1; 2 = stride-2 pad-1 convolution (UNet / adapter downsamplers):
+                          H, W are the INPUT dims (even), M = B*(H/2)*(W/2); the TMA box walks every second pixel */
+  int32_t reserved2;
 } mrisr_gemm_args;
 int mrisr_gemm(const mrisr_gemm_args* args, void* stream);
 /* N-tile the kernel will use for (N, act); GEGLU callers interleave weight/bias rows in blocks of this size:

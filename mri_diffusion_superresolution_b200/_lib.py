@@ -29,6 +29,7 @@ class GemmArgs(C.Structure):
         ("res2", C.c_void_p), ("ldr2", C.c_int64),
         ("out", C.c_void_p), ("ldo", C.c_int64),
         ("out_fp32", C.c_int32), ("reserved", C.c_int32),
+        ("conv_stride", C.c_int32), ("reserved2", C.c_int32),
     ]
 
 
@@ -79,7 +80,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.mrisr_abi_version() != 1:
+        if lib.mrisr_abi_version() != 2:
             raise RuntimeError("libmrisr_b200.so ABI version mismatch; rebuild")
         _lib = lib
     return _lib

@@ -134,9 +134,8 @@ class Adapter_XL:
             if down:                                                    # :101-102
                 if self.use_conv:
                     B, H, W, c = h.shape
-                    cols = ops.im2col3x3s2(h)
-                    h = ops.gemm(cols, p[f"body.{k}.down_opt.op.weight"], bias=p[f"body.{k}.down_opt.op.bias"]).view(
-                        B, H // 2, W // 2, c)
+                    h = ops.gemm(h, p[f"body.{k}.down_opt.op.weight"], bias=p[f"body.{k}.down_opt.op.bias"], conv=True,
+                                 stride=2).view(B, H // 2, W // 2, c)
                 else:
                     h = ops.avgpool2(h)
             if has_in:                                                  # :103-104

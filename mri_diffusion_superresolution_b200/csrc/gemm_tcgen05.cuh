@@ -37,7 +37,8 @@ struct GemmKernelParams {
   int kc1, kc2;  // 64-wide K chunks per tap taken from A1 / A2
   int taps;      // 1 or 9
   int conv;      // 0: A is [M, k]; 1: A is NHWC [B, H, W, k]
-  int H, W;
+  int H, W;      // conv: OUTPUT height / width (tile -> pixel arithmetic)
+  int stride;    // conv: 1 or 2 (the TMA box walks every stride-th input pixel)
   int m_tiles, n_tiles;
   int res_mma;    // residual operands folded into the MMA K loop (0, 1 or 2)
   int tma_store;  // bf16 output written by TMA from the swizzled staging buffers
@@ -451,7 +452,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
         const int ds = (p.taps == 9) ? tap % 3 - 1 : 0;
         for (int kc = 0; kc < kchunks; ++kc) {
           const bool first = kc < p.kc1;
-          load(first ? &maps.a1 : &maps.a2, p.conv != 0, (first ? kc : kc - p.kc1) * kBlockK, ds, h0 + dr, b0, m0, &maps.b,
+          load(first ? &maps.a1 : &maps.a2, p.conv != 0, (first ? kc : kc - p.kc1) * kBlockK, ds, h0 * p.stride + dr, b0, m0, &maps.b,
                (tap * kchunks + kc) * kBlockK, n0);
         }
       }

@@ -102,8 +102,9 @@ int load_encode() {
 
 // bf16 tensor, `rank` dims (innermost first), byte strides for dims 1..rank-1, 128B swizzle, zero OOB fill.
 int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-               const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+               const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B, int spatial_stride = 1) {
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (rank == 4) estr[1] = estr[2] = static_cast<cuuint32_t>(spatial_stride);  // NHWC conv operand: every stride-th pixel
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(ptr), dims,
                         strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -564,23 +565,27 @@ int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
       ma2 = ma1;
     }
   } else {
-    const int H = g->H, W = g->W;
+    const int cs = g->conv_stride == 2 ? 2 : 1;
+    MRISR_REQUIRE(g->conv_stride >= 0 && g->conv_stride <= 2, "gemm(conv3x3): conv_stride must be 1 or 2");
+    MRISR_REQUIRE(g->H % cs == 0 && g->W % cs == 0, "gemm(conv3x3): stride 2 needs even H, W");
+    const int H = g->H / cs, W = g->W / cs;  // output dims
     if (!is_pow2(H) || !is_pow2(W) || W > 128)
-      return fail(MRISR_E_UNSUPPORTED, "gemm(conv3x3): H (%d) and W (%d) must be powers of two, W <= 128", H, W);
-    MRISR_REQUIRE(g->M % (H * W) == 0, "gemm(conv3x3): M must be batch*H*W");
+      return fail(MRISR_E_UNSUPPORTED, "gemm(conv3x3): output H (%d) and W (%d) must be powers of two, W <= 128", H, W);
+    MRISR_REQUIRE(g->M % (H * W) == 0, "gemm(conv3x3): M must be batch*Ho*Wo");
     const int B = g->M / (H * W);
     const int TH = (128 / W) < H ? (128 / W) : H;
     const int TB = 128 / (W * TH);
-    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(W), static_cast<cuuint32_t>(TH), static_cast<cuuint32_t>(TB)};
+    // box extents are given in traversed INPUT elements: with element stride cs the unit keeps every cs-th one
+    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(W * cs), static_cast<cuuint32_t>(TH * cs), static_cast<cuuint32_t>(TB)};
     {
-      cuuint64_t dims[4] = {static_cast<cuuint64_t>(g->k1), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(B)};
-      cuuint64_t str[3] = {static_cast<cuuint64_t>(g->lda1) * 2, static_cast<cuuint64_t>(g->lda1) * 2 * W, static_cast<cuuint64_t>(g->lda1) * 2 * W * H};
-      if (int e = encode_map(&ma1, g->a1, 4, dims, str, box)) return e;
+      cuuint64_t dims[4] = {static_cast<cuuint64_t>(g->k1), static_cast<cuuint64_t>(g->W), static_cast<cuuint64_t>(g->H), static_cast<cuuint64_t>(B)};
+      cuuint64_t str[3] = {static_cast<cuuint64_t>(g->lda1) * 2, static_cast<cuuint64_t>(g->lda1) * 2 * g->W, static_cast<cuuint64_t>(g->lda1) * 2 * g->W * g->H};
+      if (int e = encode_map(&ma1, g->a1, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, cs)) return e;
     }
     if (g->k2 > 0) {
-      cuuint64_t dims[4] = {static_cast<cuuint64_t>(g->k2), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(B)};
-      cuuint64_t str[3] = {static_cast<cuuint64_t>(g->lda2) * 2, static_cast<cuuint64_t>(g->lda2) * 2 * W, static_cast<cuuint64_t>(g->lda2) * 2 * W * H};
-      if (int e = encode_map(&ma2, g->a2, 4, dims, str, box)) return e;
+      cuuint64_t dims[4] = {static_cast<cuuint64_t>(g->k2), static_cast<cuuint64_t>(g->W), static_cast<cuuint64_t>(g->H), static_cast<cuuint64_t>(B)};
+      cuuint64_t str[3] = {static_cast<cuuint64_t>(g->lda2) * 2, static_cast<cuuint64_t>(g->lda2) * 2 * g->W, static_cast<cuuint64_t>(g->lda2) * 2 * g->W * g->H};
+      if (int e = encode_map(&ma2, g->a2, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, cs)) return e;
     } else {
       ma2 = ma1;
     }
@@ -589,7 +594,8 @@ int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
   mrisr::GemmKernelParams p;
   p.M = g->M; p.N = g->N; p.n_store = g->n_store;
   p.kc1 = g->k1 / 64; p.kc2 = g->k2 / 64; p.taps = g->taps; p.conv = g->taps == 9 ? 1 : 0;
-  p.H = g->H; p.W = g->W;
+  p.stride = (g->taps == 9 && g->conv_stride == 2) ? 2 : 1;
+  p.H = g->H / p.stride; p.W = g->W / p.stride;
   p.m_tiles = (g->M + 127) / 128; p.n_tiles = g->N / BN;
   p.bias = g->bias; p.rowvec = g->rowvec; p.rowvec_stride = g->rowvec_stride;
   p.rows_per_batch = g->rows_per_batch > 0 ? g->rows_per_batch : 1;

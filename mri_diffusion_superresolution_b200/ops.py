@@ -51,11 +51,12 @@ def gemm_block_n(n: int, act: int = ACT_NONE) -> int:
 def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[Tensor] = None,
          rowvec: Optional[Tensor] = None, rowvec_stride: int = 0, rows_per_batch: int = 0, act: int = ACT_NONE,
          res1: Optional[Tensor] = None, res2: Optional[Tensor] = None, n_store: Optional[int] = None,
-         out_fp32: bool = False, conv: bool = False, out: Optional[Tensor] = None, _dbg: int = 0) -> Tensor:
+         out_fp32: bool = False, conv: bool = False, stride: int = 1, out: Optional[Tensor] = None,
+         _dbg: int = 0) -> Tensor:
     """``act(concat_K(a1, a2) @ w.T + bias + rowvec[batch]) + res1 + res2`` on the tcgen05 kernel.
 
     GEMM mode: a1 ``[M, k1]`` (+ a2 ``[M, k2]``).  ``conv=True``: a1/a2 are NHWC ``[B, H, W, k]`` and ``w`` is
-    ``[N, 9*(k1+k2)]`` (3x3, stride 1, pad 1).  Returns ``[M, n_store]`` (bf16, or fp32 if ``out_fp32``)."""
+    ``[N, 9*(k1+k2)]`` (3x3, pad 1, ``stride`` 1 or 2 -- the downsamplers, M = B*(H/2)*(W/2)).  Returns ``[M, n_store]`` (bf16, or fp32 if ``out_fp32``)."""
     lib = _lib.load()
     _cuda(a1, "gemm.a1", torch.bfloat16)
     _cuda(w, "gemm.w", torch.bfloat16)
@@ -67,7 +68,10 @@ def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[T
         lda1 = a1.stride(2)
         if a1.stride(1) != W * lda1 or a1.stride(0) != H * W * lda1:
             raise ValueError("gemm(conv): a1 must be dense in B,H,W (channel-slice views allowed)")
-        M, taps = B * H * W, 9
+        if stride not in (1, 2) or (stride == 2 and (H % 2 or W % 2)):
+            raise ValueError("gemm(conv): stride must be 1 or 2 (even H, W)")
+        M, taps = B * (H // stride) * (W // stride), 9
+        g.conv_stride = stride
         k2, lda2 = 0, 0
         if a2 is not None:
             _cuda(a2, "gemm.a2", torch.bfloat16)

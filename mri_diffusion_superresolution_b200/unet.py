@@ -443,9 +443,8 @@ class UNet2DConditionB200:
                 skips.append(s)
             if blk["ds"] is not None:
                 wd, bd = blk["ds"]
-                colsd = ops.im2col3x3s2(s)
                 h_, w_ = h_ // 2, w_ // 2
-                s = ops.gemm(colsd, wd, bias=bd).view(B, h_, w_, ch[i])
+                s = ops.gemm(s, wd, bias=bd, conv=True, stride=2).view(B, h_, w_, ch[i])  # stride-2 TMA boxes: no im2col
                 tap(f"down_blocks.{i}.downsamplers.0", s)
                 skips.append(s)
         if down_block_additional_residuals is not None:

@@ -179,6 +179,20 @@ def test_conv3x3_stride2_via_im2col(ops):
     assert _rel(out, ref) < 4e-3
 
 
+@pytest.mark.parametrize("B,H,C,N", [(2, 64, 320, 320), (3, 32, 640, 640), (2, 16, 1280, 1280), (2, 16, 64, 128)])
+def test_conv3x3_stride2_implicit(ops, B, H, C, N):
+    """Stride-2 pad-1 downsampler as an implicit GEMM: the TMA box walks every second input pixel (element strides), the
+    -1 start coordinate of the first tap row / column is the zero padding; no im2col buffer."""
+    from mri_diffusion_superresolution_b200.packing import pack_conv3x3
+    x = _bf((B, H, H, C), 60)
+    w = _bf((N, C, 3, 3), 61, 1.0 / math.sqrt(9 * C))
+    bias = _f32((N,), 62)
+    out = ops.gemm(x, pack_conv3x3(w), bias=bias, conv=True, stride=2)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, stride=2, padding=1).permute(0, 2, 3, 1).reshape(-1, N)
+    assert out.shape == (B * (H // 2) ** 2, N)
+    assert _rel(out, ref) < 4e-3
+
+
 def test_conv_in_via_im2col_first(ops):
     from mri_diffusion_superresolution_b200.packing import pack_conv3x3, pad_cols
     B, Cin, H, W, N = 2, 4, 64, 64, 320
