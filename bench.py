@@ -29,7 +29,7 @@ UNIT = "slices/s"
 GFLOP_UNET_STEP = 807.83          # UNet forward + LoRA r=16, one 64x64 latent
 GFLOP_SDPA_STEP = 126.05          # of which softmax(QK^T)V (runs in the attention kernel, not the GEMM kernel)
 GFLOP_ADAPTER = 164.96            # Adapter_XL(sk=True), once per slice
-GEMM_DRAM_BYTES_PER_LAUNCH_B32 = 28.258e9 / 258   # ncu, one batch-32 step (profiles/r1_launches_step_b32_v3.csv)
+GEMM_DRAM_BYTES_PER_LAUNCH_B32 = 28.186e9 / 258   # ncu, one batch-32 step (profiles/r1_launches_step_b32_v4.csv)
 
 
 def load_peaks():
@@ -286,7 +286,7 @@ def main():
         peak = peaks["bf16_sustained"]
         roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (implicit-GEMM conv3x3 + linear/1x1, all epilogues)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": GEMM_DRAM_BYTES_PER_LAUNCH_B32 * B / 32.0,
-                "traffic_source": "profiles/r1_launches_step_b32_v3.csv: dram__bytes_read.sum + dram__bytes_write.sum summed over "
+                "traffic_source": "profiles/r1_launches_step_b32_v4.csv: dram__bytes_read.sum + dram__bytes_write.sum summed over "
                                   "the 258 gemm_tcgen05_kernel launches of one batch-32 step / 258, scaled by batch/32",
                 "peak_source": f"{peaks['src']} bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches_per_unet_forward": len(prof), "avg_launch_ms": gemm_ms / max(1, len(prof)),
