@@ -116,7 +116,39 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-template <int D>
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x1(uint32_t taddr, uint32_t& v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x1(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
+// 2^x for a PAIR of arguments on the FMA pipe (no MUFU): Cody-Waite split x = n + f with the 1.5*2^23 magic-number
+// rounding (f in [-0.5, 0.5]), degree-3 minimax polynomial for 2^f (max relative error 7.5e-5, 26x below the bf16
+// rounding of P), exponent inserted with one integer shift-add.  Packed f32x2 instructions (FADD2 / FFMA2) process both
+// values per issue slot.  The softmax is bound by the 16/clk/SM MUFU.EX2 rate (scripts/micro/mufu_bench.cu), so a fixed
+// fraction of every row's exponentials is moved here.
+__device__ __forceinline__ void exp2_poly_pair(float x0, float x1, float& p0, float& p1) {
+  const float kMagic = 12582912.f;  // 1.5 * 2^23
+  const float2 x = make_float2(fmaxf(x0, -120.f), fmaxf(x1, -120.f));
+  const float2 t = __fadd2_rn(x, make_float2(kMagic, kMagic));
+  const float2 n = __fadd2_rn(t, make_float2(-kMagic, -kMagic));
+  const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), x);
+  float2 p = __ffma2_rn(f, make_float2(0.0551716685295105f, 0.0551716685295105f), make_float2(0.2426111251115799f, 0.2426111251115799f));
+  p = __ffma2_rn(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+  p = __ffma2_rn(p, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
+  p0 = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  p1 = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+}
+template <int D, int kPolyPairs>
 __global__ void __launch_bounds__(kAtcThreads, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                          const AttnTcArgs a) {
@@ -135,7 +167,6 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_c
   auto s_full = [&](int g) { return bar_base + 8u * (8 + g); };
   auto p_full = [&](int g) { return bar_base + 8u * (10 + g); };
   auto o_full = [&](int g) { return bar_base + 8u * (12 + g); };
-  auto o_free = [&](int g) { return bar_base + 8u * (14 + g); };
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + Cfg::kQBytes + kStages * Cfg::kKVBytes + 128);
   const uint32_t tmem_slot = bar_base + 128;
 
@@ -152,7 +183,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_c
     for (int s = 0; s < kStages; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
     for (int g = 0; g < 2; ++g) {
       mbar_init(s_full(g), 1); mbar_init(o_full(g), 1);
-      mbar_init(p_full(g), 128); mbar_init(o_free(g), 128);
+      mbar_init(p_full(g), 128);
     }
     fence_mbar_init();
   }
@@ -228,14 +259,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_c
         ATC_DBG("mma: wait p_full(%d) j=%d bar=0x%x\n", g, j, p_full(g));
         mbar_wait(p_full(g), j & 1);
         ATC_DBG("mma: got p_full(%d) j=%d\n", g, j);
-        if (j > 0) mbar_wait(o_free(g), (j - 1) & 1);
         tcgen05_fence_after();
         if (elect_one()) {
           const uint32_t sv = sKV + stage * Cfg::kKVBytes + kAtoms * Cfg::kAtomBytes;
+          const uint32_t acc0 = j > 0 ? 1u : 0u;  // O accumulates in TMEM across key tiles (lazy rescale by the softmax threads)
 #pragma unroll
           for (int k = 0; k < kAtcBK / 16; ++k)
             umma_bf16_ts(tmem_base + g * 256 + 128, tmem_base + g * 256 + k * 8,
-                         umma_smem_desc_mn(sv + k * 2048, Cfg::kAtomBytes, 1024), idesc_o, k > 0 ? 1u : 0u);
+                         umma_smem_desc_mn(sv + k * 2048, Cfg::kAtomBytes, 1024), idesc_o, k > 0 ? 1u : acc0);
           umma_commit(o_full(g));
           if (g == 1) umma_commit(kv_empty(stage));  // K_j and V_j fully consumed
         }
@@ -258,32 +289,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_c
     const int row = q0 + g * 128 + qrt * 32 + lane;  // query row within this (batch, head)
     const uint32_t t_s = tmem_base + (static_cast<uint32_t>(qrt * 32) << 16) + g * 256;
     const uint32_t t_o = t_s + 128;
-    float o_acc[DO];
-#pragma unroll
-    for (int i = 0; i < DO; ++i) o_acc[i] = 0.f;
-    float m = -INFINITY, l = 0.f;
+    // O accumulates in TMEM; probabilities are taken against a stale maximum m_used and O / l are rescaled only when a
+    // tile raises the row maximum by more than 8 in the log2 domain (see the split-row kernel below).
+    float m_used = -INFINITY, l = 0.f;
     const float sc = a.scale_log2;
-    auto add_ot = [&]() {
-#pragma unroll
-      for (int c = 0; c < DO / 16; ++c) {
-        uint32_t t[16];
-        tmem_ld_32x16(t_o + c * 16, t);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) o_acc[c * 16 + i] += __uint_as_float(t[i]);
-      }
-    };
     for (int j = 0; j < ntiles; ++j) {
-      if (j > 0) {  // fold in the previous tile's P V (scaled by the previous running max)
-        mbar_wait(o_full(g), (j - 1) & 1);
-        tcgen05_fence_after();
-        add_ot();
-        tcgen05_fence_before();
-        mbar_arrive(o_free(g));
-      }
-      ATC_DBG("sm w%d: wait s_full(%d) j=%d\n", warp, g, j);
-      mbar_wait(s_full(g), j & 1);
-      ATC_DBG("sm w%d: got s_full(%d) j=%d\n", warp, g, j);
+      mbar_wait(s_full(g), j & 1);  // S_g(j) was issued after P V_g(j-1): the tensor core is done with the previous P
       tcgen05_fence_after();
       uint32_t s[128];
 #pragma unroll
@@ -295,48 +306,79 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_c
         for (int i = 0; i < 128; ++i)
           if (kbase + i >= a.nk) s[i] = 0xff800000u;  // -inf
       }
-      // row max on the raw scores with 8 independent chains (a single 128-long dependent FMNMX chain costs ~512 cycles),
-      // scaled once afterwards (scale > 0)
+      // row max on the raw scores: 3-input max, 8 independent chains, scaled once afterwards (scale > 0)
       float mx8[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(s[i]);
+      for (int i = 0; i < 8; ++i) mx8[i] = max3(__uint_as_float(s[i]), __uint_as_float(s[8 + i]), __uint_as_float(s[16 + i]));
 #pragma unroll
-      for (int i = 8; i < 128; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(s[i]));
-      const float raw = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
-      const float mx = fmaxf(m, raw * sc);
-      const float alpha = ex2_approx(m - mx);
-      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int i = 24; i + 16 <= 128; i += 16) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) mx8[c] = max3(mx8[c], __uint_as_float(s[i + c]), __uint_as_float(s[i + 8 + c]));
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) mx8[c] = fmaxf(mx8[c], __uint_as_float(s[120 + c]));
+      const float raw = max3(max3(mx8[0], mx8[1], mx8[2]), max3(mx8[3], mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7]));
+      const float mnew = raw * sc;
+      if (j == 0) {
+        m_used = mnew;
+      } else {
+        const bool need = mnew > m_used + 8.f;
+        if (__any_sync(0xffffffffu, need)) {  // rare: rescale this row's O in TMEM (P V_g(j-1) completed: see above)
+          const float fac = need ? ex2_approx(m_used - mnew) : 1.f;
+          if (need) m_used = mnew;
+          l *= fac;
+#pragma unroll
+          for (int c = 0; c < DO / 8; ++c) {
+            uint32_t t[8];
+            tmem_ld_32x8(t_o + c * 8, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * fac);
+            tmem_st_32x8(t_o + c * 8, t);
+          }
+          tmem_st_wait();
+        }
+      }
+      const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(-m_used, -m_used);
+      float2 rs2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
       uint32_t pk[64];
 #pragma unroll
       for (int i = 0; i < 64; ++i) {
-        const float p0 = ex2_approx(fmaf(__uint_as_float(s[2 * i]), sc, -mx));
-        const float p1 = ex2_approx(fmaf(__uint_as_float(s[2 * i + 1]), sc, -mx));
-        rs4[i & 3] += p0 + p1;
-        pk[i] = pack_bf16(p0, p1);
+        const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), sc2, nm2);
+        float2 pp;
+        if ((i & 7) < kPolyPairs) {
+          exp2_poly_pair(x.x, x.y, pp.x, pp.y);
+        } else {
+          pp.x = ex2_approx(x.x);
+          pp.y = ex2_approx(x.y);
+        }
+        rs2[i & 1] = __fadd2_rn(rs2[i & 1], pp);
+        pk[i] = pack_bf16(pp.x, pp.y);
       }
-      const float rs = (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+      l += (rs2[0].x + rs2[0].y) + (rs2[1].x + rs2[1].y);
       tmem_st_32x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
       tmem_st_32x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
       tmem_st_wait();
       tcgen05_fence_before();
       mbar_arrive(p_full(g));
-      ATC_DBG("sm w%d: arrived p_full(%d) j=%d bar=0x%x\n", warp, g, j, p_full(g));
-      l = l * alpha + rs;
-#pragma unroll
-      for (int i = 0; i < DO; ++i) o_acc[i] *= alpha;
-      m = mx;
     }
     mbar_wait(o_full(g), (ntiles - 1) & 1);
     tcgen05_fence_after();
-    add_ot();
-    if (row < a.nq) {
-      const float inv = 1.f / l;
-      __nv_bfloat16* og = a.o + (static_cast<long long>(b) * a.nq + row) * a.ldo + head * D;
+    {
+      uint32_t ob[DO];
 #pragma unroll
-      for (int c = 0; c < D / 8; ++c) {
-        *reinterpret_cast<uint4*>(og + c * 8) =
-            make_uint4(pack_bf16(o_acc[c * 8] * inv, o_acc[c * 8 + 1] * inv), pack_bf16(o_acc[c * 8 + 2] * inv, o_acc[c * 8 + 3] * inv),
-                       pack_bf16(o_acc[c * 8 + 4] * inv, o_acc[c * 8 + 5] * inv), pack_bf16(o_acc[c * 8 + 6] * inv, o_acc[c * 8 + 7] * inv));
+      for (int c = 0; c < DO / 16; ++c) tmem_ld_32x16(t_o + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&ob[c * 16]));
+      tmem_ld_wait();
+      if (row < a.nq) {
+        const float inv = 1.f / l;
+        __nv_bfloat16* og = a.o + (static_cast<long long>(b) * a.nq + row) * a.ldo + head * D;
+#pragma unroll
+        for (int c = 0; c < D / 8; ++c) {
+          const uint32_t* t = &ob[c * 8];
+          *reinterpret_cast<uint4*>(og + c * 8) =
+              make_uint4(pack_bf16(__uint_as_float(t[0]) * inv, __uint_as_float(t[1]) * inv), pack_bf16(__uint_as_float(t[2]) * inv, __uint_as_float(t[3]) * inv),
+                         pack_bf16(__uint_as_float(t[4]) * inv, __uint_as_float(t[5]) * inv), pack_bf16(__uint_as_float(t[6]) * inv, __uint_as_float(t[7]) * inv));
+        }
       }
     }
   }
@@ -380,38 +422,6 @@ struct AttnSplitCfg {
   static constexpr int kSmemBytes = kQBytes + kStages * kKVBytes + kBarBytes + kOnesBytes + kMaxBytes + 1024;
 };
 
-__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_32x1(uint32_t taddr, uint32_t& v) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&v)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
-}
-__device__ __forceinline__ void tmem_st_32x1(uint32_t taddr, uint32_t v) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
-}
-// 2^x for a PAIR of arguments on the FMA pipe (no MUFU): Cody-Waite split x = n + f with the 1.5*2^23 magic-number
-// rounding (f in [-0.5, 0.5]), degree-3 minimax polynomial for 2^f (max relative error 7.5e-5, 26x below the bf16
-// rounding of P), exponent inserted with one integer shift-add.  Packed f32x2 instructions (FADD2 / FFMA2) process both
-// values per issue slot.  The softmax is bound by the 16/clk/SM MUFU.EX2 rate (scripts/micro/mufu_bench.cu), so a fixed
-// fraction of every row's exponentials is moved here.
-__device__ __forceinline__ void exp2_poly_pair(float x0, float x1, float& p0, float& p1) {
-  const float kMagic = 12582912.f;  // 1.5 * 2^23
-  const float2 x = make_float2(fmaxf(x0, -120.f), fmaxf(x1, -120.f));
-  const float2 t = __fadd2_rn(x, make_float2(kMagic, kMagic));
-  const float2 n = __fadd2_rn(t, make_float2(-kMagic, -kMagic));
-  const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), x);
-  float2 p = __ffma2_rn(f, make_float2(0.0551716685295105f, 0.0551716685295105f), make_float2(0.2426111251115799f, 0.2426111251115799f));
-  p = __ffma2_rn(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
-  p = __ffma2_rn(p, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
-  p0 = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
-  p1 = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
-}
 // spin without the printf of mbar_wait (keeps the 24-register control warps free of call overhead); traps on a hang
 __device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;

@@ -220,12 +220,6 @@ int launch_attention_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, 
                         int64_t ldo, int batch, int nq, int nk, int heads, int kv_broadcast, cudaStream_t st) {
   using Cfg = mrisr::AttnTcCfg<D>;
   if (int e = load_encode()) return e;
-  static bool configured = false;
-  if (!configured) {
-    MRISR_CHECK_CUDA(cudaFuncSetAttribute(mrisr::attention_tcgen05_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          Cfg::kSmemBytes));
-    configured = true;
-  }
   CUtensorMap mk, mv;
   const cuuint64_t rows = static_cast<cuuint64_t>(kv_broadcast ? 1 : batch) * nk;
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(heads) * D, rows};
@@ -272,9 +266,25 @@ int launch_attention_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, 
       }
     }
   }
-  launch_k(mrisr::attention_tcgen05_kernel<D>, dim3(grid), dim3(mrisr::kAtcThreads), Cfg::kSmemBytes, st, mk, mv, a);
-  MRISR_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  {
+    static const int poly = getenv("MRISR_ATTN_POLY80") ? atoi(getenv("MRISR_ATTN_POLY80")) : 3;
+    static bool configured1[4] = {false, false, false, false};
+    auto launch = [&](auto kern, int slot) -> int {
+      if (!configured1[slot]) {
+        MRISR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        configured1[slot] = true;
+      }
+      launch_k(kern, dim3(grid), dim3(mrisr::kAtcThreads), Cfg::kSmemBytes, st, mk, mv, a);
+      MRISR_CHECK_CUDA(cudaGetLastError());
+      return 0;
+    };
+    switch (poly) {
+      case 0: return launch(mrisr::attention_tcgen05_kernel<D, 0>, 0);
+      case 2: return launch(mrisr::attention_tcgen05_kernel<D, 2>, 1);
+      case 4: return launch(mrisr::attention_tcgen05_kernel<D, 4>, 2);
+      default: return launch(mrisr::attention_tcgen05_kernel<D, 3>, 3);
+    }
+  }
 }
 
 bool use_tc_attention() {
@@ -708,7 +718,8 @@ int mrisr_im2col3x3s2(const void* in, void* out, int B, int H, int W, int C, voi
 
 int mrisr_im2col_first(const float* in, void* out, int B, int Cin, int H, int W, int kpad, void* stream) {
   MRISR_REQUIRE(in && out && B > 0 && Cin > 0 && H > 0 && W > 0 && kpad >= 9 * Cin && kpad % 64 == 0, "im2col_first: bad argument");
-  const long long n = static_cast<long long>(B) * H * W * kpad;
+  const long long n = static_cast<long long>(B) * H * W * (kpad / 8);
+  MRISR_REQUIRE(n < (1ll << 31), "im2col_first: tensor too large");
   launch_k(mrisr::im2col_first_kernel, dim3(grid_for(n, 256, 8)), dim3(256), 0, as_stream(stream), in, static_cast<__nv_bfloat16*>(out), B, Cin, H, W, kpad);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;

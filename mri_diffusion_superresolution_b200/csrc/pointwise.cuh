@@ -534,20 +534,28 @@ __global__ void im2col_first_kernel(const float* __restrict__ in, __nv_bfloat16*
                                     int W, int kpad) {
   grid_dep_launch();
   grid_dep_wait();
-  const long long total = static_cast<long long>(B) * H * W * kpad;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int k = static_cast<int>(i % kpad);
-    long long p = i / kpad;
-    const int w = static_cast<int>(p % W); p /= W;
-    const int h = static_cast<int>(p % H);
-    const int b = static_cast<int>(p / H);
-    float val = 0.f;
-    if (k < 9 * Cin) {
-      const int tap = k / Cin, c = k % Cin;
-      const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
-      if (hh >= 0 && hh < H && ww >= 0 && ww < W) val = __ldg(in + ((static_cast<long long>(b) * Cin + c) * H + hh) * W + ww);
+  // one 16-byte store (8 consecutive k) per thread-iteration, 32-bit index arithmetic (kpad % 8 == 0)
+  const int kv = kpad >> 3;
+  const int total = B * H * W * kv;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int v = i % kv;
+    int p = i / kv;
+    const int w = p % W; p /= W;
+    const int h = p % H;
+    const int b = p / H;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = v * 8 + j;
+      float val = 0.f;
+      if (k < 9 * Cin) {
+        const int tap = k / Cin, c = k - tap * Cin;
+        const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) val = __ldg(in + ((static_cast<long long>(b) * Cin + c) * H + hh) * W + ww);
+      }
+      f[j] = val;
     }
-    out[i] = __float2bfloat16(val);
+    reinterpret_cast<uint4*>(out)[i] = pack8(f);
   }
 }
 
