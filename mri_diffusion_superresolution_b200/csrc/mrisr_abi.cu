@@ -336,6 +336,8 @@ int launch_layernorm_group(const void* x, int64_t ldx, const float* g, const flo
 }
 
 constexpr int kGnMaxSlabs = 64;
+constexpr int kGnMaxFusedBatch = 2048;
+__device__ int g_gn_counters[2 * kGnMaxFusedBatch];  // zero-initialised; groupnorm_fused_kernel leaves them zero
 
 }  // namespace
 
@@ -441,8 +443,23 @@ int mrisr_groupnorm(const void* x1, int64_t ld1, int c1, const void* x2, int64_t
   int R = 256 / nvec;
   if (R < 1) R = 1;
   if (R > hw) R = hw;
-  int want = (148 * 8 + batch - 1) / batch;  // >= 8 CTAs per SM chip-wide: these kernels are latency-bound below that
+  // single-launch path: needs every CTA of the grid co-resident (per-batch barrier between the two passes), so the slab
+  // count comes from the occupancy calculator; MRISR_GN_TWO_PASS=1 forces the two-kernel path (A/B runs)
+  static const bool no_fused = getenv("MRISR_GN_TWO_PASS") != nullptr;
+  const size_t smem_fused = 2 * static_cast<size_t>(R) * C * sizeof(float);
   int max_slabs = (hw + 4 * R - 1) / (4 * R);
+  bool fused = false;
+  int want = (148 * 8 + batch - 1) / batch;  // two-pass: >= 8 CTAs per SM chip-wide (latency-bound below that)
+  if (!no_fused && batch <= kGnMaxFusedBatch) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mrisr::groupnorm_fused_kernel, nvec * R, smem_fused) == cudaSuccess) {
+      const long long capacity = static_cast<long long>(per_sm) * sm_count();
+      if (capacity >= batch) {
+        fused = true;
+        want = static_cast<int>(capacity / batch);
+      }
+    }
+  }
   int nslab = want < max_slabs ? want : max_slabs;
   if (nslab > kGnMaxSlabs) nslab = kGnMaxSlabs;
   if (nslab < 1) nslab = 1;
@@ -455,6 +472,18 @@ int mrisr_groupnorm(const void* x1, int64_t ld1, int c1, const void* x2, int64_t
   a.nslab = nslab; a.pix_per_slab = pps;
   dim3 block(nvec, R), grid(nslab, batch);
   cudaStream_t st = as_stream(stream);
+  if (fused) {
+    static int* counters = nullptr;
+    if (counters == nullptr) {
+      void* sym = nullptr;
+      MRISR_CHECK_CUDA(cudaGetSymbolAddress(&sym, g_gn_counters));
+      counters = static_cast<int*>(sym);
+    }
+    launch_k(mrisr::groupnorm_fused_kernel, dim3(grid), dim3(block), smem_fused, st, a, reinterpret_cast<float2*>(workspace), gamma, beta,
+             eps, silu, static_cast<__nv_bfloat16*>(out), counters);
+    MRISR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   launch_k(mrisr::groupnorm_stats_kernel, dim3(grid), dim3(block), 2 * R * C * sizeof(float), st, a, reinterpret_cast<float2*>(workspace));
   MRISR_CHECK_CUDA(cudaGetLastError());
   launch_k(mrisr::groupnorm_apply_kernel, dim3(grid), dim3(block), 2 * C * sizeof(float), st, a, reinterpret_cast<const float2*>(workspace), gamma, beta, eps, silu, static_cast<__nv_bfloat16*>(out), nslab);

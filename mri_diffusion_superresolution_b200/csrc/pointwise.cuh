@@ -192,10 +192,8 @@ __device__ __forceinline__ uint4 gn_load(const GnArgs& a, int b, int pix, int vx
   return __ldg(reinterpret_cast<const uint4*>(a.x2 + p * a.ld2) + (vx - nv1));
 }
 
-__global__ void groupnorm_stats_kernel(GnArgs a, float2* __restrict__ partial /*[B, nslab, groups]*/) {
-  grid_dep_launch();
-  grid_dep_wait();
-  extern __shared__ float gn_sh[];  // [2][R][C]: per-thread per-channel partial sums, reduced in a FIXED order below
+__device__ __forceinline__ void gn_stats_body(const GnArgs& a, float2* __restrict__ partial /*[B, nslab, groups]*/,
+                                              float* gn_sh /*[2][R][C]: per-thread per-channel partial sums*/) {
   const int vx = threadIdx.x, ry = threadIdx.y, R = blockDim.y;
   const int b = blockIdx.y, slab = blockIdx.x;
   const int tid = ry * blockDim.x + vx;
@@ -244,12 +242,20 @@ __global__ void groupnorm_stats_kernel(GnArgs a, float2* __restrict__ partial /*
   }
 }
 
-__global__ void groupnorm_apply_kernel(GnArgs a, const float2* __restrict__ partial, const float* __restrict__ gamma,
-                                       const float* __restrict__ beta, float eps, int silu,
-                                       __nv_bfloat16* __restrict__ out /*[B,HW,c1+c2] dense*/, int stats_nslab) {
+__global__ void groupnorm_stats_kernel(GnArgs a, float2* __restrict__ partial) {
   grid_dep_launch();
   grid_dep_wait();
-  extern __shared__ float s_aff[];  // scale[C], shift[C]
+  extern __shared__ float gn_sh[];
+  gn_stats_body(a, partial, gn_sh);
+}
+
+// kCoherent: the partials were written by OTHER CTAs of the same grid (fused kernel): read them through L2 (ld.global.cg),
+// never through the non-coherent path.
+template <bool kCoherent>
+__device__ __forceinline__ void gn_apply_body(const GnArgs& a, const float2* partial, const float* __restrict__ gamma,
+                                              const float* __restrict__ beta, float eps, int silu,
+                                              __nv_bfloat16* __restrict__ out /*[B,HW,c1+c2] dense*/, int stats_nslab,
+                                              float* s_aff /*scale[C], shift[C]*/) {
   __shared__ float s_mean[64], s_rstd[64];
   const int C = a.c1 + a.c2;
   const int vx = threadIdx.x, ry = threadIdx.y, R = blockDim.y;
@@ -264,7 +270,8 @@ __global__ void groupnorm_apply_kernel(GnArgs a, const float2* __restrict__ part
     const int g = idx >> 3, part = idx & 7;
     double su = 0.0, sq = 0.0;
     for (int k = part; k < stats_nslab; k += 8) {
-      const float2 v = __ldg(partial + (static_cast<long long>(b) * stats_nslab + k) * a.groups + g);
+      const float2* pp = partial + (static_cast<long long>(b) * stats_nslab + k) * a.groups + g;
+      const float2 v = kCoherent ? __ldcg(pp) : __ldg(pp);
       su += v.x; sq += v.y;
     }
     s_part[idx * 2] = su;
@@ -317,6 +324,53 @@ __global__ void groupnorm_apply_kernel(GnArgs a, const float2* __restrict__ part
     for (int u = 0; u < 4; ++u) emit(pix + u * R, v[u]);
   }
   for (; pix < p1; pix += R) emit(pix, gn_load(a, b, pix, vx));
+}
+
+__global__ void groupnorm_apply_kernel(GnArgs a, const float2* __restrict__ partial, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, float eps, int silu, __nv_bfloat16* __restrict__ out,
+                                       int stats_nslab) {
+  grid_dep_launch();
+  grid_dep_wait();
+  extern __shared__ float gn_sh[];
+  gn_apply_body<false>(a, partial, gamma, beta, eps, silu, out, stats_nslab, gn_sh);
+}
+
+// Single-launch GroupNorm: statistics pass, a per-batch-element barrier across the slab CTAs (all CTAs of the grid are
+// co-resident: the host sizes the grid from the occupancy calculator), then the normalise pass whose second read of x
+// mostly hits L2.  One launch and one DRAM read of x instead of two launches and two reads -- the two-kernel pair spent
+// ~20 us per norm in fixed latency and every byte costs ~160 pJ at the board power cap.  counters: [2 * batch] ints, zero
+// between launches (the last CTA through the barrier of a batch element resets its pair), owned by the library: ONE
+// stream per process may run GroupNorm at a time.  The spin is bounded (trap, never a hang).
+__global__ void groupnorm_fused_kernel(GnArgs a, float2* partial, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       float eps, int silu, __nv_bfloat16* __restrict__ out, int* counters) {
+  grid_dep_launch();
+  grid_dep_wait();
+  extern __shared__ float gn_sh[];
+  gn_stats_body(a, partial, gn_sh);
+  const int b = blockIdx.y;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  __threadfence();  // this CTA's partials are visible device-wide before its arrival is
+  __syncthreads();
+  if (tid == 0) {
+    int* arrive = counters + 2 * b;
+    int* depart = arrive + 1;
+    atomicAdd(arrive, 1);
+    const long long t0 = clock64();
+    while (*reinterpret_cast<volatile int*>(arrive) < a.nslab) {
+      if (clock64() - t0 > 4000000000LL) {
+        printf("mrisr: groupnorm barrier timeout (batch %d, %d of %d slabs arrived)\n", b, *reinterpret_cast<volatile int*>(arrive), a.nslab);
+        __trap();
+      }
+      __nanosleep(64);
+    }
+    __threadfence();
+    if (atomicAdd(depart, 1) == a.nslab - 1) {  // every CTA of this batch element has left the spin: reset for the next launch
+      *reinterpret_cast<volatile int*>(arrive) = 0;
+      *reinterpret_cast<volatile int*>(depart) = 0;
+    }
+  }
+  __syncthreads();
+  gn_apply_body<true>(a, partial, gamma, beta, eps, silu, out, a.nslab, gn_sh);
 }
 
 // ---------------------------------------------------------------------------------------------------
