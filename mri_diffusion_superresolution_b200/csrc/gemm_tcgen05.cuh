@@ -121,20 +121,6 @@ __device__ __forceinline__ void add_res32(float (&f)[32], const __nv_bfloat16* _
   }
 }
 
-__device__ __forceinline__ void ld_res32(uint4 (&r)[4], const __nv_bfloat16* __restrict__ src) {
-  const uint4* p4 = reinterpret_cast<const uint4*>(src);
-#pragma unroll
-  for (int u = 0; u < 4; ++u) r[u] = __ldg(p4 + u);
-}
-__device__ __forceinline__ void add_res32r(float (&f)[32], const uint4 (&r)[4]) {
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    f[u * 8 + 0] += bf16_lo(r[u].x); f[u * 8 + 1] += bf16_hi(r[u].x);
-    f[u * 8 + 2] += bf16_lo(r[u].y); f[u * 8 + 3] += bf16_hi(r[u].y);
-    f[u * 8 + 4] += bf16_lo(r[u].z); f[u * 8 + 5] += bf16_hi(r[u].z);
-    f[u * 8 + 6] += bf16_lo(r[u].w); f[u * 8 + 7] += bf16_hi(r[u].w);
-  }
-}
 __device__ __forceinline__ void add_smem32(float (&f)[32], const float* s) {
   const float4* s4 = reinterpret_cast<const float4*>(s);
 #pragma unroll

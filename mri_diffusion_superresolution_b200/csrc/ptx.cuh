@@ -91,11 +91,6 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, 
       : "memory");
 }
 
-// Asynchronous L2 prefetch of a contiguous global range (16-byte aligned address, size a multiple of 16).
-__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gptr)), "r"(bytes) : "memory");
-}
-
 // ------------------------------------------------------------------ TMA stores (tile mode, bulk async-groups)
 // smem -> global; the issuing thread owns the bulk group.  Generic-proxy writes to the source buffer must be followed by
 // fence.proxy.async (every writing thread) and a barrier before the issue.
