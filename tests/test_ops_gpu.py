@@ -248,7 +248,21 @@ def test_groupnorm(ops, B, HW, C1, C2, silu, eps):
     assert _rel(out, ref) < 4e-3
 
 
-@pytest.mark.parametrize("rows,C", [(4096, 320), (1000, 640), (77, 1280), (5, 64)])
+@pytest.mark.parametrize("B,HW,C", [(32, 4096, 320), (64, 64, 1280), (1500, 4, 64), (7, 1024, 640)])
+def test_groupnorm_single_launch_barrier(ops, B, HW, C):
+    """The single-launch GroupNorm (statistics -> per-batch barrier -> normalise) at a full-machine grid, at a batch that
+    leaves one or two slabs per element, and at a batch beyond the co-resident capacity (two-kernel fallback); repeated
+    calls must be bit-identical (the barrier counters reset themselves, statistics are order-deterministic)."""
+    h = int(math.isqrt(HW))
+    x = _bf((B, h, h, C), 70) * 1.5 + 0.25
+    gamma, beta = _f32((C,), 71) * 0.1 + 1, _f32((C,), 72) * 0.1
+    outs = [ops.groupnorm(x, gamma, beta, 32, 1e-5, True) for _ in range(3)]
+    ref = F.silu(F.group_norm(x.float().permute(0, 3, 1, 2), 32, gamma, beta, 1e-5)).permute(0, 2, 3, 1)
+    assert _rel(outs[0], ref) < 4e-3
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+
+
+@pytest.mark.parametrize("rows,C", [(4096, 320), (1000, 640), (77, 1280), (5, 64), (131072, 320), (3, 1280), (33, 640), (100, 2048)])
 def test_layernorm(ops, rows, C):
     x = _bf((rows, C), 37) * 3 + 1
     gamma, beta = _f32((C,), 38) * 0.1 + 1, _f32((C,), 39) * 0.1
