@@ -88,8 +88,8 @@ int mrisr_layernorm(const void* x, int64_t ldx, const float* gamma, const float*
  *     out[M, n_store] = act( concat_K(A1, A2) (*) W^T + bias + rowvec[batch(m)] ) + res1 + res2
  * taps == 1: A1 [M, k1] (row stride lda1), A2 [M, k2] optional -- Linear layers, 1x1 convs, LoRA rank extension.
  * taps == 9: A1/A2 are NHWC [B, H, W, k] activations (pixel strides lda1/lda2); 3x3, pad 1 convolution, stride
- *            conv_stride (1 or 2); M = B*Ho*Wo; Wo and Ho powers of two, Wo <= 128 (the TMA box is {64ch, Wo, 128/Wo rows},
- *            traversed with element stride conv_stride).
+ *            conv_stride (1 or 2); M = B*Ho*Wo; Wo and Ho powers of two (the TMA box is {64ch, min(Wo,128), 128/Wo rows}:
+ *            whole output rows, or a 128-pixel segment of one row when Wo > 128; traversed with element stride conv_stride).
  * W: bf16 [N, taps*(k1+k2)] K-major, k index = tap*(k1+k2) + channel.  N % mrisr_gemm_block_n(N, act) == 0.
  * k1, k2 % 64 == 0.  bias fp32 [N] or NULL.  rowvec fp32: added before act, row m uses
  * rowvec[(m / rows_per_batch) * rowvec_stride + n] (time-embedding projection; NULL = none).

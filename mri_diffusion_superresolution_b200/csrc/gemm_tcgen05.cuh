@@ -427,18 +427,20 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
       const int n_blk = tile % p.n_tiles;
       const int n0 = n_blk * BN + rank * Cfg::kBRows;
       const int m0 = (tile / p.n_tiles) * kTileM + rank * kBlockM;
-      int b0 = 0, h0 = 0;
-      if (p.conv) {
+      int b0 = 0, h0 = 0, x0 = 0;
+      if (p.conv) {  // tile = 128 consecutive output pixels: whole rows (W <= 128) or a 128-pixel segment of one row
         const int hw = p.H * p.W;
         b0 = m0 / hw;
-        h0 = (m0 - b0 * hw) / p.W;
+        const int rem = m0 - b0 * hw;
+        h0 = rem / p.W;
+        x0 = rem - h0 * p.W;
       }
       for (int tap = 0; tap < p.taps; ++tap) {
         const int dr = (p.taps == 9) ? tap / 3 - 1 : 0;
         const int ds = (p.taps == 9) ? tap % 3 - 1 : 0;
         for (int kc = 0; kc < kchunks; ++kc) {
           const bool first = kc < p.kc1;
-          load(first ? &maps.a1 : &maps.a2, p.conv != 0, (first ? kc : kc - p.kc1) * kBlockK, ds, h0 * p.stride + dr, b0, m0, &maps.b,
+          load(first ? &maps.a1 : &maps.a2, p.conv != 0, (first ? kc : kc - p.kc1) * kBlockK, x0 * p.stride + ds, h0 * p.stride + dr, b0, m0, &maps.b,
                (tap * kchunks + kc) * kBlockK, n0);
         }
       }

@@ -608,14 +608,16 @@ int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
     MRISR_REQUIRE(g->conv_stride >= 0 && g->conv_stride <= 2, "gemm(conv3x3): conv_stride must be 1 or 2");
     MRISR_REQUIRE(g->H % cs == 0 && g->W % cs == 0, "gemm(conv3x3): stride 2 needs even H, W");
     const int H = g->H / cs, W = g->W / cs;  // output dims
-    if (!is_pow2(H) || !is_pow2(W) || W > 128)
-      return fail(MRISR_E_UNSUPPORTED, "gemm(conv3x3): output H (%d) and W (%d) must be powers of two, W <= 128", H, W);
+    if (!is_pow2(H) || !is_pow2(W) || W > 4096)
+      return fail(MRISR_E_UNSUPPORTED, "gemm(conv3x3): output H (%d) and W (%d) must be powers of two, W <= 4096", H, W);
     MRISR_REQUIRE(g->M % (H * W) == 0, "gemm(conv3x3): M must be batch*Ho*Wo");
     const int B = g->M / (H * W);
-    const int TH = (128 / W) < H ? (128 / W) : H;
-    const int TB = 128 / (W * TH);
+    // a 128-pixel tile is TB images x TH rows x TW pixels: whole rows when W <= 128, else a 128-pixel row segment
+    const int TW = W < 128 ? W : 128;
+    const int TH = (128 / TW) < H ? (128 / TW) : H;
+    const int TB = 128 / (TW * TH);
     // box extents are given in traversed INPUT elements: with element stride cs the unit keeps every cs-th one
-    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(W * cs), static_cast<cuuint32_t>(TH * cs), static_cast<cuuint32_t>(TB)};
+    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(TW * cs), static_cast<cuuint32_t>(TH * cs), static_cast<cuuint32_t>(TB)};
     {
       cuuint64_t dims[4] = {static_cast<cuuint64_t>(g->k1), static_cast<cuuint64_t>(g->W), static_cast<cuuint64_t>(g->H), static_cast<cuuint64_t>(B)};
       cuuint64_t str[3] = {static_cast<cuuint64_t>(g->lda1) * 2, static_cast<cuuint64_t>(g->lda1) * 2 * g->W, static_cast<cuuint64_t>(g->lda1) * 2 * g->W * g->H};

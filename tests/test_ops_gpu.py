@@ -179,6 +179,19 @@ def test_conv3x3_stride2_via_im2col(ops):
     assert _rel(out, ref) < 4e-3
 
 
+@pytest.mark.parametrize("B,H,C,N,stride", [(1, 256, 64, 64, 1), (2, 512, 64, 64, 2), (1, 512, 64, 64, 1), (1, 256, 128, 256, 2)])
+def test_conv3x3_wide_images(ops, B, H, C, N, stride):
+    """Output rows wider than one 128-pixel tile (the 512^2 / 256^2 levels of the ControlNet conditioning embedding): the
+    tile is a 128-pixel segment of one row, halo columns come from the neighbouring segment or the zero padding."""
+    from mri_diffusion_superresolution_b200.packing import pack_conv3x3
+    x = _bf((B, H, H, C), 63)
+    w = _bf((N, C, 3, 3), 64, 1.0 / math.sqrt(9 * C))
+    bias = _f32((N,), 65)
+    out = ops.gemm(x, pack_conv3x3(w), bias=bias, conv=True, stride=stride, act=ops.ACT_SILU)
+    ref = F.silu(F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, stride=stride, padding=1)).permute(0, 2, 3, 1).reshape(-1, N)
+    assert _rel(out, ref) < 4e-3
+
+
 @pytest.mark.parametrize("B,H,C,N", [(2, 64, 320, 320), (3, 32, 640, 640), (2, 16, 1280, 1280), (2, 16, 64, 128)])
 def test_conv3x3_stride2_implicit(ops, B, H, C, N):
     """Stride-2 pad-1 downsampler as an implicit GEMM: the TMA box walks every second input pixel (element strides), the
