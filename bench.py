@@ -29,6 +29,9 @@ UNIT = "slices/s"
 GFLOP_UNET_STEP = 807.83          # UNet forward + LoRA r=16, one 64x64 latent
 GFLOP_SDPA_STEP = 126.05          # of which softmax(QK^T)V (runs in the attention kernel, not the GEMM kernel)
 GFLOP_ADAPTER = 164.96            # Adapter_XL(sk=True), once per slice
+GFLOP_CONTROLNET_STEP = 268.57    # SD-1.5 ControlNet (encoder + mid copy + 13 zero convs), per step
+GFLOP_SDPA_CN_FRACTION = 50.45 / 126.05   # softmax(QK^T)V of the ControlNet's 7 transformer blocks relative to the UNet's 16
+GFLOP_CONTROLNET_EMBED = 14.72    # its condition embedding 512^2 -> 64^2, once per slice
 GEMM_DRAM_BYTES_PER_LAUNCH_B32 = 28.186e9 / 258   # ncu, one batch-32 step (profiles/r1_launches_step_b32_v4.csv)
 
 
@@ -142,6 +145,9 @@ def main():
     ap.add_argument("--inference-steps", type=int, default=50)
     ap.add_argument("--sched", default="res_srdiff", choices=["res_srdiff", "ddim", "ddpm"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cond", default="adapter", choices=["adapter", "controlnet"],
+                    help="condition branch: T2I-Adapter features once per slice (BASELINE headline, default) or the "
+                         "reference loop's own per-step ControlNet (res_srdiff.py:65-70)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -179,11 +185,26 @@ def main():
     unet.load_state_dict(params)
     del params
     torch.cuda.empty_cache()
-    adapter = Adapter_XL(sk=True, device=dev, generator=torch.Generator().manual_seed(2))
+    adapter = controlnet = None
+    if args.cond == "adapter":
+        adapter = Adapter_XL(sk=True, device=dev, generator=torch.Generator().manual_seed(2))
+    else:
+        from mri_diffusion_superresolution_b200.controlnet import ControlNetB200
+        from mri_diffusion_superresolution_b200.synthetic import init_controlnet_params
+        ccfg = UNetConfig()
+        controlnet = ControlNetB200(ccfg, device=dev)
+        cparams = init_controlnet_params(ccfg, seed=3, device=dev)
+        controlnet.load_state_dict(cparams)
+        del cparams
+        torch.cuda.empty_cache()
     sched = ResShiftScheduler()
     if args.sched == "ddim":
         sched = ResShiftScheduler(timestep_spacing="leading", steps_offset=1)
-    sampler = SliceSampler(unet, sched, adapter, num_inference_steps=NI, kind=args.sched)
+    sampler = SliceSampler(unet, sched, adapter, num_inference_steps=NI, kind=args.sched, controlnet=controlnet)
+    gflop_step = GFLOP_UNET_STEP + (GFLOP_CONTROLNET_STEP if controlnet is not None else 0.0)
+    gflop_once = GFLOP_ADAPTER if adapter is not None else GFLOP_CONTROLNET_EMBED
+    workload = ("sd15_unet_lora16_t2iadapter_512px_50step" if adapter is not None
+                else "sd15_unet_lora16_controlnet_512px_50step")
 
     # ---- synthetic inputs: axial slices of a phantom volume (each rank takes its own contiguous slice range)
     vol = phantom_volume(1234, device=dev)                                   # [128, 1, 512, 512] in [-1, 1]
@@ -266,35 +287,44 @@ def main():
     roof = None
     if rank == 0:
         sampler.unet.set_encoder_hidden_states(ehs)
-        feats = adapter(slices.expand(-1, 3, -1, -1).contiguous())
         tp = sampler.time_table[0:1]
         x = noises[0].contiguous()
-        unet(x, None, down_intrablock_additional_residuals=feats, time_proj=tp)   # warm
+        if adapter is not None:
+            feats = adapter(slices.expand(-1, 3, -1, -1).contiguous())
+
+            def one_step():
+                unet(x, None, down_intrablock_additional_residuals=feats, time_proj=tp)
+        else:
+            ctp = sampler.cn_time_table[0:1]
+
+            def one_step():
+                d_, m_ = controlnet(x, None, time_proj=ctp, return_dict=False)
+                unet(x, None, down_block_additional_residuals=d_, mid_block_additional_residual=m_, time_proj=tp)
+        one_step()   # warm
         torch.cuda.synchronize(dev)
         ops.GEMM_PROFILE = []
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
-        unet(x, None, down_intrablock_additional_residuals=feats, time_proj=tp)
+        one_step()
         s1.record()
         torch.cuda.synchronize(dev)
         prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
         gemm_ms = sum(a.elapsed_time(b) for _, _, a, b, _ in prof)
         conv_ms = sum(a.elapsed_time(b) for _, taps, a, b, _ in prof if taps == 9)
         step_ms = s0.elapsed_time(s1)
-        algo_tflop = B * (GFLOP_UNET_STEP - GFLOP_SDPA_STEP) / 1e3
+        sdpa = GFLOP_SDPA_STEP * (1.0 if controlnet is None else (1.0 + GFLOP_SDPA_CN_FRACTION))
+        algo_tflop = B * (gflop_step - sdpa) / 1e3
         achieved = algo_tflop / (gemm_ms / 1e3)
         peak = peaks["bf16_sustained"]
         roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (implicit-GEMM conv3x3 + linear/1x1, all epilogues)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": GEMM_DRAM_BYTES_PER_LAUNCH_B32 * B / 32.0,
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": GEMM_DRAM_BYTES_PER_LAUNCH_B32 * B / 32.0 if controlnet is None else None,
                 "traffic_source": "profiles/r1_launches_step_b32_v4.csv: dram__bytes_read.sum + dram__bytes_write.sum summed over "
                                   "the 258 gemm_tcgen05_kernel launches of one batch-32 step / 258, scaled by batch/32",
                 "peak_source": f"{peaks['src']} bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches_per_unet_forward": len(prof), "avg_launch_ms": gemm_ms / max(1, len(prof)),
                 "kernel_share_of_step": gemm_ms / step_ms, "conv3x3_share_of_step": conv_ms / step_ms,
-                "algorithmic_gflop_per_slice_step": GFLOP_UNET_STEP - GFLOP_SDPA_STEP}
-    whole = value * (NI * GFLOP_UNET_STEP + GFLOP_ADAPTER) / 1e3 / world   # TFLOP/s per GPU, algorithmic
-    if NI != 50:
-        pass
+                "algorithmic_gflop_per_slice_step": gflop_step - sdpa}
+    whole = value * (NI * gflop_step + gflop_once) / 1e3 / world   # TFLOP/s per GPU, algorithmic
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -307,14 +337,16 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": "sd15_unet_lora16_t2iadapter_512px_50step", "batch_per_gpu": B, "global_batch": B * world,
-                           "inference_steps": NI, "scheduler": args.sched, "lora_rank": 16, "adapter": "Adapter_XL(sk=True)",
+                "config": {"workload": workload, "batch_per_gpu": B, "global_batch": B * world,
+                           "inference_steps": NI, "scheduler": args.sched, "lora_rank": 16,
+                           "condition_branch": "Adapter_XL(sk=True), once per slice" if adapter is not None
+                           else "ControlNet (SD-1.5), every step",
                            "parallelism": f"slice-sharded x{world}, weights replicated, NCCL all_gather of final latents",
                            "l2": "working set (1.7 GB weights + GBs of activations per UNet forward) >> 126 MB L2; no flush needed",
                            "cuda_graph": True},
                 "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clk, "roofline": roof,
                 "whole_step": {"achieved_tflops_per_gpu": whole, "frac_of_sustained_peak": whole / peaks["bf16_sustained"],
-                               "algorithmic_tflop_per_slice": (NI * GFLOP_UNET_STEP + GFLOP_ADAPTER) / 1e3},
+                               "algorithmic_tflop_per_slice": (NI * gflop_step + gflop_once) / 1e3},
                 "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:

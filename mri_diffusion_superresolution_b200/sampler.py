@@ -23,8 +23,9 @@ Tensor = torch.Tensor
 
 class SliceSampler:
     def __init__(self, unet: UNet2DConditionB200, scheduler: ResShiftScheduler, adapter=None,
-                 num_inference_steps: int = 50, kind: str = "res_srdiff", use_cuda_graph: bool = True):
+                 num_inference_steps: int = 50, kind: str = "res_srdiff", use_cuda_graph: bool = True, controlnet=None):
         self.unet, self.scheduler, self.adapter = unet, scheduler, adapter
+        self.controlnet = controlnet    # ControlNetB200: the per-step condition branch of the reference loop (:65-70)
         self.n_steps = int(num_inference_steps)
         self.kind = kind
         self.use_graph = use_cuda_graph
@@ -36,6 +37,9 @@ class SliceSampler:
         self.ts_dev = torch.tensor(self.timesteps_host, dtype=torch.int64, device=self.device)
         # all N steps' time-embedding projections in one pass (they depend on t only)
         self.time_table = unet.time_projections(self.ts_dev.to(torch.float32)).contiguous()
+        self.cn_time_table = None
+        if controlnet is not None:
+            self.cn_time_table = controlnet.time_projections(self.ts_dev.to(torch.float32)).contiguous()
         self._graph = None
         self._shape = None
         self.kernel_launches_per_step: Optional[int] = None
@@ -49,6 +53,9 @@ class SliceSampler:
         self.z = torch.empty((self.n_steps, B, c, h, w), device=dev, dtype=torch.float32)
         self.idx = torch.zeros(1, dtype=torch.int32, device=dev)
         self.tp = torch.empty((1, self.time_table.shape[1]), device=dev, dtype=torch.float32)
+        self.cn_tp = None
+        if self.cn_time_table is not None:
+            self.cn_tp = torch.empty((1, self.cn_time_table.shape[1]), device=dev, dtype=torch.float32)
         self.feats = None
         if feat_like is not None:
             # static channels-last bf16 buffers (shape NCHW, strides NHWC) the captured graph reads
@@ -58,7 +65,12 @@ class SliceSampler:
 
     def _step(self, collect: Optional[List[Tensor]] = None):
         ops.select_row(self.time_table, self.idx, self.tp)
-        eps = self.unet(self.x, None, down_intrablock_additional_residuals=self.feats, time_proj=self.tp).sample
+        down_res = mid_res = None
+        if self.controlnet is not None:
+            ops.select_row(self.cn_time_table, self.idx, self.cn_tp)
+            down_res, mid_res = self.controlnet(self.x, None, time_proj=self.cn_tp, return_dict=False)
+        eps = self.unet(self.x, None, down_intrablock_additional_residuals=self.feats, time_proj=self.tp,
+                        down_block_additional_residuals=down_res, mid_block_additional_residual=mid_res).sample
         if collect is not None:
             collect.append(eps.clone())
         uses_lr = self.kind == "res_srdiff"
@@ -99,11 +111,16 @@ class SliceSampler:
         B, c, h, w = lr_latents.shape
         self.unet.set_encoder_hidden_states(encoder_hidden_states)
         feats = None
-        if self.adapter is not None:
+        if self.adapter is not None or self.controlnet is not None:
             if cond_image is None:
-                raise ValueError("cond_image is required when an adapter is attached")
+                raise ValueError("cond_image is required when an adapter / ControlNet is attached")
             img = cond_image.expand(-1, 3, -1, -1) if cond_image.shape[1] == 1 else cond_image
-            feats = self.adapter(img.contiguous())
+            img = img.contiguous()
+        if self.adapter is not None:
+            feats = self.adapter(img)
+        if self.controlnet is not None:
+            self.controlnet.set_encoder_hidden_states(encoder_hidden_states)
+            self.controlnet.set_condition(img, force=True)     # once per batch of slices: t-invariant
         shape = (B, h, w, feats is not None, tuple(encoder_hidden_states.shape))
         if self._shape != shape:
             self._alloc(B, h, w, feats)

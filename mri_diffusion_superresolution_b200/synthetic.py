@@ -93,13 +93,44 @@ def unet_param_shapes(cfg: UNetConfig) -> Dict[str, Tuple[int, ...]]:
     return s
 
 
-def init_unet_params(cfg: UNetConfig, seed: int = 0, device="cpu") -> Dict[str, Tensor]:
+def controlnet_param_shapes(cfg: UNetConfig, cond_channels=(16, 32, 96, 256), cond_in: int = 3) -> Dict[str, Tuple[int, ...]]:
+    """diffusers ``ControlNetModel`` state-dict keys -> shapes: the UNet's encoder half plus the condition embedding
+    and the thirteen zero convolutions (reference call site res_srdiff.py:65-70)."""
+    s = {k: v for k, v in unet_param_shapes(cfg).items()
+         if k.startswith(("conv_in.", "time_embedding.", "down_blocks.", "mid_block."))}
+    ch = cfg.block_out_channels
+    e = "controlnet_cond_embedding"
+    s[f"{e}.conv_in.weight"], s[f"{e}.conv_in.bias"] = (cond_channels[0], cond_in, 3, 3), (cond_channels[0],)
+    k = 0
+    for i in range(len(cond_channels) - 1):
+        for ci, co in ((cond_channels[i], cond_channels[i]), (cond_channels[i], cond_channels[i + 1])):
+            s[f"{e}.blocks.{k}.weight"], s[f"{e}.blocks.{k}.bias"] = (co, ci, 3, 3), (co,)
+            k += 1
+    s[f"{e}.conv_out.weight"], s[f"{e}.conv_out.bias"] = (ch[0], cond_channels[-1], 3, 3), (ch[0],)
+    skips = [ch[0]]
+    for i in range(len(ch)):
+        skips += [ch[i]] * cfg.layers_per_block
+        if i < len(ch) - 1:
+            skips.append(ch[i])
+    for i, c in enumerate(skips):
+        s[f"controlnet_down_blocks.{i}.weight"], s[f"controlnet_down_blocks.{i}.bias"] = (c, c, 1, 1), (c,)
+    s["controlnet_mid_block.weight"], s["controlnet_mid_block.bias"] = (ch[-1], ch[-1], 1, 1), (ch[-1],)
+    return s
+
+
+def init_controlnet_params(cfg: UNetConfig, seed: int = 3, device="cpu") -> Dict[str, Tensor]:
+    """Seeded random-init ControlNet weights (same distributions as ``init_unet_params``; the zero convolutions are
+    NOT zero -- a trained ControlNet's are not, and zeros would skip no work but make the residuals trivial)."""
+    return init_unet_params(cfg, seed, device, shapes=controlnet_param_shapes(cfg))
+
+
+def init_unet_params(cfg: UNetConfig, seed: int = 0, device="cpu", shapes=None) -> Dict[str, Tensor]:
     """Seeded random-init weights of the given architecture: fan-in scaled normal so the residual stream stays O(1),
     norm affine 1/0 + N(0, 0.02), LoRA A ~ N(0, 1/r), B ~ N(0, 0.02) (non-zero so the LoRA path is exercised).
     Values are rounded to bf16-representable numbers (what the kernels store) for matrices / conv filters."""
     g = torch.Generator(device=device).manual_seed(seed)
     out: Dict[str, Tensor] = {}
-    for name, shape in unet_param_shapes(cfg).items():
+    for name, shape in (shapes or unet_param_shapes(cfg)).items():
         if ".lora_A." in name:
             w = torch.randn(shape, generator=g, device=device) * (1.0 / cfg.lora_rank) ** 0.5
         elif ".lora_B." in name:

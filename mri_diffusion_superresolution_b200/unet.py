@@ -97,6 +97,8 @@ class _Attn:
 class UNet2DConditionB200:
     """B200-native drop-in for ``diffusers.UNet2DConditionModel`` on the denoising path."""
 
+    _encoder_only = False   # ControlNetB200 (controlnet.py) reuses conv_in / time embedding / down / mid only
+
     def __init__(self, config: Optional[UNetConfig] = None, device: Union[str, torch.device] = "cuda"):
         self.cfg = config or UNetConfig()
         self.device = torch.device(device)
@@ -245,24 +247,27 @@ class UNet2DConditionB200:
         self.mid = (resnet("mid_block.resnets.0", ch[-1], ch[-1]), attn("mid_block.attentions.0", ch[-1]),
                     resnet("mid_block.resnets.1", ch[-1], ch[-1]))
         self.up: List[dict] = []
-        rev = list(reversed(ch))
-        up_attn = list(reversed(c.down_has_attn))
-        cprev = ch[-1]
-        for i in range(nlev):
-            blk = {"res": [], "attn": [], "us": None}
-            for j in range(c.layers_per_block + 1):
-                cs = skip_ch.pop()
-                blk["res"].append(resnet(f"up_blocks.{i}.resnets.{j}", cprev + cs, rev[i]))
-                cprev = rev[i]
-                if up_attn[i]:
-                    blk["attn"].append(attn(f"up_blocks.{i}.attentions.{j}", rev[i]))
-            if i < nlev - 1:
-                blk["us"] = (self._dev(pack_conv3x3(get(f"up_blocks.{i}.upsamplers.0.conv.weight")), bf),
-                             self._dev(get(f"up_blocks.{i}.upsamplers.0.conv.bias"), f32))
-            self.up.append(blk)
-        self.n_out_w, self.n_out_b = self._dev(get("conv_norm_out.weight"), f32), self._dev(get("conv_norm_out.bias"), f32)
-        self.w_conv_out = self._dev(pad_rows(pack_conv3x3(get("conv_out.weight").float()), 64), bf)
-        self.b_conv_out = self._dev(pad_rows(get("conv_out.bias").float(), 64), f32)
+        if not self._encoder_only:
+            rev = list(reversed(ch))
+            up_attn = list(reversed(c.down_has_attn))
+            cprev = ch[-1]
+            for i in range(nlev):
+                blk = {"res": [], "attn": [], "us": None}
+                for j in range(c.layers_per_block + 1):
+                    cs = skip_ch.pop()
+                    blk["res"].append(resnet(f"up_blocks.{i}.resnets.{j}", cprev + cs, rev[i]))
+                    cprev = rev[i]
+                    if up_attn[i]:
+                        blk["attn"].append(attn(f"up_blocks.{i}.attentions.{j}", rev[i]))
+                if i < nlev - 1:
+                    blk["us"] = (self._dev(pack_conv3x3(get(f"up_blocks.{i}.upsamplers.0.conv.weight")), bf),
+                                 self._dev(get(f"up_blocks.{i}.upsamplers.0.conv.bias"), f32))
+                self.up.append(blk)
+            self.n_out_w, self.n_out_b = self._dev(get("conv_norm_out.weight"), f32), self._dev(get("conv_norm_out.bias"), f32)
+            self.w_conv_out = self._dev(pad_rows(pack_conv3x3(get("conv_out.weight").float()), 64), bf)
+            self.b_conv_out = self._dev(pad_rows(get("conv_out.bias").float(), 64), f32)
+        self.skip_ch = list(skip_ch) if self._encoder_only else None
+        self._load_extra(get, has)
 
         # all per-resnet time_emb_proj layers as ONE [sum(Cout), 4*C0] GEMM (they share the input silu(emb))
         self.temb_total = temb_total[0]
@@ -278,6 +283,9 @@ class UNet2DConditionB200:
         self._ehs_key = None
         self._temb_cache.clear()
         return SimpleNamespace(missing_keys=[], unexpected_keys=unexpected)
+
+    def _load_extra(self, get, has) -> None:
+        """Hook for subclasses with parameters beyond the UNet's (ControlNetB200)."""
 
     def all_attn(self) -> List[_Attn]:
         out = []
@@ -377,23 +385,19 @@ class UNet2DConditionB200:
         return ops.nchw_to_nhwc(t.contiguous(), torch.bfloat16).view(B * H * W, C)
 
     # ---- forward ------------------------------------------------------------------------------------------------
-    def __call__(self, sample: Tensor, timestep, encoder_hidden_states: Optional[Tensor] = None,
-                 down_block_additional_residuals: Optional[Sequence[Tensor]] = None,
-                 mid_block_additional_residual: Optional[Tensor] = None,
-                 down_intrablock_additional_residuals: Optional[Sequence[Tensor]] = None,
-                 return_dict: bool = True, time_proj: Optional[Tensor] = None,
-                 taps: Optional[Dict[str, Tensor]] = None, **unused):
+    def _prepare(self, sample: Tensor, timestep, encoder_hidden_states: Optional[Tensor], time_proj: Optional[Tensor]):
+        """Argument checks shared by the UNet and the ControlNet: fp32 NCHW sample, prompt K/V cache, fp32 time-embedding
+        projections ``[R, temb_pad]`` (R == 1 broadcasts over the batch)."""
         if not self._loaded:
-            raise RuntimeError("UNet2DConditionB200: load_state_dict() has not been called")
+            raise RuntimeError(f"{type(self).__name__}: load_state_dict() has not been called")
         c = self.cfg
         if not sample.is_cuda:
-            raise RuntimeError("UNet2DConditionB200 runs on CUDA only (no CPU path)")
+            raise RuntimeError(f"{type(self).__name__} runs on CUDA only (no CPU path)")
         B, cin, H, W = sample.shape
         if cin != c.in_channels:
             raise ValueError(f"sample has {cin} channels, expected {c.in_channels}")
         x32 = sample if sample.dtype == torch.float32 else ops.cast(sample.contiguous(), torch.float32)
         x32 = x32.contiguous()
-
         if encoder_hidden_states is not None:
             self.set_encoder_hidden_states(encoder_hidden_states)
         elif self._ehs_key is None:
@@ -401,8 +405,6 @@ class UNet2DConditionB200:
         kb = self.mid[1].kv_cache[1]
         if kb not in (1, B):
             raise ValueError(f"encoder_hidden_states batch {kb} does not match sample batch {B}")
-
-        # time-embedding projections (fp32 [R, temb_pad]); R == 1 broadcasts over the batch
         if time_proj is None:
             if torch.is_tensor(timestep):
                 tt = timestep.to(self.device, torch.float32).reshape(-1)
@@ -412,21 +414,17 @@ class UNet2DConditionB200:
                 raise ValueError("timestep must be a scalar or have one entry per sample")
             time_proj = self.time_projections(tt)
         temb_stride = 0 if time_proj.shape[0] == 1 else time_proj.stride(0)
+        return x32, time_proj, temb_stride
 
-        t2i = None
-        if down_intrablock_additional_residuals is not None:
-            t2i = list(down_intrablock_additional_residuals)
-            if len(t2i) != len(c.block_out_channels):
-                raise ValueError("down_intrablock_additional_residuals must have one tensor per down block")
-
-        def tap(name, v):
-            if taps is not None:  # debugging / layer-wise parity: fp32 NCHW copy under the oracle's tap names
-                taps[name] = ops.nhwc_to_nchw(v, torch.float32)
-
+    def _encode(self, x32: Tensor, time_proj: Tensor, temb_stride: int, t2i: Optional[List[Tensor]] = None,
+                tap=lambda name, v: None, conv_in_res: Optional[Tensor] = None) -> Tuple[Tensor, List[Tensor]]:
+        """conv_in + down blocks -> (running sample, the 12 skip tensors); ``conv_in_res`` ``[B*H*W, C0]`` is added to
+        the conv_in output in its epilogue (ControlNet condition embedding)."""
+        c = self.cfg
+        B, _, H, W = x32.shape
         ch = c.block_out_channels
-        nlev = len(ch)
         cols = ops.im2col_first(x32, self.kin)
-        s = ops.gemm(cols, self.w_conv_in, bias=self.b_conv_in).view(B, H, W, ch[0])
+        s = ops.gemm(cols, self.w_conv_in, bias=self.b_conv_in, res1=conv_in_res).view(B, H, W, ch[0])
         tap("conv_in", s)
         skips = [s]
         h_, w_ = H, W
@@ -447,6 +445,34 @@ class UNet2DConditionB200:
                 s = ops.gemm(s, wd, bias=bd, conv=True, stride=2).view(B, h_, w_, ch[i])  # stride-2 TMA boxes: no im2col
                 tap(f"down_blocks.{i}.downsamplers.0", s)
                 skips.append(s)
+        return s, skips
+
+    def _middle(self, s: Tensor, time_proj: Tensor, temb_stride: int) -> Tensor:
+        s = self._resnet(self.mid[0], s, None, time_proj, temb_stride)
+        s = self._transformer(self.mid[1], s)
+        return self._resnet(self.mid[2], s, None, time_proj, temb_stride)
+
+    def __call__(self, sample: Tensor, timestep, encoder_hidden_states: Optional[Tensor] = None,
+                 down_block_additional_residuals: Optional[Sequence[Tensor]] = None,
+                 mid_block_additional_residual: Optional[Tensor] = None,
+                 down_intrablock_additional_residuals: Optional[Sequence[Tensor]] = None,
+                 return_dict: bool = True, time_proj: Optional[Tensor] = None,
+                 taps: Optional[Dict[str, Tensor]] = None, **unused):
+        x32, time_proj, temb_stride = self._prepare(sample, timestep, encoder_hidden_states, time_proj)
+        c = self.cfg
+        B, _, H, W = x32.shape
+
+        t2i = None
+        if down_intrablock_additional_residuals is not None:
+            t2i = list(down_intrablock_additional_residuals)
+            if len(t2i) != len(c.block_out_channels):
+                raise ValueError("down_intrablock_additional_residuals must have one tensor per down block")
+
+        def tap(name, v):
+            if taps is not None:  # debugging / layer-wise parity: fp32 NCHW copy under the oracle's tap names
+                taps[name] = ops.nhwc_to_nchw(v, torch.float32)
+
+        s, skips = self._encode(x32, time_proj, temb_stride, t2i, tap)
         if down_block_additional_residuals is not None:
             if len(down_block_additional_residuals) != len(skips):
                 raise ValueError(f"expected {len(skips)} down_block_additional_residuals")
@@ -457,9 +483,7 @@ class UNet2DConditionB200:
             skips = new
             # the running sample is NOT modified: diffusers adds these to the stored skips only
 
-        s = self._resnet(self.mid[0], s, None, time_proj, temb_stride)
-        s = self._transformer(self.mid[1], s)
-        s = self._resnet(self.mid[2], s, None, time_proj, temb_stride)
+        s = self._middle(s, time_proj, temb_stride)
         tap("mid_block", s)
         if mid_block_additional_residual is not None:
             b_, hh, ww, cc = s.shape
