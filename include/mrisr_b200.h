@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MRISR_ABI_VERSION 2
+#define MRISR_ABI_VERSION 3
 
 #define MRISR_OK 0
 #define MRISR_E_INVALID (-1)     /* bad argument (null pointer, misaligned, negative size) */
@@ -119,7 +119,8 @@ typedef struct mrisr_gemm_args {
   int32_t reserved;
   int32_t conv_stride; /* taps == 9 only: 1 (or 0) = stride 1; 2 = stride-2 pad-1 convolution (UNet / adapter downsamplers):
                           H, W are the INPUT dims (even), M = B*(H/2)*(W/2); the TMA box walks every second pixel */
-  int32_t reserved2;
+  int32_t conv_pad_mode; /* taps == 9 only: 0 = zero padding 1 on every edge; 1 = zero padding on the bottom / right edge only
+                            (diffusers AutoencoderKL Downsample2D(padding=0): F.pad(x, (0,1,0,1)) then a stride-2 valid conv) */
 } mrisr_gemm_args;
 int mrisr_gemm(const mrisr_gemm_args* args, void* stream);
 /* N-tile the kernel will use for (N, act); GEGLU callers interleave weight/bias rows in blocks of this size:
@@ -151,6 +152,19 @@ int mrisr_bilinear_resize(const float* in, float* out, int planes, int Hin, int 
 /* decode_to_vis, src/adapters/res_srdiff.py:115-122: fp32 CHW image (first batch element) -> uint8 [H, W, 3]:
  * floor(clamp(x/2 + 0.5, 0, 1) * 255), grayscale (C == 1) replicated to 3 channels.  C in {1, 3}. */
 int mrisr_to_uint8_vis(const float* chw, uint8_t* out_hw3, int C, int H, int W, void* stream);
+
+/* ---- AutoencoderKL (the VAE either side of the loop: vae.encode(..).latent_dist.sample(), res_srdiff.py:50;
+ *      vae.decode(..).sample, res_srdiff.py:110).  Convs / GroupNorm / linears go through mrisr_gemm / mrisr_groupnorm;
+ *      the three helpers below cover what those do not. ---- */
+/* p[r, :] = softmax(scale * s[r, :]); s fp32 [rows, cols] (row stride lds), p bf16 (row stride ldp).  Single-head d = 512
+ * mid-block attention: S = Q K^T and O = P V run on mrisr_gemm, this is the softmax between them. */
+int mrisr_softmax_rows(const float* s, int64_t lds, void* p_bf16, int64_t ldp, int rows, int cols, float scale, void* stream);
+/* 1x1 convolution on small fp32 NCHW tensors (quant_conv 8->8, post_quant_conv 4->4): w fp32 [Cout, Cin], bias fp32
+ * [Cout] or NULL, Cin, Cout <= 16, HW = pixels per image. */
+int mrisr_channel_mix(const float* in, const float* w, const float* bias, float* out, int B, int Cin, int Cout, int HW, void* stream);
+/* DiagonalGaussianDistribution.sample(): moments fp32 [B, 2C, HW] = (mean | logvar), noise fp32 [B, C, HW] or NULL (.mode()):
+ * out = scale * (mean + exp(0.5 * clamp(logvar, -30, 20)) * noise). */
+int mrisr_gaussian_sample(const float* moments, const float* noise, float* out, int B, int C, int HW, float scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -29,7 +29,7 @@ class GemmArgs(C.Structure):
         ("res2", C.c_void_p), ("ldr2", C.c_int64),
         ("out", C.c_void_p), ("ldo", C.c_int64),
         ("out_fp32", C.c_int32), ("reserved", C.c_int32),
-        ("conv_stride", C.c_int32), ("reserved2", C.c_int32),
+        ("conv_stride", C.c_int32), ("conv_pad_mode", C.c_int32),
     ]
 
 
@@ -62,6 +62,9 @@ PROTOTYPES = {
     "mrisr_cast": (_I, [_P, _I, _P, _I, _L, _P]),
     "mrisr_bilinear_resize": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "mrisr_to_uint8_vis": (_I, [_P, _P, _I, _I, _I, _P]),
+    "mrisr_softmax_rows": (_I, [_P, _L, _P, _L, _I, _I, _F, _P]),
+    "mrisr_channel_mix": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "mrisr_gaussian_sample": (_I, [_P, _P, _P, _I, _I, _I, _F, _P]),
 }
 
 _lib = None
@@ -80,7 +83,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.mrisr_abi_version() != 2:
+        if lib.mrisr_abi_version() != 3:
             raise RuntimeError("libmrisr_b200.so ABI version mismatch; rebuild")
         _lib = lib
     return _lib

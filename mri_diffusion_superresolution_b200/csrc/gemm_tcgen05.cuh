@@ -39,6 +39,7 @@ struct GemmKernelParams {
   int conv;      // 0: A is [M, k]; 1: A is NHWC [B, H, W, k]
   int H, W;      // conv: OUTPUT height / width (tile -> pixel arithmetic)
   int stride;    // conv: 1 or 2 (the TMA box walks every stride-th input pixel)
+  int pad;       // conv: zero padding on the top / left edge (1 = symmetric pad 1; 0 = diffusers VAE (0,1,0,1) padding)
   int m_tiles, n_tiles;
   int res_mma;    // residual operands folded into the MMA K loop (0, 1 or 2)
   int tma_store;  // bf16 output written by TMA from the swizzled staging buffers
@@ -436,8 +437,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
         x0 = rem - h0 * p.W;
       }
       for (int tap = 0; tap < p.taps; ++tap) {
-        const int dr = (p.taps == 9) ? tap / 3 - 1 : 0;
-        const int ds = (p.taps == 9) ? tap % 3 - 1 : 0;
+        const int dr = (p.taps == 9) ? tap / 3 - p.pad : 0;
+        const int ds = (p.taps == 9) ? tap % 3 - p.pad : 0;
         for (int kc = 0; kc < kchunks; ++kc) {
           const bool first = kc < p.kc1;
           load(first ? &maps.a1 : &maps.a2, p.conv != 0, (first ? kc : kc - p.kc1) * kBlockK, x0 * p.stride + ds, h0 * p.stride + dr, b0, m0, &maps.b,

@@ -636,6 +636,8 @@ int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
   p.M = g->M; p.N = g->N; p.n_store = g->n_store;
   p.kc1 = g->k1 / 64; p.kc2 = g->k2 / 64; p.taps = g->taps; p.conv = g->taps == 9 ? 1 : 0;
   p.stride = (g->taps == 9 && g->conv_stride == 2) ? 2 : 1;
+  MRISR_REQUIRE(g->conv_pad_mode == 0 || (g->conv_pad_mode == 1 && g->taps == 9), "gemm: conv_pad_mode must be 0, or 1 with taps == 9");
+  p.pad = g->conv_pad_mode == 1 ? 0 : 1;
   p.H = g->H / p.stride; p.W = g->W / p.stride;
   p.m_tiles = (g->M + 127) / 128; p.n_tiles = g->N / BN;
   p.bias = g->bias; p.rowvec = g->rowvec; p.rowvec_stride = g->rowvec_stride;
@@ -824,6 +826,35 @@ int mrisr_bilinear_resize(const float* in, float* out, int planes, int Hin, int 
 int mrisr_to_uint8_vis(const float* chw, uint8_t* out, int C, int H, int W, void* stream) {
   MRISR_REQUIRE(chw && out && (C == 1 || C == 3) && H > 0 && W > 0, "to_uint8_vis: C must be 1 or 3");
   launch_k(mrisr::to_uint8_vis_kernel, dim3(grid_for(static_cast<long long>(H) * W * 3, 256, 8)), dim3(256), 0, as_stream(stream), chw, out, C, H, W);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mrisr_softmax_rows(const float* s, int64_t lds, void* p, int64_t ldp, int rows, int cols, float scale, void* stream) {
+  MRISR_REQUIRE(s && p && rows > 0 && cols > 0, "softmax_rows: bad argument");
+  MRISR_REQUIRE(cols % 4 == 0 && cols <= 49152 && lds % 4 == 0 && ldp % 4 == 0 && lds >= cols && ldp >= cols, "softmax_rows: cols (%d) must be a multiple of 4, <= 49152; strides multiples of 4", cols);
+  MRISR_REQUIRE(aligned16(s) && (reinterpret_cast<uintptr_t>(p) & 7) == 0, "softmax_rows: misaligned pointer");
+  const size_t smem = static_cast<size_t>(cols) * 4;
+  if (smem > 48 * 1024) MRISR_CHECK_CUDA(cudaFuncSetAttribute(mrisr::softmax_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const int per_sm = smem <= 16 * 1024 ? 8 : (smem <= 48 * 1024 ? 4 : 1);
+  const int grid = rows < sms * per_sm ? rows : sms * per_sm;
+  launch_k(mrisr::softmax_rows_kernel, dim3(grid), dim3(256), smem, as_stream(stream), s, static_cast<long long>(lds), static_cast<__nv_bfloat16*>(p), static_cast<long long>(ldp), rows, cols, scale * 1.4426950408889634f);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mrisr_channel_mix(const float* in, const float* w, const float* bias, float* out, int B, int Cin, int Cout, int HW, void* stream) {
+  MRISR_REQUIRE(in && w && out && B > 0 && HW > 0 && Cin > 0 && Cin <= 16 && Cout > 0 && Cout <= 16, "channel_mix: Cin, Cout must be in [1, 16]");
+  launch_k(mrisr::channel_mix_kernel, dim3(grid_for(static_cast<long long>(B) * HW, 256, 8)), dim3(256), 0, as_stream(stream), in, w, bias, out, B, Cin, Cout, HW);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mrisr_gaussian_sample(const float* moments, const float* noise, float* out, int B, int C, int HW, float scale, void* stream) {
+  MRISR_REQUIRE(moments && out && B > 0 && C > 0 && HW > 0, "gaussian_sample: bad argument");
+  launch_k(mrisr::gaussian_sample_kernel, dim3(grid_for(static_cast<long long>(B) * C * HW, 256, 8)), dim3(256), 0, as_stream(stream), moments, noise, out, B, C, HW, scale);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

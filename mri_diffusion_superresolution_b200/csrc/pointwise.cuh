@@ -722,4 +722,103 @@ __global__ void advance_index_kernel(int* idx) {
   grid_dep_launch();
   grid_dep_wait(); if (threadIdx.x == 0 && blockIdx.x == 0) *idx += 1; }
 
+// Row softmax of fp32 logits -> bf16 probabilities: p[r, :] = softmax(scale * s[r, :]).  One CTA per row (grid-stride),
+// the row is staged in shared memory so HBM sees one 4-byte read and one 2-byte write per element.  Used by the
+// single-head d = 512 mid-block attention of the VAE (QK^T and PV run on the tensor-core GEMM kernel).
+__global__ void softmax_rows_kernel(const float* __restrict__ s, long long lds, __nv_bfloat16* __restrict__ p, long long ldp,
+                                    int rows, int cols, float scale_log2e) {
+  grid_dep_launch();
+  grid_dep_wait();
+  extern __shared__ float srow[];
+  __shared__ float red[32];
+  const int nv = cols >> 2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float4* src = reinterpret_cast<const float4*>(s + r * lds);
+    float m = -INFINITY;
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+      const float4 v = __ldg(src + i);
+      reinterpret_cast<float4*>(srow)[i] = v;
+      m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    m = red[0];
+    for (int w = 1; w < nwarp; ++w) m = fmaxf(m, red[w]);
+    __syncthreads();
+    const float off = m * scale_log2e;
+    float sum = 0.f;
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {   // each thread revisits the elements it staged itself
+      float4 v = reinterpret_cast<float4*>(srow)[i];
+      v.x = exp2f(fmaf(v.x, scale_log2e, -off));
+      v.y = exp2f(fmaf(v.y, scale_log2e, -off));
+      v.z = exp2f(fmaf(v.z, scale_log2e, -off));
+      v.w = exp2f(fmaf(v.w, scale_log2e, -off));
+      reinterpret_cast<float4*>(srow)[i] = v;
+      sum += (v.x + v.y) + (v.z + v.w);
+    }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    sum = 0.f;
+    for (int w = 0; w < nwarp; ++w) sum += red[w];   // fixed order: deterministic
+    const float inv = 1.f / sum;
+    uint2* dst = reinterpret_cast<uint2*>(p + r * ldp);
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+      const float4 v = reinterpret_cast<float4*>(srow)[i];
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x * inv, v.y * inv), hi = __floats2bfloat162_rn(v.z * inv, v.w * inv);
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&lo);
+      o.y = *reinterpret_cast<const uint32_t*>(&hi);
+      dst[i] = o;
+    }
+    __syncthreads();
+  }
+}
+
+// Per-pixel channel mix (1x1 convolution) on small fp32 NCHW tensors: out[b, co, p] = bias[co] + sum_ci w[co, ci] *
+// in[b, ci, p], Cin, Cout <= 16.  AutoencoderKL quant_conv (8 -> 8) and post_quant_conv (4 -> 4).
+__global__ void channel_mix_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                                   float* __restrict__ out, int B, int Cin, int Cout, int HW) {
+  grid_dep_launch();
+  grid_dep_wait();
+  __shared__ float sw[16 * 16 + 16];
+  for (int i = threadIdx.x; i < Cin * Cout; i += blockDim.x) sw[i] = __ldg(w + i);
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[256 + i] = bias ? __ldg(bias + i) : 0.f;
+  __syncthreads();
+  const long long total = static_cast<long long>(B) * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / HW, px = i - b * HW;
+    float x[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) x[c] = c < Cin ? __ldg(in + (b * Cin + c) * HW + px) : 0.f;
+    for (int co = 0; co < Cout; ++co) {
+      float acc = sw[256 + co];
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        if (c < Cin) acc = fmaf(sw[co * Cin + c], x[c], acc);
+      out[(b * Cout + co) * HW + px] = acc;
+    }
+  }
+}
+
+// diffusers DiagonalGaussianDistribution.sample(): moments fp32 [B, 2C, HW] = (mean | logvar) ->
+// out[B, C, HW] = scale * (mean + exp(0.5 * clamp(logvar, -30, 20)) * noise); noise == nullptr gives scale * mean (.mode()).
+__global__ void gaussian_sample_kernel(const float* __restrict__ moments, const float* __restrict__ noise, float* __restrict__ out,
+                                       int B, int C, int HW, float scale) {
+  grid_dep_launch();
+  grid_dep_wait();
+  const long long per = static_cast<long long>(C) * HW, total = per * B;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / per, r = i - b * per;
+    const float mean = __ldg(moments + b * 2 * per + r);
+    float v = mean;
+    if (noise != nullptr) {
+      const float lv = fminf(fmaxf(__ldg(moments + b * 2 * per + per + r), -30.f), 20.f);
+      v = fmaf(expf(0.5f * lv), __ldg(noise + i), mean);
+    }
+    out[i] = v * scale;
+  }
+}
+
 }  // namespace mrisr

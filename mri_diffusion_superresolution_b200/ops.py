@@ -52,7 +52,7 @@ def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[T
          rowvec: Optional[Tensor] = None, rowvec_stride: int = 0, rows_per_batch: int = 0, act: int = ACT_NONE,
          res1: Optional[Tensor] = None, res2: Optional[Tensor] = None, n_store: Optional[int] = None,
          out_fp32: bool = False, conv: bool = False, stride: int = 1, out: Optional[Tensor] = None,
-         _dbg: int = 0) -> Tensor:
+         pad_mode: int = 0, _dbg: int = 0) -> Tensor:
     """``act(concat_K(a1, a2) @ w.T + bias + rowvec[batch]) + res1 + res2`` on the tcgen05 kernel.
 
     GEMM mode: a1 ``[M, k1]`` (+ a2 ``[M, k2]``).  ``conv=True``: a1/a2 are NHWC ``[B, H, W, k]`` and ``w`` is
@@ -72,6 +72,7 @@ def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[T
             raise ValueError("gemm(conv): stride must be 1 or 2 (even H, W)")
         M, taps = B * (H // stride) * (W // stride), 9
         g.conv_stride = stride
+        g.conv_pad_mode = pad_mode      # 1: zero padding on the bottom / right edge only (AutoencoderKL downsamplers)
         k2, lda2 = 0, 0
         if a2 is not None:
             _cuda(a2, "gemm.a2", torch.bfloat16)
@@ -347,6 +348,16 @@ def nhwc_to_nchw(x: Tensor, dtype=torch.float32) -> Tensor:
     return out
 
 
+def transpose_bf16(x: Tensor) -> Tensor:
+    """bf16 [B, R, C] -> [B, C, R] (V -> V^T, the K-major operand of the VAE attention's P @ V GEMM)."""
+    lib = _lib.load()
+    _cuda(x, "transpose_bf16.x", torch.bfloat16)
+    B, R, c = x.shape
+    out = torch.empty((B, c, R), device=x.device, dtype=torch.bfloat16)
+    _lib.check(lib.mrisr_transpose(x.contiguous().data_ptr(), 1, out.data_ptr(), 1, B, R, c, _stream(x)), "mrisr_transpose")
+    return out
+
+
 def cast(x: Tensor, dtype) -> Tensor:
     lib = _lib.load()
     _cuda(x, "cast.x")
@@ -354,6 +365,49 @@ def cast(x: Tensor, dtype) -> Tensor:
         return x
     out = torch.empty(x.shape, device=x.device, dtype=dtype)
     _lib.check(lib.mrisr_cast(x.data_ptr(), _DT[x.dtype], out.data_ptr(), _DT[dtype], x.numel(), _stream(x)), "mrisr_cast")
+    return out
+
+
+def softmax_rows(s: Tensor, scale: float, out: Optional[Tensor] = None) -> Tensor:
+    """bf16 ``softmax(scale * s, dim=-1)`` of fp32 logits ``[rows, cols]`` (the VAE's single-head attention)."""
+    lib = _lib.load()
+    _cuda(s, "softmax_rows.s", torch.float32)
+    rows, cols = s.shape
+    if out is None:
+        out = torch.empty((rows, cols), device=s.device, dtype=torch.bfloat16)
+    _lib.check(lib.mrisr_softmax_rows(s.data_ptr(), _rows(s, "s"), _cuda(out, "softmax_rows.out", torch.bfloat16).data_ptr(),
+                                      _rows(out, "out"), rows, cols, float(scale), _stream(s)), "mrisr_softmax_rows")
+    return out
+
+
+def channel_mix(x: Tensor, w: Tensor, bias: Optional[Tensor]) -> Tensor:
+    """1x1 conv on a small fp32 NCHW tensor (quant_conv / post_quant_conv): w fp32 ``[Cout, Cin]``."""
+    lib = _lib.load()
+    _cuda(x, "channel_mix.x", torch.float32)
+    _cuda(w, "channel_mix.w", torch.float32)
+    B, cin, H, W = x.shape
+    cout = w.shape[0]
+    if w.shape[1] != cin:
+        raise ValueError(f"channel_mix: weight is {tuple(w.shape)}, input has {cin} channels")
+    out = torch.empty((B, cout, H, W), device=x.device, dtype=torch.float32)
+    _lib.check(lib.mrisr_channel_mix(x.contiguous().data_ptr(), w.contiguous().data_ptr(), _ptr(bias), out.data_ptr(), B, cin, cout,
+                                     H * W, _stream(x)), "mrisr_channel_mix")
+    return out
+
+
+def gaussian_sample(moments: Tensor, noise: Optional[Tensor], scale: float = 1.0) -> Tensor:
+    """``scale * (mean + exp(0.5*clamp(logvar, -30, 20)) * noise)`` from fp32 moments ``[B, 2C, H, W]``; noise None = mode."""
+    lib = _lib.load()
+    _cuda(moments, "gaussian_sample.moments", torch.float32)
+    B, c2, H, W = moments.shape
+    if noise is not None:
+        _cuda(noise, "gaussian_sample.noise", torch.float32)
+        if tuple(noise.shape) != (B, c2 // 2, H, W):
+            raise ValueError("gaussian_sample: noise must be [B, C, H, W]")
+        noise = noise.contiguous()
+    out = torch.empty((B, c2 // 2, H, W), device=moments.device, dtype=torch.float32)
+    _lib.check(lib.mrisr_gaussian_sample(moments.contiguous().data_ptr(), _ptr(noise), out.data_ptr(), B, c2 // 2, H * W,
+                                         float(scale), _stream(moments)), "mrisr_gaussian_sample")
     return out
 
 

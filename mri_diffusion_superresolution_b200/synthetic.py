@@ -118,6 +118,73 @@ def controlnet_param_shapes(cfg: UNetConfig, cond_channels=(16, 32, 96, 256), co
     return s
 
 
+def vae_param_shapes(cfg=None) -> Dict[str, Tuple[int, ...]]:
+    """diffusers ``AutoencoderKL`` state-dict keys -> shapes (SD-1.5 VAE by default; call sites res_srdiff.py:50,110)."""
+    from .vae import VAEConfig
+    cfg = cfg or VAEConfig()
+    ch, n, L = cfg.block_out_channels, len(cfg.block_out_channels), cfg.latent_channels
+    s: Dict[str, Tuple[int, ...]] = {}
+
+    def conv(key, co, ci, k):
+        s[f"{key}.weight"], s[f"{key}.bias"] = (co, ci, k, k), (co,)
+
+    def resnet(key, ci, co):
+        s[f"{key}.norm1.weight"], s[f"{key}.norm1.bias"] = (ci,), (ci,)
+        conv(f"{key}.conv1", co, ci, 3)
+        s[f"{key}.norm2.weight"], s[f"{key}.norm2.bias"] = (co,), (co,)
+        conv(f"{key}.conv2", co, co, 3)
+        if ci != co:
+            conv(f"{key}.conv_shortcut", co, ci, 1)
+
+    def mid(key, c):
+        resnet(f"{key}.resnets.0", c, c)
+        s[f"{key}.attentions.0.group_norm.weight"], s[f"{key}.attentions.0.group_norm.bias"] = (c,), (c,)
+        for nm in ("to_q", "to_k", "to_v", "to_out.0"):
+            s[f"{key}.attentions.0.{nm}.weight"], s[f"{key}.attentions.0.{nm}.bias"] = (c, c), (c,)
+        resnet(f"{key}.resnets.1", c, c)
+
+    conv("encoder.conv_in", ch[0], cfg.in_channels, 3)
+    prev = ch[0]
+    for i in range(n):
+        for j in range(cfg.layers_per_block):
+            resnet(f"encoder.down_blocks.{i}.resnets.{j}", prev, ch[i])
+            prev = ch[i]
+        if i < n - 1:
+            conv(f"encoder.down_blocks.{i}.downsamplers.0.conv", ch[i], ch[i], 3)
+    mid("encoder.mid_block", ch[-1])
+    s["encoder.conv_norm_out.weight"], s["encoder.conv_norm_out.bias"] = (ch[-1],), (ch[-1],)
+    conv("encoder.conv_out", 2 * L, ch[-1], 3)
+    conv("quant_conv", 2 * L, 2 * L, 1)
+    conv("post_quant_conv", L, L, 1)
+    conv("decoder.conv_in", ch[-1], L, 3)
+    mid("decoder.mid_block", ch[-1])
+    rev = list(reversed(ch))
+    prev = rev[0]
+    for i in range(n):
+        for j in range(cfg.layers_per_block + 1):
+            resnet(f"decoder.up_blocks.{i}.resnets.{j}", prev, rev[i])
+            prev = rev[i]
+        if i < n - 1:
+            conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", rev[i], rev[i], 3)
+    s["decoder.conv_norm_out.weight"], s["decoder.conv_norm_out.bias"] = (ch[0],), (ch[0],)
+    conv("decoder.conv_out", cfg.out_channels, ch[0], 3)
+    return s
+
+
+def init_vae_params(cfg=None, seed: int = 5, device="cpu") -> Dict[str, Tensor]:
+    """Seeded random-init AutoencoderKL weights (fan-in scaled normal, norm affine 1/0 + N(0, 0.02))."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    out: Dict[str, Tensor] = {}
+    for name, shape in vae_param_shapes(cfg).items():
+        if len(shape) == 1:
+            w = torch.randn(shape, generator=g, device=device) * 0.02 + (1.0 if name.endswith("weight") and "norm" in name else 0.0)
+        else:
+            w = torch.randn(shape, generator=g, device=device) * (0.7 / math.sqrt(math.prod(shape[1:])))
+            w = w.to(torch.bfloat16).float()
+        out[name] = w
+    return out
+
+
 def init_controlnet_params(cfg: UNetConfig, seed: int = 3, device="cpu") -> Dict[str, Tensor]:
     """Seeded random-init ControlNet weights (same distributions as ``init_unet_params``; the zero convolutions are
     NOT zero -- a trained ControlNet's are not, and zeros would skip no work but make the residuals trivial)."""

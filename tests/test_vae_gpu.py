@@ -1,0 +1,164 @@
+"""Parity of the CUDA AutoencoderKL (vae.encode / vae.decode either side of the loop, res_srdiff.py:50,110) and its
+helper kernels against the CPU oracle restatement (``oracle/vae_oracle.py``) on identical seeded weights and inputs.
+Tolerances: north_star's bf16 figures -- <= 1e-2 relative L2 on the network outputs, decoded image PSNR >= 40 dB."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+REL_L2_BF16 = 1e-2
+PSNR_MIN_DB = 40.0
+SMALL = dict(block_out_channels=(64, 128, 128), layers_per_block=1)
+
+
+def _rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+def _psnr_img(a, b):
+    """PSNR of [-1, 1] images mapped to [0, 1] (reference convention: res_srdiff.py:115, eval.py:15 data_range=1)."""
+    a = (a.float().cpu() / 2 + 0.5).clamp(0, 1)
+    b = (b.float().cpu() / 2 + 0.5).clamp(0, 1)
+    return 10 * np.log10(1.0 / max(((a - b) ** 2).mean().item(), 1e-30))
+
+
+def _round_bf16(p):
+    return {k: (v.to(torch.bfloat16).float() if v.dim() > 1 else v) for k, v in p.items()}
+
+
+def _make(cfg_kw, seed=5):
+    from oracle import vae_oracle as vo
+    from mri_diffusion_superresolution_b200.vae import AutoencoderKLB200, VAEConfig
+
+    ocfg = vo.VAEConfig(**cfg_kw)
+    params = _round_bf16(vo.init_params(ocfg, seed=seed))
+    vae = AutoencoderKLB200(VAEConfig(**cfg_kw))
+    vae.load_state_dict(params)
+    return vo, ocfg, params, vae
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from mri_diffusion_superresolution_b200 import ops as o
+    return o
+
+
+@pytest.mark.parametrize("B,H,C,N", [(2, 64, 128, 128), (1, 512, 128, 128), (1, 16, 64, 256)])
+def test_conv3x3_stride2_asymmetric_pad(ops, B, H, C, N):
+    """AutoencoderKL Downsample2D(padding=0): F.pad(x, (0,1,0,1)) then a stride-2 valid conv == conv_pad_mode 1."""
+    from mri_diffusion_superresolution_b200.packing import pack_conv3x3
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(B, H, H, C, generator=g).to(torch.bfloat16).cuda()
+    w = (torch.randn(N, C, 3, 3, generator=g) / math.sqrt(9 * C)).to(torch.bfloat16).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    out = ops.gemm(x, pack_conv3x3(w), bias=bias, conv=True, stride=2, pad_mode=1)
+    ref = F.conv2d(F.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1)), w.float(), bias, stride=2).permute(0, 2, 3, 1).reshape(-1, N)
+    assert _rel(out, ref) < 4e-3
+    with pytest.raises(ValueError):
+        ops.gemm(x.view(-1, C), w.view(N, -1)[:, :C].contiguous(), pad_mode=1)     # pad mode is a conv-only argument
+
+
+@pytest.mark.parametrize("rows,cols", [(256, 256), (4096, 4096), (37, 1024), (8, 16384)])
+def test_softmax_rows(ops, rows, cols):
+    g = torch.Generator().manual_seed(32)
+    s = (torch.randn(rows, cols, generator=g) * 20).cuda()
+    p = ops.softmax_rows(s, 512 ** -0.5)
+    ref = torch.softmax(s * 512 ** -0.5, dim=-1)
+    assert p.dtype == torch.bfloat16
+    assert (p.float() - ref).abs().max().item() <= ref.max().item() * 2 ** -8
+    assert (p.float().sum(-1) - 1).abs().max().item() < 5e-3
+    # strided views (a column block of a wider logits buffer)
+    wide = torch.empty(rows, cols + 64, device="cuda")
+    wide[:, :cols] = s
+    assert torch.equal(ops.softmax_rows(wide[:, :cols], 512 ** -0.5), p)
+    with pytest.raises(ValueError):
+        ops.softmax_rows(s[:, :cols - 2], 1.0)
+
+
+def test_channel_mix_and_gaussian_sample(ops):
+    g = torch.Generator().manual_seed(33)
+    for cin, cout in ((8, 8), (4, 4), (3, 16)):
+        x = torch.randn(3, cin, 16, 16, generator=g).cuda()
+        w = torch.randn(cout, cin, generator=g).cuda()
+        b = torch.randn(cout, generator=g).cuda()
+        ref = F.conv2d(x, w[:, :, None, None], b)
+        torch.testing.assert_close(ops.channel_mix(x, w, b), ref, rtol=1e-5, atol=1e-5)
+    mom = torch.randn(2, 8, 16, 16, generator=g).cuda()
+    mom[:, 4:] *= 30                                            # exercises the (-30, 20) clamp
+    noise = torch.randn(2, 4, 16, 16, generator=g).cuda()
+    ref = mom[:, :4] + torch.exp(0.5 * mom[:, 4:].clamp(-30, 20)) * noise
+    torch.testing.assert_close(ops.gaussian_sample(mom, noise), ref, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(ops.gaussian_sample(mom, noise, 0.18215), ref * 0.18215, rtol=1e-5, atol=1e-6)
+    assert torch.equal(ops.gaussian_sample(mom, None), mom[:, :4])
+
+
+def test_vae_small_vs_oracle():
+    vo, ocfg, params, vae = _make(SMALL)
+    g = torch.Generator().manual_seed(41)
+    B = 3
+    x = (torch.rand(B, 3, 64, 64, generator=g) * 2 - 1).to(torch.bfloat16).float()
+    ref_m = vo.encode_moments(params, x, ocfg)
+    vae.max_batch = 2                                           # exercises the chunked path (2 + 1 images)
+    dist = vae.encode(x.cuda()).latent_dist
+    assert tuple(dist.parameters.shape) == tuple(ref_m.shape)
+    assert _rel(dist.parameters, ref_m) < REL_L2_BF16
+    assert torch.equal(dist.mode(), dist.mean)
+    noise = torch.randn(B, 4, 16, 16, generator=g)
+    z_ref = vo.posterior_sample(ref_m, noise)
+    z = dist.sample(noise=noise.cuda())
+    assert _rel(z, z_ref) < REL_L2_BF16
+    # global-RNG draw, exactly one torch.randn of the latent shape (RNG draw order of the reference: VAE posterior first)
+    torch.manual_seed(7)
+    a = dist.sample()
+    torch.manual_seed(7)
+    n2 = torch.randn(B, 4, 16, 16, device="cuda")
+    assert torch.equal(a, dist.sample(noise=n2))
+    ref_img = vo.decode(params, z_ref, ocfg)
+    img = vae.decode(z_ref.cuda()).sample
+    assert tuple(img.shape) == (B, 3, 64, 64) and img.dtype == torch.float32
+    assert _rel(img, ref_img) < REL_L2_BF16
+    assert _psnr_img(img, ref_img) >= PSNR_MIN_DB
+    # legacy attention key names (pre-0.20 diffusers checkpoints: query / key / value / proj_attn as 1x1 convs)
+    legacy = {}
+    for k, v in params.items():
+        for new, old in (("to_q", "query"), ("to_k", "key"), ("to_v", "value"), ("to_out.0", "proj_attn")):
+            if f".attentions.0.{new}." in k:
+                k = k.replace(f".{new}.", f".{old}.")
+                v = v[:, :, None, None] if v.dim() == 2 else v
+        legacy[k] = v
+    from mri_diffusion_superresolution_b200.vae import AutoencoderKLB200, VAEConfig
+    v2 = AutoencoderKLB200(VAEConfig(**SMALL))
+    v2.load_state_dict(legacy)
+    assert torch.equal(v2.decode(z_ref.cuda()).sample, vae.decode(z_ref.cuda()).sample)
+    with pytest.raises(KeyError):
+        v2.load_state_dict(dict(params, bogus=torch.zeros(1)))
+    with pytest.raises(RuntimeError):
+        vae.decode(z_ref)
+    with pytest.raises(ValueError):
+        vae.encode(torch.zeros(1, 3, 48, 48, device="cuda"))
+
+
+def test_vae_sd15_full_512():
+    """The real SD-1.5 VAE (83.65 M params) on one 512x512 slice: encoder moments and decoded image vs the fp32 oracle."""
+    vo, ocfg, params, vae = _make({})
+    g = torch.Generator().manual_seed(42)
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, 512), torch.linspace(-1, 1, 512), indexing="ij")
+    x = (torch.exp(-3 * (xx ** 2 + yy ** 2)) * 1.6 - 0.8 + 0.05 * torch.randn(512, 512, generator=g)).clamp(-1, 1)
+    x = x[None, None].expand(1, 3, -1, -1).to(torch.bfloat16).float()
+    torch.set_num_threads(os.cpu_count() or 8)
+    ref_m = vo.encode_moments(params, x, ocfg)
+    dist = vae.encode(x.cuda()).latent_dist
+    assert tuple(dist.parameters.shape) == (1, 8, 64, 64)
+    assert _rel(dist.parameters, ref_m) < REL_L2_BF16
+    z = ref_m[:, :4]
+    ref_img = vo.decode(params, z, ocfg)
+    img = vae.decode(z.cuda()).sample
+    assert tuple(img.shape) == (1, 3, 512, 512)
+    assert _rel(img, ref_img) < REL_L2_BF16
+    assert _psnr_img(img, ref_img) >= PSNR_MIN_DB
