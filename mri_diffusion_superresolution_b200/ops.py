@@ -81,6 +81,8 @@ def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[T
             k2, lda2 = a2.shape[3], a2.stride(2)
         g.H, g.W = H, W
     else:
+        if pad_mode or stride != 1:
+            raise ValueError("gemm: stride / pad_mode are conv-only arguments")
         lda1 = _rows(a1, "gemm.a1")
         M, k1 = a1.shape
         taps, k2, lda2 = 1, 0, 0

@@ -15,6 +15,9 @@ log_validation.npz ``log_validation`` (src/adapters/res_srdiff.py:35-105) driven
                   unet / controlnet / vae objects (deterministic closed-form functions) and injected
                   noise; records every latent the loop handed to the UNet, the timesteps, and the
                   returned image.  N = 6 and N = 50 steps.
+log_validation_nets.npz the same ``log_validation`` driven around the ORACLE UNet+LoRA / ControlNet / VAE (reduced
+                  width, 512x512 slices, 4 steps): the end-to-end pin of the full drop-in (CUDA UNet + ControlNet +
+                  VAE under this repo's ``log_validation``).
 adapter_xl_*.npz  ``Adapter_XL`` (src/adapters/modules.py:114-157) outputs for small channel configs,
                   with the module's own initialised weights stored alongside.
 """
@@ -128,6 +131,78 @@ def gen_log_validation():
     np.savez_compressed(os.path.join(OUT, "log_validation.npz"), **out)
 
 
+def gen_log_validation_nets():
+    """The REFERENCE's ``log_validation`` (src/adapters/res_srdiff.py:35-105) run end to end around the oracle
+    restatements of the three networks it calls -- ``vae.encode`` (:50), ``controlnet`` (:65-70), ``unet`` (:73-78),
+    ``vae.decode`` (:110) -- at reduced width, 512x512 slices, 4 steps, injected noise.  Records every latent handed to
+    the UNet, the timesteps, the final latents and the generated panel of the returned image."""
+    import src.adapters.res_srdiff as ref
+    from oracle import controlnet_oracle as co
+    from oracle import unet_oracle as uo
+    from oracle import vae_oracle as vo
+    from oracle.make_golden_stub import (NETS_SEEDS, NETS_STEPS, NETS_UNET_CFG, NETS_VAE_CFG, nets_fixture_inputs,
+                                         round_bf16)
+
+    ucfg = uo.UNetConfig(**NETS_UNET_CFG)
+    vcfg = vo.VAEConfig(**NETS_VAE_CFG)
+    up = round_bf16(uo.init_params(ucfg, seed=NETS_SEEDS["unet"]))
+    cp = round_bf16(co.init_params(ucfg, seed=NETS_SEEDS["controlnet"]))
+    vp = round_bf16(vo.init_params(vcfg, seed=NETS_SEEDS["vae"]))
+    lr_img, hr_img, ehs = nets_fixture_inputs()
+    g = torch.Generator().manual_seed(NETS_SEEDS["data"] + 1)
+    post_noise = torch.randn(1, 4, 64, 64, generator=g)
+    noises = [torch.randn(1, 4, 64, 64, generator=g) for _ in range(NETS_STEPS + 1)]
+    queue = list(noises)
+    rec = {"lat_in": [], "t": [], "eps": [], "final": None}
+
+    class VAE:
+        config = types.SimpleNamespace(scaling_factor=vcfg.scaling_factor)
+
+        def encode(self, x):
+            m = vo.encode_moments(vp, x.float(), vcfg)
+            return types.SimpleNamespace(latent_dist=types.SimpleNamespace(sample=lambda: vo.posterior_sample(m, post_noise)))
+
+        def decode(self, z):
+            rec["final"] = (z * vcfg.scaling_factor).clone()
+            return types.SimpleNamespace(sample=vo.decode(vp, z.float(), vcfg))
+
+    class UNet:
+        def eval(self):
+            return self
+
+        def __call__(self, latents, t, encoder_hidden_states=None, down_block_additional_residuals=None,
+                     mid_block_additional_residual=None):
+            rec["lat_in"].append(latents.clone())
+            rec["t"].append(int(t))
+            e = uo.unet_forward(up, latents, t, encoder_hidden_states, ucfg,
+                                down_block_additional_residuals=down_block_additional_residuals,
+                                mid_block_additional_residual=mid_block_additional_residual)
+            rec["eps"].append(e.clone())
+            return types.SimpleNamespace(sample=e)
+
+    class ControlNet:
+        def eval(self):
+            return self
+
+        def __call__(self, latents, t, encoder_hidden_states=None, controlnet_cond=None, return_dict=False):
+            return co.controlnet_forward(cp, latents, t, encoder_hidden_states, controlnet_cond, ucfg)
+
+    orig = torch.randn_like
+    torch.randn_like = lambda x, *a, **k: queue.pop(0).to(x.dtype)
+    try:
+        img = ref.log_validation(UNet(), ControlNet(), VAE(), [{"hr": hr_img, "lr": lr_img}], StubScheduler(), torch.float32,
+                                 types.SimpleNamespace(device=torch.device("cpu")), ehs, num_inference_steps=NETS_STEPS)
+    finally:
+        torch.randn_like = orig
+    img = np.asarray(img)
+    assert img.shape == (512, 1536, 3)
+    np.savez_compressed(os.path.join(OUT, "log_validation_nets.npz"),
+                        post_noise=post_noise.numpy(), noises=torch.stack(noises).numpy(), noises_left=np.int64(len(queue)),
+                        lat_in=torch.stack(rec["lat_in"]).numpy(), t=np.asarray(rec["t"], dtype=np.int64),
+                        eps0=rec["eps"][0].numpy(), final_latents=rec["final"].numpy(),
+                        lr_panel=img[:, :512], gen_panel=img[:, 512:1024], hr_panel=img[:, 1024:])
+
+
 def gen_prepare_condition():
     from src.adapters.res_srdiff import prepare_condition_image
 
@@ -193,6 +268,7 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gen_res_shift()
     gen_log_validation()
+    gen_log_validation_nets()
     gen_prepare_condition()
     gen_adapter()
     for f in sorted(os.listdir(OUT)):

@@ -162,3 +162,70 @@ def test_vae_sd15_full_512():
     assert tuple(img.shape) == (1, 3, 512, 512)
     assert _rel(img, ref_img) < REL_L2_BF16
     assert _psnr_img(img, ref_img) >= PSNR_MIN_DB
+
+
+def test_full_dropin_log_validation_vs_reference_golden(golden_dir):
+    """This repo's ``log_validation`` around the CUDA UNet+LoRA, ControlNet and VAE, against the REFERENCE's
+    ``log_validation`` run around the oracle restatements of the same three networks on the same weights, images and
+    injected noise (fixture: oracle/make_golden.py::gen_log_validation_nets).  Timestep bookkeeping and the number of
+    RNG draws bit-exact; step-0 latents (VAE encode + forward shifting) and every later latent handed to the UNet,
+    the final latents and the generated image panel within the bf16 tolerances."""
+    import types
+
+    from oracle import controlnet_oracle as co
+    from oracle import unet_oracle as uo
+    from oracle import vae_oracle as vo
+    from oracle.make_golden_stub import (NETS_SEEDS, NETS_STEPS, NETS_UNET_CFG, NETS_VAE_CFG, nets_fixture_inputs, round_bf16)
+    from mri_diffusion_superresolution_b200 import res_srdiff as api
+    from mri_diffusion_superresolution_b200.controlnet import ControlNetB200
+    from mri_diffusion_superresolution_b200.scheduler import ResShiftScheduler
+    from mri_diffusion_superresolution_b200.unet import UNet2DConditionB200, UNetConfig
+    from mri_diffusion_superresolution_b200.vae import AutoencoderKLB200, VAEConfig
+
+    z = np.load(os.path.join(golden_dir, "log_validation_nets.npz"))
+    ucfg = uo.UNetConfig(**NETS_UNET_CFG)
+    unet = UNet2DConditionB200(UNetConfig(**NETS_UNET_CFG))
+    unet.load_state_dict(round_bf16(uo.init_params(ucfg, seed=NETS_SEEDS["unet"])))
+    cn = ControlNetB200(UNetConfig(**NETS_UNET_CFG))
+    cn.load_state_dict(round_bf16(co.init_params(ucfg, seed=NETS_SEEDS["controlnet"])))
+    vae = AutoencoderKLB200(VAEConfig(**NETS_VAE_CFG))
+    vae.load_state_dict(round_bf16(vo.init_params(vo.VAEConfig(**NETS_VAE_CFG), seed=NETS_SEEDS["vae"])))
+    lr_img, hr_img, ehs = nets_fixture_inputs()
+
+    rec = {"lat": [], "t": []}
+    real_unet_call = unet.__call__
+
+    class RecordingUNet:                       # records what the loop hands to the UNet, then runs the CUDA UNet
+        def eval(self):
+            return self
+
+        def __call__(self, latents, t, **kw):
+            rec["lat"].append(latents.clone().cpu())
+            rec["t"].append(int(t))
+            return real_unet_call(latents, t, **kw)
+
+    queue = [torch.from_numpy(a).cuda() for a in z["noises"]]
+    post_noise = torch.from_numpy(z["post_noise"]).cuda()
+    orig_like, orig_randn = torch.randn_like, torch.randn
+    torch.randn_like = lambda x, *a, **k: queue.pop(0).to(x.dtype)
+    torch.randn = lambda *a, **k: post_noise            # the VAE posterior draw (first RNG use of the reference, :50)
+    try:
+        img = api.log_validation(RecordingUNet(), cn, vae, [{"hr": hr_img, "lr": lr_img}], ResShiftScheduler(), torch.float32,
+                                 types.SimpleNamespace(device=torch.device("cuda")), ehs.cuda(), num_inference_steps=NETS_STEPS)
+    finally:
+        torch.randn_like, torch.randn = orig_like, orig_randn
+    assert rec["t"] == z["t"].tolist()
+    assert len(queue) == int(z["noises_left"])
+    lat = torch.stack(rec["lat"])
+    ref_lat = torch.from_numpy(z["lat_in"])
+    assert _rel(lat[0], ref_lat[0]) < REL_L2_BF16                       # VAE encode + posterior sample + forward shifting
+    for i in range(NETS_STEPS):
+        rng = (ref_lat[i].max() - ref_lat[i].min()).item()
+        mse = ((lat[i] - ref_lat[i]) ** 2).mean().item()
+        assert 10 * np.log10(rng * rng / max(mse, 1e-30)) >= PSNR_MIN_DB, i
+    got = np.asarray(img).astype(np.float64)
+    assert got.shape == (512, 1536, 3)
+    np.testing.assert_array_equal(got[:, :512].astype(np.uint8), z["lr_panel"])      # pass-through panels: bit-exact
+    np.testing.assert_array_equal(got[:, 1024:].astype(np.uint8), z["hr_panel"])
+    gen, ref = got[:, 512:1024] / 255.0, z["gen_panel"].astype(np.float64) / 255.0
+    assert 10 * np.log10(1.0 / max(((gen - ref) ** 2).mean(), 1e-30)) >= PSNR_MIN_DB
