@@ -183,6 +183,7 @@ class AutoencoderKLB200:
         if strict and unexpected:
             raise KeyError(f"unexpected keys in state_dict: {unexpected[:8]}{' ...' if len(unexpected) > 8 else ''}")
         self._loaded = True
+        self._pq_scaled: Dict[float, Tensor] = {}
         return SimpleNamespace(missing_keys=[], unexpected_keys=unexpected)
 
     # ---- blocks ---------------------------------------------------------------------------------------------------
@@ -267,11 +268,17 @@ class AutoencoderKLB200:
             return (dist,)
         return SimpleNamespace(latent_dist=dist)
 
-    def _decode(self, z32: Tensor) -> Tensor:
+    def _decode(self, z32: Tensor, latent_scale: float = 1.0) -> Tensor:
         c = self.cfg
         B, _, H, W = z32.shape
         ch = c.block_out_channels
-        z = ops.channel_mix(z32, self.post_quant[0], self.post_quant[1])
+        wq = self.post_quant[0]
+        if latent_scale != 1.0:   # post_quant_conv(s * z) = (s * W) z + b: the caller's "/ scaling_factor" folded into the 4x4 mix
+            key = float(latent_scale)
+            if key not in self._pq_scaled:
+                self._pq_scaled[key] = (self.post_quant[0].double() * key).float().contiguous()
+            wq = self._pq_scaled[key]
+        z = ops.channel_mix(z32, wq, self.post_quant[1])
         cols = ops.im2col_first(z, self.kin_d)
         h = ops.gemm(cols, self.d_in[0], bias=self.d_in[1]).view(B, H, W, ch[-1])
         h = self._mid(self.d_mid, h)
@@ -286,9 +293,10 @@ class AutoencoderKLB200:
         ops.gemm(h, self.d_out[0], bias=self.d_out[1], n_store=c.out_channels, out_fp32=True, conv=True, out=o)
         return ops.nhwc_to_nchw(o.view(B, H, W, 4), torch.float32)[:, :c.out_channels]
 
-    def decode(self, z: Tensor, return_dict: bool = True):
-        """``vae.decode(z).sample`` (res_srdiff.py:110): z ``[B, 4, h, w]`` (already divided by the scaling factor) ->
-        fp32 image ``[B, 3, 8h, 8w]``."""
+    def decode(self, z: Tensor, return_dict: bool = True, latent_scale: float = 1.0):
+        """``vae.decode(z).sample`` (res_srdiff.py:110): z ``[B, 4, h, w]`` (already divided by the scaling factor, or
+        pass ``latent_scale = 1 / scaling_factor`` to have that folded into ``post_quant_conv``) -> fp32 image
+        ``[B, 3, 8h, 8w]``."""
         if not self._loaded:
             raise RuntimeError("AutoencoderKLB200: load_state_dict() has not been called")
         if not z.is_cuda:
@@ -298,7 +306,7 @@ class AutoencoderKLB200:
         self._check_pow2(z.shape[2], z.shape[3], 1)
         z32 = z if z.dtype == torch.float32 else (ops.cast(z.contiguous(), torch.float32) if z.dtype == torch.bfloat16 else z.float())
         z32 = z32.contiguous()
-        parts = [self._decode(z32[i:i + self.max_batch]) for i in range(0, z32.shape[0], self.max_batch)]
+        parts = [self._decode(z32[i:i + self.max_batch], latent_scale) for i in range(0, z32.shape[0], self.max_batch)]
         img = parts[0] if len(parts) == 1 else torch.cat(parts, 0)
         if not return_dict:
             return (img,)
