@@ -166,6 +166,23 @@ int mrisr_channel_mix(const float* in, const float* w, const float* bias, float*
  * out = scale * (mean + exp(0.5 * clamp(logvar, -30, 20)) * noise). */
 int mrisr_gaussian_sample(const float* moments, const float* noise, float* out, int B, int C, int HW, float scale, void* stream);
 
+/* ---- Evaluation metrics and slice preparation (src/eval/eval.py:9-51; notebooks/ResDif_execution.ipynb:1382-1406;
+ *      src/datasets/mri_datasets.py:162-188,284-289; slicedMRI/transform_to_2D_slices.py:116-140) ---- */
+/* One pass over N (pred, target) fp32 [H, W] pairs in [0, data_range].
+ * out[n*4 + {0..3}]  = PSNR, SSIM (11x11 Gaussian, sigma 1.5, windows fully inside the image), NMSE = |p-t|^2 / (|t|^2 + 1e-8),
+ *                      HFEN = |LoG(p) - LoG(t)| / (|LoG(t)| + 1e-8) with Gaussian sigma (replicate borders, radius
+ *                      int(4 sigma + 0.5) <= 6) and the 5-point Laplacian (mirror borders) -- MRIEvaluator semantics, per image;
+ * out[N*4 + {0..3}]  = batch PSNR, mean SSIM, |t-o| / |t|, zero-padded-Laplacian HFEN -- notebook compute_mri_metrics semantics;
+ * sums[n*8 + q]      = per-image sums {|p-t|^2, |t|^2, sum SSIM map, |LoG d|^2, |LoG t|^2, |lap d|^2, |lap t|^2, 0}.
+ * workspace: mrisr_eval_metrics_workspace_floats(N, H, W) floats.  Deterministic (no atomics). */
+int64_t mrisr_eval_metrics_workspace_floats(int N, int H, int W);
+int mrisr_eval_metrics(const float* pred, const float* target, int N, int H, int W, float data_range, float sigma,
+                       float* workspace, float* out, float* sums, void* stream);
+/* [H, W, D] volume (D innermost) -> [D, TH, TW] axial slices, centre-cropped / padded with pad_value to TH x TW
+ * (pad_or_center_crop); map_intensity != 0 applies clip((v - a_min) / (a_max - a_min), 0, 1) * 2 - 1 on the way. */
+int mrisr_slice_volume(const float* vol_hwd, int H, int W, int D, int map_intensity, float a_min, float a_max, float pad_value,
+                       float* out, int TH, int TW, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

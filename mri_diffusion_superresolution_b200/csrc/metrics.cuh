@@ -1,0 +1,265 @@
+// Evaluation metrics and slice preparation around the denoising path.
+//
+// * metrics_tile_kernel: ONE pass over a (prediction, target) image pair produces every sum the reference's metrics
+//   need -- src/eval/eval.py:15-51 (PSNR / SSIM via torchmetrics, HFEN = ||LoG(p) - LoG(t)|| / ||LoG(t)|| with
+//   skimage laplace(gaussian(sigma = 1.5)), NMSE) and notebooks/ResDif_execution.ipynb:1382-1406 (batch-level PSNR /
+//   SSIM, un-squared NMSE, HFEN with the zero-padded 3x3 Laplacian).  A CTA owns a 32 x 32 tile; both images are
+//   staged once in shared memory with a 7-pixel replicate halo (Gaussian radius 6 + Laplacian 1) and the separable
+//   filters run out of shared memory:
+//     - SSIM: 11-tap Gaussian (sigma 1.5) of x, y, x^2, y^2, xy over the windows that lie fully inside the image
+//       (torchmetrics reflect-pads by 5 and then crops the map by 5: the same set of windows);
+//     - LoG:  13-tap Gaussian with replicate borders (scipy mode="nearest", truncate 4) of d = p - t and of t, then
+//       the 5-point Laplacian whose out-of-image neighbours mirror the border pixel (scipy mode="reflect").
+//   Per-tile partial sums are written (no atomics) and reduced in a fixed order by metrics_finalize_kernel, so results
+//   are bit-reproducible.
+// * slice_volume_kernel: [H, W, D] raw-intensity volume -> [D, TH, TW] axial slices with the reference's intensity
+//   mapping clip((v - a_min) / (a_max - a_min), 0, 1) * 2 - 1 (src/datasets/mri_datasets.py:284-289) and
+//   pad_or_center_crop (:162-188) fused into a shared-memory tile transpose (coalesced on both sides).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "ptx.cuh"
+
+namespace mrisr {
+
+constexpr int kMetTile = 32;
+constexpr int kMetHalo = 7;
+constexpr int kMetExt = kMetTile + 2 * kMetHalo;  // 46
+constexpr int kMetSums = 8;
+constexpr int kMetThreads = 256;
+
+struct MetricsParams {
+  const float* pred;
+  const float* target;
+  int N, H, W;
+  int tiles_x, tiles_y;
+  float* partial;   // [N, tiles_y, tiles_x, 8]
+  float gw[11];     // SSIM window (sums to 1)
+  float hw[13];     // LoG Gaussian taps, zero-padded symmetrically when the radius is < 6
+  float c1, c2;     // (k1 R)^2, (k2 R)^2
+};
+
+__global__ void __launch_bounds__(kMetThreads) metrics_tile_kernel(const MetricsParams P) {
+  grid_dep_launch();
+  grid_dep_wait();
+  __shared__ float sp[kMetExt][kMetExt + 1];
+  __shared__ float st[kMetExt][kMetExt + 1];
+  __shared__ float buf[5 * 42 * 32];   // phase A: 5 x [42][32] row-filtered SSIM moments; phase B: LoG intermediates
+  __shared__ float red[kMetSums][kMetThreads / 32];
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * kMetTile, y0 = blockIdx.y * kMetTile, n = blockIdx.z;
+  const int H = P.H, W = P.W;
+  const float* pi = P.pred + static_cast<long long>(n) * H * W;
+  const float* ti = P.target + static_cast<long long>(n) * H * W;
+  for (int i = tid; i < kMetExt * kMetExt; i += kMetThreads) {
+    const int r = i / kMetExt, c = i - r * kMetExt;
+    const int gy = min(max(y0 - kMetHalo + r, 0), H - 1), gx = min(max(x0 - kMetHalo + c, 0), W - 1);
+    sp[r][c] = __ldg(pi + gy * W + gx);
+    st[r][c] = __ldg(ti + gy * W + gx);
+  }
+  __syncthreads();
+  float s[kMetSums];
+#pragma unroll
+  for (int q = 0; q < kMetSums; ++q) s[q] = 0.f;
+
+  // direct sums and the zero-padded Laplacian (notebook HFEN)
+  for (int i = tid; i < kMetTile * kMetTile; i += kMetThreads) {
+    const int ly = i >> 5, lx = i & 31, gy = y0 + ly, gx = x0 + lx;
+    if (gy < H && gx < W) {
+      const int r = ly + kMetHalo, c = lx + kMetHalo;
+      const float t = st[r][c], d = sp[r][c] - t;
+      s[0] = fmaf(d, d, s[0]);
+      s[1] = fmaf(t, t, s[1]);
+      float ld = -4.f * d, lt = -4.f * t;
+      if (gy > 0) { ld += sp[r - 1][c] - st[r - 1][c]; lt += st[r - 1][c]; }
+      if (gy < H - 1) { ld += sp[r + 1][c] - st[r + 1][c]; lt += st[r + 1][c]; }
+      if (gx > 0) { ld += sp[r][c - 1] - st[r][c - 1]; lt += st[r][c - 1]; }
+      if (gx < W - 1) { ld += sp[r][c + 1] - st[r][c + 1]; lt += st[r][c + 1]; }
+      s[5] = fmaf(ld, ld, s[5]);
+      s[6] = fmaf(lt, lt, s[6]);
+    }
+  }
+
+  // ---- phase A: SSIM.  Row pass over ext rows 2..43 (tile rows -5..36), tile columns 0..31.
+  for (int i = tid; i < 42 * 32; i += kMetThreads) {
+    const int rr = i >> 5, lx = i & 31, r = rr + 2;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 11; ++k) {
+      const float p = sp[r][lx + 2 + k], t = st[r][lx + 2 + k], w = P.gw[k];
+      const float wp = w * p, wt = w * t;
+      a0 += wp;
+      a1 += wt;
+      a2 = fmaf(wp, p, a2);
+      a3 = fmaf(wt, t, a3);
+      a4 = fmaf(wp, t, a4);
+    }
+    buf[0 * 1344 + i] = a0;
+    buf[1 * 1344 + i] = a1;
+    buf[2 * 1344 + i] = a2;
+    buf[3 * 1344 + i] = a3;
+    buf[4 * 1344 + i] = a4;
+  }
+  __syncthreads();
+  for (int i = tid; i < kMetTile * kMetTile; i += kMetThreads) {
+    const int ly = i >> 5, lx = i & 31, gy = y0 + ly, gx = x0 + lx;
+    if (gy >= 5 && gy <= H - 6 && gx >= 5 && gx <= W - 6) {
+      float m[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < 11; ++k) {
+        const float w = P.gw[k];
+        const int o = (ly + k) * 32 + lx;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) m[q] = fmaf(w, buf[q * 1344 + o], m[q]);
+      }
+      const float mxy = m[0] * m[1], mxx = m[0] * m[0], myy = m[1] * m[1];
+      const float vx = m[2] - mxx, vy = m[3] - myy, vxy = m[4] - mxy;
+      const float num = (2.f * mxy + P.c1) * (2.f * vxy + P.c2);
+      const float den = (mxx + myy + P.c1) * (vx + vy + P.c2);
+      s[2] += num / den;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase B: LoG of d = p - t and of t.  Row pass for all 46 ext rows at the 34 columns tile-1 .. tile+32 (centre
+  // clamped into the image: the Laplacian's out-of-image neighbour mirrors the border pixel).
+  float* hd = buf;                        // [46][34]
+  float* ht = buf + kMetExt * 34;         // [46][34]
+  float* gd = buf + 2 * kMetExt * 34;     // [34][34]
+  float* gt = gd + 34 * 34;               // [34][34]
+  for (int i = tid; i < kMetExt * 34; i += kMetThreads) {
+    const int r = i / 34, cc = i - r * 34;
+    const int ec = min(max(x0 - 1 + cc, 0), W - 1) - (x0 - kMetHalo);
+    float ad = 0.f, at = 0.f;
+#pragma unroll
+    for (int k = 0; k < 13; ++k) {
+      const float t = st[r][ec + k - 6], w = P.hw[k];
+      ad = fmaf(w, sp[r][ec + k - 6] - t, ad);
+      at = fmaf(w, t, at);
+    }
+    hd[i] = ad;
+    ht[i] = at;
+  }
+  __syncthreads();
+  for (int i = tid; i < 34 * 34; i += kMetThreads) {
+    const int rr = i / 34, cc = i - rr * 34;
+    const int er = min(max(y0 - 1 + rr, 0), H - 1) - (y0 - kMetHalo);
+    float ad = 0.f, at = 0.f;
+#pragma unroll
+    for (int k = 0; k < 13; ++k) {
+      const float w = P.hw[k];
+      ad = fmaf(w, hd[(er + k - 6) * 34 + cc], ad);
+      at = fmaf(w, ht[(er + k - 6) * 34 + cc], at);
+    }
+    gd[i] = ad;
+    gt[i] = at;
+  }
+  __syncthreads();
+  for (int i = tid; i < kMetTile * kMetTile; i += kMetThreads) {
+    const int ly = i >> 5, lx = i & 31, gy = y0 + ly, gx = x0 + lx;
+    if (gy < H && gx < W) {
+      const int o = (ly + 1) * 34 + lx + 1;
+      const float ld = 4.f * gd[o] - gd[o - 34] - gd[o + 34] - gd[o - 1] - gd[o + 1];
+      const float lt = 4.f * gt[o] - gt[o - 34] - gt[o + 34] - gt[o - 1] - gt[o + 1];
+      s[3] = fmaf(ld, ld, s[3]);
+      s[4] = fmaf(lt, lt, s[4]);
+    }
+  }
+
+  // ---- CTA reduction (fixed order) -> one partial row per tile
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int q = 0; q < kMetSums; ++q) {
+    float v = s[q];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[q][warp] = v;
+  }
+  __syncthreads();
+  if (tid < kMetSums) {
+    float v = 0.f;
+    for (int w = 0; w < kMetThreads / 32; ++w) v += red[tid][w];
+    const long long tile = (static_cast<long long>(n) * P.tiles_y + blockIdx.y) * P.tiles_x + blockIdx.x;
+    P.partial[tile * kMetSums + tid] = v;
+  }
+}
+
+// One CTA: per image, the tile partials are summed in double precision in a fixed order; writes
+//   out[n*4 + {0,1,2,3}] = PSNR, SSIM, NMSE, HFEN of image n (MRIEvaluator semantics, eval.py:18-51,84-90)
+//   out[N*4 + {0,1,2,3}] = batch-level PSNR, mean SSIM, ||t-o||/||t||, zero-padded-Laplacian HFEN (notebook semantics)
+//   sums[n*8 + q]        = the raw per-image sums (fp64 -> fp32), for callers that aggregate differently.
+__global__ void metrics_finalize_kernel(const float* __restrict__ partial, int N, int tiles, int H, int W, float data_range,
+                                        float* __restrict__ out, float* __restrict__ sums) {
+  grid_dep_launch();
+  grid_dep_wait();
+  __shared__ double red[kMetSums][kMetThreads];
+  __shared__ double tot[kMetSums];
+  const int tid = threadIdx.x;
+  if (tid < kMetSums) tot[tid] = 0.0;
+  const double npix = static_cast<double>(H) * W, nwin = static_cast<double>(H - 10) * (W - 10);
+  for (int n = 0; n < N; ++n) {
+    double a[kMetSums];
+#pragma unroll
+    for (int q = 0; q < kMetSums; ++q) a[q] = 0.0;
+    for (int t = tid; t < tiles; t += kMetThreads) {
+      const float* row = partial + (static_cast<long long>(n) * tiles + t) * kMetSums;
+#pragma unroll
+      for (int q = 0; q < kMetSums; ++q) a[q] += static_cast<double>(row[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < kMetSums; ++q) red[q][tid] = a[q];
+    __syncthreads();
+    for (int o = kMetThreads / 2; o > 0; o >>= 1) {
+      if (tid < o) {
+#pragma unroll
+        for (int q = 0; q < kMetSums; ++q) red[q][tid] += red[q][tid + o];
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      const double s0 = red[0][0], s1 = red[1][0], s2 = red[2][0], s3 = red[3][0], s4 = red[4][0];
+      out[n * 4 + 0] = static_cast<float>(10.0 * log10(static_cast<double>(data_range) * data_range / (s0 / npix)));
+      out[n * 4 + 1] = static_cast<float>(s2 / nwin);
+      out[n * 4 + 2] = static_cast<float>(s0 / (s1 + 1e-8));
+      out[n * 4 + 3] = static_cast<float>(sqrt(s3) / (sqrt(s4) + 1e-8));
+      for (int q = 0; q < kMetSums; ++q) {
+        sums[n * kMetSums + q] = static_cast<float>(red[q][0]);
+        tot[q] += red[q][0];
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    out[N * 4 + 0] = static_cast<float>(10.0 * log10(static_cast<double>(data_range) * data_range / (tot[0] / (npix * N))));
+    out[N * 4 + 1] = static_cast<float>(tot[2] / (nwin * N));
+    out[N * 4 + 2] = static_cast<float>(sqrt(tot[0]) / sqrt(tot[1]));
+    out[N * 4 + 3] = static_cast<float>(sqrt(tot[5]) / sqrt(tot[6]));
+  }
+}
+
+// [H, W, D] (D innermost) -> [D, TH, TW]: out[d, oy, ox] = map(vol[oy + off_y, ox + off_x, d]) or pad_value outside.
+__global__ void slice_volume_kernel(const float* __restrict__ vol, int H, int W, int D, float a_min, float range,
+                                    int map_intensity, float pad_value, float* __restrict__ out, int TH, int TW, int off_y,
+                                    int off_x) {
+  grid_dep_launch();
+  grid_dep_wait();
+  __shared__ float tile[32][33];
+  const int oy = blockIdx.z, sy = oy + off_y;
+  const int ox0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  const bool row_ok = sy >= 0 && sy < H;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {       // read: d fastest
+    const int sx = ox0 + j + off_x, d = d0 + threadIdx.x;
+    float v = pad_value;
+    if (row_ok && sx >= 0 && sx < W && ox0 + j < TW && d < D) {
+      v = __ldg(vol + (static_cast<long long>(sy) * W + sx) * D + d);
+      if (map_intensity) v = fminf(fmaxf(__fdiv_rn(v - a_min, range), 0.f), 1.f) * 2.f - 1.f;   // same op order as numpy: bit-exact
+    }
+    tile[j][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {       // write: ox fastest
+    const int d = d0 + j, ox = ox0 + threadIdx.x;
+    if (d < D && ox < TW) out[(static_cast<long long>(d) * TH + oy) * TW + ox] = tile[threadIdx.x][j];
+  }
+}
+
+}  // namespace mrisr

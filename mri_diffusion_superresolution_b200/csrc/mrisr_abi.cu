@@ -14,6 +14,7 @@
 #include "attention.cuh"
 #include "attention_tcgen05.cuh"
 #include "gemm_tcgen05.cuh"
+#include "metrics.cuh"
 #include "pointwise.cuh"
 
 namespace {
@@ -855,6 +856,53 @@ int mrisr_channel_mix(const float* in, const float* w, const float* bias, float*
 int mrisr_gaussian_sample(const float* moments, const float* noise, float* out, int B, int C, int HW, float scale, void* stream) {
   MRISR_REQUIRE(moments && out && B > 0 && C > 0 && HW > 0, "gaussian_sample: bad argument");
   launch_k(mrisr::gaussian_sample_kernel, dim3(grid_for(static_cast<long long>(B) * C * HW, 256, 8)), dim3(256), 0, as_stream(stream), moments, noise, out, B, C, HW, scale);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int64_t mrisr_eval_metrics_workspace_floats(int N, int H, int W) {
+  const int64_t tiles = static_cast<int64_t>((H + mrisr::kMetTile - 1) / mrisr::kMetTile) * ((W + mrisr::kMetTile - 1) / mrisr::kMetTile);
+  return static_cast<int64_t>(N) * tiles * mrisr::kMetSums;
+}
+
+int mrisr_eval_metrics(const float* pred, const float* target, int N, int H, int W, float data_range, float sigma,
+                       float* workspace, float* out, float* sums, void* stream) {
+  MRISR_REQUIRE(pred && target && workspace && out && sums, "eval_metrics: null pointer");
+  MRISR_REQUIRE(N > 0 && N <= 65535 && H >= 11 && W >= 11, "eval_metrics: need 1 <= N <= 65535 and H, W >= 11 (the SSIM window)");
+  MRISR_REQUIRE(static_cast<long long>(H) * W < (1ll << 31), "eval_metrics: image too large");
+  MRISR_REQUIRE(data_range > 0.f && sigma > 0.f, "eval_metrics: data_range and sigma must be positive");
+  const int radius = static_cast<int>(4.0 * static_cast<double>(sigma) + 0.5);   // scipy gaussian_filter, truncate = 4
+  if (radius > 6) return fail(MRISR_E_UNSUPPORTED, "eval_metrics: sigma %.3f needs a Gaussian radius of %d > 6", sigma, radius);
+  mrisr::MetricsParams P;
+  P.pred = pred; P.target = target; P.N = N; P.H = H; P.W = W;
+  P.tiles_x = (W + mrisr::kMetTile - 1) / mrisr::kMetTile;
+  P.tiles_y = (H + mrisr::kMetTile - 1) / mrisr::kMetTile;
+  P.partial = workspace;
+  {
+    double g[11], sum = 0.0;   // torchmetrics _gaussian(11, 1.5)
+    for (int k = 0; k < 11; ++k) { const double d = (k - 5) / 1.5; g[k] = std::exp(-d * d / 2.0); sum += g[k]; }
+    for (int k = 0; k < 11; ++k) P.gw[k] = static_cast<float>(g[k] / sum);
+    double h[13], hs = 0.0;    // scipy _gaussian_kernel1d(sigma, 0, radius)
+    for (int k = 0; k < 13; ++k) { const int x = k - 6; h[k] = std::abs(x) <= radius ? std::exp(-0.5 * x * x / (static_cast<double>(sigma) * sigma)) : 0.0; hs += h[k]; }
+    for (int k = 0; k < 13; ++k) P.hw[k] = static_cast<float>(h[k] / hs);
+  }
+  P.c1 = (0.01f * data_range) * (0.01f * data_range);
+  P.c2 = (0.03f * data_range) * (0.03f * data_range);
+  cudaStream_t st = as_stream(stream);
+  launch_k(mrisr::metrics_tile_kernel, dim3(P.tiles_x, P.tiles_y, N), dim3(mrisr::kMetThreads), 0, st, P);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  launch_k(mrisr::metrics_finalize_kernel, dim3(1), dim3(mrisr::kMetThreads), 0, st, static_cast<const float*>(workspace), N, P.tiles_x * P.tiles_y, H, W, data_range, out, sums);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mrisr_slice_volume(const float* vol, int H, int W, int D, int map_intensity, float a_min, float a_max, float pad_value, float* out, int TH, int TW, void* stream) {
+  MRISR_REQUIRE(vol && out && H > 0 && W > 0 && D > 0 && TH > 0 && TW > 0 && TH <= 65535, "slice_volume: bad argument");
+  MRISR_REQUIRE(!map_intensity || a_max > a_min, "slice_volume: a_max must exceed a_min");
+  // pad_or_center_crop (mri_datasets.py:162-188): crop start (H - TH) / 2 when larger, pad_top = (TH - H) / 2 when smaller
+  const int off_y = H > TH ? (H - TH) / 2 : -((TH - H) / 2);
+  const int off_x = W > TW ? (W - TW) / 2 : -((TW - W) / 2);
+  launch_k(mrisr::slice_volume_kernel, dim3((TW + 31) / 32, (D + 31) / 32, TH), dim3(32, 8), 0, as_stream(stream), vol, H, W, D, a_min, a_max - a_min, map_intensity, pad_value, out, TH, TW, off_y, off_x);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

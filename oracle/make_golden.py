@@ -18,6 +18,8 @@ log_validation.npz ``log_validation`` (src/adapters/res_srdiff.py:35-105) driven
 log_validation_nets.npz the same ``log_validation`` driven around the ORACLE UNet+LoRA / ControlNet / VAE (reduced
                   width, 512x512 slices, 4 steps): the end-to-end pin of the full drop-in (CUDA UNet + ControlNet +
                   VAE under this repo's ``log_validation``).
+eval_metrics.npz  ``MRIEvaluator.compute_nmse`` (src/eval/eval.py:39-51) and ``pad_or_center_crop``
+                  (src/datasets/mri_datasets.py:162-188) executed from the reference sources on seeded inputs.
 adapter_xl_*.npz  ``Adapter_XL`` (src/adapters/modules.py:114-157) outputs for small channel configs,
                   with the module's own initialised weights stored alongside.
 """
@@ -203,6 +205,46 @@ def gen_log_validation_nets():
                         lr_panel=img[:, :512], gen_panel=img[:, 512:1024], hr_panel=img[:, 1024:])
 
 
+def _ref_function(path, name, cls=None, extra_globals=None):
+    """Compile ONE function (or method) out of a reference source file whose module cannot be imported here because of
+    missing third-party imports at its top (torchmetrics / skimage / SimpleITK / monai), and return it.  The source is
+    read and executed from /root/reference in memory; nothing is copied into this repository."""
+    import ast
+
+    src = open(os.path.join(REF, path)).read()
+    tree = ast.parse(src)
+    body = tree.body
+    if cls is not None:
+        body = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == cls).body
+    fn = next(n for n in body if isinstance(n, ast.FunctionDef) and n.name == name)
+    mod = ast.Module(body=[fn], type_ignores=[])
+    g = {"np": np, "torch": torch}
+    g.update(extra_globals or {})
+    exec(compile(mod, os.path.join(REF, path), "exec"), g)
+    return g[name]
+
+
+def gen_eval():
+    """Reference ``MRIEvaluator.compute_nmse`` (src/eval/eval.py:39-51) and ``pad_or_center_crop``
+    (src/datasets/mri_datasets.py:162-188) run on seeded inputs; the [-1, 1] mapping lines (:284-289) are exercised
+    through the numpy expressions they consist of."""
+    nmse_fn = _ref_function("src/eval/eval.py", "compute_nmse", cls="MRIEvaluator")
+    crop_fn = _ref_function("src/datasets/mri_datasets.py", "pad_or_center_crop")
+    g = torch.Generator().manual_seed(55)
+    tgt = torch.rand(3, 48, 40, generator=g)
+    pred = (tgt + 0.05 * torch.randn(3, 48, 40, generator=g)).clamp(0, 1)
+    nm = np.asarray([nmse_fn(None, pred[i], tgt[i]) for i in range(3)], dtype=np.float64)
+    out = {"pred": pred.numpy(), "target": tgt.numpy(), "nmse": nm}
+    import hashlib
+    for tag, shape in (("small", (300, 470)), ("big", (600, 530)), ("mixed", (700, 128)), ("exact", (512, 512))):
+        q = torch.randint(-64, 65, shape, generator=g, dtype=torch.int8)         # slice values k / 64 in [-1, 1]
+        res = crop_fn(q.float() / 64.0).numpy().astype(np.float32)
+        out[f"crop_in_{tag}"] = q.numpy()
+        out[f"crop_out_shape_{tag}"] = np.asarray(res.shape)
+        out[f"crop_out_sha256_{tag}"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(res).tobytes()).digest(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, "eval_metrics.npz"), **out)
+
+
 def gen_prepare_condition():
     from src.adapters.res_srdiff import prepare_condition_image
 
@@ -269,6 +311,7 @@ if __name__ == "__main__":
     gen_res_shift()
     gen_log_validation()
     gen_log_validation_nets()
+    gen_eval()
     gen_prepare_condition()
     gen_adapter()
     for f in sorted(os.listdir(OUT)):
