@@ -183,52 +183,65 @@ __global__ void __launch_bounds__(kMetThreads) metrics_tile_kernel(const Metrics
   }
 }
 
-// One CTA: per image, the tile partials are summed in double precision in a fixed order; writes
+// Stage 2, one CTA per image: the tile partials are summed in double precision in a fixed order; writes
 //   out[n*4 + {0,1,2,3}] = PSNR, SSIM, NMSE, HFEN of image n (MRIEvaluator semantics, eval.py:18-51,84-90)
-//   out[N*4 + {0,1,2,3}] = batch-level PSNR, mean SSIM, ||t-o||/||t||, zero-padded-Laplacian HFEN (notebook semantics)
-//   sums[n*8 + q]        = the raw per-image sums (fp64 -> fp32), for callers that aggregate differently.
-__global__ void metrics_finalize_kernel(const float* __restrict__ partial, int N, int tiles, int H, int W, float data_range,
-                                        float* __restrict__ out, float* __restrict__ sums) {
+//   sums[n*8 + q]        = the raw per-image sums, for callers that aggregate differently
+//   dsums[n*8 + q]       = the same in fp64 for stage 3.
+__global__ void __launch_bounds__(kMetThreads) metrics_finalize_kernel(const float* __restrict__ partial, int tiles, int H, int W,
+                                                                         float data_range, float* __restrict__ out,
+                                                                         float* __restrict__ sums, double* __restrict__ dsums) {
   grid_dep_launch();
   grid_dep_wait();
   __shared__ double red[kMetSums][kMetThreads];
-  __shared__ double tot[kMetSums];
-  const int tid = threadIdx.x;
-  if (tid < kMetSums) tot[tid] = 0.0;
-  const double npix = static_cast<double>(H) * W, nwin = static_cast<double>(H - 10) * (W - 10);
-  for (int n = 0; n < N; ++n) {
-    double a[kMetSums];
+  const int tid = threadIdx.x, n = blockIdx.x;
+  double a[kMetSums];
 #pragma unroll
-    for (int q = 0; q < kMetSums; ++q) a[q] = 0.0;
-    for (int t = tid; t < tiles; t += kMetThreads) {
-      const float* row = partial + (static_cast<long long>(n) * tiles + t) * kMetSums;
+  for (int q = 0; q < kMetSums; ++q) a[q] = 0.0;
+  for (int t = tid; t < tiles; t += kMetThreads) {
+    const float4* row = reinterpret_cast<const float4*>(partial + (static_cast<long long>(n) * tiles + t) * kMetSums);
+    const float4 lo = __ldg(row), hi = __ldg(row + 1);
+    a[0] += lo.x; a[1] += lo.y; a[2] += lo.z; a[3] += lo.w;
+    a[4] += hi.x; a[5] += hi.y; a[6] += hi.z; a[7] += hi.w;
+  }
 #pragma unroll
-      for (int q = 0; q < kMetSums; ++q) a[q] += static_cast<double>(row[q]);
-    }
+  for (int q = 0; q < kMetSums; ++q) red[q][tid] = a[q];
+  __syncthreads();
+  for (int o = kMetThreads / 2; o > 0; o >>= 1) {
+    if (tid < o) {
 #pragma unroll
-    for (int q = 0; q < kMetSums; ++q) red[q][tid] = a[q];
-    __syncthreads();
-    for (int o = kMetThreads / 2; o > 0; o >>= 1) {
-      if (tid < o) {
-#pragma unroll
-        for (int q = 0; q < kMetSums; ++q) red[q][tid] += red[q][tid + o];
-      }
-      __syncthreads();
-    }
-    if (tid == 0) {
-      const double s0 = red[0][0], s1 = red[1][0], s2 = red[2][0], s3 = red[3][0], s4 = red[4][0];
-      out[n * 4 + 0] = static_cast<float>(10.0 * log10(static_cast<double>(data_range) * data_range / (s0 / npix)));
-      out[n * 4 + 1] = static_cast<float>(s2 / nwin);
-      out[n * 4 + 2] = static_cast<float>(s0 / (s1 + 1e-8));
-      out[n * 4 + 3] = static_cast<float>(sqrt(s3) / (sqrt(s4) + 1e-8));
-      for (int q = 0; q < kMetSums; ++q) {
-        sums[n * kMetSums + q] = static_cast<float>(red[q][0]);
-        tot[q] += red[q][0];
-      }
+      for (int q = 0; q < kMetSums; ++q) red[q][tid] += red[q][tid + o];
     }
     __syncthreads();
   }
   if (tid == 0) {
+    const double npix = static_cast<double>(H) * W, nwin = static_cast<double>(H - 10) * (W - 10);
+    const double s0 = red[0][0], s1 = red[1][0], s2 = red[2][0], s3 = red[3][0], s4 = red[4][0];
+    out[n * 4 + 0] = static_cast<float>(10.0 * log10(static_cast<double>(data_range) * data_range / (s0 / npix)));
+    out[n * 4 + 1] = static_cast<float>(s2 / nwin);
+    out[n * 4 + 2] = static_cast<float>(s0 / (s1 + 1e-8));
+    out[n * 4 + 3] = static_cast<float>(sqrt(s3) / (sqrt(s4) + 1e-8));
+  }
+  if (tid < kMetSums) {
+    sums[n * kMetSums + tid] = static_cast<float>(red[tid][0]);
+    dsums[n * kMetSums + tid] = red[tid][0];
+  }
+}
+
+// Stage 3, one warp: batch-level metrics with the notebook's compute_mri_metrics semantics (ResDif_execution.ipynb:1382-1406)
+//   out[N*4 + {0,1,2,3}] = PSNR over all pixels, mean SSIM, ||t-o|| / ||t||, zero-padded-Laplacian HFEN.
+__global__ void metrics_batch_kernel(const double* __restrict__ dsums, int N, int H, int W, float data_range, float* __restrict__ out) {
+  grid_dep_launch();
+  grid_dep_wait();
+  const int q = threadIdx.x;
+  __shared__ double tot[kMetSums];
+  if (q < kMetSums) {
+    double v = 0.0;
+    for (int n = 0; n < N; ++n) v += dsums[n * kMetSums + q];   // fixed order
+    tot[q] = v;
+  }
+  __syncthreads();
+  if (q == 0) {
+    const double npix = static_cast<double>(H) * W, nwin = static_cast<double>(H - 10) * (W - 10);
     out[N * 4 + 0] = static_cast<float>(10.0 * log10(static_cast<double>(data_range) * data_range / (tot[0] / (npix * N))));
     out[N * 4 + 1] = static_cast<float>(tot[2] / (nwin * N));
     out[N * 4 + 2] = static_cast<float>(sqrt(tot[0]) / sqrt(tot[1]));
@@ -237,28 +250,60 @@ __global__ void metrics_finalize_kernel(const float* __restrict__ partial, int N
 }
 
 // [H, W, D] (D innermost) -> [D, TH, TW]: out[d, oy, ox] = map(vol[oy + off_y, ox + off_x, d]) or pad_value outside.
-__global__ void slice_volume_kernel(const float* __restrict__ vol, int H, int W, int D, float a_min, float range,
-                                    int map_intensity, float pad_value, float* __restrict__ out, int TH, int TW, int off_y,
-                                    int off_x) {
+// A CTA moves a 32 (x) x 32 (d) tile of kSliceRows consecutive output rows: all of its 16-byte loads (d fastest) are issued
+// before the first shared-memory store, then the tiles are written transposed with ox fastest (128-byte rows on both sides).
+constexpr int kSliceRows = 4;
+__global__ void __launch_bounds__(256) slice_volume_kernel(const float* __restrict__ vol, int H, int W, int D, float a_min, float range,
+                                                           int map_intensity, float pad_value, float* __restrict__ out, int TH, int TW,
+                                                           int off_y, int off_x) {
   grid_dep_launch();
   grid_dep_wait();
-  __shared__ float tile[32][33];
-  const int oy = blockIdx.z, sy = oy + off_y;
-  const int ox0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
-  const bool row_ok = sy >= 0 && sy < H;
-  for (int j = threadIdx.y; j < 32; j += blockDim.y) {       // read: d fastest
-    const int sx = ox0 + j + off_x, d = d0 + threadIdx.x;
-    float v = pad_value;
-    if (row_ok && sx >= 0 && sx < W && ox0 + j < TW && d < D) {
-      v = __ldg(vol + (static_cast<long long>(sy) * W + sx) * D + d);
-      if (map_intensity) v = fminf(fmaxf(__fdiv_rn(v - a_min, range), 0.f), 1.f) * 2.f - 1.f;   // same op order as numpy: bit-exact
+  __shared__ float tile[kSliceRows][32][33];
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;         // load role: 8 x float4 along d, 32 pixels along x
+  const int ox0 = blockIdx.x * 32, d0 = blockIdx.y * 32, oy0 = blockIdx.z * kSliceRows;
+  const int sx = ox0 + ty + off_x, d = d0 + 4 * tx;
+  const bool vec = (D & 3) == 0;
+  float4 v[kSliceRows];
+#pragma unroll
+  for (int r = 0; r < kSliceRows; ++r) {
+    const int sy = oy0 + r + off_y;
+    v[r] = make_float4(pad_value, pad_value, pad_value, pad_value);
+    if (sy >= 0 && sy < H && oy0 + r < TH && sx >= 0 && sx < W && ox0 + ty < TW) {
+      const float* src = vol + (static_cast<long long>(sy) * W + sx) * D + d;
+      if (vec && d + 3 < D) {
+        v[r] = __ldg(reinterpret_cast<const float4*>(src));
+      } else {
+        if (d < D) v[r].x = __ldg(src);
+        if (d + 1 < D) v[r].y = __ldg(src + 1);
+        if (d + 2 < D) v[r].z = __ldg(src + 2);
+        if (d + 3 < D) v[r].w = __ldg(src + 3);
+      }
+      if (map_intensity) {   // same op order as numpy: bit-exact
+        v[r].x = fminf(fmaxf(__fdiv_rn(v[r].x - a_min, range), 0.f), 1.f) * 2.f - 1.f;
+        v[r].y = fminf(fmaxf(__fdiv_rn(v[r].y - a_min, range), 0.f), 1.f) * 2.f - 1.f;
+        v[r].z = fminf(fmaxf(__fdiv_rn(v[r].z - a_min, range), 0.f), 1.f) * 2.f - 1.f;
+        v[r].w = fminf(fmaxf(__fdiv_rn(v[r].w - a_min, range), 0.f), 1.f) * 2.f - 1.f;
+      }
     }
-    tile[j][threadIdx.x] = v;
+  }
+#pragma unroll
+  for (int r = 0; r < kSliceRows; ++r) {
+    tile[r][4 * tx + 0][ty] = v[r].x;
+    tile[r][4 * tx + 1][ty] = v[r].y;
+    tile[r][4 * tx + 2][ty] = v[r].z;
+    tile[r][4 * tx + 3][ty] = v[r].w;
   }
   __syncthreads();
-  for (int j = threadIdx.y; j < 32; j += blockDim.y) {       // write: ox fastest
-    const int d = d0 + j, ox = ox0 + threadIdx.x;
-    if (d < D && ox < TW) out[(static_cast<long long>(d) * TH + oy) * TW + ox] = tile[threadIdx.x][j];
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;      // store role: 32 pixels along ox, 8 slices per pass
+#pragma unroll
+  for (int r = 0; r < kSliceRows; ++r) {
+    const int oy = oy0 + r;
+    if (oy >= TH) break;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int dd = wrp + 8 * j;
+      if (d0 + dd < D && ox0 + lane < TW) out[(static_cast<long long>(d0 + dd) * TH + oy) * TW + ox0 + lane] = tile[r][dd][lane];
+    }
   }
 }
 

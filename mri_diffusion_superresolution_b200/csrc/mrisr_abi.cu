@@ -862,7 +862,7 @@ int mrisr_gaussian_sample(const float* moments, const float* noise, float* out, 
 
 int64_t mrisr_eval_metrics_workspace_floats(int N, int H, int W) {
   const int64_t tiles = static_cast<int64_t>((H + mrisr::kMetTile - 1) / mrisr::kMetTile) * ((W + mrisr::kMetTile - 1) / mrisr::kMetTile);
-  return static_cast<int64_t>(N) * tiles * mrisr::kMetSums;
+  return static_cast<int64_t>(N) * tiles * mrisr::kMetSums + static_cast<int64_t>(N) * mrisr::kMetSums * 2 + 2;   // partials + fp64 sums
 }
 
 int mrisr_eval_metrics(const float* pred, const float* target, int N, int H, int W, float data_range, float sigma,
@@ -891,18 +891,25 @@ int mrisr_eval_metrics(const float* pred, const float* target, int N, int H, int
   cudaStream_t st = as_stream(stream);
   launch_k(mrisr::metrics_tile_kernel, dim3(P.tiles_x, P.tiles_y, N), dim3(mrisr::kMetThreads), 0, st, P);
   MRISR_CHECK_CUDA(cudaGetLastError());
-  launch_k(mrisr::metrics_finalize_kernel, dim3(1), dim3(mrisr::kMetThreads), 0, st, static_cast<const float*>(workspace), N, P.tiles_x * P.tiles_y, H, W, data_range, out, sums);
+  const int tiles = P.tiles_x * P.tiles_y;
+  const size_t part = static_cast<size_t>(N) * tiles * mrisr::kMetSums;
+  double* dsums = reinterpret_cast<double*>(workspace + ((part + 1) & ~static_cast<size_t>(1)));   // 8-byte aligned
+  MRISR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "eval_metrics: workspace must be 16-byte aligned");
+  launch_k(mrisr::metrics_finalize_kernel, dim3(N), dim3(mrisr::kMetThreads), 0, st, static_cast<const float*>(workspace), tiles, H, W, data_range, out, sums, dsums);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  launch_k(mrisr::metrics_batch_kernel, dim3(1), dim3(32), 0, st, static_cast<const double*>(dsums), N, H, W, data_range, out);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int mrisr_slice_volume(const float* vol, int H, int W, int D, int map_intensity, float a_min, float a_max, float pad_value, float* out, int TH, int TW, void* stream) {
-  MRISR_REQUIRE(vol && out && H > 0 && W > 0 && D > 0 && TH > 0 && TW > 0 && TH <= 65535, "slice_volume: bad argument");
+  MRISR_REQUIRE(vol && out && H > 0 && W > 0 && D > 0 && TH > 0 && TW > 0 && TH <= 4 * 65535 && D <= 32 * 65535, "slice_volume: bad argument");
+  MRISR_REQUIRE((reinterpret_cast<uintptr_t>(vol) & 15) == 0, "slice_volume: volume must be 16-byte aligned");
   MRISR_REQUIRE(!map_intensity || a_max > a_min, "slice_volume: a_max must exceed a_min");
   // pad_or_center_crop (mri_datasets.py:162-188): crop start (H - TH) / 2 when larger, pad_top = (TH - H) / 2 when smaller
   const int off_y = H > TH ? (H - TH) / 2 : -((TH - H) / 2);
   const int off_x = W > TW ? (W - TW) / 2 : -((TW - W) / 2);
-  launch_k(mrisr::slice_volume_kernel, dim3((TW + 31) / 32, (D + 31) / 32, TH), dim3(32, 8), 0, as_stream(stream), vol, H, W, D, a_min, a_max - a_min, map_intensity, pad_value, out, TH, TW, off_y, off_x);
+  launch_k(mrisr::slice_volume_kernel, dim3((TW + 31) / 32, (D + 31) / 32, (TH + mrisr::kSliceRows - 1) / mrisr::kSliceRows), dim3(256), 0, as_stream(stream), vol, H, W, D, a_min, a_max - a_min, map_intensity, pad_value, out, TH, TW, off_y, off_x);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -51,7 +51,7 @@ def image_metrics(pred: Tensor, target: Tensor, data_range: float = 1.0, sigma: 
     sums = torch.empty((N, 8), device=p.device, dtype=torch.float32)
     _lib.check(lib.mrisr_eval_metrics(p.data_ptr(), t.data_ptr(), N, H, W, float(data_range), float(sigma), ws.data_ptr(),
                                       out.data_ptr(), sums.data_ptr(), torch.cuda.current_stream(p.device).cuda_stream),
-               "mrisr_eval_metrics", kernels=2)
+               "mrisr_eval_metrics", kernels=3)
     return out[:N * 4].view(N, 4), out[N * 4:], sums
 
 

@@ -38,3 +38,15 @@ for Bn, H, C in ((64, 64, 320), (64, 32, 640), (128, 16, 1280)):
     report(f"layernorm bf16 [{x2.shape[0]},{C}] (1R+1W)", 2 * x.numel() * 2, time_ms(lambda: ops.layernorm(x2, g, b, 1e-5)))
 a = torch.empty(1 << 29, dtype=torch.bfloat16, device=dev); c = torch.empty_like(a)
 report("torch copy_ 1 GiB bf16 (1R+1W) [reference point]", 2 * a.numel() * 2, time_ms(lambda: c.copy_(a)))
+# ---- SURVEY §8(f) rank 4 kernels: volume slicing (1R+1W, transpose) and the one-pass metrics kernel (2R)
+from mri_diffusion_superresolution_b200.slices import volume_to_slices
+from mri_diffusion_superresolution_b200.evalmetrics import image_metrics
+for D in (128, 256):
+    raw = torch.rand(512, 512, D, device=dev) * 1200
+    report(f"slice_volume fp32 [512,512,{D}] -> [{D},1,512,512] (1R+1W)", 2 * raw.numel() * 4, time_ms(lambda: volume_to_slices(raw, 0.0, 900.0)))
+raw = torch.rand(300, 470, 128, device=dev) * 1200
+report("slice_volume fp32 [300,470,128] -> padded 512x512 (1R+1W of the output size)", (raw.numel() + 128 * 512 * 512) * 4, time_ms(lambda: volume_to_slices(raw, 0.0, 900.0)))
+for N in (128, 512):
+    p = torch.rand(N, 512, 512, device=dev); t = torch.rand(N, 512, 512, device=dev)
+    ms = time_ms(lambda: image_metrics(p, t))
+    report(f"eval_metrics fp32 {N} pairs 512x512 (2R) [compute/smem-bound: {N / ms * 1e3:.0f} pairs/s]", 2 * p.numel() * 4, ms)
