@@ -79,9 +79,10 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-def cpu_reference_sample(n_inf: int, threads: int, repeats: int = 1):
+def cpu_reference_sample(n_inf: int, threads: int, repeats: int = 1, cond: str = "adapter"):
     """Time the CPU restatement of the reference path (oracle/, fp32 PyTorch) on the host cores: one SD-1.5+LoRA UNet
-    forward and one Adapter_XL pass for ONE slice; slices/s is extrapolated as 1 / (n_inf * t_unet + t_adapter)."""
+    forward and one Adapter_XL pass for ONE slice; slices/s is extrapolated as 1 / (n_inf * t_unet + t_adapter).
+    ``cond="controlnet"``: the per-step unit is ControlNet + UNet, the once-per-slice unit the condition embedding."""
     import torch
     from oracle import adapter_oracle as ao
     from oracle import unet_oracle as uo
@@ -92,6 +93,29 @@ def cpu_reference_sample(n_inf: int, threads: int, repeats: int = 1):
     g = torch.Generator().manual_seed(1)
     x = torch.randn(1, 4, 64, 64, generator=g)
     ehs = torch.randn(1, 77, 768, generator=g)
+    if cond == "controlnet":
+        from oracle import controlnet_oracle as co
+        ccfg = uo.UNetConfig()
+        cp = co.init_params(ccfg, seed=3)
+        img = torch.rand(1, 3, 512, 512, generator=g) * 2 - 1
+
+        def step(t):
+            d, m = co.controlnet_forward(cp, x, torch.tensor(t), ehs, img, ccfg)
+            return uo.unet_forward(params, x, torch.tensor(t), ehs, cfg, down_block_additional_residuals=d, mid_block_additional_residual=m)
+
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            co.cond_embedding_forward(cp, img, 320)
+            t_emb = time.perf_counter() - t0
+            step(999)  # warm-up
+            ts = []
+            for _ in range(repeats):
+                t0 = time.perf_counter()
+                step(979)
+                ts.append(time.perf_counter() - t0)
+        # the oracle's controlnet_forward recomputes the (t-invariant) embedding every call: count it once per slice
+        t_step = min(ts) - t_emb
+        return 1.0 / (n_inf * t_step + t_emb), t_step, t_emb
     ashapes = ao.adapter_param_shapes()
     ap = {k: torch.randn(s, generator=g) * (0.5 / max(1, int(torch.tensor(s[1:]).prod())) ** 0.5) for k, s in ashapes.items()}
     img = torch.rand(1, 3, 512, 512, generator=g) * 2 - 1
@@ -119,15 +143,18 @@ def run_reference(args):
         pass  # the sample below has its own warm-up forward; extra warm-up passes would only burn minutes of CPU
     t_all0 = time.perf_counter()
     for _ in range(max(1, min(args.steps, 3))):
-        v, t_unet, t_ad = cpu_reference_sample(args.inference_steps, threads)
+        v, t_unet, t_ad = cpu_reference_sample(args.inference_steps, threads, cond=args.cond)
         vals.append(v)
     value = statistics.median(vals)
-    sample = (f"1 slice: 1 of {args.inference_steps} fp32 UNet(SD-1.5+LoRA r16) forwards ({t_unet:.2f} s) + 1 Adapter_XL pass "
+    unit_step = "UNet(SD-1.5+LoRA r16)" if args.cond == "adapter" else "ControlNet + UNet(SD-1.5+LoRA r16)"
+    unit_once = "Adapter_XL pass" if args.cond == "adapter" else "ControlNet condition embedding"
+    sample = (f"1 slice: 1 of {args.inference_steps} fp32 {unit_step} forwards ({t_unet:.2f} s) + 1 {unit_once} "
               f"({t_ad:.2f} s), extrapolated x{args.inference_steps}; oracle/ port of the diffusers path (diffusers not installable)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": "sd15_unet_lora16_t2iadapter_512px_50step", "batch_per_gpu": 1,
+            "config": {"workload": "sd15_unet_lora16_t2iadapter_512px_50step" if args.cond == "adapter"
+                       else "sd15_unet_lora16_controlnet_512px_50step", "batch_per_gpu": 1,
                        "inference_steps": args.inference_steps, "scheduler": args.sched},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -385,9 +412,10 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        v, t_unet, t_ad = cpu_reference_sample(NI, threads)
+        v, t_unet, t_ad = cpu_reference_sample(NI, threads, cond=args.cond)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"1 slice: 1 of {NI} fp32 UNet forwards ({t_unet:.2f} s) + 1 Adapter_XL pass ({t_ad:.2f} s), extrapolated x{NI}"}
+               "sample": f"1 slice: 1 of {NI} fp32 {'UNet' if args.cond == 'adapter' else 'ControlNet + UNet'} forwards ({t_unet:.2f} s) + 1 "
+                         f"{'Adapter_XL pass' if args.cond == 'adapter' else 'condition embedding'} ({t_ad:.2f} s), extrapolated x{NI}"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -26,3 +26,14 @@ for Bn in (16,32,64,128):
     xx=x[:Bn] if Bn<=64 else torch.randn(Bn,64,64,320,device=dev).to(torch.bfloat16)
     ms=graph_ms(lambda: ops.groupnorm(xx,g,b,32,1e-5,True))
     print(f"GN B={Bn}: {ms*1e3:8.1f} us {3*xx.numel()*2/ms/1e6:8.1f} GB/s")
+
+from mri_diffusion_superresolution_b200.slices import volume_to_slices
+from mri_diffusion_superresolution_b200.evalmetrics import image_metrics
+for shape in ((512, 512, 128), (512, 512, 256), (300, 470, 128)):
+    raw = torch.rand(*shape, device=dev) * 1200
+    ms = graph_ms(lambda: volume_to_slices(raw, 0.0, 900.0))
+    nbytes = (raw.numel() + shape[2] * 512 * 512) * 4
+    print(f"slice_volume {shape}: {ms*1e3:8.1f} us {nbytes/ms/1e6:8.1f} GB/s (1R of the volume + 1W of the slices)")
+p_ = torch.rand(128, 512, 512, device=dev); t_ = torch.rand(128, 512, 512, device=dev)
+ms = graph_ms(lambda: image_metrics(p_, t_), reps=4)
+print(f"eval_metrics 128 pairs 512x512: {ms*1e3:8.1f} us {128/ms*1e3:9.0f} pairs/s {2*p_.numel()*4/ms/1e6:8.1f} GB/s algorithmic")

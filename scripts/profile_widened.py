@@ -13,6 +13,7 @@ from mri_diffusion_superresolution_b200.vae import AutoencoderKLB200
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 Bv = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+SECTION = sys.argv[3] if len(sys.argv) > 3 else "all"      # all | cn | vae | aux  (what runs inside the profiled region)
 dev = torch.device("cuda")
 peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
 cfg = UNetConfig(lora_rank=16, lora_alpha=16.0)
@@ -40,13 +41,22 @@ def ev():
 
 def run(tag):
     out = {}
-    e0 = ev(); cn.set_condition(slices.expand(-1, 3, -1, -1), force=True); e1 = ev()
-    d, m = cn(x, None, time_proj=tp_c, return_dict=False); e2 = ev()
-    unet(x, None, time_proj=tp_u, down_block_additional_residuals=d, mid_block_additional_residual=m); e3 = ev()
-    dist = vae.encode(img3).latent_dist; e4 = ev()
-    vae.decode(z); e5 = ev()
-    image_metrics(pred, tgt); e6 = ev()
-    volume_to_slices(raw, 0.0, 900.0); e7 = ev()
+    on = lambda s: tag == "warm" or SECTION in ("all", s)
+    e0 = ev()
+    if on("cn"): cn.set_condition(slices.expand(-1, 3, -1, -1), force=True)
+    e1 = ev()
+    if on("cn"): d, m = cn(x, None, time_proj=tp_c, return_dict=False)
+    e2 = ev()
+    if on("cn"): unet(x, None, time_proj=tp_u, down_block_additional_residuals=d, mid_block_additional_residual=m)
+    e3 = ev()
+    if on("vae"): dist = vae.encode(img3).latent_dist
+    e4 = ev()
+    if on("vae"): vae.decode(z)
+    e5 = ev()
+    if on("aux"): image_metrics(pred, tgt)
+    e6 = ev()
+    if on("aux"): volume_to_slices(raw, 0.0, 900.0)
+    e7 = ev()
     torch.cuda.synchronize()
     names = ["cond_embedding", "controlnet", "unet_with_residuals", "vae_encode", "vae_decode", "metrics_128x512x512", "slice_volume_512x512x128"]
     evs = [e0, e1, e2, e3, e4, e5, e6, e7]
