@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MRISR_ABI_VERSION 3
+#define MRISR_ABI_VERSION 4
 
 #define MRISR_OK 0
 #define MRISR_E_INVALID (-1)     /* bad argument (null pointer, misaligned, negative size) */
@@ -78,11 +78,12 @@ int mrisr_timestep_embedding(const float* t, void* out_bf16, int batch, int dim,
 int64_t mrisr_groupnorm_workspace_floats(int batch, int groups);
 int mrisr_groupnorm(const void* x1, int64_t ld1, int c1, const void* x2, int64_t ld2, int c2, int batch, int hw,
                     int groups, const float* gamma, const float* beta, float eps, int silu, void* out,
-                    float* workspace, void* stream);
+                    float* workspace, int f16_flags /* bit 0: x1, bit 1: x2 is IEEE half (the fp16 residual stream) */, void* stream);
 
-/* LayerNorm over the last dim: bf16 [rows, C] (row stride ldx) -> bf16 [rows, C] (row stride ldo). C % 8 == 0, C <= 2048. */
+/* LayerNorm over the last dim: bf16 (or, in_f16 != 0, IEEE half) [rows, C] (row stride ldx) -> bf16 [rows, C] (row stride ldo).
+ * C % 8 == 0, C <= 2048. */
 int mrisr_layernorm(const void* x, int64_t ldx, const float* gamma, const float* beta, float eps, void* out,
-                    int64_t ldo, int rows, int C, void* stream);
+                    int64_t ldo, int rows, int C, int in_f16, void* stream);
 
 /* Tensor-core GEMM / implicit-GEMM conv (tcgen05 + TMEM + TMA):
  *     out[M, n_store] = act( concat_K(A1, A2) (*) W^T + bias + rowvec[batch(m)] ) + res1 + res2
@@ -121,7 +122,15 @@ typedef struct mrisr_gemm_args {
                           H, W are the INPUT dims (even), M = B*(H/2)*(W/2); the TMA box walks every second pixel */
   int32_t conv_pad_mode; /* taps == 9 only: 0 = zero padding 1 on every edge; 1 = zero padding on the bottom / right edge only
                             (diffusers AutoencoderKL Downsample2D(padding=0): F.pad(x, (0,1,0,1)) then a stride-2 valid conv) */
+  int32_t f16_flags;     /* which 16-bit tensors are IEEE half instead of bfloat16 (MRISR_F16_*): the UNet keeps its residual
+                            stream in fp16 (3 more mantissa bits than bf16: the stream's rounding error is the largest term of
+                            the noise-prediction error budget), everything else stays bf16 */
+  int32_t reserved3;
 } mrisr_gemm_args;
+#define MRISR_F16_OUT 1   /* out (when out_fp32 == 0) */
+#define MRISR_F16_RES1 2  /* res1 */
+#define MRISR_F16_RES2 4  /* res2 */
+#define MRISR_F16_AB 8    /* a1, a2 and w (all of them): f16 x f16 MMAs */
 int mrisr_gemm(const mrisr_gemm_args* args, void* stream);
 /* N-tile the kernel will use for (N, act); GEGLU callers interleave weight/bias rows in blocks of this size:
  * rows [t*BN, t*BN+BN/2) = value half, rows [t*BN+BN/2, (t+1)*BN) = gate half of output columns [t*BN/2, (t+1)*BN/2). */
@@ -135,13 +144,13 @@ int mrisr_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
                     int64_t ldo, int batch, int nq, int nk, int heads, int d, int kv_broadcast, void* stream);
 
 /* Layout / resampling helpers around the tensor-core kernels (all NHWC bf16 unless stated). */
-int mrisr_upsample2x(const void* in, void* out, int B, int H, int W, int C, void* stream);          /* diffusers Upsample2D (nearest) */
+int mrisr_upsample2x(const void* in, void* out, int B, int H, int W, int C, int in_f16, void* stream); /* diffusers Upsample2D (nearest); out is bf16 */
 int mrisr_im2col3x3s2(const void* in, void* out, int B, int H, int W, int C, void* stream);         /* diffusers Downsample2D / modules.py:52-76 */
 int mrisr_im2col_first(const float* in_nchw, void* out, int B, int Cin, int H, int W, int kpad, void* stream); /* UNet conv_in */
 int mrisr_pixel_unshuffle_nhwc(const float* in_nchw, void* out, int B, int C, int Hin, int Win, int r, void* stream); /* modules.py:148 */
 int mrisr_avgpool2(const void* in, void* out, int B, int H, int W, int C, void* stream);            /* modules.py:70-72 */
-int mrisr_add(const void* a, const void* b, void* out, int64_t n, void* stream);                    /* skips += residual (res_srdiff.py:76-77) */
-/* [B, R, Cc] -> [B, Cc, R].  dtype codes: 0 = fp32, 1 = bf16.  NCHW->NHWC: R = C, Cc = H*W.  NHWC->NCHW: R = H*W, Cc = C. */
+int mrisr_add(const void* a, const void* b, void* out, int64_t n, int f16_flags, void* stream);     /* skips += residual (res_srdiff.py:76-77); f16_flags bit 0 / 1 / 2: a / b / out is IEEE half */
+/* [B, R, Cc] -> [B, Cc, R].  dtype codes: 0 = fp32, 1 = bf16, 2 = fp16 (fp16 only to / from fp32).  NCHW->NHWC: R = C, Cc = H*W.  NHWC->NCHW: R = H*W, Cc = C. */
 int mrisr_transpose(const void* src, int src_dtype, void* dst, int dst_dtype, int B, int R, int Cc, void* stream);
 int mrisr_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
 

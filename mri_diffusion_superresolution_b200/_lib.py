@@ -30,6 +30,7 @@ class GemmArgs(C.Structure):
         ("out", C.c_void_p), ("ldo", C.c_int64),
         ("out_fp32", C.c_int32), ("reserved", C.c_int32),
         ("conv_stride", C.c_int32), ("conv_pad_mode", C.c_int32),
+        ("f16_flags", C.c_int32), ("reserved3", C.c_int32),
     ]
 
 
@@ -47,17 +48,17 @@ PROTOTYPES = {
     "mrisr_advance_index": (_I, [_P, _P]),
     "mrisr_timestep_embedding": (_I, [_P, _P, _I, _I, _P]),
     "mrisr_groupnorm_workspace_floats": (_L, [_I, _I]),
-    "mrisr_groupnorm": (_I, [_P, _L, _I, _P, _L, _I, _I, _I, _I, _P, _P, _F, _I, _P, _P, _P]),
-    "mrisr_layernorm": (_I, [_P, _L, _P, _P, _F, _P, _L, _I, _I, _P]),
+    "mrisr_groupnorm": (_I, [_P, _L, _I, _P, _L, _I, _I, _I, _I, _P, _P, _F, _I, _P, _P, _I, _P]),
+    "mrisr_layernorm": (_I, [_P, _L, _P, _P, _F, _P, _L, _I, _I, _I, _P]),
     "mrisr_gemm": (_I, [C.POINTER(GemmArgs), _P]),
     "mrisr_gemm_block_n": (_I, [_I, _I]),
     "mrisr_attention": (_I, [_P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _I, _I, _P]),
-    "mrisr_upsample2x": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "mrisr_upsample2x": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "mrisr_im2col3x3s2": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "mrisr_im2col_first": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "mrisr_pixel_unshuffle_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "mrisr_avgpool2": (_I, [_P, _P, _I, _I, _I, _I, _P]),
-    "mrisr_add": (_I, [_P, _P, _P, _L, _P]),
+    "mrisr_add": (_I, [_P, _P, _P, _L, _I, _P]),
     "mrisr_transpose": (_I, [_P, _I, _P, _I, _I, _I, _I, _P]),
     "mrisr_cast": (_I, [_P, _I, _P, _I, _L, _P]),
     "mrisr_bilinear_resize": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
@@ -86,7 +87,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.mrisr_abi_version() != 3:
+        if lib.mrisr_abi_version() != 4:
             raise RuntimeError("libmrisr_b200.so ABI version mismatch; rebuild")
         _lib = lib
     return _lib

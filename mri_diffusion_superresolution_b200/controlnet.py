@@ -18,7 +18,7 @@ What runs where:
 * the thirteen 1x1 "zero" convolutions are one ``mrisr_gemm`` each (``conditioning_scale`` folded into their weights
   and biases at load time).
 
-Residuals come back as bf16 tensors in channels-last memory (shape NCHW, strides NHWC), which
+Residuals come back as 16-bit tensors (the residual-stream format, fp16 by default) in channels-last memory (shape NCHW, strides NHWC), which
 ``UNet2DConditionB200`` consumes without a copy.
 """
 from __future__ import annotations
@@ -56,8 +56,9 @@ class ControlNetB200(UNet2DConditionB200):
     _encoder_only = True
 
     def __init__(self, config: Optional[UNetConfig] = None, device="cuda",
-                 conditioning_embedding_out_channels: Sequence[int] = (16, 32, 96, 256), conditioning_channels: int = 3):
-        super().__init__(config, device)
+                 conditioning_embedding_out_channels: Sequence[int] = (16, 32, 96, 256), conditioning_channels: int = 3,
+                 stream_dtype: torch.dtype = torch.float16):
+        super().__init__(config, device, stream_dtype)
         self.cond_channels = tuple(conditioning_embedding_out_channels)
         self.cond_in = conditioning_channels
         self.config.conditioning_channels = conditioning_channels
@@ -100,7 +101,8 @@ class ControlNetB200(UNet2DConditionB200):
     def _zero_convs(self, scale: float) -> List[Tuple[Tensor, Tensor]]:
         z = self._zero_dev.get(scale)
         if z is None:
-            z = [(self._dev(pack_conv1x1(w) * scale, torch.bfloat16), self._dev(b * scale, torch.float32)) for w, b in self.zero]
+            # the zero convs read the stored skips (the fp16 residual stream) directly: weights share that format
+            z = [(self._dev(pack_conv1x1(w) * scale, self.stream_dtype), self._dev(b * scale, torch.float32)) for w, b in self.zero]
             self._zero_dev[scale] = z
         return z
 
@@ -155,10 +157,10 @@ class ControlNetB200(UNet2DConditionB200):
         down = []
         for x, (w, b) in zip(skips, zero[:-1]):
             b_, hh, ww, cc = x.shape
-            down.append(ops.gemm(x.view(b_ * hh * ww, cc), w, bias=b).view(b_, hh, ww, cc).permute(0, 3, 1, 2))
+            down.append(ops.gemm(x.view(b_ * hh * ww, cc), w, bias=b, out_dtype=self.stream_dtype).view(b_, hh, ww, cc).permute(0, 3, 1, 2))
         b_, hh, ww, cc = s.shape
         w, b = zero[-1]
-        mid = ops.gemm(s.view(b_ * hh * ww, cc), w, bias=b).view(b_, hh, ww, cc).permute(0, 3, 1, 2)
+        mid = ops.gemm(s.view(b_ * hh * ww, cc), w, bias=b, out_dtype=self.stream_dtype).view(b_, hh, ww, cc).permute(0, 3, 1, 2)
         if not return_dict:
             return down, mid
         return ControlNetOutput(down, mid)

@@ -18,6 +18,7 @@
 //   the operands and is added exactly (bf16 x 1.0) in the fp32 accumulator.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "ptx.cuh"
 
@@ -28,7 +29,8 @@ enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2, ACT_GEGLU = 3 };
 struct GemmMaps {
   CUtensorMap a1, a2, b;  // operands
   CUtensorMap r1, r2;     // residuals as [M, N] A operands (res_mma > 0)
-  CUtensorMap ident;      // 256 x 256 identity weight tile
+  CUtensorMap ident;      // 256 x 256 identity weight tile (bf16)
+  CUtensorMap ident_h;    // the same in IEEE half, for residual operands stored in fp16
   CUtensorMap out;        // bf16 output, 32 x 32 boxes, 64B swizzle (tma_store)
 };
 
@@ -55,6 +57,11 @@ struct GemmKernelParams {
   void* out;
   long long ldo;
   int out_fp32;
+  // 16-bit tensors are bf16 unless flagged IEEE half here (the fp16 residual stream, see unet.py):
+  int f16_out;  // the 16-bit output
+  int f16_ab;   // A1 / A2 / W (all three): the main K loop runs f16 x f16 MMAs
+  int f16_r1, f16_r2;  // res1 / res2 added in the epilogue
+  int f16_rm;   // bit r: residual operand r of the MMA path (res_mma > 0)
   int dbg;  // timing experiments only: bit0 = skip TMA issue, bit1 = skip MMA issue (results are garbage)
 };
 
@@ -110,8 +117,19 @@ __device__ __forceinline__ void add_vec32(float (&f)[32], const float* __restric
     f[4 * u] += b.x; f[4 * u + 1] += b.y; f[4 * u + 2] += b.z; f[4 * u + 3] += b.w;
   }
 }
-__device__ __forceinline__ void add_res32(float (&f)[32], const __nv_bfloat16* __restrict__ src) {
+__device__ __forceinline__ void add_res32(float (&f)[32], const __nv_bfloat16* __restrict__ src, bool h) {
   const uint4* r = reinterpret_cast<const uint4*>(src);
+  if (h) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint4 x = __ldg(r + u);
+      f[u * 8 + 0] += f16_lo(x.x); f[u * 8 + 1] += f16_hi(x.x);
+      f[u * 8 + 2] += f16_lo(x.y); f[u * 8 + 3] += f16_hi(x.y);
+      f[u * 8 + 4] += f16_lo(x.z); f[u * 8 + 5] += f16_hi(x.z);
+      f[u * 8 + 6] += f16_lo(x.w); f[u * 8 + 7] += f16_hi(x.w);
+    }
+    return;
+  }
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const uint4 x = __ldg(r + u);
@@ -120,6 +138,10 @@ __device__ __forceinline__ void add_res32(float (&f)[32], const __nv_bfloat16* _
     f[u * 8 + 4] += bf16_lo(x.z); f[u * 8 + 5] += bf16_hi(x.z);
     f[u * 8 + 6] += bf16_lo(x.w); f[u * 8 + 7] += bf16_hi(x.w);
   }
+}
+
+__device__ __forceinline__ float load16(const __nv_bfloat16* p, bool h) {
+  return h ? __half2float(*reinterpret_cast<const __half*>(p)) : __bfloat162float(*p);
 }
 
 __device__ __forceinline__ void add_smem32(float (&f)[32], const float* s) {
@@ -210,11 +232,19 @@ __device__ __forceinline__ void gemm_epilogue_tma(const GemmKernelParams& p, con
         if (lane_id == 0) bulk_wait_group_read<1>();  // the store that last read THIS buffer has drained it
         __syncwarp();
         uint8_t* dst = buf + lane_id * 64;
+        if (p.f16_out) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          *reinterpret_cast<uint4*>(dst + ((u ^ sw) << 4)) =
-              make_uint4(pack_bf16(f[8 * u], f[8 * u + 1]), pack_bf16(f[8 * u + 2], f[8 * u + 3]),
-                         pack_bf16(f[8 * u + 4], f[8 * u + 5]), pack_bf16(f[8 * u + 6], f[8 * u + 7]));
+          for (int u = 0; u < 4; ++u)
+            *reinterpret_cast<uint4*>(dst + ((u ^ sw) << 4)) =
+                make_uint4(pack_f16(f[8 * u], f[8 * u + 1]), pack_f16(f[8 * u + 2], f[8 * u + 3]),
+                           pack_f16(f[8 * u + 4], f[8 * u + 5]), pack_f16(f[8 * u + 6], f[8 * u + 7]));
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            *reinterpret_cast<uint4*>(dst + ((u ^ sw) << 4)) =
+                make_uint4(pack_bf16(f[8 * u], f[8 * u + 1]), pack_bf16(f[8 * u + 2], f[8 * u + 3]),
+                           pack_bf16(f[8 * u + 4], f[8 * u + 5]), pack_bf16(f[8 * u + 6], f[8 * u + 7]));
+        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane_id == 0 && m_warp0 < p.M) {
@@ -283,8 +313,8 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmKernelParams& p, ui
     const bool chunk_full = n + 32 <= p.n_store;  // warp-uniform
     if (row_ok && n < p.n_store) {
       if (chunk_full) {
-        if (r1p != nullptr) add_res32(f, r1p + c * 32);
-        if (r2p != nullptr) add_res32(f, r2p + c * 32);
+        if (r1p != nullptr) add_res32(f, r1p + c * 32, p.f16_r1 != 0);
+        if (r2p != nullptr) add_res32(f, r2p + c * 32, p.f16_r2 != 0);
         if (p.out_fp32) {
           float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<long long>(m) * p.ldo + n);
 #pragma unroll
@@ -296,10 +326,12 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmKernelParams& p, ui
         for (int j = 0; j < 32; ++j) {
           if (n + j < p.n_store) {
             float x = f[j];
-            if (p.res1 != nullptr) x += __bfloat162float(p.res1[static_cast<long long>(m) * p.ldr1 + n + j]);
-            if (p.res2 != nullptr) x += __bfloat162float(p.res2[static_cast<long long>(m) * p.ldr2 + n + j]);
+            if (p.res1 != nullptr) x += load16(p.res1 + static_cast<long long>(m) * p.ldr1 + n + j, p.f16_r1 != 0);
+            if (p.res2 != nullptr) x += load16(p.res2 + static_cast<long long>(m) * p.ldr2 + n + j, p.f16_r2 != 0);
             if (p.out_fp32)
               static_cast<float*>(p.out)[static_cast<long long>(m) * p.ldo + n + j] = x;
+            else if (p.f16_out)
+              static_cast<__half*>(p.out)[static_cast<long long>(m) * p.ldo + n + j] = __float2half_rn(x);
             else
               static_cast<__nv_bfloat16*>(p.out)[static_cast<long long>(m) * p.ldo + n + j] = __float2bfloat16(x);
           }
@@ -308,11 +340,12 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmKernelParams& p, ui
     }
     if (chunk_full && !p.out_fp32 && !(p.dbg & 4)) {
       const int sw = (lane_id >> 1) & 3;
+      const bool h_out = p.f16_out != 0;
 #pragma unroll
       for (int u = 0; u < 4; ++u)
         *reinterpret_cast<uint4*>(stage_buf + lane_id * 64 + ((u ^ sw) << 4)) =
-            make_uint4(pack_bf16(f[8 * u], f[8 * u + 1]), pack_bf16(f[8 * u + 2], f[8 * u + 3]),
-                       pack_bf16(f[8 * u + 4], f[8 * u + 5]), pack_bf16(f[8 * u + 6], f[8 * u + 7]));
+            make_uint4(pack16(f[8 * u], f[8 * u + 1], h_out), pack16(f[8 * u + 2], f[8 * u + 3], h_out),
+                       pack16(f[8 * u + 4], f[8 * u + 5], h_out), pack16(f[8 * u + 6], f[8 * u + 7], h_out));
       __syncwarp();
       const int m_base = m - lane_id;  // first row of this warp
 #pragma unroll
@@ -364,6 +397,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
     if (p.res_mma > 0) {
       tma_prefetch_desc(&maps.r1);
       tma_prefetch_desc(&maps.ident);
+      if (p.f16_rm) tma_prefetch_desc(&maps.ident_h);
     }
     if (p.tma_store) tma_prefetch_desc(&maps.out);
   }
@@ -449,20 +483,23 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
         const int rk0 = res_first(n_blk), rkn = res_count(n_blk);
         for (int r = 0; r < p.res_mma; ++r)
           for (int j = 0; j < rkn; ++j)
-            load(r == 0 ? &maps.r1 : &maps.r2, false, (rk0 + j) * kBlockK, 0, 0, 0, m0, &maps.ident, j * kBlockK, n0 - rk0 * kBlockK);
+            load(r == 0 ? &maps.r1 : &maps.r2, false, (rk0 + j) * kBlockK, 0, 0, 0, m0, ((p.f16_rm >> r) & 1) ? &maps.ident_h : &maps.ident,
+                 j * kBlockK, n0 - rk0 * kBlockK);
       }
     }
   } else if (warp == 1) {
     reg_dealloc<72>();
     if (leader) {
       // ===================== MMA issuer (leader CTA; whole warp loops, one elected lane issues) =====================
-      constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN);
+      constexpr uint32_t idesc_b = umma_idesc_bf16(kTileM, BN), idesc_h = umma_idesc_f16(kTileM, BN);
+      const uint32_t idesc_main = p.f16_ab ? idesc_h : idesc_b;
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
       for (int tile = worker; tile < total_tiles; tile += num_workers, ++it) {
         const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
-        const int kiters = kmain + p.res_mma * res_count(tile % p.n_tiles);
+        const int rcount = res_count(tile % p.n_tiles);
+        const int kiters = kmain + p.res_mma * rcount;
         mbar_wait(tempty_bar(as), aph ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -472,6 +509,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint64_t adesc = umma_smem_desc(sa, 1024, kLayoutSW128);
           const uint64_t bdesc = umma_smem_desc(sa + Cfg::kABytes, 1024, kLayoutSW128);
+          // residual operand chunks carry their own element format (bf16 or IEEE half) against the matching identity tile
+          const uint32_t idesc = ki < kmain ? idesc_main : (((p.f16_rm >> ((ki - kmain) >= rcount ? 1 : 0)) & 1) ? idesc_h : idesc_b);
           if (elect_one()) {
             if (!(p.dbg & 2)) {
 #pragma unroll

@@ -118,11 +118,12 @@ int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims
 // data: no allocation, no init kernel, safe under CUDA-graph capture.
 struct IdentityTile {
   uint16_t v[256 * 256];
-  constexpr IdentityTile() : v() {
-    for (int i = 0; i < 256; ++i) v[i * 256 + i] = 0x3F80;  // bf16 1.0
+  constexpr explicit IdentityTile(uint16_t one) : v() {
+    for (int i = 0; i < 256; ++i) v[i * 256 + i] = one;
   }
 };
-__device__ const IdentityTile g_identity_tile = IdentityTile();
+__device__ const IdentityTile g_identity_tile = IdentityTile(0x3F80);    // bf16 1.0
+__device__ const IdentityTile g_identity_tile_h = IdentityTile(0x3C00);  // IEEE half 1.0 (fp16 residual-stream operands)
 
 template <int BN, bool kPair>
 int launch_gemm(const mrisr::GemmMaps& maps, const mrisr::GemmKernelParams& p, cudaStream_t st) {
@@ -299,7 +300,7 @@ bool use_tc_attention() {
 
 template <int VPL>
 int launch_layernorm(const void* x, int64_t ldx, const float* g, const float* b, float eps, void* out, int64_t ldo, int rows,
-                     int C, cudaStream_t st) {
+                     int C, int in_f16, cudaStream_t st) {
   constexpr int kRows = VPL <= 2 ? 4 : 2;  // rows in flight per warp (register budget: ROWS * VPL uint4 + one unpacked row)
   const int wpb = 8;
   const long long need = (static_cast<long long>(rows) + wpb * kRows - 1) / (wpb * kRows);
@@ -312,14 +313,14 @@ int launch_layernorm(const void* x, int64_t ldx, const float* g, const float* b,
   const long long cap = static_cast<long long>(sm_count()) * per_sm;
   const int grid = static_cast<int>(need < cap ? (need > 0 ? need : 1) : cap);
   launch_k(mrisr::layernorm_kernel<VPL, kRows>, dim3(grid), dim3(wpb * 32), static_cast<size_t>(C) * 8, st,
-           static_cast<const __nv_bfloat16*>(x), ldx, g, b, eps, static_cast<__nv_bfloat16*>(out), ldo, rows, C);
+           static_cast<const __nv_bfloat16*>(x), ldx, g, b, eps, static_cast<__nv_bfloat16*>(out), ldo, rows, C, in_f16);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 template <int LPR, int VPL>
 int launch_layernorm_group(const void* x, int64_t ldx, const float* g, const float* b, float eps, void* out, int64_t ldo,
-                           int rows, cudaStream_t st) {
+                           int rows, int in_f16, cudaStream_t st) {
   constexpr int kRowsPerCta = 8 * (32 / LPR) * 2;
   static int per_sm = 0;
   if (per_sm == 0) {
@@ -331,7 +332,7 @@ int launch_layernorm_group(const void* x, int64_t ldx, const float* g, const flo
   const long long cap = static_cast<long long>(sm_count()) * per_sm;
   const int grid = static_cast<int>(need < cap ? (need > 0 ? need : 1) : cap);
   launch_k(mrisr::layernorm_group_kernel<LPR, VPL>, dim3(grid), dim3(256), static_cast<size_t>(LPR * VPL) * 64, st,
-           static_cast<const __nv_bfloat16*>(x), ldx, g, b, eps, static_cast<__nv_bfloat16*>(out), ldo, rows);
+           static_cast<const __nv_bfloat16*>(x), ldx, g, b, eps, static_cast<__nv_bfloat16*>(out), ldo, rows, in_f16);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -429,7 +430,7 @@ int64_t mrisr_groupnorm_workspace_floats(int batch, int groups) {
 }
 
 int mrisr_groupnorm(const void* x1, int64_t ld1, int c1, const void* x2, int64_t ld2, int c2, int batch, int hw, int groups,
-                    const float* gamma, const float* beta, float eps, int silu, void* out, float* workspace,
+                    const float* gamma, const float* beta, float eps, int silu, void* out, float* workspace, int f16_flags,
                     void* stream) {
   MRISR_REQUIRE(x1 && gamma && beta && out && workspace, "groupnorm: null pointer");
   MRISR_REQUIRE(batch > 0 && hw > 0 && c1 > 0 && c2 >= 0, "groupnorm: bad sizes");
@@ -470,6 +471,7 @@ int mrisr_groupnorm(const void* x1, int64_t ld1, int c1, const void* x2, int64_t
   a.x1 = static_cast<const __nv_bfloat16*>(x1);
   a.x2 = static_cast<const __nv_bfloat16*>(x2);
   a.ld1 = ld1; a.ld2 = ld2; a.c1 = c1; a.c2 = c2; a.hw = hw; a.batch = batch; a.groups = groups;
+  a.h1 = f16_flags & 1; a.h2 = (f16_flags >> 1) & 1;
   a.nslab = nslab; a.pix_per_slab = pps;
   dim3 block(nvec, R), grid(nslab, batch);
   cudaStream_t st = as_stream(stream);
@@ -493,7 +495,7 @@ int mrisr_groupnorm(const void* x1, int64_t ld1, int c1, const void* x2, int64_t
 }
 
 int mrisr_layernorm(const void* x, int64_t ldx, const float* gamma, const float* beta, float eps, void* out, int64_t ldo,
-                    int rows, int C, void* stream) {
+                    int rows, int C, int in_f16, void* stream) {
   MRISR_REQUIRE(x && gamma && beta && out, "layernorm: null pointer");
   MRISR_REQUIRE(rows >= 0 && C > 0 && C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0, "layernorm: C and strides must be multiples of 8");
   MRISR_REQUIRE(aligned16(x) && aligned16(out) && aligned16(gamma) && aligned16(beta), "layernorm: misaligned pointer");
@@ -501,16 +503,16 @@ int mrisr_layernorm(const void* x, int64_t ldx, const float* gamma, const float*
   const int vpl = (C / 8 + 31) / 32;
   cudaStream_t st = as_stream(stream);
   // the UNet's widths map exactly onto lane groups (every lane busy, 5 vectors each)
-  if (C == 320) return launch_layernorm_group<8, 5>(x, ldx, gamma, beta, eps, out, ldo, rows, st);
-  if (C == 640) return launch_layernorm_group<16, 5>(x, ldx, gamma, beta, eps, out, ldo, rows, st);
-  if (C == 1280) return launch_layernorm_group<32, 5>(x, ldx, gamma, beta, eps, out, ldo, rows, st);
+  if (C == 320) return launch_layernorm_group<8, 5>(x, ldx, gamma, beta, eps, out, ldo, rows, in_f16, st);
+  if (C == 640) return launch_layernorm_group<16, 5>(x, ldx, gamma, beta, eps, out, ldo, rows, in_f16, st);
+  if (C == 1280) return launch_layernorm_group<32, 5>(x, ldx, gamma, beta, eps, out, ldo, rows, in_f16, st);
   switch (vpl) {
-    case 1: return launch_layernorm<1>(x, ldx, gamma, beta, eps, out, ldo, rows, C, st);
-    case 2: return launch_layernorm<2>(x, ldx, gamma, beta, eps, out, ldo, rows, C, st);
-    case 3: return launch_layernorm<3>(x, ldx, gamma, beta, eps, out, ldo, rows, C, st);
-    case 4: return launch_layernorm<4>(x, ldx, gamma, beta, eps, out, ldo, rows, C, st);
-    case 5: return launch_layernorm<5>(x, ldx, gamma, beta, eps, out, ldo, rows, C, st);
-    case 6: case 7: case 8: return launch_layernorm<8>(x, ldx, gamma, beta, eps, out, ldo, rows, C, st);
+    case 1: return launch_layernorm<1>(x, ldx, gamma, beta, eps, out, ldo, rows, C, in_f16, st);
+    case 2: return launch_layernorm<2>(x, ldx, gamma, beta, eps, out, ldo, rows, C, in_f16, st);
+    case 3: return launch_layernorm<3>(x, ldx, gamma, beta, eps, out, ldo, rows, C, in_f16, st);
+    case 4: return launch_layernorm<4>(x, ldx, gamma, beta, eps, out, ldo, rows, C, in_f16, st);
+    case 5: return launch_layernorm<5>(x, ldx, gamma, beta, eps, out, ldo, rows, C, in_f16, st);
+    case 6: case 7: case 8: return launch_layernorm<8>(x, ldx, gamma, beta, eps, out, ldo, rows, C, in_f16, st);
     default: return fail(MRISR_E_UNSUPPORTED, "layernorm: C = %d > 2048 unsupported", C);
   }
 }
@@ -647,29 +649,42 @@ int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
   p.res1 = static_cast<const __nv_bfloat16*>(g->res1); p.ldr1 = g->ldr1;
   p.res2 = static_cast<const __nv_bfloat16*>(g->res2); p.ldr2 = g->ldr2;
   p.out = g->out; p.ldo = g->ldo; p.out_fp32 = g->out_fp32;
+  MRISR_REQUIRE((g->f16_flags & ~15) == 0, "gemm: unknown bits in f16_flags");
+  MRISR_REQUIRE(!((g->f16_flags & MRISR_F16_OUT) && g->out_fp32), "gemm: f16 output flag with out_fp32");
+  p.f16_out = (g->f16_flags & MRISR_F16_OUT) ? 1 : 0;
+  p.f16_ab = (g->f16_flags & MRISR_F16_AB) ? 1 : 0;
+  p.f16_r1 = (g->f16_flags & MRISR_F16_RES1) ? 1 : 0;
+  p.f16_r2 = (g->f16_flags & MRISR_F16_RES2) ? 1 : 0;
+  p.f16_rm = 0;
   p.dbg = g->reserved;
   p.res_mma = 0;
   p.tma_store = 0;
-  maps.r1 = ma1; maps.r2 = ma1; maps.ident = ma1; maps.out = ma1;
+  maps.r1 = ma1; maps.r2 = ma1; maps.ident = ma1; maps.ident_h = ma1; maps.out = ma1;
 
   // Residuals of activation-free GEMMs become extra A operands against the identity tile (see gemm_tcgen05.cuh): the
   // epilogue then has no residual traffic at all.  MRISR_GEMM_RES_EPILOGUE=1 keeps them in the epilogue (A/B runs).
   static const bool res_in_epilogue = getenv("MRISR_GEMM_RES_EPILOGUE") != nullptr;
   if (g->act == MRISR_ACT_NONE && (g->res1 || g->res2) && !res_in_epilogue) {
     static const void* ident = nullptr;
+    static const void* ident_h = nullptr;
     if (ident == nullptr) {
       void* sym = nullptr;
       MRISR_CHECK_CUDA(cudaGetSymbolAddress(&sym, g_identity_tile));
       ident = sym;
+      MRISR_CHECK_CUDA(cudaGetSymbolAddress(&sym, g_identity_tile_h));
+      ident_h = sym;
     }
     {
       cuuint64_t dims[2] = {256, 256};
       cuuint64_t str[1] = {512};
       cuuint32_t box[2] = {64, static_cast<cuuint32_t>(pair ? BN / 2 : BN)};
       if (int e = encode_map(&maps.ident, ident, 2, dims, str, box)) return e;
+      if (int e = encode_map(&maps.ident_h, ident_h, 2, dims, str, box)) return e;
     }
     const void* rp[2] = {g->res1 ? g->res1 : g->res2, g->res1 ? g->res2 : nullptr};
     const long long rl[2] = {g->res1 ? g->ldr1 : g->ldr2, g->ldr2};
+    const int rh[2] = {g->res1 ? p.f16_r1 : p.f16_r2, p.f16_r2};
+    p.f16_rm = (rh[0] ? 1 : 0) | ((rp[1] != nullptr && rh[1]) ? 2 : 0);
     CUtensorMap* rm[2] = {&maps.r1, &maps.r2};
     for (int i = 0; i < 2 && rp[i] != nullptr; ++i) {
       // columns >= n_store are never stored: clip them (TMA zero-fills), so R only needs n_store readable columns
@@ -732,11 +747,11 @@ int mrisr_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   }
 }
 
-int mrisr_upsample2x(const void* in, void* out, int B, int H, int W, int C, void* stream) {
+int mrisr_upsample2x(const void* in, void* out, int B, int H, int W, int C, int in_f16, void* stream) {
   MRISR_REQUIRE(in && out && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "upsample2x: bad argument");
   MRISR_REQUIRE(aligned16(in) && aligned16(out), "upsample2x: misaligned pointer");
   const long long n = static_cast<long long>(B) * H * W * (C / 8);
-  launch_k(mrisr::upsample2x_kernel, dim3(grid_for(n, 256, 8)), dim3(256), 0, as_stream(stream), static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H, W, C / 8);
+  launch_k(mrisr::upsample2x_kernel, dim3(grid_for(n, 256, 8)), dim3(256), 0, as_stream(stream), static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H, W, C / 8, in_f16);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -776,21 +791,27 @@ int mrisr_avgpool2(const void* in, void* out, int B, int H, int W, int C, void* 
   return 0;
 }
 
-int mrisr_add(const void* a, const void* b, void* out, int64_t n, void* stream) {
+int mrisr_add(const void* a, const void* b, void* out, int64_t n, int f16_flags, void* stream) {
   MRISR_REQUIRE(a && b && out && n >= 0 && n % 8 == 0, "add: bad argument");
   MRISR_REQUIRE(aligned16(a) && aligned16(b) && aligned16(out), "add: misaligned pointer");
   if (n == 0) return 0;
-  launch_k(mrisr::add_bf16_kernel, dim3(grid_for(n / 8, 256, 8)), dim3(256), 0, as_stream(stream), static_cast<const uint4*>(a), static_cast<const uint4*>(b), static_cast<uint4*>(out), n / 8);
+  launch_k(mrisr::add_bf16_kernel, dim3(grid_for(n / 8, 256, 8)), dim3(256), 0, as_stream(stream), static_cast<const uint4*>(a), static_cast<const uint4*>(b), static_cast<uint4*>(out), n / 8, f16_flags);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int mrisr_transpose(const void* src, int sdt, void* dst, int ddt, int B, int R, int Cc, void* stream) {
   MRISR_REQUIRE(src && dst && B > 0 && R > 0 && Cc > 0, "transpose: bad argument");
-  MRISR_REQUIRE((sdt == 0 || sdt == 1) && (ddt == 0 || ddt == 1), "transpose: dtype codes are 0 (fp32) / 1 (bf16)");
+  MRISR_REQUIRE(sdt >= 0 && sdt <= 2 && ddt >= 0 && ddt <= 2, "transpose: dtype codes are 0 (fp32) / 1 (bf16) / 2 (fp16)");
   dim3 block(32, 8), grid((Cc + 31) / 32, (R + 31) / 32, B);
   cudaStream_t st = as_stream(stream);
-  if (sdt == 0 && ddt == 0)
+  if (sdt == 2 && ddt == 0)
+    launch_k(mrisr::transpose_kernel<__half, float>, dim3(grid), dim3(block), 0, st, static_cast<const __half*>(src), static_cast<float*>(dst), R, Cc);
+  else if (sdt == 0 && ddt == 2)
+    launch_k(mrisr::transpose_kernel<float, __half>, dim3(grid), dim3(block), 0, st, static_cast<const float*>(src), static_cast<__half*>(dst), R, Cc);
+  else if (sdt == 2 || ddt == 2)
+    return fail(MRISR_E_UNSUPPORTED, "transpose: fp16 pairs only with fp32");
+  else if (sdt == 0 && ddt == 0)
     launch_k(mrisr::transpose_kernel<float, float>, dim3(grid), dim3(block), 0, st, static_cast<const float*>(src), static_cast<float*>(dst), R, Cc);
   else if (sdt == 0 && ddt == 1)
     launch_k(mrisr::transpose_kernel<float, __nv_bfloat16>, dim3(grid), dim3(block), 0, st, static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst), R, Cc);
@@ -810,8 +831,14 @@ int mrisr_cast(const void* src, int sdt, void* dst, int ddt, int64_t n, void* st
     launch_k(mrisr::cast_f32_bf16_kernel, dim3(grid_for(n, 256, 8)), dim3(256), 0, st, static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst), n);
   else if (sdt == 1 && ddt == 0)
     launch_k(mrisr::cast_bf16_f32_kernel, dim3(grid_for(n, 256, 8)), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(src), static_cast<float*>(dst), n);
+  else if (sdt == 0 && ddt == 2)
+    launch_k(mrisr::cast_f32_f16_kernel, dim3(grid_for(n, 256, 8)), dim3(256), 0, st, static_cast<const float*>(src), static_cast<__half*>(dst), n);
+  else if (sdt == 2 && ddt == 0)
+    launch_k(mrisr::cast_f16_f32_kernel, dim3(grid_for(n, 256, 8)), dim3(256), 0, st, static_cast<const __half*>(src), static_cast<float*>(dst), n);
+  else if (sdt == 2 && ddt == 1)
+    launch_k(mrisr::cast_f16_bf16_kernel, dim3(grid_for(n, 256, 8)), dim3(256), 0, st, static_cast<const __half*>(src), static_cast<__nv_bfloat16*>(dst), n);
   else
-    return fail(MRISR_E_INVALID, "cast: only fp32<->bf16 supported");
+    return fail(MRISR_E_INVALID, "cast: supported pairs are fp32<->bf16, fp32<->fp16, fp16->bf16");
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

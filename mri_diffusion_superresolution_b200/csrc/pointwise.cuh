@@ -3,6 +3,7 @@
 // All are 128-bit vectorised, coalesced along the channel (innermost) dimension, fp32 math.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #include "ptx.cuh"
@@ -26,6 +27,26 @@ __device__ __forceinline__ void unpack8p(const uint4& x, float2 (&f)[4]) {
 }
 __device__ __forceinline__ uint4 pack8p(const float2 (&f)[4]) {
   return make_uint4(pack_bf16(f[0].x, f[0].y), pack_bf16(f[1].x, f[1].y), pack_bf16(f[2].x, f[2].y), pack_bf16(f[3].x, f[3].y));
+}
+// IEEE-half variants (the fp16 residual stream) and dtype-switched wrappers; `h` is uniform per thread
+__device__ __forceinline__ void unpack8h(const uint4& x, float (&f)[8]) {
+  f[0] = f16_lo(x.x); f[1] = f16_hi(x.x); f[2] = f16_lo(x.y); f[3] = f16_hi(x.y);
+  f[4] = f16_lo(x.z); f[5] = f16_hi(x.z); f[6] = f16_lo(x.w); f[7] = f16_hi(x.w);
+}
+__device__ __forceinline__ void unpack8_any(const uint4& x, float (&f)[8], bool h) {
+  if (h) unpack8h(x, f); else unpack8(x, f);
+}
+__device__ __forceinline__ void unpack8p_any(const uint4& x, float2 (&f)[4], bool h) {
+  if (h) {
+    f[0] = make_float2(f16_lo(x.x), f16_hi(x.x)); f[1] = make_float2(f16_lo(x.y), f16_hi(x.y));
+    f[2] = make_float2(f16_lo(x.z), f16_hi(x.z)); f[3] = make_float2(f16_lo(x.w), f16_hi(x.w));
+  } else {
+    unpack8p(x, f);
+  }
+}
+__device__ __forceinline__ uint4 pack8_any(const float (&f)[8], bool h) {
+  if (h) return make_uint4(pack_f16(f[0], f[1]), pack_f16(f[2], f[3]), pack_f16(f[4], f[5]), pack_f16(f[6], f[7]));
+  return pack8(f);
 }
 // SiLU with ONE MUFU op: y * sigmoid(y) = h + h * tanh(h), h = y / 2 (exp + reciprocal would be two MUFU ops per element,
 // i.e. 23 per clock per SM at the HBM rate against the 16 the XU pipe delivers).  tanh.approx: |rel err| ~ 2^-11.
@@ -183,6 +204,7 @@ struct GnArgs {
   int c1, c2;          // channels from each source (multiples of 8)
   int hw, batch, groups;
   int nslab, pix_per_slab;
+  int h1, h2;          // source is IEEE half (fp16 residual stream / skip) instead of bf16
 };
 
 __device__ __forceinline__ uint4 gn_load(const GnArgs& a, int b, int pix, int vx) {
@@ -198,6 +220,7 @@ __device__ __forceinline__ void gn_stats_body(const GnArgs& a, float2* __restric
   const int b = blockIdx.y, slab = blockIdx.x;
   const int tid = ry * blockDim.x + vx;
   const int C = a.c1 + a.c2;
+  const bool hsrc = (vx < (a.c1 >> 3) ? a.h1 : a.h2) != 0;
   float s[8], ss[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s[j] = 0.f; ss[j] = 0.f; }
@@ -211,14 +234,14 @@ __device__ __forceinline__ void gn_stats_body(const GnArgs& a, float2* __restric
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       float f[8];
-      unpack8(v[u], f);
+      unpack8_any(v[u], f, hsrc);
 #pragma unroll
       for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
     }
   }
   for (; pix < p1; pix += R) {
     float f[8];
-    unpack8(gn_load(a, b, pix, vx), f);
+    unpack8_any(gn_load(a, b, pix, vx), f, hsrc);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
   }
@@ -305,9 +328,10 @@ __device__ __forceinline__ void gn_apply_body(const GnArgs& a, const float2* par
   }
   const int p0 = slab * a.pix_per_slab;
   const int p1 = min(a.hw, p0 + a.pix_per_slab);
+  const bool hsrc = (vx < (a.c1 >> 3) ? a.h1 : a.h2) != 0;
   auto emit = [&](int pix, const uint4& v) {
     float2 f[4];
-    unpack8p(v, f);
+    unpack8p_any(v, f, hsrc);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       f[j] = __ffma2_rn(f[j], sc[j], sh[j]);
@@ -382,7 +406,7 @@ template <int VPL, int ROWS>  // 8-element vectors per lane (C <= 256 * VPL), ro
 __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, __nv_bfloat16* __restrict__ out, long long ldo, int rows,
-                                                        int C) {
+                                                        int C, int in_f16) {
   extern __shared__ float4 ln_sh[];  // [2 * nvec] gamma pairs, then [2 * nvec] beta pairs
   grid_dep_launch();
   const int nvec = C >> 3;
@@ -416,7 +440,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
       float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int k = 0; k < VPL; ++k) {
-        unpack8p(raw[r][k], f[k]);  // lanes beyond nvec hold zeros: they add nothing to the sum
+        unpack8p_any(raw[r][k], f[k], in_f16 != 0);  // lanes beyond nvec hold zeros: they add nothing to the sum
 #pragma unroll
         for (int j = 0; j < 4; ++j) s2 = __fadd2_rn(s2, f[k][j]);
       }
@@ -467,7 +491,7 @@ template <int LPR, int VPL>
 __global__ void __launch_bounds__(256) layernorm_group_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               float eps, __nv_bfloat16* __restrict__ out, long long ldo,
-                                                              int rows) {
+                                                              int rows, int in_f16) {
   constexpr int RPW = 32 / LPR;     // rows per warp per pass
   constexpr int NVEC = LPR * VPL;   // 16-byte vectors per row
   constexpr int UNROLL = 2;
@@ -500,7 +524,7 @@ __global__ void __launch_bounds__(256) layernorm_group_kernel(const __nv_bfloat1
       float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int k = 0; k < VPL; ++k) {
-        unpack8p(raw[u][k], f[k]);
+        unpack8p_any(raw[u][k], f[k], in_f16 != 0);
 #pragma unroll
         for (int j = 0; j < 4; ++j) s2 = __fadd2_rn(s2, f[k][j]);
       }
@@ -544,7 +568,7 @@ __global__ void __launch_bounds__(256) layernorm_group_kernel(const __nv_bfloat1
 
 // ---------------------------------------------------------------------------------------------------
 // Nearest 2x upsample, NHWC bf16: out[b, 2h+i, 2w+j, :] = in[b, h, w, :].
-__global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int nvec) {
+__global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int nvec, int in_f16) {
   grid_dep_launch();
   grid_dep_wait();
   const long long total = static_cast<long long>(B) * H * W * nvec;
@@ -554,7 +578,12 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restric
     const int w = static_cast<int>(p % W); p /= W;
     const int h = static_cast<int>(p % H);
     const int b = static_cast<int>(p / H);
-    const uint4 x = __ldg(in + i);
+    uint4 x = __ldg(in + i);
+    if (in_f16) {   // fp16 residual stream in, bf16 conv operand out
+      float f[8];
+      unpack8h(x, f);
+      x = pack8(f);
+    }
     const long long o = ((static_cast<long long>(b) * 2 * H + 2 * h) * 2 * W + 2 * w) * nvec + v;
     out[o] = x;
     out[o + nvec] = x;
@@ -656,16 +685,17 @@ __global__ void transpose_kernel(const TI* __restrict__ src, TO* __restrict__ ds
 }
 
 // out = a + b (bf16, 8-wide); used for ControlNet-style additional residuals on stored skips.
-__global__ void add_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out, long long nvec) {
+__global__ void add_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out, long long nvec,
+                                int f16_flags /* bit0: a, bit1: b, bit2: out are IEEE half */) {
   grid_dep_launch();
   grid_dep_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     float x[8], y[8];
-    unpack8(__ldg(a + i), x);
-    unpack8(__ldg(b + i), y);
+    unpack8_any(__ldg(a + i), x, (f16_flags & 1) != 0);
+    unpack8_any(__ldg(b + i), y, (f16_flags & 2) != 0);
 #pragma unroll
     for (int j = 0; j < 8; ++j) x[j] += y[j];
-    out[i] = pack8(x);
+    out[i] = pack8_any(x, (f16_flags & 4) != 0);
   }
 }
 
@@ -707,6 +737,25 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, float
   grid_dep_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = __bfloat162float(in[i]);
+}
+
+__global__ void cast_f32_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, long long n) {
+  grid_dep_launch();
+  grid_dep_wait();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __float2half_rn(in[i]);
+}
+__global__ void cast_f16_f32_kernel(const __half* __restrict__ in, float* __restrict__ out, long long n) {
+  grid_dep_launch();
+  grid_dep_wait();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __half2float(in[i]);
+}
+__global__ void cast_f16_bf16_kernel(const __half* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  grid_dep_launch();
+  grid_dep_wait();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16(__half2float(in[i]));
 }
 
 // dst[0:n] = table[(*idx) * stride : ... + n]  -- selects the per-step row (time-embedding projections, step

@@ -135,6 +135,10 @@ constexpr uint32_t kLayoutSW128 = 2, kLayoutSW64 = 4, kLayoutSW32 = 6;
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
+// same shape with A and B in IEEE half (a_format = b_format = 0): the fp16 residual-stream operands
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t m, uint32_t n) {
+  return (1u << 4) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -237,6 +241,23 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// two packed 16-bit floats -> fp32 pair; h selects IEEE half (the fp16 residual stream) over bfloat16
+__device__ __forceinline__ float f16_lo(uint32_t v) {
+  float r;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, l;\n\t}" : "=f"(r) : "r"(v));
+  return r;
+}
+__device__ __forceinline__ float f16_hi(uint32_t v) {
+  float r;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, h;\n\t}" : "=f"(r) : "r"(v));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack16(float lo, float hi, bool h) { return h ? pack_f16(lo, hi) : pack_bf16(lo, hi); }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 

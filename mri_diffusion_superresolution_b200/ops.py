@@ -18,7 +18,17 @@ from ._lib import ACT_GEGLU, ACT_NONE, ACT_RELU, ACT_SILU, GemmArgs  # noqa: F40
 Tensor = torch.Tensor
 # bench.py sets this to a list to time every tensor-core kernel launch with CUDA events (executed flops, taps, ev0, ev1)
 GEMM_PROFILE = None
-_DT = {torch.float32: 0, torch.bfloat16: 1}
+_DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+_H16 = (torch.bfloat16, torch.float16)     # 16-bit activation formats: bf16 everywhere, IEEE half for the residual stream
+F16_OUT, F16_RES1, F16_RES2, F16_AB = 1, 2, 4, 8
+
+
+def _cuda16(t: Tensor, name: str) -> Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (this package has no CPU path)")
+    if t.dtype not in _H16:
+        raise TypeError(f"{name}: expected bfloat16 or float16, got {t.dtype}")
+    return t
 
 
 def _stream(t: Tensor) -> int:
@@ -52,14 +62,18 @@ def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[T
          rowvec: Optional[Tensor] = None, rowvec_stride: int = 0, rows_per_batch: int = 0, act: int = ACT_NONE,
          res1: Optional[Tensor] = None, res2: Optional[Tensor] = None, n_store: Optional[int] = None,
          out_fp32: bool = False, conv: bool = False, stride: int = 1, out: Optional[Tensor] = None,
-         pad_mode: int = 0, _dbg: int = 0) -> Tensor:
+         pad_mode: int = 0, out_dtype=None, _dbg: int = 0) -> Tensor:
     """``act(concat_K(a1, a2) @ w.T + bias + rowvec[batch]) + res1 + res2`` on the tcgen05 kernel.
+
+    16-bit tensors are bf16 by default; ``a1`` / ``a2`` / ``w`` may (all three) be float16, ``res1`` / ``res2`` may each be
+    float16, and ``out_dtype=torch.float16`` stores IEEE half -- the UNet keeps its residual stream in fp16.
 
     GEMM mode: a1 ``[M, k1]`` (+ a2 ``[M, k2]``).  ``conv=True``: a1/a2 are NHWC ``[B, H, W, k]`` and ``w`` is
     ``[N, 9*(k1+k2)]`` (3x3, pad 1, ``stride`` 1 or 2 -- the downsamplers, M = B*(H/2)*(W/2)).  Returns ``[M, n_store]`` (bf16, or fp32 if ``out_fp32``)."""
     lib = _lib.load()
-    _cuda(a1, "gemm.a1", torch.bfloat16)
-    _cuda(w, "gemm.w", torch.bfloat16)
+    _cuda16(a1, "gemm.a1")
+    _cuda(w, "gemm.w", a1.dtype)
+    f16 = F16_AB if a1.dtype == torch.float16 else 0
     g = GemmArgs()
     if conv:
         if a1.dim() != 4 or a1.stride(3) != 1:
@@ -75,7 +89,7 @@ def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[T
         g.conv_pad_mode = pad_mode      # 1: zero padding on the bottom / right edge only (AutoencoderKL downsamplers)
         k2, lda2 = 0, 0
         if a2 is not None:
-            _cuda(a2, "gemm.a2", torch.bfloat16)
+            _cuda(a2, "gemm.a2", a1.dtype)
             if a2.dim() != 4 or tuple(a2.shape[:3]) != (B, H, W) or a2.stride(3) != 1:
                 raise ValueError("gemm(conv): a2 must be NHWC with the same B,H,W as a1")
             k2, lda2 = a2.shape[3], a2.stride(2)
@@ -87,7 +101,7 @@ def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[T
         M, k1 = a1.shape
         taps, k2, lda2 = 1, 0, 0
         if a2 is not None:
-            _cuda(a2, "gemm.a2", torch.bfloat16)
+            _cuda(a2, "gemm.a2", a1.dtype)
             lda2 = _rows(a2, "gemm.a2")
             if a2.shape[0] != M:
                 raise ValueError("gemm: a1 and a2 must have the same number of rows")
@@ -98,11 +112,19 @@ def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[T
     prod = N // 2 if act == ACT_GEGLU else N
     n_store = prod if n_store is None else n_store
     if out is None:
-        out = torch.empty((M, n_store), device=a1.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+        odt = torch.float32 if out_fp32 else (out_dtype or torch.bfloat16)
+        if odt not in (torch.float32,) + _H16:
+            raise TypeError(f"gemm: unsupported out_dtype {odt}")
+        out = torch.empty((M, n_store), device=a1.device, dtype=odt)
     else:
-        _cuda(out, "gemm.out", torch.float32 if out_fp32 else torch.bfloat16)
+        if out_fp32:
+            _cuda(out, "gemm.out", torch.float32)
+        else:
+            _cuda16(out, "gemm.out")
         if out.shape[0] != M or out.shape[1] < n_store:
             raise ValueError("gemm: out has the wrong shape")
+    if out.dtype == torch.float16:
+        f16 |= F16_OUT
     g.M, g.N, g.n_store = M, N, n_store
     g.k1, g.k2, g.taps = k1, k2, taps
     g.a1, g.lda1 = a1.data_ptr(), lda1
@@ -117,15 +139,18 @@ def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[T
         _cuda(rowvec, "gemm.rowvec", torch.float32)
     g.rowvec, g.rowvec_stride, g.rows_per_batch = _ptr(rowvec), rowvec_stride, rows_per_batch
     g.act = act
-    for name, r in (("res1", res1), ("res2", res2)):
+    for name, r, bit in (("res1", res1, F16_RES1), ("res2", res2, F16_RES2)):
         if r is not None:
-            _cuda(r, f"gemm.{name}", torch.bfloat16)
+            _cuda16(r, f"gemm.{name}")
             if r.shape[0] != M or r.shape[1] < n_store:
                 raise ValueError(f"gemm: {name} has the wrong shape")
+            if r.dtype == torch.float16:
+                f16 |= bit
     g.res1, g.ldr1 = _ptr(res1), (_rows(res1, "gemm.res1") if res1 is not None else 0)
     g.res2, g.ldr2 = _ptr(res2), (_rows(res2, "gemm.res2") if res2 is not None else 0)
     g.out, g.ldo, g.out_fp32 = out.data_ptr(), _rows(out, "gemm.out"), int(out_fp32)
     g.reserved = _dbg
+    g.f16_flags = f16
     if GEMM_PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(torch.cuda.current_stream(a1.device))
@@ -158,28 +183,30 @@ def groupnorm(x1: Tensor, gamma: Tensor, beta: Tensor, groups: int, eps: float, 
               x2: Optional[Tensor] = None) -> Tensor:
     """GroupNorm(+SiLU) of the channel concat [x1 | x2]; x*: NHWC ``[B, H, W, c]`` (channel-slice views allowed)."""
     lib = _lib.load()
-    _cuda(x1, "groupnorm.x1", torch.bfloat16)
+    _cuda16(x1, "groupnorm.x1")
     B, H, W, c1 = x1.shape
     c2, ld2 = 0, 0
+    f16 = 1 if x1.dtype == torch.float16 else 0
     if x2 is not None:
-        _cuda(x2, "groupnorm.x2", torch.bfloat16)
+        _cuda16(x2, "groupnorm.x2")
         c2, ld2 = x2.shape[3], x2.stride(2)
+        f16 |= 2 if x2.dtype == torch.float16 else 0
     out = torch.empty((B, H, W, c1 + c2), device=x1.device, dtype=torch.bfloat16)
     ws = torch.empty((lib.mrisr_groupnorm_workspace_floats(B, groups),), device=x1.device, dtype=torch.float32)
     _lib.check(lib.mrisr_groupnorm(x1.data_ptr(), x1.stride(2), c1, _ptr(x2), ld2, c2, B, H * W, groups,
                                    _cuda(gamma, "gamma", torch.float32).data_ptr(),
                                    _cuda(beta, "beta", torch.float32).data_ptr(), float(eps), int(silu),
-                                   out.data_ptr(), ws.data_ptr(), _stream(x1)), "mrisr_groupnorm", kernels=2)
+                                   out.data_ptr(), ws.data_ptr(), f16, _stream(x1)), "mrisr_groupnorm", kernels=2)
     return out
 
 
 def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5) -> Tensor:
     lib = _lib.load()
-    _cuda(x, "layernorm.x", torch.bfloat16)
+    _cuda16(x, "layernorm.x")
     rows, c = x.shape
     out = torch.empty((rows, c), device=x.device, dtype=torch.bfloat16)
     _lib.check(lib.mrisr_layernorm(x.data_ptr(), _rows(x, "x"), gamma.data_ptr(), beta.data_ptr(), float(eps),
-                                   out.data_ptr(), c, rows, c, _stream(x)), "mrisr_layernorm")
+                                   out.data_ptr(), c, rows, c, int(x.dtype == torch.float16), _stream(x)), "mrisr_layernorm")
     return out
 
 
@@ -274,10 +301,11 @@ def advance_index(idx: Tensor) -> None:
 
 def upsample2x(x: Tensor) -> Tensor:
     lib = _lib.load()
-    _cuda(x, "upsample2x.x", torch.bfloat16)
+    _cuda16(x, "upsample2x.x")
     B, H, W, c = x.shape
-    out = torch.empty((B, 2 * H, 2 * W, c), device=x.device, dtype=torch.bfloat16)
-    _lib.check(lib.mrisr_upsample2x(x.data_ptr(), out.data_ptr(), B, H, W, c, _stream(x)), "mrisr_upsample2x")
+    out = torch.empty((B, 2 * H, 2 * W, c), device=x.device, dtype=torch.bfloat16)     # always bf16: it feeds a conv
+    _lib.check(lib.mrisr_upsample2x(x.contiguous().data_ptr(), out.data_ptr(), B, H, W, c, int(x.dtype == torch.float16), _stream(x)),
+               "mrisr_upsample2x")
     return out
 
 
@@ -321,10 +349,13 @@ def avgpool2(x: Tensor) -> Tensor:
 
 def add(a: Tensor, b: Tensor) -> Tensor:
     lib = _lib.load()
-    _cuda(a, "add.a", torch.bfloat16)
-    _cuda(b, "add.b", torch.bfloat16)
-    out = torch.empty_like(a)
-    _lib.check(lib.mrisr_add(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), _stream(a)), "mrisr_add")
+    _cuda16(a, "add.a")
+    _cuda16(b, "add.b")
+    if a.shape != b.shape or not (a.is_contiguous() and b.is_contiguous()):
+        raise ValueError("add: operands must be contiguous and of equal shape")
+    out = torch.empty_like(a)          # result keeps a's 16-bit format
+    f16 = (1 if a.dtype == torch.float16 else 0) | (2 if b.dtype == torch.float16 else 0) | (4 if out.dtype == torch.float16 else 0)
+    _lib.check(lib.mrisr_add(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), f16, _stream(a)), "mrisr_add")
     return out
 
 

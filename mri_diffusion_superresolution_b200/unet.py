@@ -99,9 +99,19 @@ class UNet2DConditionB200:
 
     _encoder_only = False   # ControlNetB200 (controlnet.py) reuses conv_in / time embedding / down / mid only
 
-    def __init__(self, config: Optional[UNetConfig] = None, device: Union[str, torch.device] = "cuda"):
+    def __init__(self, config: Optional[UNetConfig] = None, device: Union[str, torch.device] = "cuda",
+                 stream_dtype: torch.dtype = torch.float16):
         self.cfg = config or UNetConfig()
         self.device = torch.device(device)
+        # Storage format of the RESIDUAL STREAM (resnet / transformer outputs, the token stream inside a transformer block,
+        # the skip tensors).  Every other activation and all GEMM operands stay bf16.  The stream is re-rounded ~86 times
+        # between conv_in and conv_out; with bf16 (8 significand bits) that random walk is the largest term of the noise
+        # prediction's error (6.5e-3 of the 8-11e-3 total vs the fp32 oracle), IEEE half (11 bits) cuts it 4x at the same
+        # 2 bytes per element.  SD-1.5 activations are routinely held in fp16 (the reference trains under fp16 autocast,
+        # notebooks/ResDif_execution.ipynb:623).  torch.bfloat16 restores the all-bf16 behaviour.
+        if stream_dtype not in (torch.float16, torch.bfloat16):
+            raise ValueError("stream_dtype must be torch.float16 or torch.bfloat16")
+        self.stream_dtype = stream_dtype
         c = self.cfg
         self.config = SimpleNamespace(in_channels=c.in_channels, out_channels=c.out_channels,
                                       block_out_channels=c.block_out_channels, layers_per_block=c.layers_per_block,
@@ -137,6 +147,7 @@ class UNet2DConditionB200:
         sd = normalize_state_dict_keys(state_dict)
         c = self.cfg
         bf, f32 = torch.bfloat16, torch.float32
+        sd_t = self.stream_dtype      # weights of the GEMMs whose A operand IS the stream share its format
         used = set()
 
         def get(k):
@@ -161,7 +172,7 @@ class UNet2DConditionB200:
             r.b2 = self._dev(get(f"{prefix}.conv2.bias"), f32)
             r.wsc = r.bsc = None
             if has(f"{prefix}.conv_shortcut.weight"):
-                r.wsc = self._dev(pack_conv1x1(get(f"{prefix}.conv_shortcut.weight")), bf)
+                r.wsc = self._dev(pack_conv1x1(get(f"{prefix}.conv_shortcut.weight")), sd_t)   # A operand = the stream
                 r.bsc = self._dev(get(f"{prefix}.conv_shortcut.bias"), f32)
             elif cin != cout:
                 raise KeyError(f"{prefix}.conv_shortcut.weight missing")
@@ -193,7 +204,7 @@ class UNet2DConditionB200:
             a.gnw, a.gnb = self._dev(get(f"{prefix}.norm.weight"), f32), self._dev(get(f"{prefix}.norm.bias"), f32)
             a.w_in = self._dev(pack_conv1x1(get(f"{prefix}.proj_in.weight")), bf)
             a.b_in = self._dev(get(f"{prefix}.proj_in.bias"), f32)
-            a.w_out = self._dev(pack_conv1x1(get(f"{prefix}.proj_out.weight")), bf)
+            a.w_out = self._dev(pack_conv1x1(get(f"{prefix}.proj_out.weight")), sd_t)         # A operand = the token stream
             a.b_out = self._dev(get(f"{prefix}.proj_out.bias"), f32)
             tb = f"{prefix}.transformer_blocks.0"
             for n in ("norm1", "norm2", "norm3"):
@@ -240,7 +251,7 @@ class UNet2DConditionB200:
                     blk["attn"].append(attn(f"down_blocks.{i}.attentions.{j}", ch[i]))
                 skip_ch.append(ch[i])
             if i < nlev - 1:
-                blk["ds"] = (self._dev(pack_conv3x3(get(f"down_blocks.{i}.downsamplers.0.conv.weight")), bf),
+                blk["ds"] = (self._dev(pack_conv3x3(get(f"down_blocks.{i}.downsamplers.0.conv.weight")), sd_t),
                              self._dev(get(f"down_blocks.{i}.downsamplers.0.conv.bias"), f32))
                 skip_ch.append(ch[i])
             self.down.append(blk)
@@ -335,11 +346,13 @@ class UNet2DConditionB200:
         h = ops.gemm(h, r.w1, bias=r.b1, rowvec=temb[:, r.temb_off:], rowvec_stride=temb_stride, rows_per_batch=H * W,
                      conv=True)
         h = ops.groupnorm(h.view(B, H, W, r.cout), r.n2w, r.n2b, c.norm_num_groups, c.norm_eps, True)
+        sd = self.stream_dtype
         if r.wsc is not None:
-            sc = ops.gemm(x1.view(M, x1.shape[3]), r.wsc, a2=None if x2 is None else x2.view(M, x2.shape[3]), bias=r.bsc)
+            sc = ops.gemm(x1.view(M, x1.shape[3]), r.wsc, a2=None if x2 is None else x2.view(M, x2.shape[3]), bias=r.bsc,
+                          out_dtype=sd)
         else:
             sc = x1.view(M, r.cin)
-        out = ops.gemm(h, r.w2, bias=r.b2, res1=sc, res2=extra_res, conv=True)
+        out = ops.gemm(h, r.w2, bias=r.b2, res1=sc, res2=extra_res, conv=True, out_dtype=sd)
         return out.view(B, H, W, r.cout)
 
     def _lora_gemm(self, x: Tensor, a_w: Optional[Tensor], w: Tensor, **kw) -> Tensor:
@@ -353,23 +366,24 @@ class UNet2DConditionB200:
         heads = c.num_heads
         xr = x.view(M, C)
         h = ops.groupnorm(x, a.gnw, a.gnb, c.norm_num_groups, 1e-6, False)
-        h = ops.gemm(h.view(M, C), a.w_in, bias=a.b_in)
+        sd = self.stream_dtype
+        h = ops.gemm(h.view(M, C), a.w_in, bias=a.b_in, out_dtype=sd)
         # self-attention
         y = ops.layernorm(h, a.ln1[0], a.ln1[1], 1e-5)
         qkv = self._lora_gemm(y, a.a_qkv, a.w_qkv)
         o = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, heads)
-        h = self._lora_gemm(o, a.a_o1, a.w_o1, bias=a.b_o1, res1=h)
+        h = self._lora_gemm(o, a.a_o1, a.w_o1, bias=a.b_o1, res1=h, out_dtype=sd)
         # cross-attention on the cached prompt projections
         kv, kb, kl = a.kv_cache
         y = ops.layernorm(h, a.ln2[0], a.ln2[1], 1e-5)
         q = self._lora_gemm(y, a.a_q2, a.w_q2)
         o = ops.attention(q, kv[:, :C], kv[:, C:], B, heads, kv_broadcast=(kb == 1))
-        h = self._lora_gemm(o, a.a_o2, a.w_o2, bias=a.b_o2, res1=h)
+        h = self._lora_gemm(o, a.a_o2, a.w_o2, bias=a.b_o2, res1=h, out_dtype=sd)
         # GEGLU feed-forward
         y = ops.layernorm(h, a.ln3[0], a.ln3[1], 1e-5)
         f = ops.gemm(y, a.w_ff1, bias=a.b_ff1, act=ops.ACT_GEGLU)
-        h = ops.gemm(f, a.w_ff2, bias=a.b_ff2, res1=h)
-        out = ops.gemm(h, a.w_out, bias=a.b_out, res1=xr, res2=extra_res)
+        h = ops.gemm(f, a.w_ff2, bias=a.b_ff2, res1=h, out_dtype=sd)
+        out = ops.gemm(h, a.w_out, bias=a.b_out, res1=xr, res2=extra_res, out_dtype=sd)
         return out.view(B, H, W, C)
 
     def _to_nhwc(self, t: Tensor, B: int, H: int, W: int, C: int) -> Tensor:
@@ -377,7 +391,7 @@ class UNet2DConditionB200:
         already bf16 channels-last memory (what ``Adapter_XL`` of this package returns)."""
         if tuple(t.shape) != (B, C, H, W):
             raise ValueError(f"additional residual has shape {tuple(t.shape)}, expected {(B, C, H, W)}")
-        if t.dtype == torch.bfloat16 and t.stride() == (H * W * C, 1, W * C, C):
+        if t.dtype in (torch.bfloat16, torch.float16) and t.stride() == (H * W * C, 1, W * C, C):
             return t.permute(0, 2, 3, 1).reshape(B * H * W, C)
         t = t.to(self.device)
         if t.dtype not in (torch.float32, torch.bfloat16):
@@ -424,7 +438,7 @@ class UNet2DConditionB200:
         B, _, H, W = x32.shape
         ch = c.block_out_channels
         cols = ops.im2col_first(x32, self.kin)
-        s = ops.gemm(cols, self.w_conv_in, bias=self.b_conv_in, res1=conv_in_res).view(B, H, W, ch[0])
+        s = ops.gemm(cols, self.w_conv_in, bias=self.b_conv_in, res1=conv_in_res, out_dtype=self.stream_dtype).view(B, H, W, ch[0])
         tap("conv_in", s)
         skips = [s]
         h_, w_ = H, W
@@ -442,7 +456,7 @@ class UNet2DConditionB200:
             if blk["ds"] is not None:
                 wd, bd = blk["ds"]
                 h_, w_ = h_ // 2, w_ // 2
-                s = ops.gemm(s, wd, bias=bd, conv=True, stride=2).view(B, h_, w_, ch[i])  # stride-2 TMA boxes: no im2col
+                s = ops.gemm(s, wd, bias=bd, conv=True, stride=2, out_dtype=self.stream_dtype).view(B, h_, w_, ch[i])  # stride-2 TMA boxes
                 tap(f"down_blocks.{i}.downsamplers.0", s)
                 skips.append(s)
         return s, skips
@@ -498,7 +512,7 @@ class UNet2DConditionB200:
             if blk["us"] is not None:
                 wu, bu = blk["us"]
                 b_, hh, ww, cc = s.shape
-                s = ops.gemm(ops.upsample2x(s), wu, bias=bu, conv=True).view(b_, 2 * hh, 2 * ww, cc)
+                s = ops.gemm(ops.upsample2x(s), wu, bias=bu, conv=True, out_dtype=self.stream_dtype).view(b_, 2 * hh, 2 * ww, cc)
                 tap(f"up_blocks.{i}.upsamplers.0", s)
         h = ops.groupnorm(s, self.n_out_w, self.n_out_b, c.norm_num_groups, c.norm_eps, True)
         o = ops.gemm(h, self.w_conv_out, bias=self.b_conv_out, n_store=c.out_channels, out_fp32=True, conv=True)

@@ -21,7 +21,7 @@ def test_abi_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.mrisr_abi_version() == 3
+    assert lib.mrisr_abi_version() == 4
     assert lib.mrisr_gemm_block_n(320, 0) == 160 and lib.mrisr_gemm_block_n(2560, 3) == 256 and lib.mrisr_gemm_block_n(100, 0) == 0
 
 

@@ -362,3 +362,78 @@ def test_layout_helpers(ops):
     ops.advance_index(idx)
     ops.select_row(table, idx, dst)
     assert torch.equal(dst, table[2])
+
+
+# ------------------------------------------------------------------------------------------------ fp16 residual stream
+def _h16(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(torch.float16).cuda()
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 320, 320), (1000, 640, 1280), (8192, 160 * 8, 320), (300, 1280, 2560)])
+def test_gemm_fp16_stream_residuals_and_output(ops, M, N, K):
+    """The residual stream in IEEE half: fp16 residual operands ride the MMA against an fp16 identity tile, mixed with a
+    bf16 second residual (T2I feature), and the output is stored as fp16 -- with the main operands in bf16."""
+    a = _bf((M, K), 71)
+    w = _bf((N, K), 72, 1.0 / math.sqrt(K))
+    bias = _f32((N,), 73)
+    r1 = _h16((M, N), 74, 3.0)
+    r2 = _bf((M, N), 75, 0.5)
+    ref = a.float() @ w.float().t() + bias + r1.float() + r2.float()
+    out = ops.gemm(a, w, bias=bias, res1=r1, res2=r2, out_dtype=torch.float16)
+    assert out.dtype == torch.float16
+    assert _rel(out, ref) < 5e-4                                   # fp16 output rounding: 2^-11
+    assert (out.float() - ref).abs().max().item() < 0.02
+    # only-res2-given ordering, bf16 output, and the identity add being exact: out == fp16(r) when W == 0
+    z = torch.zeros_like(w)
+    assert torch.equal(ops.gemm(a, z, res2=r1, out_dtype=torch.float16), r1)
+    assert torch.equal(ops.gemm(a, z, res1=r2, res2=r1, out_dtype=torch.float16), (r2.float() + r1.float()).to(torch.float16))
+    out_b = ops.gemm(a, w, bias=bias, res1=r1)
+    assert out_b.dtype == torch.bfloat16 and _rel(out_b, a.float() @ w.float().t() + bias + r1.float()) < 4e-3
+    # epilogue-residual path (activation present) with an fp16 residual and fp16 / fp32 outputs
+    ref_s = F.silu(a.float() @ w.float().t() + bias) + r1.float()
+    assert _rel(ops.gemm(a, w, bias=bias, act=ops.ACT_SILU, res1=r1, out_dtype=torch.float16), ref_s) < 5e-4
+    assert _rel(ops.gemm(a, w, bias=bias, act=ops.ACT_SILU, res1=r1, out_fp32=True), ref_s) < 2e-5
+
+
+@pytest.mark.parametrize("conv", [False, True])
+def test_gemm_fp16_operands(ops, conv):
+    """GEMMs whose A operand IS the stream (shortcut 1x1 conv over [x | skip], stride-2 downsampler, proj_out, ControlNet
+    zero convs) run f16 x f16 MMAs with fp16 copies of their weights."""
+    from mri_diffusion_superresolution_b200.packing import pack_conv3x3
+    if conv:
+        x = _h16((2, 32, 32, 128), 81)
+        w4 = (torch.randn(192, 128, 3, 3, generator=torch.Generator().manual_seed(82)) / math.sqrt(9 * 128)).to(torch.float16).cuda()
+        out = ops.gemm(x, pack_conv3x3(w4), conv=True, stride=2, out_dtype=torch.float16)
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), w4.float(), stride=2, padding=1).permute(0, 2, 3, 1).reshape(-1, 192)
+    else:
+        a1, a2 = _h16((3000, 320), 83), _h16((3000, 640), 84)
+        w = _h16((640, 960), 85, 1.0 / math.sqrt(960))
+        out = ops.gemm(a1, w, a2=a2, out_dtype=torch.float16)
+        ref = torch.cat([a1, a2], 1).float() @ w.float().t()
+    assert out.dtype == torch.float16 and _rel(out, ref) < 5e-4
+    with pytest.raises(TypeError):
+        ops.gemm(_h16((128, 64), 1), _bf((64, 64), 2))             # operand formats must match
+
+
+def test_norms_add_upsample_read_fp16(ops):
+    x = _h16((3, 16, 16, 320), 91, 4.0)
+    x2 = _bf((3, 16, 16, 64), 92)
+    g, b = 1 + 0.1 * _f32((384,), 93), 0.1 * _f32((384,), 94)
+    out = ops.groupnorm(x, g, b, 32, 1e-5, True, x2=x2)
+    cat = torch.cat([x.float(), x2.float()], -1).permute(0, 3, 1, 2)
+    ref = F.silu(F.group_norm(cat, 32, g, b, 1e-5)).permute(0, 2, 3, 1)
+    assert out.dtype == torch.bfloat16 and _rel(out, ref) < 4e-3
+    for C in (320, 640, 1280, 96):
+        t = _h16((500, C), 95, 3.0)
+        gg, bb = 1 + 0.1 * _f32((C,), 96), 0.1 * _f32((C,), 97)
+        assert _rel(ops.layernorm(t, gg, bb, 1e-5), F.layer_norm(t.float(), (C,), gg, bb, 1e-5)) < 4e-3
+    a, r = _h16((2, 8, 8, 64), 98), _bf((2, 8, 8, 64), 99)
+    s = ops.add(a, r)
+    assert s.dtype == torch.float16 and torch.equal(s, (a.float() + r.float()).to(torch.float16))
+    up = ops.upsample2x(a)
+    assert up.dtype == torch.bfloat16
+    assert torch.equal(up, a.float().to(torch.bfloat16).repeat_interleave(2, 1).repeat_interleave(2, 2))
+    nchw = ops.nhwc_to_nchw(a, torch.float32)
+    assert torch.equal(nchw, a.float().permute(0, 3, 1, 2))
+    assert torch.equal(ops.cast(a, torch.float32), a.float()) and torch.equal(ops.cast(a.float(), torch.float16), a)
