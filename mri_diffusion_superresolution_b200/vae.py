@@ -9,7 +9,8 @@ its legacy ``query/key/value/proj_attn`` names).
 
 Every conv is one ``mrisr_gemm`` launch (implicit GEMM through TMA, 128-pixel row-segment tiles at the 128..512-pixel
 levels; the asymmetric (0,1,0,1)-padded stride-2 downsamplers use ``conv_pad_mode = 1``), GroupNorm(+SiLU) is the
-UNet's fused kernel, residual adds ride the GEMM as operands.  The single-head d = 512 attention of the mid block is
+UNet's fused kernel, residual adds ride the GEMM as operands; the residual stream is stored in IEEE half like the UNet's
+(``stream_dtype``), every other activation in bf16.  The single-head d = 512 attention of the mid block is
 QK^T and PV on the same GEMM kernel with ``mrisr_softmax_rows`` between them (fp32 logits).  Images are processed in
 chunks of ``max_batch`` slices: one 512^2 x 128-channel activation is 67 MB.
 """
@@ -64,10 +65,14 @@ class _Res:
 class AutoencoderKLB200:
     """B200-native drop-in for ``diffusers.AutoencoderKL`` (SD-1.5 configuration) on the path's two call sites."""
 
-    def __init__(self, config: Optional[VAEConfig] = None, device="cuda", max_batch: int = 8):
+    def __init__(self, config: Optional[VAEConfig] = None, device="cuda", max_batch: int = 8,
+                 stream_dtype: torch.dtype = torch.float16):
         self.cfg = config or VAEConfig()
         self.device = torch.device(device)
         self.max_batch = int(max_batch)
+        if stream_dtype not in (torch.float16, torch.bfloat16):
+            raise ValueError("stream_dtype must be torch.float16 or torch.bfloat16")
+        self.stream_dtype = stream_dtype      # residual-stream storage format, as in UNet2DConditionB200
         c = self.cfg
         self.config = SimpleNamespace(scaling_factor=c.scaling_factor, latent_channels=c.latent_channels,
                                       in_channels=c.in_channels, out_channels=c.out_channels,
@@ -105,6 +110,7 @@ class AutoencoderKLB200:
             sd[k] = v
         c = self.cfg
         bf, f32 = torch.bfloat16, torch.float32
+        sd_t = self.stream_dtype      # weights of the GEMMs whose A operand IS the stream share its format
         used = set()
 
         def get(k):
@@ -120,7 +126,7 @@ class AutoencoderKLB200:
             r.w2, r.b2 = self._dev(pack_conv3x3(get(f"{prefix}.conv2.weight")), bf), self._dev(get(f"{prefix}.conv2.bias"), f32)
             r.wsc = r.bsc = None
             if cin != cout:
-                r.wsc = self._dev(pack_conv1x1(get(f"{prefix}.conv_shortcut.weight")), bf)
+                r.wsc = self._dev(pack_conv1x1(get(f"{prefix}.conv_shortcut.weight")), sd_t)
                 r.bsc = self._dev(get(f"{prefix}.conv_shortcut.bias"), f32)
             return r
 
@@ -148,7 +154,7 @@ class AutoencoderKLB200:
                 blk["res"].append(resnet(f"encoder.down_blocks.{i}.resnets.{j}", prev, ch[i]))
                 prev = ch[i]
             if i < n - 1:
-                blk["ds"] = (self._dev(pack_conv3x3(get(f"encoder.down_blocks.{i}.downsamplers.0.conv.weight")), bf),
+                blk["ds"] = (self._dev(pack_conv3x3(get(f"encoder.down_blocks.{i}.downsamplers.0.conv.weight")), sd_t),
                              self._dev(get(f"encoder.down_blocks.{i}.downsamplers.0.conv.bias"), f32))
             self.e_down.append(blk)
         self.e_mid = mid("encoder.mid_block", ch[-1])
@@ -194,8 +200,9 @@ class AutoencoderKLB200:
         h = ops.groupnorm(x, r.n1[0], r.n1[1], c.norm_num_groups, c.norm_eps, True)
         h = ops.gemm(h, r.w1, bias=r.b1, conv=True).view(B, H, W, r.cout)
         h = ops.groupnorm(h, r.n2[0], r.n2[1], c.norm_num_groups, c.norm_eps, True)
-        sc = ops.gemm(x.view(M, r.cin), r.wsc, bias=r.bsc) if r.wsc is not None else x.view(M, r.cin)
-        return ops.gemm(h, r.w2, bias=r.b2, res1=sc, conv=True).view(B, H, W, r.cout)
+        sd = self.stream_dtype
+        sc = ops.gemm(x.view(M, r.cin), r.wsc, bias=r.bsc, out_dtype=sd) if r.wsc is not None else x.view(M, r.cin)
+        return ops.gemm(h, r.w2, bias=r.b2, res1=sc, conv=True, out_dtype=sd).view(B, H, W, r.cout)
 
     def _attention(self, m: dict, x: Tensor) -> Tensor:
         """diffusers ``Attention(heads=1, dim_head=C, residual_connection=True)`` on the flattened feature map."""
@@ -218,7 +225,7 @@ class AutoencoderKLB200:
             ops.softmax_rows(s, C ** -0.5, out=p)
             ops.gemm(p, vt[b], out=o[b * n:(b + 1) * n])                                   # O = P V
         wo, bo = m["lin"]["to_out.0"]
-        return ops.gemm(o, wo, bias=bo, res1=xr).view(B, H, W, C)
+        return ops.gemm(o, wo, bias=bo, res1=xr, out_dtype=self.stream_dtype).view(B, H, W, C)
 
     def _mid(self, m: dict, x: Tensor) -> Tensor:
         x = self._resnet(m["r0"], x)
@@ -237,14 +244,15 @@ class AutoencoderKLB200:
         B, _, H, W = x32.shape
         ch = c.block_out_channels
         cols = ops.im2col_first(x32, self.kin_e)
-        h = ops.gemm(cols, self.e_in[0], bias=self.e_in[1]).view(B, H, W, ch[0])
+        sd = self.stream_dtype
+        h = ops.gemm(cols, self.e_in[0], bias=self.e_in[1], out_dtype=sd).view(B, H, W, ch[0])
         del cols
         for blk in self.e_down:
             for r in blk["res"]:
                 h = self._resnet(r, h)
             if blk["ds"] is not None:
                 H, W = H // 2, W // 2
-                h = ops.gemm(h, blk["ds"][0], bias=blk["ds"][1], conv=True, stride=2, pad_mode=1).view(B, H, W, h.shape[3])
+                h = ops.gemm(h, blk["ds"][0], bias=blk["ds"][1], conv=True, stride=2, pad_mode=1, out_dtype=sd).view(B, H, W, h.shape[3])
         h = self._mid(self.e_mid, h)
         h = ops.groupnorm(h, self.e_nout[0], self.e_nout[1], c.norm_num_groups, c.norm_eps, True)
         o = ops.gemm(h, self.e_out[0], bias=self.e_out[1], n_store=2 * c.latent_channels, out_fp32=True, conv=True)
@@ -280,14 +288,15 @@ class AutoencoderKLB200:
             wq = self._pq_scaled[key]
         z = ops.channel_mix(z32, wq, self.post_quant[1])
         cols = ops.im2col_first(z, self.kin_d)
-        h = ops.gemm(cols, self.d_in[0], bias=self.d_in[1]).view(B, H, W, ch[-1])
+        sd = self.stream_dtype
+        h = ops.gemm(cols, self.d_in[0], bias=self.d_in[1], out_dtype=sd).view(B, H, W, ch[-1])
         h = self._mid(self.d_mid, h)
         for blk in self.d_up:
             for r in blk["res"]:
                 h = self._resnet(r, h)
             if blk["us"] is not None:
                 H, W = 2 * H, 2 * W
-                h = ops.gemm(ops.upsample2x(h), blk["us"][0], bias=blk["us"][1], conv=True).view(B, H, W, h.shape[3])
+                h = ops.gemm(ops.upsample2x(h), blk["us"][0], bias=blk["us"][1], conv=True, out_dtype=sd).view(B, H, W, h.shape[3])
         h = ops.groupnorm(h, self.d_nout[0], self.d_nout[1], c.norm_num_groups, c.norm_eps, True)
         o = torch.zeros((B * H * W, 4), device=z32.device, dtype=torch.float32)       # 16-byte row pitch; column 3 unused
         ops.gemm(h, self.d_out[0], bias=self.d_out[1], n_store=c.out_channels, out_fp32=True, conv=True, out=o)
