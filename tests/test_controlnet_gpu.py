@@ -151,12 +151,11 @@ def test_controlnet_sd15_full_forward():
     ref_down, ref_mid = co.controlnet_forward(params, x, t, ehs, cond, ocfg)
     down, mid = cn(x.cuda(), t.cuda(), encoder_hidden_states=ehs.cuda(), controlnet_cond=cond.cuda(), return_dict=False)
     assert [tuple(d.shape) for d in down] == [tuple(r.shape) for r in ref_down]
-    # The 1e-2 criterion of north_star is stated for the noise prediction; the residuals are intermediate tensors of
-    # the bf16 residual stream whose rounding error grows with depth (measured 3e-3 at 64x64 ... 1.03e-2 at 8x8), so the
-    # deepest ones get 1.5e-2 here and the criterion proper is checked on eps below.
+    # every residual within 1e-2 (with an all-bf16 residual stream the 8x8 ones measured 1.03e-2; the fp16 stream the UNet
+    # and ControlNet use brings them to ~6e-3)
     for i, (d, r) in enumerate(zip(down, ref_down)):
-        assert _rel(d, r) < (REL_L2_BF16 if i < 9 else 1.5e-2), i
-    assert _rel(mid, ref_mid) < 1.5e-2
+        assert _rel(d, r) < REL_L2_BF16, i
+    assert _rel(mid, ref_mid) < REL_L2_BF16
     # the criterion proper: eps of the LoRA UNet fed with these residuals vs the fp32 oracle pair
     from mri_diffusion_superresolution_b200.unet import UNet2DConditionB200, UNetConfig
     up = _round_bf16(uo.init_params(ocfg, seed=0))

@@ -147,6 +147,20 @@ def test_unet_sd15_full_forward():
                down_intrablock_additional_residuals=[f.cuda() for f in feats]).sample
     assert out.shape == (1, 4, 64, 64)
     assert _rel(out, ref) < REL_L2_BF16
+    # a low-amplitude latent (late steps): the hardest case of scripts/eps_error_sweep.py (1.14e-2 with a bf16 residual
+    # stream, 7.0e-3 with the fp16 stream); and the all-bf16 stream for comparison -- it must be the less accurate one
+    x2 = torch.randn(1, 4, 64, 64, generator=torch.Generator().manual_seed(5)) * 0.4
+    t2 = torch.tensor(499)
+    ref2 = uo.unet_forward(params, x2, t2, ehs, ocfg)
+    e16 = _rel(unet(x2.cuda(), t2.cuda(), encoder_hidden_states=ehs.cuda()).sample, ref2)
+    assert e16 < 0.8 * REL_L2_BF16
+    from mri_diffusion_superresolution_b200.unet import UNet2DConditionB200, UNetConfig
+    del unet
+    torch.cuda.empty_cache()
+    ub = UNet2DConditionB200(UNetConfig(**kw), stream_dtype=torch.bfloat16)
+    ub.load_state_dict(params)
+    eb = _rel(ub(x2.cuda(), t2.cuda(), encoder_hidden_states=ehs.cuda()).sample, ref2)
+    assert e16 < eb
 
 
 def test_sampler_loop_vs_oracle():
