@@ -317,3 +317,39 @@ def test_api_helpers_vs_reference_golden(golden_dir):
     np.testing.assert_allclose(out_a.cpu().numpy(), p["out_a"], rtol=1e-6, atol=1e-6)
     out_b = api.prepare_condition_image(torch.from_numpy(p["b"]).cuda(), target_size=(32, 32))
     np.testing.assert_array_equal(out_b.cpu().numpy(), p["out_b"])
+
+
+def test_sd15_full_50_step_loop_psnr():
+    """BASELINE configuration end to end on the real architecture: SD-1.5 UNet + LoRA r16 + T2I features, 50 Res-SRDiff steps,
+    one 64x64 latent, CUDA-graph replay, against the fp32 CPU oracle loop on identical injected noise.  north_star: the
+    final 50-step result within PSNR >= 40 dB of the reference; timestep bookkeeping bit-exact."""
+    from oracle import sched_oracle as so
+    from mri_diffusion_superresolution_b200.sampler import SliceSampler
+    from mri_diffusion_superresolution_b200.scheduler import ResShiftScheduler
+
+    kw = dict(lora_rank=16, lora_alpha=16.0)
+    uo, ocfg, params, unet = _make(kw)
+    N = 50
+    g = torch.Generator().manual_seed(31)
+    lr = torch.randn(1, 4, 64, 64, generator=g) * 0.8
+    ehs = torch.randn(1, 77, 768, generator=g)
+    feats = [torch.randn(1, c, 64 >> i, 64 >> i, generator=g) * 0.5 for i, c in enumerate((320, 640, 1280, 1280))]
+    noises = torch.randn(N + 1, 1, 4, 64, 64, generator=g)
+    ab = so.alphas_cumprod(so.make_betas())
+    ts = so.timesteps(N)
+    assert ts.tolist() == list(range(999, 0, -20))
+    torch.set_num_threads(os.cpu_count() or 8)
+    with torch.no_grad():
+        ref_lat, ref_eps, _, _ = so.res_srdiff_loop(
+            lambda x, t: uo.unet_forward(params, x, t, ehs, ocfg, down_intrablock_additional_residuals=feats), lr, ab, ts, list(noises))
+
+    class FixedFeatures:                       # stands in for Adapter_XL: the features are a function of the LR image only
+        def __call__(self, img):
+            return [f.cuda() for f in feats]
+
+    sampler = SliceSampler(unet, ResShiftScheduler(), FixedFeatures(), num_inference_steps=N, kind="res_srdiff")
+    assert sampler.timesteps_host == ts.tolist()
+    out = sampler.sample(lr.cuda(), ehs.cuda(), cond_image=torch.zeros(1, 1, 512, 512, device="cuda"), noises=noises.cuda())
+    psnr = _psnr(out, ref_lat)
+    print(f"50-step SD-1.5 loop: final-latent PSNR {psnr:.1f} dB, rel-L2 {_rel(out, ref_lat):.2e}")
+    assert psnr >= PSNR_MIN_DB
