@@ -71,6 +71,9 @@ int mrisr_advance_index(int* idx, void* stream);
 
 /* diffusers get_timestep_embedding(flip_sin_to_cos=True, downscale_freq_shift=0): t fp32[batch] -> bf16 [batch, dim] = [cos|sin]. */
 int mrisr_timestep_embedding(const float* t, void* out_bf16, int batch, int dim, void* stream);
+/* fp32 variant with both conventions of the reference: variant 0 = the diffusers one above; variant 1 = the MNIST notebook's
+ * SinusoidalPositionEmbeddings (notebooks/MNIST_Super_Resolution.ipynb:140-152): divisor half-1, [sin | cos]. */
+int mrisr_sinusoidal_embedding(const float* t, float* out, int batch, int dim, int variant, void* stream);
 
 /* GroupNorm (+ optional SiLU) over NHWC bf16 whose channels are the concat of x1 [B,HW,c1] (pixel stride ld1) and
  * optional x2 [B,HW,c2] (UNet skip concat, diffusers `torch.cat([h, skip], 1)`), writing dense bf16 [B,HW,c1+c2].

@@ -47,6 +47,7 @@ PROTOTYPES = {
     "mrisr_select_row": (_I, [_P, _P, _L, _P, _I, _P]),
     "mrisr_advance_index": (_I, [_P, _P]),
     "mrisr_timestep_embedding": (_I, [_P, _P, _I, _I, _P]),
+    "mrisr_sinusoidal_embedding": (_I, [_P, _P, _I, _I, _I, _P]),
     "mrisr_groupnorm_workspace_floats": (_L, [_I, _I]),
     "mrisr_groupnorm": (_I, [_P, _L, _I, _P, _L, _I, _I, _I, _I, _P, _P, _F, _I, _P, _P, _I, _P]),
     "mrisr_layernorm": (_I, [_P, _L, _P, _P, _F, _P, _L, _I, _I, _I, _P]),

@@ -425,6 +425,14 @@ int mrisr_timestep_embedding(const float* t, void* out, int batch, int dim, void
   return 0;
 }
 
+int mrisr_sinusoidal_embedding(const float* t, float* out, int batch, int dim, int variant, void* stream) {
+  MRISR_REQUIRE(t && out && batch > 0 && dim >= 4 && dim % 2 == 0 && (variant == 0 || variant == 1), "sinusoidal_embedding: bad argument");
+  const int n = batch * (dim / 2);
+  launch_k(mrisr::sinusoidal_embedding_kernel, dim3((n + 127) / 128), dim3(128), 0, as_stream(stream), t, out, batch, dim, variant);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int64_t mrisr_groupnorm_workspace_floats(int batch, int groups) {
   return static_cast<int64_t>(batch) * kGnMaxSlabs * groups * 2;
 }

@@ -193,6 +193,30 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, __nv_bflo
   out[(long long)b * dim + half + j] = __float2bfloat16(sinf(ang));
 }
 
+// fp32 sinusoidal position embedding, both conventions of the reference:
+//   variant 0: SD / diffusers  -- freq_j = exp(-ln(1e4) * j / half),       out = [cos | sin]
+//   variant 1: MNIST notebook  -- freq_j = exp(j * -(ln(1e4) / (half - 1))), out = [sin | cos]
+//              (SinusoidalPositionEmbeddings, notebooks/MNIST_Super_Resolution.ipynb:140-152; same fp32 op order)
+__global__ void sinusoidal_embedding_kernel(const float* __restrict__ t, float* __restrict__ out, int batch, int dim, int variant) {
+  grid_dep_launch();
+  grid_dep_wait();
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch * half) return;
+  const int b = i / half, j = i % half;
+  float freq;
+  if (variant == 1) {
+    const float c = __fdiv_rn(logf(10000.0f), static_cast<float>(half - 1));
+    freq = expf(static_cast<float>(j) * -c);
+  } else {
+    freq = expf(-9.210340371976184f * static_cast<float>(j) / static_cast<float>(half));
+  }
+  const float ang = __ldg(t + b) * freq;
+  const float sn = sinf(ang), cs = cosf(ang);
+  out[(long long)b * dim + j] = variant == 1 ? sn : cs;
+  out[(long long)b * dim + half + j] = variant == 1 ? cs : sn;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // GroupNorm over NHWC bf16, input = channel concat of up to two tensors ([B,HW,c1] ++ [B,HW,c2]).
 // Pass 1: per-(batch, slab, group) partial sums.  Pass 2: combine in fp64, normalise, optional SiLU, store bf16.

@@ -20,6 +20,8 @@ log_validation_nets.npz the same ``log_validation`` driven around the ORACLE UNe
                   VAE under this repo's ``log_validation``).
 eval_metrics.npz  ``MRIEvaluator.compute_nmse`` (src/eval/eval.py:39-51) and ``pad_or_center_crop``
                   (src/datasets/mri_datasets.py:162-188) executed from the reference sources on seeded inputs.
+mnist_toy.npz     the schedule, ``forward_pass`` and ``SinusoidalPositionEmbeddings`` cells of
+                  notebooks/MNIST_Super_Resolution.ipynb (:121-129, :140-152) executed on seeded inputs.
 adapter_xl_*.npz  ``Adapter_XL`` (src/adapters/modules.py:114-157) outputs for small channel configs,
                   with the module's own initialised weights stored alongside.
 """
@@ -245,6 +247,33 @@ def gen_eval():
     np.savez_compressed(os.path.join(OUT, "eval_metrics.npz"), **out)
 
 
+def gen_mnist():
+    """The two runnable cells of notebooks/MNIST_Super_Resolution.ipynb (schedule + forward_pass :121-129,
+    SinusoidalPositionEmbeddings :140-152) executed from the notebook JSON on seeded inputs."""
+    import json
+    import math
+    import torch.nn as nn
+
+    nb = json.load(open(os.path.join(REF, "notebooks", "MNIST_Super_Resolution.ipynb")))
+    cells = ["".join(c["source"]) for c in nb["cells"] if c["cell_type"] == "code"]
+    ns = {"torch": torch, "nn": nn, "math": math}
+    exec(next(c for c in cells if "def forward_pass" in c), ns)
+    exec(next(c for c in cells if "class SinusoidalPositionEmbeddings" in c), ns)
+    g = torch.Generator().manual_seed(9)
+    x0 = torch.rand(4, 1, 28, 28, generator=g) * 2 - 1
+    noise = torch.randn(4, 1, 28, 28, generator=g)
+    t_vec = torch.tensor([0, 17, 500, 999])
+    out = {"alphas_cumprod": ns["alphas_cumprod"].numpy(), "x0": x0.numpy(), "noise": noise.numpy(), "t_vec": t_vec.numpy(),
+           "fwd_scalar": ns["forward_pass"](x0, 321, noise).numpy(),
+           "fwd_vec": ns["forward_pass"](x0, t_vec.view(-1, 1, 1, 1), noise).numpy()}
+    emb = ns["SinusoidalPositionEmbeddings"](32)
+    t_emb = torch.tensor([0, 1, 17, 500, 999])
+    out["t_emb"] = t_emb.numpy()
+    out["emb32"] = emb(t_emb).numpy()
+    out["emb64"] = ns["SinusoidalPositionEmbeddings"](64)(t_emb.float()).numpy()
+    np.savez_compressed(os.path.join(OUT, "mnist_toy.npz"), **out)
+
+
 def gen_prepare_condition():
     from src.adapters.res_srdiff import prepare_condition_image
 
@@ -312,6 +341,7 @@ if __name__ == "__main__":
     gen_log_validation()
     gen_log_validation_nets()
     gen_eval()
+    gen_mnist()
     gen_prepare_condition()
     gen_adapter()
     for f in sorted(os.listdir(OUT)):

@@ -112,3 +112,23 @@ def test_volume_slicing_bit_exact(golden_dir):
         volume_to_slices(torch.zeros(4, 4, device="cuda"), 0, 1)
     with pytest.raises(ValueError):
         volume_to_slices(torch.zeros(4, 4, 4, device="cuda"), 1.0, 1.0)
+
+
+def test_mnist_toy_pieces_vs_reference_golden(golden_dir):
+    """The runnable cells of the MNIST notebook (forward_pass, SinusoidalPositionEmbeddings) on the GPU vs the notebook's
+    own output.  forward_pass is bit-exact; the embedding is fp32 sin / cos of arguments up to 999 rad, where one ulp of
+    the frequency moves the result by 6e-5: tolerance 2e-4 absolute."""
+    from mri_diffusion_superresolution_b200 import mnist
+
+    z = np.load(os.path.join(golden_dir, "mnist_toy.npz"))
+    x0, noise = torch.from_numpy(z["x0"]).cuda(), torch.from_numpy(z["noise"]).cuda()
+    np.testing.assert_array_equal(mnist.forward_pass(x0, 321, noise).cpu().numpy(), z["fwd_scalar"])
+    np.testing.assert_array_equal(mnist.forward_pass(x0, torch.from_numpy(z["t_vec"]), noise).cpu().numpy(), z["fwd_vec"])
+    t = torch.from_numpy(z["t_emb"]).cuda()
+    e32 = mnist.SinusoidalPositionEmbeddings(32)(t)
+    assert tuple(e32.shape) == (5, 32) and e32.dtype == torch.float32
+    np.testing.assert_allclose(e32.cpu().numpy(), z["emb32"], rtol=0, atol=2e-4)
+    np.testing.assert_allclose(mnist.SinusoidalPositionEmbeddings(64)(t.float()).cpu().numpy(), z["emb64"], rtol=0, atol=2e-4)
+    np.testing.assert_array_equal(e32[0].cpu().numpy(), np.r_[np.zeros(16), np.ones(16)].astype(np.float32))   # [sin | cos] at t = 0
+    with pytest.raises(RuntimeError):
+        mnist.forward_pass(x0.cpu(), 3, noise.cpu())
