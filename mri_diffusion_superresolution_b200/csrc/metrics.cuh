@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(kMetThreads) metrics_tile_kernel(const Metrics
   grid_dep_wait();
   __shared__ float sp[kMetExt][kMetExt + 1];
   __shared__ float st[kMetExt][kMetExt + 1];
-  __shared__ float buf[5 * 42 * 32];   // phase A: 5 x [42][32] row-filtered SSIM moments; phase B: LoG intermediates
+  __shared__ float buf[5 * 42 * 33];   // phase A: 5 x [42][33] row-filtered SSIM moments (pitch 33: conflict-free); phase B: LoG intermediates
   __shared__ float red[kMetSums][kMetThreads / 32];
   const int tid = threadIdx.x;
   const int x0 = blockIdx.x * kMetTile, y0 = blockIdx.y * kMetTile, n = blockIdx.z;
@@ -101,12 +101,12 @@ __global__ void __launch_bounds__(kMetThreads) metrics_tile_kernel(const Metrics
         a3 = fmaf(wt, t, a3);
         a4 = fmaf(wp, t, a4);
       }
-      const int o = rr * 32 + seg * 8 + j;
-      buf[0 * 1344 + o] = a0;
-      buf[1 * 1344 + o] = a1;
-      buf[2 * 1344 + o] = a2;
-      buf[3 * 1344 + o] = a3;
-      buf[4 * 1344 + o] = a4;
+      const int o = rr * 33 + seg * 8 + j;
+      buf[0 * 1386 + o] = a0;
+      buf[1 * 1386 + o] = a1;
+      buf[2 * 1386 + o] = a2;
+      buf[3 * 1386 + o] = a3;
+      buf[4 * 1386 + o] = a4;
     }
   }
   __syncthreads();
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kMetThreads) metrics_tile_kernel(const Metrics
     for (int q = 0; q < 5; ++q) {
       float col[14];
 #pragma unroll
-      for (int k = 0; k < 14; ++k) col[k] = buf[q * 1344 + (ly0 + k) * 32 + lx];
+      for (int k = 0; k < 14; ++k) col[k] = buf[q * 1386 + (ly0 + k) * 33 + lx];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float acc = 0.f;
@@ -146,34 +146,88 @@ __global__ void __launch_bounds__(kMetThreads) metrics_tile_kernel(const Metrics
   float* ht = buf + kMetExt * 34;         // [46][34]
   float* gd = buf + 2 * kMetExt * 34;     // [34][34]
   float* gt = gd + 34 * 34;               // [34][34]
-  for (int i = tid; i < kMetExt * 34; i += kMetThreads) {
-    const int r = i / 34, cc = i - r * 34;
-    const int ec = min(max(x0 - 1 + cc, 0), W - 1) - (x0 - kMetHalo);
-    float ad = 0.f, at = 0.f;
+  // Tiles whose 34 x 34 Gaussian outputs all lie inside the image need no centre clamping: register-tiled sliding windows
+  // (7 columns per thread in the row pass, 5 rows per thread in the column pass: 5x fewer shared-memory loads).
+  const bool interior = x0 >= 1 && y0 >= 1 && x0 + 32 <= W - 1 && y0 + 32 <= H - 1;
+  if (interior) {
+    if (tid < kMetExt * 5) {
+      const int r = tid / 5, seg = tid - r * 5, c0 = seg * 7;        // centres cc = c0 .. c0+6 (cc < 34), ext col = cc + 6
+      float dv[19], tv[19];
 #pragma unroll
-    for (int k = 0; k < 13; ++k) {
-      const float t = st[r][ec + k - 6], w = P.hw[k];
-      ad = fmaf(w, sp[r][ec + k - 6] - t, ad);
-      at = fmaf(w, t, at);
-    }
-    hd[i] = ad;
-    ht[i] = at;
-  }
-  __syncthreads();
-  for (int i = tid; i < 34 * 34; i += kMetThreads) {
-    const int rr = i / 34, cc = i - rr * 34;
-    const int er = min(max(y0 - 1 + rr, 0), H - 1) - (y0 - kMetHalo);
-    float ad = 0.f, at = 0.f;
+      for (int k = 0; k < 19; ++k) {
+        const int c = min(c0 + k, kMetExt - 1);
+        tv[k] = st[r][c];
+        dv[k] = sp[r][c] - tv[k];
+      }
 #pragma unroll
-    for (int k = 0; k < 13; ++k) {
-      const float w = P.hw[k];
-      ad = fmaf(w, hd[(er + k - 6) * 34 + cc], ad);
-      at = fmaf(w, ht[(er + k - 6) * 34 + cc], at);
+      for (int j = 0; j < 7; ++j) {
+        if (c0 + j < 34) {
+          float ad = 0.f, at = 0.f;
+#pragma unroll
+          for (int k = 0; k < 13; ++k) {
+            ad = fmaf(P.hw[k], dv[j + k], ad);
+            at = fmaf(P.hw[k], tv[j + k], at);
+          }
+          hd[r * 34 + c0 + j] = ad;
+          ht[r * 34 + c0 + j] = at;
+        }
+      }
     }
-    gd[i] = ad;
-    gt[i] = at;
+    __syncthreads();
+    if (tid < 34 * 7) {
+      const int cc = tid % 34, r0 = (tid / 34) * 5;                   // centres rr = r0 .. r0+4 (rr < 34), ext row = rr + 6
+      float dv[17], tv[17];
+#pragma unroll
+      for (int k = 0; k < 17; ++k) {
+        const int r = min(r0 + k, kMetExt - 1);
+        dv[k] = hd[r * 34 + cc];
+        tv[k] = ht[r * 34 + cc];
+      }
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        if (r0 + j < 34) {
+          float ad = 0.f, at = 0.f;
+#pragma unroll
+          for (int k = 0; k < 13; ++k) {
+            ad = fmaf(P.hw[k], dv[j + k], ad);
+            at = fmaf(P.hw[k], tv[j + k], at);
+          }
+          gd[(r0 + j) * 34 + cc] = ad;
+          gt[(r0 + j) * 34 + cc] = at;
+        }
+      }
+    }
+    __syncthreads();
+  } else {
+    for (int i = tid; i < kMetExt * 34; i += kMetThreads) {
+      const int r = i / 34, cc = i - r * 34;
+      const int ec = min(max(x0 - 1 + cc, 0), W - 1) - (x0 - kMetHalo);
+      float ad = 0.f, at = 0.f;
+  #pragma unroll
+      for (int k = 0; k < 13; ++k) {
+        const float t = st[r][ec + k - 6], w = P.hw[k];
+        ad = fmaf(w, sp[r][ec + k - 6] - t, ad);
+        at = fmaf(w, t, at);
+      }
+      hd[i] = ad;
+      ht[i] = at;
+    }
+    __syncthreads();
+    for (int i = tid; i < 34 * 34; i += kMetThreads) {
+      const int rr = i / 34, cc = i - rr * 34;
+      const int er = min(max(y0 - 1 + rr, 0), H - 1) - (y0 - kMetHalo);
+      float ad = 0.f, at = 0.f;
+  #pragma unroll
+      for (int k = 0; k < 13; ++k) {
+        const float w = P.hw[k];
+        ad = fmaf(w, hd[(er + k - 6) * 34 + cc], ad);
+        at = fmaf(w, ht[(er + k - 6) * 34 + cc], at);
+      }
+      gd[i] = ad;
+      gt[i] = at;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   for (int i = tid; i < kMetTile * kMetTile; i += kMetThreads) {
     const int ly = i >> 5, lx = i & 31, gy = y0 + ly, gx = x0 + lx;
     if (gy < H && gx < W) {
