@@ -32,7 +32,7 @@ GFLOP_ADAPTER = 164.96            # Adapter_XL(sk=True), once per slice
 GFLOP_CONTROLNET_STEP = 268.57    # SD-1.5 ControlNet (encoder + mid copy + 13 zero convs), per step
 GFLOP_SDPA_CN_FRACTION = 50.45 / 126.05   # softmax(QK^T)V of the ControlNet's 7 transformer blocks relative to the UNet's 16
 GFLOP_CONTROLNET_EMBED = 14.72    # its condition embedding 512^2 -> 64^2, once per slice
-GEMM_DRAM_BYTES_PER_LAUNCH_B32 = 28.186e9 / 258   # ncu, one batch-32 step (profiles/r1_launches_step_b32_v4.csv)
+GEMM_DRAM_BYTES_PER_LAUNCH_B32 = 28.140e9 / 258   # ncu, one batch-32 step (profiles/r1_launches_step_b32_v5.csv)
 
 
 def load_peaks():
@@ -401,7 +401,7 @@ def main():
         peak = peaks["bf16_sustained"]
         roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (implicit-GEMM conv3x3 + linear/1x1, all epilogues)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": GEMM_DRAM_BYTES_PER_LAUNCH_B32 * B / 32.0 if controlnet is None else None,
-                "traffic_source": "profiles/r1_launches_step_b32_v4.csv: dram__bytes_read.sum + dram__bytes_write.sum summed over "
+                "traffic_source": "profiles/r1_launches_step_b32_v5.csv: dram__bytes_read.sum + dram__bytes_write.sum summed over "
                                   "the 258 gemm_tcgen05_kernel launches of one batch-32 step / 258, scaled by batch/32",
                 "peak_source": f"{peaks['src']} bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches_per_unet_forward": len(prof), "avg_launch_ms": gemm_ms / max(1, len(prof)),
