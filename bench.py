@@ -175,9 +175,10 @@ def main():
     ap.add_argument("--cond", default="adapter", choices=["adapter", "controlnet"],
                     help="condition branch: T2I-Adapter features once per slice (BASELINE headline, default) or the "
                          "reference loop's own per-step ControlNet (res_srdiff.py:65-70)")
-    ap.add_argument("--with-vae", action="store_true",
-                    help="also time the whole image-to-image pipeline (VAE encode -> loop -> VAE decode -> uint8) from host "
-                         "slices to host images (SURVEY.md §8(f) rank 2); reported under \"pipeline\", the headline is unchanged")
+    ap.add_argument("--with-vae", action="store_true", help="(default at N=1; kept for compatibility)")
+    ap.add_argument("--no-vae", action="store_true",
+                    help="skip the extra whole-pipeline measurement (VAE encode -> loop -> VAE decode -> uint8, host slices to host "
+                         "images; SURVEY.md §8(f) rank 2) that is reported under \"pipeline\"; the headline numbers are unaffected")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -315,56 +316,59 @@ def main():
 
     # ---- optional: the whole image-to-image pipeline, host slices -> host uint8 images (VAE either side of the loop)
     pipeline = None
-    if args.with_vae:
-        from mri_diffusion_superresolution_b200.synthetic import init_vae_params
-        from mri_diffusion_superresolution_b200.vae import AutoencoderKLB200
-        vae = AutoencoderKLB200(device=dev)
-        vparams = init_vae_params(None, seed=5, device=dev)
-        vae.load_state_dict(vparams)
-        del vparams
-        sf = vae.config.scaling_factor
-        h_sl = slices.cpu().pin_memory()
-        h_img = torch.empty((B, 512, 512, 3), dtype=torch.uint8).pin_memory()
-        gen2 = torch.Generator(device=dev).manual_seed(199 + rank)
+    if (args.with_vae or world == 1) and not args.no_vae:
+        try:
+            from mri_diffusion_superresolution_b200.synthetic import init_vae_params
+            from mri_diffusion_superresolution_b200.vae import AutoencoderKLB200
+            vae = AutoencoderKLB200(device=dev)
+            vparams = init_vae_params(None, seed=5, device=dev)
+            vae.load_state_dict(vparams)
+            del vparams
+            sf = vae.config.scaling_factor
+            h_sl = slices.cpu().pin_memory()
+            h_img = torch.empty((B, 512, 512, 3), dtype=torch.uint8).pin_memory()
+            gen2 = torch.Generator(device=dev).manual_seed(199 + rank)
 
-        def step_full(timing=None):
-            evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-            d_sl = h_sl.to(dev, non_blocking=True)
-            evs[0].record()
-            lat = vae.encode(d_sl.expand(-1, 3, -1, -1)).latent_dist.sample(generator=gen2, scale=sf)   # res_srdiff.py:49-50
-            evs[1].record()
-            o = sampler.sample(lat, ehs, cond_image=d_sl, generator=gen2)
-            evs[2].record()
-            img = vae.decode(o, latent_scale=1.0 / sf).sample                                        # res_srdiff.py:110
-            for b in range(B):
-                h_img[b].copy_(ops.to_uint8_vis(img[b].contiguous()), non_blocking=True)                # res_srdiff.py:115-122
-            evs[3].record()
-            torch.cuda.current_stream().synchronize()
-            if timing is not None:
-                timing.append([evs[i].elapsed_time(evs[i + 1]) for i in range(3)])
-            return int(h_img[0, 0, 0, 0])
+            def step_full(timing=None):
+                evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                d_sl = h_sl.to(dev, non_blocking=True)
+                evs[0].record()
+                lat = vae.encode(d_sl.expand(-1, 3, -1, -1)).latent_dist.sample(generator=gen2, scale=sf)   # res_srdiff.py:49-50
+                evs[1].record()
+                o = sampler.sample(lat, ehs, cond_image=d_sl, generator=gen2)
+                evs[2].record()
+                img = vae.decode(o, latent_scale=1.0 / sf).sample                                        # res_srdiff.py:110
+                for b in range(B):
+                    h_img[b].copy_(ops.to_uint8_vis(img[b].contiguous()), non_blocking=True)                # res_srdiff.py:115-122
+                evs[3].record()
+                torch.cuda.current_stream().synchronize()
+                if timing is not None:
+                    timing.append([evs[i].elapsed_time(evs[i + 1]) for i in range(3)])
+                return int(h_img[0, 0, 0, 0])
 
-        step_full()
-        barrier()
-        tm = []
-        w0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_full(tm)
-        barrier()
-        w = time.perf_counter() - w0
-        tw = torch.tensor([w], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
-        enc_ms = statistics.median(t[0] for t in tm)
-        dec_ms = statistics.median(t[2] for t in tm)
-        pipeline = {"value": world * B * args.steps / float(tw.item()), "unit": UNIT,
-                    "what": "host slices -> VAE encode (posterior sample) -> 50-step loop -> VAE decode -> uint8 -> host images",
-                    "h2d_bytes_per_step": int(h_sl.numel() * 4), "d2h_bytes_per_step": int(h_img.numel()),
-                    "vae_encode_ms": enc_ms, "vae_decode_ms": dec_ms, "loop_ms": statistics.median(t[1] for t in tm),
-                    "vae_encode_tflops": B * 1.1167 / (enc_ms / 1e3), "vae_decode_tflops": B * 2.5145 / (dec_ms / 1e3),
-                    "vae_algorithmic_tflop_per_slice": {"encode": 1.1167, "decode": 2.5145}}
-        del vae
-        torch.cuda.empty_cache()
+            step_full()
+            barrier()
+            tm = []
+            w0 = time.perf_counter()
+            for _ in range(args.steps):
+                step_full(tm)
+            barrier()
+            w = time.perf_counter() - w0
+            tw = torch.tensor([w], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+            enc_ms = statistics.median(t[0] for t in tm)
+            dec_ms = statistics.median(t[2] for t in tm)
+            pipeline = {"value": world * B * args.steps / float(tw.item()), "unit": UNIT,
+                        "what": "host slices -> VAE encode (posterior sample) -> 50-step loop -> VAE decode -> uint8 -> host images",
+                        "h2d_bytes_per_step": int(h_sl.numel() * 4), "d2h_bytes_per_step": int(h_img.numel()),
+                        "vae_encode_ms": enc_ms, "vae_decode_ms": dec_ms, "loop_ms": statistics.median(t[1] for t in tm),
+                        "vae_encode_tflops": B * 1.1167 / (enc_ms / 1e3), "vae_decode_tflops": B * 2.5145 / (dec_ms / 1e3),
+                        "vae_algorithmic_tflop_per_slice": {"encode": 1.1167, "decode": 2.5145}}
+            del vae
+            torch.cuda.empty_cache()
+        except Exception as exc:   # the extra measurement must never take the headline line down with it
+            pipeline = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     # ---- roofline of the dominant kernel (gemm_tcgen05_kernel: every conv / linear): CUDA events around each launch
     roof = None

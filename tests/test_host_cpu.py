@@ -173,3 +173,33 @@ def test_slice_sharding_two_ranks_gloo(n_slices):
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res)
     assert res[0][2][0] == 0 and res[1][2][1] == n_slices and res[0][2][1] == res[1][2][0]
+
+
+def test_no_cpu_path_widened_rows():
+    """ControlNet / VAE / metrics / slicing / MNIST pieces: the product refuses CPU tensors and bad arguments loudly."""
+    from mri_diffusion_superresolution_b200 import mnist
+    from mri_diffusion_superresolution_b200.controlnet import ControlNetB200
+    from mri_diffusion_superresolution_b200.evalmetrics import MRIEvaluator, image_metrics
+    from mri_diffusion_superresolution_b200.slices import volume_to_slices
+    from mri_diffusion_superresolution_b200.unet import UNet2DConditionB200, UNetConfig
+    from mri_diffusion_superresolution_b200.vae import AutoencoderKLB200, VAEConfig
+
+    with pytest.raises(RuntimeError):
+        image_metrics(torch.zeros(1, 1, 16, 16), torch.zeros(1, 1, 16, 16))
+    with pytest.raises(RuntimeError):
+        MRIEvaluator(device="cpu")
+    with pytest.raises(RuntimeError):
+        volume_to_slices(torch.zeros(4, 4, 4), 0.0, 1.0)
+    with pytest.raises(RuntimeError):
+        mnist.forward_pass(torch.zeros(1, 1, 28, 28), 3, torch.zeros(1, 1, 28, 28))
+    vae = AutoencoderKLB200(VAEConfig(block_out_channels=(64, 128), layers_per_block=1), device="cpu")
+    with pytest.raises(RuntimeError):
+        vae.decode(torch.zeros(1, 4, 8, 8))                       # weights not loaded
+    with pytest.raises(ValueError):
+        AutoencoderKLB200(VAEConfig(block_out_channels=(48, 96)), device="cpu")
+    with pytest.raises(ValueError):
+        UNet2DConditionB200(UNetConfig(), device="cpu", stream_dtype=torch.float32)
+    cn = ControlNetB200(UNetConfig(), device="cpu")
+    with pytest.raises(RuntimeError):
+        cn(torch.zeros(1, 4, 64, 64), 10, encoder_hidden_states=torch.zeros(1, 77, 768), controlnet_cond=torch.zeros(1, 3, 512, 512))
+    assert cn.config.conditioning_embedding_out_channels == (16, 32, 96, 256) and cn.stream_dtype == torch.float16
