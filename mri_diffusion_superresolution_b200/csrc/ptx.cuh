@@ -241,9 +241,10 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// saturating: a stream value beyond the half range clamps to +-65504 instead of turning into inf (and NaN downstream)
 __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
   uint32_t r;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
 // two packed 16-bit floats -> fp32 pair; h selects IEEE half (the fp16 residual stream) over bfloat16

@@ -437,3 +437,13 @@ def test_norms_add_upsample_read_fp16(ops):
     nchw = ops.nhwc_to_nchw(a, torch.float32)
     assert torch.equal(nchw, a.float().permute(0, 3, 1, 2))
     assert torch.equal(ops.cast(a, torch.float32), a.float()) and torch.equal(ops.cast(a.float(), torch.float16), a)
+
+
+def test_fp16_stream_saturates_instead_of_overflowing(ops):
+    """Values beyond the IEEE-half range clamp to +-65504 when the stream is stored (no inf / NaN downstream)."""
+    a = torch.full((128, 64), 200.0, dtype=torch.bfloat16, device="cuda")
+    w = torch.full((64, 64), 8.0, dtype=torch.bfloat16, device="cuda")            # 64 * 200 * 8 = 102400 > 65504
+    out = ops.gemm(a, w, out_dtype=torch.float16)
+    assert torch.isfinite(out).all() and float(out.max()) == 65504.0
+    out = ops.gemm(a, -w, res1=torch.zeros(128, 64, dtype=torch.float16, device="cuda"), out_dtype=torch.float16)
+    assert torch.isfinite(out).all() and float(out.min()) == -65504.0
