@@ -189,6 +189,7 @@ int mrisr_gaussian_sample(const float* moments, const float* noise, float* out, 
  * workspace: mrisr_eval_metrics_workspace_floats(N, H, W) floats.  Deterministic (no atomics). */
 int64_t mrisr_eval_metrics_workspace_floats(int N, int H, int W);
 int mrisr_eval_metrics(const float* pred, const float* target, int N, int H, int W, float data_range, float sigma,
+                       int from_pm1 /* inputs in [-1, 1]: (x / 2 + 0.5).clamp(0, 1) is applied on load (res_srdiff.py:115) */,
                        float* workspace, float* out, float* sums, void* stream);
 /* [H, W, D] volume (D innermost) -> [D, TH, TW] axial slices, centre-cropped / padded with pad_value to TH x TW
  * (pad_or_center_crop); map_intensity != 0 applies clip((v - a_min) / (a_max - a_min), 0, 1) * 2 - 1 on the way. */

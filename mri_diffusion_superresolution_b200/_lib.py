@@ -68,7 +68,7 @@ PROTOTYPES = {
     "mrisr_channel_mix": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "mrisr_gaussian_sample": (_I, [_P, _P, _P, _I, _I, _I, _F, _P]),
     "mrisr_eval_metrics_workspace_floats": (_L, [_I, _I, _I]),
-    "mrisr_eval_metrics": (_I, [_P, _P, _I, _I, _I, _F, _F, _P, _P, _P, _P]),
+    "mrisr_eval_metrics": (_I, [_P, _P, _I, _I, _I, _F, _F, _I, _P, _P, _P, _P]),
     "mrisr_slice_volume": (_I, [_P, _I, _I, _I, _I, _F, _F, _F, _P, _I, _I, _P]),
 }
 

@@ -37,6 +37,7 @@ struct MetricsParams {
   float gw[11];     // SSIM window (sums to 1)
   float hw[13];     // LoG Gaussian taps, zero-padded symmetrically when the radius is < 6
   float c1, c2;     // (k1 R)^2, (k2 R)^2
+  int from_pm1;     // inputs are [-1, 1] images: map them with (x / 2 + 0.5).clamp(0, 1) on load (res_srdiff.py:115)
 };
 
 __global__ void __launch_bounds__(kMetThreads) metrics_tile_kernel(const MetricsParams P) {
@@ -54,8 +55,13 @@ __global__ void __launch_bounds__(kMetThreads) metrics_tile_kernel(const Metrics
   for (int i = tid; i < kMetExt * kMetExt; i += kMetThreads) {
     const int r = i / kMetExt, c = i - r * kMetExt;
     const int gy = min(max(y0 - kMetHalo + r, 0), H - 1), gx = min(max(x0 - kMetHalo + c, 0), W - 1);
-    sp[r][c] = __ldg(pi + gy * W + gx);
-    st[r][c] = __ldg(ti + gy * W + gx);
+    float pv = __ldg(pi + gy * W + gx), tv = __ldg(ti + gy * W + gx);
+    if (P.from_pm1) {
+      pv = fminf(fmaxf(fmaf(pv, 0.5f, 0.5f), 0.f), 1.f);
+      tv = fminf(fmaxf(fmaf(tv, 0.5f, 0.5f), 0.f), 1.f);
+    }
+    sp[r][c] = pv;
+    st[r][c] = tv;
   }
   __syncthreads();
   float s[kMetSums];

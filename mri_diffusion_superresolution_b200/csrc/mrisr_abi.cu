@@ -900,7 +900,7 @@ int64_t mrisr_eval_metrics_workspace_floats(int N, int H, int W) {
   return static_cast<int64_t>(N) * tiles * mrisr::kMetSums + static_cast<int64_t>(N) * mrisr::kMetSums * 2 + 2;   // partials + fp64 sums
 }
 
-int mrisr_eval_metrics(const float* pred, const float* target, int N, int H, int W, float data_range, float sigma,
+int mrisr_eval_metrics(const float* pred, const float* target, int N, int H, int W, float data_range, float sigma, int from_pm1,
                        float* workspace, float* out, float* sums, void* stream) {
   MRISR_REQUIRE(pred && target && workspace && out && sums, "eval_metrics: null pointer");
   MRISR_REQUIRE(N > 0 && N <= 65535 && H >= 11 && W >= 11, "eval_metrics: need 1 <= N <= 65535 and H, W >= 11 (the SSIM window)");
@@ -921,6 +921,7 @@ int mrisr_eval_metrics(const float* pred, const float* target, int N, int H, int
     for (int k = 0; k < 13; ++k) { const int x = k - 6; h[k] = std::abs(x) <= radius ? std::exp(-0.5 * x * x / (static_cast<double>(sigma) * sigma)) : 0.0; hs += h[k]; }
     for (int k = 0; k < 13; ++k) P.hw[k] = static_cast<float>(h[k] / hs);
   }
+  P.from_pm1 = from_pm1 ? 1 : 0;
   P.c1 = (0.01f * data_range) * (0.01f * data_range);
   P.c2 = (0.03f * data_range) * (0.03f * data_range);
   cudaStream_t st = as_stream(stream);

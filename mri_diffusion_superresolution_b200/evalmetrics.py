@@ -38,9 +38,12 @@ def _as_batch(x: Tensor, name: str) -> Tensor:
     return x.contiguous()
 
 
-def image_metrics(pred: Tensor, target: Tensor, data_range: float = 1.0, sigma: float = 1.5) -> Tuple[Tensor, Tensor, Tensor]:
+def image_metrics(pred: Tensor, target: Tensor, data_range: float = 1.0, sigma: float = 1.5,
+                  from_pm1: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
     """-> (per_image fp32 [N, 4] = PSNR, SSIM, NMSE, HFEN with ``MRIEvaluator`` semantics; batch fp32 [4] = PSNR, SSIM,
-    NMSE, HFEN with the notebook's ``compute_mri_metrics`` semantics; sums fp32 [N, 8]).  All on the device, no sync."""
+    NMSE, HFEN with the notebook's ``compute_mri_metrics`` semantics; sums fp32 [N, 8]).  All on the device, no sync.
+    ``from_pm1``: the inputs are [-1, 1] images (network space) and are mapped with ``(x / 2 + 0.5).clamp(0, 1)``
+    (res_srdiff.py:115) as they are loaded."""
     lib = _lib.load()
     p, t = _as_batch(pred, "pred"), _as_batch(target, "target")
     if p.shape != t.shape:
@@ -49,7 +52,7 @@ def image_metrics(pred: Tensor, target: Tensor, data_range: float = 1.0, sigma: 
     ws = torch.empty((lib.mrisr_eval_metrics_workspace_floats(N, H, W),), device=p.device, dtype=torch.float32)
     out = torch.empty((N * 4 + 4,), device=p.device, dtype=torch.float32)
     sums = torch.empty((N, 8), device=p.device, dtype=torch.float32)
-    _lib.check(lib.mrisr_eval_metrics(p.data_ptr(), t.data_ptr(), N, H, W, float(data_range), float(sigma), ws.data_ptr(),
+    _lib.check(lib.mrisr_eval_metrics(p.data_ptr(), t.data_ptr(), N, H, W, float(data_range), float(sigma), int(from_pm1), ws.data_ptr(),
                                       out.data_ptr(), sums.data_ptr(), torch.cuda.current_stream(p.device).cuda_stream),
                "mrisr_eval_metrics", kernels=3)
     return out[:N * 4].view(N, 4), out[N * 4:], sums

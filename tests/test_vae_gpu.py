@@ -261,3 +261,63 @@ def test_full_dropin_log_validation_vs_reference_golden(golden_dir):
     np.testing.assert_array_equal(got[:, 1024:].astype(np.uint8), z["hr_panel"])
     gen, ref = got[:, 512:1024] / 255.0, z["gen_panel"].astype(np.float64) / 255.0
     assert 10 * np.log10(1.0 / max(((gen - ref) ** 2).mean(), 1e-30)) >= PSNR_MIN_DB
+
+
+def test_volume_pipeline_config5():
+    """BASELINE config 5 end to end at reduced width: raw LR volume -> slices -> VAE encode -> loop (ControlNet branch) -> VAE
+    decode -> per-slice metrics against the HR volume.  Checked against the same stages called one by one (bit-identical,
+    same generator), a ragged tail batch, and the CPU metric oracle on the mapped images."""
+    from oracle import controlnet_oracle as co
+    from oracle import eval_oracle as eo
+    from oracle import unet_oracle as uo
+    from oracle import vae_oracle as vo
+    from oracle.make_golden_stub import NETS_SEEDS, NETS_UNET_CFG, NETS_VAE_CFG, round_bf16
+    from mri_diffusion_superresolution_b200.controlnet import ControlNetB200
+    from mri_diffusion_superresolution_b200.pipeline import VolumePipeline
+    from mri_diffusion_superresolution_b200.sampler import SliceSampler
+    from mri_diffusion_superresolution_b200.scheduler import ResShiftScheduler
+    from mri_diffusion_superresolution_b200.slices import volume_to_slices
+    from mri_diffusion_superresolution_b200.unet import UNet2DConditionB200, UNetConfig
+    from mri_diffusion_superresolution_b200.vae import AutoencoderKLB200, VAEConfig
+
+    ucfg = uo.UNetConfig(**NETS_UNET_CFG)
+    unet = UNet2DConditionB200(UNetConfig(**NETS_UNET_CFG))
+    unet.load_state_dict(round_bf16(uo.init_params(ucfg, seed=NETS_SEEDS["unet"])))
+    cn = ControlNetB200(UNetConfig(**NETS_UNET_CFG))
+    cn.load_state_dict(round_bf16(co.init_params(ucfg, seed=NETS_SEEDS["controlnet"])))
+    vae = AutoencoderKLB200(VAEConfig(**NETS_VAE_CFG))
+    vae.load_state_dict(round_bf16(vo.init_params(vo.VAEConfig(**NETS_VAE_CFG), seed=NETS_SEEDS["vae"])))
+    N, D, batch = 3, 5, 4
+    sampler = SliceSampler(unet, ResShiftScheduler(), None, num_inference_steps=N, controlnet=cn)
+    pipe = VolumePipeline(sampler, vae, batch=batch)
+    g = torch.Generator().manual_seed(61)
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, 300), torch.linspace(-1, 1, 400), indexing="ij")
+    base = (torch.exp(-2 * (xx ** 2 + yy ** 2)) * 800)[..., None] * torch.linspace(0.6, 1.0, D)
+    hr_vol = (base + 20 * torch.randn(300, 400, D, generator=g)).clamp_min(0).cuda()
+    lr_vol = (base * 2.0 + 120 * torch.randn(300, 400, D, generator=g)).clamp_min(0).cuda()
+    ehs = torch.randn(1, 77, NETS_UNET_CFG["cross_attention_dim"], generator=g).cuda()
+    res = pipe.run(lr_vol, (0.0, 2000.0), ehs, hr_volume_hwd=hr_vol, hr_clip=(0.0, 900.0),
+                   generator=torch.Generator(device="cuda").manual_seed(5))
+    gen = res["generated"]
+    assert tuple(gen.shape) == (D, 1, 512, 512) and bool(torch.isfinite(gen).all())
+    assert torch.equal(res["lr_slices"], volume_to_slices(lr_vol, 0.0, 2000.0))
+    # stage-by-stage replay with the same generator: first batch of 4, then the padded tail batch
+    gg = torch.Generator(device="cuda").manual_seed(5)
+    sf = vae.config.scaling_factor
+    lr = res["lr_slices"]
+    manual = []
+    for sl in (lr[:4], torch.cat([lr[4:], lr[4:].expand(3, -1, -1, -1)], 0)):
+        sl = sl.contiguous()
+        lat = vae.encode(sl.expand(-1, 3, -1, -1)).latent_dist.sample(generator=gg, scale=sf)
+        lat = sampler.sample(lat, ehs, cond_image=sl, generator=gg)
+        manual.append(vae.decode(lat, latent_scale=1.0 / sf).sample[:, :1])
+    assert torch.equal(gen[:4], manual[0]) and torch.equal(gen[4:], manual[1][:1])
+    # metrics: the kernel's in-load (x / 2 + 0.5).clamp(0, 1) map + the four metrics vs the CPU oracle on slice 2
+    hr = volume_to_slices(hr_vol, 0.0, 900.0)
+    a = (gen[2, 0].cpu() / 2 + 0.5).clamp(0, 1).numpy()
+    b = (hr[2, 0].cpu() / 2 + 0.5).clamp(0, 1).numpy()
+    ref = eo.evaluator_metrics(a, b)
+    got = res["metrics"][2].cpu().tolist()
+    assert abs(got[0] - ref["PSNR"]) < 1e-3 and got[1] == pytest.approx(ref["SSIM"], rel=2e-4, abs=2e-6)
+    assert got[2] == pytest.approx(ref["NMSE"], rel=2e-4) and got[3] == pytest.approx(ref["HFEN"], rel=2e-4)
+    assert res["mean_metrics"][0] == pytest.approx(float(res["metrics"][:, 0].double().mean()), rel=1e-6)
