@@ -431,7 +431,9 @@ def main():
                            else "ControlNet (SD-1.5), every step",
                            "parallelism": f"slice-sharded x{world}, weights replicated, NCCL all_gather of final latents",
                            "l2": "working set (1.7 GB weights + GBs of activations per UNet forward) >> 126 MB L2; no flush needed",
-                           "cuda_graph": True},
+                           "cuda_graph": True,
+                           "numerics": "bf16 x bf16 -> fp32 MMAs; residual stream stored in fp16 (its 1x1 / stride-2 consumers run "
+                                       "f16 x f16 -> fp32); norms, softmax, scheduler in fp32"},
                 "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clk, "roofline": roof,
                 "whole_step": {"achieved_tflops_per_gpu": whole, "frac_of_sustained_peak": whole / peaks["bf16_sustained"],
                                "algorithmic_tflop_per_slice": (NI * gflop_step + gflop_once) / 1e3},
