@@ -97,8 +97,9 @@ int mrisr_layernorm(const void* x, int64_t ldx, const float* gamma, const float*
  * W: bf16 [N, taps*(k1+k2)] K-major, k index = tap*(k1+k2) + channel.  N % mrisr_gemm_block_n(N, act) == 0.
  * k1, k2 % 64 == 0.  bias fp32 [N] or NULL.  rowvec fp32: added before act, row m uses
  * rowvec[(m / rows_per_batch) * rowvec_stride + n] (time-embedding projection; NULL = none).
- * res1/res2: bf16 [M, *] row strides ldr1/ldr2, added after act (NULL = none).
- * out: bf16 (out_fp32 = 0) or fp32, row stride ldo; only columns < n_store are written (GEGLU: n_store <= N/2). */
+ * res1/res2: 16-bit [M, *] (bf16, or IEEE half when flagged in f16_flags) row strides ldr1/ldr2, added after act (NULL = none).
+ * out: bf16 / IEEE half (out_fp32 = 0; half when MRISR_F16_OUT, stored saturating) or fp32, row stride ldo; only columns
+ *      < n_store are written (GEGLU: n_store <= N/2).  A1 / A2 / W are bf16, or all three IEEE half with MRISR_F16_AB. */
 typedef struct mrisr_gemm_args {
   int32_t M, N, n_store;
   int32_t k1, k2, taps;
