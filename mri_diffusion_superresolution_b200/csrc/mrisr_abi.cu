@@ -453,6 +453,44 @@ int mrisr_groupnorm(const void* x1, int64_t ld1, int c1, const void* x2, int64_t
   int R = 256 / nvec;
   if (R < 1) R = 1;
   if (R > hw) R = hw;
+  // small levels: one CTA per (batch element, G whole groups), the slice staged in shared memory -- single pass, no barrier
+  static const bool no_small = getenv("MRISR_GN_NO_SMALL") != nullptr;
+  if (!no_small && hw <= 256) {
+    const int cpg = C / groups;
+    int G = 0;
+    for (int cand = groups; cand >= 1; cand >>= 1) {   // largest power-of-two divisor of `groups` whose slice fits
+      if (groups % cand) continue;
+      const long long cc = static_cast<long long>(cand) * cpg;
+      // the CTA's channel range must be whole 8-channel vectors and must not straddle the x1 | x2 boundary inside a vector
+      if (cc % 8 != 0 || (c1 % 8) != 0) continue;
+      const long long nvv = cc / 8;
+      if (nvv > 256) continue;
+      int Rr = static_cast<int>(256 / nvv); if (Rr > hw) Rr = hw; if (Rr < 1) Rr = 1;
+      const long long bytes = static_cast<long long>(hw) * cc * 2 + (2LL * Rr * cc + 2 * cc) * 4;
+      const long long ctas = static_cast<long long>(groups / cand) * batch;
+      if (bytes > 100 * 1024) continue;
+      G = cand;                                            // coarsest split that fits ...
+      if (ctas >= 2LL * sm_count()) break;                 // ... and fills the chip; otherwise keep refining
+    }
+    if (G > 0) {
+      const int cc = G * cpg, nvv = cc / 8;
+      int Rr = 256 / nvv; if (Rr > hw) Rr = hw; if (Rr < 1) Rr = 1;
+      const size_t smem_small = static_cast<size_t>(hw) * cc * 2 + (2 * static_cast<size_t>(Rr) * cc + 2 * cc) * 4;
+      static size_t configured_small = 0;
+      if (smem_small > 48 * 1024 && smem_small > configured_small) {
+        MRISR_CHECK_CUDA(cudaFuncSetAttribute(mrisr::groupnorm_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 + 4096));
+        configured_small = 100 * 1024 + 4096;
+      }
+      mrisr::GnArgs as;
+      as.x1 = static_cast<const __nv_bfloat16*>(x1); as.x2 = static_cast<const __nv_bfloat16*>(x2);
+      as.ld1 = ld1; as.ld2 = ld2; as.c1 = c1; as.c2 = c2; as.hw = hw; as.batch = batch; as.groups = groups;
+      as.h1 = f16_flags & 1; as.h2 = (f16_flags >> 1) & 1; as.nslab = 1; as.pix_per_slab = hw;
+      launch_k(mrisr::groupnorm_small_kernel, dim3(groups / G, batch), dim3(nvv, Rr), smem_small, as_stream(stream), as, G, gamma, beta, eps,
+               silu, static_cast<__nv_bfloat16*>(out));
+      MRISR_CHECK_CUDA(cudaGetLastError());
+      return 0;
+    }
+  }
   // single-launch path: needs every CTA of the grid co-resident (per-batch barrier between the two passes), so the slab
   // count comes from the occupancy calculator; MRISR_GN_TWO_PASS=1 forces the two-kernel path (A/B runs)
   static const bool no_fused = getenv("MRISR_GN_TWO_PASS") != nullptr;

@@ -421,6 +421,101 @@ __global__ void groupnorm_fused_kernel(GnArgs a, float2* partial, const float* _
   gn_apply_body<true>(a, partial, gamma, beta, eps, silu, out, a.nslab, gn_sh);
 }
 
+// Single-pass GroupNorm for the small levels (16x16, 8x8: a few hundred KB per image).  Groups are independent, so a CTA
+// owns batch element b and G whole groups (Cc = G * cpg channels): it stages its hw x Cc slice in shared memory while
+// accumulating the statistics, reduces them in a fixed order, and normalises out of shared memory -- one DRAM read, one
+// write, no second launch and no grid barrier (the two-phase kernel spends ~15 us of fixed latency on a 2.6 MB tensor).
+// Thread (tx, ry): tx indexes an 8-channel vector inside the CTA's channel range, ry strides pixels.
+__global__ void groupnorm_small_kernel(GnArgs a, int G, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                       int silu, __nv_bfloat16* __restrict__ out) {
+  grid_dep_launch();
+  grid_dep_wait();
+  extern __shared__ __align__(16) uint8_t gns_raw[];
+  const int C = a.c1 + a.c2, cpg = C / a.groups;
+  const int Cc = G * cpg, nv = Cc >> 3;
+  const int tx = threadIdx.x, ry = threadIdx.y, R = blockDim.y;
+  const int tid = ry * nv + tx, nthr = nv * R;
+  const int b = blockIdx.y, g0 = blockIdx.x * G, vx = (g0 * cpg >> 3) + tx;   // vector index in the concatenated row
+  uint4* s_data = reinterpret_cast<uint4*>(gns_raw);                           // [hw][nv]
+  float* s_red = reinterpret_cast<float*>(gns_raw + static_cast<size_t>(a.hw) * nv * 16);   // [2][R][Cc]
+  float* s_aff = s_red + 2 * R * Cc;                                           // scale[Cc], shift[Cc]
+  __shared__ float s_mean[64], s_rstd[64];
+  const bool hsrc = (vx < (a.c1 >> 3) ? a.h1 : a.h2) != 0;
+  float s[8], ss[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; ss[j] = 0.f; }
+  int pix = ry;
+  for (; pix + 3 * R < a.hw; pix += 4 * R) {   // 4 independent 16-byte loads in flight per thread
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = gn_load(a, b, pix + u * R, vx);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      s_data[(pix + u * R) * nv + tx] = v[u];
+      float f[8];
+      unpack8_any(v[u], f, hsrc);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
+    }
+  }
+  for (; pix < a.hw; pix += R) {
+    const uint4 v = gn_load(a, b, pix, vx);
+    s_data[pix * nv + tx] = v;
+    float f[8];
+    unpack8_any(v, f, hsrc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
+  }
+  float* sh_s = s_red + ry * Cc + tx * 8;
+  float* sh_q = s_red + R * Cc + ry * Cc + tx * 8;
+  *reinterpret_cast<float4*>(sh_s) = make_float4(s[0], s[1], s[2], s[3]);
+  *reinterpret_cast<float4*>(sh_s + 4) = make_float4(s[4], s[5], s[6], s[7]);
+  *reinterpret_cast<float4*>(sh_q) = make_float4(ss[0], ss[1], ss[2], ss[3]);
+  *reinterpret_cast<float4*>(sh_q + 4) = make_float4(ss[4], ss[5], ss[6], ss[7]);
+  __syncthreads();
+  if (tid < G) {   // fixed-order reduction: bit-reproducible
+    double su = 0.0, sq = 0.0;
+    for (int r = 0; r < R; ++r) {
+      const float* ps = s_red + r * Cc + tid * cpg;
+      const float* pq = s_red + R * Cc + r * Cc + tid * cpg;
+      float a0 = 0.f, a1 = 0.f;
+      for (int c = 0; c < cpg; ++c) { a0 += ps[c]; a1 += pq[c]; }
+      su += a0;
+      sq += a1;
+    }
+    const double n = static_cast<double>(a.hw) * cpg;
+    const double mean = su / n;
+    double var = sq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[tid] = static_cast<float>(mean);
+    s_rstd[tid] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+  __syncthreads();
+  for (int c = tid; c < Cc; c += nthr) {
+    const int g = c / cpg;
+    const float sc = s_rstd[g] * __ldg(gamma + g0 * cpg + c);
+    s_aff[c] = sc;
+    s_aff[Cc + c] = __ldg(beta + g0 * cpg + c) - s_mean[g] * sc;
+  }
+  __syncthreads();
+  float2 sc[4], sh[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sc[j] = make_float2(s_aff[tx * 8 + 2 * j], s_aff[tx * 8 + 2 * j + 1]);
+    sh[j] = make_float2(s_aff[Cc + tx * 8 + 2 * j], s_aff[Cc + tx * 8 + 2 * j + 1]);
+  }
+  for (pix = ry; pix < a.hw; pix += R) {   // every thread re-reads exactly the vectors it staged itself
+    float2 f[4];
+    unpack8p_any(s_data[pix * nv + tx], f, hsrc);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      f[j] = __ffma2_rn(f[j], sc[j], sh[j]);
+      if (silu) { f[j].x = silu_tanh(f[j].x); f[j].y = silu_tanh(f[j].y); }
+    }
+    reinterpret_cast<uint4*>(out + (static_cast<long long>(b) * a.hw + pix) * C)[vx] = pack8p(f);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // LayerNorm over the last dim of a bf16 [rows, C] matrix.  Persistent CTAs (grid ~ resident capacity), one warp per
 // row, kLnRows rows of a warp IN FLIGHT at once (all their 16-byte loads are issued before the first reduction: a

@@ -447,3 +447,26 @@ def test_fp16_stream_saturates_instead_of_overflowing(ops):
     assert torch.isfinite(out).all() and float(out.max()) == 65504.0
     out = ops.gemm(a, -w, res1=torch.zeros(128, 64, dtype=torch.float16, device="cuda"), out_dtype=torch.float16)
     assert torch.isfinite(out).all() and float(out.min()) == -65504.0
+
+
+@pytest.mark.parametrize("B,HW,C1,C2,h1,h2", [(32, 64, 1280, 0, True, False), (32, 64, 1280, 1280, True, True), (32, 256, 1280, 640, True, False),
+                                               (5, 256, 1280, 1280, False, True), (1, 64, 1280, 0, False, False), (3, 16, 128, 64, True, True),
+                                               (2, 256, 512, 0, True, False), (4, 64, 64, 0, False, False)])
+def test_groupnorm_small_single_pass(ops, B, HW, C1, C2, h1, h2):
+    """The single-pass GroupNorm of the 16x16 / 8x8 levels (one CTA per batch element and group subset, slice staged in shared
+    memory): concat sources, fp16 / bf16 mixes, batch sizes from 1 to a full machine; identical to the two-phase kernel's
+    result up to rounding, and bit-reproducible."""
+    import os
+    h = int(math.isqrt(HW))
+    g = torch.Generator().manual_seed(HW + C1 + C2)
+    mk = lambda c, half: (torch.randn(B, h, h, c, generator=g) * 1.5 + 0.3).to(torch.float16 if half else torch.bfloat16).cuda()
+    x1 = mk(C1, h1)
+    x2 = mk(C2, h2) if C2 else None
+    C = C1 + C2
+    gamma, beta = _f32((C,), 81) * 0.1 + 1, _f32((C,), 82) * 0.1
+    out = ops.groupnorm(x1, gamma, beta, 32, 1e-5, True, x2=x2)
+    xin = x1.float() if x2 is None else torch.cat([x1.float(), x2.float()], -1)
+    ref = F.silu(F.group_norm(xin.permute(0, 3, 1, 2), 32, gamma, beta, 1e-5)).permute(0, 2, 3, 1)
+    assert (out.float() - ref).abs().max().item() < 0.03
+    assert _rel(out, ref) < 4e-3
+    assert torch.equal(out, ops.groupnorm(x1, gamma, beta, 32, 1e-5, True, x2=x2))
