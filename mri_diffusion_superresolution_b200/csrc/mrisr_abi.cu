@@ -455,7 +455,9 @@ int mrisr_groupnorm(const void* x1, int64_t ld1, int c1, const void* x2, int64_t
   if (R > hw) R = hw;
   // small levels: one CTA per (batch element, G whole groups), the slice staged in shared memory -- single pass, no barrier
   static const bool no_small = getenv("MRISR_GN_NO_SMALL") != nullptr;
-  if (!no_small && hw <= 256) {
+  // measured (batch 32, CUDA-graph timing, scripts/gn_small_bench.py): 8x8 x 1280: 7.7 vs 12.8 us, 8x8 x 2560: 12.0 vs 14.5,
+  // 16x16 x 1280: 16.2 vs 18.2; wider 16x16 inputs (1920 / 2560 channels) are faster on the two-phase kernel
+  if (!no_small && (hw <= 64 || (hw <= 256 && C <= 1280))) {
     const int cpg = C / groups;
     int G = 0;
     for (int cand = groups; cand >= 1; cand >>= 1) {   // largest power-of-two divisor of `groups` whose slice fits
@@ -466,16 +468,17 @@ int mrisr_groupnorm(const void* x1, int64_t ld1, int c1, const void* x2, int64_t
       const long long nvv = cc / 8;
       if (nvv > 256) continue;
       int Rr = static_cast<int>(256 / nvv); if (Rr > hw) Rr = hw; if (Rr < 1) Rr = 1;
-      const long long bytes = static_cast<long long>(hw) * cc * 2 + (2LL * Rr * cc + 2 * cc) * 4;
+      const long long bytes = static_cast<long long>(hw) * cc * 2 + (2LL * Rr * cc + 2 * cc + 2LL * Rr * cand) * 4;
       const long long ctas = static_cast<long long>(groups / cand) * batch;
       if (bytes > 100 * 1024) continue;
       G = cand;                                            // coarsest split that fits ...
-      if (ctas >= 2LL * sm_count()) break;                 // ... and fills the chip; otherwise keep refining
+      static const int fill = getenv("MRISR_GN_SMALL_FILL") ? atoi(getenv("MRISR_GN_SMALL_FILL")) : 2;
+      if (ctas >= static_cast<long long>(fill) * sm_count()) break;   // ... and fills the chip; otherwise keep refining
     }
     if (G > 0) {
       const int cc = G * cpg, nvv = cc / 8;
       int Rr = 256 / nvv; if (Rr > hw) Rr = hw; if (Rr < 1) Rr = 1;
-      const size_t smem_small = static_cast<size_t>(hw) * cc * 2 + (2 * static_cast<size_t>(Rr) * cc + 2 * cc) * 4;
+      const size_t smem_small = static_cast<size_t>(hw) * cc * 2 + (2 * static_cast<size_t>(Rr) * cc + 2 * cc + 2 * static_cast<size_t>(Rr) * G) * 4;
       static size_t configured_small = 0;
       if (smem_small > 48 * 1024 && smem_small > configured_small) {
         MRISR_CHECK_CUDA(cudaFuncSetAttribute(mrisr::groupnorm_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024 + 4096));

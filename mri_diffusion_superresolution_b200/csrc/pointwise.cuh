@@ -473,16 +473,23 @@ __global__ void groupnorm_small_kernel(GnArgs a, int G, const float* __restrict_
   *reinterpret_cast<float4*>(sh_q) = make_float4(ss[0], ss[1], ss[2], ss[3]);
   *reinterpret_cast<float4*>(sh_q + 4) = make_float4(ss[4], ss[5], ss[6], ss[7]);
   __syncthreads();
-  if (tid < G) {   // fixed-order reduction: bit-reproducible
+  // fixed-order (bit-reproducible) reduction in two short steps: (pixel-row slot r, group g) partials over the group's
+  // channels by R * G threads, then one thread per group over the R slots -- a single thread per group walking R * cpg
+  // values serially cost more than the whole rest of the kernel
+  float* s_part = s_aff + 2 * Cc;                                              // [R * G][2]
+  for (int idx = tid; idx < R * G; idx += nthr) {
+    const int r = idx / G, g = idx - r * G;
+    const float* ps = s_red + r * Cc + g * cpg;
+    const float* pq = s_red + R * Cc + r * Cc + g * cpg;
+    float a0 = 0.f, a1 = 0.f;
+    for (int c = 0; c < cpg; ++c) { a0 += ps[c]; a1 += pq[c]; }
+    s_part[2 * idx] = a0;
+    s_part[2 * idx + 1] = a1;
+  }
+  __syncthreads();
+  if (tid < G) {
     double su = 0.0, sq = 0.0;
-    for (int r = 0; r < R; ++r) {
-      const float* ps = s_red + r * Cc + tid * cpg;
-      const float* pq = s_red + R * Cc + r * Cc + tid * cpg;
-      float a0 = 0.f, a1 = 0.f;
-      for (int c = 0; c < cpg; ++c) { a0 += ps[c]; a1 += pq[c]; }
-      su += a0;
-      sq += a1;
-    }
+    for (int r = 0; r < R; ++r) { su += s_part[2 * (r * G + tid)]; sq += s_part[2 * (r * G + tid) + 1]; }
     const double n = static_cast<double>(a.hw) * cpg;
     const double mean = su / n;
     double var = sq / n - mean * mean;
