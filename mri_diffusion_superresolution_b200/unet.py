@@ -343,8 +343,9 @@ class UNet2DConditionB200:
         B, H, W, _ = x1.shape
         M = B * H * W
         h = ops.groupnorm(x1, r.n1w, r.n1b, c.norm_num_groups, c.norm_eps, True, x2=x2)
+        # conv1's output is only ever read by norm2: stored in the stream's format too (3 more significand bits for free)
         h = ops.gemm(h, r.w1, bias=r.b1, rowvec=temb[:, r.temb_off:], rowvec_stride=temb_stride, rows_per_batch=H * W,
-                     conv=True)
+                     conv=True, out_dtype=self.stream_dtype)
         h = ops.groupnorm(h.view(B, H, W, r.cout), r.n2w, r.n2b, c.norm_num_groups, c.norm_eps, True)
         sd = self.stream_dtype
         if r.wsc is not None:

@@ -198,7 +198,7 @@ class AutoencoderKLB200:
         B, H, W, _ = x.shape
         M = B * H * W
         h = ops.groupnorm(x, r.n1[0], r.n1[1], c.norm_num_groups, c.norm_eps, True)
-        h = ops.gemm(h, r.w1, bias=r.b1, conv=True).view(B, H, W, r.cout)
+        h = ops.gemm(h, r.w1, bias=r.b1, conv=True, out_dtype=self.stream_dtype).view(B, H, W, r.cout)   # read by norm2 only
         h = ops.groupnorm(h, r.n2[0], r.n2[1], c.norm_num_groups, c.norm_eps, True)
         sd = self.stream_dtype
         sc = ops.gemm(x.view(M, r.cin), r.wsc, bias=r.bsc, out_dtype=sd) if r.wsc is not None else x.view(M, r.cin)
