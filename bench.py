@@ -121,7 +121,7 @@ def cpu_reference_sample(n_inf: int, threads: int, repeats: int = 1, cond: str =
     img = torch.rand(1, 3, 512, 512, generator=g) * 2 - 1
     with torch.no_grad():
         t0 = time.perf_counter()
-        feats = ao.adapter_forward(ap, img)
+        feats = ao.adapter_forward(ap, img) if cond == "adapter" else None
         t_ad = time.perf_counter() - t0
         uo.unet_forward(params, x, torch.tensor(999), ehs, cfg, down_intrablock_additional_residuals=feats)  # warm-up
         ts = []
@@ -172,9 +172,9 @@ def main():
     ap.add_argument("--inference-steps", type=int, default=50)
     ap.add_argument("--sched", default="res_srdiff", choices=["res_srdiff", "ddim", "ddpm"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cond", default="adapter", choices=["adapter", "controlnet"],
+    ap.add_argument("--cond", default="adapter", choices=["adapter", "controlnet", "none"],
                     help="condition branch: T2I-Adapter features once per slice (BASELINE headline, default) or the "
-                         "reference loop's own per-step ControlNet (res_srdiff.py:65-70)")
+                         "reference loop's own per-step ControlNet (res_srdiff.py:65-70), or none (BASELINE config 2: LoRA-only UNet)")
     ap.add_argument("--with-vae", action="store_true", help="(default at N=1; kept for compatibility)")
     ap.add_argument("--no-vae", action="store_true",
                     help="skip the extra whole-pipeline measurement (VAE encode -> loop -> VAE decode -> uint8, host slices to host "
@@ -219,7 +219,7 @@ def main():
     adapter = controlnet = None
     if args.cond == "adapter":
         adapter = Adapter_XL(sk=True, device=dev, generator=torch.Generator().manual_seed(2))
-    else:
+    elif args.cond == "controlnet":
         from mri_diffusion_superresolution_b200.controlnet import ControlNetB200
         from mri_diffusion_superresolution_b200.synthetic import init_controlnet_params
         ccfg = UNetConfig()
@@ -233,9 +233,9 @@ def main():
         sched = ResShiftScheduler(timestep_spacing="leading", steps_offset=1)
     sampler = SliceSampler(unet, sched, adapter, num_inference_steps=NI, kind=args.sched, controlnet=controlnet)
     gflop_step = GFLOP_UNET_STEP + (GFLOP_CONTROLNET_STEP if controlnet is not None else 0.0)
-    gflop_once = GFLOP_ADAPTER if adapter is not None else GFLOP_CONTROLNET_EMBED
+    gflop_once = GFLOP_ADAPTER if adapter is not None else (GFLOP_CONTROLNET_EMBED if controlnet is not None else 0.0)
     workload = ("sd15_unet_lora16_t2iadapter_512px_50step" if adapter is not None
-                else "sd15_unet_lora16_controlnet_512px_50step")
+                else "sd15_unet_lora16_controlnet_512px_50step" if controlnet is not None else "sd15_unet_lora16_512px_50step")
 
     # ---- synthetic inputs: axial slices of a phantom volume (each rank takes its own contiguous slice range)
     vol = phantom_volume(1234, device=dev)                                   # [128, 1, 512, 512] in [-1, 1]
@@ -381,6 +381,9 @@ def main():
 
             def one_step():
                 unet(x, None, down_intrablock_additional_residuals=feats, time_proj=tp)
+        elif controlnet is None:
+            def one_step():
+                unet(x, None, time_proj=tp)
         else:
             ctp = sampler.cn_time_table[0:1]
 
@@ -428,7 +431,7 @@ def main():
                 "config": {"workload": workload, "batch_per_gpu": B, "global_batch": B * world,
                            "inference_steps": NI, "scheduler": args.sched, "lora_rank": 16,
                            "condition_branch": "Adapter_XL(sk=True), once per slice" if adapter is not None
-                           else "ControlNet (SD-1.5), every step",
+                           else "ControlNet (SD-1.5), every step" if controlnet is not None else "none (LoRA-only UNet)",
                            "parallelism": f"slice-sharded x{world}, weights replicated, NCCL all_gather of final latents",
                            "l2": "working set (1.7 GB weights + GBs of activations per UNet forward) >> 126 MB L2; no flush needed",
                            "cuda_graph": True,
