@@ -12,7 +12,7 @@ SOURCES = ["mrisr_abi.cu"]
 DEPS = ["mrisr_abi.cu", "ptx.cuh", "gemm_tcgen05.cuh", "attention.cuh", "attention_tcgen05.cuh", "pointwise.cuh", "metrics.cuh",
         os.path.join("..", "..", "include", "mrisr_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-shared", "--cudart", "shared"]
 
 
 def needs_build() -> bool:

@@ -83,6 +83,7 @@ def load() -> C.CDLL:
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python -m mri_diffusion_superresolution_b200._build` "
                 "(or __graft_entry__.build()).  This package has no CPU or PyTorch fallback path.")
+        import torch  # noqa: F401  -- maps libcudart.so.12 (the library links the shared runtime) before the dlopen
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(lib, name)
