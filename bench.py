@@ -23,16 +23,20 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "MRI slices/sec (512^2, 50-step, LoRA+T2I-Adapter UNet)"
+METRICS = {"adapter": "MRI slices/sec (512^2, 50-step, LoRA+T2I-Adapter UNet)",
+           "controlnet": "MRI slices/sec (512^2, 50-step, LoRA UNet + per-step ControlNet)",
+           "none": "MRI slices/sec (512^2, 50-step, LoRA-only UNet)"}
 UNIT = "slices/s"
 # algorithmic work per slice (2*MAC)
 GFLOP_UNET_STEP = 807.83          # UNet forward + LoRA r=16, one 64x64 latent
 GFLOP_SDPA_STEP = 126.05          # of which softmax(QK^T)V (runs in the attention kernel, not the GEMM kernel)
+GFLOP_CONV3_STEP = 400.33         # of which 3x3 convolutions (resnets + up/down-samplers + conv_in/out)
+GFLOP_CONV3_CN_FRACTION = 0.3     # ControlNet's share of 3x3-conv work relative to the UNet's (encoder + mid copy), approximate
 GFLOP_ADAPTER = 164.96            # Adapter_XL(sk=True), once per slice
 GFLOP_CONTROLNET_STEP = 268.57    # SD-1.5 ControlNet (encoder + mid copy + 13 zero convs), per step
 GFLOP_SDPA_CN_FRACTION = 50.45 / 126.05   # softmax(QK^T)V of the ControlNet's 7 transformer blocks relative to the UNet's 16
 GFLOP_CONTROLNET_EMBED = 14.72    # its condition embedding 512^2 -> 64^2, once per slice
-GEMM_DRAM_BYTES_PER_LAUNCH_B32 = 28.140e9 / 258   # ncu, one batch-32 step (profiles/r1_launches_step_b32_v5.csv)
+TRAFFIC_JSON = os.path.join(ROOT, "profiles", "r2_traffic_b32.json")   # per-class DRAM bytes from THIS round's ncu launch list
 
 
 def load_peaks():
@@ -150,12 +154,14 @@ def run_reference(args):
     unit_once = "Adapter_XL pass" if args.cond == "adapter" else "ControlNet condition embedding"
     sample = (f"1 slice: 1 of {args.inference_steps} fp32 {unit_step} forwards ({t_unet:.2f} s) + 1 {unit_once} "
               f"({t_ad:.2f} s), extrapolated x{args.inference_steps}; oracle/ port of the diffusers path (diffusers not installable)")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": METRICS[args.cond], "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
             "config": {"workload": "sd15_unet_lora16_t2iadapter_512px_50step" if args.cond == "adapter"
-                       else "sd15_unet_lora16_controlnet_512px_50step", "batch_per_gpu": 1,
-                       "inference_steps": args.inference_steps, "scheduler": args.sched},
+                       else "sd15_unet_lora16_controlnet_512px_50step" if args.cond == "controlnet"
+                       else "sd15_unet_lora16_512px_50step", "batch_per_gpu": 1,
+                       "inference_steps": args.inference_steps, "scheduler": args.sched,
+                       "cpu_sample": f"extrapolated: 1 timed forward x{args.inference_steps} + 1 condition pass, batch 1, fp32"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t_all0}
@@ -180,6 +186,10 @@ def main():
                     help="skip the extra whole-pipeline measurement (VAE encode -> loop -> VAE decode -> uint8, host slices to host "
                          "images; SURVEY.md §8(f) rank 2) that is reported under \"pipeline\"; the headline numbers are unaffected")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gate", action="store_true",
+                    help="skip the step-0 parity gate against the CPU oracle (debugging only: a line printed without the gate "
+                         "carries \"parity_gate\": null and is not a reportable number)")
+    ap.add_argument("--profile-steps", type=int, default=20, help="eager steps timed per kernel class for the roofline list")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -214,6 +224,9 @@ def main():
     unet = UNet2DConditionB200(cfg, device=dev)
     params = init_unet_params(cfg, seed=0, device=dev)
     unet.load_state_dict(params)
+    gate_params = None
+    if rank == 0 and not args.no_gate:
+        gate_params = {k: v.cpu() for k, v in params.items()}    # fp32 host copy for the CPU oracle (parity gate below)
     del params
     torch.cuda.empty_cache()
     adapter = controlnet = None
@@ -257,6 +270,27 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
+
+    # ---- parity gate BEFORE any timing: one UNet(+LoRA, +adapter features) evaluation of the WHOLE batch
+    # at the first timestep, slices 0 / 13 / 31 against the fp32 CPU oracle run at batch 1 on the same weights and inputs.
+    # No line is printed if it fails.
+    gate = None
+    if gate_params is not None:
+        from oracle import parity_gate as pg
+        from oracle import unet_oracle as uo
+        t_gate0 = time.perf_counter()
+        res = pg.step0_gate(unet, gate_params, uo.UNetConfig(lora_rank=16, lora_alpha=16.0), noises[0].contiguous(), ehs,
+                            int(sampler.timesteps_host[0]), adapter=adapter, cond_images=slices if adapter is not None else None,
+                            slices=(0, 13, 31), check_features=True)
+        gate = {"tolerance_rel_l2": pg.REL_L2_BF16, "worst_eps_rel_l2": res["worst_eps"], "worst_rel_l2": res["worst"],
+                "slices": [0, min(13, B - 1), B - 1], "batch": B, "timestep": int(sampler.timesteps_host[0]),
+                "what": ("CUDA UNet+LoRA + Adapter_XL features" if adapter is not None else "CUDA UNet+LoRA (condition branch not gated)"
+                         if controlnet is not None else "CUDA UNet+LoRA") + " on the full batch vs oracle/ fp32 at batch 1",
+                "seconds": time.perf_counter() - t_gate0}
+        del gate_params
+        if not res["worst"] < pg.REL_L2_BF16:
+            raise SystemExit(f"bench: parity gate FAILED ({res}); refusing to time a path whose results differ from the oracle")
+    barrier()
 
     for _ in range(args.warmup):
         step_device()
@@ -370,50 +404,122 @@ def main():
         except Exception as exc:   # the extra measurement must never take the headline line down with it
             pipeline = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
-    # ---- roofline of the dominant kernel (gemm_tcgen05_kernel: every conv / linear): CUDA events around each launch
+    # ---- roofline, one entry per kernel class.  Every launch of `--profile-steps` eager denoising steps is bracketed by CUDA
+    # events on the launching stream (ops.PROFILE); per class the per-step sum is taken and the MEDIAN over the steps is
+    # reported, with the SM clock sampled during exactly that window.  achieved = ALGORITHMIC work of the class per step
+    # (SURVEY.md §8(d) figures x batch) / that time; peaks from MEASURED_PEAKS.json (sustained: the kernels run inside a
+    # long power-capped step).  Eager stepping with events between launches forgoes the PDL overlap the graph loop has,
+    # so these fractions are conservative.
     roof = None
     if rank == 0:
         sampler.unet.set_encoder_hidden_states(ehs)
-        tp = sampler.time_table[0:1]
-        x = noises[0].contiguous()
-        if adapter is not None:
-            feats = adapter(slices.expand(-1, 3, -1, -1).contiguous())
-
-            def one_step():
-                unet(x, None, down_intrablock_additional_residuals=feats, time_proj=tp)
-        elif controlnet is None:
-            def one_step():
-                unet(x, None, time_proj=tp)
-        else:
-            ctp = sampler.cn_time_table[0:1]
-
-            def one_step():
-                d_, m_ = controlnet(x, None, time_proj=ctp, return_dict=False)
-                unet(x, None, down_block_additional_residuals=d_, mid_block_additional_residual=m_, time_proj=tp)
-        one_step()   # warm
+        sampler.sample(lr_lat, ehs, cond_image=slices, noises=noises)       # leaves sampler.x / feats / z populated
+        sampler.idx.zero_()
+        sampler.x.copy_(noises[0])
+        sampler._step()                                                     # warm (eager)
         torch.cuda.synchronize(dev)
-        ops.GEMM_PROFILE = []
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        one_step()
-        s1.record()
+        nprof = max(3, args.profile_steps)
+        clocks_p = ClockSampler(local)
+        clocks_p.start()
+        ops.PROFILE = []
+        marks = []
+        for i in range(nprof):
+            sampler.idx.zero_()
+            sampler.x.copy_(noises[0])
+            n0 = len(ops.PROFILE)
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            sampler._step()
+            s1.record()
+            marks.append((n0, len(ops.PROFILE), s0, s1))
         torch.cuda.synchronize(dev)
-        prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
-        gemm_ms = sum(a.elapsed_time(b) for _, _, a, b, _ in prof)
-        conv_ms = sum(a.elapsed_time(b) for _, taps, a, b, _ in prof if taps == 9)
-        step_ms = s0.elapsed_time(s1)
+        clk_p = clocks_p.stop()
+        prof, ops.PROFILE = ops.PROFILE, None
+        per_step = []
+        for n0, n1, s0, s1 in marks:
+            acc = {}
+            for cls, work, a, b_, _ in prof[n0:n1]:
+                e = acc.setdefault(cls, [0.0, 0.0, 0])
+                e[0] += a.elapsed_time(b_)
+                e[1] += work
+                e[2] += 1
+            acc["__step__"] = [s0.elapsed_time(s1), 0.0, n1 - n0]
+            per_step.append(acc)
+        names = sorted({k for a in per_step for k in a})
+        med = {k: (statistics.median(a.get(k, [0, 0, 0])[0] for a in per_step), per_step[0].get(k, [0, 0, 0])[1],
+                   per_step[0].get(k, [0, 0, 0])[2]) for k in names}
+        step_ms = med["__step__"][0]
         sdpa = GFLOP_SDPA_STEP * (1.0 if controlnet is None else (1.0 + GFLOP_SDPA_CN_FRACTION))
-        algo_tflop = B * (gflop_step - sdpa) / 1e3
-        achieved = algo_tflop / (gemm_ms / 1e3)
-        peak = peaks["bf16_sustained"]
-        roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (implicit-GEMM conv3x3 + linear/1x1, all epilogues)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": GEMM_DRAM_BYTES_PER_LAUNCH_B32 * B / 32.0 if controlnet is None else None,
-                "traffic_source": "profiles/r1_launches_step_b32_v5.csv: dram__bytes_read.sum + dram__bytes_write.sum summed over "
-                                  "the 258 gemm_tcgen05_kernel launches of one batch-32 step / 258, scaled by batch/32",
-                "peak_source": f"{peaks['src']} bf16_tflops_sustained (kernel timed inside a long step)",
-                "launches_per_unet_forward": len(prof), "avg_launch_ms": gemm_ms / max(1, len(prof)),
-                "kernel_share_of_step": gemm_ms / step_ms, "conv3x3_share_of_step": conv_ms / step_ms,
-                "algorithmic_gflop_per_slice_step": gflop_step - sdpa}
+        traffic = None
+        if os.path.exists(TRAFFIC_JSON) and controlnet is None:
+            with open(TRAFFIC_JSON) as f:
+                traffic = json.load(f)
+        tpeak, hpeak = peaks["bf16_sustained"], peaks["hbm"]
+
+        def entry(label, keys, bound, algorithmic, unit_work):
+            ms_c = sum(med[k][0] for k in keys if k in med)
+            n_c = sum(med[k][2] for k in keys if k in med)
+            if ms_c <= 0.0:
+                return None
+            peak = tpeak if bound == "tensor" else hpeak
+            ach = algorithmic / (ms_c / 1e3) / (1e12 if bound == "tensor" else 1e9)
+            tr = None
+            if traffic is not None and traffic.get("batch") == 32:
+                tb = sum(traffic["classes"].get(k, {}).get("dram_bytes", 0.0) for k in keys)
+                tn = sum(traffic["classes"].get(k, {}).get("launches", 0) for k in keys)
+                tr = tb / tn * B / 32.0 if tn else None
+            return {"class": label, "bound": bound, "launches_per_step": n_c, "ms_per_step": ms_c, "avg_launch_ms": ms_c / max(1, n_c),
+                    "share_of_step": ms_c / step_ms, "algorithmic_per_step": algorithmic, "algorithmic_unit": unit_work,
+                    "achieved": ach, "peak": peak, "unit": "TFLOP/s" if bound == "tensor" else "GB/s", "frac": ach / peak,
+                    "traffic": tr}
+
+        classes = [
+            entry("gemm_tcgen05_kernel: implicit-GEMM conv3x3 + linear / 1x1 (all epilogues, LoRA)", ["conv3x3", "gemm"], "tensor",
+                  B * (gflop_step - sdpa) * 1e9, "FLOP"),
+            entry("gemm_tcgen05_kernel: conv3x3 only", ["conv3x3"], "tensor",
+                  B * GFLOP_CONV3_STEP * (1.0 if controlnet is None else 1.0 + GFLOP_CONV3_CN_FRACTION) * 1e9, "FLOP"),
+            entry("attention_tcgen05_split_kernel<40>: 64x64 self-attention", ["attn_self_d40"], "tensor",
+                  med.get("attn_self_d40", (0, 0, 0))[1], "FLOP"),
+            entry("other attention (d=80/160 self, prompt cross)", ["attn_self", "attn_cross"], "tensor",
+                  med.get("attn_self", (0, 0, 0))[1] + med.get("attn_cross", (0, 0, 0))[1], "FLOP"),
+            entry("groupnorm (+SiLU): 1 read + 1 write", ["groupnorm"], "hbm", med.get("groupnorm", (0, 0, 0))[1], "B"),
+            entry("layernorm: 1 read + 1 write", ["layernorm"], "hbm", med.get("layernorm", (0, 0, 0))[1], "B"),
+            entry("sched_step_indexed (launch-bound at this batch; see large_batch)", ["sched_step"], "hbm",
+                  med.get("sched_step", (0, 0, 0))[1], "B"),
+        ]
+        classes = [c for c in classes if c is not None]
+        # the scheduler kernel at a batch where it is HBM- rather than launch-bound (B >= 4096)
+        try:
+            nb = 4096
+            xs = [torch.randn((nb, 4, 64, 64), device=dev) for _ in range(4)]
+            ctab = sampler.coef[1:2].contiguous()
+            izero = torch.zeros(1, dtype=torch.int32, device=dev)
+            for _ in range(3):
+                ops.sched_step_indexed(xs[0], xs[1], ctab, izero, lr=xs[2], z_table=xs[3].view(1, *xs[3].shape), out=xs[0])
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record()
+            for _ in range(10):
+                ops.sched_step_indexed(xs[0], xs[1], ctab, izero, lr=xs[2], z_table=xs[3].view(1, *xs[3].shape), out=xs[0])
+            q1.record()
+            torch.cuda.synchronize(dev)
+            gbs = 10 * 5 * xs[0].numel() * 4 / (q0.elapsed_time(q1) / 1e3) / 1e9
+            for c in classes:
+                if c["class"].startswith("sched_step"):
+                    c["large_batch"] = {"batch": nb, "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                                        "peak_note": "MEASURED_PEAKS.json hbm_gbs (burst copy figure: kernel timed alone)"}
+            del xs
+        except Exception as exc:
+            classes.append({"class": "sched_step large batch", "error": f"{type(exc).__name__}: {exc}"[:200]})
+        dom = dict(classes[0])
+        roof = {"bound": dom["bound"], "kernel": dom["class"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"],
+                "frac": dom["frac"], "traffic": dom["traffic"],
+                "traffic_source": (traffic or {}).get("source"),
+                "peak_source": f"{peaks['src']}: bf16_tflops_sustained / hbm_gbs (kernels timed inside a long power-capped step)",
+                "method": f"CUDA events around every launch of {nprof} eager steps on the launching stream; per-class per-step sums, median over steps",
+                "launches_per_unet_forward": dom["launches_per_step"], "avg_launch_ms": dom["avg_launch_ms"],
+                "kernel_share_of_step": dom["share_of_step"], "eager_step_ms": step_ms,
+                "algorithmic_gflop_per_slice_step": gflop_step - sdpa,
+                "clocks_during_profile": clk_p, "classes": classes}
     whole = value * (NI * gflop_step + gflop_once) / 1e3 / world   # TFLOP/s per GPU, algorithmic
 
     cpu = None
@@ -425,7 +531,7 @@ def main():
                          f"{'Adapter_XL pass' if args.cond == 'adapter' else 'condition embedding'} ({t_ad:.2f} s), extrapolated x{NI}"}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        line = {"metric": METRICS[args.cond], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": workload, "batch_per_gpu": B, "global_batch": B * world,
@@ -435,9 +541,10 @@ def main():
                            "parallelism": f"slice-sharded x{world}, weights replicated, NCCL all_gather of final latents",
                            "l2": "working set (1.7 GB weights + GBs of activations per UNet forward) >> 126 MB L2; no flush needed",
                            "cuda_graph": True,
+                           "cpu_baseline_note": "extrapolated: 1 timed oracle forward x inference_steps + 1 condition pass, batch 1, fp32",
                            "numerics": "bf16 x bf16 -> fp32 MMAs; residual stream stored in fp16 (its 1x1 / stride-2 consumers run "
                                        "f16 x f16 -> fp32); norms, softmax, scheduler in fp32"},
-                "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clk, "roofline": roof,
+                "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clk, "parity_gate": gate, "roofline": roof,
                 "whole_step": {"achieved_tflops_per_gpu": whole, "frac_of_sustained_peak": whole / peaks["bf16_sustained"],
                                "algorithmic_tflop_per_slice": (NI * gflop_step + gflop_once) / 1e3},
                 "cpu_baseline": cpu}

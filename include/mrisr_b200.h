@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MRISR_ABI_VERSION 4
+#define MRISR_ABI_VERSION 5
 
 #define MRISR_OK 0
 #define MRISR_E_INVALID (-1)     /* bad argument (null pointer, misaligned, negative size) */
@@ -58,13 +58,14 @@ int mrisr_res_shift(const float* hr, const float* lr, const float* noise, float*
 
 /* Graph-replayable form of mrisr_sched_step: step i = *idx (DEVICE int32) selects coef_table[i][0..3] and the
  * noise slab z_table + i*z_stride (z_table may be NULL), so ONE captured step serves all N iterations of the loop
- * (res_srdiff.py:63) with no host sync (the reference syncs on `prev_t > 0`, :92; here c4 == 0 encodes it). */
+ * (res_srdiff.py:63) with no host sync (the reference syncs on `prev_t > 0`, :92; here c4 == 0 encodes it).
+ * n_rows = rows of coef_table (and slabs of z_table): *idx outside [0, n_rows) makes the kernel trap. */
 int mrisr_sched_step_indexed(const float* x, const float* eps, const float* lr, const float* z_table, int64_t z_stride,
-                             float* out, int64_t n, const float* coef_table, const int* idx, void* stream);
+                             float* out, int64_t n, const float* coef_table, const int* idx, int n_rows, void* stream);
 
 /* Selects row *idx of a device table (per-step time-embedding projections / step coefficients) and advances the
  * device-side step counter -- lets one captured CUDA graph replay all N steps of the loop (res_srdiff.py:63). */
-int mrisr_select_row(const float* table, const int* idx, int64_t stride, float* dst, int n, void* stream);
+int mrisr_select_row(const float* table, const int* idx, int n_rows, int64_t stride, float* dst, int n, void* stream);
 int mrisr_advance_index(int* idx, void* stream);
 
 /* --- UNet building blocks (diffusers UNet2DConditionModel.forward; call site src/adapters/res_srdiff.py:73-78) */
@@ -77,11 +78,25 @@ int mrisr_sinusoidal_embedding(const float* t, float* out, int batch, int dim, i
 
 /* GroupNorm (+ optional SiLU) over NHWC bf16 whose channels are the concat of x1 [B,HW,c1] (pixel stride ld1) and
  * optional x2 [B,HW,c2] (UNet skip concat, diffusers `torch.cat([h, skip], 1)`), writing dense bf16 [B,HW,c1+c2].
- * workspace: fp32, at least mrisr_groupnorm_workspace_floats(batch, groups). c1, c2 % 8 == 0; groups <= 64. */
+ * Self-contained form (statistics computed here): a statistics kernel + a normalise kernel (two reads of x), or one
+ * single-pass kernel for small images.  workspace: fp32, at least mrisr_groupnorm_workspace_floats(batch, groups), owned by
+ * the caller for the duration of the call: no library-owned state, so concurrent streams are safe.
+ * c1, c2 % 8 == 0; groups <= 64. */
 int64_t mrisr_groupnorm_workspace_floats(int batch, int groups);
 int mrisr_groupnorm(const void* x1, int64_t ld1, int c1, const void* x2, int64_t ld2, int c2, int batch, int hw,
                     int groups, const float* gamma, const float* beta, float eps, int silu, void* out,
                     float* workspace, int f16_flags /* bit 0: x1, bit 1: x2 is IEEE half (the fp16 residual stream) */, void* stream);
+/* The fused form (north_star "conv2d fused with GroupNorm+SiLU"; diffusers ResnetBlock2D norm1/norm2, Transformer2DModel.norm,
+ * conv_norm_out behind the call site src/adapters/res_srdiff.py:73-78): the statistics come from the PRODUCING mrisr_gemm's
+ * epilogue (mrisr_gemm_args.gn_stats), this call is the single normalise(+SiLU) pass -- one read and one write of x, no
+ * statistics pass, no grid barrier.  part1 / part2: fp32 pairs (sum, sum of squares) per 128-row block and channel as
+ * written by mrisr_gemm for x1 / x2: element [(ph * phase_stride + b * (hw_part / 128) + j) * ldp + c] with ldp counted in
+ * PAIRS; n_phases = 4 / hw_part = hw / 4 / phase_stride = blocks per phase for outputs of a taps == 4 (up2x) GEMM,
+ * otherwise n_phases = 1, hw_part = hw.  hw_part % 128 == 0. */
+int mrisr_groupnorm_apply_stats(const void* x1, int64_t ld1, int c1, const float* part1, int64_t ldp1, int n_phases1, int64_t phase_stride1,
+                                const void* x2, int64_t ld2, int c2, const float* part2, int64_t ldp2, int n_phases2, int64_t phase_stride2,
+                                int batch, int hw, int groups, const float* gamma, const float* beta, float eps, int silu,
+                                void* out, int f16_flags, void* stream);
 
 /* LayerNorm over the last dim: bf16 (or, in_f16 != 0, IEEE half) [rows, C] (row stride ldx) -> bf16 [rows, C] (row stride ldo).
  * C % 8 == 0, C <= 2048. */
@@ -94,6 +109,12 @@ int mrisr_layernorm(const void* x, int64_t ldx, const float* gamma, const float*
  * taps == 9: A1/A2 are NHWC [B, H, W, k] activations (pixel strides lda1/lda2); 3x3, pad 1 convolution, stride
  *            conv_stride (1 or 2); M = B*Ho*Wo; Wo and Ho powers of two (the TMA box is {64ch, min(Wo,128), 128/Wo rows}:
  *            whole output rows, or a 128-pixel segment of one row when Wo > 128; traversed with element stride conv_stride).
+ * taps == 4: nearest-2x upsample + 3x3 pad-1 convolution (diffusers Upsample2D: F.interpolate(scale 2, "nearest") then conv)
+ *            folded into four 2x2 sub-pixel convolutions over the LOW-resolution input A1 = NHWC [B, H, W, k1]
+ *            (k2 = 0, no residuals): output pixel (2y+a, 2x+b) = sum over the 2x2 input neighbourhood
+ *            rows {y-1+a, y+a} x cols {x-1+b, x+b} with the 3x3 filter's taps pre-summed per phase.  M = B*H*W (low-res
+ *            pixels); W is [4*N, 4*k1] (phase-major rows, k index = (ty*2+tx)*k1 + channel); out is NHWC [B, 2H, 2W, n_store]
+ *            with pixel stride ldo -- 4/9 of the multiply-adds of the unfolded form and no 4x-sized intermediate.
  * W: bf16 [N, taps*(k1+k2)] K-major, k index = tap*(k1+k2) + channel.  N % mrisr_gemm_block_n(N, act) == 0.
  * k1, k2 % 64 == 0.  bias fp32 [N] or NULL.  rowvec fp32: added before act, row m uses
  * rowvec[(m / rows_per_batch) * rowvec_stride + n] (time-embedding projection; NULL = none).
@@ -130,6 +151,11 @@ typedef struct mrisr_gemm_args {
                             stream in fp16 (3 more mantissa bits than bf16: the stream's rounding error is the largest term of
                             the noise-prediction error budget), everything else stays bf16 */
   int32_t reserved3;
+  float* gn_stats;       /* NULL, or fp32 pairs [(taps == 4 ? 4 : 1) * M/128][ld_stats] receiving, per 128-row block of the output
+                            and per output channel, (sum, sum of squares) of the STORED values: the GroupNorm statistics of the
+                            consumer, produced in this GEMM's epilogue (see mrisr_groupnorm_apply_stats).  Needs a 16-bit output,
+                            n_store == N, M % 128 == 0, act != GEGLU, residuals only with act == NONE.  Deterministic. */
+  int64_t ld_stats;      /* row pitch of gn_stats in PAIRS (>= N) */
 } mrisr_gemm_args;
 #define MRISR_F16_OUT 1   /* out (when out_fp32 == 0) */
 #define MRISR_F16_RES1 2  /* res1 */

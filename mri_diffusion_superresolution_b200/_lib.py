@@ -10,6 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmrisr_b200.so")
 
+ABI_VERSION = 5
 ACT_NONE, ACT_RELU, ACT_SILU, ACT_GEGLU = 0, 1, 2, 3
 E_INVALID, E_UNSUPPORTED, E_CUDA = -1, -2, -3
 
@@ -31,6 +32,7 @@ class GemmArgs(C.Structure):
         ("out_fp32", C.c_int32), ("reserved", C.c_int32),
         ("conv_stride", C.c_int32), ("conv_pad_mode", C.c_int32),
         ("f16_flags", C.c_int32), ("reserved3", C.c_int32),
+        ("gn_stats", C.c_void_p), ("ld_stats", C.c_int64),
     ]
 
 
@@ -43,13 +45,14 @@ PROTOTYPES = {
     "mrisr_device_info": (_I, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "mrisr_sched_step": (_I, [_P, _P, _P, _P, _P, _L, _P, _P]),
     "mrisr_res_shift": (_I, [_P, _P, _P, _P, _L, _I, _P, _I, _P, _I, _P]),
-    "mrisr_sched_step_indexed": (_I, [_P, _P, _P, _P, _L, _P, _L, _P, _P, _P]),
-    "mrisr_select_row": (_I, [_P, _P, _L, _P, _I, _P]),
+    "mrisr_sched_step_indexed": (_I, [_P, _P, _P, _P, _L, _P, _L, _P, _P, _I, _P]),
+    "mrisr_select_row": (_I, [_P, _P, _I, _L, _P, _I, _P]),
     "mrisr_advance_index": (_I, [_P, _P]),
     "mrisr_timestep_embedding": (_I, [_P, _P, _I, _I, _P]),
     "mrisr_sinusoidal_embedding": (_I, [_P, _P, _I, _I, _I, _P]),
     "mrisr_groupnorm_workspace_floats": (_L, [_I, _I]),
     "mrisr_groupnorm": (_I, [_P, _L, _I, _P, _L, _I, _I, _I, _I, _P, _P, _F, _I, _P, _P, _I, _P]),
+    "mrisr_groupnorm_apply_stats": (_I, [_P, _L, _I, _P, _L, _I, _L, _P, _L, _I, _P, _L, _I, _L, _I, _I, _I, _P, _P, _F, _I, _P, _I, _P]),
     "mrisr_layernorm": (_I, [_P, _L, _P, _P, _F, _P, _L, _I, _I, _I, _P]),
     "mrisr_gemm": (_I, [C.POINTER(GemmArgs), _P]),
     "mrisr_gemm_block_n": (_I, [_I, _I]),
@@ -89,7 +92,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.mrisr_abi_version() != 4:
+        if lib.mrisr_abi_version() != ABI_VERSION:
             raise RuntimeError("libmrisr_b200.so ABI version mismatch; rebuild")
         _lib = lib
     return _lib

@@ -114,8 +114,11 @@ class ControlNetB200(UNet2DConditionB200):
             raise RuntimeError("ControlNetB200 runs on CUDA only (no CPU path)")
         if controlnet_cond.dim() != 4 or controlnet_cond.shape[1] != self.cond_in:
             raise ValueError(f"controlnet_cond must be [B, {self.cond_in}, H, W]")
-        key = (controlnet_cond.data_ptr(), tuple(controlnet_cond.shape), tuple(controlnet_cond.stride()), controlnet_cond._version)
-        if key == self._cond_key and not force:
+        # identity of the tensor OBJECT (held strongly) + its version counter -- never its address, which the caching
+        # allocator recycles: log_validation builds a fresh control_image per call
+        key = (controlnet_cond, controlnet_cond._version)
+        if (not force and self._cond_key is not None and self._cond_key[0] is controlnet_cond
+                and self._cond_key[1] == controlnet_cond._version):
             return self._cond_embed
         B, _, H, W = controlnet_cond.shape
         down = 2 ** (len(self.cond_channels) - 1)
@@ -135,6 +138,8 @@ class ControlNetB200(UNet2DConditionB200):
         if old is not None and old.shape == h.shape:
             old.copy_(h)      # keep the address a captured CUDA graph reads
             h = old
+        else:
+            self.generation += 1
         self._cond_embed, self._cond_key = h, key
         return h
 

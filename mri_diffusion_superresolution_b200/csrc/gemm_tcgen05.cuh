@@ -16,6 +16,14 @@
 // * Residual tensors of activation-free GEMMs never touch the epilogue: R[M, N] is consumed as one more A operand
 //   against a 0/1 identity weight tile (BN/64 extra k-chunks per tile), i.e. it rides the same deep TMA pipeline as
 //   the operands and is added exactly (bf16 x 1.0) in the fp32 accumulator.
+// * GroupNorm statistics of the OUTPUT are produced by the epilogue (gn_part != nullptr): per-channel sum and sum of
+//   squares of every 128-row block of the stored (rounded) tile, reduced over rows on the legacy tensor path
+//   (ldmatrix.trans of the staged chunk + mma.sync against a ones / its own fragment), combined across the four
+//   32-row warps of the CTA in a fixed order (deterministic, no atomics on data) -- the consumer's GroupNorm is then a
+//   single normalise+SiLU pass (1 read + 1 write) with no statistics pass, no grid barrier and no re-read.
+// * up2x: nearest-2x upsample + 3x3 conv (diffusers Upsample2D) as four 2x2 sub-pixel convolutions over the
+//   LOW-resolution input with pre-summed weights (packing.pack_upsample_fold): 4/9 of the MACs, no 4x intermediate;
+//   phase (a, b) writes output pixels (2y+a, 2x+b) through a strided 4-D TMA store.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -31,7 +39,7 @@ struct GemmMaps {
   CUtensorMap r1, r2;     // residuals as [M, N] A operands (res_mma > 0)
   CUtensorMap ident;      // 256 x 256 identity weight tile (bf16)
   CUtensorMap ident_h;    // the same in IEEE half, for residual operands stored in fp16
-  CUtensorMap out;        // bf16 output, 32 x 32 boxes, 64B swizzle (tma_store)
+  CUtensorMap out[4];     // 16-bit output, 32-row x 32-channel boxes, 64B swizzle (tma_store); [ph] = sub-pixel phase (up2x)
 };
 
 struct GemmKernelParams {
@@ -63,6 +71,10 @@ struct GemmKernelParams {
   int f16_r1, f16_r2;  // res1 / res2 added in the epilogue
   int f16_rm;   // bit r: residual operand r of the MMA path (res_mma > 0)
   int dbg;  // timing experiments only: bit0 = skip TMA issue, bit1 = skip MMA issue (results are garbage)
+  int up2x;           // 1: taps == 4, four output phases folded into the tile loop (see header)
+  float2* gn_part;    // [phases * M/128][ld_part] (sum, sum of squares) per 128-row block and output channel, or nullptr
+  long long ld_part;
+  int part_phase_stride;  // 128-row blocks per phase (M / 128)
 };
 
 constexpr int kBlockM = 128;
@@ -82,8 +94,12 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kEpiBytes = 8 * 4096;     // per-epilogue-warp: two 32x32 bf16 staging buffers (TMA store double buffer)
   static constexpr int kBiasBytes = 8 * BN * 4;  // epilogue-staged bias, one slab per epilogue warp
-  static constexpr int kBarBytes = 256;          // <= 2*8+4 mbarriers + the TMEM base slot
-  static constexpr int kFixedBytes = kEpiBytes + kBiasBytes + kBarBytes + 1024;  // +1024: manual alignment slack
+  static constexpr int kBarBytes = 256;          // <= 2*8+4 mbarriers + the TMEM base slot + 6 statistics counters
+  // GroupNorm-statistics staging: ring of 3 tiles x 4 lane-quarter warps x BN columns x (sum, sumsq).  Ring depth 3: the
+  // accumulator hand-back happens BEFORE the epilogue arithmetic, so epilogue warps of one CTA can be two tiles apart.
+  static constexpr int kStatRing = 3;
+  static constexpr int kStatBytes = kStatRing * 4 * BN * 8;
+  static constexpr int kFixedBytes = kEpiBytes + kBiasBytes + kStatBytes + kBarBytes + 1024;  // +1024: manual alignment slack
   static constexpr int kFit = (232448 - kFixedBytes) / kStageBytes;
   static constexpr int kStages = kFit > 8 ? 8 : kFit;
   static_assert(kStages >= 3, "shared-memory budget");
@@ -166,6 +182,48 @@ __device__ __forceinline__ void gemm_stage_bias(const GemmKernelParams& p, float
   __syncwarp();
 }
 
+// Column sums and sums of squares of one staged 32-row x 32-channel 16-bit chunk (TMA 64B-swizzle layout: 64-byte rows,
+// 16-byte slot ^= (row >> 1) & 3), reduced over the 32 rows on the legacy tensor path: ldmatrix.trans delivers X^T
+// fragments; ones(16x16) * X gives the column sums, X^T * X has the sums of squares on its diagonal (exact fp16/bf16
+// products, fp32 accumulation).  16 MMAs + 4 ldmatrix per chunk instead of ~280 shuffle / select / add instructions.
+// Lane (g, t) with t == g >> 1 ends up owning columns 16 i + g and 16 i + 8 + g (i = 0, 1) and writes them to `slot`.
+struct GemmStatCtx {
+  float2* slots;   // this tile's ring entry: [4 lane quarters][BN]
+  int* counter;    // this tile's ring entry: arrivals of the lane-quarter warps, one counter per chunk half
+  long long block; // 128-row block index in gn_part
+};
+template <bool kF16>
+__device__ __forceinline__ void gemm_chunk_col_stats(uint32_t buf_addr, int lane, float2* slot) {
+  constexpr uint32_t one2 = kF16 ? 0x3C003C00u : 0x3F803F80u;
+  const uint32_t ones[4] = {one2, one2, one2, one2};
+  const int mat = lane >> 3, rr = lane & 7;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    float su1[4] = {0.f, 0.f, 0.f, 0.f}, su2[4] = {0.f, 0.f, 0.f, 0.f};
+    float sq1[4] = {0.f, 0.f, 0.f, 0.f}, sq2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const int row = 16 * ks + (mat >> 1) * 8 + rr;
+      const int slot16 = 2 * i + (mat & 1);
+      uint32_t a[4];
+      ldsm_x4_t(buf_addr + row * 64 + ((slot16 ^ ((row >> 1) & 3)) << 4), a[0], a[1], a[2], a[3]);
+      if (kF16) {
+        mma_f16_16816(su1, ones, a[0], a[2]); mma_f16_16816(su2, ones, a[1], a[3]);
+        mma_f16_16816(sq1, a, a[0], a[2]);    mma_f16_16816(sq2, a, a[1], a[3]);
+      } else {
+        mma_bf16_16816(su1, ones, a[0], a[2]); mma_bf16_16816(su2, ones, a[1], a[3]);
+        mma_bf16_16816(sq1, a, a[0], a[2]);    mma_bf16_16816(sq2, a, a[1], a[3]);
+      }
+    }
+    if (t == (g >> 1)) {
+      const bool odd = (g & 1) != 0;
+      slot[16 * i + g] = make_float2(odd ? su1[1] : su1[0], odd ? sq1[1] : sq1[0]);
+      slot[16 * i + 8 + g] = make_float2(odd ? su2[1] : su2[0], odd ? sq2[3] : sq2[2]);
+    }
+  }
+}
+
 // TMA-store epilogue (bf16 output, every chunk of the tile inside n_store, no residual left for the epilogue).
 // Thread (lane quarter q, lane) owns TMEM lane q*32+lane == output row m; two warps share a lane quarter and split the
 // 32-column chunks.  ALL of the warp's TMEM loads are issued up front and waited for once, then `release()` hands the
@@ -176,7 +234,7 @@ __device__ __forceinline__ void gemm_stage_bias(const GemmKernelParams& p, float
 template <int BN, bool kGeglu, typename Release>
 __device__ __forceinline__ void gemm_epilogue_tma(const GemmKernelParams& p, const CUtensorMap* tm_out, uint32_t t_row, int m,
                                                   int n_blk, int half, const float* sbias, uint8_t* stage_buf,
-                                                  uint32_t& buf_sel, Release release) {
+                                                  uint32_t& buf_sel, Release release, const GemmStatCtx& st) {
   constexpr int kOutCols = kGeglu ? BN / 2 : BN;
   constexpr int kChunks = kOutCols / 32;
   constexpr int kMaxC = (kChunks + 1) / 2;
@@ -199,6 +257,15 @@ __device__ __forceinline__ void gemm_epilogue_tma(const GemmKernelParams& p, con
   const int m_warp0 = m - lane_id;
   const int n_o0 = n_blk * kOutCols;
   const int sw = (lane_id >> 1) & 3;
+  const bool stats = !kGeglu && st.slots != nullptr;
+  int up_b = 0, up_y = 0, up_x = 0;   // up2x: the warp's 32 rows are low-resolution pixels (b, y.., x..) of one phase
+  if (p.up2x) {
+    const int hw = p.H * p.W;
+    up_b = m_warp0 / hw;
+    const int rem = m_warp0 - up_b * hw;
+    up_y = rem / p.W;
+    up_x = rem - up_y * p.W;
+  }
   tmem_ld_wait();
   release();
 #pragma unroll
@@ -248,10 +315,35 @@ __device__ __forceinline__ void gemm_epilogue_tma(const GemmKernelParams& p, con
         fence_proxy_async_smem();
         __syncwarp();
         if (lane_id == 0 && m_warp0 < p.M) {
-          tma_store_2d(tm_out, smem_u32(buf), n_o0 + c * 32, m_warp0);
+          if (p.up2x) tma_store_4d(tm_out, smem_u32(buf), n_o0 + c * 32, up_x, up_y, up_b);
+          else tma_store_2d(tm_out, smem_u32(buf), n_o0 + c * 32, m_warp0);
           bulk_commit_group();
         }
+        if (stats) {  // GroupNorm statistics of exactly the values just staged (what the consumer's norm will read)
+          float2* slot = st.slots + ((m >> 5) & 3) * BN + c * 32;
+          if (p.f16_out) gemm_chunk_col_stats<true>(smem_u32(buf), lane_id, slot);
+          else gemm_chunk_col_stats<false>(smem_u32(buf), lane_id, slot);
+        }
       }
+    }
+  }
+  if (stats) {
+    // the LAST of the four lane-quarter warps that share this chunk half adds the four 32-row partials in a fixed order
+    // and publishes the 128-row block's sums: deterministic, and no warp ever waits for another
+    __syncwarp();
+    __threadfence_block();
+    int old = 0;
+    if (lane_id == 0) old = atomicAdd(st.counter + half, 1);
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if (old == 3) {
+      __threadfence_block();
+      float2* dst = p.gn_part + st.block * p.ld_part + n_blk * BN;
+      for (int col = c_begin * 32 + lane_id; col < (c_begin + nc) * 32; col += 32) {
+        const float2 a0 = st.slots[col], a1 = st.slots[BN + col], a2 = st.slots[2 * BN + col], a3 = st.slots[3 * BN + col];
+        dst[col] = make_float2(((a0.x + a1.x) + a2.x) + a3.x, ((a0.y + a1.y) + a2.y) + a3.y);
+      }
+      __syncwarp();
+      if (lane_id == 0) st.counter[half] = 0;
     }
   }
 }
@@ -374,7 +466,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   uint8_t* sepi_base = smem_al + kStages * Cfg::kStageBytes;  // 1024-aligned: the TMA swizzle pattern is address-based
   float* sbias_base = reinterpret_cast<float*>(sepi_base + Cfg::kEpiBytes);
-  const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes + Cfg::kEpiBytes + Cfg::kBiasBytes;
+  float2* sstat_base = reinterpret_cast<float2*>(sepi_base + Cfg::kEpiBytes + Cfg::kBiasBytes);   // [ring][4][BN]
+  const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes + Cfg::kEpiBytes + Cfg::kBiasBytes + Cfg::kStatBytes;
+  int* scnt_base = reinterpret_cast<int*>(sepi_base + Cfg::kEpiBytes + Cfg::kBiasBytes + Cfg::kStatBytes + 8 * (2 * kStages + 5));   // [ring][2]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
@@ -399,7 +493,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
       tma_prefetch_desc(&maps.ident);
       if (p.f16_rm) tma_prefetch_desc(&maps.ident_h);
     }
-    if (p.tma_store) tma_prefetch_desc(&maps.out);
+    if (p.tma_store) {
+      tma_prefetch_desc(&maps.out[0]);
+      if (p.up2x) { tma_prefetch_desc(&maps.out[1]); tma_prefetch_desc(&maps.out[2]); tma_prefetch_desc(&maps.out[3]); }
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -410,6 +507,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), (kPair ? 2 : 1) * kEpilogueThreads);
     }
+    for (int s = 0; s < 2 * Cfg::kStatRing; ++s) scnt_base[s] = 0;
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -421,7 +519,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int m_tiles = (p.M + kTileM - 1) / kTileM;
-  const int total_tiles = m_tiles * p.n_tiles;
+  const int n_phases = p.up2x ? 4 : 1;   // tile -> (m tile, sub-pixel phase, n tile): the phases of an m tile share its input rows in L2
+  const int total_tiles = m_tiles * n_phases * p.n_tiles;
   const int kchunks = p.kc1 + p.kc2;
   const int kmain = p.taps * kchunks;
   // residual-as-operand: the k-chunks of R that intersect this tile's columns [n_blk*BN, n_blk*BN + BN)
@@ -460,8 +559,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
     };
     for (int tile = worker; tile < total_tiles; tile += num_workers) {
       const int n_blk = tile % p.n_tiles;
-      const int n0 = n_blk * BN + rank * Cfg::kBRows;
-      const int m0 = (tile / p.n_tiles) * kTileM + rank * kBlockM;
+      const int tq = tile / p.n_tiles;
+      const int ph = p.up2x ? (tq & 3) : 0;
+      const int n0 = ph * p.N + n_blk * BN + rank * Cfg::kBRows;   // up2x: the four phases' folded filters are stacked along N
+      const int m0 = (p.up2x ? (tq >> 2) : tq) * kTileM + rank * kBlockM;
       int b0 = 0, h0 = 0, x0 = 0;
       if (p.conv) {  // tile = 128 consecutive output pixels: whole rows (W <= 128) or a 128-pixel segment of one row
         const int hw = p.H * p.W;
@@ -471,8 +572,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
         x0 = rem - h0 * p.W;
       }
       for (int tap = 0; tap < p.taps; ++tap) {
-        const int dr = (p.taps == 9) ? tap / 3 - p.pad : 0;
-        const int ds = (p.taps == 9) ? tap % 3 - p.pad : 0;
+        // up2x: output row 2y+a reads input rows {y-1, y} (a = 0) or {y, y+1} (a = 1); same along x
+        const int dr = p.up2x ? (tap >> 1) - 1 + (ph >> 1) : (p.taps == 9) ? tap / 3 - p.pad : 0;
+        const int ds = p.up2x ? (tap & 1) - 1 + (ph & 1) : (p.taps == 9) ? tap % 3 - p.pad : 0;
         for (int kc = 0; kc < kchunks; ++kc) {
           const bool first = kc < p.kc1;
           load(first ? &maps.a1 : &maps.a2, p.conv != 0, (first ? kc : kc - p.kc1) * kBlockK, x0 * p.stride + ds, h0 * p.stride + dr, b0, m0, &maps.b,
@@ -484,7 +586,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
         for (int r = 0; r < p.res_mma; ++r)
           for (int j = 0; j < rkn; ++j)
             load(r == 0 ? &maps.r1 : &maps.r2, false, (rk0 + j) * kBlockK, 0, 0, 0, m0, ((p.f16_rm >> r) & 1) ? &maps.ident_h : &maps.ident,
-                 j * kBlockK, n0 - rk0 * kBlockK);
+                 j * kBlockK, n0 - ph * p.N - rk0 * kBlockK);
       }
     }
   } else if (warp == 1) {
@@ -548,8 +650,15 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
     for (int tile = worker; tile < total_tiles; tile += num_workers, ++it) {
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
       const int n_blk = tile % p.n_tiles;
-      const int m = (tile / p.n_tiles) * kTileM + rank * kBlockM + q * 32 + lane;
+      const int tq = tile / p.n_tiles;
+      const int ph = p.up2x ? (tq & 3) : 0;
+      const int m_tile = p.up2x ? (tq >> 2) : tq;
+      const int m = m_tile * kTileM + rank * kBlockM + q * 32 + lane;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+      GemmStatCtx st;
+      st.slots = p.gn_part != nullptr ? sstat_base + (it % Cfg::kStatRing) * 4 * BN : nullptr;
+      st.counter = scnt_base + (it % Cfg::kStatRing) * 2;
+      st.block = static_cast<long long>(ph) * p.part_phase_stride + m_tile * (kPair ? 2 : 1) + rank;
       __syncwarp();  // every lane finished reading the previous tile's slab
       gemm_stage_bias<BN>(p, sbias, n_blk, lane);
       mbar_wait(tfull_bar(as), aph);
@@ -562,9 +671,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
       if (p.tma_store && (n_blk + 1) * out_cols <= p.n_store && (BN % 64 == 0 || p.act != ACT_GEGLU)) {
         if (p.act == ACT_GEGLU) {
           if constexpr (BN % 64 == 0)
-            gemm_epilogue_tma<BN, true>(p, &maps.out, t_row, m, n_blk, half, sbias, stage_buf, buf_sel, release);
+            gemm_epilogue_tma<BN, true>(p, &maps.out[0], t_row, m, n_blk, half, sbias, stage_buf, buf_sel, release, st);
         } else {
-          gemm_epilogue_tma<BN, false>(p, &maps.out, t_row, m, n_blk, half, sbias, stage_buf, buf_sel, release);
+          gemm_epilogue_tma<BN, false>(p, &maps.out[ph], t_row, m, n_blk, half, sbias, stage_buf, buf_sel, release, st);
         }
       } else {
         gemm_epilogue_rows<BN>(p, t_row, m, n_blk, half, sbias, stage_buf);

@@ -338,8 +338,6 @@ int launch_layernorm_group(const void* x, int64_t ldx, const float* g, const flo
 }
 
 constexpr int kGnMaxSlabs = 64;
-constexpr int kGnMaxFusedBatch = 2048;
-__device__ int g_gn_counters[2 * kGnMaxFusedBatch];  // zero-initialised; groupnorm_fused_kernel leaves them zero
 
 }  // namespace
 
@@ -389,23 +387,23 @@ int mrisr_res_shift(const float* hr, const float* lr, const float* noise, float*
 }
 
 int mrisr_sched_step_indexed(const float* x, const float* eps, const float* lr, const float* z_table, int64_t z_stride,
-                             float* out, int64_t n, const float* coef_table, const int* idx, void* stream) {
-  MRISR_REQUIRE(x && eps && out && coef_table && idx, "sched_step_indexed: null pointer");
+                             float* out, int64_t n, const float* coef_table, const int* idx, int n_rows, void* stream) {
+  MRISR_REQUIRE(x && eps && out && coef_table && idx && n_rows > 0, "sched_step_indexed: null pointer / n_rows <= 0");
   MRISR_REQUIRE(n >= 0 && n % 4 == 0 && z_stride % 4 == 0, "sched_step_indexed: n and z_stride must be multiples of 4");
   MRISR_REQUIRE(aligned16(x) && aligned16(eps) && aligned16(out) && (!lr || aligned16(lr)) && (!z_table || aligned16(z_table)),
                 "sched_step_indexed: pointers must be 16-byte aligned");
   if (n == 0) return 0;
   const long long n4 = n / 4;
   launch_k(mrisr::sched_step_indexed_kernel, dim3(grid_for(n4, 256, 8)), dim3(256), 0, as_stream(stream), reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(eps), reinterpret_cast<const float4*>(lr),
-      reinterpret_cast<const float4*>(z_table), z_stride / 4, reinterpret_cast<float4*>(out), n4, coef_table, idx);
+      reinterpret_cast<const float4*>(z_table), z_stride / 4, reinterpret_cast<float4*>(out), n4, coef_table, idx, n_rows);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-int mrisr_select_row(const float* table, const int* idx, int64_t stride, float* dst, int n, void* stream) {
-  MRISR_REQUIRE(table && idx && dst && n >= 0, "select_row: bad argument");
+int mrisr_select_row(const float* table, const int* idx, int n_rows, int64_t stride, float* dst, int n, void* stream) {
+  MRISR_REQUIRE(table && idx && dst && n >= 0 && n_rows > 0, "select_row: bad argument");
   if (n == 0) return 0;
-  launch_k(mrisr::select_row_kernel, dim3(grid_for(n, 256, 2)), dim3(256), 0, as_stream(stream), table, idx, stride, dst, n);
+  launch_k(mrisr::select_row_kernel, dim3(grid_for(n, 256, 2)), dim3(256), 0, as_stream(stream), table, idx, stride, dst, n, n_rows);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -494,23 +492,11 @@ int mrisr_groupnorm(const void* x1, int64_t ld1, int c1, const void* x2, int64_t
       return 0;
     }
   }
-  // single-launch path: needs every CTA of the grid co-resident (per-batch barrier between the two passes), so the slab
-  // count comes from the occupancy calculator; MRISR_GN_TWO_PASS=1 forces the two-kernel path (A/B runs)
-  static const bool no_fused = getenv("MRISR_GN_TWO_PASS") != nullptr;
-  const size_t smem_fused = 2 * static_cast<size_t>(R) * C * sizeof(float);
+  // statistics kernel + normalise kernel; the caller-owned workspace carries the per-slab partials between them (no
+  // library-owned state: any number of streams may run this concurrently).  The fused form -- statistics from the
+  // producing GEMM's epilogue, one pass here -- is mrisr_groupnorm_apply_stats.
   int max_slabs = (hw + 4 * R - 1) / (4 * R);
-  bool fused = false;
-  int want = (148 * 8 + batch - 1) / batch;  // two-pass: >= 8 CTAs per SM chip-wide (latency-bound below that)
-  if (!no_fused && batch <= kGnMaxFusedBatch) {
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mrisr::groupnorm_fused_kernel, nvec * R, smem_fused) == cudaSuccess) {
-      const long long capacity = static_cast<long long>(per_sm) * sm_count();
-      if (capacity >= batch) {
-        fused = true;
-        want = static_cast<int>(capacity / batch);
-      }
-    }
-  }
+  const int want = (sm_count() * 8 + batch - 1) / batch;  // >= 8 CTAs per SM chip-wide (latency-bound below that)
   int nslab = want < max_slabs ? want : max_slabs;
   if (nslab > kGnMaxSlabs) nslab = kGnMaxSlabs;
   if (nslab < 1) nslab = 1;
@@ -524,21 +510,55 @@ int mrisr_groupnorm(const void* x1, int64_t ld1, int c1, const void* x2, int64_t
   a.nslab = nslab; a.pix_per_slab = pps;
   dim3 block(nvec, R), grid(nslab, batch);
   cudaStream_t st = as_stream(stream);
-  if (fused) {
-    static int* counters = nullptr;
-    if (counters == nullptr) {
-      void* sym = nullptr;
-      MRISR_CHECK_CUDA(cudaGetSymbolAddress(&sym, g_gn_counters));
-      counters = static_cast<int*>(sym);
-    }
-    launch_k(mrisr::groupnorm_fused_kernel, dim3(grid), dim3(block), smem_fused, st, a, reinterpret_cast<float2*>(workspace), gamma, beta,
-             eps, silu, static_cast<__nv_bfloat16*>(out), counters);
-    MRISR_CHECK_CUDA(cudaGetLastError());
-    return 0;
-  }
   launch_k(mrisr::groupnorm_stats_kernel, dim3(grid), dim3(block), 2 * R * C * sizeof(float), st, a, reinterpret_cast<float2*>(workspace));
   MRISR_CHECK_CUDA(cudaGetLastError());
   launch_k(mrisr::groupnorm_apply_kernel, dim3(grid), dim3(block), 2 * C * sizeof(float), st, a, reinterpret_cast<const float2*>(workspace), gamma, beta, eps, silu, static_cast<__nv_bfloat16*>(out), nslab);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mrisr_groupnorm_apply_stats(const void* x1, int64_t ld1, int c1, const float* part1, int64_t ldp1, int n_phases1, int64_t phase_stride1,
+                                const void* x2, int64_t ld2, int c2, const float* part2, int64_t ldp2, int n_phases2, int64_t phase_stride2,
+                                int batch, int hw, int groups, const float* gamma, const float* beta, float eps, int silu,
+                                void* out, int f16_flags, void* stream) {
+  MRISR_REQUIRE(x1 && part1 && gamma && beta && out, "groupnorm_apply_stats: null pointer");
+  MRISR_REQUIRE(batch > 0 && hw > 0 && c1 > 0 && c2 >= 0, "groupnorm_apply_stats: bad sizes");
+  if (c2 == 0) { x2 = nullptr; ld2 = 0; part2 = nullptr; }
+  MRISR_REQUIRE(c2 == 0 || (x2 && part2), "groupnorm_apply_stats: c2 > 0 but x2 / part2 is null");
+  const int C = c1 + c2;
+  MRISR_REQUIRE(c1 % 8 == 0 && c2 % 8 == 0 && ld1 % 8 == 0 && ld2 % 8 == 0, "groupnorm_apply_stats: channels/strides must be multiples of 8");
+  MRISR_REQUIRE(groups > 0 && groups <= 64 && C % groups == 0, "groupnorm_apply_stats: groups must divide C and be <= 64");
+  MRISR_REQUIRE(aligned16(x1) && aligned16(out) && (!x2 || aligned16(x2)), "groupnorm_apply_stats: misaligned pointer");
+  MRISR_REQUIRE((n_phases1 == 1 || n_phases1 == 4) && (c2 == 0 || n_phases2 == 1 || n_phases2 == 4), "groupnorm_apply_stats: n_phases must be 1 or 4");
+  MRISR_REQUIRE(hw % (128 * n_phases1) == 0 && (c2 == 0 || hw % (128 * n_phases2) == 0), "groupnorm_apply_stats: hw / n_phases must be a multiple of 128 (the statistics' block size)");
+  MRISR_REQUIRE(ldp1 >= c1 && (c2 == 0 || ldp2 >= c2), "groupnorm_apply_stats: ldp < channels");
+  MRISR_REQUIRE((reinterpret_cast<uintptr_t>(part1) & 7u) == 0 && (!part2 || (reinterpret_cast<uintptr_t>(part2) & 7u) == 0), "groupnorm_apply_stats: partials must be 8-byte aligned");
+  const int nvec = C / 8;
+  if (nvec > 512) return fail(MRISR_E_UNSUPPORTED, "groupnorm_apply_stats: C = %d > 4096 unsupported", C);
+  int R = 256 / nvec;
+  if (R < 1) R = 1;
+  if (R > hw) R = hw;
+  // slabs per batch element: enough CTAs for >= 4 per SM chip-wide, but every CTA re-reads its element's block partials
+  // (hw / 128 * C pairs from L2), so no more than 16 slabs: <= 25 % extra L2 reads on top of the tensor itself
+  int nslab = (sm_count() * 4 + batch - 1) / batch;
+  if (nslab > 16) nslab = 16;
+  const int max_slabs = (hw + 8 * R - 1) / (8 * R);
+  if (nslab > max_slabs) nslab = max_slabs;
+  if (nslab < 1) nslab = 1;
+  const int pps = (hw + nslab - 1) / nslab;
+  nslab = (hw + pps - 1) / pps;
+  mrisr::GnArgs a;
+  a.x1 = static_cast<const __nv_bfloat16*>(x1);
+  a.x2 = static_cast<const __nv_bfloat16*>(x2);
+  a.ld1 = ld1; a.ld2 = ld2; a.c1 = c1; a.c2 = c2; a.hw = hw; a.batch = batch; a.groups = groups;
+  a.h1 = f16_flags & 1; a.h2 = (f16_flags >> 1) & 1;
+  a.nslab = nslab; a.pix_per_slab = pps;
+  mrisr::GnPartArgs q;
+  q.part[0] = reinterpret_cast<const float2*>(part1); q.ldp[0] = ldp1; q.nph[0] = n_phases1; q.pstride[0] = phase_stride1;
+  q.nblk[0] = hw / (128 * n_phases1);
+  q.part[1] = reinterpret_cast<const float2*>(part2); q.ldp[1] = ldp2; q.nph[1] = c2 ? n_phases2 : 1; q.pstride[1] = phase_stride2;
+  q.nblk[1] = c2 ? hw / (128 * n_phases2) : 0;
+  launch_k(mrisr::groupnorm_apply_cpart_kernel, dim3(nslab, batch), dim3(nvec, R), 2 * static_cast<size_t>(C) * sizeof(float), as_stream(stream), a, q, gamma, beta, eps, silu, static_cast<__nv_bfloat16*>(out));
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -588,7 +608,7 @@ int mrisr_gemm_block_n(int N, int act) {
 // N-tile for a given problem: GEGLU weights are interleaved per tile at load time, so their BN depends on N only; every
 // other GEMM picks, per call, the tile width that minimises waves x (BN + fixed per-tile cost) on the 74 CTA pairs --
 // at batch 32 the 16x16 level (M = 8192, N = 1280) is 3 waves of BN=256 tiles but 4 waves of the 37 % narrower BN=160.
-static int pick_block_n(int M, int N, int act) {
+static int pick_block_n(int M, int N, int act, int phases = 1) {
   const int fixed = mrisr_gemm_block_n(N, act);
   if (act == MRISR_ACT_GEGLU || fixed == 0 || getenv("MRISR_GEMM_BN") != nullptr) return fixed;
   const int pairs = sm_count() / 2 > 0 ? sm_count() / 2 : 1;
@@ -599,7 +619,7 @@ static int pick_block_n(int M, int N, int act) {
   for (int i = 0; i < 5; ++i) {
     const int bn = cand[i];
     if (N % bn != 0) continue;
-    const long long tiles = static_cast<long long>(m_tiles) * (N / bn);
+    const long long tiles = static_cast<long long>(m_tiles) * phases * (N / bn);
     const long long waves = (tiles + pairs - 1) / pairs;
     const long long cost = waves * (bn + 40);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
@@ -611,11 +631,14 @@ int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
   MRISR_REQUIRE(g != nullptr, "gemm: null args");
   MRISR_REQUIRE(g->a1 && g->w && g->out, "gemm: null a1/w/out");
   MRISR_REQUIRE(g->M > 0 && g->N > 0 && g->n_store > 0, "gemm: M, N, n_store must be positive");
-  MRISR_REQUIRE(g->taps == 1 || g->taps == 9, "gemm: taps must be 1 or 9");
+  MRISR_REQUIRE(g->taps == 1 || g->taps == 9 || g->taps == 4, "gemm: taps must be 1, 9 or 4 (folded nearest-2x upsample + 3x3)");
+  const bool up2x = g->taps == 4;
+  MRISR_REQUIRE(!up2x || (g->k2 == 0 && !g->res1 && !g->res2 && !g->out_fp32 && g->act != MRISR_ACT_GEGLU && g->conv_stride <= 1 && g->conv_pad_mode == 0),
+                "gemm(up2x): needs k2 == 0, no residuals, a 16-bit output, stride 1");
   MRISR_REQUIRE(g->k1 > 0 && g->k1 % 64 == 0 && g->k2 >= 0 && g->k2 % 64 == 0, "gemm: k1 (%d) / k2 (%d) must be multiples of 64", g->k1, g->k2);
   MRISR_REQUIRE(g->k2 == 0 || g->a2, "gemm: k2 > 0 but a2 is null");
   MRISR_REQUIRE(g->act >= 0 && g->act <= 3, "gemm: bad act");
-  const int BN = pick_block_n(g->M, g->N, g->act);
+  const int BN = pick_block_n(g->M, g->N, g->act, up2x ? 4 : 1);
   if (BN == 0) return fail(MRISR_E_UNSUPPORTED, "gemm: N = %d is not a multiple of 64", g->N);
   const int out_cols = g->act == MRISR_ACT_GEGLU ? g->N / 2 : g->N;
   MRISR_REQUIRE(g->n_store <= out_cols, "gemm: n_store (%d) > produced columns (%d)", g->n_store, out_cols);
@@ -636,7 +659,7 @@ int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
   CUtensorMap& ma1 = maps.a1;
   CUtensorMap& ma2 = maps.a2;
   {
-    cuuint64_t dims[2] = {static_cast<cuuint64_t>(ktot), static_cast<cuuint64_t>(g->N)};
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(ktot), static_cast<cuuint64_t>(g->N) * (up2x ? 4 : 1)};
     cuuint64_t str[1] = {static_cast<cuuint64_t>(ktot) * 2};
     cuuint32_t box[2] = {64, static_cast<cuuint32_t>(pair ? BN / 2 : BN)};
     if (int e = encode_map(&maps.b, g->w, 2, dims, str, box)) return e;
@@ -686,9 +709,11 @@ int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
 
   mrisr::GemmKernelParams p;
   p.M = g->M; p.N = g->N; p.n_store = g->n_store;
-  p.kc1 = g->k1 / 64; p.kc2 = g->k2 / 64; p.taps = g->taps; p.conv = g->taps == 9 ? 1 : 0;
+  p.kc1 = g->k1 / 64; p.kc2 = g->k2 / 64; p.taps = g->taps; p.conv = g->taps != 1 ? 1 : 0;
+  p.up2x = up2x ? 1 : 0;
   p.stride = (g->taps == 9 && g->conv_stride == 2) ? 2 : 1;
   MRISR_REQUIRE(g->conv_pad_mode == 0 || (g->conv_pad_mode == 1 && g->taps == 9), "gemm: conv_pad_mode must be 0, or 1 with taps == 9");
+  MRISR_REQUIRE(!up2x || (g->H * g->W >= 32), "gemm(up2x): needs at least 32 input pixels per image");
   p.pad = g->conv_pad_mode == 1 ? 0 : 1;
   p.H = g->H / p.stride; p.W = g->W / p.stride;
   p.m_tiles = (g->M + 127) / 128; p.n_tiles = g->N / BN;
@@ -708,7 +733,9 @@ int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
   p.dbg = g->reserved;
   p.res_mma = 0;
   p.tma_store = 0;
-  maps.r1 = ma1; maps.r2 = ma1; maps.ident = ma1; maps.ident_h = ma1; maps.out = ma1;
+  maps.r1 = ma1; maps.r2 = ma1; maps.ident = ma1; maps.ident_h = ma1;
+  for (int i = 0; i < 4; ++i) maps.out[i] = ma1;
+  p.gn_part = nullptr; p.ld_part = 0; p.part_phase_stride = 0;
 
   // Residuals of activation-free GEMMs become extra A operands against the identity tile (see gemm_tcgen05.cuh): the
   // epilogue then has no residual traffic at all.  MRISR_GEMM_RES_EPILOGUE=1 keeps them in the epilogue (A/B runs).
@@ -747,12 +774,36 @@ int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
     p.res2 = nullptr;
   }
   // bf16 outputs whose residuals (if any) are out of the epilogue go through the TMA-store epilogue
-  if (!g->out_fp32 && p.res1 == nullptr && p.res2 == nullptr && g->n_store >= 32) {
+  if (up2x) {
+    // phase (a, b) owns output pixels (2y+a, 2x+b) of the [B, 2H, 2W, n_store] tensor: a strided 4-D view whose 32-row store
+    // box is {32 channels, min(W, 32) pixels, 32 / min(W, 32) rows, 1 image} of LOW-resolution coordinates
+    MRISR_REQUIRE(g->n_store >= 32 && g->n_store % 32 == 0 && g->n_store == g->N, "gemm(up2x): n_store must equal N (a multiple of 32)");
+    const int tw = g->W < 32 ? g->W : 32, th = 32 / tw;
+    const int B = g->M / (g->H * g->W);
+    for (int ph = 0; ph < 4; ++ph) {
+      const int a = ph >> 1, b = ph & 1;
+      const char* base = static_cast<const char*>(g->out) + (static_cast<long long>(a) * 2 * g->W + b) * g->ldo * 2;
+      cuuint64_t dims[4] = {static_cast<cuuint64_t>(g->n_store), static_cast<cuuint64_t>(g->W), static_cast<cuuint64_t>(g->H), static_cast<cuuint64_t>(B)};
+      cuuint64_t str[3] = {static_cast<cuuint64_t>(g->ldo) * 4, static_cast<cuuint64_t>(g->ldo) * 2 * 2 * (2 * g->W),
+                           static_cast<cuuint64_t>(g->ldo) * 2 * (2 * g->W) * (2 * g->H)};
+      cuuint32_t box[4] = {32, static_cast<cuuint32_t>(tw), static_cast<cuuint32_t>(th), 1};
+      if (int e = encode_map(&maps.out[ph], base, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
+    }
+    p.tma_store = 1;
+  } else if (!g->out_fp32 && p.res1 == nullptr && p.res2 == nullptr && g->n_store >= 32) {
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(g->n_store), static_cast<cuuint64_t>(g->M)};
     cuuint64_t str[1] = {static_cast<cuuint64_t>(g->ldo) * 2};
     cuuint32_t box[2] = {32, 32};
-    if (int e = encode_map(&maps.out, g->out, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
+    if (int e = encode_map(&maps.out[0], g->out, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
     p.tma_store = 1;
+  }
+  if (g->gn_stats != nullptr) {
+    MRISR_REQUIRE(p.tma_store == 1 && g->n_store == g->N && g->M % 128 == 0 && g->act != MRISR_ACT_GEGLU && g->ld_stats >= g->N,
+                  "gemm: gn_stats needs a 16-bit TMA-stored output (no epilogue residual), n_store == N, M %% 128 == 0, ld_stats >= N");
+    MRISR_REQUIRE((reinterpret_cast<uintptr_t>(g->gn_stats) & 7u) == 0, "gemm: gn_stats must be 8-byte aligned");
+    p.gn_part = reinterpret_cast<float2*>(g->gn_stats);
+    p.ld_part = g->ld_stats;
+    p.part_phase_stride = g->M / 128;
   }
   cudaStream_t st = as_stream(stream);
   return pair ? dispatch_gemm<true>(BN, maps, p, st) : dispatch_gemm<false>(BN, maps, p, st);

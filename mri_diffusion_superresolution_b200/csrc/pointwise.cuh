@@ -88,10 +88,11 @@ __global__ void sched_step_kernel(const float4* __restrict__ x, const float4* __
 __global__ void sched_step_indexed_kernel(const float4* __restrict__ x, const float4* __restrict__ eps,
                                           const float4* __restrict__ lr, const float4* __restrict__ z_table,
                                           long long z_stride4, float4* out, long long n4,
-                                          const float* __restrict__ coef_table, const int* __restrict__ idx) {
+                                          const float* __restrict__ coef_table, const int* __restrict__ idx, int n_rows) {
   grid_dep_launch();
   grid_dep_wait();
   const int step = __ldg(idx);
+  if (step < 0 || step >= n_rows) __trap();  // a replayed graph ran past the table: fail loudly, never read out of bounds
   const float* coef = coef_table + 4 * step;
   const float c1 = __ldg(coef), c2 = __ldg(coef + 1), c3 = __ldg(coef + 2), c4 = __ldg(coef + 3);
   const bool use_lr = lr != nullptr && c3 != 0.f;
@@ -383,42 +384,96 @@ __global__ void groupnorm_apply_kernel(GnArgs a, const float2* __restrict__ part
   gn_apply_body<false>(a, partial, gamma, beta, eps, silu, out, stats_nslab, gn_sh);
 }
 
-// Single-launch GroupNorm: statistics pass, a per-batch-element barrier across the slab CTAs (all CTAs of the grid are
-// co-resident: the host sizes the grid from the occupancy calculator), then the normalise pass whose second read of x
-// mostly hits L2.  One launch and one DRAM read of x instead of two launches and two reads -- the two-kernel pair spent
-// ~20 us per norm in fixed latency and every byte costs ~160 pJ at the board power cap.  counters: [2 * batch] ints, zero
-// between launches (the last CTA through the barrier of a batch element resets its pair), owned by the library: ONE
-// stream per process may run GroupNorm at a time.  The spin is bounded (trap, never a hang).
-__global__ void groupnorm_fused_kernel(GnArgs a, float2* partial, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                       float eps, int silu, __nv_bfloat16* __restrict__ out, int* counters) {
+// GroupNorm whose statistics were produced by the epilogue of the GEMM / conv that wrote x (gemm_tcgen05.cuh, gn_part):
+// per 128-row block and channel (sum, sum of squares).  This kernel is the ONLY pass over x: it adds the block partials
+// of its batch element per channel (fixed order), folds them into the 32 group statistics (fp64), and streams
+// normalise(+SiLU) -- one read, one write, no statistics pass, no grid barrier, no library-owned state.
+// Partials of source s for batch element b: rows (ph * pstride + b * nblk + j), j < nblk, ph < nph (nph = 4 when x was
+// written by an up2x GEMM, whose 128-row blocks are per sub-pixel phase).
+struct GnPartArgs {
+  const float2* part[2];
+  long long ldp[2];
+  long long pstride[2];
+  int nph[2];
+  int nblk[2];
+};
+__global__ void groupnorm_apply_cpart_kernel(GnArgs a, GnPartArgs q, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                             float eps, int silu, __nv_bfloat16* __restrict__ out) {
   grid_dep_launch();
   grid_dep_wait();
-  extern __shared__ float gn_sh[];
-  gn_stats_body(a, partial, gn_sh);
-  const int b = blockIdx.y;
-  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  __threadfence();  // this CTA's partials are visible device-wide before its arrival is
-  __syncthreads();
-  if (tid == 0) {
-    int* arrive = counters + 2 * b;
-    int* depart = arrive + 1;
-    atomicAdd(arrive, 1);
-    const long long t0 = clock64();
-    while (*reinterpret_cast<volatile int*>(arrive) < a.nslab) {
-      if (clock64() - t0 > 4000000000LL) {
-        printf("mrisr: groupnorm barrier timeout (batch %d, %d of %d slabs arrived)\n", b, *reinterpret_cast<volatile int*>(arrive), a.nslab);
-        __trap();
+  extern __shared__ float gn_sh[];   // scale[C], shift[C] (first used as per-channel sum[C], sumsq[C])
+  __shared__ float s_mean[64], s_rstd[64];
+  const int C = a.c1 + a.c2;
+  const int vx = threadIdx.x, ry = threadIdx.y, R = blockDim.y;
+  const int b = blockIdx.y, slab = blockIdx.x;
+  const int tid = ry * blockDim.x + vx, nthr = blockDim.x * blockDim.y;
+  const int cpg = C / a.groups;
+  for (int c = tid; c < C; c += nthr) {
+    const int s = c < a.c1 ? 0 : 1;
+    const int cc = s == 0 ? c : c - a.c1;
+    float su[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int ph = 0; ph < q.nph[s]; ++ph) {
+      const float2* pp = q.part[s] + (ph * q.pstride[s] + static_cast<long long>(b) * q.nblk[s]) * q.ldp[s] + cc;
+      int j = 0;
+      for (; j + 3 < q.nblk[s]; j += 4) {   // four independent L2 loads in flight
+        float2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(pp + (j + u) * q.ldp[s]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { su[u] += v[u].x; sq[u] += v[u].y; }
       }
-      __nanosleep(64);
+      for (; j < q.nblk[s]; ++j) { const float2 v = __ldg(pp + j * q.ldp[s]); su[0] += v.x; sq[0] += v.y; }
     }
-    __threadfence();
-    if (atomicAdd(depart, 1) == a.nslab - 1) {  // every CTA of this batch element has left the spin: reset for the next launch
-      *reinterpret_cast<volatile int*>(arrive) = 0;
-      *reinterpret_cast<volatile int*>(depart) = 0;
-    }
+    gn_sh[c] = (su[0] + su[1]) + (su[2] + su[3]);
+    gn_sh[C + c] = (sq[0] + sq[1]) + (sq[2] + sq[3]);
   }
   __syncthreads();
-  gn_apply_body<true>(a, partial, gamma, beta, eps, silu, out, a.nslab, gn_sh);
+  for (int g = tid; g < a.groups; g += nthr) {
+    double su = 0.0, sq = 0.0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { su += gn_sh[c]; sq += gn_sh[C + c]; }
+    const double n = static_cast<double>(a.hw) * cpg;
+    const double mean = su / n;
+    double var = sq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[g] = static_cast<float>(mean);
+    s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += nthr) {
+    const int g = c / cpg;
+    const float sc = s_rstd[g] * __ldg(gamma + c);
+    gn_sh[c] = sc;
+    gn_sh[C + c] = __ldg(beta + c) - s_mean[g] * sc;
+  }
+  __syncthreads();
+  float2 sc[4], sh[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sc[j] = make_float2(gn_sh[vx * 8 + 2 * j], gn_sh[vx * 8 + 2 * j + 1]);
+    sh[j] = make_float2(gn_sh[C + vx * 8 + 2 * j], gn_sh[C + vx * 8 + 2 * j + 1]);
+  }
+  const int p0 = slab * a.pix_per_slab;
+  const int p1 = min(a.hw, p0 + a.pix_per_slab);
+  const bool hsrc = (vx < (a.c1 >> 3) ? a.h1 : a.h2) != 0;
+  auto emit = [&](int pix, const uint4& v) {
+    float2 f[4];
+    unpack8p_any(v, f, hsrc);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      f[j] = __ffma2_rn(f[j], sc[j], sh[j]);
+      if (silu) { f[j].x = silu_tanh(f[j].x); f[j].y = silu_tanh(f[j].y); }
+    }
+    reinterpret_cast<uint4*>(out + (static_cast<long long>(b) * a.hw + pix) * C)[vx] = pack8p(f);
+  };
+  int pix = p0 + ry;
+  for (; pix + 7 * R < p1; pix += 8 * R) {  // 8 independent 16-byte loads in flight per thread (no second pass to hide latency behind)
+    uint4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = gn_load(a, b, pix + u * R, vx);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) emit(pix + u * R, v[u]);
+  }
+  for (; pix < p1; pix += R) emit(pix, gn_load(a, b, pix, vx));
 }
 
 // Single-pass GroupNorm for the small levels (16x16, 8x8: a few hundred KB per image).  Groups are independent, so a CTA
@@ -887,10 +942,12 @@ __global__ void cast_f16_bf16_kernel(const __half* __restrict__ in, __nv_bfloat1
 // dst[0:n] = table[(*idx) * stride : ... + n]  -- selects the per-step row (time-embedding projections, step
 // coefficients) inside a replayed CUDA graph without host involvement; idx lives in device memory.
 __global__ void select_row_kernel(const float* __restrict__ table, const int* __restrict__ idx, long long stride,
-                                  float* __restrict__ dst, int n) {
+                                  float* __restrict__ dst, int n, int n_rows) {
   grid_dep_launch();
   grid_dep_wait();
-  const float* src = table + static_cast<long long>(__ldg(idx)) * stride;
+  const int row = __ldg(idx);
+  if (row < 0 || row >= n_rows) __trap();
+  const float* src = table + static_cast<long long>(row) * stride;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = __ldg(src + i);
 }
 __global__ void advance_index_kernel(int* idx) {

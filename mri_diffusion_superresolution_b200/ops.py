@@ -16,8 +16,22 @@ from . import _lib
 from ._lib import ACT_GEGLU, ACT_NONE, ACT_RELU, ACT_SILU, GemmArgs  # noqa: F401
 
 Tensor = torch.Tensor
-# bench.py sets this to a list to time every tensor-core kernel launch with CUDA events (executed flops, taps, ev0, ev1)
-GEMM_PROFILE = None
+# bench.py sets this to a list to time every kernel launch of the hot path with CUDA events on the launching stream:
+# entries are (class, algorithmic work [FLOP for tensor-bound classes, bytes for HBM-bound ones], ev0, ev1, detail)
+PROFILE = None
+
+
+def _launch(cls: str, work: float, t: Tensor, code_fn, what: str, kernels: int = 1, detail=None) -> None:
+    """Run one C-ABI call (``code_fn()`` returns its status code); under PROFILE, bracket it with CUDA events."""
+    if PROFILE is None:
+        _lib.check(code_fn(), what, kernels)
+        return
+    st = torch.cuda.current_stream(t.device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    _lib.check(code_fn(), what, kernels)
+    e1.record(st)
+    PROFILE.append((cls, float(work), e0, e1, detail))
 _DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 _H16 = (torch.bfloat16, torch.float16)     # 16-bit activation formats: bf16 everywhere, IEEE half for the residual stream
 F16_OUT, F16_RES1, F16_RES2, F16_AB = 1, 2, 4, 8
@@ -62,14 +76,18 @@ def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[T
          rowvec: Optional[Tensor] = None, rowvec_stride: int = 0, rows_per_batch: int = 0, act: int = ACT_NONE,
          res1: Optional[Tensor] = None, res2: Optional[Tensor] = None, n_store: Optional[int] = None,
          out_fp32: bool = False, conv: bool = False, stride: int = 1, out: Optional[Tensor] = None,
-         pad_mode: int = 0, out_dtype=None, _dbg: int = 0) -> Tensor:
+         pad_mode: int = 0, out_dtype=None, _dbg: int = 0, up2x: bool = False, gn_stats: bool = False) -> Tensor:
     """``act(concat_K(a1, a2) @ w.T + bias + rowvec[batch]) + res1 + res2`` on the tcgen05 kernel.
 
     16-bit tensors are bf16 by default; ``a1`` / ``a2`` / ``w`` may (all three) be float16, ``res1`` / ``res2`` may each be
     float16, and ``out_dtype=torch.float16`` stores IEEE half -- the UNet keeps its residual stream in fp16.
 
     GEMM mode: a1 ``[M, k1]`` (+ a2 ``[M, k2]``).  ``conv=True``: a1/a2 are NHWC ``[B, H, W, k]`` and ``w`` is
-    ``[N, 9*(k1+k2)]`` (3x3, pad 1, ``stride`` 1 or 2 -- the downsamplers, M = B*(H/2)*(W/2)).  Returns ``[M, n_store]`` (bf16, or fp32 if ``out_fp32``)."""
+    ``[N, 9*(k1+k2)]`` (3x3, pad 1, ``stride`` 1 or 2 -- the downsamplers, M = B*(H/2)*(W/2)).  Returns ``[M, n_store]`` (bf16, or fp32 if ``out_fp32``).
+    ``up2x=True`` (with ``conv=True``): nearest-2x upsample + 3x3 conv folded into four 2x2 sub-pixel convs; ``w`` is
+    ``packing.pack_upsample_fold`` ``[4N, 4*k1]``, the result is ``[B*2H*2W, N]`` (NHWC at the doubled resolution).
+    ``gn_stats=True``: the epilogue also writes the GroupNorm statistics of the output (per 128-row block and channel);
+    they ride on the returned tensor as ``._gn_part`` for ``ops.groupnorm`` (pass it along explicitly through views)."""
     lib = _lib.load()
     _cuda16(a1, "gemm.a1")
     _cuda(w, "gemm.w", a1.dtype)
@@ -84,7 +102,9 @@ def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[T
             raise ValueError("gemm(conv): a1 must be dense in B,H,W (channel-slice views allowed)")
         if stride not in (1, 2) or (stride == 2 and (H % 2 or W % 2)):
             raise ValueError("gemm(conv): stride must be 1 or 2 (even H, W)")
-        M, taps = B * (H // stride) * (W // stride), 9
+        M, taps = B * (H // stride) * (W // stride), (4 if up2x else 9)
+        if up2x and (stride != 1 or a2 is not None or res1 is not None or res2 is not None or out_fp32):
+            raise ValueError("gemm(up2x): no stride / second source / residuals / fp32 output")
         g.conv_stride = stride
         g.conv_pad_mode = pad_mode      # 1: zero padding on the bottom / right edge only (AutoencoderKL downsamplers)
         k2, lda2 = 0, 0
@@ -106,22 +126,25 @@ def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[T
             if a2.shape[0] != M:
                 raise ValueError("gemm: a1 and a2 must have the same number of rows")
             k2 = a2.shape[1]
-    if w.dim() != 2 or not w.is_contiguous() or w.shape[1] != taps * (k1 + k2):
+    if up2x and not conv:
+        raise ValueError("gemm: up2x is a conv mode")
+    if w.dim() != 2 or not w.is_contiguous() or w.shape[1] != taps * (k1 + k2) or (up2x and w.shape[0] % 4):
         raise ValueError(f"gemm: weight must be contiguous [N, {taps * (k1 + k2)}], got {tuple(w.shape)}")
-    N = w.shape[0]
+    N = w.shape[0] // 4 if up2x else w.shape[0]
+    m_out = 4 * M if up2x else M
     prod = N // 2 if act == ACT_GEGLU else N
     n_store = prod if n_store is None else n_store
     if out is None:
         odt = torch.float32 if out_fp32 else (out_dtype or torch.bfloat16)
         if odt not in (torch.float32,) + _H16:
             raise TypeError(f"gemm: unsupported out_dtype {odt}")
-        out = torch.empty((M, n_store), device=a1.device, dtype=odt)
+        out = torch.empty((m_out, n_store), device=a1.device, dtype=odt)
     else:
         if out_fp32:
             _cuda(out, "gemm.out", torch.float32)
         else:
             _cuda16(out, "gemm.out")
-        if out.shape[0] != M or out.shape[1] < n_store:
+        if out.shape[0] != m_out or out.shape[1] < n_store:
             raise ValueError("gemm: out has the wrong shape")
     if out.dtype == torch.float16:
         f16 |= F16_OUT
@@ -151,15 +174,26 @@ def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[T
     g.out, g.ldo, g.out_fp32 = out.data_ptr(), _rows(out, "gemm.out"), int(out_fp32)
     g.reserved = _dbg
     g.f16_flags = f16
-    if GEMM_PROFILE is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(torch.cuda.current_stream(a1.device))
-        _lib.check(lib.mrisr_gemm(C.byref(g), _stream(a1)), "mrisr_gemm")
-        e1.record(torch.cuda.current_stream(a1.device))
-        GEMM_PROFILE.append((2.0 * M * N * taps * (k1 + k2), taps, e0, e1, (M, N, taps * (k1 + k2), act, res1 is not None)))
-        return out
-    _lib.check(lib.mrisr_gemm(C.byref(g), _stream(a1)), "mrisr_gemm")
+    part = None
+    if gn_stats:
+        if M % 128 or out_fp32 or n_store != N:
+            raise ValueError("gemm: gn_stats needs M % 128 == 0, a 16-bit output and n_store == N")
+        part = torch.empty(((4 if up2x else 1) * (M // 128), N, 2), device=a1.device, dtype=torch.float32)
+        g.gn_stats, g.ld_stats = part.data_ptr(), N
+    _launch("conv3x3" if taps == 9 else "gemm", 2.0 * M * N * taps * (k1 + k2), a1,
+            lambda: lib.mrisr_gemm(C.byref(g), _stream(a1)), "mrisr_gemm",
+            detail=(M, N, taps * (k1 + k2), act, res1 is not None))
+    if part is not None:
+        out._gn_part = (part, 4 if up2x else 1, M // 128)      # (partials, sub-pixel phases, 128-row blocks per phase)
     return out
+
+
+def carry_stats(view: Tensor, src: Tensor) -> Tensor:
+    """Hand the producer's GroupNorm statistics (``gemm(..., gn_stats=True)``) to a reshaped view of its output."""
+    part = getattr(src, "_gn_part", None)
+    if part is not None:
+        view._gn_part = part
+    return view
 
 
 def attention(q: Tensor, k: Tensor, v: Tensor, batch: int, heads: int, kv_broadcast: bool = False) -> Tensor:
@@ -173,15 +207,20 @@ def attention(q: Tensor, k: Tensor, v: Tensor, batch: int, heads: int, kv_broadc
     nq = q.shape[0] // batch
     nk = k.shape[0] if kv_broadcast else k.shape[0] // batch
     o = torch.empty((q.shape[0], c), device=q.device, dtype=torch.bfloat16)
-    _lib.check(lib.mrisr_attention(q.data_ptr(), _rows(q, "q"), k.data_ptr(), _rows(k, "k"), v.data_ptr(), _rows(v, "v"),
-                                   o.data_ptr(), c, batch, nq, nk, heads, d, int(kv_broadcast), _stream(q)),
-               "mrisr_attention")
+    cls = "attn_self_d40" if (d == 40 and nk >= 128) else ("attn_self" if nk == nq else "attn_cross")
+    _launch(cls, 4.0 * batch * heads * nq * nk * d, q,
+            lambda: lib.mrisr_attention(q.data_ptr(), _rows(q, "q"), k.data_ptr(), _rows(k, "k"), v.data_ptr(), _rows(v, "v"),
+                                        o.data_ptr(), c, batch, nq, nk, heads, d, int(kv_broadcast), _stream(q)),
+            "mrisr_attention", detail=(batch, heads, nq, nk, d))
     return o
 
 
 def groupnorm(x1: Tensor, gamma: Tensor, beta: Tensor, groups: int, eps: float, silu: bool,
               x2: Optional[Tensor] = None) -> Tensor:
-    """GroupNorm(+SiLU) of the channel concat [x1 | x2]; x*: NHWC ``[B, H, W, c]`` (channel-slice views allowed)."""
+    """GroupNorm(+SiLU) of the channel concat [x1 | x2]; x*: NHWC ``[B, H, W, c]`` (channel-slice views allowed).
+
+    When every source carries the statistics its producing GEMM / conv emitted (``._gn_part``), this is ONE normalise pass
+    (``mrisr_groupnorm_apply_stats``: 1 read + 1 write); otherwise the self-contained two-kernel / small-image form."""
     lib = _lib.load()
     _cuda16(x1, "groupnorm.x1")
     B, H, W, c1 = x1.shape
@@ -191,12 +230,31 @@ def groupnorm(x1: Tensor, gamma: Tensor, beta: Tensor, groups: int, eps: float, 
         _cuda16(x2, "groupnorm.x2")
         c2, ld2 = x2.shape[3], x2.stride(2)
         f16 |= 2 if x2.dtype == torch.float16 else 0
-    out = torch.empty((B, H, W, c1 + c2), device=x1.device, dtype=torch.bfloat16)
+    hw, C = H * W, c1 + c2
+    out = torch.empty((B, H, W, C), device=x1.device, dtype=torch.bfloat16)
+    p1 = getattr(x1, "_gn_part", None)
+    p2 = getattr(x2, "_gn_part", None) if x2 is not None else None
+    small = hw <= 64 or (hw <= 256 and C <= 1280)          # the single-pass shared-memory kernel wins there (mrisr_groupnorm)
+    fused = (not small and p1 is not None and (x2 is None or p2 is not None) and x1.stride(2) == c1
+             and (x2 is None or ld2 == c2))
+    work = 4.0 * B * hw * C                                 # algorithmic bytes: one 2-byte read + one 2-byte write per element
+    if fused:
+        pt2, nph2, ps2 = p2 if p2 is not None else (None, 1, 0)
+        _launch("groupnorm", work, x1,
+                lambda: lib.mrisr_groupnorm_apply_stats(
+                    x1.data_ptr(), x1.stride(2), c1, p1[0].data_ptr(), p1[0].shape[1], p1[1], p1[2],
+                    _ptr(x2), ld2, c2, _ptr(pt2), (pt2.shape[1] if pt2 is not None else 0), nph2, ps2,
+                    B, hw, groups, _cuda(gamma, "gamma", torch.float32).data_ptr(),
+                    _cuda(beta, "beta", torch.float32).data_ptr(), float(eps), int(silu), out.data_ptr(), f16, _stream(x1)),
+                "mrisr_groupnorm_apply_stats")
+        return out
     ws = torch.empty((lib.mrisr_groupnorm_workspace_floats(B, groups),), device=x1.device, dtype=torch.float32)
-    _lib.check(lib.mrisr_groupnorm(x1.data_ptr(), x1.stride(2), c1, _ptr(x2), ld2, c2, B, H * W, groups,
-                                   _cuda(gamma, "gamma", torch.float32).data_ptr(),
-                                   _cuda(beta, "beta", torch.float32).data_ptr(), float(eps), int(silu),
-                                   out.data_ptr(), ws.data_ptr(), f16, _stream(x1)), "mrisr_groupnorm", kernels=2)
+    _launch("groupnorm", work, x1,
+            lambda: lib.mrisr_groupnorm(x1.data_ptr(), x1.stride(2), c1, _ptr(x2), ld2, c2, B, hw, groups,
+                                        _cuda(gamma, "gamma", torch.float32).data_ptr(),
+                                        _cuda(beta, "beta", torch.float32).data_ptr(), float(eps), int(silu),
+                                        out.data_ptr(), ws.data_ptr(), f16, _stream(x1)),
+            "mrisr_groupnorm", kernels=1 if small else 2)
     return out
 
 
@@ -205,8 +263,9 @@ def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5) -> Tens
     _cuda16(x, "layernorm.x")
     rows, c = x.shape
     out = torch.empty((rows, c), device=x.device, dtype=torch.bfloat16)
-    _lib.check(lib.mrisr_layernorm(x.data_ptr(), _rows(x, "x"), gamma.data_ptr(), beta.data_ptr(), float(eps),
-                                   out.data_ptr(), c, rows, c, int(x.dtype == torch.float16), _stream(x)), "mrisr_layernorm")
+    _launch("layernorm", 4.0 * rows * c, x,
+            lambda: lib.mrisr_layernorm(x.data_ptr(), _rows(x, "x"), gamma.data_ptr(), beta.data_ptr(), float(eps),
+                                        out.data_ptr(), c, rows, c, int(x.dtype == torch.float16), _stream(x)), "mrisr_layernorm")
     return out
 
 
@@ -244,9 +303,11 @@ def sched_step_indexed(x: Tensor, eps: Tensor, coef_table: Tensor, idx: Tensor, 
     if z_table is not None:
         _cuda(z_table, "sched_step_indexed.z_table", torch.float32)
         zs = z_table.stride(0)
-    _lib.check(lib.mrisr_sched_step_indexed(x.data_ptr(), eps.data_ptr(), _ptr(lr), _ptr(z_table), zs, out.data_ptr(),
-                                            x.numel(), coef_table.data_ptr(), idx.data_ptr(), _stream(x)),
-               "mrisr_sched_step_indexed")
+    nstreams = 3 + (lr is not None) + (z_table is not None)       # reads of x, eps (+lr, +z) and the write, fp32
+    _launch("sched_step", 4.0 * nstreams * x.numel(), x,
+            lambda: lib.mrisr_sched_step_indexed(x.data_ptr(), eps.data_ptr(), _ptr(lr), _ptr(z_table), zs, out.data_ptr(),
+                                                 x.numel(), coef_table.data_ptr(), idx.data_ptr(), coef_table.shape[0],
+                                                 _stream(x)), "mrisr_sched_step_indexed")
     return out
 
 
@@ -289,7 +350,7 @@ def select_row(table: Tensor, idx: Tensor, dst: Tensor) -> Tensor:
     lib = _lib.load()
     _cuda(table, "select_row.table", torch.float32)
     _cuda(idx, "select_row.idx", torch.int32)
-    _lib.check(lib.mrisr_select_row(table.data_ptr(), idx.data_ptr(), table.stride(0), dst.data_ptr(), dst.numel(),
+    _lib.check(lib.mrisr_select_row(table.data_ptr(), idx.data_ptr(), table.shape[0], table.stride(0), dst.data_ptr(), dst.numel(),
                                     _stream(table)), "mrisr_select_row")
     return dst
 

@@ -24,6 +24,29 @@ def pack_conv3x3(w: Tensor) -> Tensor:
     return w.permute(0, 2, 3, 1).reshape(co, 9 * ci).contiguous()
 
 
+def pack_upsample_fold(w: Tensor) -> Tensor:
+    """Nearest-2x upsample followed by a 3x3 pad-1 convolution (diffusers ``Upsample2D``) folded into four 2x2 sub-pixel
+    convolutions over the LOW-resolution input: output row 2y+a reads upsampled rows 2y+a-1 .. 2y+a+1, i.e. input rows
+    {y-1, y, y} for a = 0 and {y, y, y+1} for a = 1 -- the filter taps that land on the same input row are summed (in
+    fp32, before the single rounding to the storage type).  [Cout, Cin, 3, 3] -> [4*Cout, 4*Cin]: rows phase-major
+    (phase = 2a + b), k = (ty*2 + tx)*Cin + c with input offset (ty - 1 + a, tx - 1 + b)."""
+    co, ci, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    w = w.float()
+    groups = {0: ([0], [1, 2]), 1: ([0, 1], [2])}     # phase bit -> original taps landing on 2x2 tap 0 / tap 1
+    out = torch.empty((4, co, 4, ci), dtype=torch.float32, device=w.device)
+    for a in (0, 1):
+        for b in (0, 1):
+            for ty in (0, 1):
+                for tx in (0, 1):
+                    acc = torch.zeros((co, ci), dtype=torch.float32, device=w.device)
+                    for ky in groups[a][ty]:
+                        for kx in groups[b][tx]:
+                            acc += w[:, :, ky, kx]
+                    out[2 * a + b, :, ty * 2 + tx, :] = acc
+    return out.reshape(4 * co, 4 * ci).contiguous()
+
+
 def pack_conv1x1(w: Tensor) -> Tensor:
     return w.reshape(w.shape[0], w.shape[1]).contiguous()
 

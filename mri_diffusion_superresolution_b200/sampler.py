@@ -121,7 +121,10 @@ class SliceSampler:
         if self.controlnet is not None:
             self.controlnet.set_encoder_hidden_states(encoder_hidden_states)
             self.controlnet.set_condition(img, force=True)     # once per batch of slices: t-invariant
-        shape = (B, h, w, feats is not None, tuple(encoder_hidden_states.shape))
+        # the captured graph bakes in the addresses of the prompt K/V caches, the ControlNet condition embedding and the
+        # packed weights: their owners bump `generation` whenever one of those buffers is reallocated
+        shape = (B, h, w, feats is not None, tuple(encoder_hidden_states.shape), self.unet.generation,
+                 self.controlnet.generation if self.controlnet is not None else -1)
         if self._shape != shape:
             self._alloc(B, h, w, feats)
             self._shape = shape

@@ -23,8 +23,8 @@ from typing import Dict, List, Optional, Sequence, Tuple, Union
 import torch
 
 from . import ops
-from .packing import (LORA_PAD, pack_conv1x1, pack_conv3x3, pack_geglu, pack_lora_down, pack_lora_up, pad_cols,
-                      pad_rows, pad_to)
+from .packing import (LORA_PAD, pack_conv1x1, pack_conv3x3, pack_geglu, pack_lora_down, pack_lora_up, pack_upsample_fold,
+                      pad_cols, pad_rows, pad_to)
 
 Tensor = torch.Tensor
 
@@ -119,7 +119,8 @@ class UNet2DConditionB200:
                                       attention_head_dim=c.num_heads, norm_num_groups=c.norm_num_groups)
         self.dtype = torch.bfloat16
         self._loaded = False
-        self._ehs_key = None
+        self._ehs_key = None          # (strong reference to the keyed tensor, its _version): identity, not address
+        self.generation = 0           # bumped whenever a buffer a captured CUDA graph may hold is reallocated
         self._temb_cache: Dict[Tuple, Tensor] = {}
         for ch in c.block_out_channels:
             if ch % 64 or ch % c.norm_num_groups or (ch // c.num_heads) not in (8, 16, 32, 40, 64, 80, 160):
@@ -271,8 +272,11 @@ class UNet2DConditionB200:
                     if up_attn[i]:
                         blk["attn"].append(attn(f"up_blocks.{i}.attentions.{j}", rev[i]))
                 if i < nlev - 1:
-                    blk["us"] = (self._dev(pack_conv3x3(get(f"up_blocks.{i}.upsamplers.0.conv.weight")), bf),
-                                 self._dev(get(f"up_blocks.{i}.upsamplers.0.conv.bias"), f32))
+                    # nearest-2x + 3x3 conv folded into four 2x2 sub-pixel convs on the low-resolution stream (its format)
+                    # (the unfolded filter serves images of fewer than 32 pixels, below the fold's store-box granularity)
+                    blk["us"] = (self._dev(pack_upsample_fold(get(f"up_blocks.{i}.upsamplers.0.conv.weight")), sd_t),
+                                 self._dev(get(f"up_blocks.{i}.upsamplers.0.conv.bias"), f32),
+                                 self._dev(pack_conv3x3(get(f"up_blocks.{i}.upsamplers.0.conv.weight")), bf))
                 self.up.append(blk)
             self.n_out_w, self.n_out_b = self._dev(get("conv_norm_out.weight"), f32), self._dev(get("conv_norm_out.bias"), f32)
             self.w_conv_out = self._dev(pad_rows(pack_conv3x3(get("conv_out.weight").float()), 64), bf)
@@ -292,6 +296,9 @@ class UNet2DConditionB200:
             raise KeyError(f"unexpected keys in state_dict: {unexpected[:8]}{' ...' if len(unexpected) > 8 else ''}")
         self._loaded = True
         self._ehs_key = None
+        self.generation += 1
+        for a in self.all_attn():
+            a.kv_cache = None
         self._temb_cache.clear()
         return SimpleNamespace(missing_keys=[], unexpected_keys=unexpected)
 
@@ -323,8 +330,9 @@ class UNet2DConditionB200:
         res_srdiff.py:67,75)."""
         if ehs.dim() != 3 or ehs.shape[2] != self.cfg.cross_attention_dim:
             raise ValueError(f"encoder_hidden_states must be [B, L, {self.cfg.cross_attention_dim}]")
-        key = (ehs.data_ptr(), tuple(ehs.shape), ehs._version)
-        if key == self._ehs_key:
+        # The cache key is the tensor OBJECT (held strongly, so its address cannot be recycled by the allocator) plus its
+        # version counter: a fresh tensor that happens to land on a freed block's address must not hit the cache.
+        if self._ehs_key is not None and self._ehs_key[0] is ehs and self._ehs_key[1] == ehs._version:
             return
         ctx = ops.cast(ehs.to(self.device).contiguous(), torch.bfloat16) if ehs.dtype == torch.float32 else \
             ehs.to(self.device, torch.bfloat16).contiguous()
@@ -333,8 +341,10 @@ class UNet2DConditionB200:
             t = ops.gemm(ctx2, a.a_kv2) if a.a_kv2 is not None else None
             # reuse the existing buffer when the shape is unchanged: a captured CUDA graph holds its address
             old = a.kv_cache[0] if (a.kv_cache is not None and a.kv_cache[1:] == (ctx.shape[0], ctx.shape[1])) else None
+            if old is None:
+                self.generation += 1
             a.kv_cache = (ops.gemm(ctx2, a.w_kv2, a2=t, out=old), ctx.shape[0], ctx.shape[1])
-        self._ehs_key = key
+        self._ehs_key = (ehs, ehs._version)
 
     # ---- blocks ---------------------------------------------------------------------------------------------------
     def _resnet(self, r: _Resnet, x1: Tensor, x2: Optional[Tensor], temb: Tensor, temb_stride: int,
@@ -342,19 +352,22 @@ class UNet2DConditionB200:
         c = self.cfg
         B, H, W, _ = x1.shape
         M = B * H * W
+        # Every GroupNorm input is the output of a GEMM / conv of this network: that producer's epilogue already reduced the
+        # statistics (gn_stats), so each norm below is one normalise+SiLU pass.
+        stats = (H * W) % 128 == 0
         h = ops.groupnorm(x1, r.n1w, r.n1b, c.norm_num_groups, c.norm_eps, True, x2=x2)
         # conv1's output is only ever read by norm2: stored in the stream's format too (3 more significand bits for free)
         h = ops.gemm(h, r.w1, bias=r.b1, rowvec=temb[:, r.temb_off:], rowvec_stride=temb_stride, rows_per_batch=H * W,
-                     conv=True, out_dtype=self.stream_dtype)
-        h = ops.groupnorm(h.view(B, H, W, r.cout), r.n2w, r.n2b, c.norm_num_groups, c.norm_eps, True)
+                     conv=True, out_dtype=self.stream_dtype, gn_stats=stats)
+        h = ops.groupnorm(ops.carry_stats(h.view(B, H, W, r.cout), h), r.n2w, r.n2b, c.norm_num_groups, c.norm_eps, True)
         sd = self.stream_dtype
         if r.wsc is not None:
             sc = ops.gemm(x1.view(M, x1.shape[3]), r.wsc, a2=None if x2 is None else x2.view(M, x2.shape[3]), bias=r.bsc,
                           out_dtype=sd)
         else:
             sc = x1.view(M, r.cin)
-        out = ops.gemm(h, r.w2, bias=r.b2, res1=sc, res2=extra_res, conv=True, out_dtype=sd)
-        return out.view(B, H, W, r.cout)
+        out = ops.gemm(h, r.w2, bias=r.b2, res1=sc, res2=extra_res, conv=True, out_dtype=sd, gn_stats=stats)
+        return ops.carry_stats(out.view(B, H, W, r.cout), out)
 
     def _lora_gemm(self, x: Tensor, a_w: Optional[Tensor], w: Tensor, **kw) -> Tensor:
         t = ops.gemm(x, a_w) if a_w is not None else None
@@ -384,8 +397,8 @@ class UNet2DConditionB200:
         y = ops.layernorm(h, a.ln3[0], a.ln3[1], 1e-5)
         f = ops.gemm(y, a.w_ff1, bias=a.b_ff1, act=ops.ACT_GEGLU)
         h = ops.gemm(f, a.w_ff2, bias=a.b_ff2, res1=h, out_dtype=sd)
-        out = ops.gemm(h, a.w_out, bias=a.b_out, res1=xr, res2=extra_res, out_dtype=sd)
-        return out.view(B, H, W, C)
+        out = ops.gemm(h, a.w_out, bias=a.b_out, res1=xr, res2=extra_res, out_dtype=sd, gn_stats=(H * W) % 128 == 0)
+        return ops.carry_stats(out.view(B, H, W, C), out)
 
     def _to_nhwc(self, t: Tensor, B: int, H: int, W: int, C: int) -> Tensor:
         """Additional residual given as NCHW (reference convention) -> bf16 [B*H*W, C]; zero-copy when the tensor is
@@ -439,7 +452,9 @@ class UNet2DConditionB200:
         B, _, H, W = x32.shape
         ch = c.block_out_channels
         cols = ops.im2col_first(x32, self.kin)
-        s = ops.gemm(cols, self.w_conv_in, bias=self.b_conv_in, res1=conv_in_res, out_dtype=self.stream_dtype).view(B, H, W, ch[0])
+        s0 = ops.gemm(cols, self.w_conv_in, bias=self.b_conv_in, res1=conv_in_res, out_dtype=self.stream_dtype,
+                      gn_stats=(H * W) % 128 == 0)
+        s = ops.carry_stats(s0.view(B, H, W, ch[0]), s0)
         tap("conv_in", s)
         skips = [s]
         h_, w_ = H, W
@@ -457,7 +472,8 @@ class UNet2DConditionB200:
             if blk["ds"] is not None:
                 wd, bd = blk["ds"]
                 h_, w_ = h_ // 2, w_ // 2
-                s = ops.gemm(s, wd, bias=bd, conv=True, stride=2, out_dtype=self.stream_dtype).view(B, h_, w_, ch[i])  # stride-2 TMA boxes
+                s0 = ops.gemm(s, wd, bias=bd, conv=True, stride=2, out_dtype=self.stream_dtype, gn_stats=(h_ * w_) % 128 == 0)  # stride-2 TMA boxes
+                s = ops.carry_stats(s0.view(B, h_, w_, ch[i]), s0)
                 tap(f"down_blocks.{i}.downsamplers.0", s)
                 skips.append(s)
         return s, skips
@@ -511,9 +527,14 @@ class UNet2DConditionB200:
                     s = self._transformer(blk["attn"][j], s)
                 tap(f"up_blocks.{i}.{j}", s)
             if blk["us"] is not None:
-                wu, bu = blk["us"]
+                wu, bu, wu_plain = blk["us"]
                 b_, hh, ww, cc = s.shape
-                s = ops.gemm(ops.upsample2x(s), wu, bias=bu, conv=True, out_dtype=self.stream_dtype).view(b_, 2 * hh, 2 * ww, cc)
+                if hh * ww >= 32:
+                    # Upsample2D: the 4x-sized nearest-neighbour intermediate is never materialised (four sub-pixel 2x2 convs)
+                    s0 = ops.gemm(s, wu, bias=bu, conv=True, up2x=True, out_dtype=self.stream_dtype, gn_stats=(hh * ww) % 128 == 0)
+                else:
+                    s0 = ops.gemm(ops.upsample2x(s), wu_plain, bias=bu, conv=True, out_dtype=self.stream_dtype)
+                s = ops.carry_stats(s0.view(b_, 2 * hh, 2 * ww, cc), s0)
                 tap(f"up_blocks.{i}.upsamplers.0", s)
         h = ops.groupnorm(s, self.n_out_w, self.n_out_b, c.norm_num_groups, c.norm_eps, True)
         o = ops.gemm(h, self.w_conv_out, bias=self.b_conv_out, n_store=c.out_channels, out_fp32=True, conv=True)

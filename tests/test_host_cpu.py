@@ -21,7 +21,7 @@ def test_abi_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.mrisr_abi_version() == 4
+    assert lib.mrisr_abi_version() == _lib.ABI_VERSION
     assert lib.mrisr_gemm_block_n(320, 0) == 160 and lib.mrisr_gemm_block_n(2560, 3) == 256 and lib.mrisr_gemm_block_n(100, 0) == 0
 
 
@@ -203,3 +203,27 @@ def test_no_cpu_path_widened_rows():
     with pytest.raises(RuntimeError):
         cn(torch.zeros(1, 4, 64, 64), 10, encoder_hidden_states=torch.zeros(1, 77, 768), controlnet_cond=torch.zeros(1, 3, 512, 512))
     assert cn.config.conditioning_embedding_out_channels == (16, 32, 96, 256) and cn.stream_dtype == torch.float16
+
+
+def test_upsample_fold_weights_are_exact():
+    """packing.pack_upsample_fold: four 2x2 sub-pixel filters == nearest-2x upsample + 3x3 pad-1 conv (fp64, exact)."""
+    import torch.nn.functional as F
+    from mri_diffusion_superresolution_b200.packing import pack_upsample_fold
+    g = torch.Generator().manual_seed(4)
+    co, ci, H, W = 5, 3, 6, 4
+    w = torch.randn(co, ci, 3, 3, generator=g, dtype=torch.float64)
+    x = torch.randn(2, ci, H, W, generator=g, dtype=torch.float64)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, padding=1)
+    wf = pack_upsample_fold(w.float()).double().view(4, co, 4, ci)   # float32 sums of the taps: compare at 1e-6
+    out = torch.zeros_like(ref)
+    xp = F.pad(x, (1, 1, 1, 1))
+    for a in (0, 1):
+        for b in (0, 1):
+            acc = torch.zeros(2, co, H, W, dtype=torch.float64)
+            for ty in (0, 1):
+                for tx in (0, 1):
+                    dy, dx = ty - 1 + a, tx - 1 + b
+                    patch = xp[:, :, 1 + dy:1 + dy + H, 1 + dx:1 + dx + W]
+                    acc += torch.einsum("oc,bchw->bohw", wf[2 * a + b, :, ty * 2 + tx, :], patch)
+            out[:, :, a::2, b::2] = acc
+    assert (out - ref).abs().max().item() < 1e-5

@@ -262,10 +262,10 @@ def test_groupnorm(ops, B, HW, C1, C2, silu, eps):
 
 
 @pytest.mark.parametrize("B,HW,C", [(32, 4096, 320), (64, 64, 1280), (1500, 4, 64), (7, 1024, 640)])
-def test_groupnorm_single_launch_barrier(ops, B, HW, C):
-    """The single-launch GroupNorm (statistics -> per-batch barrier -> normalise) at a full-machine grid, at a batch that
-    leaves one or two slabs per element, and at a batch beyond the co-resident capacity (two-kernel fallback); repeated
-    calls must be bit-identical (the barrier counters reset themselves, statistics are order-deterministic)."""
+def test_groupnorm_self_contained_repeatable(ops, B, HW, C):
+    """The self-contained GroupNorm (statistics kernel + normalise kernel, or the single-pass small-image kernel) at a
+    full-machine grid, at one or two slabs per element and at a very large batch; repeated calls must be bit-identical
+    (statistics are order-deterministic, no library-owned state)."""
     h = int(math.isqrt(HW))
     x = _bf((B, h, h, C), 70) * 1.5 + 0.25
     gamma, beta = _f32((C,), 71) * 0.1 + 1, _f32((C,), 72) * 0.1
@@ -470,3 +470,94 @@ def test_groupnorm_small_single_pass(ops, B, HW, C1, C2, h1, h2):
     assert (out.float() - ref).abs().max().item() < 0.03
     assert _rel(out, ref) < 4e-3
     assert torch.equal(out, ops.groupnorm(x1, gamma, beta, 32, 1e-5, True, x2=x2))
+
+
+# ------------------------------------------------------------------------------------------------ fused GroupNorm statistics
+@pytest.mark.parametrize("M,N,K,f16", [(4096, 320, 320, True), (8192, 640, 1344, False), (131072, 320, 384, True), (1024, 1280, 640, True),
+                                       (2048, 64, 64, True), (4096, 192, 128, False), (4096, 256, 64, True), (4096, 128, 64, True)])
+def test_gemm_epilogue_groupnorm_statistics(ops, M, N, K, f16):
+    """gn_stats: per 128-row block and output channel, (sum, sum of squares) of the STORED output, bit-reproducible."""
+    a = _bf((M, K), 80)
+    w = _bf((N, K), 81, 1.0 / math.sqrt(K))
+    bias = _f32((N,), 82)
+    r = _h16((M, N), 83) if f16 else _bf((M, N), 83)
+    od = torch.float16 if f16 else torch.bfloat16
+    out = ops.gemm(a, w, bias=bias, res1=r, out_dtype=od, gn_stats=True)
+    part, nph, nblk = out._gn_part
+    assert nph == 1 and nblk == M // 128 and tuple(part.shape) == (M // 128, N, 2)
+    plain = ops.gemm(a, w, bias=bias, res1=r, out_dtype=od)
+    assert torch.equal(out, plain)                                       # statistics do not perturb the output
+    y = out.float().view(M // 128, 128, N)
+    ref = torch.stack([y.sum(1), (y * y).sum(1)], -1)
+    assert (part - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+    assert _rel(part, ref) < 1e-4
+    again = ops.gemm(a, w, bias=bias, res1=r, out_dtype=od, gn_stats=True)
+    assert torch.equal(again._gn_part[0], part)
+
+
+@pytest.mark.parametrize("B,H,C1,C2,silu", [(2, 64, 320, 0, True), (2, 32, 640, 320, True), (3, 16, 1280, 1280, True), (32, 64, 320, 0, False),
+                                            (2, 32, 64, 64, True)])
+def test_groupnorm_fused_with_producer_statistics(ops, B, H, C1, C2, silu):
+    """conv -> GroupNorm(+SiLU) where the conv epilogue supplies the statistics and the norm is one pass, against
+    torch.group_norm of the stored conv outputs (and against the self-contained kernels)."""
+    from mri_diffusion_superresolution_b200.packing import pack_conv3x3
+    outs, parts = [], []
+    for i, c in enumerate([C1] + ([C2] if C2 else [])):
+        x = _bf((B, H, H, c), 90 + i)
+        w = _bf((c, c, 3, 3), 92 + i, 1.0 / math.sqrt(9 * c))
+        bias = _f32((c,), 94 + i) + 0.3
+        y = ops.gemm(x, pack_conv3x3(w), bias=bias, conv=True, out_dtype=torch.float16 if i == 0 else torch.bfloat16, gn_stats=True)
+        outs.append(ops.carry_stats(y.view(B, H, H, c), y))
+    C = C1 + C2
+    gamma, beta = _f32((C,), 96) * 0.1 + 1, _f32((C,), 97) * 0.1
+    x2 = outs[1] if C2 else None
+    fused = ops.groupnorm(outs[0], gamma, beta, 32, 1e-5, silu, x2=x2)
+    plain = ops.groupnorm(outs[0].clone(), gamma, beta, 32, 1e-5, silu, x2=None if x2 is None else x2.clone())   # clones carry no statistics
+    xin = outs[0].float() if x2 is None else torch.cat([outs[0].float(), x2.float()], -1)
+    ref = F.group_norm(xin.permute(0, 3, 1, 2), 32, gamma, beta, 1e-5)
+    ref = (F.silu(ref) if silu else ref).permute(0, 2, 3, 1)
+    assert _rel(fused, ref) < 4e-3
+    assert (fused.float() - plain.float()).abs().max().item() < 0.04
+    assert torch.equal(fused, ops.groupnorm(outs[0], gamma, beta, 32, 1e-5, silu, x2=x2))
+
+
+@pytest.mark.parametrize("B,H,C,N,f16,stats", [(2, 8, 64, 64, False, False), (2, 16, 128, 128, True, True), (1, 32, 640, 640, True, True),
+                                               (3, 16, 1280, 1280, True, True), (2, 8, 1280, 1280, False, False)])
+def test_upsample_conv_folded(ops, B, H, C, N, f16, stats):
+    """taps == 4: nearest-2x upsample + 3x3 conv as four sub-pixel 2x2 convs, against F.interpolate + F.conv2d; the
+    epilogue statistics of the (phase-strided) output feed a one-pass GroupNorm."""
+    from mri_diffusion_superresolution_b200.packing import pack_upsample_fold
+    dt = torch.float16 if f16 else torch.bfloat16
+    x = (_h16 if f16 else _bf)((B, H, H, C), 100)
+    w = _bf((N, C, 3, 3), 101, 1.0 / math.sqrt(9 * C))
+    bias = _f32((N,), 102)
+    wf = pack_upsample_fold(w.float()).to(dt)
+    out = ops.gemm(x, wf, bias=bias, conv=True, up2x=True, out_dtype=torch.float16, gn_stats=stats)
+    assert tuple(out.shape) == (B * 4 * H * H, N)
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    ref = F.conv2d(up, w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(B * 4 * H * H, N)
+    assert _rel(out, ref) < 5e-3
+    if stats:
+        v = ops.carry_stats(out.view(B, 2 * H, 2 * H, N), out)
+        gamma, beta = _f32((N,), 103) * 0.1 + 1, _f32((N,), 104) * 0.1
+        got = ops.groupnorm(v, gamma, beta, 32, 1e-5, True)
+        want = F.silu(F.group_norm(out.float().view(B, 2 * H, 2 * H, N).permute(0, 3, 1, 2), 32, gamma, beta, 1e-5)).permute(0, 2, 3, 1)
+        assert _rel(got, want) < 4e-3
+
+
+def test_groupnorm_two_streams_concurrently(ops):
+    """No library-owned GroupNorm state: two streams running norms at the same time give the single-stream results."""
+    xs = [_bf((32, 64, 64, 320), 110 + i) * (1 + i) for i in range(2)]
+    gamma, beta = _f32((320,), 112) * 0.1 + 1, _f32((320,), 113) * 0.1
+    want = [ops.groupnorm(x, gamma, beta, 32, 1e-5, True) for x in xs]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    got = [[], []]
+    for rep in range(8):
+        for i, st in enumerate(streams):
+            with torch.cuda.stream(st):
+                got[i].append(ops.groupnorm(xs[i], gamma, beta, 32, 1e-5, True))
+    torch.cuda.synchronize()
+    for i in range(2):
+        for g in got[i]:
+            assert torch.equal(g, want[i])
