@@ -223,6 +223,59 @@ int mrisr_eval_metrics(const float* pred, const float* target, int N, int H, int
 int mrisr_slice_volume(const float* vol_hwd, int H, int W, int D, int map_intensity, float a_min, float a_max, float pad_value,
                        float* out, int TH, int TW, void* stream);
 
+/* --- LoRA fine-tune step (BASELINE config 4): forward process src/adapters/res_srdiff.py:7-25 (mrisr_res_shift with
+ * per-sample timesteps), epsilon-prediction MSE and the optimizer settings of notebooks/ResDif_execution.ipynb:599-633 (AdamW
+ * beta 0.9 / 0.999, weight decay 1e-2, eps 1e-8, max_grad_norm 1.0, fp16 mixed precision).  Gradients flow through the frozen
+ * UNet into the LoRA A / B matrices only: every dgrad contraction is an mrisr_gemm with transposed / tap-flipped weights; the
+ * entry points below are the rest of the backward pass.  Gradient activations are IEEE half under a static loss scale. */
+
+/* Backward of mrisr_groupnorm: dz [B,hw,c1+c2] (half, dense) -> dx1 [B*hw,c1] (row pitch lddx1), dx2 [B*hw,c2] (row pitch
+ * lddx2), half -- they may be the two column ranges of one buffer.  gamma / beta are frozen (no parameter gradients). */
+int mrisr_groupnorm_backward(const void* x1, int64_t ld1, int c1, const void* x2, int64_t ld2, int c2, const void* dz, int batch, int hw,
+                             int groups, const float* gamma, const float* beta, float eps, int silu, void* dx1, int64_t lddx1, void* dx2,
+                             int64_t lddx2, int f16_flags, void* stream);
+/* Backward of mrisr_layernorm: dx = dLN(dy) (+ dres, the gradient arriving over the residual connection); all gradients half. */
+int mrisr_layernorm_backward(const void* x, int64_t ldx, int x_f16, const void* dy, const float* gamma, float eps, const void* dres,
+                             void* dx, int rows, int C, void* stream);
+/* diffusers GEGLU un-fused for training: pre bf16 [M, 2F] = [hidden | gate] (kept for backward) -> out bf16 [M, F]; and its backward. */
+int mrisr_geglu_forward(const void* pre, void* out, int64_t M, int F, void* stream);
+int mrisr_geglu_backward(const void* pre, const void* df, void* dpre, int64_t M, int F, void* stream);
+/* half NHWC [B,h,w,C] -> [B,2h,2w,C] with the values at even (y, x) and zeros elsewhere: the transposed stride-2 convolution
+ * (backward of the UNet downsamplers) is then a stride-1 mrisr_gemm conv with the flipped filter. */
+int mrisr_zero_insert2x(const void* in, void* out, int B, int h, int w, int C, void* stream);
+/* half NHWC [B,2h,2w,C] -> [B,h,w,C], sum over each 2x2 block: backward of the nearest-2x upsample (diffusers Upsample2D). */
+int mrisr_sumpool2(const void* in, void* out, int B, int h, int w, int C, void* stream);
+/* loss = mean((pred - target)^2) over fp32 NCHW [B,C,HW]; dout = half NHWC [B,HW,cpad] = (pred - target) * grad_scale in the
+ * first C channels, zeros in the padding (grad_scale = 2 * loss_scale / (B*C*HW)).  workspace >= 1024 floats. */
+int mrisr_mse_grad(const float* pred, const float* target, int B, int C, int HW, int cpad, float grad_scale, void* dout, float* workspace,
+                   float* loss, void* stream);
+/* out fp32 [64, Q] = scale * X^T Y, X [M, 64] (row stride ldx), Y [M, Q] (row stride ldy), each bf16 or half: the rank-16 LoRA
+ * weight gradients (dA_stack = u^T x, d(sB)^T = t^T dy).  Deterministic (fixed-order two-stage reduction over M). */
+int64_t mrisr_xty64_workspace_floats(int M, int Q);
+int mrisr_xty64(const void* X, int64_t ldx, int x_f16, const void* Y, int64_t ldy, int y_f16, int M, int Q, float scale, float* workspace,
+                float* out, void* stream);
+/* Backward of mrisr_attention (flash-style, P is recomputed): q/k/v/o bf16 as in the forward call, d_o / dq / dk / dv half;
+ * stats_ws >= 2*batch*heads*nq floats (row log-sum-exp and rowsum(dO*O), recomputed here). d in {8,16,40,80,160}. */
+int mrisr_attention_backward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o, int64_t ldo,
+                             const void* d_o, int64_t lddo, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                             float* stats_ws, int batch, int nq, int nk, int heads, int d, void* stream);
+/* One trainable tensor [rows, cols]: fp32 master p and AdamW moments m, v (dense); its gradient as a strided window
+ * grad(i,j) = g[i*g_sr + j*g_sc] * g_scale of an mrisr_xty64 result; up to two packed 16-bit destinations that receive
+ * p(i,j) * scale after the update (the forward GEMM's and the dgrad GEMM's operand), so no re-packing pass exists. */
+typedef struct mrisr_adam_desc {
+  float* p; float* m; float* v;
+  const float* g; int64_t g_sr, g_sc; float g_scale;
+  int32_t rows, cols;
+  void* d1; int64_t d1_sr, d1_sc; float d1_scale; int32_t d1_f16;
+  void* d2; int64_t d2_sr, d2_sc; float d2_scale; int32_t d2_f16;
+} mrisr_adam_desc;
+/* out2 = {global gradient 2-norm over all descriptors, clip coefficient min(1, max_norm / (norm + 1e-6))} (torch clip_grad_norm_);
+ * desc is a DEVICE array; workspace >= n_desc floats. */
+int mrisr_grad_sqnorm(const mrisr_adam_desc* desc, int n_desc, float max_norm, float* workspace, float* out2, void* stream);
+/* torch.optim.AdamW (decoupled weight decay) over all descriptors; clip = out2 of mrisr_grad_sqnorm or NULL; step counts from 1. */
+int mrisr_adamw(const mrisr_adam_desc* desc, int n_desc, const float* clip, float lr, float beta1, float beta2, float eps, float weight_decay,
+                int step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,6 +36,17 @@ class GemmArgs(C.Structure):
     ]
 
 
+class AdamDesc(C.Structure):
+    """mrisr_adam_desc (include/mrisr_b200.h)."""
+    _fields_ = [
+        ("p", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p),
+        ("g", C.c_void_p), ("g_sr", C.c_int64), ("g_sc", C.c_int64), ("g_scale", C.c_float),
+        ("rows", C.c_int32), ("cols", C.c_int32),
+        ("d1", C.c_void_p), ("d1_sr", C.c_int64), ("d1_sc", C.c_int64), ("d1_scale", C.c_float), ("d1_f16", C.c_int32),
+        ("d2", C.c_void_p), ("d2_sr", C.c_int64), ("d2_sc", C.c_int64), ("d2_scale", C.c_float), ("d2_f16", C.c_int32),
+    ]
+
+
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
 # name -> (restype, argtypes); must list every symbol include/mrisr_b200.h declares.
@@ -72,6 +83,18 @@ PROTOTYPES = {
     "mrisr_gaussian_sample": (_I, [_P, _P, _P, _I, _I, _I, _F, _P]),
     "mrisr_eval_metrics_workspace_floats": (_L, [_I, _I, _I]),
     "mrisr_eval_metrics": (_I, [_P, _P, _I, _I, _I, _F, _F, _I, _P, _P, _P, _P]),
+    "mrisr_groupnorm_backward": (_I, [_P, _L, _I, _P, _L, _I, _P, _I, _I, _I, _P, _P, _F, _I, _P, _L, _P, _L, _I, _P]),
+    "mrisr_layernorm_backward": (_I, [_P, _L, _I, _P, _P, _F, _P, _P, _I, _I, _P]),
+    "mrisr_geglu_forward": (_I, [_P, _P, _L, _I, _P]),
+    "mrisr_geglu_backward": (_I, [_P, _P, _P, _L, _I, _P]),
+    "mrisr_zero_insert2x": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "mrisr_sumpool2": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "mrisr_mse_grad": (_I, [_P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P]),
+    "mrisr_xty64_workspace_floats": (_L, [_I, _I]),
+    "mrisr_xty64": (_I, [_P, _L, _I, _P, _L, _I, _I, _I, _F, _P, _P, _P]),
+    "mrisr_attention_backward": (_I, [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _P]),
+    "mrisr_grad_sqnorm": (_I, [_P, _I, _F, _P, _P, _P]),
+    "mrisr_adamw": (_I, [_P, _I, _P, _F, _F, _F, _F, _F, _I, _P]),
     "mrisr_slice_volume": (_I, [_P, _I, _I, _I, _I, _F, _F, _F, _P, _I, _I, _P]),
 }
 

@@ -17,8 +17,8 @@
 //   against a 0/1 identity weight tile (BN/64 extra k-chunks per tile), i.e. it rides the same deep TMA pipeline as
 //   the operands and is added exactly (bf16 x 1.0) in the fp32 accumulator.
 // * GroupNorm statistics of the OUTPUT are produced by the epilogue (gn_part != nullptr): per-channel sum and sum of
-//   squares of every 128-row block of the stored (rounded) tile, reduced over rows on the legacy tensor path
-//   (ldmatrix.trans of the staged chunk + mma.sync against a ones / its own fragment), combined across the four
+//   squares of every 128-row block of the stored (rounded) tile, reduced over the rows of each staged 32 x 32 chunk
+//   out of shared memory (one lane per column), combined across the four
 //   32-row warps of the CTA in a fixed order (deterministic, no atomics on data) -- the consumer's GroupNorm is then a
 //   single normalise+SiLU pass (1 read + 1 write) with no statistics pass, no grid barrier and no re-read.
 // * up2x: nearest-2x upsample + 3x3 conv (diffusers Upsample2D) as four 2x2 sub-pixel convolutions over the
@@ -183,45 +183,28 @@ __device__ __forceinline__ void gemm_stage_bias(const GemmKernelParams& p, float
 }
 
 // Column sums and sums of squares of one staged 32-row x 32-channel 16-bit chunk (TMA 64B-swizzle layout: 64-byte rows,
-// 16-byte slot ^= (row >> 1) & 3), reduced over the 32 rows on the legacy tensor path: ldmatrix.trans delivers X^T
-// fragments; ones(16x16) * X gives the column sums, X^T * X has the sums of squares on its diagonal (exact fp16/bf16
-// products, fp32 accumulation).  16 MMAs + 4 ldmatrix per chunk instead of ~280 shuffle / select / add instructions.
-// Lane (g, t) with t == g >> 1 ends up owning columns 16 i + g and 16 i + 8 + g (i = 0, 1) and writes them to `slot`.
+// 16-byte slot ^= (row >> 1) & 3): lane l walks column l down the 32 rows out of shared memory (all lanes of a load hit one
+// 64-byte row: conflict-free) and accumulates in fp32 -- ~130 issue slots per chunk on the epilogue warps, which idle behind
+// the main loop anyway.  (A first version reduced the rows on the legacy tensor path -- ldmatrix.trans + mma.sync against
+// ones / its own fragment, 16 HMMA per chunk: measured +17 us on a 171 us 3x3 conv, the legacy MMAs take tensor-pipe
+// cycles from the tcgen05 main loop; this form costs nothing measurable.)
 struct GemmStatCtx {
   float2* slots;   // this tile's ring entry: [4 lane quarters][BN]
   int* counter;    // this tile's ring entry: arrivals of the lane-quarter warps, one counter per chunk half
   long long block; // 128-row block index in gn_part
 };
 template <bool kF16>
-__device__ __forceinline__ void gemm_chunk_col_stats(uint32_t buf_addr, int lane, float2* slot) {
-  constexpr uint32_t one2 = kF16 ? 0x3C003C00u : 0x3F803F80u;
-  const uint32_t ones[4] = {one2, one2, one2, one2};
-  const int mat = lane >> 3, rr = lane & 7;
-  const int g = lane >> 2, t = lane & 3;
+__device__ __forceinline__ void gemm_chunk_col_stats(const uint8_t* buf, int lane, float2* slot) {
+  const int s16 = lane >> 3, e = (lane & 7) * 2;
+  float su = 0.f, sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    float su1[4] = {0.f, 0.f, 0.f, 0.f}, su2[4] = {0.f, 0.f, 0.f, 0.f};
-    float sq1[4] = {0.f, 0.f, 0.f, 0.f}, sq2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      const int row = 16 * ks + (mat >> 1) * 8 + rr;
-      const int slot16 = 2 * i + (mat & 1);
-      uint32_t a[4];
-      ldsm_x4_t(buf_addr + row * 64 + ((slot16 ^ ((row >> 1) & 3)) << 4), a[0], a[1], a[2], a[3]);
-      if (kF16) {
-        mma_f16_16816(su1, ones, a[0], a[2]); mma_f16_16816(su2, ones, a[1], a[3]);
-        mma_f16_16816(sq1, a, a[0], a[2]);    mma_f16_16816(sq2, a, a[1], a[3]);
-      } else {
-        mma_bf16_16816(su1, ones, a[0], a[2]); mma_bf16_16816(su2, ones, a[1], a[3]);
-        mma_bf16_16816(sq1, a, a[0], a[2]);    mma_bf16_16816(sq2, a, a[1], a[3]);
-      }
-    }
-    if (t == (g >> 1)) {
-      const bool odd = (g & 1) != 0;
-      slot[16 * i + g] = make_float2(odd ? su1[1] : su1[0], odd ? sq1[1] : sq1[0]);
-      slot[16 * i + 8 + g] = make_float2(odd ? su2[1] : su2[0], odd ? sq2[3] : sq2[2]);
-    }
+  for (int r = 0; r < 32; ++r) {
+    const uint16_t raw = *reinterpret_cast<const uint16_t*>(buf + r * 64 + ((s16 ^ ((r >> 1) & 3)) << 4) + e);
+    const float v = kF16 ? __half2float(__ushort_as_half(raw)) : __uint_as_float(static_cast<uint32_t>(raw) << 16);
+    su += v;
+    sq = fmaf(v, v, sq);
   }
+  slot[lane] = make_float2(su, sq);
 }
 
 // TMA-store epilogue (bf16 output, every chunk of the tile inside n_store, no residual left for the epilogue).
@@ -321,8 +304,8 @@ __device__ __forceinline__ void gemm_epilogue_tma(const GemmKernelParams& p, con
         }
         if (stats) {  // GroupNorm statistics of exactly the values just staged (what the consumer's norm will read)
           float2* slot = st.slots + ((m >> 5) & 3) * BN + c * 32;
-          if (p.f16_out) gemm_chunk_col_stats<true>(smem_u32(buf), lane_id, slot);
-          else gemm_chunk_col_stats<false>(smem_u32(buf), lane_id, slot);
+          if (p.f16_out) gemm_chunk_col_stats<true>(buf, lane_id, slot);
+          else gemm_chunk_col_stats<false>(buf, lane_id, slot);
         }
       }
     }

@@ -16,6 +16,7 @@
 #include "gemm_tcgen05.cuh"
 #include "metrics.cuh"
 #include "pointwise.cuh"
+#include "train.cuh"
 
 namespace {
 
@@ -339,6 +340,32 @@ int launch_layernorm_group(const void* x, int64_t ldx, const float* g, const flo
 
 constexpr int kGnMaxSlabs = 64;
 
+template <int D>
+int launch_attention_backward(const mrisr::AttnBwdArgs& a, cudaStream_t st) {
+  using Cfg = mrisr::AttnBwdCfg<D>;
+  static bool configured = false;
+  if (!configured) {
+    MRISR_CHECK_CUDA(cudaFuncSetAttribute(mrisr::attention_bwd_dq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    MRISR_CHECK_CUDA(cudaFuncSetAttribute(mrisr::attention_bwd_dkdv_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    MRISR_CHECK_CUDA(cudaFuncSetAttribute(mrisr::attention_bwd_dkdv_kernel<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    MRISR_CHECK_CUDA(cudaFuncSetAttribute(mrisr::attention_bwd_dkdv_kernel<D, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  launch_k(mrisr::attention_bwd_dq_kernel<D>, dim3((a.nq + 63) / 64, a.heads, a.batch), dim3(mrisr::kAbThreads), Cfg::kSmemBytes, st, a);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  const dim3 gk((a.nk + 63) / 64, a.heads, a.batch);
+  if (D > 80) {   // the dK and dV accumulators do not fit the register file together: two sweeps
+    launch_k(mrisr::attention_bwd_dkdv_kernel<D, 1>, gk, dim3(mrisr::kAbThreads), Cfg::kSmemBytes, st, a);
+    MRISR_CHECK_CUDA(cudaGetLastError());
+    launch_k(mrisr::attention_bwd_dkdv_kernel<D, 2>, gk, dim3(mrisr::kAbThreads), Cfg::kSmemBytes, st, a);
+  } else {
+    launch_k(mrisr::attention_bwd_dkdv_kernel<D, 0>, gk, dim3(mrisr::kAbThreads), Cfg::kSmemBytes, st, a);
+  }
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+
 }  // namespace
 
 extern "C" {
@@ -558,7 +585,11 @@ int mrisr_groupnorm_apply_stats(const void* x1, int64_t ld1, int c1, const float
   q.nblk[0] = hw / (128 * n_phases1);
   q.part[1] = reinterpret_cast<const float2*>(part2); q.ldp[1] = ldp2; q.nph[1] = c2 ? n_phases2 : 1; q.pstride[1] = phase_stride2;
   q.nblk[1] = c2 ? hw / (128 * n_phases2) : 0;
-  launch_k(mrisr::groupnorm_apply_cpart_kernel, dim3(nslab, batch), dim3(nvec, R), 2 * static_cast<size_t>(C) * sizeof(float), as_stream(stream), a, q, gamma, beta, eps, silu, static_cast<__nv_bfloat16*>(out));
+  // the block partials are added by (channel, part) work items so that every thread of the CTA has loads in flight
+  int nparts = C <= 320 ? 8 : C <= 640 ? 4 : C <= 1280 ? 2 : 1;
+  const int nb_min = q.nblk[0] * q.nph[0];
+  while (nparts > 1 && nparts > nb_min) nparts >>= 1;
+  launch_k(mrisr::groupnorm_apply_cpart_kernel, dim3(nslab, batch), dim3(nvec, R), static_cast<size_t>(2 * nparts + 2) * C * sizeof(float), as_stream(stream), a, q, gamma, beta, eps, silu, static_cast<__nv_bfloat16*>(out), nparts);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1038,6 +1069,153 @@ int mrisr_slice_volume(const float* vol, int H, int W, int D, int map_intensity,
   const int off_y = H > TH ? (H - TH) / 2 : -((TH - H) / 2);
   const int off_x = W > TW ? (W - TW) / 2 : -((TW - W) / 2);
   launch_k(mrisr::slice_volume_kernel, dim3((TW + 31) / 32, (D + 31) / 32, (TH + mrisr::kSliceRows - 1) / mrisr::kSliceRows), dim3(256), 0, as_stream(stream), vol, H, W, D, a_min, a_max - a_min, map_intensity, pad_value, out, TH, TW, off_y, off_x);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+
+// ====================================================================================================================
+// LoRA fine-tune step (BASELINE config 4): backward-pass kernels (train.cuh).  The dgrad contractions go through mrisr_gemm.
+
+int mrisr_groupnorm_backward(const void* x1, int64_t ld1, int c1, const void* x2, int64_t ld2, int c2, const void* dz, int batch, int hw,
+                             int groups, const float* gamma, const float* beta, float eps, int silu, void* dx1, int64_t lddx1, void* dx2,
+                             int64_t lddx2, int f16_flags, void* stream) {
+  MRISR_REQUIRE(x1 && dz && gamma && beta && dx1, "groupnorm_backward: null pointer");
+  MRISR_REQUIRE(batch > 0 && hw > 0 && c1 > 0 && c2 >= 0 && (c2 == 0 || (x2 && dx2)), "groupnorm_backward: bad sizes");
+  MRISR_REQUIRE(groups > 0 && (c1 + c2) % groups == 0, "groupnorm_backward: groups must divide the channel count");
+  mrisr::GnBwdArgs a;
+  a.x1 = x1; a.x2 = x2; a.ld1 = ld1; a.ld2 = ld2; a.c1 = c1; a.c2 = c2; a.hw = hw; a.groups = groups;
+  a.h1 = f16_flags & 1; a.h2 = (f16_flags >> 1) & 1;
+  a.dz = static_cast<const __half*>(dz); a.dx1 = static_cast<__half*>(dx1); a.dx2 = static_cast<__half*>(dx2); a.ldd1 = lddx1; a.ldd2 = lddx2;
+  launch_k(mrisr::groupnorm_backward_kernel, dim3(groups, batch), dim3(256), 0, as_stream(stream), a, gamma, beta, eps, silu);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mrisr_layernorm_backward(const void* x, int64_t ldx, int x_f16, const void* dy, const float* gamma, float eps, const void* dres,
+                             void* dx, int rows, int C, void* stream) {
+  MRISR_REQUIRE(x && dy && gamma && dx && rows >= 0 && C > 0, "layernorm_backward: bad argument");
+  if (rows == 0) return 0;
+  launch_k(mrisr::layernorm_backward_kernel, dim3((rows + 7) / 8), dim3(256), 0, as_stream(stream), x, static_cast<long long>(ldx), x_f16,
+           static_cast<const __half*>(dy), gamma, eps, static_cast<const __half*>(dres), static_cast<__half*>(dx), rows, C);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mrisr_geglu_forward(const void* pre, void* out, int64_t M, int F, void* stream) {
+  MRISR_REQUIRE(pre && out && M >= 0 && F > 0, "geglu_forward: bad argument");
+  if (M == 0) return 0;
+  launch_k(mrisr::geglu_forward_kernel, dim3(grid_for(M * F, 256, 8)), dim3(256), 0, as_stream(stream), static_cast<const __nv_bfloat16*>(pre),
+           static_cast<__nv_bfloat16*>(out), static_cast<long long>(M), F);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mrisr_geglu_backward(const void* pre, const void* df, void* dpre, int64_t M, int F, void* stream) {
+  MRISR_REQUIRE(pre && df && dpre && M >= 0 && F > 0, "geglu_backward: bad argument");
+  if (M == 0) return 0;
+  launch_k(mrisr::geglu_backward_kernel, dim3(grid_for(M * F, 256, 8)), dim3(256), 0, as_stream(stream), static_cast<const __nv_bfloat16*>(pre),
+           static_cast<const __half*>(df), static_cast<__half*>(dpre), static_cast<long long>(M), F);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mrisr_zero_insert2x(const void* in, void* out, int B, int h, int w, int C, void* stream) {
+  MRISR_REQUIRE(in && out && B > 0 && h > 0 && w > 0 && C > 0 && C % 8 == 0 && aligned16(in) && aligned16(out), "zero_insert2x: bad argument");
+  launch_k(mrisr::zero_insert2x_kernel, dim3(grid_for(static_cast<long long>(B) * 4 * h * w * (C / 8), 256, 8)), dim3(256), 0, as_stream(stream),
+           static_cast<const uint4*>(in), static_cast<uint4*>(out), B, h, w, C / 8);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mrisr_sumpool2(const void* in, void* out, int B, int h, int w, int C, void* stream) {
+  MRISR_REQUIRE(in && out && B > 0 && h > 0 && w > 0 && C > 0, "sumpool2: bad argument");
+  launch_k(mrisr::sumpool2_kernel, dim3(grid_for(static_cast<long long>(B) * h * w * C, 256, 8)), dim3(256), 0, as_stream(stream),
+           static_cast<const __half*>(in), static_cast<__half*>(out), B, h, w, C);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mrisr_mse_grad(const float* pred, const float* target, int B, int C, int HW, int cpad, float grad_scale, void* dout, float* workspace,
+                   float* loss, void* stream) {
+  MRISR_REQUIRE(pred && target && dout && workspace && loss && B > 0 && C > 0 && HW > 0 && cpad >= C, "mse_grad: bad argument");
+  const int blocks = grid_for(static_cast<long long>(B) * HW * cpad, 256, 4) < 1024 ? grid_for(static_cast<long long>(B) * HW * cpad, 256, 4) : 1024;
+  cudaStream_t st = as_stream(stream);
+  launch_k(mrisr::mse_grad_kernel, dim3(blocks), dim3(256), 0, st, pred, target, B, C, HW, cpad, grad_scale, static_cast<__half*>(dout), workspace);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  launch_k(mrisr::mse_finalize_kernel, dim3(1), dim3(32), 0, st, static_cast<const float*>(workspace), blocks,
+           1.0f / (static_cast<float>(B) * C * HW), loss);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int64_t mrisr_xty64_workspace_floats(int M, int Q) {
+  const int64_t msplit = (M + 255) / 256;
+  return msplit * 64 * static_cast<int64_t>(Q);
+}
+
+int mrisr_xty64(const void* X, int64_t ldx, int x_f16, const void* Y, int64_t ldy, int y_f16, int M, int Q, float scale, float* workspace,
+                float* out, void* stream) {
+  MRISR_REQUIRE(X && Y && workspace && out && M > 0 && Q > 0 && ldx >= 64 && ldy >= Q, "xty64: bad argument");
+  const int msplit = (M + 255) / 256;
+  cudaStream_t st = as_stream(stream);
+  launch_k(mrisr::xty64_partial_kernel, dim3((Q + 63) / 64, msplit), dim3(256), 0, st, X, static_cast<long long>(ldx), x_f16, Y,
+           static_cast<long long>(ldy), y_f16, M, Q, 256, workspace);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  launch_k(mrisr::xty64_reduce_kernel, dim3(grid_for(64LL * Q, 256, 4)), dim3(256), 0, st, static_cast<const float*>(workspace), msplit, Q, scale, out);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mrisr_attention_backward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o, int64_t ldo,
+                             const void* d_o, int64_t lddo, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                             float* stats_ws, int batch, int nq, int nk, int heads, int d, void* stream) {
+  MRISR_REQUIRE(q && k && v && o && d_o && dq && dk && dv && stats_ws, "attention_backward: null pointer");
+  MRISR_REQUIRE(batch > 0 && nq > 0 && nk > 0 && heads > 0, "attention_backward: bad sizes");
+  MRISR_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o) && aligned16(d_o) && aligned16(dq) && aligned16(dk) && aligned16(dv),
+                "attention_backward: misaligned pointer");
+  MRISR_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && lddo % 8 == 0 && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0,
+                "attention_backward: row strides must be multiples of 8");
+  mrisr::AttnBwdArgs a;
+  a.q = static_cast<const __nv_bfloat16*>(q); a.k = static_cast<const __nv_bfloat16*>(k); a.v = static_cast<const __nv_bfloat16*>(v);
+  a.o = static_cast<const __nv_bfloat16*>(o);
+  a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo;
+  a.d_o = static_cast<const __half*>(d_o); a.lddo = lddo;
+  a.dq = static_cast<__half*>(dq); a.dk = static_cast<__half*>(dk); a.dv = static_cast<__half*>(dv);
+  a.lddq = lddq; a.lddk = lddk; a.lddv = lddv;
+  a.lse = stats_ws; a.dsum = stats_ws + static_cast<long long>(batch) * heads * nq;
+  a.nq = nq; a.nk = nk; a.heads = heads; a.batch = batch;
+  a.scale = static_cast<float>(1.0 / std::sqrt(static_cast<double>(d)));
+  a.scale_log2 = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(d)));
+  cudaStream_t st = as_stream(stream);
+  switch (d) {
+    case 8: return launch_attention_backward<8>(a, st);
+    case 16: return launch_attention_backward<16>(a, st);
+    case 40: return launch_attention_backward<40>(a, st);
+    case 80: return launch_attention_backward<80>(a, st);
+    case 160: return launch_attention_backward<160>(a, st);
+    default: return fail(MRISR_E_UNSUPPORTED, "attention_backward: head dim %d unsupported (8, 16, 40, 80, 160)", d);
+  }
+}
+
+static_assert(sizeof(mrisr_adam_desc) == sizeof(mrisr::AdamDesc), "mrisr_adam_desc must mirror mrisr::AdamDesc");
+
+int mrisr_grad_sqnorm(const mrisr_adam_desc* desc, int n_desc, float max_norm, float* workspace, float* out2, void* stream) {
+  MRISR_REQUIRE(desc && workspace && out2 && n_desc > 0, "grad_sqnorm: bad argument");
+  cudaStream_t st = as_stream(stream);
+  launch_k(mrisr::sqnorm_multi_kernel, dim3(n_desc), dim3(256), 0, st, reinterpret_cast<const mrisr::AdamDesc*>(desc), workspace);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  launch_k(mrisr::sqnorm_finalize_kernel, dim3(1), dim3(32), 0, st, static_cast<const float*>(workspace), n_desc, max_norm, out2);
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mrisr_adamw(const mrisr_adam_desc* desc, int n_desc, const float* clip, float lr, float beta1, float beta2, float eps, float weight_decay,
+                int step, void* stream) {
+  MRISR_REQUIRE(desc && n_desc > 0 && step >= 1, "adamw: bad argument");
+  const float bc1 = 1.f - std::pow(beta1, static_cast<float>(step)), bc2 = 1.f - std::pow(beta2, static_cast<float>(step));
+  launch_k(mrisr::adamw_multi_kernel, dim3(n_desc), dim3(256), 0, as_stream(stream), reinterpret_cast<const mrisr::AdamDesc*>(desc), clip, lr,
+           beta1, beta2, eps, weight_decay, bc1, bc2);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

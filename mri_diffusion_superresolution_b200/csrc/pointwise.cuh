@@ -398,39 +398,57 @@ struct GnPartArgs {
   int nblk[2];
 };
 __global__ void groupnorm_apply_cpart_kernel(GnArgs a, GnPartArgs q, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                             float eps, int silu, __nv_bfloat16* __restrict__ out) {
+                                             float eps, int silu, __nv_bfloat16* __restrict__ out, int nparts) {
   grid_dep_launch();
   grid_dep_wait();
-  extern __shared__ float gn_sh[];   // scale[C], shift[C] (first used as per-channel sum[C], sumsq[C])
+  extern __shared__ float gn_sh[];   // [nparts][sum[C] | sumsq[C]] partial totals, then scale[C], shift[C]
   __shared__ float s_mean[64], s_rstd[64];
   const int C = a.c1 + a.c2;
   const int vx = threadIdx.x, ry = threadIdx.y, R = blockDim.y;
   const int b = blockIdx.y, slab = blockIdx.x;
   const int tid = ry * blockDim.x + vx, nthr = blockDim.x * blockDim.y;
   const int cpg = C / a.groups;
-  for (int c = tid; c < C; c += nthr) {
+  const int p0 = slab * a.pix_per_slab;
+  const int p1 = min(a.hw, p0 + a.pix_per_slab);
+  // (A) the first eight 16-byte loads of this thread's pixels do not depend on the statistics: put them in flight now, so the
+  // prologue below (block partials -> group statistics -> per-channel scale / shift: three dependent L2 round trips) is hidden
+  int pix = p0 + ry;
+  const bool pre = pix + 7 * R < p1;
+  uint4 first[8];
+  if (pre) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) first[u] = gn_load(a, b, pix + u * R, vx);
+  }
+  // (B) per-channel totals of this batch element: (channel, part) work items, part p adds blocks p, p + nparts, ... (fixed order)
+  float* s_aff = gn_sh + nparts * 2 * C;
+  for (int it = tid; it < C * nparts; it += nthr) {
+    const int part = it / C, c = it - part * C;
     const int s = c < a.c1 ? 0 : 1;
     const int cc = s == 0 ? c : c - a.c1;
-    float su[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int ph = 0; ph < q.nph[s]; ++ph) {
-      const float2* pp = q.part[s] + (ph * q.pstride[s] + static_cast<long long>(b) * q.nblk[s]) * q.ldp[s] + cc;
-      int j = 0;
-      for (; j + 3 < q.nblk[s]; j += 4) {   // four independent L2 loads in flight
-        float2 v[4];
+    const int nb = q.nph[s] * q.nblk[s];
+    float su = 0.f, sq = 0.f;
+    for (int j0 = part; j0 < nb; j0 += 4 * nparts) {   // up to four independent L2 loads in flight
+      float2 v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = __ldg(pp + (j + u) * q.ldp[s]);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { su[u] += v[u].x; sq[u] += v[u].y; }
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * nparts;
+        v[u] = make_float2(0.f, 0.f);
+        if (j < nb) {
+          const int ph = j / q.nblk[s], jj = j - ph * q.nblk[s];
+          v[u] = __ldg(q.part[s] + (ph * q.pstride[s] + static_cast<long long>(b) * q.nblk[s] + jj) * q.ldp[s] + cc);
+        }
       }
-      for (; j < q.nblk[s]; ++j) { const float2 v = __ldg(pp + j * q.ldp[s]); su[0] += v.x; sq[0] += v.y; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { su += v[u].x; sq += v[u].y; }
     }
-    gn_sh[c] = (su[0] + su[1]) + (su[2] + su[3]);
-    gn_sh[C + c] = (sq[0] + sq[1]) + (sq[2] + sq[3]);
+    gn_sh[part * 2 * C + c] = su;
+    gn_sh[part * 2 * C + C + c] = sq;
   }
   __syncthreads();
   for (int g = tid; g < a.groups; g += nthr) {
     double su = 0.0, sq = 0.0;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { su += gn_sh[c]; sq += gn_sh[C + c]; }
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c)
+      for (int part = 0; part < nparts; ++part) { su += gn_sh[part * 2 * C + c]; sq += gn_sh[part * 2 * C + C + c]; }
     const double n = static_cast<double>(a.hw) * cpg;
     const double mean = su / n;
     double var = sq / n - mean * mean;
@@ -442,20 +460,18 @@ __global__ void groupnorm_apply_cpart_kernel(GnArgs a, GnPartArgs q, const float
   for (int c = tid; c < C; c += nthr) {
     const int g = c / cpg;
     const float sc = s_rstd[g] * __ldg(gamma + c);
-    gn_sh[c] = sc;
-    gn_sh[C + c] = __ldg(beta + c) - s_mean[g] * sc;
+    s_aff[c] = sc;
+    s_aff[C + c] = __ldg(beta + c) - s_mean[g] * sc;
   }
   __syncthreads();
   float2 sc[4], sh[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    sc[j] = make_float2(gn_sh[vx * 8 + 2 * j], gn_sh[vx * 8 + 2 * j + 1]);
-    sh[j] = make_float2(gn_sh[C + vx * 8 + 2 * j], gn_sh[C + vx * 8 + 2 * j + 1]);
+    sc[j] = make_float2(s_aff[vx * 8 + 2 * j], s_aff[vx * 8 + 2 * j + 1]);
+    sh[j] = make_float2(s_aff[C + vx * 8 + 2 * j], s_aff[C + vx * 8 + 2 * j + 1]);
   }
-  const int p0 = slab * a.pix_per_slab;
-  const int p1 = min(a.hw, p0 + a.pix_per_slab);
   const bool hsrc = (vx < (a.c1 >> 3) ? a.h1 : a.h2) != 0;
-  auto emit = [&](int pix, const uint4& v) {
+  auto emit = [&](int pixel, const uint4& v) {
     float2 f[4];
     unpack8p_any(v, f, hsrc);
 #pragma unroll
@@ -463,10 +479,14 @@ __global__ void groupnorm_apply_cpart_kernel(GnArgs a, GnPartArgs q, const float
       f[j] = __ffma2_rn(f[j], sc[j], sh[j]);
       if (silu) { f[j].x = silu_tanh(f[j].x); f[j].y = silu_tanh(f[j].y); }
     }
-    reinterpret_cast<uint4*>(out + (static_cast<long long>(b) * a.hw + pix) * C)[vx] = pack8p(f);
+    reinterpret_cast<uint4*>(out + (static_cast<long long>(b) * a.hw + pixel) * C)[vx] = pack8p(f);
   };
-  int pix = p0 + ry;
-  for (; pix + 7 * R < p1; pix += 8 * R) {  // 8 independent 16-byte loads in flight per thread (no second pass to hide latency behind)
+  if (pre) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) emit(pix + u * R, first[u]);
+    pix += 8 * R;
+  }
+  for (; pix + 7 * R < p1; pix += 8 * R) {  // 8 independent 16-byte loads in flight per thread
     uint4 v[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) v[u] = gn_load(a, b, pix + u * R, vx);

@@ -1,0 +1,631 @@
+// Backward-pass kernels of the LoRA fine-tune step (BASELINE config 4): gradients flow
+// through the frozen SD-1.5 UNet into the LoRA A / B matrices only.  The contractions of the backward pass (dgrad of
+// every conv / linear) run on the same tcgen05 GEMM kernel as the forward pass with transposed / tap-flipped weights;
+// this file holds what is not a GEMM: GroupNorm / LayerNorm / GEGLU backward, flash-style attention backward
+// (mma.sync), the skinny X^T Y reductions of the rank-16 weight gradients, the fused loss gradient, gradient-norm
+// clipping and a multi-tensor AdamW that also refreshes the packed 16-bit copies the GEMMs read.
+// Gradient activations are IEEE half under a static loss scale (the reference trains under fp16 autocast,
+// notebooks/ResDif_execution.ipynb:623); all reductions and the optimizer state are fp32.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#include "ptx.cuh"
+
+namespace mrisr {
+
+__device__ __forceinline__ float ld16(const void* p, long long i, bool h) {
+  return h ? __half2float(static_cast<const __half*>(p)[i]) : __bfloat162float(static_cast<const __nv_bfloat16*>(p)[i]);
+}
+__device__ __forceinline__ void st16(void* p, long long i, float v, bool h) {
+  if (h) static_cast<__half*>(p)[i] = __float2half_rn(v);
+  else static_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16(v);
+}
+
+// sum over the CTA of up to kN values per thread (fixed order: warp shuffles, then warp 0 over the warp partials)
+template <int kN>
+__device__ __forceinline__ void block_sum(float (&v)[kN], float* sh /* [kN * 32] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < kN; ++i)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  __syncthreads();   // sh may still be read from a previous call
+  if (lane == 0)
+#pragma unroll
+    for (int i = 0; i < kN; ++i) sh[i * 32 + warp] = v[i];
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kN; ++i) {
+    float a = 0.f;
+    for (int w = 0; w < nw; ++w) a += sh[i * 32 + w];
+    v[i] = a;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// GroupNorm(+SiLU) backward.  z = silu(y), y = xhat * gamma + beta, xhat = (x - mean) * rstd over one (batch element, group).
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dz * silu'(y) * gamma.   One CTA per (group, batch element);
+// three passes over its hw x cpg slice (statistics, the two reductions, the result) -- the slice is L2-resident.
+// x is the channel concat of x1 | x2 (either 16-bit format), dz (dense) / dx are IEEE half; dx1 / dx2 are [B*hw, c1|c2] with row pitches ldd1 / ldd2.
+struct GnBwdArgs {
+  const void* x1; const void* x2;
+  long long ld1, ld2;
+  int c1, c2, hw, groups;
+  int h1, h2;
+  const __half* dz;   // [B, hw, c1 + c2]
+  __half* dx1; __half* dx2;
+  long long ldd1, ldd2;   // row pitches of dx1 / dx2 (they may be the two column ranges of one [B*hw, c1+c2] buffer)
+};
+__global__ void __launch_bounds__(256) groupnorm_backward_kernel(GnBwdArgs a, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, float eps, int silu) {
+  __shared__ float sh[2 * 32];
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int C = a.c1 + a.c2, cpg = C / a.groups;
+  const int n = a.hw * cpg;
+  const int c0 = g * cpg;
+  auto load_x = [&](int pix, int c) -> float {
+    const long long p = static_cast<long long>(b) * a.hw + pix;
+    return c < a.c1 ? ld16(a.x1, p * a.ld1 + c, a.h1 != 0) : ld16(a.x2, p * a.ld2 + (c - a.c1), a.h2 != 0);
+  };
+  float s[2] = {0.f, 0.f};
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const int pix = e / cpg, c = c0 + (e - pix * cpg);
+    const float x = load_x(pix, c);
+    s[0] += x; s[1] += x * x;
+  }
+  block_sum<2>(s, sh);
+  const float mean = s[0] / n;
+  const float rstd = rsqrtf(fmaxf(s[1] / n - mean * mean, 0.f) + eps);
+  float r[2] = {0.f, 0.f};
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const int pix = e / cpg, c = c0 + (e - pix * cpg);
+    const float xh = (load_x(pix, c) - mean) * rstd;
+    const float ga = __ldg(gamma + c);
+    float d = __half2float(a.dz[(static_cast<long long>(b) * a.hw + pix) * C + c]);
+    if (silu) {
+      const float y = xh * ga + __ldg(beta + c);
+      const float sg = 1.f / (1.f + __expf(-y));
+      d *= sg * (1.f + y * (1.f - sg));
+    }
+    const float gg = d * ga;
+    r[0] += gg; r[1] += gg * xh;
+  }
+  block_sum<2>(r, sh);
+  const float m1 = r[0] / n, m2 = r[1] / n;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const int pix = e / cpg, c = c0 + (e - pix * cpg);
+    const float xh = (load_x(pix, c) - mean) * rstd;
+    const float ga = __ldg(gamma + c);
+    float d = __half2float(a.dz[(static_cast<long long>(b) * a.hw + pix) * C + c]);
+    if (silu) {
+      const float y = xh * ga + __ldg(beta + c);
+      const float sg = 1.f / (1.f + __expf(-y));
+      d *= sg * (1.f + y * (1.f - sg));
+    }
+    const float dx = rstd * (d * ga - m1 - xh * m2);
+    const long long p = static_cast<long long>(b) * a.hw + pix;
+    if (c < a.c1) a.dx1[p * a.ldd1 + c] = __float2half_rn(dx);
+    else a.dx2[p * a.ldd2 + (c - a.c1)] = __float2half_rn(dx);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// LayerNorm backward, one warp per row: dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) (+ dres), g = dy * gamma.
+__global__ void __launch_bounds__(256) layernorm_backward_kernel(const void* __restrict__ x, long long ldx, int x_f16,
+                                                                  const __half* __restrict__ dy, const float* __restrict__ gamma,
+                                                                  float eps, const __half* __restrict__ dres, __half* __restrict__ dx,
+                                                                  int rows, int C) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const long long xo = static_cast<long long>(row) * ldx, yo = static_cast<long long>(row) * C;
+  float s0 = 0.f, s1 = 0.f;
+  for (int c = lane; c < C; c += 32) { const float v = ld16(x, xo + c, x_f16 != 0); s0 += v; s1 += v * v; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+  const float mean = s0 / C;
+  const float rstd = rsqrtf(fmaxf(s1 / C - mean * mean, 0.f) + eps);
+  float r0 = 0.f, r1 = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float xh = (ld16(x, xo + c, x_f16 != 0) - mean) * rstd;
+    const float gg = __half2float(dy[yo + c]) * __ldg(gamma + c);
+    r0 += gg; r1 += gg * xh;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { r0 += __shfl_xor_sync(0xffffffffu, r0, o); r1 += __shfl_xor_sync(0xffffffffu, r1, o); }
+  const float m1 = r0 / C, m2 = r1 / C;
+  for (int c = lane; c < C; c += 32) {
+    const float xh = (ld16(x, xo + c, x_f16 != 0) - mean) * rstd;
+    const float gg = __half2float(dy[yo + c]) * __ldg(gamma + c);
+    float v = rstd * (gg - m1 - xh * m2);
+    if (dres != nullptr) v += __half2float(dres[yo + c]);
+    dx[yo + c] = __float2half_rn(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// GEGLU (diffusers GEGLU: hidden, gate = proj(x).chunk(2, -1); hidden * gelu(gate), exact erf GELU), un-fused for training so
+// that the pre-activation [M, 2F] = [hidden | gate] is kept for the backward pass.
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+__global__ void geglu_forward_kernel(const __nv_bfloat16* __restrict__ pre, __nv_bfloat16* __restrict__ out, long long M, int F) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < M * F; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long m = i / F;
+    const int f = static_cast<int>(i - m * F);
+    const float a = __bfloat162float(pre[m * 2 * F + f]), g = __bfloat162float(pre[m * 2 * F + F + f]);
+    out[i] = __float2bfloat16(a * gelu_erf(g));
+  }
+}
+__global__ void geglu_backward_kernel(const __nv_bfloat16* __restrict__ pre, const __half* __restrict__ df, __half* __restrict__ dpre,
+                                      long long M, int F) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < M * F; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long m = i / F;
+    const int f = static_cast<int>(i - m * F);
+    const float a = __bfloat162float(pre[m * 2 * F + f]), g = __bfloat162float(pre[m * 2 * F + F + f]);
+    const float d = __half2float(df[i]);
+    dpre[m * 2 * F + f] = __float2half_rn(d * gelu_erf(g));
+    dpre[m * 2 * F + F + f] = __float2half_rn(d * a * gelu_erf_grad(g));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Spatial helpers of the backward pass.  zero_insert2x: [B,h,w,C] -> [B,2h,2w,C], value at (2y, 2x), zeros elsewhere (the
+// transposed stride-2 convolution = a stride-1 convolution of this with the flipped filter).  sumpool2: [B,2h,2w,C] ->
+// [B,h,w,C] sum of each 2x2 block (backward of the nearest-2x upsample).  IEEE half, 8-channel vectors.
+__global__ void zero_insert2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int h, int w, int nvec) {
+  const long long total = static_cast<long long>(B) * 4 * h * w * nvec;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % nvec);
+    long long p = i / nvec;
+    const int X = static_cast<int>(p % (2 * w)); p /= 2 * w;
+    const int Y = static_cast<int>(p % (2 * h));
+    const int b = static_cast<int>(p / (2 * h));
+    uint4 r = make_uint4(0u, 0u, 0u, 0u);
+    if (((X | Y) & 1) == 0) r = __ldg(in + ((static_cast<long long>(b) * h + (Y >> 1)) * w + (X >> 1)) * nvec + v);
+    out[i] = r;
+  }
+}
+__global__ void sumpool2_kernel(const __half* __restrict__ in, __half* __restrict__ out, int B, int h, int w, int C) {
+  const long long total = static_cast<long long>(B) * h * w * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    long long p = i / C;
+    const int x = static_cast<int>(p % w); p /= w;
+    const int y = static_cast<int>(p % h);
+    const int b = static_cast<int>(p / h);
+    const long long r0 = ((static_cast<long long>(b) * 2 * h + 2 * y) * 2 * w + 2 * x) * C + c;
+    const long long r1 = r0 + static_cast<long long>(2 * w) * C;
+    out[i] = __float2half_rn((__half2float(in[r0]) + __half2float(in[r0 + C])) + (__half2float(in[r1]) + __half2float(in[r1 + C])));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Loss and its gradient: L = mean((eps_hat - target)^2) (prediction_type "epsilon", MSE); dL/deps_hat * loss_scale is
+// written as IEEE half NHWC with the 4 latent channels zero-padded to `cpad` (the conv_out dgrad's K granularity).
+// Deterministic two-stage loss reduction: partial[blockIdx.x], then mse_finalize_kernel.
+__global__ void __launch_bounds__(256) mse_grad_kernel(const float* __restrict__ pred, const float* __restrict__ target, int B, int Cc, int HW,
+                                                       int cpad, float grad_scale, __half* __restrict__ dout, float* __restrict__ partial) {
+  __shared__ float sh[32];
+  const long long total = static_cast<long long>(B) * HW * cpad;
+  float acc[1] = {0.f};
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cpad);
+    const long long p = i / cpad;
+    float gval = 0.f;
+    if (c < Cc) {
+      const long long b = p / HW, pix = p - b * HW;
+      const long long src = (b * Cc + c) * HW + pix;
+      const float d = pred[src] - target[src];
+      acc[0] += d * d;
+      gval = d * grad_scale;
+    }
+    dout[i] = __float2half_rn(gval);
+  }
+  block_sum<1>(acc, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc[0];
+}
+__global__ void mse_finalize_kernel(const float* __restrict__ partial, int n, float inv_count, float* __restrict__ loss) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double a = 0.0;
+    for (int i = 0; i < n; ++i) a += partial[i];
+    *loss = static_cast<float>(a * inv_count);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// out[64, Q] = scale * X^T Y with X [M, 64] and Y [M, Q] (any 16-bit format each): the rank-16 LoRA weight gradients
+//   dA_stack = u^T x   (u = dy * (s B), the gradient at the LoRA bottleneck; x = the projection's input)
+//   d(sB)^T  = t^T dy  (t = x A^T, kept from the forward pass)
+// fp32 FMA on the CUDA cores (64 x Q x M MACs: ~0.2 GFLOP per projection at batch 2), split over M into `msplit` chunks whose
+// partial products are summed by a second kernel in a fixed order (deterministic, no atomics).
+constexpr int kXtyRows = 32;
+__global__ void __launch_bounds__(256) xty64_partial_kernel(const void* __restrict__ X, long long ldx, int x_f16,
+                                                             const void* __restrict__ Y, long long ldy, int y_f16, int M, int Q,
+                                                             int rows_per_split, float* __restrict__ partial /*[msplit][64][Q]*/) {
+  __shared__ float sx[kXtyRows][64 + 1];
+  __shared__ float sy[kXtyRows][64 + 1];
+  const int q0 = blockIdx.x * 64;
+  const int m_begin = blockIdx.y * rows_per_split;
+  const int m_end = min(M, m_begin + rows_per_split);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // thread computes rows 4*ty.., cols 4*tx.. of the 64x64 tile
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int m0 = m_begin; m0 < m_end; m0 += kXtyRows) {
+    for (int e = threadIdx.x; e < kXtyRows * 64; e += 256) {
+      const int r = e >> 6, c = e & 63;
+      const int m = m0 + r;
+      const bool ok = m < m_end;
+      sx[r][c] = ok ? ld16(X, static_cast<long long>(m) * ldx + c, x_f16 != 0) : 0.f;
+      sy[r][c] = (ok && q0 + c < Q) ? ld16(Y, static_cast<long long>(m) * ldy + q0 + c, y_f16 != 0) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < kXtyRows; ++r) {
+      float xv[4], yv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { xv[i] = sx[r][4 * ty + i]; yv[i] = sy[r][4 * tx + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xv[i], yv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* dst = partial + static_cast<long long>(blockIdx.y) * 64 * Q;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (q0 + 4 * tx + j < Q) dst[static_cast<long long>(4 * ty + i) * Q + q0 + 4 * tx + j] = acc[i][j];
+}
+__global__ void xty64_reduce_kernel(const float* __restrict__ partial, int msplit, int Q, float scale, float* __restrict__ out) {
+  const long long n = 64LL * Q;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float a = 0.f;
+    for (int s = 0; s < msplit; ++s) a += partial[static_cast<long long>(s) * n + i];
+    out[i] = a * scale;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Multi-tensor gradient norm + AdamW over the LoRA matrices (3.19 M parameters in 256 tensors at r = 16).  One descriptor per
+// parameter tensor [rows, cols] (fp32 master, moments); its gradient is a strided window of an X^T Y result; after the update
+// the new value is written (scaled, in the format the kernels read) into up to two packed 16-bit destinations -- the forward
+// GEMM's operand and the backward (dgrad) GEMM's operand -- so no re-packing pass exists.
+struct AdamDesc {
+  float* p; float* m; float* v;
+  const float* g; long long g_sr, g_sc; float g_scale;   // grad(i, j) = g[i * g_sr + j * g_sc] * g_scale
+  int rows, cols;
+  void* d1; long long d1_sr, d1_sc; float d1_scale; int d1_f16;   // packed destination 1 (nullptr = none)
+  void* d2; long long d2_sr, d2_sc; float d2_scale; int d2_f16;
+};
+__global__ void __launch_bounds__(256) sqnorm_multi_kernel(const AdamDesc* __restrict__ desc, float* __restrict__ per_tensor) {
+  __shared__ float sh[32];
+  const AdamDesc d = desc[blockIdx.x];
+  const int n = d.rows * d.cols;
+  float acc[1] = {0.f};
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const int i = e / d.cols, j = e - i * d.cols;
+    const float gv = d.g[i * d.g_sr + j * d.g_sc] * d.g_scale;
+    acc[0] += gv * gv;
+  }
+  block_sum<1>(acc, sh);
+  if (threadIdx.x == 0) per_tensor[blockIdx.x] = acc[0];
+}
+__global__ void sqnorm_finalize_kernel(const float* __restrict__ per_tensor, int n, float max_norm, float* __restrict__ out /*[2]: norm, clip coef*/) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double a = 0.0;
+    for (int i = 0; i < n; ++i) a += per_tensor[i];
+    const float norm = static_cast<float>(sqrt(a));
+    out[0] = norm;
+    out[1] = max_norm > 0.f ? fminf(1.f, max_norm / (norm + 1e-6f)) : 1.f;   // torch.nn.utils.clip_grad_norm_
+  }
+}
+__global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamDesc* __restrict__ desc, const float* __restrict__ clip /*[2]*/,
+                                                          float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2) {
+  const AdamDesc d = desc[blockIdx.x];
+  const int n = d.rows * d.cols;
+  const float coef = clip != nullptr ? clip[1] : 1.f;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const int i = e / d.cols, j = e - i * d.cols;
+    const float gv = d.g[i * d.g_sr + j * d.g_sc] * d.g_scale * coef;
+    float p = d.p[e] * (1.f - lr * wd);               // decoupled weight decay (torch.optim.AdamW)
+    const float m = beta1 * d.m[e] + (1.f - beta1) * gv;
+    const float v = beta2 * d.v[e] + (1.f - beta2) * gv * gv;
+    p -= lr * (m / bc1) / (sqrtf(v / bc2) + eps);
+    d.p[e] = p; d.m[e] = m; d.v[e] = v;
+    if (d.d1 != nullptr) st16(d.d1, i * d.d1_sr + j * d.d1_sc, p * d.d1_scale, d.d1_f16 != 0);
+    if (d.d2 != nullptr) st16(d.d2, i * d.d2_sr + j * d.d2_sc, p * d.d2_scale, d.d2_f16 != 0);
+  }
+}
+
+}  // namespace mrisr
+
+// ===================================================================================================
+// Attention backward (diffusers Attention -> F.scaled_dot_product_attention, call site src/adapters/res_srdiff.py:73-78).
+// Flash-style: the N x N probability matrix is never stored; both kernels recompute S = Q K^T tile by tile.
+//   attention_bwd_dq_kernel   : one CTA = 64 queries of one (batch, head).  Pass 1 over the key tiles: row log-sum-exp (log2
+//                               domain) -- so the forward pass may use the fast tcgen05 kernels, which do not export it;
+//                               D_i = rowsum(dO_i * O_i).  Pass 2: P = 2^(s - lse), dP = dO V^T, dS = P (dP - D), dQ += dS K.
+//   attention_bwd_dkdv_kernel : one CTA = 64 keys.  Over the query tiles: dV += P^T dO, dK += dS^T Q.
+// mma.sync m16n8k16, bf16 operands (Q, K, V, O as stored by the forward pass; dO arrives in IEEE half under the loss scale and
+// is rounded to bf16 once), fp32 accumulation; dQ / dK / dV leave in IEEE half.  4 warps x 16 rows.
+namespace mrisr {
+
+struct AttnBwdArgs {
+  const __nv_bfloat16 *q, *k, *v, *o;
+  long long ldq, ldk, ldv, ldo;
+  const __half* d_o; long long lddo;
+  __half *dq, *dk, *dv;
+  long long lddq, lddk, lddv;
+  float* lse;    // [batch * heads * nq]  (written by the dq kernel, read by the dk/dv kernel)
+  float* dsum;   // [batch * heads * nq]
+  int nq, nk, heads, batch;
+  float scale_log2, scale;
+};
+
+template <int D>
+struct AttnBwdCfg {
+  static constexpr int DP = (D + 15) / 16 * 16;   // head dim padded to the MMA K granularity (zero columns)
+  static constexpr int LDS = DP + 8;              // smem row pitch (elements): conflict-free ldmatrix
+  static constexpr int kTileElems = 64 * LDS;
+  static constexpr int kSmemBytes = 4 * kTileElems * 2 + 2 * 64 * 4;
+};
+constexpr int kAbThreads = 128;
+
+template <int D, bool kHalfSrc>
+__device__ __forceinline__ void ab_load_tile(__nv_bfloat16* s, const void* g, long long ld, int row0, int nrows, int col0) {
+  using Cfg = AttnBwdCfg<D>;
+  constexpr int kVec = Cfg::DP / 8;
+  for (int e = threadIdx.x; e < 64 * kVec; e += kAbThreads) {
+    const int r = e / kVec, v = e - r * kVec;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (row0 + r < nrows && v * 8 < D) {
+      val = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(g) + static_cast<long long>(row0 + r) * ld + col0 + v * 8));
+      if (kHalfSrc)
+        val = make_uint4(pack_bf16(f16_lo(val.x), f16_hi(val.x)), pack_bf16(f16_lo(val.y), f16_hi(val.y)),
+                         pack_bf16(f16_lo(val.z), f16_hi(val.z)), pack_bf16(f16_lo(val.w), f16_hi(val.w)));
+    }
+    *reinterpret_cast<uint4*>(s + r * Cfg::LDS + v * 8) = val;
+  }
+}
+
+// acc[8][4] (16 rows x 64 cols) = A[16 x DP] * B^T, A rows r0.. of sa, B rows (= output columns) 0..63 of sb, both [rows][d]
+template <int D>
+__device__ __forceinline__ void ab_mma_nt(float (&acc)[8][4], const __nv_bfloat16* sa, int r0, const __nv_bfloat16* sb, int lane) {
+  using Cfg = AttnBwdCfg<D>;
+  const int mat = lane >> 3, rr = lane & 7;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < Cfg::DP / 16; ++ks) {
+    uint32_t a[4];
+    ldsm_x4(smem_u32(sa + (r0 + (mat & 1) * 8 + rr) * Cfg::LDS + ks * 16 + (mat >> 1) * 8), a[0], a[1], a[2], a[3]);
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {   // two 8-column blocks per ldmatrix
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4(smem_u32(sb + (jj * 16 + (mat >> 1) * 8 + rr) * Cfg::LDS + ks * 16 + (mat & 1) * 8), b0, b1, b2, b3);
+      mma_bf16_16816(acc[2 * jj], a, b0, b1);
+      mma_bf16_16816(acc[2 * jj + 1], a, b2, b3);
+    }
+  }
+}
+
+// out[DP/8][4] (16 rows x DP cols) += P[16 x 64] * B, P given as C fragments (converted to bf16 A fragments), B = sb [64 rows][d]
+template <int D>
+__device__ __forceinline__ void ab_mma_pn(float (&out)[AttnBwdCfg<D>::DP / 8][4], const float (&p)[8][4], const __nv_bfloat16* sb, int lane) {
+  using Cfg = AttnBwdCfg<D>;
+  const int mat = lane >> 3, rr = lane & 7;
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {     // 16 rows of B (k) per step
+    uint32_t a[4];
+    a[0] = pack_bf16(p[2 * jj][0], p[2 * jj][1]);
+    a[1] = pack_bf16(p[2 * jj][2], p[2 * jj][3]);
+    a[2] = pack_bf16(p[2 * jj + 1][0], p[2 * jj + 1][1]);
+    a[3] = pack_bf16(p[2 * jj + 1][2], p[2 * jj + 1][3]);
+#pragma unroll
+    for (int nb = 0; nb < Cfg::DP / 16; ++nb) {   // two 8-column d blocks per ldmatrix
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4_t(smem_u32(sb + (jj * 16 + (mat & 1) * 8 + rr) * Cfg::LDS + nb * 16 + (mat >> 1) * 8), b0, b1, b2, b3);
+      mma_bf16_16816(out[2 * nb], a, b0, b1);
+      mma_bf16_16816(out[2 * nb + 1], a, b2, b3);
+    }
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kAbThreads) attention_bwd_dq_kernel(AttnBwdArgs a) {
+  using Cfg = AttnBwdCfg<D>;
+  extern __shared__ __align__(16) uint8_t ab_raw[];
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(ab_raw);
+  __nv_bfloat16* sdO = sQ + Cfg::kTileElems;
+  __nv_bfloat16* sK = sdO + Cfg::kTileElems;
+  __nv_bfloat16* sV = sK + Cfg::kTileElems;
+  float* sDs = reinterpret_cast<float*>(sV + Cfg::kTileElems);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int q0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+  const long long qrow0 = static_cast<long long>(b) * a.nq, krow0 = static_cast<long long>(b) * a.nk;
+  const long long stat0 = (static_cast<long long>(b) * a.heads + h) * a.nq;
+  ab_load_tile<D, false>(sQ, a.q + qrow0 * a.ldq, a.ldq, q0, a.nq, h * D);
+  ab_load_tile<D, true>(sdO, a.d_o + qrow0 * a.lddo, a.lddo, q0, a.nq, h * D);
+  __syncthreads();
+  {  // D_i = sum_d dO[i, d] * O[i, d] (the bf16-rounded dO the MMAs below see)
+    const int r = threadIdx.x >> 1, part = threadIdx.x & 1;
+    float acc = 0.f;
+    if (q0 + r < a.nq) {
+      const __nv_bfloat16* orow = a.o + (qrow0 + q0 + r) * a.ldo + h * D;
+      for (int c = part * (D / 2); c < (part + 1) * (D / 2); ++c) acc += __bfloat162float(sdO[r * Cfg::LDS + c]) * __bfloat162float(orow[c]);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (part == 0) {
+      sDs[r] = acc;
+      if (q0 + r < a.nq) a.dsum[stat0 + q0 + r] = acc;
+    }
+  }
+  const int r0 = warp * 16;
+  // ---- pass 1: log2-domain log-sum-exp of the two rows this thread owns (g, g + 8)
+  float mx[2] = {-INFINITY, -INFINITY}, sm[2] = {0.f, 0.f};
+  const int ktiles = (a.nk + 63) / 64;
+  for (int kt = 0; kt < ktiles; ++kt) {
+    __syncthreads();
+    ab_load_tile<D, false>(sK, a.k + krow0 * a.ldk, a.ldk, kt * 64, a.nk, h * D);
+    __syncthreads();
+    float s[8][4];
+    ab_mma_nt<D>(s, sQ, r0, sK, lane);
+    float tm[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int col = kt * 64 + j * 8 + 2 * t + (i & 1);
+        s[j][i] = col < a.nk ? s[j][i] * a.scale_log2 : -INFINITY;
+        tm[i >> 1] = fmaxf(tm[i >> 1], s[j][i]);
+      }
+#pragma unroll
+    for (int rrow = 0; rrow < 2; ++rrow) {
+      tm[rrow] = fmaxf(tm[rrow], __shfl_xor_sync(0xffffffffu, tm[rrow], 1));
+      tm[rrow] = fmaxf(tm[rrow], __shfl_xor_sync(0xffffffffu, tm[rrow], 2));
+      const float nm = fmaxf(mx[rrow], tm[rrow]);
+      float add = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { add += exp2f(s[j][2 * rrow] - nm) + exp2f(s[j][2 * rrow + 1] - nm); }
+      add += __shfl_xor_sync(0xffffffffu, add, 1);
+      add += __shfl_xor_sync(0xffffffffu, add, 2);
+      sm[rrow] = sm[rrow] * exp2f(mx[rrow] - nm) + add;
+      mx[rrow] = nm;
+    }
+  }
+  float lse[2], dsv[2];
+#pragma unroll
+  for (int rrow = 0; rrow < 2; ++rrow) {
+    lse[rrow] = mx[rrow] + log2f(sm[rrow]);
+    dsv[rrow] = sDs[r0 + g + 8 * rrow];
+    const int qi = q0 + r0 + g + 8 * rrow;
+    if (t == 0 && qi < a.nq) a.lse[stat0 + qi] = lse[rrow];
+  }
+  // ---- pass 2: dQ
+  float dq[Cfg::DP / 8][4];
+#pragma unroll
+  for (int j = 0; j < Cfg::DP / 8; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dq[j][i] = 0.f;
+  for (int kt = 0; kt < ktiles; ++kt) {
+    __syncthreads();
+    ab_load_tile<D, false>(sK, a.k + krow0 * a.ldk, a.ldk, kt * 64, a.nk, h * D);
+    ab_load_tile<D, false>(sV, a.v + krow0 * a.ldv, a.ldv, kt * 64, a.nk, h * D);
+    __syncthreads();
+    float s[8][4], dp[8][4];
+    ab_mma_nt<D>(s, sQ, r0, sK, lane);
+    ab_mma_nt<D>(dp, sdO, r0, sV, lane);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int col = kt * 64 + j * 8 + 2 * t + (i & 1);
+        const float p = col < a.nk ? exp2f(s[j][i] * a.scale_log2 - lse[i >> 1]) : 0.f;
+        s[j][i] = p * (dp[j][i] - dsv[i >> 1]);     // dS
+      }
+    ab_mma_pn<D>(dq, s, sK, lane);
+  }
+#pragma unroll
+  for (int rrow = 0; rrow < 2; ++rrow) {
+    const int qi = q0 + r0 + g + 8 * rrow;
+    if (qi >= a.nq) continue;
+    __half* dst = a.dq + (qrow0 + qi) * a.lddq + h * D;
+#pragma unroll
+    for (int j = 0; j < Cfg::DP / 8; ++j) {
+      const int c = j * 8 + 2 * t;
+      if (c < D) *reinterpret_cast<__half2*>(dst + c) = __floats2half2_rn(dq[j][2 * rrow] * a.scale, dq[j][2 * rrow + 1] * a.scale);
+    }
+  }
+}
+
+// kMode: 0 = dK and dV in one sweep; 1 = dV only; 2 = dK only (head dim 160: the two accumulators do not fit the register file together)
+template <int D, int kMode>
+__global__ void __launch_bounds__(kAbThreads) attention_bwd_dkdv_kernel(AttnBwdArgs a) {
+  using Cfg = AttnBwdCfg<D>;
+  extern __shared__ __align__(16) uint8_t ab_raw[];
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(ab_raw);
+  __nv_bfloat16* sdO = sQ + Cfg::kTileElems;
+  __nv_bfloat16* sK = sdO + Cfg::kTileElems;
+  __nv_bfloat16* sV = sK + Cfg::kTileElems;
+  float* sL = reinterpret_cast<float*>(sV + Cfg::kTileElems);
+  float* sDs = sL + 64;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int k0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+  const long long qrow0 = static_cast<long long>(b) * a.nq, krow0 = static_cast<long long>(b) * a.nk;
+  const long long stat0 = (static_cast<long long>(b) * a.heads + h) * a.nq;
+  ab_load_tile<D, false>(sK, a.k + krow0 * a.ldk, a.ldk, k0, a.nk, h * D);
+  ab_load_tile<D, false>(sV, a.v + krow0 * a.ldv, a.ldv, k0, a.nk, h * D);
+  const int r0 = warp * 16;
+  float dk[kMode != 1 ? Cfg::DP / 8 : 1][4], dv[kMode != 2 ? Cfg::DP / 8 : 1][4];
+#pragma unroll
+  for (int j = 0; j < (kMode != 1 ? Cfg::DP / 8 : 1); ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dk[j][i] = 0.f;
+#pragma unroll
+  for (int j = 0; j < (kMode != 2 ? Cfg::DP / 8 : 1); ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dv[j][i] = 0.f;
+  const int qtiles = (a.nq + 63) / 64;
+  for (int qt = 0; qt < qtiles; ++qt) {
+    __syncthreads();
+    ab_load_tile<D, false>(sQ, a.q + qrow0 * a.ldq, a.ldq, qt * 64, a.nq, h * D);
+    ab_load_tile<D, true>(sdO, a.d_o + qrow0 * a.lddo, a.lddo, qt * 64, a.nq, h * D);
+    if (threadIdx.x < 64) {
+      const int qi = qt * 64 + threadIdx.x;
+      sL[threadIdx.x] = qi < a.nq ? a.lse[stat0 + qi] : 0.f;
+      sDs[threadIdx.x] = qi < a.nq ? a.dsum[stat0 + qi] : 0.f;
+    }
+    __syncthreads();
+    float s[8][4];
+    ab_mma_nt<D>(s, sK, r0, sQ, lane);            // S^T: rows = keys, cols = queries
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int qc = j * 8 + 2 * t + (i & 1);
+        s[j][i] = (qt * 64 + qc < a.nq) ? exp2f(s[j][i] * a.scale_log2 - sL[qc]) : 0.f;   // P^T
+      }
+    if constexpr (kMode != 2) ab_mma_pn<D>(dv, s, sdO, lane);
+    if constexpr (kMode != 1) {
+      float dp[8][4];
+      ab_mma_nt<D>(dp, sV, r0, sdO, lane);        // dP^T
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int qc = j * 8 + 2 * t + (i & 1);
+          s[j][i] *= dp[j][i] - sDs[qc];           // dS^T
+        }
+      ab_mma_pn<D>(dk, s, sQ, lane);
+    }
+  }
+#pragma unroll
+  for (int rrow = 0; rrow < 2; ++rrow) {
+    const int ki = k0 + r0 + g + 8 * rrow;
+    if (ki >= a.nk) continue;
+#pragma unroll
+    for (int j = 0; j < Cfg::DP / 8; ++j) {
+      const int c = j * 8 + 2 * t;
+      if (c >= D) continue;
+      if constexpr (kMode != 1)
+        *reinterpret_cast<__half2*>(a.dk + (krow0 + ki) * a.lddk + h * D + c) = __floats2half2_rn(dk[j][2 * rrow] * a.scale, dk[j][2 * rrow + 1] * a.scale);
+      if constexpr (kMode != 2)
+        *reinterpret_cast<__half2*>(a.dv + (krow0 + ki) * a.lddv + h * D + c) = __floats2half2_rn(dv[j][2 * rrow], dv[j][2 * rrow + 1]);
+    }
+  }
+}
+
+}  // namespace mrisr

@@ -8,6 +8,7 @@ viewed as ``[B*H*W, C]`` is the token matrix of the transformer blocks.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -32,6 +33,7 @@ def _launch(cls: str, work: float, t: Tensor, code_fn, what: str, kernels: int =
     _lib.check(code_fn(), what, kernels)
     e1.record(st)
     PROFILE.append((cls, float(work), e0, e1, detail))
+_NO_GN_STATS = bool(os.environ.get("MRISR_NO_GN_STATS"))     # A/B runs: GroupNorm computes its own statistics (two kernels)
 _DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 _H16 = (torch.bfloat16, torch.float16)     # 16-bit activation formats: bf16 everywhere, IEEE half for the residual stream
 F16_OUT, F16_RES1, F16_RES2, F16_AB = 1, 2, 4, 8
@@ -175,7 +177,7 @@ def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[T
     g.reserved = _dbg
     g.f16_flags = f16
     part = None
-    if gn_stats:
+    if gn_stats and not _NO_GN_STATS:
         if M % 128 or out_fp32 or n_store != N:
             raise ValueError("gemm: gn_stats needs M % 128 == 0, a 16-bit output and n_store == N")
         part = torch.empty(((4 if up2x else 1) * (M // 128), N, 2), device=a1.device, dtype=torch.float32)
@@ -509,3 +511,124 @@ def device_info() -> Tuple[int, int]:
     sms, cc = C.c_int(0), C.c_int(0)
     _lib.check(_lib.load().mrisr_device_info(C.byref(sms), C.byref(cc)), "mrisr_device_info")
     return sms.value, cc.value
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# Backward-pass wrappers of the LoRA fine-tune step (csrc/train.cuh).  Gradient activations are float16 (loss-scaled).
+def groupnorm_backward(x1: Tensor, dz: Tensor, gamma: Tensor, beta: Tensor, groups: int, eps: float, silu: bool,
+                       x2: Optional[Tensor] = None) -> Tuple[Tensor, Optional[Tensor]]:
+    """dz ``[B, H, W, c1+c2]`` (float16, dense) -> (dx1 ``[B*H*W, c1]``, dx2 ``[B*H*W, c2]`` | None), float16, dense."""
+    lib = _lib.load()
+    _cuda16(x1, "groupnorm_backward.x1")
+    _cuda(dz, "groupnorm_backward.dz", torch.float16)
+    B, H, W, c1 = x1.shape
+    c2, ld2 = (x2.shape[3], x2.stride(2)) if x2 is not None else (0, 0)
+    C = c1 + c2
+    if not dz.is_contiguous() or dz.numel() != B * H * W * C:
+        raise ValueError("groupnorm_backward: dz must be dense [B, H, W, c1+c2]")
+    f16 = (1 if x1.dtype == torch.float16 else 0) | (2 if (x2 is not None and x2.dtype == torch.float16) else 0)
+    dx1 = torch.empty((B * H * W, c1), device=x1.device, dtype=torch.float16)
+    dx2 = torch.empty((B * H * W, c2), device=x1.device, dtype=torch.float16) if x2 is not None else None
+    _lib.check(lib.mrisr_groupnorm_backward(x1.data_ptr(), x1.stride(2), c1, _ptr(x2), ld2, c2, dz.data_ptr(), B, H * W, groups,
+                                            gamma.data_ptr(), beta.data_ptr(), float(eps), int(silu), dx1.data_ptr(), c1,
+                                            _ptr(dx2), c2, f16, _stream(x1)), "mrisr_groupnorm_backward")
+    return dx1, dx2
+
+
+def layernorm_backward(x: Tensor, dy: Tensor, gamma: Tensor, eps: float = 1e-5, dres: Optional[Tensor] = None) -> Tensor:
+    lib = _lib.load()
+    _cuda16(x, "layernorm_backward.x")
+    _cuda(dy, "layernorm_backward.dy", torch.float16)
+    rows, c = x.shape
+    if not dy.is_contiguous() or (dres is not None and (not dres.is_contiguous() or dres.dtype != torch.float16)):
+        raise ValueError("layernorm_backward: dy / dres must be dense float16")
+    dx = torch.empty((rows, c), device=x.device, dtype=torch.float16)
+    _lib.check(lib.mrisr_layernorm_backward(x.data_ptr(), _rows(x, "x"), int(x.dtype == torch.float16), dy.data_ptr(), gamma.data_ptr(),
+                                            float(eps), _ptr(dres), dx.data_ptr(), rows, c, _stream(x)), "mrisr_layernorm_backward")
+    return dx
+
+
+def geglu_forward(pre: Tensor) -> Tensor:
+    lib = _lib.load()
+    _cuda(pre, "geglu_forward.pre", torch.bfloat16)
+    M, f2 = pre.shape
+    out = torch.empty((M, f2 // 2), device=pre.device, dtype=torch.bfloat16)
+    _lib.check(lib.mrisr_geglu_forward(pre.contiguous().data_ptr(), out.data_ptr(), M, f2 // 2, _stream(pre)), "mrisr_geglu_forward")
+    return out
+
+
+def geglu_backward(pre: Tensor, df: Tensor) -> Tensor:
+    lib = _lib.load()
+    _cuda(pre, "geglu_backward.pre", torch.bfloat16)
+    _cuda(df, "geglu_backward.df", torch.float16)
+    M, f2 = pre.shape
+    out = torch.empty((M, f2), device=pre.device, dtype=torch.float16)
+    _lib.check(lib.mrisr_geglu_backward(pre.data_ptr(), df.contiguous().data_ptr(), out.data_ptr(), M, f2 // 2, _stream(pre)),
+               "mrisr_geglu_backward")
+    return out
+
+
+def zero_insert2x(x: Tensor) -> Tensor:
+    lib = _lib.load()
+    _cuda(x, "zero_insert2x.x", torch.float16)
+    B, h, w, c = x.shape
+    out = torch.empty((B, 2 * h, 2 * w, c), device=x.device, dtype=torch.float16)
+    _lib.check(lib.mrisr_zero_insert2x(x.contiguous().data_ptr(), out.data_ptr(), B, h, w, c, _stream(x)), "mrisr_zero_insert2x")
+    return out
+
+
+def sumpool2(x: Tensor) -> Tensor:
+    lib = _lib.load()
+    _cuda(x, "sumpool2.x", torch.float16)
+    B, h2, w2, c = x.shape
+    out = torch.empty((B, h2 // 2, w2 // 2, c), device=x.device, dtype=torch.float16)
+    _lib.check(lib.mrisr_sumpool2(x.contiguous().data_ptr(), out.data_ptr(), B, h2 // 2, w2 // 2, c, _stream(x)), "mrisr_sumpool2")
+    return out
+
+
+def mse_grad(pred: Tensor, target: Tensor, grad_scale: float, cpad: int = 64) -> Tuple[Tensor, Tensor]:
+    """fp32 NCHW pred / target -> (loss fp32 [1], d loss / d pred * grad_scale as float16 NHWC ``[B, H, W, cpad]``)."""
+    lib = _lib.load()
+    _cuda(pred, "mse_grad.pred", torch.float32)
+    _cuda(target, "mse_grad.target", torch.float32)
+    B, c, H, W = pred.shape
+    dout = torch.empty((B, H, W, cpad), device=pred.device, dtype=torch.float16)
+    ws = torch.empty((1024,), device=pred.device, dtype=torch.float32)
+    loss = torch.empty((1,), device=pred.device, dtype=torch.float32)
+    _lib.check(lib.mrisr_mse_grad(pred.contiguous().data_ptr(), target.contiguous().data_ptr(), B, c, H * W, cpad, float(grad_scale),
+                                  dout.data_ptr(), ws.data_ptr(), loss.data_ptr(), _stream(pred)), "mrisr_mse_grad", kernels=2)
+    return loss, dout
+
+
+def xty64(x64: Tensor, y: Tensor, out: Tensor, scale: float = 1.0) -> Tensor:
+    """out fp32 ``[64, Q]`` = scale * x64^T y   (x64 ``[M, 64]``, y ``[M, Q]``, 16-bit each; row-strided views allowed)."""
+    lib = _lib.load()
+    _cuda16(x64, "xty64.x")
+    _cuda16(y, "xty64.y")
+    M, q = y.shape
+    if x64.shape[0] != M or x64.shape[1] != 64 or tuple(out.shape) != (64, q) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("xty64: shapes must be x [M, 64], y [M, Q], out fp32 [64, Q]")
+    ws = torch.empty((lib.mrisr_xty64_workspace_floats(M, q),), device=y.device, dtype=torch.float32)
+    _lib.check(lib.mrisr_xty64(x64.data_ptr(), _rows(x64, "x"), int(x64.dtype == torch.float16), y.data_ptr(), _rows(y, "y"),
+                               int(y.dtype == torch.float16), M, q, float(scale), ws.data_ptr(), out.data_ptr(), _stream(y)),
+               "mrisr_xty64", kernels=2)
+    return out
+
+
+def attention_backward(q: Tensor, k: Tensor, v: Tensor, o: Tensor, d_o: Tensor, batch: int, heads: int,
+                       dq: Tensor, dk: Tensor, dv: Tensor) -> None:
+    """Backward of ``attention`` (no K/V broadcast): q/k/v/o bf16 (column-slice views allowed), d_o float16; writes the float16
+    views dq / dk / dv (e.g. the three column ranges of one ``[M, 3C]`` buffer)."""
+    lib = _lib.load()
+    for n, t in (("q", q), ("k", k), ("v", v), ("o", o)):
+        _cuda(t, f"attention_backward.{n}", torch.bfloat16)
+    for n, t in (("d_o", d_o), ("dq", dq), ("dk", dk), ("dv", dv)):
+        _cuda(t, f"attention_backward.{n}", torch.float16)
+    c = q.shape[1]
+    d = c // heads
+    nq, nk = q.shape[0] // batch, k.shape[0] // batch
+    ws = torch.empty((2 * batch * heads * nq,), device=q.device, dtype=torch.float32)
+    _lib.check(lib.mrisr_attention_backward(q.data_ptr(), _rows(q, "q"), k.data_ptr(), _rows(k, "k"), v.data_ptr(), _rows(v, "v"),
+                                            o.data_ptr(), _rows(o, "o"), d_o.data_ptr(), _rows(d_o, "d_o"), dq.data_ptr(), _rows(dq, "dq"),
+                                            dk.data_ptr(), _rows(dk, "dk"), dv.data_ptr(), _rows(dv, "dv"), ws.data_ptr(), batch, nq, nk,
+                                            heads, d, _stream(q)), "mrisr_attention_backward", kernels=2)

@@ -16,6 +16,7 @@ one ``mrisr_attention`` per attention, one GroupNorm / LayerNorm kernel per norm
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from types import SimpleNamespace
 from typing import Dict, List, Optional, Sequence, Tuple, Union
@@ -27,6 +28,7 @@ from .packing import (LORA_PAD, pack_conv1x1, pack_conv3x3, pack_geglu, pack_lor
                       pad_cols, pad_rows, pad_to)
 
 Tensor = torch.Tensor
+_NO_UP_FOLD = bool(os.environ.get("MRISR_NO_UP_FOLD"))   # A/B runs: materialise the nearest-2x intermediate
 
 
 @dataclass
@@ -529,7 +531,7 @@ class UNet2DConditionB200:
             if blk["us"] is not None:
                 wu, bu, wu_plain = blk["us"]
                 b_, hh, ww, cc = s.shape
-                if hh * ww >= 32:
+                if hh * ww >= 32 and not _NO_UP_FOLD:
                     # Upsample2D: the 4x-sized nearest-neighbour intermediate is never materialised (four sub-pixel 2x2 convs)
                     s0 = ops.gemm(s, wu, bias=bu, conv=True, up2x=True, out_dtype=self.stream_dtype, gn_stats=(hh * ww) % 128 == 0)
                 else:

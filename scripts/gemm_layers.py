@@ -11,12 +11,12 @@ unet = UNet2DConditionB200(cfg, device=dev); unet.load_state_dict(init_unet_para
 x = torch.randn(B, 4, 64, 64, device=dev); ehs = torch.randn(1, 77, 768, device=dev)
 feats = [torch.randn(B, 64 >> i, 64 >> i, c, device=dev).to(torch.bfloat16).permute(0, 3, 1, 2) for i, c in enumerate((320, 640, 1280, 1280))]
 unet(x, 500, encoder_hidden_states=ehs, down_intrablock_additional_residuals=feats); torch.cuda.synchronize()
-ops.GEMM_PROFILE = []
+ops.PROFILE = []
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); unet(x, 500, encoder_hidden_states=ehs, down_intrablock_additional_residuals=feats); e1.record(); torch.cuda.synchronize()
-prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
+prof, ops.PROFILE = [q for q in ops.PROFILE if q[0] in ('gemm', 'conv3x3')], None
 agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
-for fl, taps, a, b, shp in prof:
+for cls, fl, a, b, shp in prof:
     k = shp; agg[k][0] += 1; agg[k][1] += a.elapsed_time(b); agg[k][2] += fl
 tot = sum(v[1] for v in agg.values())
 print(f"forward {e0.elapsed_time(e1):.2f} ms, gemm total {tot:.2f} ms over {len(prof)} launches")

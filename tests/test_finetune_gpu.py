@@ -1,0 +1,234 @@
+"""LoRA fine-tune step (BASELINE config 4): every backward kernel against torch autograd of the
+same op in fp32, then the whole step -- forward shifting, UNet forward, MSE, backward into the LoRA matrices, clip, AdamW --
+against ``oracle/finetune_oracle.py`` (autograd through the fp32 oracle UNet).  Tolerance: LoRA gradients <= 1e-2 relative L2
+(the north_star's bf16 figure for the forward pass, applied to the backward pass)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+REL_L2 = 1e-2
+
+
+def _rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
+
+
+def _r(shape, seed, scale=1.0, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype)
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from mri_diffusion_superresolution_b200 import ops as o
+    return o
+
+
+@pytest.mark.parametrize("B,H,C1,C2,silu,eps", [(2, 16, 64, 0, True, 1e-5), (2, 32, 320, 0, True, 1e-5), (1, 16, 1280, 640, True, 1e-5),
+                                                  (2, 8, 640, 320, True, 1e-5), (2, 16, 320, 0, False, 1e-6)])
+def test_groupnorm_backward(ops, B, H, C1, C2, silu, eps):
+    x1 = (_r((B, H, H, C1), 1) + 0.3).to(torch.float16)
+    x2 = (_r((B, H, H, C2), 2) * 1.5).to(torch.bfloat16) if C2 else None
+    C = C1 + C2
+    gamma, beta = _r((C,), 3, 0.1) + 1, _r((C,), 4, 0.1)
+    dz = _r((B, H, H, C), 5, 0.5).to(torch.float16)
+    xs = [x1.float().requires_grad_(True)] + ([x2.float().requires_grad_(True)] if C2 else [])
+    xin = torch.cat(xs, -1).permute(0, 3, 1, 2)
+    y = F.group_norm(xin, 32, gamma, beta, eps)
+    y = F.silu(y) if silu else y
+    y.backward(dz.float().permute(0, 3, 1, 2))
+    dx1, dx2 = ops.groupnorm_backward(x1.cuda(), dz.cuda(), gamma.cuda(), beta.cuda(), 32, eps, silu, x2=None if x2 is None else x2.cuda())
+    assert _rel(dx1.view(B, H, H, C1), xs[0].grad) < 3e-3
+    if C2:
+        assert _rel(dx2.view(B, H, H, C2), xs[1].grad) < 3e-3
+
+
+@pytest.mark.parametrize("rows,C", [(300, 320), (77, 1280), (1000, 64)])
+def test_layernorm_backward(ops, rows, C):
+    x = _r((rows, C), 6).to(torch.float16)
+    gamma, beta = _r((C,), 7, 0.1) + 1, _r((C,), 8, 0.1)
+    dy, dres = _r((rows, C), 9, 0.5).to(torch.float16), _r((rows, C), 10, 0.5).to(torch.float16)
+    xr = x.float().requires_grad_(True)
+    F.layer_norm(xr, (C,), gamma, beta, 1e-5).backward(dy.float())
+    dx = ops.layernorm_backward(x.cuda(), dy.cuda(), gamma.cuda(), 1e-5, dres=dres.cuda())
+    assert _rel(dx, xr.grad + dres.float()) < 3e-3
+    assert _rel(ops.layernorm_backward(x.cuda(), dy.cuda(), gamma.cuda(), 1e-5), xr.grad) < 3e-3
+
+
+def test_geglu_forward_backward(ops):
+    M, Fh = 500, 1280
+    pre = _r((M, 2 * Fh), 11).to(torch.bfloat16)
+    df = _r((M, Fh), 12, 0.5).to(torch.float16)
+    pr = pre.float().requires_grad_(True)
+    a, g = pr.chunk(2, -1)
+    out = a * F.gelu(g)
+    out.backward(df.float())
+    assert _rel(ops.geglu_forward(pre.cuda()), out.detach()) < 4e-3
+    assert _rel(ops.geglu_backward(pre.cuda(), df.cuda()), pr.grad) < 3e-3
+
+
+@pytest.mark.parametrize("B,heads,d,nq,nk", [(2, 8, 40, 256, 256), (1, 8, 40, 1024, 1024), (2, 8, 40, 256, 77), (2, 8, 80, 256, 256),
+                                             (2, 8, 160, 64, 64), (2, 8, 160, 64, 77), (2, 8, 16, 16, 16), (3, 8, 8, 64, 77), (1, 8, 16, 100, 77)])
+def test_attention_backward(ops, B, heads, d, nq, nk):
+    C = heads * d
+    q, k, v = (_r((B * n, C), 20 + i).to(torch.bfloat16) for i, n in enumerate((nq, nk, nk)))
+    d_o = _r((B * nq, C), 23, 0.5).to(torch.float16)
+
+    def split(t, n):
+        return t.float().view(B, n, heads, d).permute(0, 2, 1, 3)
+
+    qr, kr, vr = (split(t, n).requires_grad_(True) for t, n in ((q, nq), (k, nk), (v, nk)))
+    o_ref = F.scaled_dot_product_attention(qr, kr, vr)
+    o_ref.backward(split(d_o, nq))
+    o = ops.attention(q.cuda(), k.cuda(), v.cuda(), B, heads)
+    dq = torch.empty((B * nq, C), device="cuda", dtype=torch.float16)
+    dkv = torch.empty((B * nk, 2 * C), device="cuda", dtype=torch.float16)
+    ops.attention_backward(q.cuda(), k.cuda(), v.cuda(), o, d_o.cuda(), B, heads, dq, dkv[:, :C], dkv[:, C:])
+
+    def merge(t, n):
+        return t.permute(0, 2, 1, 3).reshape(B * n, C)
+
+    assert _rel(dq, merge(qr.grad, nq)) < 8e-3
+    assert _rel(dkv[:, :C], merge(kr.grad, nk)) < 8e-3
+    assert _rel(dkv[:, C:], merge(vr.grad, nk)) < 8e-3
+
+
+def test_xty64_and_spatial_helpers(ops):
+    M, Q = 8192 + 77, 960
+    x, y = _r((M, 64), 30).to(torch.float16), _r((M, Q + 64), 31).to(torch.bfloat16)
+    out = torch.empty((64, Q), device="cuda", dtype=torch.float32)
+    ops.xty64(x.cuda(), y.cuda()[:, :Q], out, scale=0.25)
+    ref = 0.25 * x.float().t() @ y.float()[:, :Q]
+    assert _rel(out, ref) < 1e-5
+    again = torch.empty_like(out)
+    ops.xty64(x.cuda(), y.cuda()[:, :Q], again, scale=0.25)
+    assert torch.equal(out, again)                                  # fixed-order reduction: bit-reproducible
+    g = _r((2, 8, 8, 64), 32).to(torch.float16)
+    z = ops.zero_insert2x(g.cuda()).cpu()
+    assert torch.equal(z[:, ::2, ::2], g) and float(z[:, 1::2].abs().max()) == 0 and float(z[:, :, 1::2].abs().max()) == 0
+    u = _r((2, 16, 16, 64), 33).to(torch.float16)
+    s = ops.sumpool2(u.cuda()).cpu().float()
+    ref = F.avg_pool2d(u.float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1) * 4
+    assert _rel(s, ref) < 2e-3
+
+
+def test_conv_dgrad_forms(ops):
+    """The three convolution data-gradients of the UNet as forward convs with the tap-flipped filter: stride 1, stride 2
+    (zero insertion) and nearest-2x upsample (+ 2x2 sum)."""
+    from mri_diffusion_superresolution_b200.finetune import _dgrad3x3
+    B, H, Ci, Co = 2, 16, 64, 128
+    w = _r((Co, Ci, 3, 3), 40, 1 / math.sqrt(9 * Ci)).to(torch.bfloat16).float()
+    wd = _dgrad3x3(w).to(torch.float16).cuda()
+    x = _r((B, Ci, H, H), 41).requires_grad_(True)
+    dy = _r((B, Co, H, H), 42, 0.5).to(torch.float16)
+    F.conv2d(x, w, padding=1).backward(dy.float())
+    got = ops.gemm(dy.permute(0, 2, 3, 1).contiguous().cuda(), wd, conv=True, out_dtype=torch.float16).view(B, H, H, Ci)
+    assert _rel(got.permute(0, 3, 1, 2), x.grad) < 3e-3
+    x2 = _r((B, Ci, H, H), 43).requires_grad_(True)
+    dy2 = _r((B, Co, H // 2, H // 2), 44, 0.5).to(torch.float16)
+    F.conv2d(x2, w, stride=2, padding=1).backward(dy2.float())
+    z = ops.zero_insert2x(dy2.permute(0, 2, 3, 1).contiguous().cuda())
+    got2 = ops.gemm(z, wd, conv=True, out_dtype=torch.float16).view(B, H, H, Ci)
+    assert _rel(got2.permute(0, 3, 1, 2), x2.grad) < 3e-3
+    x3 = _r((B, Ci, H // 2, H // 2), 45).requires_grad_(True)
+    F.conv2d(F.interpolate(x3, scale_factor=2, mode="nearest"), w, padding=1).backward(dy.float())
+    du = ops.gemm(dy.permute(0, 2, 3, 1).contiguous().cuda(), wd, conv=True, out_dtype=torch.float16).view(B, H, H, Ci)
+    got3 = ops.sumpool2(du)
+    assert _rel(got3.permute(0, 3, 1, 2), x3.grad) < 3e-3
+
+
+def test_mse_grad(ops):
+    pred, tgt = _r((2, 4, 16, 16), 50), _r((2, 4, 16, 16), 51)
+    loss, d = ops.mse_grad(pred.cuda(), tgt.cuda(), 2.0 * 1024 / pred.numel(), cpad=64)
+    assert abs(float(loss) - float(((pred - tgt) ** 2).mean())) < 1e-6
+    ref = (2.0 * 1024 / pred.numel()) * (pred - tgt).permute(0, 2, 3, 1)
+    assert _rel(d[..., :4], ref) < 1e-3 and float(d[..., 4:].abs().max()) == 0
+
+
+SMALL = dict(block_out_channels=(64, 128, 128), down_has_attn=(True, True, False), layers_per_block=1, num_heads=8,
+             cross_attention_dim=64, sample_size=16, lora_rank=4, lora_alpha=8.0)
+WIDE = dict(block_out_channels=(320,), down_has_attn=(True,), layers_per_block=1, num_heads=8, cross_attention_dim=768,
+            sample_size=64, lora_rank=16, lora_alpha=16.0)
+
+
+def _setup(kw, seed=0):
+    from oracle import parity_gate as pg
+    from oracle import unet_oracle as uo
+    from mri_diffusion_superresolution_b200.finetune import LoRAFineTuner
+    from mri_diffusion_superresolution_b200.unet import UNet2DConditionB200, UNetConfig
+    ocfg = uo.UNetConfig(**kw)
+    params = pg.round_bf16(uo.init_params(ocfg, seed=seed))
+    unet = UNet2DConditionB200(UNetConfig(**kw))
+    unet.load_state_dict(params)
+    return ocfg, params, unet, LoRAFineTuner(unet, params)
+
+
+def _batch(kw, B, seed, with_feats):
+    g = torch.Generator().manual_seed(seed)
+    s, ch = kw["sample_size"], kw["block_out_channels"]
+    hr, lr, noise = (torch.randn(B, 4, s, s, generator=g) * 0.8 for _ in range(3))
+    t = torch.tensor([700, 40][:B] if B <= 2 else [700, 40, 333][:B])
+    ehs = torch.randn(B, 77, kw["cross_attention_dim"], generator=g)
+    feats = [torch.randn(B, c, s >> i, s >> i, generator=g) * 0.5 for i, c in enumerate(ch)] if with_feats else None
+    return hr, lr, t, noise, ehs, feats
+
+
+@pytest.mark.parametrize("name,kw,B,with_feats", [("reduced net", SMALL, 2, True), ("full-width 64x64 level", WIDE, 2, False)])
+def test_lora_gradients_vs_oracle_autograd(name, kw, B, with_feats):
+    from oracle import finetune_oracle as fo
+    ocfg, params, unet, ft = _setup(kw)
+    hr, lr, t, noise, ehs, feats = _batch(kw, B, 5, with_feats)
+    torch.set_num_threads(os.cpu_count() or 8)
+    loss_ref, grads_ref, eps_ref = fo.loss_and_lora_grads(params, ocfg, hr, lr, t, noise, ehs, feats)
+    loss, eps_hat = ft.forward_backward(hr.cuda(), lr.cuda(), t.cuda(), noise.cuda(), ehs.cuda(),
+                                        None if feats is None else [f.cuda() for f in feats])
+    assert _rel(eps_hat, eps_ref) < REL_L2
+    assert abs(float(loss) - loss_ref) < 2e-2 * loss_ref
+    got = ft.lora_grads()
+    assert sorted(got) == sorted(grads_ref)
+    num = sum(float(((got[k].cpu() - grads_ref[k]) ** 2).sum()) for k in got)
+    den = sum(float((grads_ref[k] ** 2).sum()) for k in got)
+    worst = max((_rel(got[k], grads_ref[k]), k) for k in got)
+    print(f"{name}: LoRA gradient rel-L2 over {len(got)} tensors {math.sqrt(num / den):.2e}; worst single tensor {worst[0]:.2e} ({worst[1]})")
+    assert math.sqrt(num / den) < REL_L2
+    assert worst[0] < 5 * REL_L2
+
+
+def test_finetune_step_updates_parameters_and_packed_operands():
+    """clip + AdamW against the oracle's formulas on the CUDA gradients, and the refreshed packed operands: after the step
+    the SAME UNet object (inference path) must agree with the oracle evaluated at the updated LoRA matrices."""
+    from oracle import finetune_oracle as fo
+    from oracle import unet_oracle as uo
+    ocfg, params, unet, ft = _setup(SMALL, seed=2)
+    hr, lr, t, noise, ehs, feats = _batch(SMALL, 2, 9, False)
+    lr_rate = 1e-2                                        # large, so that the update is far above the bf16 rounding of the operands
+    before = ft.lora_state_dict()
+    loss0, _ = ft.forward_backward(hr.cuda(), lr.cuda(), t.cuda(), noise.cuda(), ehs.cuda())
+    grads = {k: v.cpu() for k, v in ft.lora_grads().items()}
+    info = ft.optimizer_step(lr_rate).cpu()
+    norm_ref, coef_ref = fo.clip_coef(grads, 1.0)
+    assert abs(float(info[0]) - norm_ref) < 1e-3 * norm_ref and abs(float(info[1]) - coef_ref) < 1e-3
+    after = ft.lora_state_dict()
+    newp = dict(params)
+    for k in grads:
+        p_ref, _, _ = fo.adamw_step(before[k].cpu(), grads[k] * coef_ref, torch.zeros_like(grads[k]), torch.zeros_like(grads[k]), 1, lr_rate)
+        assert _rel(after[k], p_ref) < 1e-4, k
+        newp[k] = after[k].cpu()
+    x = torch.randn(2, 4, 16, 16, generator=torch.Generator().manual_seed(3))
+    ref = uo.unet_forward(newp, x, torch.tensor(500), ehs, ocfg)
+    old = uo.unet_forward(params, x, torch.tensor(500), ehs, ocfg)
+    got = unet(x.cuda(), torch.tensor(500), encoder_hidden_states=ehs.cuda()).sample
+    assert _rel(old, ref) > 3 * _rel(got, ref)             # the step moved the network, and the CUDA UNet moved with it
+    assert _rel(got, ref) < REL_L2
+    losses = [float(loss0)]
+    for _ in range(4):                                     # a few more steps on the same batch: the loss must go down
+        l, _ = ft.step(hr.cuda(), lr.cuda(), t.cuda(), noise.cuda(), ehs.cuda(), lr=lr_rate)
+        losses.append(float(l))
+    assert losses[-1] < losses[0]
