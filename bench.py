@@ -169,6 +169,194 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+GFLOP_FT_STEP = 807.83 + 681.78 + 2.5 * 126.05 + 2 * 4.56   # per slice: forward + dgrad of every conv / linear + attention
+                                                             # backward (5 instead of 2 matmuls) + the rank-16 weight gradients
+
+
+def run_finetune(args):
+    """BASELINE config 4: LoRA fine-tune steps/sec on 512x512 slices (64x64 latents), full SD-1.5 + LoRA r16 (+ T2I features)."""
+    import torch
+    import torch.distributed as dist
+    from mri_diffusion_superresolution_b200 import _lib
+    from mri_diffusion_superresolution_b200.finetune import LoRAFineTuner
+    from mri_diffusion_superresolution_b200.synthetic import init_unet_params
+    from mri_diffusion_superresolution_b200.unet import UNet2DConditionB200, UNetConfig
+
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch if args.batch != 32 else 2            # reference run config: train_batch_size 2 (ResDif_execution.ipynb:599)
+    peaks = load_peaks()
+    cfg = UNetConfig(lora_rank=16, lora_alpha=16.0)
+    unet = UNet2DConditionB200(cfg, device=dev)
+    params = init_unet_params(cfg, seed=0, device=dev)
+    unet.load_state_dict(params)
+    ft = LoRAFineTuner(unet, params)
+    del params
+    torch.cuda.empty_cache()
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    mk = lambda *shape: torch.randn(shape, generator=g, device=dev)
+    hr, lr_, noise = mk(B, 4, 64, 64), mk(B, 4, 64, 64), mk(B, 4, 64, 64)
+    ehs = mk(B, 77, 768)
+    feats = [mk(B, c, 64 >> i, 64 >> i) * 0.5 for i, c in enumerate((320, 640, 1280, 1280))]
+    ts = torch.randint(0, 1000, (B,), generator=g, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step():
+        return ft.step(hr, lr_, ts, noise, ehs, lr=1e-5, down_intrablock_additional_residuals=feats)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    n0 = _lib.LAUNCHES[0]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = max(args.steps, 5)
+    e0.record()
+    for _ in range(steps):
+        loss, info = step()
+    e1.record()
+    barrier()
+    clk = clocks.stop()
+    launches = _lib.LAUNCHES[0] - n0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    value = world * steps / (ms / 1e3)
+    # end to end: the batch comes from pinned host memory every step, the loss goes back to the host
+    hbufs = [t.cpu().pin_memory() for t in (hr, lr_, noise, ehs)] + [f.cpu().pin_memory() for f in feats]
+    h_ts = ts.cpu().pin_memory()
+
+    def step_e2e():
+        d = [t.to(dev, non_blocking=True) for t in hbufs]
+        l, _ = ft.step(d[0], d[1], h_ts.to(dev, non_blocking=True), d[2], d[3], lr=1e-5, down_intrablock_additional_residuals=d[4:])
+        return float(l.cpu())
+
+    step_e2e()
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(steps):
+        last = step_e2e()
+    barrier()
+    w = torch.tensor([time.perf_counter() - w0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(w, op=dist.ReduceOp.MAX)
+    e2e = {"value": world * steps / float(w.item()), "unit": "steps/s", "h2d_bytes_per_step": int(sum(t.numel() * 4 for t in hbufs) + 8 * B),
+           "d2h_bytes_per_step": 4}
+    tflops = value / world * B * GFLOP_FT_STEP / 1e3
+    if rank == 0:
+        print(json.dumps({
+            "metric": "LoRA fine-tune steps/sec (fwd + bwd through the LoRA matrices + clip + AdamW, 512^2 slices)", "value": value,
+            "unit": "steps/s", "n_gpus": world, "steps": steps, "warmup": max(3, args.warmup), "ms_per_step": ms / steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 forward / f16 gradients (loss scale 4096), fp32 optimizer",
+            "data": "synthetic",
+            "config": {"workload": "sd15_unet_lora16_finetune_step_512px", "batch_per_gpu": B, "global_batch": B * world, "lora_rank": 16,
+                       "trainable_params": ft.n_params, "optimizer": "AdamW beta 0.9/0.999 wd 1e-2 eps 1e-8, max_grad_norm 1.0",
+                       "parallelism": f"replicas x{world} (no gradient all-reduce: the reference's config is single-process)",
+                       "cuda_graph": False, "l2": "working set >> 126 MB L2"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "final_loss": float(loss), "grad_norm": float(info[0]),
+            "roofline": {"bound": "tensor", "kernel": "whole step (launch-bound at batch 2: ~2.6 k kernel launches, eager)",
+                         "achieved": tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": tflops / peaks["bf16_sustained"],
+                         "traffic": None, "algorithmic_gflop_per_slice_step": GFLOP_FT_STEP},
+            "cpu_baseline": None}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_volumes(args):
+    """BASELINE config 5: a fixed sweep of --volumes synthetic volumes x 128 axial slices through the product entry point
+    VolumePipeline.run_sweep (volume -> slices -> VAE encode -> 50-step loop -> VAE decode), slices sharded over the ranks, one
+    all_gather of the generated slices at the end.  STRONG scaling: the sweep does not grow with the GPU count."""
+    import torch
+    import torch.distributed as dist
+    from mri_diffusion_superresolution_b200 import _lib
+    from mri_diffusion_superresolution_b200.adapter import Adapter_XL
+    from mri_diffusion_superresolution_b200.pipeline import VolumePipeline
+    from mri_diffusion_superresolution_b200.sampler import SliceSampler
+    from mri_diffusion_superresolution_b200.scheduler import ResShiftScheduler
+    from mri_diffusion_superresolution_b200.synthetic import init_unet_params, init_vae_params
+    from mri_diffusion_superresolution_b200.unet import UNet2DConditionB200, UNetConfig
+    from mri_diffusion_superresolution_b200.vae import AutoencoderKLB200
+
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = UNetConfig(lora_rank=16, lora_alpha=16.0)
+    unet = UNet2DConditionB200(cfg, device=dev)
+    unet.load_state_dict(init_unet_params(cfg, seed=0, device=dev))
+    adapter = Adapter_XL(sk=True, device=dev, generator=torch.Generator().manual_seed(2))
+    vae = AutoencoderKLB200(device=dev)
+    vae.load_state_dict(init_vae_params(None, seed=5, device=dev))
+    torch.cuda.empty_cache()
+    sampler = SliceSampler(unet, ResShiftScheduler(), adapter, num_inference_steps=args.inference_steps, kind=args.sched)
+    pipe = VolumePipeline(sampler, vae, batch=args.batch)
+    V, D = args.volumes, 128
+    gvol = torch.Generator(device=dev).manual_seed(1234)
+    vols = [torch.rand((512, 512, D), generator=gvol, device=dev) * 900.0 for _ in range(V)]     # raw intensities, [H, W, D]
+    ehs = torch.randn((1, 77, 768), generator=torch.Generator(device=dev).manual_seed(1236), device=dev)
+    gen = torch.Generator(device=dev).manual_seed(7 + rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def sweep():
+        return pipe.run_sweep(vols, (0.0, 900.0), ehs, generator=gen)
+
+    pipe.run_sweep(vols[:1], (0.0, 900.0), ehs, generator=gen) if world == 1 else sweep()     # warm-up (graph capture, allocator)
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    n0 = _lib.LAUNCHES[0]
+    steps = max(1, min(args.steps, 2))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = sweep()
+    e1.record()
+    barrier()
+    clk = clocks.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    S = V * D
+    assert tuple(out.shape) == (S, 1, 512, 512) and bool(torch.isfinite(out).all())
+    value = S * steps / (ms / 1e3)
+    per_rank = -(-S // world)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "MRI slices/sec, volume sweep (volume -> slices -> VAE -> 50-step LoRA+T2I-Adapter loop -> VAE decode)", "value": value,
+            "unit": "slices/s", "n_gpus": world, "steps": steps, "warmup": 1, "ms_per_step": ms / steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"volume_sweep_{V}x{D}_slices_512px_50step", "volumes": V, "slices_per_volume": D, "total_slices": S,
+                       "slices_per_rank": per_rank, "batch_per_gpu": args.batch, "inference_steps": args.inference_steps,
+                       "parallelism": f"slice list sharded x{world} (parallel.sharded_apply), weights replicated, one NCCL all_gather of the generated slices",
+                       "entry_point": "pipeline.VolumePipeline.run_sweep", "cuda_graph": True},
+            "e2e": {"value": value, "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "note": "volumes are generated on the device; see the headline workload for the host-buffer number"},
+            "gpu_launches": int((_lib.LAUNCHES[0] - n0) + steps * (per_rank // args.batch) * args.inference_steps * (sampler.kernel_launches_per_step or 0)),
+            "clocks": clk, "roofline": None, "cpu_baseline": None}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -190,10 +378,20 @@ def main():
                     help="skip the step-0 parity gate against the CPU oracle (debugging only: a line printed without the gate "
                          "carries \"parity_gate\": null and is not a reportable number)")
     ap.add_argument("--profile-steps", type=int, default=20, help="eager steps timed per kernel class for the roofline list")
+    ap.add_argument("--workload", default="sample", choices=["sample", "finetune", "volumes"],
+                    help="sample: the headline 50-step loop (BASELINE config 3 / 2); finetune: one LoRA fine-tune step (config 4: "
+                         "fwd + bwd through the LoRA matrices + clip + AdamW, batch --batch, default 2); volumes: a FIXED sweep of "
+                         "--volumes synthetic volumes x 128 slices through VolumePipeline.run_sweep, slices sharded over the ranks "
+                         "(config 5, strong scaling)")
+    ap.add_argument("--volumes", type=int, default=8)
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "finetune":
+        return run_finetune(args)
+    if args.workload == "volumes":
+        return run_volumes(args)
     if args.warmup < 3:
         print(f"[bench] note: warmup {args.warmup} < 3 breaks the timing rules; use >= 3 for a reportable number", file=sys.stderr)
 

@@ -559,7 +559,8 @@ int mrisr_groupnorm_apply_stats(const void* x1, int64_t ld1, int c1, const float
   MRISR_REQUIRE((n_phases1 == 1 || n_phases1 == 4) && (c2 == 0 || n_phases2 == 1 || n_phases2 == 4), "groupnorm_apply_stats: n_phases must be 1 or 4");
   MRISR_REQUIRE(hw % (128 * n_phases1) == 0 && (c2 == 0 || hw % (128 * n_phases2) == 0), "groupnorm_apply_stats: hw / n_phases must be a multiple of 128 (the statistics' block size)");
   MRISR_REQUIRE(ldp1 >= c1 && (c2 == 0 || ldp2 >= c2), "groupnorm_apply_stats: ldp < channels");
-  MRISR_REQUIRE((reinterpret_cast<uintptr_t>(part1) & 7u) == 0 && (!part2 || (reinterpret_cast<uintptr_t>(part2) & 7u) == 0), "groupnorm_apply_stats: partials must be 8-byte aligned");
+  MRISR_REQUIRE((reinterpret_cast<uintptr_t>(part1) & 15u) == 0 && (!part2 || (reinterpret_cast<uintptr_t>(part2) & 15u) == 0) && ldp1 % 2 == 0 && ldp2 % 2 == 0,
+                "groupnorm_apply_stats: partials must be 16-byte aligned with an even row pitch");
   const int nvec = C / 8;
   if (nvec > 512) return fail(MRISR_E_UNSUPPORTED, "groupnorm_apply_stats: C = %d > 4096 unsupported", C);
   int R = 256 / nvec;
@@ -585,11 +586,8 @@ int mrisr_groupnorm_apply_stats(const void* x1, int64_t ld1, int c1, const float
   q.nblk[0] = hw / (128 * n_phases1);
   q.part[1] = reinterpret_cast<const float2*>(part2); q.ldp[1] = ldp2; q.nph[1] = c2 ? n_phases2 : 1; q.pstride[1] = phase_stride2;
   q.nblk[1] = c2 ? hw / (128 * n_phases2) : 0;
-  // the block partials are added by (channel, part) work items so that every thread of the CTA has loads in flight
-  int nparts = C <= 320 ? 8 : C <= 640 ? 4 : C <= 1280 ? 2 : 1;
-  const int nb_min = q.nblk[0] * q.nph[0];
-  while (nparts > 1 && nparts > nb_min) nparts >>= 1;
-  launch_k(mrisr::groupnorm_apply_cpart_kernel, dim3(nslab, batch), dim3(nvec, R), static_cast<size_t>(2 * nparts + 2) * C * sizeof(float), as_stream(stream), a, q, gamma, beta, eps, silu, static_cast<__nv_bfloat16*>(out), nparts);
+  if (nvec * R < 32) return fail(MRISR_E_UNSUPPORTED, "groupnorm_apply_stats: needs at least one full warp per CTA (C * rows >= 256)");
+  launch_k(mrisr::groupnorm_apply_cpart_kernel, dim3(nslab, batch), dim3(nvec, R), static_cast<size_t>(2 * R + 2) * C * sizeof(float), as_stream(stream), a, q, gamma, beta, eps, silu, static_cast<__nv_bfloat16*>(out), 0);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

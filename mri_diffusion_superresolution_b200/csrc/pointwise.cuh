@@ -397,11 +397,12 @@ struct GnPartArgs {
   int nph[2];
   int nblk[2];
 };
-__global__ void groupnorm_apply_cpart_kernel(GnArgs a, GnPartArgs q, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                             float eps, int silu, __nv_bfloat16* __restrict__ out, int nparts) {
+__global__ void __launch_bounds__(512, 2)   // <= 64 registers: four 240..256-thread CTAs per SM (the first version held 95 and ran two)
+groupnorm_apply_cpart_kernel(GnArgs a, GnPartArgs q, const float* __restrict__ gamma, const float* __restrict__ beta,
+                             float eps, int silu, __nv_bfloat16* __restrict__ out, int nparts) {
   grid_dep_launch();
   grid_dep_wait();
-  extern __shared__ float gn_sh[];   // [nparts][sum[C] | sumsq[C]] partial totals, then scale[C], shift[C]
+  extern __shared__ __align__(16) float gn_sh[];   // [R][sum[C] | sumsq[C]] block partials added per thread row, then scale[C], shift[C]
   __shared__ float s_mean[64], s_rstd[64];
   const int C = a.c1 + a.c2;
   const int vx = threadIdx.x, ry = threadIdx.y, R = blockDim.y;
@@ -410,70 +411,95 @@ __global__ void groupnorm_apply_cpart_kernel(GnArgs a, GnPartArgs q, const float
   const int cpg = C / a.groups;
   const int p0 = slab * a.pix_per_slab;
   const int p1 = min(a.hw, p0 + a.pix_per_slab);
-  // (A) the first eight 16-byte loads of this thread's pixels do not depend on the statistics: put them in flight now, so the
+  // (A) the first four 16-byte loads of this thread's pixels do not depend on the statistics: put them in flight now, so the
   // prologue below (block partials -> group statistics -> per-channel scale / shift: three dependent L2 round trips) is hidden
   int pix = p0 + ry;
-  const bool pre = pix + 7 * R < p1;
-  uint4 first[8];
-  if (pre) {
+  uint4 cur[4];
+  bool have = pix + 3 * R < p1;
+  if (have) {
 #pragma unroll
-    for (int u = 0; u < 8; ++u) first[u] = gn_load(a, b, pix + u * R, vx);
+    for (int u = 0; u < 4; ++u) cur[u] = gn_load(a, b, pix + u * R, vx);
   }
-  // (B) per-channel totals of this batch element: (channel, part) work items, part p adds blocks p, p + nparts, ... (fixed order)
-  float* s_aff = gn_sh + nparts * 2 * C;
-  for (int it = tid; it < C * nparts; it += nthr) {
-    const int part = it / C, c = it - part * C;
-    const int s = c < a.c1 ? 0 : 1;
-    const int cc = s == 0 ? c : c - a.c1;
-    const int nb = q.nph[s] * q.nblk[s];
-    float su = 0.f, sq = 0.f;
-    for (int j0 = part; j0 < nb; j0 += 4 * nparts) {   // up to four independent L2 loads in flight
-      float2 v[4];
+  // (B) block partials of this batch element, no integer divisions: thread (vx, ry) owns the 8 channels of its vector and adds
+  // the 128-row blocks j = ry, ry + R, ... (four 16-byte L2 loads per block, eight in flight), then the R rows are added per channel
+  float* s_aff = gn_sh + R * 2 * C;
+  {
+    const int nv1 = a.c1 >> 3;
+    const bool s0 = vx < nv1;
+    const int cv = s0 ? vx : vx - nv1;
+    const float2* qpart = s0 ? q.part[0] : q.part[1];
+    const long long qldp = s0 ? q.ldp[0] : q.ldp[1], qps = s0 ? q.pstride[0] : q.pstride[1];
+    const int qnblk = s0 ? q.nblk[0] : q.nblk[1], qnph = s0 ? q.nph[0] : q.nph[1];
+    float su[8], sq[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int j = j0 + u * nparts;
-        v[u] = make_float2(0.f, 0.f);
-        if (j < nb) {
-          const int ph = j / q.nblk[s], jj = j - ph * q.nblk[s];
-          v[u] = __ldg(q.part[s] + (ph * q.pstride[s] + static_cast<long long>(b) * q.nblk[s] + jj) * q.ldp[s] + cc);
+    for (int j = 0; j < 8; ++j) { su[j] = 0.f; sq[j] = 0.f; }
+    auto add4 = [&](const float4* p4) {
+      const float4 v0 = __ldg(p4), v1 = __ldg(p4 + 1), v2 = __ldg(p4 + 2), v3 = __ldg(p4 + 3);
+      su[0] += v0.x; sq[0] += v0.y; su[1] += v0.z; sq[1] += v0.w; su[2] += v1.x; sq[2] += v1.y; su[3] += v1.z; sq[3] += v1.w;
+      su[4] += v2.x; sq[4] += v2.y; su[5] += v2.z; sq[5] += v2.w; su[6] += v3.x; sq[6] += v3.y; su[7] += v3.z; sq[7] += v3.w;
+    };
+    for (int ph = 0; ph < qnph; ++ph) {
+      const float2* base = qpart + (ph * qps + static_cast<long long>(b) * qnblk) * qldp + cv * 8;
+      int j = ry;
+      for (; j + R < qnblk; j += 2 * R) {
+        add4(reinterpret_cast<const float4*>(base + j * qldp));
+        add4(reinterpret_cast<const float4*>(base + (j + R) * qldp));
+      }
+      if (j < qnblk) add4(reinterpret_cast<const float4*>(base + j * qldp));
+    }
+    float* ds = gn_sh + ry * 2 * C + vx * 8;
+    *reinterpret_cast<float4*>(ds) = make_float4(su[0], su[1], su[2], su[3]);
+    *reinterpret_cast<float4*>(ds + 4) = make_float4(su[4], su[5], su[6], su[7]);
+    *reinterpret_cast<float4*>(ds + C) = make_float4(sq[0], sq[1], sq[2], sq[3]);
+    *reinterpret_cast<float4*>(ds + C + 4) = make_float4(sq[4], sq[5], sq[6], sq[7]);
+  }
+  __syncthreads();
+  // (C) group statistics: one (full) warp per group at a time, lanes over the group's R x cpg partial entries, fp64 from here
+  {
+    const int lane = tid & 31, warp = tid >> 5, nfull = nthr >> 5;
+    const int cnt = R * cpg;
+    if (warp < nfull) {
+      for (int g = warp; g < a.groups; g += nfull) {
+        double su = 0.0, sq = 0.0;
+        for (int idx = lane; idx < cnt; idx += 32) {
+          const int r = idx / cpg, c = g * cpg + (idx - r * cpg);
+          su += gn_sh[r * 2 * C + c];
+          sq += gn_sh[r * 2 * C + C + c];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { su += __shfl_xor_sync(0xffffffffu, su, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
+        if (lane == 0) {
+          const double n = static_cast<double>(a.hw) * cpg;
+          const double mean = su / n;
+          double var = sq / n - mean * mean;
+          if (var < 0.0) var = 0.0;
+          s_mean[g] = static_cast<float>(mean);
+          s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
         }
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { su += v[u].x; sq += v[u].y; }
     }
-    gn_sh[part * 2 * C + c] = su;
-    gn_sh[part * 2 * C + C + c] = sq;
   }
   __syncthreads();
-  for (int g = tid; g < a.groups; g += nthr) {
-    double su = 0.0, sq = 0.0;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c)
-      for (int part = 0; part < nparts; ++part) { su += gn_sh[part * 2 * C + c]; sq += gn_sh[part * 2 * C + C + c]; }
-    const double n = static_cast<double>(a.hw) * cpg;
-    const double mean = su / n;
-    double var = sq / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    s_mean[g] = static_cast<float>(mean);
-    s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-  }
-  __syncthreads();
+  // scale / shift stay in shared memory (16 registers the load pipeline needs), laid out [4][nvec] float4 = {scale 0-3, scale 4-7,
+  // shift 0-3, shift 4-7} per 8-channel vector: the lanes of a warp read CONSECUTIVE 16-byte words (conflict-free; a
+  // [C]-ordered layout puts lanes 32 bytes apart: two-way bank conflicts on every one of four loads per vector)
+  const int nvec = C >> 3;
   for (int c = tid; c < C; c += nthr) {
     const int g = c / cpg;
     const float sc = s_rstd[g] * __ldg(gamma + c);
-    s_aff[c] = sc;
-    s_aff[C + c] = __ldg(beta + c) - s_mean[g] * sc;
+    const int vec = c >> 3, e = c & 7;
+    s_aff[(((e >> 2)) * nvec + vec) * 4 + (e & 3)] = sc;
+    s_aff[((2 + (e >> 2)) * nvec + vec) * 4 + (e & 3)] = __ldg(beta + c) - s_mean[g] * sc;
   }
   __syncthreads();
-  float2 sc[4], sh[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    sc[j] = make_float2(s_aff[vx * 8 + 2 * j], s_aff[vx * 8 + 2 * j + 1]);
-    sh[j] = make_float2(s_aff[C + vx * 8 + 2 * j], s_aff[C + vx * 8 + 2 * j + 1]);
-  }
+  const float4* aff4 = reinterpret_cast<const float4*>(s_aff) + vx;
   const bool hsrc = (vx < (a.c1 >> 3) ? a.h1 : a.h2) != 0;
   auto emit = [&](int pixel, const uint4& v) {
     float2 f[4];
     unpack8p_any(v, f, hsrc);
+    const float4 s0 = aff4[0], s1 = aff4[nvec], h0 = aff4[2 * nvec], h1 = aff4[3 * nvec];
+    const float2 sc[4] = {make_float2(s0.x, s0.y), make_float2(s0.z, s0.w), make_float2(s1.x, s1.y), make_float2(s1.z, s1.w)};
+    const float2 sh[4] = {make_float2(h0.x, h0.y), make_float2(h0.z, h0.w), make_float2(h1.x, h1.y), make_float2(h1.z, h1.w)};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       f[j] = __ffma2_rn(f[j], sc[j], sh[j]);
@@ -481,17 +507,23 @@ __global__ void groupnorm_apply_cpart_kernel(GnArgs a, GnPartArgs q, const float
     }
     reinterpret_cast<uint4*>(out + (static_cast<long long>(b) * a.hw + pixel) * C)[vx] = pack8p(f);
   };
-  if (pre) {
+  // software pipeline: the next four loads are issued before the current four are normalised and stored
+  while (have) {
+    const int nxt = pix + 4 * R;
+    const bool more = nxt + 3 * R < p1;
+    uint4 nx[4];
+    if (more) {
 #pragma unroll
-    for (int u = 0; u < 8; ++u) emit(pix + u * R, first[u]);
-    pix += 8 * R;
-  }
-  for (; pix + 7 * R < p1; pix += 8 * R) {  // 8 independent 16-byte loads in flight per thread
-    uint4 v[8];
+      for (int u = 0; u < 4; ++u) nx[u] = gn_load(a, b, nxt + u * R, vx);
+    }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = gn_load(a, b, pix + u * R, vx);
+    for (int u = 0; u < 4; ++u) emit(pix + u * R, cur[u]);
+    pix = nxt;
+    have = more;
+    if (more) {
 #pragma unroll
-    for (int u = 0; u < 8; ++u) emit(pix + u * R, v[u]);
+      for (int u = 0; u < 4; ++u) cur[u] = nx[u];
+    }
   }
   for (; pix < p1; pix += R) emit(pix, gn_load(a, b, pix, vx));
 }

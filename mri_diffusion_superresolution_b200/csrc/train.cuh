@@ -60,6 +60,8 @@ struct GnBwdArgs {
 };
 __global__ void __launch_bounds__(256) groupnorm_backward_kernel(GnBwdArgs a, const float* __restrict__ gamma,
                                                                   const float* __restrict__ beta, float eps, int silu) {
+  grid_dep_launch();
+  grid_dep_wait();   // launched with programmatic dependent launch: inputs are the predecessor's output
   __shared__ float sh[2 * 32];
   const int g = blockIdx.x, b = blockIdx.y;
   const int C = a.c1 + a.c2, cpg = C / a.groups;
@@ -117,6 +119,8 @@ __global__ void __launch_bounds__(256) layernorm_backward_kernel(const void* __r
                                                                   const __half* __restrict__ dy, const float* __restrict__ gamma,
                                                                   float eps, const __half* __restrict__ dres, __half* __restrict__ dx,
                                                                   int rows, int C) {
+  grid_dep_launch();
+  grid_dep_wait();   // launched with programmatic dependent launch: inputs are the predecessor's output
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -153,6 +157,8 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
 __global__ void geglu_forward_kernel(const __nv_bfloat16* __restrict__ pre, __nv_bfloat16* __restrict__ out, long long M, int F) {
+  grid_dep_launch();
+  grid_dep_wait();   // launched with programmatic dependent launch: inputs are the predecessor's output
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < M * F; i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long m = i / F;
     const int f = static_cast<int>(i - m * F);
@@ -162,6 +168,8 @@ __global__ void geglu_forward_kernel(const __nv_bfloat16* __restrict__ pre, __nv
 }
 __global__ void geglu_backward_kernel(const __nv_bfloat16* __restrict__ pre, const __half* __restrict__ df, __half* __restrict__ dpre,
                                       long long M, int F) {
+  grid_dep_launch();
+  grid_dep_wait();   // launched with programmatic dependent launch: inputs are the predecessor's output
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < M * F; i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long m = i / F;
     const int f = static_cast<int>(i - m * F);
@@ -177,6 +185,8 @@ __global__ void geglu_backward_kernel(const __nv_bfloat16* __restrict__ pre, con
 // transposed stride-2 convolution = a stride-1 convolution of this with the flipped filter).  sumpool2: [B,2h,2w,C] ->
 // [B,h,w,C] sum of each 2x2 block (backward of the nearest-2x upsample).  IEEE half, 8-channel vectors.
 __global__ void zero_insert2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int h, int w, int nvec) {
+  grid_dep_launch();
+  grid_dep_wait();   // launched with programmatic dependent launch: inputs are the predecessor's output
   const long long total = static_cast<long long>(B) * 4 * h * w * nvec;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int v = static_cast<int>(i % nvec);
@@ -190,6 +200,8 @@ __global__ void zero_insert2x_kernel(const uint4* __restrict__ in, uint4* __rest
   }
 }
 __global__ void sumpool2_kernel(const __half* __restrict__ in, __half* __restrict__ out, int B, int h, int w, int C) {
+  grid_dep_launch();
+  grid_dep_wait();   // launched with programmatic dependent launch: inputs are the predecessor's output
   const long long total = static_cast<long long>(B) * h * w * C;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % C);
@@ -209,6 +221,8 @@ __global__ void sumpool2_kernel(const __half* __restrict__ in, __half* __restric
 // Deterministic two-stage loss reduction: partial[blockIdx.x], then mse_finalize_kernel.
 __global__ void __launch_bounds__(256) mse_grad_kernel(const float* __restrict__ pred, const float* __restrict__ target, int B, int Cc, int HW,
                                                        int cpad, float grad_scale, __half* __restrict__ dout, float* __restrict__ partial) {
+  grid_dep_launch();
+  grid_dep_wait();   // launched with programmatic dependent launch: inputs are the predecessor's output
   __shared__ float sh[32];
   const long long total = static_cast<long long>(B) * HW * cpad;
   float acc[1] = {0.f};
@@ -229,6 +243,8 @@ __global__ void __launch_bounds__(256) mse_grad_kernel(const float* __restrict__
   if (threadIdx.x == 0) partial[blockIdx.x] = acc[0];
 }
 __global__ void mse_finalize_kernel(const float* __restrict__ partial, int n, float inv_count, float* __restrict__ loss) {
+  grid_dep_launch();
+  grid_dep_wait();   // launched with programmatic dependent launch: inputs are the predecessor's output
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     double a = 0.0;
     for (int i = 0; i < n; ++i) a += partial[i];
@@ -246,6 +262,8 @@ constexpr int kXtyRows = 32;
 __global__ void __launch_bounds__(256) xty64_partial_kernel(const void* __restrict__ X, long long ldx, int x_f16,
                                                              const void* __restrict__ Y, long long ldy, int y_f16, int M, int Q,
                                                              int rows_per_split, float* __restrict__ partial /*[msplit][64][Q]*/) {
+  grid_dep_launch();
+  grid_dep_wait();   // launched with programmatic dependent launch: inputs are the predecessor's output
   __shared__ float sx[kXtyRows][64 + 1];
   __shared__ float sy[kXtyRows][64 + 1];
   const int q0 = blockIdx.x * 64;
@@ -286,6 +304,8 @@ __global__ void __launch_bounds__(256) xty64_partial_kernel(const void* __restri
       if (q0 + 4 * tx + j < Q) dst[static_cast<long long>(4 * ty + i) * Q + q0 + 4 * tx + j] = acc[i][j];
 }
 __global__ void xty64_reduce_kernel(const float* __restrict__ partial, int msplit, int Q, float scale, float* __restrict__ out) {
+  grid_dep_launch();
+  grid_dep_wait();   // launched with programmatic dependent launch: inputs are the predecessor's output
   const long long n = 64LL * Q;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
     float a = 0.f;
@@ -307,6 +327,8 @@ struct AdamDesc {
   void* d2; long long d2_sr, d2_sc; float d2_scale; int d2_f16;
 };
 __global__ void __launch_bounds__(256) sqnorm_multi_kernel(const AdamDesc* __restrict__ desc, float* __restrict__ per_tensor) {
+  grid_dep_launch();
+  grid_dep_wait();   // launched with programmatic dependent launch: inputs are the predecessor's output
   __shared__ float sh[32];
   const AdamDesc d = desc[blockIdx.x];
   const int n = d.rows * d.cols;
@@ -320,6 +342,8 @@ __global__ void __launch_bounds__(256) sqnorm_multi_kernel(const AdamDesc* __res
   if (threadIdx.x == 0) per_tensor[blockIdx.x] = acc[0];
 }
 __global__ void sqnorm_finalize_kernel(const float* __restrict__ per_tensor, int n, float max_norm, float* __restrict__ out /*[2]: norm, clip coef*/) {
+  grid_dep_launch();
+  grid_dep_wait();   // launched with programmatic dependent launch: inputs are the predecessor's output
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     double a = 0.0;
     for (int i = 0; i < n; ++i) a += per_tensor[i];
@@ -330,6 +354,8 @@ __global__ void sqnorm_finalize_kernel(const float* __restrict__ per_tensor, int
 }
 __global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamDesc* __restrict__ desc, const float* __restrict__ clip /*[2]*/,
                                                           float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2) {
+  grid_dep_launch();
+  grid_dep_wait();   // launched with programmatic dependent launch: inputs are the predecessor's output
   const AdamDesc d = desc[blockIdx.x];
   const int n = d.rows * d.cols;
   const float coef = clip != nullptr ? clip[1] : 1.f;
@@ -444,6 +470,8 @@ __device__ __forceinline__ void ab_mma_pn(float (&out)[AttnBwdCfg<D>::DP / 8][4]
 
 template <int D>
 __global__ void __launch_bounds__(kAbThreads) attention_bwd_dq_kernel(AttnBwdArgs a) {
+  grid_dep_launch();
+  grid_dep_wait();   // launched with programmatic dependent launch: inputs are the predecessor's output
   using Cfg = AttnBwdCfg<D>;
   extern __shared__ __align__(16) uint8_t ab_raw[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(ab_raw);
@@ -553,6 +581,8 @@ __global__ void __launch_bounds__(kAbThreads) attention_bwd_dq_kernel(AttnBwdArg
 // kMode: 0 = dK and dV in one sweep; 1 = dV only; 2 = dK only (head dim 160: the two accumulators do not fit the register file together)
 template <int D, int kMode>
 __global__ void __launch_bounds__(kAbThreads) attention_bwd_dkdv_kernel(AttnBwdArgs a) {
+  grid_dep_launch();
+  grid_dep_wait();   // launched with programmatic dependent launch: inputs are the predecessor's output
   using Cfg = AttnBwdCfg<D>;
   extern __shared__ __align__(16) uint8_t ab_raw[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(ab_raw);

@@ -20,6 +20,7 @@ argument of ``step``), training of the adapter itself.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -334,6 +335,11 @@ class LoRAFineTuner:
                                d_qkv[:, :Cc], d_qkv[:, Cc:2 * Cc], d_qkv[:, 2 * Cc:])
         d_y1 = self._lora_bwd(d["qkv"], d_qkv, y1, t1)
         d_ha = ops.layernorm_backward(h_a, d_y1, a.ln1[0], 1e-5, dres=d_hb)
+        if os.environ.get("MRISR_FT_DEBUG"):
+            for nm, t in (("d_hd", d_hd), ("d_f", d_f), ("d_pre", d_pre), ("d_y3", d_y3), ("d_hc", d_hc), ("d_o2", d_o2), ("d_q2", d_q2),
+                          ("d_kv", d_kv), ("d_y2", d_y2), ("d_hb", d_hb), ("d_o1", d_o1), ("d_qkv", d_qkv), ("d_y1", d_y1), ("d_ha", d_ha)):
+                f = t.float()
+                print(f"[ft-debug]    attn C={Cc} {nm:6s} finite {bool(torch.isfinite(f).all())} absmax {float(f.abs().max()):.4g}")
         d_g0 = ops.gemm(d_ha, d["wd_in"], out_dtype=F16).view(B, H, W, Cc)
         dx, _ = ops.groupnorm_backward(x, d_g0, a.gnw, a.gnb, c.norm_num_groups, 1e-6, False)
         return ops.add(dx, dz).view(B, H, W, Cc)
@@ -421,8 +427,19 @@ class LoRAFineTuner:
         ds = ops.groupnorm_backward(s_last, d_hn, u.n_out_w, u.n_out_b, c.norm_num_groups, c.norm_eps, True)[0].view(B, H, W, ch[0])
         dskips: List[Tensor] = []          # gradients of the skip tensors, pushed in the order the up path consumed them
         first_attn = next(k for k, (kind, _) in enumerate(tape) if kind == "attn")
+        dbg = bool(os.environ.get("MRISR_FT_DEBUG"))
+
+        def _report(tag, t):
+            if dbg:
+                f = t.float()
+                print(f"[ft-debug] {tag:28s} shape {tuple(t.shape)} finite {bool(torch.isfinite(f).all())} absmax {float(f.abs().max()):.4g}")
+
+        _report("d_eps", d_eps)
+        _report("ds after conv_out/norm_out", ds)
         for k in range(len(tape) - 1, first_attn - 1, -1):       # nothing trainable precedes the first transformer block
             kind, ctx = tape[k]
+            if dbg and k < len(tape) - 1:
+                _report(f"ds before tape[{k}] ({kind})", ds)
             if kind == "res_cat":
                 ds, dsk = self._resnet_bwd(ctx, ds)
                 dskips.append(dsk)

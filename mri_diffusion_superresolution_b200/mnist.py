@@ -49,3 +49,31 @@ class SinusoidalPositionEmbeddings:
         return out
 
     forward = __call__
+
+
+@torch.no_grad()
+def sample(eps_model, shape, num_steps: int = T, generator=None, device="cuda", noises: Tensor = None) -> Tensor:
+    """DDPM ancestral sampling on the notebook's schedule (:121-125) -- the reverse loop the notebook never wrote
+    (its train cell stops at an undefined ``MNISTSRModel``, :222-271; SURVEY.md §3.5: config 1 "must be built from the schedule
+    + standard DDPM ancestral sampling and is therefore unpinned").  ``eps_model(x_t fp32 [B,1,28,28], t int64 [B]) -> eps`` is
+    the caller's network (e.g. one conditioned on the 14x14 low-resolution digit, :64-77); every update
+        x_{t-1} = (x_t - beta_t / sqrt(1 - abar_t) * eps) / sqrt(alpha_t) + sqrt(beta~_t) * z
+    runs as ONE ``mrisr_sched_step`` launch with host-precomputed coefficients (no per-step host sync).
+    ``noises`` ``[num_steps + 1, *shape]`` injects x_T and the per-step draws (parity tests)."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("mnist.sample (B200) runs on CUDA only (no CPU path)")
+    sch = make_scheduler()
+    sch.config.timestep_spacing = "trailing"
+    sch.set_timesteps(num_steps)
+    coef, book = sch.step_table("ddpm")
+    ctab = torch.tensor(coef, dtype=torch.float32, device=dev)
+    if noises is None:
+        noises = torch.randn((num_steps + 1,) + tuple(shape), generator=generator, device=dev, dtype=torch.float32)
+    x = noises[0].clone()
+    B = shape[0]
+    for i, (t, _, flag) in enumerate(book):
+        tt = torch.full((B,), t, device=dev, dtype=torch.int64)
+        eps = eps_model(x, tt).float().contiguous()
+        x = ops.sched_step(x, eps, ctab[i], z=noises[i + 1].contiguous() if flag else None)
+    return x

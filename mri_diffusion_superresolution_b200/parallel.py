@@ -3,7 +3,7 @@ takes a contiguous range of the slice batch, weights are replicated, and the ONL
 latents (NCCL over NVLink on GPUs; the same code runs on gloo for the CPU tests)."""
 from __future__ import annotations
 
-from typing import List, Tuple
+from typing import Callable, List, Tuple
 
 import torch
 import torch.distributed as dist
@@ -33,3 +33,13 @@ def gather_slices(local: torch.Tensor, n_slices: int) -> torch.Tensor:
     bufs: List[torch.Tensor] = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(bufs, pad.contiguous())
     return torch.cat([b[: hi - lo] for b, (lo, hi) in zip(bufs, sizes)], dim=0)
+
+
+def sharded_apply(n_slices: int, process: Callable[[int, int], torch.Tensor]) -> torch.Tensor:
+    """BASELINE config 5 (strong scaling): the ``n_slices`` slices of a sweep are split into contiguous per-rank ranges
+    (``shard_range``), every rank runs ``process(lo, hi) -> [hi - lo, ...]`` on its own range with NO communication, and ONE
+    ``all_gather`` at the end returns all results in global slice order on every rank.  Single process: ``process(0, n)``."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return process(0, n_slices)
+    lo, hi = shard_range(n_slices, dist.get_rank(), dist.get_world_size())
+    return gather_slices(process(lo, hi), n_slices)

@@ -10,16 +10,18 @@
          PSNR / SSIM / NMSE / HFEN per slice (src/eval/eval.py:84-90)
 
 Every stage runs on the sm_100a kernels; slices are processed in batches of ``batch`` through one ``SliceSampler`` (CUDA
-graph replay).  Under ``torch.distributed`` each rank takes a contiguous range of the volume's slices
-(``parallel.shard_range``) -- the path has no per-step communication.
+graph replay).  Under ``torch.distributed`` (one process per GPU) ``run`` / ``run_sweep`` shard the slice list: each rank takes
+a contiguous range (``parallel.sharded_apply`` -> ``shard_range``), runs it with no communication, and one ``all_gather``
+returns every generated slice on every rank (strong scaling over a fixed sweep; weights are replicated).
 """
 from __future__ import annotations
 
-from typing import Dict, Optional, Tuple
+from typing import Dict, Optional, Sequence, Tuple
 
 import torch
 
 from .evalmetrics import image_metrics
+from .parallel import sharded_apply
 from .sampler import SliceSampler
 from .slices import volume_to_slices
 
@@ -58,7 +60,8 @@ class VolumePipeline:
         """-> ``{"generated": [D,1,512,512] in [-1,1], "metrics": [D,4] (PSNR, SSIM, NMSE, HFEN) if a ground truth is given,
         "mean_metrics": [PSNR, SSIM, NMSE, HFEN] averaged over the slices}``.  ``lr_clip`` / ``hr_clip`` are the dataset's intensity windows (mri_datasets.py:191)."""
         lr = volume_to_slices(lr_volume_hwd, lr_clip[0], lr_clip[1])
-        gen = self.super_resolve_slices(lr, prompt_embeds, generator)
+        # under torch.distributed every rank super-resolves its own contiguous range of the D slices; one all_gather at the end
+        gen = sharded_apply(lr.shape[0], lambda lo, hi: self.super_resolve_slices(lr[lo:hi], prompt_embeds, generator))
         res = {"generated": gen, "lr_slices": lr}
         if hr_volume_hwd is not None:
             hr = volume_to_slices(hr_volume_hwd, hr_clip[0], hr_clip[1])
@@ -66,3 +69,12 @@ class VolumePipeline:
             res["metrics"] = per
             res["mean_metrics"] = per.double().mean(0).cpu().tolist()  # the one host read-back: 4 numbers per volume
         return res
+
+    @torch.no_grad()
+    def run_sweep(self, lr_volumes_hwd: Sequence[Tensor], lr_clip: Tuple[float, float], prompt_embeds: Tensor,
+                  generator: Optional[torch.Generator] = None) -> Tensor:
+        """BASELINE config 5: a sweep over several volumes.  The axial slices of all volumes form ONE list of S = sum(D_v)
+        slices, sharded contiguously over the ranks (128 slices per GPU for 8 volumes on 8 GPUs); returns the generated
+        slices ``[S, 1, 512, 512]`` in volume-major order on every rank."""
+        lr = torch.cat([volume_to_slices(v, lr_clip[0], lr_clip[1]) for v in lr_volumes_hwd], 0)
+        return sharded_apply(lr.shape[0], lambda lo, hi: self.super_resolve_slices(lr[lo:hi], prompt_embeds, generator))

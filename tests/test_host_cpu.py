@@ -156,6 +156,42 @@ def _gloo_worker(rank, world, port, n_slices, q):
     dist.destroy_process_group()
 
 
+def _gloo_sweep_worker(rank, world, port, n_slices, q):
+    """The config-5 entry point's host logic (parallel.sharded_apply, what VolumePipeline.run / run_sweep call) with a CPU
+    stand-in for the per-range GPU work."""
+    import torch.distributed as dist
+    from mri_diffusion_superresolution_b200.parallel import sharded_apply
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    vol = torch.arange(n_slices * 6, dtype=torch.float32).view(n_slices, 1, 2, 3)
+    seen = []
+
+    def process(lo, hi):
+        seen.append((lo, hi))
+        return vol[lo:hi] * 3.0 + 1.0
+
+    out = sharded_apply(n_slices, process)
+    q.put((rank, bool(torch.equal(out, vol * 3.0 + 1.0)), seen[0]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_slices", [1024, 129])
+def test_volume_sweep_sharding_two_ranks_gloo(n_slices):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + n_slices % 7
+    procs = [ctx.Process(target=_gloo_sweep_worker, args=(r, 2, port, n_slices, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res)
+    assert res[0][2] == (0, (n_slices + 1) // 2) and res[1][2] == ((n_slices + 1) // 2, n_slices)
+
+
 @pytest.mark.parametrize("n_slices", [8, 7, 1])
 def test_slice_sharding_two_ranks_gloo(n_slices):
     import torch.multiprocessing as mp

@@ -353,3 +353,26 @@ def test_sd15_full_50_step_loop_psnr():
     psnr = _psnr(out, ref_lat)
     print(f"50-step SD-1.5 loop: final-latent PSNR {psnr:.1f} dB, rel-L2 {_rel(out, ref_lat):.2e}")
     assert psnr >= PSNR_MIN_DB
+
+
+def test_mnist_ddpm_sampling_loop_vs_oracle():
+    """BASELINE config 1: DDPM ancestral sampling on the notebook's linear-beta schedule (mnist.sample: one fused step kernel
+    per update, coefficients precomputed on the host) against oracle/mnist_oracle.py (Ho et al. Algorithm 2 in fp64) with the
+    same eps model and injected noise, on the full 1000-step chain."""
+    from oracle import mnist_oracle as mo
+    from mri_diffusion_superresolution_b200 import mnist
+    g = torch.Generator().manual_seed(8)
+    w = torch.randn(1, 1, 3, 3, generator=g) * 0.2
+
+    def eps_fn(x, t):                       # any deterministic eps model: a small conv with a timestep-dependent gain
+        return torch.nn.functional.conv2d(x, w.to(x.device), padding=1) * (0.5 + t.view(-1, 1, 1, 1).float().to(x.device) / 1000.0)
+
+    noises = torch.randn(1001, 2, 1, 28, 28, generator=g)
+    got = mnist.sample(eps_fn, (2, 1, 28, 28), num_steps=1000, noises=noises.cuda())
+    want = mo.ddpm_sample(eps_fn, noises, T=1000)
+    assert got.shape == want.shape and _rel(got, want) < 1e-3
+    sch = mnist.make_scheduler()
+    sch.config.timestep_spacing = "trailing"
+    sch.set_timesteps(1000)
+    _, book = sch.step_table("ddpm")
+    assert [b[0] for b in book] == list(range(999, -1, -1)) and [b[2] for b in book] == [True] * 999 + [False]    # bookkeeping exact
