@@ -513,6 +513,7 @@ int mrisr_groupnorm(const void* x1, int64_t ld1, int c1, const void* x2, int64_t
       as.x1 = static_cast<const __nv_bfloat16*>(x1); as.x2 = static_cast<const __nv_bfloat16*>(x2);
       as.ld1 = ld1; as.ld2 = ld2; as.c1 = c1; as.c2 = c2; as.hw = hw; as.batch = batch; as.groups = groups;
       as.h1 = f16_flags & 1; as.h2 = (f16_flags >> 1) & 1; as.nslab = 1; as.pix_per_slab = hw;
+      as.inv_n = 1.0 / (static_cast<double>(hw) * cpg);
       launch_k(mrisr::groupnorm_small_kernel, dim3(groups / G, batch), dim3(nvv, Rr), smem_small, as_stream(stream), as, G, gamma, beta, eps,
                silu, static_cast<__nv_bfloat16*>(out));
       MRISR_CHECK_CUDA(cudaGetLastError());
@@ -535,6 +536,7 @@ int mrisr_groupnorm(const void* x1, int64_t ld1, int c1, const void* x2, int64_t
   a.ld1 = ld1; a.ld2 = ld2; a.c1 = c1; a.c2 = c2; a.hw = hw; a.batch = batch; a.groups = groups;
   a.h1 = f16_flags & 1; a.h2 = (f16_flags >> 1) & 1;
   a.nslab = nslab; a.pix_per_slab = pps;
+  a.inv_n = 1.0 / (static_cast<double>(hw) * (C / groups));
   dim3 block(nvec, R), grid(nslab, batch);
   cudaStream_t st = as_stream(stream);
   launch_k(mrisr::groupnorm_stats_kernel, dim3(grid), dim3(block), 2 * R * C * sizeof(float), st, a, reinterpret_cast<float2*>(workspace));
@@ -570,6 +572,8 @@ int mrisr_groupnorm_apply_stats(const void* x1, int64_t ld1, int c1, const float
   // (hw / 128 * C pairs from L2), so no more than 16 slabs: <= 25 % extra L2 reads on top of the tensor itself
   int nslab = (sm_count() * 4 + batch - 1) / batch;
   if (nslab > 16) nslab = 16;
+  if (const char* e = getenv("MRISR_GN_NSLAB")) nslab = atoi(e);   // tuning runs
+  if (const char* e = getenv("MRISR_GN_ROWS")) { R = atoi(e); if (R < 1) R = 1; if (R > hw) R = hw; if (nvec * R > 512) R = 512 / nvec; }
   const int max_slabs = (hw + 8 * R - 1) / (8 * R);
   if (nslab > max_slabs) nslab = max_slabs;
   if (nslab < 1) nslab = 1;
@@ -581,13 +585,14 @@ int mrisr_groupnorm_apply_stats(const void* x1, int64_t ld1, int c1, const float
   a.ld1 = ld1; a.ld2 = ld2; a.c1 = c1; a.c2 = c2; a.hw = hw; a.batch = batch; a.groups = groups;
   a.h1 = f16_flags & 1; a.h2 = (f16_flags >> 1) & 1;
   a.nslab = nslab; a.pix_per_slab = pps;
+  a.inv_n = 1.0 / (static_cast<double>(hw) * (C / groups));
   mrisr::GnPartArgs q;
   q.part[0] = reinterpret_cast<const float2*>(part1); q.ldp[0] = ldp1; q.nph[0] = n_phases1; q.pstride[0] = phase_stride1;
   q.nblk[0] = hw / (128 * n_phases1);
   q.part[1] = reinterpret_cast<const float2*>(part2); q.ldp[1] = ldp2; q.nph[1] = c2 ? n_phases2 : 1; q.pstride[1] = phase_stride2;
   q.nblk[1] = c2 ? hw / (128 * n_phases2) : 0;
   if (nvec * R < 32) return fail(MRISR_E_UNSUPPORTED, "groupnorm_apply_stats: needs at least one full warp per CTA (C * rows >= 256)");
-  launch_k(mrisr::groupnorm_apply_cpart_kernel, dim3(nslab, batch), dim3(nvec, R), static_cast<size_t>(2 * R + 2) * C * sizeof(float), as_stream(stream), a, q, gamma, beta, eps, silu, static_cast<__nv_bfloat16*>(out), 0);
+  launch_k(mrisr::groupnorm_apply_cpart_kernel, dim3(nslab, batch), dim3(nvec, R), static_cast<size_t>(2 * R + 2) * C * sizeof(float), as_stream(stream), a, q, gamma, beta, eps, silu, static_cast<__nv_bfloat16*>(out));
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

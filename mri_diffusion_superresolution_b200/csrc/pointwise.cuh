@@ -230,6 +230,7 @@ struct GnArgs {
   int hw, batch, groups;
   int nslab, pix_per_slab;
   int h1, h2;          // source is IEEE half (fp16 residual stream / skip) instead of bf16
+  double inv_n;        // 1 / (hw * channels per group), from the host: no fp64 division in the kernels
 };
 
 __device__ __forceinline__ uint4 gn_load(const GnArgs& a, int b, int pix, int vx) {
@@ -330,12 +331,11 @@ __device__ __forceinline__ void gn_apply_body(const GnArgs& a, const float2* par
     double su = 0.0, sq = 0.0;
 #pragma unroll
     for (int part = 0; part < 8; ++part) { su += s_part[(g * 8 + part) * 2]; sq += s_part[(g * 8 + part) * 2 + 1]; }
-    const double n = static_cast<double>(a.hw) * cpg;
-    const double mean = su / n;
-    double var = sq / n - mean * mean;
+    const double mean = su * a.inv_n;       // fp64 for the cancellation only; no fp64 division / square root (software sequences)
+    double var = sq * a.inv_n - mean * mean;
     if (var < 0.0) var = 0.0;
     s_mean[g] = static_cast<float>(mean);
-    s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    s_rstd[g] = rsqrtf(static_cast<float>(var) + eps);
   }
   __syncthreads();
   for (int c = tid; c < C; c += nthr) {
@@ -399,7 +399,7 @@ struct GnPartArgs {
 };
 __global__ void __launch_bounds__(512, 2)   // <= 64 registers: four 240..256-thread CTAs per SM (the first version held 95 and ran two)
 groupnorm_apply_cpart_kernel(GnArgs a, GnPartArgs q, const float* __restrict__ gamma, const float* __restrict__ beta,
-                             float eps, int silu, __nv_bfloat16* __restrict__ out, int nparts) {
+                             float eps, int silu, __nv_bfloat16* __restrict__ out) {
   grid_dep_launch();
   grid_dep_wait();
   extern __shared__ __align__(16) float gn_sh[];   // [R][sum[C] | sumsq[C]] block partials added per thread row, then scale[C], shift[C]
@@ -469,12 +469,13 @@ groupnorm_apply_cpart_kernel(GnArgs a, GnPartArgs q, const float* __restrict__ g
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { su += __shfl_xor_sync(0xffffffffu, su, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
         if (lane == 0) {
-          const double n = static_cast<double>(a.hw) * cpg;
-          const double mean = su / n;
-          double var = sq / n - mean * mean;
+          // fp64 only where the cancellation is (E[x^2] - mean^2); no fp64 division / square root: those are ~10^2-instruction
+          // software sequences, and a first version that ran them on one lane per group cost ~10 us per CTA
+          const double mean = su * a.inv_n;
+          double var = sq * a.inv_n - mean * mean;
           if (var < 0.0) var = 0.0;
           s_mean[g] = static_cast<float>(mean);
-          s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+          s_rstd[g] = rsqrtf(static_cast<float>(var) + eps);
         }
       }
     }
@@ -597,12 +598,11 @@ __global__ void groupnorm_small_kernel(GnArgs a, int G, const float* __restrict_
   if (tid < G) {
     double su = 0.0, sq = 0.0;
     for (int r = 0; r < R; ++r) { su += s_part[2 * (r * G + tid)]; sq += s_part[2 * (r * G + tid) + 1]; }
-    const double n = static_cast<double>(a.hw) * cpg;
-    const double mean = su / n;
-    double var = sq / n - mean * mean;
+    const double mean = su * a.inv_n;
+    double var = sq * a.inv_n - mean * mean;
     if (var < 0.0) var = 0.0;
     s_mean[tid] = static_cast<float>(mean);
-    s_rstd[tid] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    s_rstd[tid] = rsqrtf(static_cast<float>(var) + eps);
   }
   __syncthreads();
   for (int c = tid; c < Cc; c += nthr) {
