@@ -227,7 +227,7 @@ def run_finetune(args):
     e1.record()
     barrier()
     clk = clocks.stop()
-    launches = _lib.LAUNCHES[0] - n0
+    launches = (_lib.LAUNCHES[0] - n0) + steps * ft.kernel_launches_per_step     # eager launches + graph-replayed ones
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -263,9 +263,9 @@ def run_finetune(args):
             "config": {"workload": "sd15_unet_lora16_finetune_step_512px", "batch_per_gpu": B, "global_batch": B * world, "lora_rank": 16,
                        "trainable_params": ft.n_params, "optimizer": "AdamW beta 0.9/0.999 wd 1e-2 eps 1e-8, max_grad_norm 1.0",
                        "parallelism": f"replicas x{world} (no gradient all-reduce: the reference's config is single-process)",
-                       "cuda_graph": False, "l2": "working set >> 126 MB L2"},
+                       "cuda_graph": True, "kernel_launches_per_step": ft.kernel_launches_per_step, "l2": "working set >> 126 MB L2"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "final_loss": float(loss), "grad_norm": float(info[0]),
-            "roofline": {"bound": "tensor", "kernel": "whole step (launch-bound at batch 2: ~2.6 k kernel launches, eager)",
+            "roofline": {"bound": "tensor", "kernel": "whole step: forward + backward + clip + AdamW replayed as one CUDA graph",
                          "achieved": tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": tflops / peaks["bf16_sustained"],
                          "traffic": None, "algorithmic_gflop_per_slice_step": GFLOP_FT_STEP},
             "cpu_baseline": None}))

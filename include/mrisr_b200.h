@@ -272,9 +272,12 @@ typedef struct mrisr_adam_desc {
 /* out2 = {global gradient 2-norm over all descriptors, clip coefficient min(1, max_norm / (norm + 1e-6))} (torch clip_grad_norm_);
  * desc is a DEVICE array; workspace >= n_desc floats. */
 int mrisr_grad_sqnorm(const mrisr_adam_desc* desc, int n_desc, float max_norm, float* workspace, float* out2, void* stream);
-/* torch.optim.AdamW (decoupled weight decay) over all descriptors; clip = out2 of mrisr_grad_sqnorm or NULL; step counts from 1. */
-int mrisr_adamw(const mrisr_adam_desc* desc, int n_desc, const float* clip, float lr, float beta1, float beta2, float eps, float weight_decay,
-                int step, void* stream);
+/* torch.optim.AdamW (decoupled weight decay) over all descriptors; clip = out2 of mrisr_grad_sqnorm or NULL.  What changes from
+ * step to step lives in DEVICE memory -- lr: fp32[1]; step: int32[1], the number of updates applied so far (bias correction uses
+ * step + 1) -- so that a whole training step replays as one captured CUDA graph.  A non-finite clip[0] (fp16 overflow under the
+ * loss scale) skips the update and leaves *step unchanged; otherwise *step is incremented after the update. */
+int mrisr_adamw(const mrisr_adam_desc* desc, int n_desc, const float* clip, const float* lr, float beta1, float beta2, float eps,
+                float weight_decay, int* step, void* stream);
 
 #ifdef __cplusplus
 }

@@ -57,6 +57,22 @@ int sm_count() {
   return g_sm_count;
 }
 
+// The kernel-attribute flags (cudaFuncSetAttribute is per device), the cached SM count and the identity-tile symbol
+// addresses below are per-process statics: this library serves ONE device per process (the deployment model: one process
+// per GPU under torchrun).  A call made with another device current fails loudly instead of launching with missing
+// shared-memory opt-ins or foreign-device pointers.
+int g_first_device = -1;
+int one_device_check() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(MRISR_E_CUDA, "cudaGetDevice failed");
+  if (g_first_device < 0) g_first_device = dev;
+  if (dev != g_first_device)
+    return fail(MRISR_E_UNSUPPORTED, "libmrisr_b200 was first used on device %d and is now called with device %d current: "
+                "one device per process (launch one process per GPU)", g_first_device, dev);
+  return 0;
+}
+#define MRISR_ONE_DEVICE() do { if (int _d = one_device_check()) return _d; } while (0)
+
 inline int grid_for(long long work_items, int threads, int per_sm = 8) {
   long long blocks = (work_items + threads - 1) / threads;
   const long long cap = static_cast<long long>(sm_count()) * per_sm;
@@ -465,6 +481,7 @@ int64_t mrisr_groupnorm_workspace_floats(int batch, int groups) {
 int mrisr_groupnorm(const void* x1, int64_t ld1, int c1, const void* x2, int64_t ld2, int c2, int batch, int hw, int groups,
                     const float* gamma, const float* beta, float eps, int silu, void* out, float* workspace, int f16_flags,
                     void* stream) {
+  MRISR_ONE_DEVICE();
   MRISR_REQUIRE(x1 && gamma && beta && out && workspace, "groupnorm: null pointer");
   MRISR_REQUIRE(batch > 0 && hw > 0 && c1 > 0 && c2 >= 0, "groupnorm: bad sizes");
   if (c2 == 0) { x2 = nullptr; ld2 = 0; }
@@ -550,6 +567,7 @@ int mrisr_groupnorm_apply_stats(const void* x1, int64_t ld1, int c1, const float
                                 const void* x2, int64_t ld2, int c2, const float* part2, int64_t ldp2, int n_phases2, int64_t phase_stride2,
                                 int batch, int hw, int groups, const float* gamma, const float* beta, float eps, int silu,
                                 void* out, int f16_flags, void* stream) {
+  MRISR_ONE_DEVICE();
   MRISR_REQUIRE(x1 && part1 && gamma && beta && out, "groupnorm_apply_stats: null pointer");
   MRISR_REQUIRE(batch > 0 && hw > 0 && c1 > 0 && c2 >= 0, "groupnorm_apply_stats: bad sizes");
   if (c2 == 0) { x2 = nullptr; ld2 = 0; part2 = nullptr; }
@@ -599,6 +617,7 @@ int mrisr_groupnorm_apply_stats(const void* x1, int64_t ld1, int c1, const float
 
 int mrisr_layernorm(const void* x, int64_t ldx, const float* gamma, const float* beta, float eps, void* out, int64_t ldo,
                     int rows, int C, int in_f16, void* stream) {
+  MRISR_ONE_DEVICE();
   MRISR_REQUIRE(x && gamma && beta && out, "layernorm: null pointer");
   MRISR_REQUIRE(rows >= 0 && C > 0 && C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0, "layernorm: C and strides must be multiples of 8");
   MRISR_REQUIRE(aligned16(x) && aligned16(out) && aligned16(gamma) && aligned16(beta), "layernorm: misaligned pointer");
@@ -662,6 +681,7 @@ static int pick_block_n(int M, int N, int act, int phases = 1) {
 }
 
 int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
+  MRISR_ONE_DEVICE();
   MRISR_REQUIRE(g != nullptr, "gemm: null args");
   MRISR_REQUIRE(g->a1 && g->w && g->out, "gemm: null a1/w/out");
   MRISR_REQUIRE(g->M > 0 && g->N > 0 && g->n_store > 0, "gemm: M, N, n_store must be positive");
@@ -845,6 +865,7 @@ int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
 
 int mrisr_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
                     int batch, int nq, int nk, int heads, int d, int kv_broadcast, void* stream) {
+  MRISR_ONE_DEVICE();
   MRISR_REQUIRE(q && k && v && o, "attention: null pointer");
   MRISR_REQUIRE(batch > 0 && nq > 0 && nk > 0 && heads > 0, "attention: bad sizes");
   MRISR_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o), "attention: misaligned pointer");
@@ -1085,7 +1106,8 @@ int mrisr_groupnorm_backward(const void* x1, int64_t ld1, int c1, const void* x2
                              int64_t lddx2, int f16_flags, void* stream) {
   MRISR_REQUIRE(x1 && dz && gamma && beta && dx1, "groupnorm_backward: null pointer");
   MRISR_REQUIRE(batch > 0 && hw > 0 && c1 > 0 && c2 >= 0 && (c2 == 0 || (x2 && dx2)), "groupnorm_backward: bad sizes");
-  MRISR_REQUIRE(groups > 0 && (c1 + c2) % groups == 0, "groupnorm_backward: groups must divide the channel count");
+  MRISR_REQUIRE(groups > 0 && (c1 + c2) % groups == 0 && ((c1 + c2) / groups) % 2 == 0 && c1 % 2 == 0 && ld1 % 2 == 0 && ld2 % 2 == 0 && lddx1 % 2 == 0 && lddx2 % 2 == 0,
+                "groupnorm_backward: groups must divide the channel count into even-sized groups; even strides");
   mrisr::GnBwdArgs a;
   a.x1 = x1; a.x2 = x2; a.ld1 = ld1; a.ld2 = ld2; a.c1 = c1; a.c2 = c2; a.hw = hw; a.groups = groups;
   a.h1 = f16_flags & 1; a.h2 = (f16_flags >> 1) & 1;
@@ -1152,18 +1174,19 @@ int mrisr_mse_grad(const float* pred, const float* target, int B, int C, int HW,
   return 0;
 }
 
+constexpr int kXtyRowsPerSplit = 64;   // short per-CTA loops: the reduction is latency-, not bandwidth-bound (256 rows: 35 us per call)
 int64_t mrisr_xty64_workspace_floats(int M, int Q) {
-  const int64_t msplit = (M + 255) / 256;
+  const int64_t msplit = (M + kXtyRowsPerSplit - 1) / kXtyRowsPerSplit;
   return msplit * 64 * static_cast<int64_t>(Q);
 }
 
 int mrisr_xty64(const void* X, int64_t ldx, int x_f16, const void* Y, int64_t ldy, int y_f16, int M, int Q, float scale, float* workspace,
                 float* out, void* stream) {
   MRISR_REQUIRE(X && Y && workspace && out && M > 0 && Q > 0 && ldx >= 64 && ldy >= Q, "xty64: bad argument");
-  const int msplit = (M + 255) / 256;
+  const int msplit = (M + kXtyRowsPerSplit - 1) / kXtyRowsPerSplit;
   cudaStream_t st = as_stream(stream);
   launch_k(mrisr::xty64_partial_kernel, dim3((Q + 63) / 64, msplit), dim3(256), 0, st, X, static_cast<long long>(ldx), x_f16, Y,
-           static_cast<long long>(ldy), y_f16, M, Q, 256, workspace);
+           static_cast<long long>(ldy), y_f16, M, Q, kXtyRowsPerSplit, workspace);
   MRISR_CHECK_CUDA(cudaGetLastError());
   launch_k(mrisr::xty64_reduce_kernel, dim3(grid_for(64LL * Q, 256, 4)), dim3(256), 0, st, static_cast<const float*>(workspace), msplit, Q, scale, out);
   MRISR_CHECK_CUDA(cudaGetLastError());
@@ -1173,6 +1196,7 @@ int mrisr_xty64(const void* X, int64_t ldx, int x_f16, const void* Y, int64_t ld
 int mrisr_attention_backward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o, int64_t ldo,
                              const void* d_o, int64_t lddo, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
                              float* stats_ws, int batch, int nq, int nk, int heads, int d, void* stream) {
+  MRISR_ONE_DEVICE();
   MRISR_REQUIRE(q && k && v && o && d_o && dq && dk && dv && stats_ws, "attention_backward: null pointer");
   MRISR_REQUIRE(batch > 0 && nq > 0 && nk > 0 && heads > 0, "attention_backward: bad sizes");
   MRISR_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o) && aligned16(d_o) && aligned16(dq) && aligned16(dk) && aligned16(dv),
@@ -1213,12 +1237,14 @@ int mrisr_grad_sqnorm(const mrisr_adam_desc* desc, int n_desc, float max_norm, f
   return 0;
 }
 
-int mrisr_adamw(const mrisr_adam_desc* desc, int n_desc, const float* clip, float lr, float beta1, float beta2, float eps, float weight_decay,
-                int step, void* stream) {
-  MRISR_REQUIRE(desc && n_desc > 0 && step >= 1, "adamw: bad argument");
-  const float bc1 = 1.f - std::pow(beta1, static_cast<float>(step)), bc2 = 1.f - std::pow(beta2, static_cast<float>(step));
-  launch_k(mrisr::adamw_multi_kernel, dim3(n_desc), dim3(256), 0, as_stream(stream), reinterpret_cast<const mrisr::AdamDesc*>(desc), clip, lr,
-           beta1, beta2, eps, weight_decay, bc1, bc2);
+int mrisr_adamw(const mrisr_adam_desc* desc, int n_desc, const float* clip, const float* lr, float beta1, float beta2, float eps,
+                float weight_decay, int* step, void* stream) {
+  MRISR_REQUIRE(desc && n_desc > 0 && lr && step, "adamw: bad argument");
+  cudaStream_t st = as_stream(stream);
+  launch_k(mrisr::adamw_multi_kernel, dim3(n_desc), dim3(256), 0, st, reinterpret_cast<const mrisr::AdamDesc*>(desc), clip, lr,
+           beta1, beta2, eps, weight_decay, static_cast<const int*>(step));
+  MRISR_CHECK_CUDA(cudaGetLastError());
+  launch_k(mrisr::adam_advance_kernel, dim3(1), dim3(32), 0, st, step, clip);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -58,6 +58,13 @@ struct GnBwdArgs {
   __half* dx1; __half* dx2;
   long long ldd1, ldd2;   // row pitches of dx1 / dx2 (they may be the two column ranges of one [B*hw, c1+c2] buffer)
 };
+// Thread t owns pixels t, t + 256, ... and walks the group's channels as packed 16-bit pairs (cpg and c1 are even): no integer
+// division per element and 4-byte loads (a first version indexed single elements with a division each: 167 us per launch at
+// batch 2, 23 % of the fine-tune step).
+__device__ __forceinline__ float2 gnb_ld2(const void* p, long long i, bool h) {
+  const uint32_t v = *reinterpret_cast<const uint32_t*>(static_cast<const uint16_t*>(p) + i);
+  return h ? make_float2(f16_lo(v), f16_hi(v)) : make_float2(bf16_lo(v), bf16_hi(v));
+}
 __global__ void __launch_bounds__(256) groupnorm_backward_kernel(GnBwdArgs a, const float* __restrict__ gamma,
                                                                   const float* __restrict__ beta, float eps, int silu) {
   grid_dep_launch();
@@ -67,49 +74,53 @@ __global__ void __launch_bounds__(256) groupnorm_backward_kernel(GnBwdArgs a, co
   const int C = a.c1 + a.c2, cpg = C / a.groups;
   const int n = a.hw * cpg;
   const int c0 = g * cpg;
-  auto load_x = [&](int pix, int c) -> float {
-    const long long p = static_cast<long long>(b) * a.hw + pix;
-    return c < a.c1 ? ld16(a.x1, p * a.ld1 + c, a.h1 != 0) : ld16(a.x2, p * a.ld2 + (c - a.c1), a.h2 != 0);
+  const long long row0 = static_cast<long long>(b) * a.hw;
+  auto load_x2 = [&](long long p, int c) -> float2 {   // channels c, c + 1 of pixel row p (c even; a pair never straddles x1 | x2)
+    return c < a.c1 ? gnb_ld2(a.x1, p * a.ld1 + c, a.h1 != 0) : gnb_ld2(a.x2, p * a.ld2 + (c - a.c1), a.h2 != 0);
   };
   float s[2] = {0.f, 0.f};
-  for (int e = threadIdx.x; e < n; e += blockDim.x) {
-    const int pix = e / cpg, c = c0 + (e - pix * cpg);
-    const float x = load_x(pix, c);
-    s[0] += x; s[1] += x * x;
+  for (int pix = threadIdx.x; pix < a.hw; pix += blockDim.x) {
+    for (int c = c0; c < c0 + cpg; c += 2) {
+      const float2 x = load_x2(row0 + pix, c);
+      s[0] += x.x + x.y; s[1] += x.x * x.x + x.y * x.y;
+    }
   }
   block_sum<2>(s, sh);
   const float mean = s[0] / n;
   const float rstd = rsqrtf(fmaxf(s[1] / n - mean * mean, 0.f) + eps);
-  float r[2] = {0.f, 0.f};
-  for (int e = threadIdx.x; e < n; e += blockDim.x) {
-    const int pix = e / cpg, c = c0 + (e - pix * cpg);
-    const float xh = (load_x(pix, c) - mean) * rstd;
+  auto dgrad = [&](float xh, float d, int c) -> float {   // dz * silu'(y) * gamma
     const float ga = __ldg(gamma + c);
-    float d = __half2float(a.dz[(static_cast<long long>(b) * a.hw + pix) * C + c]);
     if (silu) {
       const float y = xh * ga + __ldg(beta + c);
       const float sg = 1.f / (1.f + __expf(-y));
       d *= sg * (1.f + y * (1.f - sg));
     }
-    const float gg = d * ga;
-    r[0] += gg; r[1] += gg * xh;
+    return d * ga;
+  };
+  float r[2] = {0.f, 0.f};
+  for (int pix = threadIdx.x; pix < a.hw; pix += blockDim.x) {
+    const __half2* dzp = reinterpret_cast<const __half2*>(a.dz + (row0 + pix) * C + c0);
+    for (int c = c0; c < c0 + cpg; c += 2) {
+      const float2 x = load_x2(row0 + pix, c);
+      const float2 d = __half22float2(dzp[(c - c0) >> 1]);
+      const float xh0 = (x.x - mean) * rstd, xh1 = (x.y - mean) * rstd;
+      const float g0 = dgrad(xh0, d.x, c), g1 = dgrad(xh1, d.y, c + 1);
+      r[0] += g0 + g1; r[1] += g0 * xh0 + g1 * xh1;
+    }
   }
   block_sum<2>(r, sh);
   const float m1 = r[0] / n, m2 = r[1] / n;
-  for (int e = threadIdx.x; e < n; e += blockDim.x) {
-    const int pix = e / cpg, c = c0 + (e - pix * cpg);
-    const float xh = (load_x(pix, c) - mean) * rstd;
-    const float ga = __ldg(gamma + c);
-    float d = __half2float(a.dz[(static_cast<long long>(b) * a.hw + pix) * C + c]);
-    if (silu) {
-      const float y = xh * ga + __ldg(beta + c);
-      const float sg = 1.f / (1.f + __expf(-y));
-      d *= sg * (1.f + y * (1.f - sg));
+  for (int pix = threadIdx.x; pix < a.hw; pix += blockDim.x) {
+    const __half2* dzp = reinterpret_cast<const __half2*>(a.dz + (row0 + pix) * C + c0);
+    for (int c = c0; c < c0 + cpg; c += 2) {
+      const float2 x = load_x2(row0 + pix, c);
+      const float2 d = __half22float2(dzp[(c - c0) >> 1]);
+      const float xh0 = (x.x - mean) * rstd, xh1 = (x.y - mean) * rstd;
+      const float g0 = dgrad(xh0, d.x, c), g1 = dgrad(xh1, d.y, c + 1);
+      const __half2 o = __floats2half2_rn(rstd * (g0 - m1 - xh0 * m2), rstd * (g1 - m1 - xh1 * m2));
+      if (c < a.c1) *reinterpret_cast<__half2*>(a.dx1 + (row0 + pix) * a.ldd1 + c) = o;
+      else *reinterpret_cast<__half2*>(a.dx2 + (row0 + pix) * a.ldd2 + (c - a.c1)) = o;
     }
-    const float dx = rstd * (d * ga - m1 - xh * m2);
-    const long long p = static_cast<long long>(b) * a.hw + pix;
-    if (c < a.c1) a.dx1[p * a.ldd1 + c] = __float2half_rn(dx);
-    else a.dx2[p * a.ldd2 + (c - a.c1)] = __float2half_rn(dx);
   }
 }
 
@@ -353,12 +364,20 @@ __global__ void sqnorm_finalize_kernel(const float* __restrict__ per_tensor, int
   }
 }
 __global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamDesc* __restrict__ desc, const float* __restrict__ clip /*[2]*/,
-                                                          float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2) {
+                                                          const float* __restrict__ lr_dev, float beta1, float beta2, float eps, float wd,
+                                                          const int* __restrict__ step_dev) {
   grid_dep_launch();
   grid_dep_wait();   // launched with programmatic dependent launch: inputs are the predecessor's output
+  // Everything that changes from step to step is read from DEVICE memory (learning rate, step counter, clip coefficient), so the
+  // whole training step -- forward, backward, clip, update -- replays as one captured CUDA graph with no host decision inside.
+  // A non-finite gradient norm (fp16 overflow under the loss scale) skips the update, like torch.cuda.amp.GradScaler.
+  if (clip != nullptr && !isfinite(clip[0])) return;
   const AdamDesc d = desc[blockIdx.x];
   const int n = d.rows * d.cols;
   const float coef = clip != nullptr ? clip[1] : 1.f;
+  const float lr = *lr_dev;
+  const float step = static_cast<float>(*step_dev + 1);
+  const float bc1 = 1.f - powf(beta1, step), bc2 = 1.f - powf(beta2, step);
   for (int e = threadIdx.x; e < n; e += blockDim.x) {
     const int i = e / d.cols, j = e - i * d.cols;
     const float gv = d.g[i * d.g_sr + j * d.g_sc] * d.g_scale * coef;
@@ -370,6 +389,12 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamDesc* __rest
     if (d.d1 != nullptr) st16(d.d1, i * d.d1_sr + j * d.d1_sc, p * d.d1_scale, d.d1_f16 != 0);
     if (d.d2 != nullptr) st16(d.d2, i * d.d2_sr + j * d.d2_sc, p * d.d2_scale, d.d2_f16 != 0);
   }
+}
+// after adamw_multi_kernel: the step counter advances iff the update was applied
+__global__ void adam_advance_kernel(int* step_dev, const float* __restrict__ clip) {
+  grid_dep_launch();
+  grid_dep_wait();
+  if (threadIdx.x == 0 && blockIdx.x == 0 && (clip == nullptr || isfinite(clip[0]))) *step_dev += 1;
 }
 
 }  // namespace mrisr
@@ -405,6 +430,11 @@ struct AttnBwdCfg {
   static constexpr int kSmemBytes = 4 * kTileElems * 2 + 2 * 64 * 4;
 };
 constexpr int kAbThreads = 128;
+__device__ __forceinline__ float ab_ex2(float x) {   // MUFU.EX2: exp2f() is a ~10-instruction sequence
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 template <int D, bool kHalfSrc>
 __device__ __forceinline__ void ab_load_tile(__nv_bfloat16* s, const void* g, long long ld, int row0, int nrows, int col0) {
@@ -526,10 +556,10 @@ __global__ void __launch_bounds__(kAbThreads) attention_bwd_dq_kernel(AttnBwdArg
       const float nm = fmaxf(mx[rrow], tm[rrow]);
       float add = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { add += exp2f(s[j][2 * rrow] - nm) + exp2f(s[j][2 * rrow + 1] - nm); }
+      for (int j = 0; j < 8; ++j) { add += ab_ex2(s[j][2 * rrow] - nm) + ab_ex2(s[j][2 * rrow + 1] - nm); }
       add += __shfl_xor_sync(0xffffffffu, add, 1);
       add += __shfl_xor_sync(0xffffffffu, add, 2);
-      sm[rrow] = sm[rrow] * exp2f(mx[rrow] - nm) + add;
+      sm[rrow] = sm[rrow] * ab_ex2(mx[rrow] - nm) + add;
       mx[rrow] = nm;
     }
   }
@@ -560,7 +590,7 @@ __global__ void __launch_bounds__(kAbThreads) attention_bwd_dq_kernel(AttnBwdArg
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int col = kt * 64 + j * 8 + 2 * t + (i & 1);
-        const float p = col < a.nk ? exp2f(s[j][i] * a.scale_log2 - lse[i >> 1]) : 0.f;
+        const float p = col < a.nk ? ab_ex2(s[j][i] * a.scale_log2 - lse[i >> 1]) : 0.f;
         s[j][i] = p * (dp[j][i] - dsv[i >> 1]);     // dS
       }
     ab_mma_pn<D>(dq, s, sK, lane);
@@ -626,7 +656,7 @@ __global__ void __launch_bounds__(kAbThreads) attention_bwd_dkdv_kernel(AttnBwdA
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int qc = j * 8 + 2 * t + (i & 1);
-        s[j][i] = (qt * 64 + qc < a.nq) ? exp2f(s[j][i] * a.scale_log2 - sL[qc]) : 0.f;   // P^T
+        s[j][i] = (qt * 64 + qc < a.nq) ? ab_ex2(s[j][i] * a.scale_log2 - sL[qc]) : 0.f;   // P^T
       }
     if constexpr (kMode != 2) ab_mma_pn<D>(dv, s, sdO, lane);
     if constexpr (kMode != 1) {

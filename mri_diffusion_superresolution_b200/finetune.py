@@ -65,7 +65,6 @@ class LoRAFineTuner:
         self.unet, self.cfg, self.dev = unet, c, unet.device
         self.sched = scheduler or ResShiftScheduler()
         self.betas, self.eps, self.wd, self.max_norm, self.loss_scale = betas, eps, weight_decay, max_grad_norm, float(loss_scale)
-        self.step_count = 0
         sd = normalize_state_dict_keys(state_dict)
         self._sd = sd
         dev = self.dev
@@ -169,6 +168,12 @@ class LoRAFineTuner:
         self.desc_dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
         self.norm_ws = torch.empty(len(self._descs), device=dev, dtype=torch.float32)
         self.clip = torch.zeros(2, device=dev, dtype=torch.float32)
+        # per-step scalars live on the device, so that a whole step can replay as one CUDA graph
+        self.lr_dev = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+        self._graph = None
+        self._gkey = None
+        self.kernel_launches_per_step = 0
         # write the packed 16-bit destinations once from the masters (also fills the dgrad operands' LoRA parts)
         self._refresh_packed()
 
@@ -202,8 +207,10 @@ class LoRAFineTuner:
             g.ga.zero_()
             g.gb.zero_()
         m, v = self.m32.clone(), self.v32.clone()
-        _lib.check(lib.mrisr_adamw(self.desc_dev.data_ptr(), len(self._descs), None, 0.0, 0.0, 0.0, 1.0, 0.0, 1,
-                                   torch.cuda.current_stream(self.dev).cuda_stream), "mrisr_adamw")
+        zero_lr = torch.zeros(1, device=self.dev, dtype=torch.float32)
+        tmp_step = torch.zeros(1, device=self.dev, dtype=torch.int32)
+        _lib.check(lib.mrisr_adamw(self.desc_dev.data_ptr(), len(self._descs), None, zero_lr.data_ptr(), 0.0, 0.0, 1.0, 0.0,
+                                   tmp_step.data_ptr(), torch.cuda.current_stream(self.dev).cuda_stream), "mrisr_adamw", kernels=2)
         self.m32.copy_(m)
         self.v32.copy_(v)
         self.unet._ehs_key = None
@@ -467,22 +474,62 @@ class LoRAFineTuner:
     @torch.no_grad()
     def optimizer_step(self, lr: float) -> Tensor:
         """Global-norm clip (max_grad_norm) + AdamW on the fp32 masters; rewrites the packed 16-bit operands.  Returns the
-        device tensor {gradient norm, clip coefficient}.  A non-finite norm (fp16 overflow under the loss scale) skips the step."""
+        device tensor {gradient norm, clip coefficient}.  A non-finite norm (fp16 overflow under the loss scale) skips the
+        update on the device (no host decision: the step is graph-capturable)."""
+        self.lr_dev.fill_(float(lr))
+        return self._optimizer_step_device()
+
+    def _optimizer_step_device(self) -> Tensor:
         lib = _lib.load()
         st = torch.cuda.current_stream(self.dev).cuda_stream
         _lib.check(lib.mrisr_grad_sqnorm(self.desc_dev.data_ptr(), len(self._descs), float(self.max_norm), self.norm_ws.data_ptr(),
                                          self.clip.data_ptr(), st), "mrisr_grad_sqnorm", kernels=2)
-        if not bool(torch.isfinite(self.clip[0])):
-            return self.clip.clone()
-        self.step_count += 1
-        _lib.check(lib.mrisr_adamw(self.desc_dev.data_ptr(), len(self._descs), self.clip.data_ptr(), float(lr), self.betas[0],
-                                   self.betas[1], float(self.eps), float(self.wd), self.step_count, st), "mrisr_adamw")
+        _lib.check(lib.mrisr_adamw(self.desc_dev.data_ptr(), len(self._descs), self.clip.data_ptr(), self.lr_dev.data_ptr(),
+                                   self.betas[0], self.betas[1], float(self.eps), float(self.wd), self.step_dev.data_ptr(), st),
+                   "mrisr_adamw", kernels=2)
         self.unet._ehs_key = None        # the cached prompt K/V were projected with the old to_k / to_v LoRA
-        return self.clip.clone()
+        return self.clip
+
+    @property
+    def step_count(self) -> int:
+        """Number of optimizer updates applied so far (device counter; reading it synchronises)."""
+        return int(self.step_dev.item())
 
     def step(self, hr_latents, lr_latents, timesteps, noise, encoder_hidden_states, lr: float = 1e-5,
-             down_intrablock_additional_residuals=None) -> Tuple[Tensor, Tensor]:
-        loss, _ = self.forward_backward(hr_latents, lr_latents, timesteps, noise, encoder_hidden_states,
-                                        down_intrablock_additional_residuals)
-        info = self.optimizer_step(lr)
-        return loss, info
+             down_intrablock_additional_residuals=None, use_cuda_graph: bool = True) -> Tuple[Tensor, Tensor]:
+        """One fine-tune step; returns (loss fp32 [1], {gradient norm, clip coefficient} fp32 [2]) as device tensors.
+        ``use_cuda_graph``: the ~1.3 k kernel launches of a step (forward, loss, backward, clip, AdamW) are captured once per input
+        shape and replayed -- at the reference's batch of 2 the eager step is bound by launch overhead, not by the GPU."""
+        feats = down_intrablock_additional_residuals
+        if not use_cuda_graph:
+            loss, _ = self.forward_backward(hr_latents, lr_latents, timesteps, noise, encoder_hidden_states, feats)
+            return loss, self.optimizer_step(lr).clone()
+        ins = [hr_latents.float(), lr_latents.float(), timesteps.to(torch.int64).reshape(-1), noise.float(), encoder_hidden_states.float()]
+        ins += [f.float() for f in feats] if feats is not None else []
+        key = tuple((tuple(t.shape), t.dtype) for t in ins)
+        if self._graph is None or self._gkey != key:
+            self._static = [torch.empty(t.shape, device=self.dev, dtype=t.dtype) for t in ins]
+            for dst, src in zip(self._static, ins):
+                dst.copy_(src)
+            sfe = self._static[5:] if feats is not None else None
+            side = torch.cuda.Stream(device=self.dev)
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(side):     # warm-up outside capture: kernel attributes, allocator; NO parameter update
+                self.forward_backward(*self._static[:5], sfe)
+                lib = _lib.load()
+                _lib.check(lib.mrisr_grad_sqnorm(self.desc_dev.data_ptr(), len(self._descs), float(self.max_norm), self.norm_ws.data_ptr(),
+                                                 self.clip.data_ptr(), side.cuda_stream), "mrisr_grad_sqnorm", kernels=2)
+            torch.cuda.current_stream(self.dev).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            n0 = _lib.LAUNCHES[0]
+            with torch.cuda.graph(g):
+                self._g_loss, _ = self.forward_backward(*self._static[:5], sfe)
+                self._optimizer_step_device()
+            self.kernel_launches_per_step = _lib.LAUNCHES[0] - n0
+            self._graph, self._gkey = g, key
+        for dst, src in zip(self._static, ins):
+            dst.copy_(src, non_blocking=True)
+        self.lr_dev.fill_(float(lr))
+        self._graph.replay()
+        self.unet._ehs_key = None
+        return self._g_loss.clone(), self.clip.clone()
