@@ -31,6 +31,8 @@ struct AttnTcArgs {
   int nq, nk, heads, batch;
   int kv_rows_per_batch;  // nk, or 0 when one context is shared by every batch element
   float scale_log2;       // log2(e) / sqrt(d)
+  int lag_max;            // split kernel: from the third key tile on, decide the (lazy) rescale on the row maxima of tile j - 2 (no
+                          // per-tile barrier between the two threads of a row); 0 = exchange the maxima of tile j itself
 };
 
 constexpr int kAtcThreads = 384;
@@ -418,7 +420,7 @@ struct AttnSplitCfg {
   static constexpr int kStages = 4;
   static constexpr int kBarBytes = 1024;                    // 16 mbarriers + TMEM slot, padded to the ones tile alignment
   static constexpr int kOnesBytes = 2048;
-  static constexpr int kMaxBytes = 2 * 2 * 128 * 2 * 4;     // [tile parity][query tile][row][half] partial maxima
+  static constexpr int kMaxBytes = 4 * 2 * 128 * 2 * 4;     // [tile & 3][query tile][row][half] partial maxima (ring of 4: tile j reads j - 2)
   static constexpr int kSmemBytes = kQBytes + kStages * kKVBytes + kBarBytes + kOnesBytes + kMaxBytes + 1024;
 };
 
@@ -470,7 +472,7 @@ attention_tcgen05_split_kernel(const __grid_constant__ CUtensorMap tmK, const __
     for (int st = 0; st < kStages; ++st) { mbar_init(kv_full(st), 1); mbar_init(kv_empty(st), 1); }
     for (int g = 0; g < 2; ++g) {
       mbar_init(s_full(g), 1); mbar_init(o_full(g), 1);
-      mbar_init(p_full(g), 256); mbar_init(s_free(g), 1);
+      mbar_init(p_full(g), 256); mbar_init(s_free(g), 256);
     }
     fence_mbar_init();
   }
@@ -618,14 +620,28 @@ attention_tcgen05_split_kernel(const __grid_constant__ CUtensorMap tmK, const __
       // exchange the partial maximum with the thread that owns the other 64 keys of this row.  Every thread of the
       // query tile passes this barrier only after its S loads completed, so right after it one thread hands the S
       // columns back to the MMA warp (s_free): the next tile's Q K^T runs under this tile's exponentials.
-      float* mslot = smax + (((j & 1) * 2 + g) * 128 + rloc) * 2;
+      float* mslot = smax + (((j & 3) * 2 + g) * 128 + rloc) * 2;
       mslot[half] = raw;
       TL(2);
-      asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
+      const bool lagged = a.lag_max != 0 && j >= 2;
+      if (!lagged) asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
       TL(3);
-      if ((i16 & 7) == 0 && lane == 0) mbar_arrive(s_free(g));
-      raw = fmaxf(raw, mslot[half ^ 1]);
-      const float mnew = raw * sc;  // identical in both threads of the row, so both take the same decisions below
+      // every softmax thread hands its S columns back once ITS loads completed (256 arrivals): the next tile's Q K^T runs under
+      // this tile's exponentials
+      mbar_arrive(s_free(g));
+      float mnew;
+      if (lagged) {
+        // Both threads of the row read the SAME two values -- the half maxima of tile j - 2, visible since this thread waited for
+        // o_full(j - 2) before it stored P(j - 1) -- so they take identical decisions without meeting at a barrier, and the eight
+        // warps of the query tile drift apart instead of entering the exponential phase in lock-step.  m_used then lags the true
+        // running maximum by at most two tiles' growth: P = 2^(s - m_used) may exceed 2^8 for a tile or two (bf16 / fp32 have the
+        // range; O / l stay consistent because they are accumulated against the same m_used).
+        const float* prev = smax + ((((j - 2) & 3) * 2 + g) * 128 + rloc) * 2;
+        mnew = fmaxf(prev[0], prev[1]) * sc;
+      } else {
+        raw = fmaxf(raw, mslot[half ^ 1]);
+        mnew = raw * sc;  // identical in both threads of the row, so both take the same decisions below
+      }
       bool o_done = j == 0;         // PV(j-1) known complete (nothing to wait for on the first tile)
       if (j == 0) {
         m_used = mnew;

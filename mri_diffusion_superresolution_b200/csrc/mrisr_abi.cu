@@ -257,6 +257,8 @@ int launch_attention_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, 
   a.nq = nq; a.nk = nk; a.heads = heads; a.batch = batch;
   a.kv_rows_per_batch = kv_broadcast ? 0 : nk;
   a.scale_log2 = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(D)));
+  static const int lag_max = getenv("MRISR_ATTN_LAGMAX") ? atoi(getenv("MRISR_ATTN_LAGMAX")) : 1;   // =0: per-tile maximum exchange (A/B runs)
+  a.lag_max = lag_max;
   dim3 grid((nq + mrisr::kAtcBQ - 1) / mrisr::kAtcBQ, heads, batch);
   if constexpr (D == 40) {
     // two threads per query row (16 softmax warps): see attention_tcgen05_split_kernel
