@@ -156,6 +156,11 @@ typedef struct mrisr_gemm_args {
                             consumer, produced in this GEMM's epilogue (see mrisr_groupnorm_apply_stats).  Needs a 16-bit output,
                             n_store == N, M % 128 == 0, act != GEGLU, residuals only with act == NONE.  Deterministic. */
   int64_t ld_stats;      /* row pitch of gn_stats in PAIRS (>= N) */
+  const void* lora_a;    /* NULL, or the stacked LoRA A matrices of the projections that share this input: bf16 [64, k1] (zero rows
+                            beyond the sum of the ranks).  Then W is [N, k1 + 64] = [W | s B] and the launch computes the peft form
+                            out = x W^T + bf16(x A^T) (s B)^T in ONE pass over x: the rank-r down-projection is a second
+                            accumulator of the same k loop, rounded to bf16 and fed back as a last k-chunk (taps == 1, k2 == 0,
+                            N % 160 == 0, bf16 operands).  Without it the caller computes t = x A^T itself and passes it as A2. */
 } mrisr_gemm_args;
 #define MRISR_F16_OUT 1   /* out (when out_fp32 == 0) */
 #define MRISR_F16_RES1 2  /* res1 */

@@ -21,6 +21,13 @@
 //   out of shared memory (one lane per column), combined across the four
 //   32-row warps of the CTA in a fixed order (deterministic, no atomics on data) -- the consumer's GroupNorm is then a
 //   single normalise+SiLU pass (1 read + 1 write) with no statistics pass, no grid barrier and no re-read.
+// * kLora: the peft LoRA update y = x W^T + ((x A^T) rounded to bf16) (s B)^T inside ONE launch.  Every k-chunk of x feeds two MMAs: the
+//   main one (N = BN) and a skinny one against the stacked A matrices (N = 64) into a second TMEM accumulator T; after the main K
+//   loop the epilogue warps round T to bf16 into a shared-memory A tile and the MMA warp issues one more k-chunk -- A = that tile,
+//   B = the (s B) columns appended to W -- into the main accumulator.  The rank-16 down-projection no longer exists as a separate
+//   GEMM that re-reads x (65 launches and 3 GB of DRAM reads per batch-32 step); numerics are those of the two-GEMM form (T is
+//   rounded to bf16 exactly once).  These GEMMs are memory-bound (K = 320..1280), so the dependent T round trip hides behind the
+//   TMA ring that keeps filling meanwhile.
 // * up2x: nearest-2x upsample + 3x3 conv (diffusers Upsample2D) as four 2x2 sub-pixel convolutions over the
 //   LOW-resolution input with pre-summed weights (packing.pack_upsample_fold): 4/9 of the MACs, no 4x intermediate;
 //   phase (a, b) writes output pixels (2y+a, 2x+b) through a strided 4-D TMA store.
@@ -39,6 +46,7 @@ struct GemmMaps {
   CUtensorMap r1, r2;     // residuals as [M, N] A operands (res_mma > 0)
   CUtensorMap ident;      // 256 x 256 identity weight tile (bf16)
   CUtensorMap ident_h;    // the same in IEEE half, for residual operands stored in fp16
+  CUtensorMap b2;         // kLora: the stacked LoRA A matrices [64, K] (second B operand of every main k-chunk)
   CUtensorMap out[4];     // 16-bit output, 32-row x 32-channel boxes, 64B swizzle (tma_store); [ph] = sub-pixel phase (up2x)
 };
 
@@ -85,13 +93,18 @@ constexpr int kEpilogueThreads = 256;
 // kPair: a cluster of two CTAs on one TPC computes a 256 x BN tile with cta_group::2 MMAs; each CTA stages its own 128
 // rows of A and HALF of the W tile, so every SM pulls 16 KB + BN*64 B per k-chunk from L2 instead of 16 KB + BN*128 B
 // (the round-1 profile showed the single-CTA kernel bound by L2->SM operand delivery).
-template <int BN, bool kPair>
+constexpr int kLoraN = 64;   // rows of the stacked LoRA A matrices == width of the K extension
+template <int BN, bool kPair, bool kLora = false>
 struct GemmCfg {
   static constexpr int kTileM = kPair ? 2 * kBlockM : kBlockM;
   static constexpr int kBRows = kPair ? BN / 2 : BN;
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = kBRows * kBlockK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kB2Rows = kPair ? kLoraN / 2 : kLoraN;
+  static constexpr int kB2Bytes = kLora ? kB2Rows * kBlockK * 2 : 0;
+  static constexpr int kTBytes = kLora ? kBlockM * kLoraN * 2 : 0;   // T = x A^T rounded to bf16, as a 128 x 64 SW128 A tile
+  static constexpr int kStageBytes = kABytes + kBBytes + kB2Bytes;
+  static_assert(!kLora || (kBBytes % 1024 == 0 && kStageBytes % 1024 == 0), "swizzled tiles must stay 1024-byte aligned");
   static constexpr int kEpiBytes = 8 * 4096;     // per-epilogue-warp: two 32x32 bf16 staging buffers (TMA store double buffer)
   static constexpr int kBiasBytes = 8 * BN * 4;  // epilogue-staged bias, one slab per epilogue warp
   static constexpr int kBarBytes = 256;          // <= 2*8+4 mbarriers + the TMEM base slot + 6 statistics counters
@@ -99,11 +112,13 @@ struct GemmCfg {
   // accumulator hand-back happens BEFORE the epilogue arithmetic, so epilogue warps of one CTA can be two tiles apart.
   static constexpr int kStatRing = 3;
   static constexpr int kStatBytes = kStatRing * 4 * BN * 8;
-  static constexpr int kFixedBytes = kEpiBytes + kBiasBytes + kStatBytes + kBarBytes + 1024;  // +1024: manual alignment slack
+  static constexpr int kFixedBytes = kTBytes + kEpiBytes + kBiasBytes + kStatBytes + kBarBytes + 1024;  // +1024: manual alignment slack
   static constexpr int kFit = (232448 - kFixedBytes) / kStageBytes;
   static constexpr int kStages = kFit > 8 ? 8 : kFit;
   static_assert(kStages >= 3, "shared-memory budget");
-  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kTmemNeed = 2 * BN + (kLora ? 2 * kLoraN : 0);
+  static_assert(kTmemNeed <= 512, "TMEM budget");
+  static constexpr int kTmemCols = (kTmemNeed <= 128) ? 128 : (kTmemNeed <= 256) ? 256 : 512;
   static constexpr int kSmemBytes = kStages * kStageBytes + kFixedBytes;
 };
 
@@ -438,19 +453,23 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmKernelParams& p, ui
 // Persistent kernel: grid = #SMs (pairs: clusters of 2).  Pair protocol: both CTAs' TMA loads complete on the LEADER's
 // full barrier; the leader's commits are multicast to both CTAs' empty / accumulator-full barriers; both CTAs' epilogue
 // warps arrive on the leader's accumulator-empty barrier.
-template <int BN, bool kPair>
+template <int BN, bool kPair, bool kLora = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParams p) {
-  using Cfg = GemmCfg<BN, kPair>;
+  using Cfg = GemmCfg<BN, kPair, kLora>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kTileM = Cfg::kTileM;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  uint8_t* sepi_base = smem_al + kStages * Cfg::kStageBytes;  // 1024-aligned: the TMA swizzle pattern is address-based
+  const uint32_t st_addr = smem_base + kStages * Cfg::kStageBytes;   // kLora: the bf16 T tile (1024-aligned)
+  uint8_t* st_ptr = smem_al + kStages * Cfg::kStageBytes;
+  uint8_t* sepi_base = st_ptr + Cfg::kTBytes;  // 1024-aligned: the TMA swizzle pattern is address-based
   float* sbias_base = reinterpret_cast<float*>(sepi_base + Cfg::kEpiBytes);
   float2* sstat_base = reinterpret_cast<float2*>(sepi_base + Cfg::kEpiBytes + Cfg::kBiasBytes);   // [ring][4][BN]
-  const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes + Cfg::kEpiBytes + Cfg::kBiasBytes + Cfg::kStatBytes;
+  const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes + Cfg::kTBytes + Cfg::kEpiBytes + Cfg::kBiasBytes + Cfg::kStatBytes;
+  auto tT_full = [&](int s) { return bar_base + 8u * (2 * kStages + 8 + s); };    // kLora: T accumulator complete (MMA -> epilogue)
+  auto tT_ready = [&](int s) { return bar_base + 8u * (2 * kStages + 10 + s); };  // kLora: bf16 T tile staged (epilogue -> MMA)
   int* scnt_base = reinterpret_cast<int*>(sepi_base + Cfg::kEpiBytes + Cfg::kBiasBytes + Cfg::kStatBytes + 8 * (2 * kStages + 5));   // [ring][2]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
@@ -476,6 +495,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
       tma_prefetch_desc(&maps.ident);
       if (p.f16_rm) tma_prefetch_desc(&maps.ident_h);
     }
+    if (kLora) tma_prefetch_desc(&maps.b2);
     if (p.tma_store) {
       tma_prefetch_desc(&maps.out[0]);
       if (p.up2x) { tma_prefetch_desc(&maps.out[1]); tma_prefetch_desc(&maps.out[2]); tma_prefetch_desc(&maps.out[3]); }
@@ -489,6 +509,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), (kPair ? 2 : 1) * kEpilogueThreads);
+      if (kLora) {
+        mbar_init(tT_full(s), 1);
+        mbar_init(tT_ready(s), (kPair ? 2 : 1) * kEpilogueThreads);
+      }
     }
     for (int s = 0; s < 2 * Cfg::kStatRing; ++s) scnt_base[s] = 0;
     fence_mbar_init();
@@ -520,7 +544,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
     grid_dep_wait();  // operands may be the previous kernel's output
     int stage = 0;
     uint32_t phase = 0;
-    auto load = [&](const CUtensorMap* ma, bool conv, int c0, int ds, int hh, int bb, int m0, const CUtensorMap* mb, int kb, int nb) {
+    auto load = [&](const CUtensorMap* ma, bool conv, int c0, int ds, int hh, int bb, int m0, const CUtensorMap* mb, int kb, int nb,
+                    int lora_k = -1) {
       mbar_wait(empty_bar(stage), phase ^ 1u);
       const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
       const uint32_t sb = sa + Cfg::kABytes;
@@ -528,13 +553,16 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
         if (p.dbg & 1) {
           if (leader) mbar_arrive(full_bar(stage));
         } else if (kPair) {
-          if (leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+          // lora_k >= 0: a main k-chunk of a kLora GEMM also stages the stacked LoRA A rows of that chunk (second B operand)
+          if (leader) mbar_expect_tx(full_bar(stage), 2 * (lora_k >= 0 ? Cfg::kStageBytes : Cfg::kABytes + Cfg::kBBytes));
           if (conv) tma_load_4d_pair(sa, ma, full_bar(stage), c0, ds, hh, bb); else tma_load_2d_pair(sa, ma, full_bar(stage), c0, m0);
           tma_load_2d_pair(sb, mb, full_bar(stage), kb, nb);
+          if (kLora && lora_k >= 0) tma_load_2d_pair(sb + Cfg::kBBytes, &maps.b2, full_bar(stage), lora_k, rank * Cfg::kB2Rows);
         } else {
-          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          mbar_expect_tx(full_bar(stage), lora_k >= 0 ? Cfg::kStageBytes : Cfg::kABytes + Cfg::kBBytes);
           if (conv) tma_load_4d(sa, ma, full_bar(stage), c0, ds, hh, bb); else tma_load_2d(sa, ma, full_bar(stage), c0, m0);
           tma_load_2d(sb, mb, full_bar(stage), kb, nb);
+          if (kLora && lora_k >= 0) tma_load_2d(sb + Cfg::kBBytes, &maps.b2, full_bar(stage), lora_k, 0);
         }
       }
       __syncwarp();
@@ -561,7 +589,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
         for (int kc = 0; kc < kchunks; ++kc) {
           const bool first = kc < p.kc1;
           load(first ? &maps.a1 : &maps.a2, p.conv != 0, (first ? kc : kc - p.kc1) * kBlockK, x0 * p.stride + ds, h0 * p.stride + dr, b0, m0, &maps.b,
-               (tap * kchunks + kc) * kBlockK, n0);
+               (tap * kchunks + kc) * kBlockK, n0, kLora ? kc * kBlockK : -1);
         }
       }
       if (p.res_mma > 0) {
@@ -570,6 +598,21 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
           for (int j = 0; j < rkn; ++j)
             load(r == 0 ? &maps.r1 : &maps.r2, false, (rk0 + j) * kBlockK, 0, 0, 0, m0, ((p.f16_rm >> r) & 1) ? &maps.ident_h : &maps.ident,
                  j * kBlockK, n0 - ph * p.N - rk0 * kBlockK);
+      }
+      if (kLora) {  // the K extension: only its B tile, the (s B) columns appended to W; its A operand is the staged T tile
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t sb = smem_base + stage * Cfg::kStageBytes + Cfg::kABytes;
+        if (elect_one()) {
+          if (kPair) {
+            if (leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::kBBytes);
+            tma_load_2d_pair(sb, &maps.b, full_bar(stage), kchunks * kBlockK, n0);
+          } else {
+            mbar_expect_tx(full_bar(stage), Cfg::kBBytes);
+            tma_load_2d(sb, &maps.b, full_bar(stage), kchunks * kBlockK, n0);
+          }
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -588,6 +631,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
         mbar_wait(tempty_bar(as), aph ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
+        const uint32_t t_tmem = tmem_base + 2 * BN + as * kLoraN;   // kLora: T = x A^T accumulator of this stage
+        constexpr uint32_t idesc_t = umma_idesc_bf16(kTileM, kLoraN);
         for (int ki = 0; ki < kiters; ++ki) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
@@ -603,15 +648,44 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
                 if (kPair) umma_bf16_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
                 else umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
               }
+              if (kLora && ki < kmain) {   // the same x tile against the stacked LoRA A rows of this k-chunk
+                const uint64_t b2desc = umma_smem_desc(sa + Cfg::kABytes + Cfg::kBBytes, 1024, kLayoutSW128);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                  if (kPair) umma_bf16_pair(t_tmem, adesc + 2u * k, b2desc + 2u * k, idesc_t, (ki > 0 || k > 0) ? 1u : 0u);
+                  else umma_bf16(t_tmem, adesc + 2u * k, b2desc + 2u * k, idesc_t, (ki > 0 || k > 0) ? 1u : 0u);
+                }
+              }
             }
             // free the smem slot once these MMAs retire; the last k-chunk also publishes the accumulator
             if (kPair) {
               umma_commit_pair(empty_bar(stage));
-              if (ki == kiters - 1) umma_commit_pair(tfull_bar(as));
+              if (kLora && ki == kmain - 1) umma_commit_pair(tT_full(as));   // T complete: the epilogue warps may round it
+              if (!kLora && ki == kiters - 1) umma_commit_pair(tfull_bar(as));
             } else {
               umma_commit(empty_bar(stage));
-              if (ki == kiters - 1) umma_commit(tfull_bar(as));
+              if (kLora && ki == kmain - 1) umma_commit(tT_full(as));
+              if (!kLora && ki == kiters - 1) umma_commit(tfull_bar(as));
             }
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        if (kLora) {
+          // K extension: A = the bf16 T tile the epilogue warps staged (both CTAs of a pair), B = the (s B) columns of this N tile
+          mbar_wait(tT_ready(as), aph);
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint64_t adesc = umma_smem_desc(st_addr, 1024, kLayoutSW128);
+          const uint64_t bdesc = umma_smem_desc(smem_base + stage * Cfg::kStageBytes + Cfg::kABytes, 1024, kLayoutSW128);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              if (kPair) umma_bf16_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc_b, 1u);
+              else umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc_b, 1u);
+            }
+            if (kPair) { umma_commit_pair(empty_bar(stage)); umma_commit_pair(tfull_bar(as)); }
+            else { umma_commit(empty_bar(stage)); umma_commit(tfull_bar(as)); }
           }
           __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -644,6 +718,24 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
       st.block = static_cast<long long>(ph) * p.part_phase_stride + m_tile * (kPair ? 2 : 1) + rank;
       __syncwarp();  // every lane finished reading the previous tile's slab
       gemm_stage_bias<BN>(p, sbias, n_blk, lane);
+      if (kLora) {
+        // round this thread's row of T = x A^T (its 32 of the 64 columns) to bf16 into the SW128 A tile of the K extension
+        mbar_wait(tT_full(as), aph);
+        tcgen05_fence_after();
+        uint32_t tv[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 2 * BN + as * kLoraN + half * 32, tv);
+        tmem_ld_wait();
+        const int r = q * 32 + lane;
+        uint8_t* trow = st_ptr + r * 128;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          *reinterpret_cast<uint4*>(trow + (((half * 4 + u) ^ (r & 7)) << 4)) =
+              make_uint4(pack_bf16(__uint_as_float(tv[8 * u]), __uint_as_float(tv[8 * u + 1])), pack_bf16(__uint_as_float(tv[8 * u + 2]), __uint_as_float(tv[8 * u + 3])),
+                         pack_bf16(__uint_as_float(tv[8 * u + 4]), __uint_as_float(tv[8 * u + 5])), pack_bf16(__uint_as_float(tv[8 * u + 6]), __uint_as_float(tv[8 * u + 7])));
+        fence_proxy_async_smem();   // the MMA (async proxy) reads what this thread just wrote (generic proxy)
+        tcgen05_fence_before();
+        if (kPair) mbar_arrive_leader(tT_ready(as)); else mbar_arrive(tT_ready(as));
+      }
       mbar_wait(tfull_bar(as), aph);
       tcgen05_fence_after();
       auto release = [&]() {

@@ -142,12 +142,12 @@ struct IdentityTile {
 __device__ const IdentityTile g_identity_tile = IdentityTile(0x3F80);    // bf16 1.0
 __device__ const IdentityTile g_identity_tile_h = IdentityTile(0x3C00);  // IEEE half 1.0 (fp16 residual-stream operands)
 
-template <int BN, bool kPair>
+template <int BN, bool kPair, bool kLora = false>
 int launch_gemm(const mrisr::GemmMaps& maps, const mrisr::GemmKernelParams& p, cudaStream_t st) {
-  using Cfg = mrisr::GemmCfg<BN, kPair>;
+  using Cfg = mrisr::GemmCfg<BN, kPair, kLora>;
   static bool configured = false;
   if (!configured) {
-    MRISR_CHECK_CUDA(cudaFuncSetAttribute(mrisr::gemm_tcgen05_kernel<BN, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MRISR_CHECK_CUDA(cudaFuncSetAttribute(mrisr::gemm_tcgen05_kernel<BN, kPair, kLora>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           Cfg::kSmemBytes));
     configured = true;
   }
@@ -168,7 +168,7 @@ int launch_gemm(const mrisr::GemmMaps& maps, const mrisr::GemmKernelParams& p, c
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl() ? 2 : 1;
-  MRISR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mrisr::gemm_tcgen05_kernel<BN, kPair>, maps, p));
+  MRISR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mrisr::gemm_tcgen05_kernel<BN, kPair, kLora>, maps, p));
   return 0;
 }
 
@@ -694,7 +694,13 @@ int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
   MRISR_REQUIRE(g->k1 > 0 && g->k1 % 64 == 0 && g->k2 >= 0 && g->k2 % 64 == 0, "gemm: k1 (%d) / k2 (%d) must be multiples of 64", g->k1, g->k2);
   MRISR_REQUIRE(g->k2 == 0 || g->a2, "gemm: k2 > 0 but a2 is null");
   MRISR_REQUIRE(g->act >= 0 && g->act <= 3, "gemm: bad act");
-  const int BN = pick_block_n(g->M, g->N, g->act, up2x ? 4 : 1);
+  const bool lora = g->lora_a != nullptr;   // LoRA down-projection fused into this launch (see gemm_tcgen05.cuh, kLora)
+  if (lora) {
+    MRISR_REQUIRE(g->taps == 1 && g->k2 == 0 && g->N % 160 == 0 && !(g->f16_flags & MRISR_F16_AB) && g->act != MRISR_ACT_GEGLU && aligned16(g->lora_a),
+                  "gemm(lora_a): needs taps == 1, k2 == 0, bf16 operands, N %% 160 == 0 (w is [N, k1 + 64]: the (s B) columns appended)");
+    if (!use_pair_kernel()) return fail(MRISR_E_UNSUPPORTED, "gemm(lora_a): needs the CTA-pair kernel");
+  }
+  const int BN = lora ? 160 : pick_block_n(g->M, g->N, g->act, up2x ? 4 : 1);
   if (BN == 0) return fail(MRISR_E_UNSUPPORTED, "gemm: N = %d is not a multiple of 64", g->N);
   const int out_cols = g->act == MRISR_ACT_GEGLU ? g->N / 2 : g->N;
   MRISR_REQUIRE(g->n_store <= out_cols, "gemm: n_store (%d) > produced columns (%d)", g->n_store, out_cols);
@@ -709,7 +715,7 @@ int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
   MRISR_REQUIRE(!(g->act == MRISR_ACT_GEGLU && g->rowvec), "gemm: rowvec unsupported with GEGLU");
   if (int e = load_encode()) return e;
 
-  const int ktot = g->taps * (g->k1 + g->k2);
+  const int ktot = g->taps * (g->k1 + g->k2) + (lora ? 64 : 0);
   const bool pair = use_pair_kernel();
   mrisr::GemmMaps maps;
   CUtensorMap& ma1 = maps.a1;
@@ -789,8 +795,14 @@ int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
   p.dbg = g->reserved;
   p.res_mma = 0;
   p.tma_store = 0;
-  maps.r1 = ma1; maps.r2 = ma1; maps.ident = ma1; maps.ident_h = ma1;
+  maps.r1 = ma1; maps.r2 = ma1; maps.ident = ma1; maps.ident_h = ma1; maps.b2 = ma1;
   for (int i = 0; i < 4; ++i) maps.out[i] = ma1;
+  if (lora) {   // stacked LoRA A matrices [64, k1]: each CTA of the pair stages 32 of the 64 rows per k-chunk
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(g->k1), 64};
+    cuuint64_t str[1] = {static_cast<cuuint64_t>(g->k1) * 2};
+    cuuint32_t box[2] = {64, 32};
+    if (int e = encode_map(&maps.b2, g->lora_a, 2, dims, str, box)) return e;
+  }
   p.gn_part = nullptr; p.ld_part = 0; p.part_phase_stride = 0;
 
   // Residuals of activation-free GEMMs become extra A operands against the identity tile (see gemm_tcgen05.cuh): the
@@ -862,6 +874,7 @@ int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
     p.part_phase_stride = g->M / 128;
   }
   cudaStream_t st = as_stream(stream);
+  if (lora) return launch_gemm<160, true, true>(maps, p, st);
   return pair ? dispatch_gemm<true>(BN, maps, p, st) : dispatch_gemm<false>(BN, maps, p, st);
 }
 

@@ -33,6 +33,7 @@ def _launch(cls: str, work: float, t: Tensor, code_fn, what: str, kernels: int =
     _lib.check(code_fn(), what, kernels)
     e1.record(st)
     PROFILE.append((cls, float(work), e0, e1, detail))
+_GN_SMALL_MAXHW = int(os.environ.get("MRISR_GN_SMALL_MAXHW", "256"))    # tuning runs
 _NO_GN_STATS = bool(os.environ.get("MRISR_NO_GN_STATS"))     # A/B runs: GroupNorm computes its own statistics (two kernels)
 _DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 _H16 = (torch.bfloat16, torch.float16)     # 16-bit activation formats: bf16 everywhere, IEEE half for the residual stream
@@ -78,7 +79,8 @@ def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[T
          rowvec: Optional[Tensor] = None, rowvec_stride: int = 0, rows_per_batch: int = 0, act: int = ACT_NONE,
          res1: Optional[Tensor] = None, res2: Optional[Tensor] = None, n_store: Optional[int] = None,
          out_fp32: bool = False, conv: bool = False, stride: int = 1, out: Optional[Tensor] = None,
-         pad_mode: int = 0, out_dtype=None, _dbg: int = 0, up2x: bool = False, gn_stats: bool = False) -> Tensor:
+         pad_mode: int = 0, out_dtype=None, _dbg: int = 0, up2x: bool = False, gn_stats: bool = False,
+         lora_a: Optional[Tensor] = None) -> Tensor:
     """``act(concat_K(a1, a2) @ w.T + bias + rowvec[batch]) + res1 + res2`` on the tcgen05 kernel.
 
     16-bit tensors are bf16 by default; ``a1`` / ``a2`` / ``w`` may (all three) be float16, ``res1`` / ``res2`` may each be
@@ -88,6 +90,8 @@ def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[T
     ``[N, 9*(k1+k2)]`` (3x3, pad 1, ``stride`` 1 or 2 -- the downsamplers, M = B*(H/2)*(W/2)).  Returns ``[M, n_store]`` (bf16, or fp32 if ``out_fp32``).
     ``up2x=True`` (with ``conv=True``): nearest-2x upsample + 3x3 conv folded into four 2x2 sub-pixel convs; ``w`` is
     ``packing.pack_upsample_fold`` ``[4N, 4*k1]``, the result is ``[B*2H*2W, N]`` (NHWC at the doubled resolution).
+    ``lora_a`` (bf16 ``[64, k1]``, the stacked LoRA A matrices; ``w`` is then ``[N, k1 + 64] = [W | s B]``): the peft update
+    ``x W^T + bf16(x A^T) (s B)^T`` in ONE launch -- the down-projection is a second accumulator of the same k loop.
     ``gn_stats=True``: the epilogue also writes the GroupNorm statistics of the output (per 128-row block and channel);
     they ride on the returned tensor as ``._gn_part`` for ``ops.groupnorm`` (pass it along explicitly through views)."""
     lib = _lib.load()
@@ -130,7 +134,13 @@ def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[T
             k2 = a2.shape[1]
     if up2x and not conv:
         raise ValueError("gemm: up2x is a conv mode")
-    if w.dim() != 2 or not w.is_contiguous() or w.shape[1] != taps * (k1 + k2) or (up2x and w.shape[0] % 4):
+    kext = 0
+    if lora_a is not None:
+        _cuda(lora_a, "gemm.lora_a", torch.bfloat16)
+        if conv or a2 is not None or tuple(lora_a.shape) != (64, k1) or not lora_a.is_contiguous():
+            raise ValueError("gemm(lora_a): a plain GEMM with lora_a [64, k1] and w [N, k1 + 64]")
+        kext = 64
+    if w.dim() != 2 or not w.is_contiguous() or w.shape[1] != taps * (k1 + k2) + kext or (up2x and w.shape[0] % 4):
         raise ValueError(f"gemm: weight must be contiguous [N, {taps * (k1 + k2)}], got {tuple(w.shape)}")
     N = w.shape[0] // 4 if up2x else w.shape[0]
     m_out = 4 * M if up2x else M
@@ -176,13 +186,14 @@ def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[T
     g.out, g.ldo, g.out_fp32 = out.data_ptr(), _rows(out, "gemm.out"), int(out_fp32)
     g.reserved = _dbg
     g.f16_flags = f16
+    g.lora_a = _ptr(lora_a)
     part = None
     if gn_stats and not _NO_GN_STATS:
         if M % 128 or out_fp32 or n_store != N:
             raise ValueError("gemm: gn_stats needs M % 128 == 0, a 16-bit output and n_store == N")
         part = torch.empty(((4 if up2x else 1) * (M // 128), N, 2), device=a1.device, dtype=torch.float32)
         g.gn_stats, g.ld_stats = part.data_ptr(), N
-    _launch("conv3x3" if taps == 9 else "gemm", 2.0 * M * N * taps * (k1 + k2), a1,
+    _launch("conv3x3" if taps == 9 else "gemm", 2.0 * M * N * (taps * (k1 + k2) + kext) + 2.0 * M * kext * k1, a1,
             lambda: lib.mrisr_gemm(C.byref(g), _stream(a1)), "mrisr_gemm",
             detail=(M, N, taps * (k1 + k2), act, res1 is not None))
     if part is not None:
@@ -236,7 +247,7 @@ def groupnorm(x1: Tensor, gamma: Tensor, beta: Tensor, groups: int, eps: float, 
     out = torch.empty((B, H, W, C), device=x1.device, dtype=torch.bfloat16)
     p1 = getattr(x1, "_gn_part", None)
     p2 = getattr(x2, "_gn_part", None) if x2 is not None else None
-    small = hw <= 64 or (hw <= 256 and C <= 1280)          # the single-pass shared-memory kernel wins there (mrisr_groupnorm)
+    small = hw <= 64 or (hw <= _GN_SMALL_MAXHW and C <= 1280)   # the single-pass shared-memory kernel wins there (mrisr_groupnorm)
     fused = (not small and p1 is not None and (x2 is None or p2 is not None) and x1.stride(2) == c1
              and (x2 is None or ld2 == c2))
     work = 4.0 * B * hw * C                                 # algorithmic bytes: one 2-byte read + one 2-byte write per element

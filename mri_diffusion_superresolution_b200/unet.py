@@ -28,6 +28,12 @@ from .packing import (LORA_PAD, pack_conv1x1, pack_conv3x3, pack_geglu, pack_lor
                       pad_cols, pad_rows, pad_to)
 
 Tensor = torch.Tensor
+# Every N tile of a fused launch recomputes T = x A^T for its rows (the skinny MMA rides each k-chunk).  Measured on the 50-step loop
+# (profiles/r2_ab_toggles.txt): fusing the projections of up to 8 tiles (to_out / cross to_q, N = 320 / 640 / 1280) gains 0.7 %, fusing the
+# stacked QKV projection as well (N = 3C: 6 / 12 / 24 tiles) LOSES 0.4 % -- the loop is power-bound and the redundant MMAs cost more
+# than the saved re-read of x.  So QKV keeps its own skinny down-projection GEMM (16 of the 64 per step).
+_LORA_FUSE_MAX_NTILES = int(os.environ.get("MRISR_LORA_FUSE_MAX_NTILES", "8"))
+_NO_LORA_FUSE = bool(os.environ.get("MRISR_NO_LORA_FUSE"))   # A/B runs: LoRA down-projection as its own GEMM
 _NO_UP_FOLD = bool(os.environ.get("MRISR_NO_UP_FOLD"))   # A/B runs: materialise the nearest-2x intermediate
 
 
@@ -372,7 +378,14 @@ class UNet2DConditionB200:
         return ops.carry_stats(out.view(B, H, W, r.cout), out)
 
     def _lora_gemm(self, x: Tensor, a_w: Optional[Tensor], w: Tensor, **kw) -> Tensor:
-        t = ops.gemm(x, a_w) if a_w is not None else None
+        """peft LoRA linear ``x W^T + (alpha / r) (x A^T) B^T`` (unmerged).  Widths that tile by 160 (all of SD-1.5's) take the
+        fused launch: the down-projection is a second accumulator of the same k loop (``mrisr_gemm_args.lora_a``), x is read
+        once.  Other widths (reduced test nets): the down-projection is its own skinny GEMM and enters as a K extension."""
+        if a_w is None:
+            return ops.gemm(x, w, **kw)
+        if w.shape[0] % 160 == 0 and not _NO_LORA_FUSE and w.shape[0] // 160 <= _LORA_FUSE_MAX_NTILES:
+            return ops.gemm(x, w, lora_a=a_w, **kw)
+        t = ops.gemm(x, a_w)
         return ops.gemm(x, w, a2=t, **kw)
 
     def _transformer(self, a: _Attn, x: Tensor, extra_res: Optional[Tensor] = None) -> Tensor:

@@ -38,7 +38,7 @@ def loss_and_lora_grads(params: Dict[str, Tensor], cfg, hr_lat: Tensor, lr_lat: 
     eps_hat = uo.unet_forward(p, x_t, t, ehs, cfg, down_intrablock_additional_residuals=feats)
     loss = ((eps_hat - noise) ** 2).mean()
     loss.backward()
-    return float(loss), {k: p[k].grad.detach().clone() for k in keys}, eps_hat.detach()
+    return float(loss.detach()), {k: p[k].grad.detach().clone() for k in keys}, eps_hat.detach()
 
 
 def clip_coef(grads: Dict[str, Tensor], max_norm: float) -> Tuple[float, float]:

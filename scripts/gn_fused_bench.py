@@ -20,7 +20,7 @@ def graph_ms(fn, reps=10):
 
 
 def main():
-  for B, H, C1, C2 in ((32, 64, 320, 0), (32, 64, 320, 320), (32, 32, 640, 0), (32, 32, 640, 640), (32, 32, 1280, 640), (32, 16, 1280, 1280)):
+  for B, H, C1, C2 in ((32, 64, 320, 0), (32, 64, 320, 320), (32, 32, 640, 0), (32, 32, 640, 640), (32, 32, 1280, 640), (32, 16, 1280, 1280), (32, 16, 1280, 0), (32, 16, 640, 0)):
       srcs = []
       for c in [C1] + ([C2] if C2 else []):
           x = (torch.randn(B, H, H, c, device=dev)).to(torch.bfloat16)

@@ -561,3 +561,33 @@ def test_groupnorm_two_streams_concurrently(ops):
     for i in range(2):
         for g in got[i]:
             assert torch.equal(g, want[i])
+
+
+# ------------------------------------------------------------------------------------------------ LoRA fused into the projection GEMM
+@pytest.mark.parametrize("M,N,K,res", [(4096, 320, 320, True), (131072, 960, 320, False), (1000, 640, 640, True), (300, 1280, 1280, True),
+                                       (8192, 3840, 1280, False), (77, 320, 320, False)])
+def test_gemm_lora_fused(ops, M, N, K, res):
+    """mrisr_gemm_args.lora_a: x W^T + bf16(x A^T) (s B)^T in one launch (the down-projection as a second accumulator of the same
+    k loop) against the two-GEMM form it replaces and against fp32 torch (peft LoRA linear, unmerged)."""
+    from mri_diffusion_superresolution_b200.packing import pack_lora_down, pack_lora_up
+    x = _bf((M, K), 120)
+    nproj = 3 if N % 3 == 0 and N // 3 >= 160 else 1
+    ws = [_bf((N // nproj, K), 121 + i, 1.0 / math.sqrt(K)).float().cpu() for i in range(nproj)]
+    As = [_bf((16, K), 125 + i, 1.0 / math.sqrt(K)).float().cpu() for i in range(nproj)]
+    Bs = [_bf((N // nproj, 16), 129 + i, 0.2).float().cpu() for i in range(nproj)]
+    a_stack = pack_lora_down(As).to(torch.bfloat16).cuda()
+    w_ext = pack_lora_up(ws, Bs, 1.0).to(torch.bfloat16).cuda()
+    bias = _f32((N,), 133)
+    r = _h16((M, N), 134) if res else None
+    fused = ops.gemm(x, w_ext, lora_a=a_stack, bias=bias, res1=r, out_dtype=torch.float16)
+    t = ops.gemm(x, a_stack)
+    two = ops.gemm(x, w_ext, a2=t, bias=bias, res1=r, out_dtype=torch.float16)
+    xf = x.float().cpu()
+    ref = torch.cat([xf @ w.t() + ((xf @ a.t()).to(torch.bfloat16).float() @ b.to(torch.bfloat16).float().t()) for w, a, b in zip(ws, As, Bs)], 1)
+    ref = ref + bias.cpu() + (r.float().cpu() if res else 0)
+    assert fused.shape == (M, N)
+    assert _rel(fused.cpu(), ref) < 4e-3
+    assert _rel(fused, two) < 1.5e-3                      # same roundings, different accumulation order
+    lora_part = torch.cat([(xf @ a.t()) @ b.t() for a, b in zip(As, Bs)], 1)
+    assert lora_part.norm() > 0.05 * ref.norm()             # the LoRA term matters here
+    assert torch.equal(fused, ops.gemm(x, w_ext, lora_a=a_stack, bias=bias, res1=r, out_dtype=torch.float16))
