@@ -33,7 +33,7 @@ class GemmArgs(C.Structure):
         ("conv_stride", C.c_int32), ("conv_pad_mode", C.c_int32),
         ("f16_flags", C.c_int32), ("reserved3", C.c_int32),
         ("gn_stats", C.c_void_p), ("ld_stats", C.c_int64),
-        ("lora_a", C.c_void_p),
+        ("lora_a", C.c_void_p), ("lora_n", C.c_int32), ("reserved4", C.c_int32),
     ]
 
 

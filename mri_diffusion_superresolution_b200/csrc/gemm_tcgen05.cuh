@@ -83,6 +83,8 @@ struct GemmKernelParams {
   float2* gn_part;    // [phases * M/128][ld_part] (sum, sum of squares) per 128-row block and output channel, or nullptr
   long long ld_part;
   int part_phase_stride;  // 128-row blocks per phase (M / 128)
+  int lora_n;             // kLora: rows of the stacked A matrix actually used (sum of the ranks rounded up to 16; <= kLoraN): the skinny
+                          // MMA's N and the K extension's length -- the executed LoRA work follows the rank, not the 64-wide padding
 };
 
 constexpr int kBlockM = 128;
@@ -554,12 +556,12 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
           if (leader) mbar_arrive(full_bar(stage));
         } else if (kPair) {
           // lora_k >= 0: a main k-chunk of a kLora GEMM also stages the stacked LoRA A rows of that chunk (second B operand)
-          if (leader) mbar_expect_tx(full_bar(stage), 2 * (lora_k >= 0 ? Cfg::kStageBytes : Cfg::kABytes + Cfg::kBBytes));
+          if (leader) mbar_expect_tx(full_bar(stage), 2 * (Cfg::kABytes + Cfg::kBBytes + (lora_k >= 0 ? (p.lora_n / 2) * 128 : 0)));
           if (conv) tma_load_4d_pair(sa, ma, full_bar(stage), c0, ds, hh, bb); else tma_load_2d_pair(sa, ma, full_bar(stage), c0, m0);
           tma_load_2d_pair(sb, mb, full_bar(stage), kb, nb);
-          if (kLora && lora_k >= 0) tma_load_2d_pair(sb + Cfg::kBBytes, &maps.b2, full_bar(stage), lora_k, rank * Cfg::kB2Rows);
+          if (kLora && lora_k >= 0) tma_load_2d_pair(sb + Cfg::kBBytes, &maps.b2, full_bar(stage), lora_k, rank * (p.lora_n / 2));
         } else {
-          mbar_expect_tx(full_bar(stage), lora_k >= 0 ? Cfg::kStageBytes : Cfg::kABytes + Cfg::kBBytes);
+          mbar_expect_tx(full_bar(stage), Cfg::kABytes + Cfg::kBBytes + (lora_k >= 0 ? p.lora_n * 128 : 0));
           if (conv) tma_load_4d(sa, ma, full_bar(stage), c0, ds, hh, bb); else tma_load_2d(sa, ma, full_bar(stage), c0, m0);
           tma_load_2d(sb, mb, full_bar(stage), kb, nb);
           if (kLora && lora_k >= 0) tma_load_2d(sb + Cfg::kBBytes, &maps.b2, full_bar(stage), lora_k, 0);
@@ -632,7 +634,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         const uint32_t t_tmem = tmem_base + 2 * BN + as * kLoraN;   // kLora: T = x A^T accumulator of this stage
-        constexpr uint32_t idesc_t = umma_idesc_bf16(kTileM, kLoraN);
+        const uint32_t idesc_t = umma_idesc_bf16(kTileM, kLora ? p.lora_n : kLoraN);
         for (int ki = 0; ki < kiters; ++ki) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
@@ -679,8 +681,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
           const uint64_t adesc = umma_smem_desc(st_addr, 1024, kLayoutSW128);
           const uint64_t bdesc = umma_smem_desc(smem_base + stage * Cfg::kStageBytes + Cfg::kABytes, 1024, kLayoutSW128);
           if (elect_one()) {
-#pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
+            for (int k = 0; k < p.lora_n / 16; ++k) {   // only the k-steps that carry ranks (the rest of the 64-wide extension is zero)
               if (kPair) umma_bf16_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc_b, 1u);
               else umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc_b, 1u);
             }
@@ -722,16 +723,18 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
         // round this thread's row of T = x A^T (its 32 of the 64 columns) to bf16 into the SW128 A tile of the K extension
         mbar_wait(tT_full(as), aph);
         tcgen05_fence_after();
-        uint32_t tv[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 2 * BN + as * kLoraN + half * 32, tv);
-        tmem_ld_wait();
-        const int r = q * 32 + lane;
-        uint8_t* trow = st_ptr + r * 128;
+        if (half * 32 < p.lora_n) {   // (columns >= lora_n of the accumulator were never written and are never read back by the MMA)
+          uint32_t tv[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 2 * BN + as * kLoraN + half * 32, tv);
+          tmem_ld_wait();
+          const int r = q * 32 + lane;
+          uint8_t* trow = st_ptr + r * 128;
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          *reinterpret_cast<uint4*>(trow + (((half * 4 + u) ^ (r & 7)) << 4)) =
-              make_uint4(pack_bf16(__uint_as_float(tv[8 * u]), __uint_as_float(tv[8 * u + 1])), pack_bf16(__uint_as_float(tv[8 * u + 2]), __uint_as_float(tv[8 * u + 3])),
-                         pack_bf16(__uint_as_float(tv[8 * u + 4]), __uint_as_float(tv[8 * u + 5])), pack_bf16(__uint_as_float(tv[8 * u + 6]), __uint_as_float(tv[8 * u + 7])));
+          for (int u = 0; u < 4; ++u)
+            *reinterpret_cast<uint4*>(trow + (((half * 4 + u) ^ (r & 7)) << 4)) =
+                make_uint4(pack_bf16(__uint_as_float(tv[8 * u]), __uint_as_float(tv[8 * u + 1])), pack_bf16(__uint_as_float(tv[8 * u + 2]), __uint_as_float(tv[8 * u + 3])),
+                           pack_bf16(__uint_as_float(tv[8 * u + 4]), __uint_as_float(tv[8 * u + 5])), pack_bf16(__uint_as_float(tv[8 * u + 6]), __uint_as_float(tv[8 * u + 7])));
+        }
         fence_proxy_async_smem();   // the MMA (async proxy) reads what this thread just wrote (generic proxy)
         tcgen05_fence_before();
         if (kPair) mbar_arrive_leader(tT_ready(as)); else mbar_arrive(tT_ready(as));

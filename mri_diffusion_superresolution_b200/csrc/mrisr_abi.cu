@@ -699,6 +699,7 @@ int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
     MRISR_REQUIRE(g->taps == 1 && g->k2 == 0 && g->N % 160 == 0 && !(g->f16_flags & MRISR_F16_AB) && g->act != MRISR_ACT_GEGLU && aligned16(g->lora_a),
                   "gemm(lora_a): needs taps == 1, k2 == 0, bf16 operands, N %% 160 == 0 (w is [N, k1 + 64]: the (s B) columns appended)");
     if (!use_pair_kernel()) return fail(MRISR_E_UNSUPPORTED, "gemm(lora_a): needs the CTA-pair kernel");
+    MRISR_REQUIRE(g->lora_n == 0 || (g->lora_n % 16 == 0 && g->lora_n >= 16 && g->lora_n <= 64), "gemm(lora_a): lora_n must be 16, 32, 48 or 64 (0 = 64)");
   }
   const int BN = lora ? 160 : pick_block_n(g->M, g->N, g->act, up2x ? 4 : 1);
   if (BN == 0) return fail(MRISR_E_UNSUPPORTED, "gemm: N = %d is not a multiple of 64", g->N);
@@ -800,9 +801,10 @@ int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
   if (lora) {   // stacked LoRA A matrices [64, k1]: each CTA of the pair stages 32 of the 64 rows per k-chunk
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(g->k1), 64};
     cuuint64_t str[1] = {static_cast<cuuint64_t>(g->k1) * 2};
-    cuuint32_t box[2] = {64, 32};
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>((g->lora_n ? g->lora_n : 64) / 2)};
     if (int e = encode_map(&maps.b2, g->lora_a, 2, dims, str, box)) return e;
   }
+  p.lora_n = lora ? (g->lora_n ? g->lora_n : 64) : 64;
   p.gn_part = nullptr; p.ld_part = 0; p.part_phase_stride = 0;
 
   // Residuals of activation-free GEMMs become extra A operands against the identity tile (see gemm_tcgen05.cuh): the

@@ -80,7 +80,7 @@ def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[T
          res1: Optional[Tensor] = None, res2: Optional[Tensor] = None, n_store: Optional[int] = None,
          out_fp32: bool = False, conv: bool = False, stride: int = 1, out: Optional[Tensor] = None,
          pad_mode: int = 0, out_dtype=None, _dbg: int = 0, up2x: bool = False, gn_stats: bool = False,
-         lora_a: Optional[Tensor] = None) -> Tensor:
+         lora_a: Optional[Tensor] = None, lora_n: int = 64) -> Tensor:
     """``act(concat_K(a1, a2) @ w.T + bias + rowvec[batch]) + res1 + res2`` on the tcgen05 kernel.
 
     16-bit tensors are bf16 by default; ``a1`` / ``a2`` / ``w`` may (all three) be float16, ``res1`` / ``res2`` may each be
@@ -187,13 +187,14 @@ def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[T
     g.reserved = _dbg
     g.f16_flags = f16
     g.lora_a = _ptr(lora_a)
+    g.lora_n = int(lora_n) if lora_a is not None else 0
     part = None
     if gn_stats and not _NO_GN_STATS:
         if M % 128 or out_fp32 or n_store != N:
             raise ValueError("gemm: gn_stats needs M % 128 == 0, a 16-bit output and n_store == N")
         part = torch.empty(((4 if up2x else 1) * (M // 128), N, 2), device=a1.device, dtype=torch.float32)
         g.gn_stats, g.ld_stats = part.data_ptr(), N
-    _launch("conv3x3" if taps == 9 else "gemm", 2.0 * M * N * (taps * (k1 + k2) + kext) + 2.0 * M * kext * k1, a1,
+    _launch("conv3x3" if taps == 9 else "gemm", 2.0 * M * N * (taps * (k1 + k2) + (lora_n if kext else 0)) + 2.0 * M * (lora_n if kext else 0) * k1, a1,
             lambda: lib.mrisr_gemm(C.byref(g), _stream(a1)), "mrisr_gemm",
             detail=(M, N, taps * (k1 + k2), act, res1 is not None))
     if part is not None:

@@ -384,9 +384,13 @@ class UNet2DConditionB200:
         if a_w is None:
             return ops.gemm(x, w, **kw)
         if w.shape[0] % 160 == 0 and not _NO_LORA_FUSE and w.shape[0] // 160 <= _LORA_FUSE_MAX_NTILES:
-            return ops.gemm(x, w, lora_a=a_w, **kw)
+            return ops.gemm(x, w, lora_a=a_w, lora_n=min(64, -(-self._lora_rows(w.shape[0], x.shape[1]) // 16) * 16), **kw)
         t = ops.gemm(x, a_w)
         return ops.gemm(x, w, a2=t, **kw)
+
+    def _lora_rows(self, n_out: int, k_in: int) -> int:
+        """Rows of the stacked A matrix that carry ranks: three projections share the self-attention input (N = 3C), one otherwise."""
+        return self.cfg.lora_rank * (3 if n_out == 3 * k_in else 1)
 
     def _transformer(self, a: _Attn, x: Tensor, extra_res: Optional[Tensor] = None) -> Tensor:
         c = self.cfg

@@ -579,7 +579,9 @@ def test_gemm_lora_fused(ops, M, N, K, res):
     w_ext = pack_lora_up(ws, Bs, 1.0).to(torch.bfloat16).cuda()
     bias = _f32((N,), 133)
     r = _h16((M, N), 134) if res else None
-    fused = ops.gemm(x, w_ext, lora_a=a_stack, bias=bias, res1=r, out_dtype=torch.float16)
+    fused = ops.gemm(x, w_ext, lora_a=a_stack, lora_n=16 * nproj, bias=bias, res1=r, out_dtype=torch.float16)
+    full = ops.gemm(x, w_ext, lora_a=a_stack, bias=bias, res1=r, out_dtype=torch.float16)     # lora_n = 64: the whole padded extension
+    assert _rel(fused, full) < 1e-4
     t = ops.gemm(x, a_stack)
     two = ops.gemm(x, w_ext, a2=t, bias=bias, res1=r, out_dtype=torch.float16)
     xf = x.float().cpu()
@@ -590,4 +592,4 @@ def test_gemm_lora_fused(ops, M, N, K, res):
     assert _rel(fused, two) < 1.5e-3                      # same roundings, different accumulation order
     lora_part = torch.cat([(xf @ a.t()) @ b.t() for a, b in zip(As, Bs)], 1)
     assert lora_part.norm() > 0.05 * ref.norm()             # the LoRA term matters here
-    assert torch.equal(fused, ops.gemm(x, w_ext, lora_a=a_stack, bias=bias, res1=r, out_dtype=torch.float16))
+    assert torch.equal(fused, ops.gemm(x, w_ext, lora_a=a_stack, lora_n=16 * nproj, bias=bias, res1=r, out_dtype=torch.float16))
