@@ -196,6 +196,8 @@ def run_finetune(args):
     params = init_unet_params(cfg, seed=0, device=dev)
     unet.load_state_dict(params)
     ft = LoRAFineTuner(unet, params)
+    if world > 1:
+        ft.enable_data_parallel()       # DDP semantics for the LoRA matrices: one all-reduce of the flat gradient buffer per step
     del params
     torch.cuda.empty_cache()
     g = torch.Generator(device=dev).manual_seed(100 + rank)
@@ -262,8 +264,11 @@ def run_finetune(args):
             "data": "synthetic",
             "config": {"workload": "sd15_unet_lora16_finetune_step_512px", "batch_per_gpu": B, "global_batch": B * world, "lora_rank": 16,
                        "trainable_params": ft.n_params, "optimizer": "AdamW beta 0.9/0.999 wd 1e-2 eps 1e-8, max_grad_norm 1.0",
-                       "parallelism": f"replicas x{world} (no gradient all-reduce: the reference's config is single-process)",
-                       "cuda_graph": True, "kernel_launches_per_step": ft.kernel_launches_per_step, "l2": "working set >> 126 MB L2"},
+                       "parallelism": ("single process (the reference's run config)" if world == 1 else
+                                       f"data parallel x{world}: micro-batch {B} per GPU, frozen UNet replicated, ONE NCCL all-reduce of the "
+                                       f"flat LoRA gradient buffer ({ft.gbuf.numel() * 4 / 1e6:.1f} MB) per step"),
+                       "value_counts": "micro-batch steps summed over the ranks (optimizer steps/s of the data-parallel job = value / n_gpus)",
+                       "cuda_graph": world == 1, "kernel_launches_per_step": ft.kernel_launches_per_step, "l2": "working set >> 126 MB L2"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "final_loss": float(loss), "grad_norm": float(info[0]),
             "roofline": {"bound": "tensor", "kernel": "whole step: forward + backward + clip + AdamW replayed as one CUDA graph",
                          "achieved": tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": tflops / peaks["bf16_sustained"],

@@ -644,3 +644,15 @@ def attention_backward(q: Tensor, k: Tensor, v: Tensor, o: Tensor, d_o: Tensor, 
                                             o.data_ptr(), _rows(o, "o"), d_o.data_ptr(), _rows(d_o, "d_o"), dq.data_ptr(), _rows(dq, "dq"),
                                             dk.data_ptr(), _rows(dk, "dk"), dv.data_ptr(), _rows(dv, "dv"), ws.data_ptr(), batch, nq, nk,
                                             heads, d, _stream(q)), "mrisr_attention_backward", kernels=2)
+
+
+def scale_(x: Tensor, factor: float) -> Tensor:
+    """x *= factor for an fp32 buffer, on the axpy kernel (``mrisr_sched_step`` with c1 = factor, c2 = 0): gradient averaging."""
+    _cuda(x, "scale_.x", torch.float32)
+    n = x.numel()
+    if n % 4:
+        raise ValueError("scale_: length must be a multiple of 4")
+    coef = torch.tensor([factor, 0.0, 0.0, 0.0], device=x.device, dtype=torch.float32)
+    flat = x.view(-1)
+    sched_step(flat, flat, coef, out=flat)
+    return x

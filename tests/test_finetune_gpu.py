@@ -256,3 +256,18 @@ def test_finetune_step_updates_parameters_and_packed_operands():
         l, _ = ft.step(hr.cuda(), lr.cuda(), t.cuda(), noise.cuda(), ehs.cuda(), lr=lr_rate)
         losses.append(float(l))
     assert losses[-1] < losses[0]
+
+
+def test_flat_gradient_buffer_and_scale(ops):
+    """The LoRA gradients of all projection groups live in ONE flat buffer (a single all-reduce under data parallelism);
+    ops.scale_ averages it in place."""
+    ocfg, params, unet, ft = _setup(SMALL)
+    assert ft.gbuf.is_contiguous() and ft.gbuf.numel() == sum(g.ga.numel() + g.gb.numel() for g in ft._groups())
+    hr, lr, t, noise, ehs, _ = _batch(SMALL, 2, 4, False)
+    ft.forward_backward(hr.cuda(), lr.cuda(), t.cuda(), noise.cuda(), ehs.cuda())
+    before = ft.gbuf.clone()
+    g0 = {k: v.clone() for k, v in ft.lora_grads().items()}
+    ops.scale_(ft.gbuf, 0.5)
+    assert torch.equal(ft.gbuf, before * 0.5)
+    g1 = ft.lora_grads()
+    assert all(torch.equal(g1[k], g0[k] * 0.5) for k in g0)
