@@ -263,3 +263,23 @@ def test_upsample_fold_weights_are_exact():
                     acc += torch.einsum("oc,bchw->bohw", wf[2 * a + b, :, ty * 2 + tx, :], patch)
             out[:, :, a::2, b::2] = acc
     assert (out - ref).abs().max().item() < 1e-5
+
+
+def test_dgrad_filter_packing_matches_autograd():
+    """finetune._dgrad3x3: the data gradient of a 3x3 pad-1 convolution is a 3x3 pad-1 convolution of dY with the tap-flipped,
+    channel-transposed filter in the GEMM's [N = Cin, K = tap*Cout + co] layout -- checked against torch autograd on the CPU
+    (the GPU test runs the same packing through mrisr_gemm)."""
+    import torch.nn.functional as F
+    from mri_diffusion_superresolution_b200.finetune import _dgrad3x3
+    g = torch.Generator().manual_seed(11)
+    co, ci, H = 6, 4, 5
+    w = torch.randn(co, ci, 3, 3, generator=g, dtype=torch.float64)
+    x = torch.randn(2, ci, H, H, generator=g, dtype=torch.float64, requires_grad=True)
+    dy = torch.randn(2, co, H, H, generator=g, dtype=torch.float64)
+    F.conv2d(x, w, padding=1).backward(dy)
+    wd = _dgrad3x3(w.float()).double()                                   # [ci, 9*co], k = tap*co + c
+    filt = wd.view(ci, 3, 3, co).permute(0, 3, 1, 2).contiguous()        # conv2d weight [out = ci, in = co, 3, 3]
+    got = F.conv2d(dy, filt, padding=1)
+    assert (got - x.grad).abs().max().item() < 1e-5
+    wp = _dgrad3x3(w.float(), pad_cout_to=8)
+    assert wp.shape == (ci, 9 * 8) and float(wp.view(ci, 9, 8)[:, :, co:].abs().max()) == 0.0
