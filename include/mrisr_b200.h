@@ -241,7 +241,8 @@ int mrisr_slice_volume(const float* vol_hwd, int H, int W, int D, int map_intens
  * lddx2), half -- they may be the two column ranges of one buffer.  gamma / beta are frozen (no parameter gradients). */
 int mrisr_groupnorm_backward(const void* x1, int64_t ld1, int c1, const void* x2, int64_t ld2, int c2, const void* dz, int batch, int hw,
                              int groups, const float* gamma, const float* beta, float eps, int silu, void* dx1, int64_t lddx1, void* dx2,
-                             int64_t lddx2, int f16_flags, void* stream);
+                             int64_t lddx2, float* workspace /* >= 2 * mrisr_groupnorm_workspace_floats(batch, groups), or NULL: the
+                             one-CTA-per-(group, image) form */, int f16_flags, void* stream);
 /* Backward of mrisr_layernorm: dx = dLN(dy) (+ dres, the gradient arriving over the residual connection); all gradients half. */
 int mrisr_layernorm_backward(const void* x, int64_t ldx, int x_f16, const void* dy, const float* gamma, float eps, const void* dres,
                              void* dx, int rows, int C, void* stream);

@@ -84,7 +84,7 @@ PROTOTYPES = {
     "mrisr_gaussian_sample": (_I, [_P, _P, _P, _I, _I, _I, _F, _P]),
     "mrisr_eval_metrics_workspace_floats": (_L, [_I, _I, _I]),
     "mrisr_eval_metrics": (_I, [_P, _P, _I, _I, _I, _F, _F, _I, _P, _P, _P, _P]),
-    "mrisr_groupnorm_backward": (_I, [_P, _L, _I, _P, _L, _I, _P, _I, _I, _I, _P, _P, _F, _I, _P, _L, _P, _L, _I, _P]),
+    "mrisr_groupnorm_backward": (_I, [_P, _L, _I, _P, _L, _I, _P, _I, _I, _I, _P, _P, _F, _I, _P, _L, _P, _L, _P, _I, _P]),
     "mrisr_layernorm_backward": (_I, [_P, _L, _I, _P, _P, _F, _P, _P, _I, _I, _P]),
     "mrisr_geglu_forward": (_I, [_P, _P, _L, _I, _P]),
     "mrisr_geglu_backward": (_I, [_P, _P, _P, _L, _I, _P]),

@@ -1120,11 +1120,44 @@ int mrisr_slice_volume(const float* vol, int H, int W, int D, int map_intensity,
 
 int mrisr_groupnorm_backward(const void* x1, int64_t ld1, int c1, const void* x2, int64_t ld2, int c2, const void* dz, int batch, int hw,
                              int groups, const float* gamma, const float* beta, float eps, int silu, void* dx1, int64_t lddx1, void* dx2,
-                             int64_t lddx2, int f16_flags, void* stream) {
+                             int64_t lddx2, float* workspace, int f16_flags, void* stream) {
   MRISR_REQUIRE(x1 && dz && gamma && beta && dx1, "groupnorm_backward: null pointer");
   MRISR_REQUIRE(batch > 0 && hw > 0 && c1 > 0 && c2 >= 0 && (c2 == 0 || (x2 && dx2)), "groupnorm_backward: bad sizes");
   MRISR_REQUIRE(groups > 0 && (c1 + c2) % groups == 0 && ((c1 + c2) / groups) % 2 == 0 && c1 % 2 == 0 && ld1 % 2 == 0 && ld2 % 2 == 0 && lddx1 % 2 == 0 && lddx2 % 2 == 0,
                 "groupnorm_backward: groups must divide the channel count into even-sized groups; even strides");
+  const int C = c1 + c2;
+  // large levels: slab-parallel three-launch form (statistics, reductions, result), each launch fills the machine
+  if (workspace != nullptr && hw >= 1024 && C % 8 == 0 && c1 % 8 == 0 && C / 8 <= 512 && ld1 % 8 == 0 && ld2 % 8 == 0 && lddx1 % 8 == 0 && lddx2 % 8 == 0 &&
+      groups <= 64 && aligned16(x1) && aligned16(dz) && aligned16(dx1) && (!x2 || (aligned16(x2) && aligned16(dx2)))) {
+    const int nvec = C / 8;
+    int R = 256 / nvec; if (R < 1) R = 1; if (R > hw) R = hw;
+    int nslab = (sm_count() * 4 + batch - 1) / batch;
+    const int max_slabs = (hw + 4 * R - 1) / (4 * R);
+    if (nslab > max_slabs) nslab = max_slabs;
+    if (nslab > kGnMaxSlabs) nslab = kGnMaxSlabs;
+    if (nslab < 1) nslab = 1;
+    const int pps = (hw + nslab - 1) / nslab;
+    nslab = (hw + pps - 1) / pps;
+    mrisr::GnArgs ga;
+    ga.x1 = static_cast<const __nv_bfloat16*>(x1); ga.x2 = static_cast<const __nv_bfloat16*>(x2);
+    ga.ld1 = ld1; ga.ld2 = ld2; ga.c1 = c1; ga.c2 = c2; ga.hw = hw; ga.batch = batch; ga.groups = groups;
+    ga.h1 = f16_flags & 1; ga.h2 = (f16_flags >> 1) & 1; ga.nslab = nslab; ga.pix_per_slab = pps;
+    ga.inv_n = 1.0 / (static_cast<double>(hw) * (C / groups));
+    float2* p1 = reinterpret_cast<float2*>(workspace);
+    float2* p2 = p1 + static_cast<long long>(batch) * nslab * groups;
+    dim3 block(nvec, R), grid(nslab, batch);
+    cudaStream_t st = as_stream(stream);
+    launch_k(mrisr::groupnorm_stats_kernel, dim3(grid), dim3(block), 2 * R * C * sizeof(float), st, ga, p1);
+    MRISR_CHECK_CUDA(cudaGetLastError());
+    launch_k(mrisr::groupnorm_bwd_reduce_kernel, dim3(grid), dim3(block), 2 * R * C * sizeof(float), st, ga, static_cast<const float2*>(p1),
+             static_cast<const __half*>(dz), gamma, beta, eps, silu, p2);
+    MRISR_CHECK_CUDA(cudaGetLastError());
+    launch_k(mrisr::groupnorm_bwd_apply_kernel, dim3(grid), dim3(block), 0, st, ga, static_cast<const float2*>(p1), static_cast<const float2*>(p2),
+             static_cast<const __half*>(dz), gamma, beta, eps, silu, static_cast<__half*>(dx1), static_cast<long long>(lddx1),
+             static_cast<__half*>(dx2), static_cast<long long>(lddx2));
+    MRISR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   mrisr::GnBwdArgs a;
   a.x1 = x1; a.x2 = x2; a.ld1 = ld1; a.ld2 = ld2; a.c1 = c1; a.c2 = c2; a.hw = hw; a.groups = groups;
   a.h1 = f16_flags & 1; a.h2 = (f16_flags >> 1) & 1;

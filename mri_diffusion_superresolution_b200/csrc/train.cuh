@@ -11,6 +11,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 
+#include "pointwise.cuh"
 #include "ptx.cuh"
 
 namespace mrisr {
@@ -121,6 +122,141 @@ __global__ void __launch_bounds__(256) groupnorm_backward_kernel(GnBwdArgs a, co
       if (c < a.c1) *reinterpret_cast<__half2*>(a.dx1 + (row0 + pix) * a.ldd1 + c) = o;
       else *reinterpret_cast<__half2*>(a.dx2 + (row0 + pix) * a.ldd2 + (c - a.c1)) = o;
     }
+  }
+}
+
+// Slab-parallel form of the same backward pass for the large levels (hw >= 1024): the one-CTA-per-(group, image) kernel above runs
+// on 64 CTAs at the reference's batch of 2 (73 us per norm); here the image is cut into pixel slabs as in the forward kernels
+// (thread (vx, ry) = 8 channels x strided pixels, 16-byte loads), in three launches that each fill the machine:
+//   groupnorm_stats_kernel (pointwise.cuh)   partial1[b][slab][g] = (sum x, sum x^2)
+//   groupnorm_bwd_reduce_kernel              partial2[b][slab][g] = (sum g, sum g * xhat),   g = dz * silu'(y) * gamma
+//   groupnorm_bwd_apply_kernel               dx = rstd * (g - mean(g) - xhat * mean(g * xhat))
+// All partial sums are combined in a fixed order (deterministic).
+__device__ __forceinline__ void gnb_group_stats(const GnArgs& a, const float2* __restrict__ partial, float eps, float* s_mean, float* s_rstd,
+                                                int tid, int nthr) {
+  const int C = a.c1 + a.c2, cpg = C / a.groups;
+  for (int g = tid; g < a.groups; g += nthr) {
+    double su = 0.0, sq = 0.0;
+    for (int k = 0; k < a.nslab; ++k) {
+      const float2 v = __ldg(partial + (static_cast<long long>(blockIdx.y) * a.nslab + k) * a.groups + g);
+      su += v.x; sq += v.y;
+    }
+    const double mean = su * a.inv_n;
+    double var = sq * a.inv_n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[g] = static_cast<float>(mean);
+    s_rstd[g] = rsqrtf(static_cast<float>(var) + eps);
+  }
+  (void)cpg;
+}
+// per-thread: gg[8] and xhat[8] of one 8-channel vector of one pixel
+__device__ __forceinline__ void gnb_vec(const uint4& xv, const uint4& dv, bool hsrc, const float (&mean8)[8], const float (&rstd8)[8],
+                                        const float (&ga)[8], const float (&be)[8], int silu, float (&gg)[8], float (&xh)[8]) {
+  float x[8], d[8];
+  unpack8_any(xv, x, hsrc);
+  unpack8h(dv, d);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    xh[j] = (x[j] - mean8[j]) * rstd8[j];
+    float dd = d[j];
+    if (silu) {
+      const float y = xh[j] * ga[j] + be[j];
+      const float sg = 1.f / (1.f + __expf(-y));
+      dd *= sg * (1.f + y * (1.f - sg));
+    }
+    gg[j] = dd * ga[j];
+  }
+}
+__global__ void groupnorm_bwd_reduce_kernel(GnArgs a, const float2* __restrict__ partial1, const __half* __restrict__ dz,
+                                            const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
+                                            float2* __restrict__ partial2) {
+  grid_dep_launch();
+  grid_dep_wait();
+  extern __shared__ float gnb_sh[];   // [2][R][C] per-thread-row channel sums
+  __shared__ float s_mean[64], s_rstd[64];
+  const int C = a.c1 + a.c2, cpg = C / a.groups;
+  const int vx = threadIdx.x, ry = threadIdx.y, R = blockDim.y;
+  const int b = blockIdx.y, slab = blockIdx.x;
+  const int tid = ry * blockDim.x + vx, nthr = blockDim.x * blockDim.y;
+  gnb_group_stats(a, partial1, eps, s_mean, s_rstd, tid, nthr);
+  __syncthreads();
+  float mean8[8], rstd8[8], ga[8], be[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = vx * 8 + j;
+    mean8[j] = s_mean[c / cpg]; rstd8[j] = s_rstd[c / cpg];
+    ga[j] = __ldg(gamma + c); be[j] = __ldg(beta + c);
+  }
+  const bool hsrc = (vx < (a.c1 >> 3) ? a.h1 : a.h2) != 0;
+  float s0[8], s1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s0[j] = 0.f; s1[j] = 0.f; }
+  const int p0 = slab * a.pix_per_slab, p1 = min(a.hw, p0 + a.pix_per_slab);
+  for (int pix = p0 + ry; pix < p1; pix += R) {
+    const uint4 xv = gn_load(a, b, pix, vx);
+    const uint4 dv = __ldg(reinterpret_cast<const uint4*>(dz + (static_cast<long long>(b) * a.hw + pix) * C) + vx);
+    float gg[8], xh[8];
+    gnb_vec(xv, dv, hsrc, mean8, rstd8, ga, be, silu, gg, xh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s0[j] += gg[j]; s1[j] += gg[j] * xh[j]; }
+  }
+  float* sh_s = gnb_sh + ry * C + vx * 8;
+  float* sh_q = gnb_sh + R * C + ry * C + vx * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sh_s[j] = s0[j]; sh_q[j] = s1[j]; }
+  __syncthreads();
+  if (tid < a.groups) {
+    float su = 0.f, sq = 0.f;
+    for (int r = 0; r < R; ++r) {
+      const float* ps = gnb_sh + r * C + tid * cpg;
+      const float* pq = gnb_sh + R * C + r * C + tid * cpg;
+      for (int c = 0; c < cpg; ++c) { su += ps[c]; sq += pq[c]; }
+    }
+    partial2[(static_cast<long long>(b) * a.nslab + slab) * a.groups + tid] = make_float2(su, sq);
+  }
+}
+__global__ void groupnorm_bwd_apply_kernel(GnArgs a, const float2* __restrict__ partial1, const float2* __restrict__ partial2,
+                                           const __half* __restrict__ dz, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                           float eps, int silu, __half* __restrict__ dx1, long long ldd1, __half* __restrict__ dx2, long long ldd2) {
+  grid_dep_launch();
+  grid_dep_wait();
+  __shared__ float s_mean[64], s_rstd[64], s_m1[64], s_m2[64];
+  const int C = a.c1 + a.c2, cpg = C / a.groups;
+  const int vx = threadIdx.x, ry = threadIdx.y, R = blockDim.y;
+  const int b = blockIdx.y, slab = blockIdx.x;
+  const int tid = ry * blockDim.x + vx, nthr = blockDim.x * blockDim.y;
+  gnb_group_stats(a, partial1, eps, s_mean, s_rstd, tid, nthr);
+  for (int g = tid; g < a.groups; g += nthr) {
+    double su = 0.0, sq = 0.0;
+    for (int k = 0; k < a.nslab; ++k) {
+      const float2 v = __ldg(partial2 + (static_cast<long long>(b) * a.nslab + k) * a.groups + g);
+      su += v.x; sq += v.y;
+    }
+    s_m1[g] = static_cast<float>(su * a.inv_n);
+    s_m2[g] = static_cast<float>(sq * a.inv_n);
+  }
+  __syncthreads();
+  float mean8[8], rstd8[8], ga[8], be[8], m1[8], m2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = vx * 8 + j, g = c / cpg;
+    mean8[j] = s_mean[g]; rstd8[j] = s_rstd[g]; m1[j] = s_m1[g]; m2[j] = s_m2[g];
+    ga[j] = __ldg(gamma + c); be[j] = __ldg(beta + c);
+  }
+  const int nv1 = a.c1 >> 3;
+  const bool hsrc = (vx < nv1 ? a.h1 : a.h2) != 0;
+  const int p0 = slab * a.pix_per_slab, p1 = min(a.hw, p0 + a.pix_per_slab);
+  for (int pix = p0 + ry; pix < p1; pix += R) {
+    const long long row = static_cast<long long>(b) * a.hw + pix;
+    const uint4 xv = gn_load(a, b, pix, vx);
+    const uint4 dv = __ldg(reinterpret_cast<const uint4*>(dz + row * C) + vx);
+    float gg[8], xh[8], o[8];
+    gnb_vec(xv, dv, hsrc, mean8, rstd8, ga, be, silu, gg, xh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = rstd8[j] * (gg[j] - m1[j] - xh[j] * m2[j]);
+    const uint4 ov = make_uint4(pack_f16(o[0], o[1]), pack_f16(o[2], o[3]), pack_f16(o[4], o[5]), pack_f16(o[6], o[7]));
+    if (vx < nv1) reinterpret_cast<uint4*>(dx1 + row * ldd1)[vx] = ov;
+    else reinterpret_cast<uint4*>(dx2 + row * ldd2)[vx - nv1] = ov;
   }
 }
 

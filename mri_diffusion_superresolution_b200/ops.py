@@ -541,9 +541,11 @@ def groupnorm_backward(x1: Tensor, dz: Tensor, gamma: Tensor, beta: Tensor, grou
     f16 = (1 if x1.dtype == torch.float16 else 0) | (2 if (x2 is not None and x2.dtype == torch.float16) else 0)
     dx1 = torch.empty((B * H * W, c1), device=x1.device, dtype=torch.float16)
     dx2 = torch.empty((B * H * W, c2), device=x1.device, dtype=torch.float16) if x2 is not None else None
+    ws = torch.empty((2 * lib.mrisr_groupnorm_workspace_floats(B, groups),), device=x1.device, dtype=torch.float32)
     _lib.check(lib.mrisr_groupnorm_backward(x1.data_ptr(), x1.stride(2), c1, _ptr(x2), ld2, c2, dz.data_ptr(), B, H * W, groups,
                                             gamma.data_ptr(), beta.data_ptr(), float(eps), int(silu), dx1.data_ptr(), c1,
-                                            _ptr(dx2), c2, f16, _stream(x1)), "mrisr_groupnorm_backward")
+                                            _ptr(dx2), c2, ws.data_ptr(), f16, _stream(x1)), "mrisr_groupnorm_backward",
+               kernels=3 if H * W >= 1024 else 1)
     return dx1, dx2
 
 
