@@ -160,10 +160,12 @@ typedef struct mrisr_gemm_args {
                             beyond the sum of the ranks).  Then W is [N, k1 + 64] = [W | s B] and the launch computes the peft form
                             out = x W^T + bf16(x A^T) (s B)^T in ONE pass over x: the rank-r down-projection is a second
                             accumulator of the same k loop, rounded to bf16 and fed back as a last k-chunk (taps == 1, k2 == 0,
-                            N % 160 == 0, bf16 operands).  Without it the caller computes t = x A^T itself and passes it as A2. */
+                            N % 160 == 0; operands bf16, or IEEE half with MRISR_F16_AB).  Without it the caller computes t = x A^T itself and passes it as A2. */
   int32_t lora_n;        /* with lora_a: how many of the 64 stacked rows carry ranks, rounded up to 16 (16 / 32 / 48 / 64; 0 = 64):
                             the executed down-projection and K extension follow the rank, not the 64-wide padding */
   int32_t reserved4;
+  void* lora_t_out;      /* with lora_a: NULL, or a 16-bit [M, 64] buffer (operand format, row pitch 64) that receives the rounded
+                            T = x A^T -- the fine-tune step keeps it for the rank-16 weight gradients */
 } mrisr_gemm_args;
 #define MRISR_F16_OUT 1   /* out (when out_fp32 == 0) */
 #define MRISR_F16_RES1 2  /* res1 */

@@ -34,6 +34,7 @@ class GemmArgs(C.Structure):
         ("f16_flags", C.c_int32), ("reserved3", C.c_int32),
         ("gn_stats", C.c_void_p), ("ld_stats", C.c_int64),
         ("lora_a", C.c_void_p), ("lora_n", C.c_int32), ("reserved4", C.c_int32),
+        ("lora_t_out", C.c_void_p),
     ]
 
 

@@ -83,6 +83,8 @@ struct GemmKernelParams {
   float2* gn_part;    // [phases * M/128][ld_part] (sum, sum of squares) per 128-row block and output channel, or nullptr
   long long ld_part;
   int part_phase_stride;  // 128-row blocks per phase (M / 128)
+  void* lora_t_out;       // kLora: optional [M, kLoraN] 16-bit copy of the rounded T = x A^T (row pitch kLoraN): the fine-tune step keeps it for
+                          // the rank-16 weight gradients (forward: t = x A^T; backward: u = dy (s B)); written by the N tile 0 of every M tile
   int lora_n;             // kLora: rows of the stacked A matrix actually used (sum of the ranks rounded up to 16; <= kLoraN): the skinny
                           // MMA's N and the K extension's length -- the executed LoRA work follows the rank, not the 64-wide padding
 };
@@ -634,7 +636,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         const uint32_t t_tmem = tmem_base + 2 * BN + as * kLoraN;   // kLora: T = x A^T accumulator of this stage
-        const uint32_t idesc_t = umma_idesc_bf16(kTileM, kLora ? p.lora_n : kLoraN);
+        const uint32_t idesc_t = p.f16_ab ? umma_idesc_f16(kTileM, kLora ? p.lora_n : kLoraN) : umma_idesc_bf16(kTileM, kLora ? p.lora_n : kLoraN);
         for (int ki = 0; ki < kiters; ++ki) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
@@ -682,8 +684,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
           const uint64_t bdesc = umma_smem_desc(smem_base + stage * Cfg::kStageBytes + Cfg::kABytes, 1024, kLayoutSW128);
           if (elect_one()) {
             for (int k = 0; k < p.lora_n / 16; ++k) {   // only the k-steps that carry ranks (the rest of the 64-wide extension is zero)
-              if (kPair) umma_bf16_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc_b, 1u);
-              else umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc_b, 1u);
+              if (kPair) umma_bf16_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc_main, 1u);
+              else umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc_main, 1u);
             }
             if (kPair) { umma_commit_pair(empty_bar(stage)); umma_commit_pair(tfull_bar(as)); }
             else { umma_commit(empty_bar(stage)); umma_commit(tfull_bar(as)); }
@@ -729,11 +731,21 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
           tmem_ld_wait();
           const int r = q * 32 + lane;
           uint8_t* trow = st_ptr + r * 128;
+          const bool th = p.f16_ab != 0;   // T takes the operands' 16-bit format (bf16 forward, IEEE half in the fine-tune backward pass)
+          uint16_t* tg = (p.lora_t_out != nullptr && n_blk == 0 && m < p.M)
+                             ? static_cast<uint16_t*>(p.lora_t_out) + static_cast<long long>(m) * kLoraN + half * 32 : nullptr;
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            *reinterpret_cast<uint4*>(trow + (((half * 4 + u) ^ (r & 7)) << 4)) =
-                make_uint4(pack_bf16(__uint_as_float(tv[8 * u]), __uint_as_float(tv[8 * u + 1])), pack_bf16(__uint_as_float(tv[8 * u + 2]), __uint_as_float(tv[8 * u + 3])),
-                           pack_bf16(__uint_as_float(tv[8 * u + 4]), __uint_as_float(tv[8 * u + 5])), pack_bf16(__uint_as_float(tv[8 * u + 6]), __uint_as_float(tv[8 * u + 7])));
+          for (int u = 0; u < 4; ++u) {
+            uint4 pk = make_uint4(pack16(__uint_as_float(tv[8 * u]), __uint_as_float(tv[8 * u + 1]), th), pack16(__uint_as_float(tv[8 * u + 2]), __uint_as_float(tv[8 * u + 3]), th),
+                                  pack16(__uint_as_float(tv[8 * u + 4]), __uint_as_float(tv[8 * u + 5]), th), pack16(__uint_as_float(tv[8 * u + 6]), __uint_as_float(tv[8 * u + 7]), th));
+            if (half * 32 + u * 8 >= p.lora_n) pk = make_uint4(0u, 0u, 0u, 0u);   // accumulator columns the skinny MMA never wrote
+            *reinterpret_cast<uint4*>(trow + (((half * 4 + u) ^ (r & 7)) << 4)) = pk;
+            if (tg != nullptr) reinterpret_cast<uint4*>(tg)[u] = pk;
+          }
+        } else if (p.lora_t_out != nullptr && n_blk == 0 && m < p.M) {   // unused columns of the saved copy: zeros
+          uint4* tg = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.lora_t_out) + static_cast<long long>(m) * kLoraN + half * 32);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) tg[u] = make_uint4(0u, 0u, 0u, 0u);
         }
         fence_proxy_async_smem();   // the MMA (async proxy) reads what this thread just wrote (generic proxy)
         tcgen05_fence_before();

@@ -696,8 +696,8 @@ int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
   MRISR_REQUIRE(g->act >= 0 && g->act <= 3, "gemm: bad act");
   const bool lora = g->lora_a != nullptr;   // LoRA down-projection fused into this launch (see gemm_tcgen05.cuh, kLora)
   if (lora) {
-    MRISR_REQUIRE(g->taps == 1 && g->k2 == 0 && g->N % 160 == 0 && !(g->f16_flags & MRISR_F16_AB) && g->act != MRISR_ACT_GEGLU && aligned16(g->lora_a),
-                  "gemm(lora_a): needs taps == 1, k2 == 0, bf16 operands, N %% 160 == 0 (w is [N, k1 + 64]: the (s B) columns appended)");
+    MRISR_REQUIRE(g->taps == 1 && g->k2 == 0 && g->N % 160 == 0 && g->act != MRISR_ACT_GEGLU && aligned16(g->lora_a) && (!g->lora_t_out || aligned16(g->lora_t_out)),
+                  "gemm(lora_a): needs taps == 1, k2 == 0, N %% 160 == 0 (w is [N, k1 + 64]: the (s B) columns appended)");
     if (!use_pair_kernel()) return fail(MRISR_E_UNSUPPORTED, "gemm(lora_a): needs the CTA-pair kernel");
     MRISR_REQUIRE(g->lora_n == 0 || (g->lora_n % 16 == 0 && g->lora_n >= 16 && g->lora_n <= 64), "gemm(lora_a): lora_n must be 16, 32, 48 or 64 (0 = 64)");
   }
@@ -805,6 +805,7 @@ int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
     if (int e = encode_map(&maps.b2, g->lora_a, 2, dims, str, box)) return e;
   }
   p.lora_n = lora ? (g->lora_n ? g->lora_n : 64) : 64;
+  p.lora_t_out = lora ? g->lora_t_out : nullptr;
   p.gn_part = nullptr; p.ld_part = 0; p.part_phase_stride = 0;
 
   // Residuals of activation-free GEMMs become extra A operands against the identity tile (see gemm_tcgen05.cuh): the

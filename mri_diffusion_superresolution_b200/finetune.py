@@ -244,7 +244,15 @@ class LoRAFineTuner:
         return out
 
     # ---- forward (activations kept) ---------------------------------------------------------------------------------
+    def _lora_rows(self, g: _Group) -> int:
+        return min(64, -(-(self.cfg.lora_rank * len(g.keys)) // 16) * 16)
+
     def _lora_fwd(self, x: Tensor, g: _Group, **kw) -> Tuple[Tensor, Tensor]:
+        """y = x W^T + bf16(x A^T) (s B)^T and t = bf16(x A^T) (kept for the weight gradient).  Widths that tile by 160: ONE launch
+        (the down-projection is a second accumulator of the GEMM, which also writes t out); otherwise two GEMMs."""
+        if g.w_fwd.shape[0] % 160 == 0:
+            t = torch.empty((x.shape[0], LORA_PAD), device=self.dev, dtype=x.dtype)
+            return ops.gemm(x, g.w_fwd, lora_a=g.a_fwd, lora_n=self._lora_rows(g), lora_t_out=t, **kw), t
         t = ops.gemm(x, g.a_fwd)
         return ops.gemm(x, g.w_fwd, a2=t, **kw), t
 
@@ -313,6 +321,13 @@ class LoRAFineTuner:
     def _lora_bwd(self, g: _Group, dy: Tensor, x: Tensor, t: Tensor, need_dx: bool = True) -> Optional[Tensor]:
         """y = [x | t] [W | sB]^T with t = x A^T.  dx = [dy | u] [W^T | A^T]^T, u = dy (sB); accumulates nothing: the weight
         gradients GA = u^T x and GB = t^T dy overwrite this group's buffers (one use per step)."""
+        if need_dx and g.wd_ext.shape[0] % 160 == 0:
+            # the same fused launch, transposed: dx = dy W + half(dy (s B)) A with u = half(dy (s B)) written out for the weight gradient
+            u = torch.empty((dy.shape[0], LORA_PAD), device=self.dev, dtype=F16)
+            dx = ops.gemm(dy, g.wd_ext, lora_a=g.sbt, lora_n=self._lora_rows(g), lora_t_out=u, out_dtype=F16)
+            ops.xty64(u, x, g.ga)
+            ops.xty64(t, dy, g.gb)
+            return dx
         u = ops.gemm(dy, g.sbt, out_dtype=F16)                                    # [M, 64]
         ops.xty64(u, x, g.ga)
         ops.xty64(t, dy, g.gb)

@@ -80,7 +80,7 @@ def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[T
          res1: Optional[Tensor] = None, res2: Optional[Tensor] = None, n_store: Optional[int] = None,
          out_fp32: bool = False, conv: bool = False, stride: int = 1, out: Optional[Tensor] = None,
          pad_mode: int = 0, out_dtype=None, _dbg: int = 0, up2x: bool = False, gn_stats: bool = False,
-         lora_a: Optional[Tensor] = None, lora_n: int = 64) -> Tensor:
+         lora_a: Optional[Tensor] = None, lora_n: int = 64, lora_t_out: Optional[Tensor] = None) -> Tensor:
     """``act(concat_K(a1, a2) @ w.T + bias + rowvec[batch]) + res1 + res2`` on the tcgen05 kernel.
 
     16-bit tensors are bf16 by default; ``a1`` / ``a2`` / ``w`` may (all three) be float16, ``res1`` / ``res2`` may each be
@@ -136,9 +136,11 @@ def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[T
         raise ValueError("gemm: up2x is a conv mode")
     kext = 0
     if lora_a is not None:
-        _cuda(lora_a, "gemm.lora_a", torch.bfloat16)
+        _cuda(lora_a, "gemm.lora_a", a1.dtype)
         if conv or a2 is not None or tuple(lora_a.shape) != (64, k1) or not lora_a.is_contiguous():
             raise ValueError("gemm(lora_a): a plain GEMM with lora_a [64, k1] and w [N, k1 + 64]")
+        if lora_t_out is not None and (lora_t_out.dtype != a1.dtype or tuple(lora_t_out.shape) != (a1.shape[0], 64) or not lora_t_out.is_contiguous()):
+            raise ValueError("gemm(lora_t_out): a contiguous [M, 64] buffer in the operands' format")
         kext = 64
     if w.dim() != 2 or not w.is_contiguous() or w.shape[1] != taps * (k1 + k2) + kext or (up2x and w.shape[0] % 4):
         raise ValueError(f"gemm: weight must be contiguous [N, {taps * (k1 + k2)}], got {tuple(w.shape)}")
@@ -188,6 +190,7 @@ def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[T
     g.f16_flags = f16
     g.lora_a = _ptr(lora_a)
     g.lora_n = int(lora_n) if lora_a is not None else 0
+    g.lora_t_out = _ptr(lora_t_out) if lora_a is not None else None
     part = None
     if gn_stats and not _NO_GN_STATS:
         if M % 128 or out_fp32 or n_store != N:

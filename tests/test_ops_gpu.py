@@ -593,3 +593,23 @@ def test_gemm_lora_fused(ops, M, N, K, res):
     lora_part = torch.cat([(xf @ a.t()) @ b.t() for a, b in zip(As, Bs)], 1)
     assert lora_part.norm() > 0.05 * ref.norm()             # the LoRA term matters here
     assert torch.equal(fused, ops.gemm(x, w_ext, lora_a=a_stack, lora_n=16 * nproj, bias=bias, res1=r, out_dtype=torch.float16))
+
+
+@pytest.mark.parametrize("f16", [False, True])
+def test_gemm_lora_fused_saves_t_and_takes_f16(ops, f16):
+    """The fused launch in the fine-tune step's two uses: bf16 forward (t = x A^T kept) and IEEE-half backward (u = dy (s B) kept)."""
+    M, N, K = 4096 + 40, 640, 320
+    dt = torch.float16 if f16 else torch.bfloat16
+    mk = _h16 if f16 else _bf
+    x = mk((M, K), 140)
+    a_stack = torch.zeros((64, K), dtype=dt, device="cuda")
+    a_stack[:16] = mk((16, K), 141, 1.0 / math.sqrt(K))
+    w_ext = torch.zeros((N, K + 64), dtype=dt, device="cuda")
+    w_ext[:, :K] = mk((N, K), 142, 1.0 / math.sqrt(K))
+    w_ext[:, K:K + 16] = mk((N, 16), 143, 0.2)
+    t = torch.full((M, 64), 7.0, dtype=dt, device="cuda")
+    out = ops.gemm(x, w_ext, lora_a=a_stack, lora_n=16, lora_t_out=t, out_dtype=torch.float16)
+    t_ref = (x.float() @ a_stack.float().t())
+    assert _rel(t[:, :16], t_ref[:, :16]) < 4e-3 and float(t[:, 16:].float().abs().max()) == 0.0
+    ref = x.float() @ w_ext[:, :K].float().t() + t.float() @ w_ext[:, K:].float().t()
+    assert _rel(out, ref) < 4e-3
