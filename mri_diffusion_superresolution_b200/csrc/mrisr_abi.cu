@@ -1225,7 +1225,7 @@ int mrisr_mse_grad(const float* pred, const float* target, int B, int C, int HW,
   return 0;
 }
 
-constexpr int kXtyRowsPerSplit = 64;   // short per-CTA loops: the reduction is latency-, not bandwidth-bound (256 rows: 35 us per call)
+constexpr int kXtyRowsPerSplit = 256;   // 4 staged 64-row tiles per CTA (tensor-core partial products), msplit = M / 256
 int64_t mrisr_xty64_workspace_floats(int M, int Q) {
   const int64_t msplit = (M + kXtyRowsPerSplit - 1) / kXtyRowsPerSplit;
   return msplit * 64 * static_cast<int64_t>(Q);
@@ -1236,7 +1236,8 @@ int mrisr_xty64(const void* X, int64_t ldx, int x_f16, const void* Y, int64_t ld
   MRISR_REQUIRE(X && Y && workspace && out && M > 0 && Q > 0 && ldx >= 64 && ldy >= Q, "xty64: bad argument");
   const int msplit = (M + kXtyRowsPerSplit - 1) / kXtyRowsPerSplit;
   cudaStream_t st = as_stream(stream);
-  launch_k(mrisr::xty64_partial_kernel, dim3((Q + 63) / 64, msplit), dim3(256), 0, st, X, static_cast<long long>(ldx), x_f16, Y,
+  MRISR_REQUIRE(ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0, "xty64: X must be 16-byte aligned with a row pitch that is a multiple of 8");
+  launch_k(mrisr::xty64_partial_kernel, dim3((Q + 63) / 64, msplit), dim3(128), 0, st, X, static_cast<long long>(ldx), x_f16, Y,
            static_cast<long long>(ldy), y_f16, M, Q, kXtyRowsPerSplit, workspace);
   MRISR_CHECK_CUDA(cudaGetLastError());
   launch_k(mrisr::xty64_reduce_kernel, dim3(grid_for(64LL * Q, 256, 4)), dim3(256), 0, st, static_cast<const float*>(workspace), msplit, Q, scale, out);

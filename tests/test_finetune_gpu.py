@@ -106,8 +106,10 @@ def test_xty64_and_spatial_helpers(ops):
     x, y = _r((M, 64), 30).to(torch.float16), _r((M, Q + 64), 31).to(torch.bfloat16)
     out = torch.empty((64, Q), device="cuda", dtype=torch.float32)
     ops.xty64(x.cuda(), y.cuda()[:, :Q], out, scale=0.25)
-    ref = 0.25 * x.float().t() @ y.float()[:, :Q]
+    # tensor-core reduction with bf16 operands: an IEEE-half input is rounded to bf16 once, the accumulation is fp32
+    ref = 0.25 * x.bfloat16().float().t() @ y.float()[:, :Q]
     assert _rel(out, ref) < 1e-5
+    assert _rel(out, 0.25 * x.float().t() @ y.float()[:, :Q]) < 2e-3
     again = torch.empty_like(out)
     ops.xty64(x.cuda(), y.cuda()[:, :Q], again, scale=0.25)
     assert torch.equal(out, again)                                  # fixed-order reduction: bit-reproducible
