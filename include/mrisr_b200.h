@@ -265,10 +265,13 @@ int mrisr_mse_grad(const float* pred, const float* target, int B, int C, int HW,
 int64_t mrisr_xty64_workspace_floats(int M, int Q);
 int mrisr_xty64(const void* X, int64_t ldx, int x_f16, const void* Y, int64_t ldy, int y_f16, int M, int Q, float scale, float* workspace,
                 float* out, void* stream);
-/* Backward of mrisr_attention (flash-style, P is recomputed): q/k/v/o bf16 as in the forward call, d_o / dq / dk / dv half;
- * stats_ws >= 2*batch*heads*nq floats (row log-sum-exp and rowsum(dO*O), recomputed here). d in {8,16,40,80,160}. */
+/* Backward of mrisr_attention (flash-style, P is recomputed): q/k/v/o bf16 as in the forward call, dq / dk / dv half, d_o bf16
+ * (d_o_f16 = 0: every streamed tile is a cp.async copy) or half (rounded to bf16 on load);
+ * stats_ws >= mrisr_attention_backward_workspace(...) floats: row log-sum-exp and rowsum(dO*O) (recomputed here) and, when the
+ * key count is small (cross attention), the fp32 partial dK / dV of the query-range splits.  d in {8,16,40,80,160}. */
+int64_t mrisr_attention_backward_workspace(int batch, int nq, int nk, int heads, int d);
 int mrisr_attention_backward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o, int64_t ldo,
-                             const void* d_o, int64_t lddo, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                             const void* d_o, int64_t lddo, int d_o_f16, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
                              float* stats_ws, int batch, int nq, int nk, int heads, int d, void* stream);
 /* One trainable tensor [rows, cols]: fp32 master p and AdamW moments m, v (dense); its gradient as a strided window
  * grad(i,j) = g[i*g_sr + j*g_sc] * g_scale of an mrisr_xty64 result; up to two packed 16-bit destinations that receive

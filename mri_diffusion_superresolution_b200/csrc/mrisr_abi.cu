@@ -358,6 +358,17 @@ int launch_layernorm_group(const void* x, int64_t ldx, const float* g, const flo
 
 constexpr int kGnMaxSlabs = 64;
 
+// Query-range splits of the dK / dV sweep: enough CTAs for ~4 per SM when there are few key tiles, at least two query tiles each.
+void attention_backward_split(int batch, int nq, int nk, int heads, int* nsplit, int* qtiles_per_split) {
+  const int ktiles = (nk + 63) / 64, qtiles = (nq + 63) / 64;
+  const long long ctas = static_cast<long long>(ktiles) * heads * batch;
+  int want = static_cast<int>(std::min<long long>(std::max(qtiles / 2, 1), (4 * 148 + ctas - 1) / ctas));
+  const int per = (qtiles + want - 1) / want;
+  *qtiles_per_split = per;
+  *nsplit = (qtiles + per - 1) / per;
+}
+long long attention_backward_dp(int d) { return (d + 15) / 16 * 16; }
+
 template <int D>
 int launch_attention_backward(const mrisr::AttnBwdArgs& a, cudaStream_t st) {
   using Cfg = mrisr::AttnBwdCfg<D>;
@@ -371,7 +382,7 @@ int launch_attention_backward(const mrisr::AttnBwdArgs& a, cudaStream_t st) {
   }
   launch_k(mrisr::attention_bwd_dq_kernel<D>, dim3((a.nq + 63) / 64, a.heads, a.batch), dim3(mrisr::kAbThreads), Cfg::kSmemBytes, st, a);
   MRISR_CHECK_CUDA(cudaGetLastError());
-  const dim3 gk((a.nk + 63) / 64, a.heads, a.batch);
+  const dim3 gk((a.nk + 63) / 64 * a.nsplit, a.heads, a.batch);
   if (D > 80) {   // the dK and dV accumulators do not fit the register file together: two sweeps
     launch_k(mrisr::attention_bwd_dkdv_kernel<D, 1>, gk, dim3(mrisr::kAbThreads), Cfg::kSmemBytes, st, a);
     MRISR_CHECK_CUDA(cudaGetLastError());
@@ -380,6 +391,11 @@ int launch_attention_backward(const mrisr::AttnBwdArgs& a, cudaStream_t st) {
     launch_k(mrisr::attention_bwd_dkdv_kernel<D, 0>, gk, dim3(mrisr::kAbThreads), Cfg::kSmemBytes, st, a);
   }
   MRISR_CHECK_CUDA(cudaGetLastError());
+  if (a.nsplit > 1) {
+    const long long total = static_cast<long long>(a.batch) * a.nk * a.heads * (D / 2);
+    launch_k(mrisr::attention_bwd_reduce_kernel<D>, dim3(static_cast<unsigned>(std::min<long long>((total + 255) / 256, 148 * 8))), dim3(256), 0, st, a);
+    MRISR_CHECK_CUDA(cudaGetLastError());
+  }
   return 0;
 }
 
@@ -1245,8 +1261,17 @@ int mrisr_xty64(const void* X, int64_t ldx, int x_f16, const void* Y, int64_t ld
   return 0;
 }
 
+int64_t mrisr_attention_backward_workspace(int batch, int nq, int nk, int heads, int d) {
+  if (batch <= 0 || nq <= 0 || nk <= 0 || heads <= 0 || d <= 0) return 0;
+  int nsplit = 1, per = 1;
+  attention_backward_split(batch, nq, nk, heads, &nsplit, &per);
+  long long n = 2ll * batch * heads * nq;
+  if (nsplit > 1) n += 2ll * nsplit * batch * heads * ((nk + 63) / 64) * 64 * attention_backward_dp(d);
+  return n;
+}
+
 int mrisr_attention_backward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o, int64_t ldo,
-                             const void* d_o, int64_t lddo, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                             const void* d_o, int64_t lddo, int d_o_f16, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
                              float* stats_ws, int batch, int nq, int nk, int heads, int d, void* stream) {
   MRISR_ONE_DEVICE();
   MRISR_REQUIRE(q && k && v && o && d_o && dq && dk && dv && stats_ws, "attention_backward: null pointer");
@@ -1259,10 +1284,12 @@ int mrisr_attention_backward(const void* q, int64_t ldq, const void* k, int64_t 
   a.q = static_cast<const __nv_bfloat16*>(q); a.k = static_cast<const __nv_bfloat16*>(k); a.v = static_cast<const __nv_bfloat16*>(v);
   a.o = static_cast<const __nv_bfloat16*>(o);
   a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo;
-  a.d_o = static_cast<const __half*>(d_o); a.lddo = lddo;
+  a.d_o = d_o; a.lddo = lddo; a.d_o_f16 = d_o_f16 != 0;
   a.dq = static_cast<__half*>(dq); a.dk = static_cast<__half*>(dk); a.dv = static_cast<__half*>(dv);
   a.lddq = lddq; a.lddk = lddk; a.lddv = lddv;
   a.lse = stats_ws; a.dsum = stats_ws + static_cast<long long>(batch) * heads * nq;
+  a.part = stats_ws + 2ll * batch * heads * nq;   // (8-byte aligned: an even number of floats precedes it)
+  attention_backward_split(batch, nq, nk, heads, &a.nsplit, &a.qtiles_per_split);
   a.nq = nq; a.nk = nk; a.heads = heads; a.batch = batch;
   a.scale = static_cast<float>(1.0 / std::sqrt(static_cast<double>(d)));
   a.scale_log2 = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(d)));

@@ -583,13 +583,18 @@ namespace mrisr {
 struct AttnBwdArgs {
   const __nv_bfloat16 *q, *k, *v, *o;
   long long ldq, ldk, ldv, ldo;
-  const __half* d_o; long long lddo;
+  const void* d_o; long long lddo;   // bf16 (streamed with cp.async) or IEEE half (rounded to bf16 on load), see d_o_f16
+  int d_o_f16;
   __half *dq, *dk, *dv;
   long long lddq, lddk, lddv;
   float* lse;    // [batch * heads * nq]  (written by the dq kernel, read by the dk/dv kernel)
   float* dsum;   // [batch * heads * nq]
   int nq, nk, heads, batch;
   float scale_log2, scale;
+  // dK / dV with few key tiles (cross attention: 77 keys = 2 tiles) split the query range over `nsplit` CTAs per key tile, each
+  // writing fp32 partial sums [split][batch][head][dk | dv][key tiles * 64][DP]; attention_bwd_reduce_kernel adds them in split order.
+  float* part;
+  int nsplit, qtiles_per_split;
 };
 
 template <int D>
@@ -597,7 +602,10 @@ struct AttnBwdCfg {
   static constexpr int DP = (D + 15) / 16 * 16;   // head dim padded to the MMA K granularity (zero columns)
   static constexpr int LDS = DP + 8;              // smem row pitch (elements): conflict-free ldmatrix
   static constexpr int kTileElems = 64 * LDS;
-  static constexpr int kSmemBytes = 4 * kTileElems * 2 + 2 * 64 * 4;
+  // the streamed operand pair (K, V in the dQ kernel; Q, dO in the dK/dV kernel) is double-buffered with cp.async up to head dim 80
+  // (the first version loaded every tile synchronously: ncu showed 5 of 6 issue slots stalled on the global loads at 3-4 CTAs / SM)
+  static constexpr int kBufs = D <= 80 ? 2 : 1;
+  static constexpr int kSmemBytes = (2 + 2 * kBufs) * kTileElems * 2 + 2 * kBufs * 64 * 4;
 };
 constexpr int kAbThreads = 128;
 __device__ __forceinline__ float ab_ex2(float x) {   // MUFU.EX2: exp2f() is a ~10-instruction sequence
@@ -620,6 +628,30 @@ __device__ __forceinline__ void ab_load_tile(__nv_bfloat16* s, const void* g, lo
                          pack_bf16(f16_lo(val.z), f16_hi(val.z)), pack_bf16(f16_lo(val.w), f16_hi(val.w)));
     }
     *reinterpret_cast<uint4*>(s + r * Cfg::LDS + v * 8) = val;
+  }
+}
+
+__device__ __forceinline__ void ab_cp_async16(uint32_t dst, const void* src, bool valid) {   // zero-fills when !valid
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void ab_cp_async4(uint32_t dst, const void* src, bool valid) {
+  const int n = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void ab_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void ab_cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// bf16 tile, asynchronous: rows past `nrows` and the pad columns [D, DP) arrive as zeros
+template <int D>
+__device__ __forceinline__ void ab_load_tile_async(__nv_bfloat16* s, const void* g, long long ld, int row0, int nrows, int col0) {
+  using Cfg = AttnBwdCfg<D>;
+  constexpr int kVec = Cfg::DP / 8;
+  const uint32_t s0 = smem_u32(s);
+  for (int e = threadIdx.x; e < 64 * kVec; e += kAbThreads) {
+    const int r = e / kVec, v = e - r * kVec;
+    const bool valid = row0 + r < nrows && v * 8 < D;
+    const uint16_t* src = static_cast<const uint16_t*>(g) + (valid ? static_cast<long long>(row0 + r) * ld + col0 + v * 8 : 0);
+    ab_cp_async16(s0 + (r * Cfg::LDS + v * 8) * 2, src, valid);
   }
 }
 
@@ -673,21 +705,28 @@ __global__ void __launch_bounds__(kAbThreads) attention_bwd_dq_kernel(AttnBwdArg
   grid_dep_launch();
   grid_dep_wait();   // launched with programmatic dependent launch: inputs are the predecessor's output
   using Cfg = AttnBwdCfg<D>;
+  constexpr int NB = Cfg::kBufs;
   extern __shared__ __align__(16) uint8_t ab_raw[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(ab_raw);
   __nv_bfloat16* sdO = sQ + Cfg::kTileElems;
-  __nv_bfloat16* sK = sdO + Cfg::kTileElems;
-  __nv_bfloat16* sV = sK + Cfg::kTileElems;
-  float* sDs = reinterpret_cast<float*>(sV + Cfg::kTileElems);
+  __nv_bfloat16* sK = sdO + Cfg::kTileElems;            // [NB] tiles
+  __nv_bfloat16* sV = sK + NB * Cfg::kTileElems;        // [NB] tiles
+  float* sDs = reinterpret_cast<float*>(sV + NB * Cfg::kTileElems);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int q0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
   const long long qrow0 = static_cast<long long>(b) * a.nq, krow0 = static_cast<long long>(b) * a.nk;
   const long long stat0 = (static_cast<long long>(b) * a.heads + h) * a.nq;
+  const __nv_bfloat16* kbase = a.k + krow0 * a.ldk;
+  const __nv_bfloat16* vbase = a.v + krow0 * a.ldv;
+  const int ktiles = (a.nk + 63) / 64;
+  ab_load_tile_async<D>(sK, kbase, a.ldk, 0, a.nk, h * D);   // first key tile of pass 1, in flight under the Q / dO loads
+  ab_cp_commit();
   ab_load_tile<D, false>(sQ, a.q + qrow0 * a.ldq, a.ldq, q0, a.nq, h * D);
-  ab_load_tile<D, true>(sdO, a.d_o + qrow0 * a.lddo, a.lddo, q0, a.nq, h * D);
+  if (a.d_o_f16) ab_load_tile<D, true>(sdO, static_cast<const uint16_t*>(a.d_o) + qrow0 * a.lddo, a.lddo, q0, a.nq, h * D);
+  else ab_load_tile<D, false>(sdO, static_cast<const uint16_t*>(a.d_o) + qrow0 * a.lddo, a.lddo, q0, a.nq, h * D);
   __syncthreads();
-  {  // D_i = sum_d dO[i, d] * O[i, d] (the bf16-rounded dO the MMAs below see)
+  {  // D_i = sum_d dO[i, d] * O[i, d] (the bf16 dO the MMAs below see)
     const int r = threadIdx.x >> 1, part = threadIdx.x & 1;
     float acc = 0.f;
     if (q0 + r < a.nq) {
@@ -703,13 +742,21 @@ __global__ void __launch_bounds__(kAbThreads) attention_bwd_dq_kernel(AttnBwdArg
   const int r0 = warp * 16;
   // ---- pass 1: log2-domain log-sum-exp of the two rows this thread owns (g, g + 8)
   float mx[2] = {-INFINITY, -INFINITY}, sm[2] = {0.f, 0.f};
-  const int ktiles = (a.nk + 63) / 64;
   for (int kt = 0; kt < ktiles; ++kt) {
-    __syncthreads();
-    ab_load_tile<D, false>(sK, a.k + krow0 * a.ldk, a.ldk, kt * 64, a.nk, h * D);
-    __syncthreads();
+    ab_cp_wait_all();
+    __syncthreads();   // tile kt has landed; every warp is past tile kt - 1, so the other buffer is free
+    const __nv_bfloat16* cK = sK + (kt % NB) * Cfg::kTileElems;
+    if (NB == 2) {   // prefetch: the next key tile, or (last iteration) the first K / V pair of pass 2
+      if (kt + 1 < ktiles) {
+        ab_load_tile_async<D>(sK + ((kt + 1) % NB) * Cfg::kTileElems, kbase, a.ldk, (kt + 1) * 64, a.nk, h * D);
+      } else {
+        ab_load_tile_async<D>(sK + (ktiles % NB) * Cfg::kTileElems, kbase, a.ldk, 0, a.nk, h * D);
+        ab_load_tile_async<D>(sV + (ktiles % NB) * Cfg::kTileElems, vbase, a.ldv, 0, a.nk, h * D);
+      }
+      ab_cp_commit();
+    }
     float s[8][4];
-    ab_mma_nt<D>(s, sQ, r0, sK, lane);
+    ab_mma_nt<D>(s, sQ, r0, cK, lane);
     float tm[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -732,6 +779,16 @@ __global__ void __launch_bounds__(kAbThreads) attention_bwd_dq_kernel(AttnBwdArg
       sm[rrow] = sm[rrow] * ab_ex2(mx[rrow] - nm) + add;
       mx[rrow] = nm;
     }
+    if (NB == 1) {
+      __syncthreads();
+      if (kt + 1 < ktiles) {
+        ab_load_tile_async<D>(sK, kbase, a.ldk, (kt + 1) * 64, a.nk, h * D);
+      } else {
+        ab_load_tile_async<D>(sK, kbase, a.ldk, 0, a.nk, h * D);
+        ab_load_tile_async<D>(sV, vbase, a.ldv, 0, a.nk, h * D);
+      }
+      ab_cp_commit();
+    }
   }
   float lse[2], dsv[2];
 #pragma unroll
@@ -741,20 +798,26 @@ __global__ void __launch_bounds__(kAbThreads) attention_bwd_dq_kernel(AttnBwdArg
     const int qi = q0 + r0 + g + 8 * rrow;
     if (t == 0 && qi < a.nq) a.lse[stat0 + qi] = lse[rrow];
   }
-  // ---- pass 2: dQ
+  // ---- pass 2: dQ.  Tile i of this pass lives in buffer (ktiles + i) % NB (the pass-1 loop left tile 0 in flight there).
   float dq[Cfg::DP / 8][4];
 #pragma unroll
   for (int j = 0; j < Cfg::DP / 8; ++j)
 #pragma unroll
     for (int i = 0; i < 4; ++i) dq[j][i] = 0.f;
   for (int kt = 0; kt < ktiles; ++kt) {
+    ab_cp_wait_all();
     __syncthreads();
-    ab_load_tile<D, false>(sK, a.k + krow0 * a.ldk, a.ldk, kt * 64, a.nk, h * D);
-    ab_load_tile<D, false>(sV, a.v + krow0 * a.ldv, a.ldv, kt * 64, a.nk, h * D);
-    __syncthreads();
+    const int cur = (ktiles + kt) % NB;
+    const __nv_bfloat16* cK = sK + cur * Cfg::kTileElems;
+    const __nv_bfloat16* cV = sV + cur * Cfg::kTileElems;
+    if (NB == 2 && kt + 1 < ktiles) {
+      ab_load_tile_async<D>(sK + (cur ^ 1) * Cfg::kTileElems, kbase, a.ldk, (kt + 1) * 64, a.nk, h * D);
+      ab_load_tile_async<D>(sV + (cur ^ 1) * Cfg::kTileElems, vbase, a.ldv, (kt + 1) * 64, a.nk, h * D);
+      ab_cp_commit();
+    }
     float s[8][4], dp[8][4];
-    ab_mma_nt<D>(s, sQ, r0, sK, lane);
-    ab_mma_nt<D>(dp, sdO, r0, sV, lane);
+    ab_mma_nt<D>(s, sQ, r0, cK, lane);
+    ab_mma_nt<D>(dp, sdO, r0, cV, lane);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
 #pragma unroll
@@ -763,7 +826,13 @@ __global__ void __launch_bounds__(kAbThreads) attention_bwd_dq_kernel(AttnBwdArg
         const float p = col < a.nk ? ab_ex2(s[j][i] * a.scale_log2 - lse[i >> 1]) : 0.f;
         s[j][i] = p * (dp[j][i] - dsv[i >> 1]);     // dS
       }
-    ab_mma_pn<D>(dq, s, sK, lane);
+    ab_mma_pn<D>(dq, s, cK, lane);
+    if (NB == 1 && kt + 1 < ktiles) {
+      __syncthreads();
+      ab_load_tile_async<D>(sK, kbase, a.ldk, (kt + 1) * 64, a.nk, h * D);
+      ab_load_tile_async<D>(sV, vbase, a.ldv, (kt + 1) * 64, a.nk, h * D);
+      ab_cp_commit();
+    }
   }
 #pragma unroll
   for (int rrow = 0; rrow < 2; ++rrow) {
@@ -785,15 +854,18 @@ __global__ void __launch_bounds__(kAbThreads) attention_bwd_dkdv_kernel(AttnBwdA
   grid_dep_wait();   // launched with programmatic dependent launch: inputs are the predecessor's output
   using Cfg = AttnBwdCfg<D>;
   extern __shared__ __align__(16) uint8_t ab_raw[];
-  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(ab_raw);
-  __nv_bfloat16* sdO = sQ + Cfg::kTileElems;
-  __nv_bfloat16* sK = sdO + Cfg::kTileElems;
+  constexpr int NB = Cfg::kBufs;
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(ab_raw);
   __nv_bfloat16* sV = sK + Cfg::kTileElems;
-  float* sL = reinterpret_cast<float*>(sV + Cfg::kTileElems);
-  float* sDs = sL + 64;
+  __nv_bfloat16* sQ = sV + Cfg::kTileElems;             // [NB] tiles
+  __nv_bfloat16* sdO = sQ + NB * Cfg::kTileElems;       // [NB] tiles
+  float* sL = reinterpret_cast<float*>(sdO + NB * Cfg::kTileElems);   // [NB][64]
+  float* sDs = sL + NB * 64;                                          // [NB][64]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int k0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+  const int ktiles = (a.nk + 63) / 64;
+  const int split = blockIdx.x / ktiles;
+  const int k0 = (blockIdx.x - split * ktiles) * 64, h = blockIdx.y, b = blockIdx.z;
   const long long qrow0 = static_cast<long long>(b) * a.nq, krow0 = static_cast<long long>(b) * a.nk;
   const long long stat0 = (static_cast<long long>(b) * a.heads + h) * a.nq;
   ab_load_tile<D, false>(sK, a.k + krow0 * a.ldk, a.ldk, k0, a.nk, h * D);
@@ -809,38 +881,74 @@ __global__ void __launch_bounds__(kAbThreads) attention_bwd_dkdv_kernel(AttnBwdA
 #pragma unroll
     for (int i = 0; i < 4; ++i) dv[j][i] = 0.f;
   const int qtiles = (a.nq + 63) / 64;
-  for (int qt = 0; qt < qtiles; ++qt) {
-    __syncthreads();
-    ab_load_tile<D, false>(sQ, a.q + qrow0 * a.ldq, a.ldq, qt * 64, a.nq, h * D);
-    ab_load_tile<D, true>(sdO, a.d_o + qrow0 * a.lddo, a.lddo, qt * 64, a.nq, h * D);
+  const int qt_begin = split * a.qtiles_per_split, qt_end = min(qtiles, qt_begin + a.qtiles_per_split);
+  const __nv_bfloat16* qbase = a.q + qrow0 * a.ldq;
+  const uint16_t* dobase = static_cast<const uint16_t*>(a.d_o) + qrow0 * a.lddo;
+  // one query tile (Q, dO, the rows' log-sum-exp and D) into buffer `buf`; asynchronous except an IEEE-half dO (converted on load)
+  auto load_q_tile = [&](int qt, int buf) {
+    ab_load_tile_async<D>(sQ + buf * Cfg::kTileElems, qbase, a.ldq, qt * 64, a.nq, h * D);
+    if (a.d_o_f16) ab_load_tile<D, true>(sdO + buf * Cfg::kTileElems, dobase, a.lddo, qt * 64, a.nq, h * D);
+    else ab_load_tile_async<D>(sdO + buf * Cfg::kTileElems, dobase, a.lddo, qt * 64, a.nq, h * D);
     if (threadIdx.x < 64) {
       const int qi = qt * 64 + threadIdx.x;
-      sL[threadIdx.x] = qi < a.nq ? a.lse[stat0 + qi] : 0.f;
-      sDs[threadIdx.x] = qi < a.nq ? a.dsum[stat0 + qi] : 0.f;
+      const bool ok = qi < a.nq;
+      ab_cp_async4(smem_u32(sL + buf * 64 + threadIdx.x), a.lse + (ok ? stat0 + qi : 0), ok);
+      ab_cp_async4(smem_u32(sDs + buf * 64 + threadIdx.x), a.dsum + (ok ? stat0 + qi : 0), ok);
     }
-    __syncthreads();
+    ab_cp_commit();
+  };
+  if (qt_begin < qt_end) load_q_tile(qt_begin, 0);
+  for (int qt = qt_begin; qt < qt_end; ++qt) {
+    ab_cp_wait_all();
+    __syncthreads();   // tile qt has landed (and K / V on the first trip); every warp is past tile qt - 1
+    const int cur = (qt - qt_begin) % NB;
+    const __nv_bfloat16* cQ = sQ + cur * Cfg::kTileElems;
+    const __nv_bfloat16* cdO = sdO + cur * Cfg::kTileElems;
+    const float* cL = sL + cur * 64;
+    const float* cDs = sDs + cur * 64;
+    if (NB == 2 && qt + 1 < qt_end) load_q_tile(qt + 1, cur ^ 1);
     float s[8][4];
-    ab_mma_nt<D>(s, sK, r0, sQ, lane);            // S^T: rows = keys, cols = queries
+    ab_mma_nt<D>(s, sK, r0, cQ, lane);            // S^T: rows = keys, cols = queries
 #pragma unroll
     for (int j = 0; j < 8; ++j)
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int qc = j * 8 + 2 * t + (i & 1);
-        s[j][i] = (qt * 64 + qc < a.nq) ? ab_ex2(s[j][i] * a.scale_log2 - sL[qc]) : 0.f;   // P^T
+        s[j][i] = (qt * 64 + qc < a.nq) ? ab_ex2(s[j][i] * a.scale_log2 - cL[qc]) : 0.f;   // P^T
       }
-    if constexpr (kMode != 2) ab_mma_pn<D>(dv, s, sdO, lane);
+    if constexpr (kMode != 2) ab_mma_pn<D>(dv, s, cdO, lane);
     if constexpr (kMode != 1) {
       float dp[8][4];
-      ab_mma_nt<D>(dp, sV, r0, sdO, lane);        // dP^T
+      ab_mma_nt<D>(dp, sV, r0, cdO, lane);        // dP^T
 #pragma unroll
       for (int j = 0; j < 8; ++j)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int qc = j * 8 + 2 * t + (i & 1);
-          s[j][i] *= dp[j][i] - sDs[qc];           // dS^T
+          s[j][i] *= dp[j][i] - cDs[qc];           // dS^T
         }
-      ab_mma_pn<D>(dk, s, sQ, lane);
+      ab_mma_pn<D>(dk, s, cQ, lane);
     }
+    if (NB == 1 && qt + 1 < qt_end) {
+      __syncthreads();
+      load_q_tile(qt + 1, 0);
+    }
+  }
+  if (a.nsplit > 1) {   // fp32 partial sums of this query range
+    const long long tile_elems = static_cast<long long>(ktiles) * 64 * Cfg::DP;
+    float* pk = a.part + ((static_cast<long long>(split) * a.batch + b) * a.heads + h) * 2 * tile_elems;
+    float* pv = pk + tile_elems;
+#pragma unroll
+    for (int rrow = 0; rrow < 2; ++rrow) {
+      const long long row = static_cast<long long>(k0 + r0 + g + 8 * rrow) * Cfg::DP;
+#pragma unroll
+      for (int j = 0; j < Cfg::DP / 8; ++j) {
+        const int c = j * 8 + 2 * t;
+        if constexpr (kMode != 1) *reinterpret_cast<float2*>(pk + row + c) = make_float2(dk[j][2 * rrow], dk[j][2 * rrow + 1]);
+        if constexpr (kMode != 2) *reinterpret_cast<float2*>(pv + row + c) = make_float2(dv[j][2 * rrow], dv[j][2 * rrow + 1]);
+      }
+    }
+    return;
   }
 #pragma unroll
   for (int rrow = 0; rrow < 2; ++rrow) {
@@ -855,6 +963,33 @@ __global__ void __launch_bounds__(kAbThreads) attention_bwd_dkdv_kernel(AttnBwdA
       if constexpr (kMode != 2)
         *reinterpret_cast<__half2*>(a.dv + (krow0 + ki) * a.lddv + h * D + c) = __floats2half2_rn(dv[j][2 * rrow], dv[j][2 * rrow + 1]);
     }
+  }
+}
+
+// dK / dV = sum over the query splits, in split order (bit-reproducible); one thread = one (batch, key, head, column pair)
+template <int D>
+__global__ void __launch_bounds__(256) attention_bwd_reduce_kernel(AttnBwdArgs a) {
+  grid_dep_launch();
+  grid_dep_wait();
+  using Cfg = AttnBwdCfg<D>;
+  const int ktiles = (a.nk + 63) / 64;
+  const long long tile_elems = static_cast<long long>(ktiles) * 64 * Cfg::DP;
+  const long long total = static_cast<long long>(a.batch) * a.nk * a.heads * (D / 2);
+  for (long long e = blockIdx.x * 256ll + threadIdx.x; e < total; e += gridDim.x * 256ll) {
+    const int cp = static_cast<int>(e % (D / 2));
+    long long r = e / (D / 2);
+    const int h = static_cast<int>(r % a.heads);
+    r /= a.heads;
+    const int ki = static_cast<int>(r % a.nk), b = static_cast<int>(r / a.nk);
+    float2 sk = make_float2(0.f, 0.f), sv = make_float2(0.f, 0.f);
+    for (int sp = 0; sp < a.nsplit; ++sp) {
+      const float* pk = a.part + ((static_cast<long long>(sp) * a.batch + b) * a.heads + h) * 2 * tile_elems + static_cast<long long>(ki) * Cfg::DP + 2 * cp;
+      const float2 vk = *reinterpret_cast<const float2*>(pk), vv = *reinterpret_cast<const float2*>(pk + tile_elems);
+      sk.x += vk.x; sk.y += vk.y; sv.x += vv.x; sv.y += vv.y;
+    }
+    const long long row = static_cast<long long>(b) * a.nk + ki;
+    *reinterpret_cast<__half2*>(a.dk + row * a.lddk + h * D + 2 * cp) = __floats2half2_rn(sk.x * a.scale, sk.y * a.scale);
+    *reinterpret_cast<__half2*>(a.dv + row * a.lddv + h * D + 2 * cp) = __floats2half2_rn(sv.x, sv.y);
   }
 }
 

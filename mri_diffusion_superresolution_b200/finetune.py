@@ -318,13 +318,13 @@ class LoRAFineTuner:
         out = ops.gemm(h_d, a.w_out, bias=a.b_out, res1=x.view(M, Cc), res2=extra_res, out_dtype=F16).view(B, H, W, Cc)
         return out, (a, x, h_a, y1, t1, qkv, o1, t2, h_b, y2, t3, q2, ehs2, t4, kv, o2, t5, h_c, pre, h_d)
 
-    def _lora_bwd(self, g: _Group, dy: Tensor, x: Tensor, t: Tensor, need_dx: bool = True) -> Optional[Tensor]:
+    def _lora_bwd(self, g: _Group, dy: Tensor, x: Tensor, t: Tensor, need_dx: bool = True, out_dtype=F16) -> Optional[Tensor]:
         """y = [x | t] [W | sB]^T with t = x A^T.  dx = [dy | u] [W^T | A^T]^T, u = dy (sB); accumulates nothing: the weight
         gradients GA = u^T x and GB = t^T dy overwrite this group's buffers (one use per step)."""
         if need_dx and g.wd_ext.shape[0] % 160 == 0:
             # the same fused launch, transposed: dx = dy W + half(dy (s B)) A with u = half(dy (s B)) written out for the weight gradient
             u = torch.empty((dy.shape[0], LORA_PAD), device=self.dev, dtype=F16)
-            dx = ops.gemm(dy, g.wd_ext, lora_a=g.sbt, lora_n=self._lora_rows(g), lora_t_out=u, out_dtype=F16)
+            dx = ops.gemm(dy, g.wd_ext, lora_a=g.sbt, lora_n=self._lora_rows(g), lora_t_out=u, out_dtype=out_dtype)
             ops.xty64(u, x, g.ga)
             ops.xty64(t, dy, g.gb)
             return dx
@@ -333,7 +333,7 @@ class LoRAFineTuner:
         ops.xty64(t, dy, g.gb)
         if not need_dx:
             return None
-        return ops.gemm(dy, g.wd_ext, a2=u, out_dtype=F16)
+        return ops.gemm(dy, g.wd_ext, a2=u, out_dtype=out_dtype)
 
     def _transformer_bwd(self, ctx, dout: Tensor) -> Tensor:
         a, x, h_a, y1, t1, qkv, o1, t2, h_b, y2, t3, q2, ehs2, t4, kv, o2, t5, h_c, pre, h_d = ctx
@@ -349,7 +349,8 @@ class LoRAFineTuner:
         d_y3 = ops.gemm(d_pre, d["wd_ff1"], out_dtype=F16)
         d_hc = ops.layernorm_backward(h_c, d_y3, a.ln3[0], 1e-5, dres=d_hd)
         # cross-attention
-        d_o2 = self._lora_bwd(d["o2"], d_hc, o2, t5)
+        # dO leaves the out-projection dgrad in bf16 (the attention backward's operand format: its tiles are then plain async copies)
+        d_o2 = self._lora_bwd(d["o2"], d_hc, o2, t5, out_dtype=torch.bfloat16)
         d_q2 = torch.empty((M, Cc), device=self.dev, dtype=F16)
         d_kv = torch.empty((kv.shape[0], 2 * Cc), device=self.dev, dtype=F16)
         ops.attention_backward(q2, kv[:, :Cc], kv[:, Cc:], o2, d_o2, B, heads, d_q2, d_kv[:, :Cc], d_kv[:, Cc:])
@@ -357,7 +358,7 @@ class LoRAFineTuner:
         d_y2 = self._lora_bwd(d["q2"], d_q2, y2, t3)
         d_hb = ops.layernorm_backward(h_b, d_y2, a.ln2[0], 1e-5, dres=d_hc)
         # self-attention
-        d_o1 = self._lora_bwd(d["o1"], d_hb, o1, t2)
+        d_o1 = self._lora_bwd(d["o1"], d_hb, o1, t2, out_dtype=torch.bfloat16)
         d_qkv = torch.empty((M, 3 * Cc), device=self.dev, dtype=F16)
         ops.attention_backward(qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:], o1, d_o1, B, heads,
                                d_qkv[:, :Cc], d_qkv[:, Cc:2 * Cc], d_qkv[:, 2 * Cc:])

@@ -634,19 +634,24 @@ def xty64(x64: Tensor, y: Tensor, out: Tensor, scale: float = 1.0) -> Tensor:
 
 def attention_backward(q: Tensor, k: Tensor, v: Tensor, o: Tensor, d_o: Tensor, batch: int, heads: int,
                        dq: Tensor, dk: Tensor, dv: Tensor) -> None:
-    """Backward of ``attention`` (no K/V broadcast): q/k/v/o bf16 (column-slice views allowed), d_o float16; writes the float16
-    views dq / dk / dv (e.g. the three column ranges of one ``[M, 3C]`` buffer)."""
+    """Backward of ``attention`` (no K/V broadcast): q/k/v/o bf16 (column-slice views allowed), d_o bfloat16 (the fast path: every
+    streamed tile is an asynchronous copy) or float16 (rounded to bf16 on load); writes the float16 views dq / dk / dv (e.g. the three
+    column ranges of one ``[M, 3C]`` buffer)."""
     lib = _lib.load()
     for n, t in (("q", q), ("k", k), ("v", v), ("o", o)):
         _cuda(t, f"attention_backward.{n}", torch.bfloat16)
-    for n, t in (("d_o", d_o), ("dq", dq), ("dk", dk), ("dv", dv)):
+    for n, t in (("dq", dq), ("dk", dk), ("dv", dv)):
         _cuda(t, f"attention_backward.{n}", torch.float16)
+    if d_o.dtype not in (torch.float16, torch.bfloat16):
+        raise TypeError("attention_backward.d_o must be bfloat16 or float16")
+    _cuda(d_o, "attention_backward.d_o", d_o.dtype)
     c = q.shape[1]
     d = c // heads
     nq, nk = q.shape[0] // batch, k.shape[0] // batch
-    ws = torch.empty((2 * batch * heads * nq,), device=q.device, dtype=torch.float32)
+    ws = torch.empty((lib.mrisr_attention_backward_workspace(batch, nq, nk, heads, d),), device=q.device, dtype=torch.float32)
     _lib.check(lib.mrisr_attention_backward(q.data_ptr(), _rows(q, "q"), k.data_ptr(), _rows(k, "k"), v.data_ptr(), _rows(v, "v"),
-                                            o.data_ptr(), _rows(o, "o"), d_o.data_ptr(), _rows(d_o, "d_o"), dq.data_ptr(), _rows(dq, "dq"),
+                                            o.data_ptr(), _rows(o, "o"), d_o.data_ptr(), _rows(d_o, "d_o"), int(d_o.dtype == torch.float16),
+                                            dq.data_ptr(), _rows(dq, "dq"),
                                             dk.data_ptr(), _rows(dk, "dk"), dv.data_ptr(), _rows(dv, "dv"), ws.data_ptr(), batch, nq, nk,
                                             heads, d, _stream(q)), "mrisr_attention_backward", kernels=2)
 

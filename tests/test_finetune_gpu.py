@@ -76,11 +76,15 @@ def test_geglu_forward_backward(ops):
 
 
 @pytest.mark.parametrize("B,heads,d,nq,nk", [(2, 8, 40, 256, 256), (1, 8, 40, 1024, 1024), (2, 8, 40, 256, 77), (2, 8, 80, 256, 256),
-                                             (2, 8, 160, 64, 64), (2, 8, 160, 64, 77), (2, 8, 16, 16, 16), (3, 8, 8, 64, 77), (1, 8, 16, 100, 77)])
-def test_attention_backward(ops, B, heads, d, nq, nk):
+                                             (2, 8, 160, 64, 64), (2, 8, 160, 64, 77), (2, 8, 16, 16, 16), (3, 8, 8, 64, 77), (1, 8, 16, 100, 77),
+                                             (2, 8, 40, 4096, 77), (2, 8, 80, 1000, 77), (2, 8, 160, 256, 77), (1, 8, 40, 200, 520)])
+@pytest.mark.parametrize("do_dtype", [torch.bfloat16, torch.float16])
+def test_attention_backward(ops, B, heads, d, nq, nk, do_dtype):
+    """Both dO formats (bf16: every tile an asynchronous copy; IEEE half: rounded on load), single / double-buffered head dims,
+    ragged tiles, and the query-split dK / dV of the few-key (cross-attention) shapes."""
     C = heads * d
     q, k, v = (_r((B * n, C), 20 + i).to(torch.bfloat16) for i, n in enumerate((nq, nk, nk)))
-    d_o = _r((B * nq, C), 23, 0.5).to(torch.float16)
+    d_o = _r((B * nq, C), 23, 0.5).to(do_dtype)
 
     def split(t, n):
         return t.float().view(B, n, heads, d).permute(0, 2, 1, 3)
