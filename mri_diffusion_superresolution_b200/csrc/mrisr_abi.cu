@@ -1241,7 +1241,7 @@ int mrisr_mse_grad(const float* pred, const float* target, int B, int C, int HW,
   return 0;
 }
 
-constexpr int kXtyRowsPerSplit = 256;   // 4 staged 64-row tiles per CTA (tensor-core partial products), msplit = M / 256
+constexpr int kXtyRowsPerSplit = mrisr::kXtyRows;   // one 256-row slab per CTA (tensor-core partial products), msplit = M / 256
 int64_t mrisr_xty64_workspace_floats(int M, int Q) {
   const int64_t msplit = (M + kXtyRowsPerSplit - 1) / kXtyRowsPerSplit;
   return msplit * 64 * static_cast<int64_t>(Q);
@@ -1253,9 +1253,16 @@ int mrisr_xty64(const void* X, int64_t ldx, int x_f16, const void* Y, int64_t ld
   const int msplit = (M + kXtyRowsPerSplit - 1) / kXtyRowsPerSplit;
   cudaStream_t st = as_stream(stream);
   MRISR_REQUIRE(ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0, "xty64: X must be 16-byte aligned with a row pitch that is a multiple of 8");
-  launch_k(mrisr::xty64_partial_kernel, dim3((Q + 63) / 64, msplit), dim3(128), 0, st, X, static_cast<long long>(ldx), x_f16, Y,
-           static_cast<long long>(ldy), y_f16, M, Q, kXtyRowsPerSplit, workspace);
+  static bool configured = false;
+  if (!configured) {
+    MRISR_CHECK_CUDA(cudaFuncSetAttribute(mrisr::xty64_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mrisr::kXtySmemBytes));
+    configured = true;
+  }
+  // a single slab (M <= 256): the partial product is the result
+  launch_k(mrisr::xty64_partial_kernel, dim3((Q + 63) / 64, msplit), dim3(256), mrisr::kXtySmemBytes, st, X, static_cast<long long>(ldx), x_f16, Y,
+           static_cast<long long>(ldy), y_f16, M, Q, msplit == 1 ? scale : 1.0f, msplit == 1 ? out : workspace);
   MRISR_CHECK_CUDA(cudaGetLastError());
+  if (msplit == 1) return 0;
   launch_k(mrisr::xty64_reduce_kernel, dim3(grid_for(64LL * Q, 256, 4)), dim3(256), 0, st, static_cast<const float*>(workspace), msplit, Q, scale, out);
   MRISR_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -405,83 +405,89 @@ __global__ void mse_finalize_kernel(const float* __restrict__ partial, int n, fl
 //   d(sB)^T  = t^T dy  (t = x A^T, kept from the forward pass)
 // fp32 FMA on the CUDA cores (64 x Q x M MACs: ~0.2 GFLOP per projection at batch 2), split over M into `msplit` chunks whose
 // partial products are summed by a second kernel in a fixed order (deterministic, no atomics).
-// Tensor-core form (mma.sync m16n8k16, bf16 operands, fp32 accumulation): one CTA = a 64-column tile of Y x `rows_per_split` rows; X
-// and Y tiles (64 rows x 64 columns) are staged in shared memory as bf16 (IEEE-half inputs are rounded once: the sum over thousands
-// of rows averages that rounding out) and both operands come from ldmatrix.trans -- A = X^T (16 X columns x 16 rows per MMA), B = Y.
-// Warp w owns X columns 16 w .. 16 w + 15 and all 64 Y columns (8 accumulators).  (The first version was an fp32-FMA kernel:
-// 2.9 + 1.5 ms of the 28 ms step at 25 % of the FMA peak.)
-constexpr int kXtyRows = 64;
+// Tensor-core form (mma.sync m16n8k16, bf16 operands, fp32 accumulation): one CTA = a 64-column tile of Y x 256 rows.  The whole
+// 256-row slab of X and Y is fetched in ONE round trip (16 independent 16-byte loads per thread), staged in shared memory as bf16
+// (IEEE-half inputs are rounded once: the sum over thousands of rows averages that rounding out), and both operands come from
+// ldmatrix.trans -- A = X^T (16 X columns x 16 rows per MMA), B = Y.  Warp w owns X columns 16 (w & 3) .. +15 and Y columns
+// 32 (w >> 2) .. +31.  These reductions are latency-, not throughput-bound (160 launches of a few MB each per step): the first
+// versions (fp32 FMAs, then 4 serialised 64-row tiles) cost ~20 us per call inside the graph.
+constexpr int kXtyRows = 256;
 constexpr int kXtyLds = 64 + 8;   // smem row pitch (elements): conflict-free ldmatrix
+constexpr int kXtySmemBytes = 2 * kXtyRows * kXtyLds * 2;
 __device__ __forceinline__ uint4 xty_to_bf16(const uint4& v, bool h) {
   if (!h) return v;
   return make_uint4(pack_bf16(f16_lo(v.x), f16_hi(v.x)), pack_bf16(f16_lo(v.y), f16_hi(v.y)), pack_bf16(f16_lo(v.z), f16_hi(v.z)),
                     pack_bf16(f16_lo(v.w), f16_hi(v.w)));
 }
-__global__ void __launch_bounds__(128) xty64_partial_kernel(const void* __restrict__ X, long long ldx, int x_f16,
+__global__ void __launch_bounds__(256) xty64_partial_kernel(const void* __restrict__ X, long long ldx, int x_f16,
                                                              const void* __restrict__ Y, long long ldy, int y_f16, int M, int Q,
-                                                             int rows_per_split, float* __restrict__ partial /*[msplit][64][Q]*/) {
+                                                             float scale, float* __restrict__ partial /*[msplit][64][Q]*/) {
   grid_dep_launch();
   grid_dep_wait();   // launched with programmatic dependent launch: inputs are the predecessor's output
-  __shared__ __align__(16) __nv_bfloat16 sx[kXtyRows * kXtyLds];
-  __shared__ __align__(16) __nv_bfloat16 sy[kXtyRows * kXtyLds];
+  extern __shared__ __align__(16) uint8_t xty_raw[];
+  __nv_bfloat16* sx = reinterpret_cast<__nv_bfloat16*>(xty_raw);
+  __nv_bfloat16* sy = sx + kXtyRows * kXtyLds;
   const int q0 = blockIdx.x * 64;
-  const int m_begin = blockIdx.y * rows_per_split;
-  const int m_end = min(M, m_begin + rows_per_split);
+  const int m0 = blockIdx.y * kXtyRows;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int mat = lane >> 3, rr = lane & 7;
-  float acc[8][4];
+  const bool yvec = (ldy % 8 == 0) && (q0 + 64 <= Q) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0);
+  {
+    const int v = threadIdx.x & 7, rbase = threadIdx.x >> 3;   // rows rbase + 32 i
+    uint4 xv[8], yv[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
+    for (int i = 0; i < 8; ++i) {
+      const int m = m0 + rbase + 32 * i;
+      xv[i] = make_uint4(0u, 0u, 0u, 0u);
+      yv[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (m < M) {
+        xv[i] = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(X) + static_cast<long long>(m) * ldx) + v);
+        if (yvec) yv[i] = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(Y) + static_cast<long long>(m) * ldy + q0) + v);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = rbase + 32 * i;
+      *reinterpret_cast<uint4*>(sx + r * kXtyLds + v * 8) = xty_to_bf16(xv[i], x_f16 != 0);
+      if (yvec) *reinterpret_cast<uint4*>(sy + r * kXtyLds + v * 8) = xty_to_bf16(yv[i], y_f16 != 0);
+    }
+  }
+  if (!yvec) {   // ragged last column tile / unaligned view: element-wise
+    for (int e = threadIdx.x; e < kXtyRows * 64; e += 256) {
+      const int r = e >> 6, c = e & 63;
+      const bool ok = m0 + r < M && q0 + c < Q;
+      sy[r * kXtyLds + c] = __float2bfloat16(ok ? ld16(Y, static_cast<long long>(m0 + r) * ldy + q0 + c, y_f16 != 0) : 0.f);
+    }
+  }
+  __syncthreads();
+  const int wx = warp & 3, wy = warp >> 2;
+  float acc[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
-  const bool yvec = (ldy % 8 == 0) && (q0 + 64 <= Q) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0);
-  for (int m0 = m_begin; m0 < m_end; m0 += kXtyRows) {
-    for (int e = threadIdx.x; e < kXtyRows * 8; e += 128) {   // 64 rows x 8 16-byte vectors, X and Y
-      const int r = e >> 3, v = e & 7;
-      const int m = m0 + r;
-      uint4 xv = make_uint4(0u, 0u, 0u, 0u), yv = make_uint4(0u, 0u, 0u, 0u);
-      if (m < m_end) {
-        xv = xty_to_bf16(__ldg(reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(X) + static_cast<long long>(m) * ldx) + v), x_f16 != 0);
-        if (yvec) {
-          yv = xty_to_bf16(__ldg(reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(Y) + static_cast<long long>(m) * ldy + q0) + v), y_f16 != 0);
-        } else {   // ragged last column tile / unaligned view: element-wise
-          uint16_t t[8];
+  const int ksteps = (min(M - m0, kXtyRows) + 15) / 16;   // rows past M are zeros
+  for (int ks = 0; ks < ksteps; ++ks) {
+    // A = X^T: m = X column (16 warp-owned columns), k = row.  ldmatrix.trans of [row][col] blocks: a0 (m 0-7, k 0-7), a1 (m 8-15, k 0-7),
+    // a2 (m 0-7, k 8-15), a3 (m 8-15, k 8-15)
+    uint32_t a[4];
+    ldsm_x4_t(smem_u32(sx + (ks * 16 + (mat >> 1) * 8 + rr) * kXtyLds + wx * 16 + (mat & 1) * 8), a[0], a[1], a[2], a[3]);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int c = q0 + v * 8 + j;
-            t[j] = c < Q ? __bfloat16_as_ushort(__float2bfloat16(ld16(Y, static_cast<long long>(m) * ldy + c, y_f16 != 0))) : uint16_t(0);
-          }
-          yv = make_uint4(t[0] | (uint32_t(t[1]) << 16), t[2] | (uint32_t(t[3]) << 16), t[4] | (uint32_t(t[5]) << 16), t[6] | (uint32_t(t[7]) << 16));
-        }
-      }
-      *reinterpret_cast<uint4*>(sx + r * kXtyLds + v * 8) = xv;
-      *reinterpret_cast<uint4*>(sy + r * kXtyLds + v * 8) = yv;
+    for (int jj = 0; jj < 2; ++jj) {   // B = Y (k = row, n = column): two 8-column blocks per ldmatrix.trans
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4_t(smem_u32(sy + (ks * 16 + (mat & 1) * 8 + rr) * kXtyLds + wy * 32 + jj * 16 + (mat >> 1) * 8), b0, b1, b2, b3);
+      mma_bf16_16816(acc[2 * jj], a, b0, b1);
+      mma_bf16_16816(acc[2 * jj + 1], a, b2, b3);
     }
-    __syncthreads();
-#pragma unroll
-    for (int ks = 0; ks < kXtyRows / 16; ++ks) {
-      // A = X^T: m = X column (16 warp-owned columns), k = row.  ldmatrix.trans of [row][col] blocks: a0 (m 0-7, k 0-7), a1 (m 8-15, k 0-7),
-      // a2 (m 0-7, k 8-15), a3 (m 8-15, k 8-15)
-      uint32_t a[4];
-      ldsm_x4_t(smem_u32(sx + (ks * 16 + (mat >> 1) * 8 + rr) * kXtyLds + warp * 16 + (mat & 1) * 8), a[0], a[1], a[2], a[3]);
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {   // B = Y (k = row, n = column): two 8-column blocks per ldmatrix.trans
-        uint32_t b0, b1, b2, b3;
-        ldsm_x4_t(smem_u32(sy + (ks * 16 + (mat & 1) * 8 + rr) * kXtyLds + jj * 16 + (mat >> 1) * 8), b0, b1, b2, b3);
-        mma_bf16_16816(acc[2 * jj], a, b0, b1);
-        mma_bf16_16816(acc[2 * jj + 1], a, b2, b3);
-      }
-    }
-    __syncthreads();
   }
   float* dst = partial + static_cast<long long>(blockIdx.y) * 64 * Q;
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = q0 + j * 8 + 2 * t;
-    const int r0 = warp * 16 + g;
-    if (c < Q) { dst[static_cast<long long>(r0) * Q + c] = acc[j][0]; dst[static_cast<long long>(r0 + 8) * Q + c] = acc[j][2]; }
-    if (c + 1 < Q) { dst[static_cast<long long>(r0) * Q + c + 1] = acc[j][1]; dst[static_cast<long long>(r0 + 8) * Q + c + 1] = acc[j][3]; }
+  for (int j = 0; j < 4; ++j) {
+    const int c = q0 + wy * 32 + j * 8 + 2 * t;
+    const int r0 = wx * 16 + g;
+    if (c < Q) { dst[static_cast<long long>(r0) * Q + c] = acc[j][0] * scale; dst[static_cast<long long>(r0 + 8) * Q + c] = acc[j][2] * scale; }
+    if (c + 1 < Q) { dst[static_cast<long long>(r0) * Q + c + 1] = acc[j][1] * scale; dst[static_cast<long long>(r0 + 8) * Q + c + 1] = acc[j][3] * scale; }
   }
 }
 __global__ void xty64_reduce_kernel(const float* __restrict__ partial, int msplit, int Q, float scale, float* __restrict__ out) {
