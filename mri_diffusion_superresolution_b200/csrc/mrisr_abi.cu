@@ -1143,8 +1143,10 @@ int mrisr_groupnorm_backward(const void* x1, int64_t ld1, int c1, const void* x2
   MRISR_REQUIRE(groups > 0 && (c1 + c2) % groups == 0 && ((c1 + c2) / groups) % 2 == 0 && c1 % 2 == 0 && ld1 % 2 == 0 && ld2 % 2 == 0 && lddx1 % 2 == 0 && lddx2 % 2 == 0,
                 "groupnorm_backward: groups must divide the channel count into even-sized groups; even strides");
   const int C = c1 + c2;
-  // large levels: slab-parallel three-launch form (statistics, reductions, result), each launch fills the machine
-  if (workspace != nullptr && hw >= 1024 && C % 8 == 0 && c1 % 8 == 0 && C / 8 <= 512 && ld1 % 8 == 0 && ld2 % 8 == 0 && lddx1 % 8 == 0 && lddx2 % 8 == 0 &&
+  // slab-parallel three-launch form (statistics, reductions, result), each launch spread over the machine; the single-kernel form
+  // below (one CTA per (group, batch), three serial passes) is left for tiny or unaligned inputs
+  static const int min_hw = [] { const char* e = std::getenv("MRISR_GNB_MINHW"); return e ? std::atoi(e) : 64; }();   // tuning runs (1024 -> 64: fine-tune step -0.6 ms)
+  if (workspace != nullptr && hw >= min_hw && C % 8 == 0 && c1 % 8 == 0 && C / 8 <= 512 && ld1 % 8 == 0 && ld2 % 8 == 0 && lddx1 % 8 == 0 && lddx2 % 8 == 0 &&
       groups <= 64 && aligned16(x1) && aligned16(dz) && aligned16(dx1) && (!x2 || (aligned16(x2) && aligned16(dx2)))) {
     const int nvec = C / 8;
     int R = 256 / nvec; if (R < 1) R = 1; if (R > hw) R = hw;

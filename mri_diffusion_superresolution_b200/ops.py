@@ -548,7 +548,7 @@ def groupnorm_backward(x1: Tensor, dz: Tensor, gamma: Tensor, beta: Tensor, grou
     _lib.check(lib.mrisr_groupnorm_backward(x1.data_ptr(), x1.stride(2), c1, _ptr(x2), ld2, c2, dz.data_ptr(), B, H * W, groups,
                                             gamma.data_ptr(), beta.data_ptr(), float(eps), int(silu), dx1.data_ptr(), c1,
                                             _ptr(dx2), c2, ws.data_ptr(), f16, _stream(x1)), "mrisr_groupnorm_backward",
-               kernels=3 if H * W >= 1024 else 1)
+               kernels=3 if H * W >= 64 else 1)
     return dx1, dx2
 
 

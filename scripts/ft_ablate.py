@@ -35,6 +35,8 @@ def timed():
 
 base = timed()
 print(f"full step: {base:.2f} ms")
+if len(sys.argv) > 1 and sys.argv[1] == "base":   # A/B runs of an environment toggle: the full step only
+    sys.exit(0)
 real = {n: getattr(ops, n) for n in ("xty64", "attention_backward", "groupnorm_backward", "layernorm_backward", "geglu_backward", "geglu_forward")}
 fake = {
     "xty64": lambda x, y, out, scale=1.0: out,

@@ -33,7 +33,8 @@ def ops():
 
 @pytest.mark.parametrize("B,H,C1,C2,silu,eps", [(2, 16, 64, 0, True, 1e-5), (2, 32, 320, 0, True, 1e-5), (1, 16, 1280, 640, True, 1e-5),
                                                   (2, 8, 640, 320, True, 1e-5), (2, 16, 320, 0, False, 1e-6), (2, 64, 320, 320, True, 1e-5),
-                                                  (3, 32, 640, 320, True, 1e-5), (2, 64, 320, 0, False, 1e-6), (1, 32, 64, 0, True, 1e-5)])
+                                                  (3, 32, 640, 320, True, 1e-5), (2, 64, 320, 0, False, 1e-6), (1, 32, 64, 0, True, 1e-5),
+                                                  (2, 4, 64, 0, True, 1e-5), (1, 4, 320, 320, True, 1e-5)])   # < 64 pixels: single-kernel form
 def test_groupnorm_backward(ops, B, H, C1, C2, silu, eps):
     x1 = (_r((B, H, H, C1), 1) + 0.3).to(torch.float16)
     x2 = (_r((B, H, H, C2), 2) * 1.5).to(torch.bfloat16) if C2 else None
