@@ -674,12 +674,18 @@ __device__ __forceinline__ void ab_mma_nt(float (&acc)[8][4], const __nv_bfloat1
   for (int ks = 0; ks < Cfg::DP / 16; ++ks) {
     uint32_t a[4];
     ldsm_x4(smem_u32(sa + (r0 + (mat & 1) * 8 + rr) * Cfg::LDS + ks * 16 + (mat >> 1) * 8), a[0], a[1], a[2], a[3]);
+    const bool half_step = ks * 16 + 8 >= D;   // head dim 40: the last step holds 8 real columns + 8 zero columns -> one k = 8 MMA
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {   // two 8-column blocks per ldmatrix
       uint32_t b0, b1, b2, b3;
       ldsm_x4(smem_u32(sb + (jj * 16 + (mat >> 1) * 8 + rr) * Cfg::LDS + ks * 16 + (mat & 1) * 8), b0, b1, b2, b3);
-      mma_bf16_16816(acc[2 * jj], a, b0, b1);
-      mma_bf16_16816(acc[2 * jj + 1], a, b2, b3);
+      if (half_step) {
+        mma_bf16_1688(acc[2 * jj], a[0], a[1], b0);
+        mma_bf16_1688(acc[2 * jj + 1], a[0], a[1], b2);
+      } else {
+        mma_bf16_16816(acc[2 * jj], a, b0, b1);
+        mma_bf16_16816(acc[2 * jj + 1], a, b2, b3);
+      }
     }
   }
 }
@@ -701,13 +707,13 @@ __device__ __forceinline__ void ab_mma_pn(float (&out)[AttnBwdCfg<D>::DP / 8][4]
       uint32_t b0, b1, b2, b3;
       ldsm_x4_t(smem_u32(sb + (jj * 16 + (mat & 1) * 8 + rr) * Cfg::LDS + nb * 16 + (mat >> 1) * 8), b0, b1, b2, b3);
       mma_bf16_16816(out[2 * nb], a, b0, b1);
-      mma_bf16_16816(out[2 * nb + 1], a, b2, b3);
+      if ((2 * nb + 1) * 8 < D) mma_bf16_16816(out[2 * nb + 1], a, b2, b3);   // (a block of pad columns only is never stored)
     }
   }
 }
 
 template <int D>
-__global__ void __launch_bounds__(kAbThreads) attention_bwd_dq_kernel(AttnBwdArgs a) {
+__global__ void __launch_bounds__(kAbThreads, D <= 40 ? 4 : 1) attention_bwd_dq_kernel(AttnBwdArgs a) {
   grid_dep_launch();
   grid_dep_wait();   // launched with programmatic dependent launch: inputs are the predecessor's output
   using Cfg = AttnBwdCfg<D>;
@@ -763,13 +769,14 @@ __global__ void __launch_bounds__(kAbThreads) attention_bwd_dq_kernel(AttnBwdArg
     }
     float s[8][4];
     ab_mma_nt<D>(s, sQ, r0, cK, lane);
+    const bool full_tile = kt * 64 + 64 <= a.nk;
     float tm[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int j = 0; j < 8; ++j)
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int col = kt * 64 + j * 8 + 2 * t + (i & 1);
-        s[j][i] = col < a.nk ? s[j][i] * a.scale_log2 : -INFINITY;
+        s[j][i] = (full_tile || col < a.nk) ? s[j][i] * a.scale_log2 : -INFINITY;
         tm[i >> 1] = fmaxf(tm[i >> 1], s[j][i]);
       }
 #pragma unroll
@@ -822,6 +829,7 @@ __global__ void __launch_bounds__(kAbThreads) attention_bwd_dq_kernel(AttnBwdArg
       ab_cp_commit();
     }
     float s[8][4], dp[8][4];
+    const bool full_tile = kt * 64 + 64 <= a.nk;
     ab_mma_nt<D>(s, sQ, r0, cK, lane);
     ab_mma_nt<D>(dp, sdO, r0, cV, lane);
 #pragma unroll
@@ -829,7 +837,7 @@ __global__ void __launch_bounds__(kAbThreads) attention_bwd_dq_kernel(AttnBwdArg
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int col = kt * 64 + j * 8 + 2 * t + (i & 1);
-        const float p = col < a.nk ? ab_ex2(s[j][i] * a.scale_log2 - lse[i >> 1]) : 0.f;
+        const float p = (full_tile || col < a.nk) ? ab_ex2(s[j][i] * a.scale_log2 - lse[i >> 1]) : 0.f;
         s[j][i] = p * (dp[j][i] - dsv[i >> 1]);     // dS
       }
     ab_mma_pn<D>(dq, s, cK, lane);
@@ -914,13 +922,14 @@ __global__ void __launch_bounds__(kAbThreads) attention_bwd_dkdv_kernel(AttnBwdA
     const float* cDs = sDs + cur * 64;
     if (NB == 2 && qt + 1 < qt_end) load_q_tile(qt + 1, cur ^ 1);
     float s[8][4];
+    const bool full_tile = qt * 64 + 64 <= a.nq;
     ab_mma_nt<D>(s, sK, r0, cQ, lane);            // S^T: rows = keys, cols = queries
 #pragma unroll
     for (int j = 0; j < 8; ++j)
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int qc = j * 8 + 2 * t + (i & 1);
-        s[j][i] = (qt * 64 + qc < a.nq) ? ab_ex2(s[j][i] * a.scale_log2 - cL[qc]) : 0.f;   // P^T
+        s[j][i] = (full_tile || qt * 64 + qc < a.nq) ? ab_ex2(s[j][i] * a.scale_log2 - cL[qc]) : 0.f;   // P^T
       }
     if constexpr (kMode != 2) ab_mma_pn<D>(dv, s, cdO, lane);
     if constexpr (kMode != 1) {
