@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MRISR_ABI_VERSION 5
+#define MRISR_ABI_VERSION 6
 
 #define MRISR_OK 0
 #define MRISR_E_INVALID (-1)     /* bad argument (null pointer, misaligned, negative size) */
@@ -166,7 +166,15 @@ typedef struct mrisr_gemm_args {
   int32_t reserved4;
   void* lora_t_out;      /* with lora_a: NULL, or a 16-bit [M, 64] buffer (operand format, row pitch 64) that receives the rounded
                             T = x A^T -- the fine-tune step keeps it for the rank-16 weight gradients */
+  void* splitk_ws;       /* NULL, or an fp32 scratch buffer of splitk_ws_floats >= mrisr_gemm_splitk_workspace_floats(...) elements:
+                            allows the split-K form for small-M deep-K problems (M <= 1024: the K range of every tile is worked on by
+                            several CTA pairs, a second kernel sums the fp32 partial tiles in fixed order and applies bias /
+                            activation / residuals).  Results differ from the single-pass form only by fp32 summation order. */
+  int64_t splitk_ws_floats;
 } mrisr_gemm_args;
+/* fp32 elements of split-K scratch mrisr_gemm would use for this problem; 0 = the problem is not split (large M, shallow K, GEGLU,
+ * fused LoRA / GroupNorm statistics / upsample fold) and splitk_ws may stay NULL. */
+int64_t mrisr_gemm_splitk_workspace_floats(int M, int N, int k1, int k2, int taps, int act, int has_lora, int has_stats);
 #define MRISR_F16_OUT 1   /* out (when out_fp32 == 0) */
 #define MRISR_F16_RES1 2  /* res1 */
 #define MRISR_F16_RES2 4  /* res2 */

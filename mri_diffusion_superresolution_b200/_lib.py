@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmrisr_b200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 ACT_NONE, ACT_RELU, ACT_SILU, ACT_GEGLU = 0, 1, 2, 3
 E_INVALID, E_UNSUPPORTED, E_CUDA = -1, -2, -3
 
@@ -35,6 +35,7 @@ class GemmArgs(C.Structure):
         ("gn_stats", C.c_void_p), ("ld_stats", C.c_int64),
         ("lora_a", C.c_void_p), ("lora_n", C.c_int32), ("reserved4", C.c_int32),
         ("lora_t_out", C.c_void_p),
+        ("splitk_ws", C.c_void_p), ("splitk_ws_floats", C.c_int64),
     ]
 
 
@@ -94,6 +95,7 @@ PROTOTYPES = {
     "mrisr_mse_grad": (_I, [_P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P]),
     "mrisr_xty64_workspace_floats": (_L, [_I, _I]),
     "mrisr_xty64": (_I, [_P, _L, _I, _P, _L, _I, _I, _I, _F, _P, _P, _P]),
+    "mrisr_gemm_splitk_workspace_floats": (_L, [_I, _I, _I, _I, _I, _I, _I, _I]),
     "mrisr_attention_backward_workspace": (_L, [_I, _I, _I, _I, _I]),
     "mrisr_attention_backward": (_I, [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _I, _P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _P]),
     "mrisr_grad_sqnorm": (_I, [_P, _I, _F, _P, _P, _P]),

@@ -85,6 +85,8 @@ struct GemmKernelParams {
   int part_phase_stride;  // 128-row blocks per phase (M / 128)
   void* lora_t_out;       // kLora: optional [M, kLoraN] 16-bit copy of the rounded T = x A^T (row pitch kLoraN): the fine-tune step keeps it for
                           // the rank-16 weight gradients (forward: t = x A^T; backward: u = dy (s B)); written by the N tile 0 of every M tile
+  int ksplit;             // > 1: split-K (weight-bound small-M GEMMs, see mrisr_gemm): tile -> (tile, K slice); every slice writes its raw fp32
+                          // accumulator to out + slice * M rows (out_fp32, no bias / activation / residual: gemm_splitk_reduce_kernel applies them)
   int lora_n;             // kLora: rows of the stacked A matrix actually used (sum of the ranks rounded up to 16; <= kLoraN): the skinny
                           // MMA's N and the K extension's length -- the executed LoRA work follows the rank, not the 64-wide padding
 };
@@ -355,7 +357,7 @@ __device__ __forceinline__ void gemm_epilogue_tma(const GemmKernelParams& p, con
 // a swizzled shared-memory transpose (8 rows x 64 contiguous bytes per store instruction).
 template <int BN>
 __device__ __forceinline__ void gemm_epilogue_rows(const GemmKernelParams& p, uint32_t t_row, int m, int n_blk, int half,
-                                                   const float* sbias, uint8_t* stage_buf) {
+                                                   const float* sbias, uint8_t* stage_buf, long long row_off = 0) {
   const int lane_id = threadIdx.x & 31;
   const bool row_ok = m < p.M;
   const bool geglu = p.act == ACT_GEGLU;
@@ -410,7 +412,7 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmKernelParams& p, ui
         if (r1p != nullptr) add_res32(f, r1p + c * 32, p.f16_r1 != 0);
         if (r2p != nullptr) add_res32(f, r2p + c * 32, p.f16_r2 != 0);
         if (p.out_fp32) {
-          float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<long long>(m) * p.ldo + n);
+          float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + (m + row_off) * p.ldo + n);   // (row_off: split-K slice)
 #pragma unroll
           for (int u = 0; u < 8; ++u) o[u] = make_float4(f[4 * u], f[4 * u + 1], f[4 * u + 2], f[4 * u + 3]);
         }
@@ -531,9 +533,11 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
 
   const int m_tiles = (p.M + kTileM - 1) / kTileM;
   const int n_phases = p.up2x ? 4 : 1;   // tile -> (m tile, sub-pixel phase, n tile): the phases of an m tile share its input rows in L2
-  const int total_tiles = m_tiles * n_phases * p.n_tiles;
+  const int ksplit = p.ksplit;
+  const int total_tiles = m_tiles * n_phases * p.n_tiles * ksplit;   // split-K: the K slices of a tile are adjacent work items
   const int kchunks = p.kc1 + p.kc2;
   const int kmain = p.taps * kchunks;
+  const int kper = (kmain + ksplit - 1) / ksplit;   // main k-chunks (tap-major order) per K slice; the host guarantees no empty slice
   // residual-as-operand: the k-chunks of R that intersect this tile's columns [n_blk*BN, n_blk*BN + BN)
   auto res_first = [&](int n_blk) { return (n_blk * BN) >> 6; };
   auto res_count = [&](int n_blk) { return p.res_mma > 0 ? ((n_blk * BN + BN + 63) >> 6) - ((n_blk * BN) >> 6) : 0; };
@@ -573,8 +577,11 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
       if (++stage == kStages) { stage = 0; phase ^= 1u; }
     };
     for (int tile = worker; tile < total_tiles; tile += num_workers) {
-      const int n_blk = tile % p.n_tiles;
-      const int tq = tile / p.n_tiles;
+      const int t2 = ksplit > 1 ? tile / ksplit : tile;
+      const int f0 = ksplit > 1 ? (tile - t2 * ksplit) * kper : 0;
+      const int f1 = min(kmain, f0 + kper);
+      const int n_blk = t2 % p.n_tiles;
+      const int tq = t2 / p.n_tiles;
       const int ph = p.up2x ? (tq & 3) : 0;
       const int n0 = ph * p.N + n_blk * BN + rank * Cfg::kBRows;   // up2x: the four phases' folded filters are stacked along N
       const int m0 = (p.up2x ? (tq >> 2) : tq) * kTileM + rank * kBlockM;
@@ -586,11 +593,13 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
         h0 = rem / p.W;
         x0 = rem - h0 * p.W;
       }
-      for (int tap = 0; tap < p.taps; ++tap) {
+      const int tap0 = f0 / kchunks;
+      for (int tap = tap0; tap < p.taps && tap * kchunks < f1; ++tap) {
         // up2x: output row 2y+a reads input rows {y-1, y} (a = 0) or {y, y+1} (a = 1); same along x
         const int dr = p.up2x ? (tap >> 1) - 1 + (ph >> 1) : (p.taps == 9) ? tap / 3 - p.pad : 0;
         const int ds = p.up2x ? (tap & 1) - 1 + (ph & 1) : (p.taps == 9) ? tap % 3 - p.pad : 0;
-        for (int kc = 0; kc < kchunks; ++kc) {
+        const int kc_begin = max(f0 - tap * kchunks, 0), kc_end = min(f1 - tap * kchunks, kchunks);
+        for (int kc = kc_begin; kc < kc_end; ++kc) {
           const bool first = kc < p.kc1;
           load(first ? &maps.a1 : &maps.a2, p.conv != 0, (first ? kc : kc - p.kc1) * kBlockK, x0 * p.stride + ds, h0 * p.stride + dr, b0, m0, &maps.b,
                (tap * kchunks + kc) * kBlockK, n0, kLora ? kc * kBlockK : -1);
@@ -630,8 +639,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
       uint32_t it = 0;
       for (int tile = worker; tile < total_tiles; tile += num_workers, ++it) {
         const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
-        const int rcount = res_count(tile % p.n_tiles);
-        const int kiters = kmain + p.res_mma * rcount;
+        const int t2 = ksplit > 1 ? tile / ksplit : tile;
+        const int rcount = res_count(t2 % p.n_tiles);
+        const int kmain_t = ksplit > 1 ? min(kmain, (tile - t2 * ksplit + 1) * kper) - (tile - t2 * ksplit) * kper : kmain;   // this K slice
+        const int kiters = kmain_t + p.res_mma * rcount;
         mbar_wait(tempty_bar(as), aph ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -644,7 +655,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
           const uint64_t adesc = umma_smem_desc(sa, 1024, kLayoutSW128);
           const uint64_t bdesc = umma_smem_desc(sa + Cfg::kABytes, 1024, kLayoutSW128);
           // residual operand chunks carry their own element format (bf16 or IEEE half) against the matching identity tile
-          const uint32_t idesc = ki < kmain ? idesc_main : (((p.f16_rm >> ((ki - kmain) >= rcount ? 1 : 0)) & 1) ? idesc_h : idesc_b);
+          const uint32_t idesc = ki < kmain_t ? idesc_main : (((p.f16_rm >> ((ki - kmain_t) >= rcount ? 1 : 0)) & 1) ? idesc_h : idesc_b);
           if (elect_one()) {
             if (!(p.dbg & 2)) {
 #pragma unroll
@@ -652,7 +663,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
                 if (kPair) umma_bf16_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
                 else umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (ki > 0 || k > 0) ? 1u : 0u);
               }
-              if (kLora && ki < kmain) {   // the same x tile against the stacked LoRA A rows of this k-chunk
+              if (kLora && ki < kmain_t) {   // the same x tile against the stacked LoRA A rows of this k-chunk
                 const uint64_t b2desc = umma_smem_desc(sa + Cfg::kABytes + Cfg::kBBytes, 1024, kLayoutSW128);
 #pragma unroll
                 for (int k = 0; k < kBlockK / 16; ++k) {
@@ -664,11 +675,11 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
             // free the smem slot once these MMAs retire; the last k-chunk also publishes the accumulator
             if (kPair) {
               umma_commit_pair(empty_bar(stage));
-              if (kLora && ki == kmain - 1) umma_commit_pair(tT_full(as));   // T complete: the epilogue warps may round it
+              if (kLora && ki == kmain_t - 1) umma_commit_pair(tT_full(as));   // T complete: the epilogue warps may round it
               if (!kLora && ki == kiters - 1) umma_commit_pair(tfull_bar(as));
             } else {
               umma_commit(empty_bar(stage));
-              if (kLora && ki == kmain - 1) umma_commit(tT_full(as));
+              if (kLora && ki == kmain_t - 1) umma_commit(tT_full(as));
               if (!kLora && ki == kiters - 1) umma_commit(tfull_bar(as));
             }
           }
@@ -709,8 +720,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
     grid_dep_wait();  // the previous kernel may still read the buffer this one overwrites
     for (int tile = worker; tile < total_tiles; tile += num_workers, ++it) {
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
-      const int n_blk = tile % p.n_tiles;
-      const int tq = tile / p.n_tiles;
+      const int t2 = ksplit > 1 ? tile / ksplit : tile;
+      const int n_blk = t2 % p.n_tiles;
+      const int tq = t2 / p.n_tiles;
       const int ph = p.up2x ? (tq & 3) : 0;
       const int m_tile = p.up2x ? (tq >> 2) : tq;
       const int m = m_tile * kTileM + rank * kBlockM + q * 32 + lane;
@@ -766,7 +778,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
           gemm_epilogue_tma<BN, false>(p, &maps.out[ph], t_row, m, n_blk, half, sbias, stage_buf, buf_sel, release, st);
         }
       } else {
-        gemm_epilogue_rows<BN>(p, t_row, m, n_blk, half, sbias, stage_buf);
+        gemm_epilogue_rows<BN>(p, t_row, m, n_blk, half, sbias, stage_buf, ksplit > 1 ? static_cast<long long>(tile - t2 * ksplit) * p.M : 0ll);
         release();
       }
     }
@@ -779,6 +791,54 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
   if (warp == 2) {
     tcgen05_fence_after();
     if (kPair) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base); else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// Second half of a split-K GEMM: out = act(sum over the K slices + bias + rowvec) + res1 + res2, 4 columns per thread, slices added
+// in index order (bit-reproducible).  ws is [ksplit][M][ldw] fp32.
+struct SplitKReduceArgs {
+  const float* ws; long long ldw; int ksplit, M, n_store;
+  const float* bias; const float* rowvec; long long rowvec_stride; int rows_per_batch; int act;
+  const __nv_bfloat16* res1; long long ldr1; const __nv_bfloat16* res2; long long ldr2;
+  void* out; long long ldo; int out_fp32, f16_out, f16_r1, f16_r2;
+};
+__global__ void __launch_bounds__(256) gemm_splitk_reduce_kernel(SplitKReduceArgs a) {
+  grid_dep_launch();
+  grid_dep_wait();
+  const int nvec = (a.n_store + 3) / 4;
+  const long long total = static_cast<long long>(a.M) * nvec;
+  for (long long e = blockIdx.x * 256ll + threadIdx.x; e < total; e += gridDim.x * 256ll) {
+    const int m = static_cast<int>(e / nvec), n = static_cast<int>(e - static_cast<long long>(m) * nvec) * 4;
+    float4 acc = *reinterpret_cast<const float4*>(a.ws + static_cast<long long>(m) * a.ldw + n);
+    for (int s = 1; s < a.ksplit; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(a.ws + (static_cast<long long>(s) * a.M + m) * a.ldw + n);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float f[4] = {acc.x, acc.y, acc.z, acc.w};
+    const float* rv = a.rowvec != nullptr ? a.rowvec + static_cast<long long>(m / a.rows_per_batch) * a.rowvec_stride : nullptr;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (n + j >= a.n_store) continue;
+      float x = f[j];
+      if (a.bias != nullptr) x += __ldg(a.bias + n + j);
+      if (rv != nullptr) x += __ldg(rv + n + j);
+      if (a.act == ACT_RELU) x = fmaxf(x, 0.f);
+      else if (a.act == ACT_SILU) x = act_silu(x);
+      if (a.res1 != nullptr) x += load16(a.res1 + static_cast<long long>(m) * a.ldr1 + n + j, a.f16_r1 != 0);
+      if (a.res2 != nullptr) x += load16(a.res2 + static_cast<long long>(m) * a.ldr2 + n + j, a.f16_r2 != 0);
+      f[j] = x;
+    }
+    const long long o = static_cast<long long>(m) * a.ldo + n;
+    if (n + 4 <= a.n_store) {
+      if (a.out_fp32) *reinterpret_cast<float4*>(static_cast<float*>(a.out) + o) = make_float4(f[0], f[1], f[2], f[3]);
+      else *reinterpret_cast<uint2*>(static_cast<uint16_t*>(a.out) + o) = make_uint2(pack16(f[0], f[1], a.f16_out != 0), pack16(f[2], f[3], a.f16_out != 0));
+    } else {
+      for (int j = 0; j < 4 && n + j < a.n_store; ++j) {
+        if (a.out_fp32) static_cast<float*>(a.out)[o + j] = f[j];
+        else if (a.f16_out) static_cast<__half*>(a.out)[o + j] = __float2half_rn(f[j]);
+        else static_cast<__nv_bfloat16*>(a.out)[o + j] = __float2bfloat16(f[j]);
+      }
+    }
   }
 }
 

@@ -151,7 +151,7 @@ int launch_gemm(const mrisr::GemmMaps& maps, const mrisr::GemmKernelParams& p, c
                                           Cfg::kSmemBytes));
     configured = true;
   }
-  const int tiles = ((p.M + Cfg::kTileM - 1) / Cfg::kTileM) * p.n_tiles;
+  const int tiles = ((p.M + Cfg::kTileM - 1) / Cfg::kTileM) * p.n_tiles * (p.ksplit > 1 ? p.ksplit : 1);   // split-K: one worker per K slice
   const int max_workers = kPair ? sm_count() / 2 : sm_count();
   const int workers = tiles < max_workers ? tiles : max_workers;
   cudaLaunchConfig_t cfg{};
@@ -698,6 +698,44 @@ static int pick_block_n(int M, int N, int act, int phases = 1) {
   return best;
 }
 
+// Split-K plan.  Small-M GEMMs with a deep K (the 16x16 / 8x8 levels at small batch: M <= 1024 rows against 1280 x 11520 filters)
+// are bound by how fast the few busy SMs can pull operands: BN = 64 tiles fill 80 CTAs but re-read the activation tile once per
+// N tile (measured 26-32 us per conv, ~90 B/clk/SM of operand traffic).  Instead: the widest N tile, and the K range of every
+// tile cut into `ksplit` slices worked on by different CTA pairs; the slices leave fp32 partial tiles that
+// gemm_splitk_reduce_kernel sums (fixed order) and finishes (bias, activation, residuals, rounding).
+struct SplitKPlan { int ksplit, bn; };
+static SplitKPlan plan_splitk(int M, int N, int k1, int k2, int taps, int act, bool lora, bool stats) {
+  SplitKPlan none = {1, 0};
+  static const bool off = [] { const char* e = getenv("MRISR_GEMM_SPLITK"); return e != nullptr && e[0] == '0'; }();
+  if (off || lora || stats || taps == 4 || act == MRISR_ACT_GEGLU || M > 1024 || !use_pair_kernel() || getenv("MRISR_GEMM_BN") != nullptr) return none;
+  const int bn = mrisr_gemm_block_n(N, act);
+  if (bn == 0) return none;
+  const int kmain = taps * ((k1 + k2) / 64);
+  // Measured (scripts/splitk_bench.py, B200): the fp32 partial tiles cost 2 x ksplit x M x N x 4 bytes of traffic plus a second
+  // launch, so the split only pays when the serial K loop it replaces is long against M: 8x8 level (M = 128) 33 -> 23 us at
+  // K = 11520, 61 -> 28 us at K = 23040; 16x16 level (M = 512) 64 -> 46 us at K = 23040 but 35 -> 36 us at K = 11520.
+  static const bool forced = getenv("MRISR_GEMM_KSPLIT") != nullptr;
+  if (!forced && !(M <= 256 ? kmain >= 150 : kmain >= 300)) return none;
+  const int pairs = sm_count() / 2 > 0 ? sm_count() / 2 : 1;
+  const int tiles = ((M + 255) / 256) * (N / bn);
+  int ks = pairs / tiles;
+  if (ks > kmain / 8) ks = kmain / 8;   // at least 8 k-chunks (512 of K) per slice
+  if (ks > 16) ks = 16;
+  if (const char* e = getenv("MRISR_GEMM_KSPLIT")) ks = atoi(e);   // tuning runs
+  if (ks < 2) return none;
+  const int per = (kmain + ks - 1) / ks;
+  ks = (kmain + per - 1) / per;         // no empty slice
+  if (ks < 2) return none;
+  SplitKPlan plan = {ks, bn};
+  return plan;
+}
+
+int64_t mrisr_gemm_splitk_workspace_floats(int M, int N, int k1, int k2, int taps, int act, int has_lora, int has_stats) {
+  if (M <= 0 || N <= 0 || k1 <= 0 || k2 < 0) return 0;
+  const SplitKPlan plan = plan_splitk(M, N, k1, k2, taps, act, has_lora != 0, has_stats != 0);
+  return plan.ksplit > 1 ? static_cast<int64_t>(plan.ksplit) * M * N : 0;
+}
+
 int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
   MRISR_ONE_DEVICE();
   MRISR_REQUIRE(g != nullptr, "gemm: null args");
@@ -717,7 +755,15 @@ int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
     if (!use_pair_kernel()) return fail(MRISR_E_UNSUPPORTED, "gemm(lora_a): needs the CTA-pair kernel");
     MRISR_REQUIRE(g->lora_n == 0 || (g->lora_n % 16 == 0 && g->lora_n >= 16 && g->lora_n <= 64), "gemm(lora_a): lora_n must be 16, 32, 48 or 64 (0 = 64)");
   }
-  const int BN = lora ? 160 : pick_block_n(g->M, g->N, g->act, up2x ? 4 : 1);
+  SplitKPlan splitk = {1, 0};
+  if (g->splitk_ws != nullptr) {
+    splitk = plan_splitk(g->M, g->N, g->k1, g->k2, g->taps, g->act, lora, g->gn_stats != nullptr);
+    if (splitk.ksplit > 1) {
+      MRISR_REQUIRE(g->splitk_ws_floats >= static_cast<int64_t>(splitk.ksplit) * g->M * g->N && aligned16(g->splitk_ws),
+                    "gemm: splitk_ws too small (mrisr_gemm_splitk_workspace_floats) or misaligned");
+    }
+  }
+  const int BN = lora ? 160 : splitk.ksplit > 1 ? splitk.bn : pick_block_n(g->M, g->N, g->act, up2x ? 4 : 1);
   if (BN == 0) return fail(MRISR_E_UNSUPPORTED, "gemm: N = %d is not a multiple of 64", g->N);
   const int out_cols = g->act == MRISR_ACT_GEGLU ? g->N / 2 : g->N;
   MRISR_REQUIRE(g->n_store <= out_cols, "gemm: n_store (%d) > produced columns (%d)", g->n_store, out_cols);
@@ -823,6 +869,26 @@ int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
   p.lora_n = lora ? (g->lora_n ? g->lora_n : 64) : 64;
   p.lora_t_out = lora ? g->lora_t_out : nullptr;
   p.gn_part = nullptr; p.ld_part = 0; p.part_phase_stride = 0;
+  p.ksplit = 1;
+  if (splitk.ksplit > 1) {
+    // every K slice of a tile writes its raw fp32 accumulator to ws[slice][M][N]; the reduce kernel finishes the tile
+    p.ksplit = splitk.ksplit;
+    p.bias = nullptr; p.rowvec = nullptr; p.act = MRISR_ACT_NONE; p.res1 = nullptr; p.res2 = nullptr;
+    p.out = g->splitk_ws; p.ldo = g->N; p.out_fp32 = 1; p.f16_out = 0; p.n_store = g->N;
+    cudaStream_t st = as_stream(stream);
+    if (int e = dispatch_gemm<true>(BN, maps, p, st)) return e;
+    mrisr::SplitKReduceArgs r;
+    r.ws = static_cast<const float*>(g->splitk_ws); r.ldw = g->N; r.ksplit = splitk.ksplit; r.M = g->M; r.n_store = g->n_store;
+    r.bias = g->bias; r.rowvec = g->rowvec; r.rowvec_stride = g->rowvec_stride; r.rows_per_batch = g->rows_per_batch > 0 ? g->rows_per_batch : 1;
+    r.act = g->act;
+    r.res1 = static_cast<const __nv_bfloat16*>(g->res1); r.ldr1 = g->ldr1; r.res2 = static_cast<const __nv_bfloat16*>(g->res2); r.ldr2 = g->ldr2;
+    r.out = g->out; r.ldo = g->ldo; r.out_fp32 = g->out_fp32;
+    r.f16_out = (g->f16_flags & MRISR_F16_OUT) ? 1 : 0; r.f16_r1 = (g->f16_flags & MRISR_F16_RES1) ? 1 : 0; r.f16_r2 = (g->f16_flags & MRISR_F16_RES2) ? 1 : 0;
+    const long long total = static_cast<long long>(g->M) * ((g->n_store + 3) / 4);
+    launch_k(mrisr::gemm_splitk_reduce_kernel, dim3(grid_for(total, 256, 1)), dim3(256), 0, st, r);
+    MRISR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
 
   // Residuals of activation-free GEMMs become extra A operands against the identity tile (see gemm_tcgen05.cuh): the
   // epilogue then has no residual traffic at all.  MRISR_GEMM_RES_EPILOGUE=1 keeps them in the epilogue (A/B runs).

@@ -191,6 +191,15 @@ def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[T
     g.lora_a = _ptr(lora_a)
     g.lora_n = int(lora_n) if lora_a is not None else 0
     g.lora_t_out = _ptr(lora_t_out) if lora_a is not None else None
+    # small-M deep-K problems run split-K (see mrisr_gemm_splitk_workspace_floats); it wins over producer-side GroupNorm statistics,
+    # which the small levels' single-pass norm does not use anyway
+    splitk_ws = None
+    if M <= 1024 and not up2x:
+        nws = lib.mrisr_gemm_splitk_workspace_floats(M, N, k1, k2, taps, act, int(lora_a is not None), 0)
+        if nws > 0:
+            splitk_ws = torch.empty((nws,), device=a1.device, dtype=torch.float32)
+            g.splitk_ws, g.splitk_ws_floats = splitk_ws.data_ptr(), nws
+            gn_stats = False
     part = None
     if gn_stats and not _NO_GN_STATS:
         if M % 128 or out_fp32 or n_store != N:
@@ -198,7 +207,7 @@ def gemm(a1: Tensor, w: Tensor, *, a2: Optional[Tensor] = None, bias: Optional[T
         part = torch.empty(((4 if up2x else 1) * (M // 128), N, 2), device=a1.device, dtype=torch.float32)
         g.gn_stats, g.ld_stats = part.data_ptr(), N
     _launch("conv3x3" if taps == 9 else "gemm", 2.0 * M * N * (taps * (k1 + k2) + (lora_n if kext else 0)) + 2.0 * M * (lora_n if kext else 0) * k1, a1,
-            lambda: lib.mrisr_gemm(C.byref(g), _stream(a1)), "mrisr_gemm",
+            lambda: lib.mrisr_gemm(C.byref(g), _stream(a1)), "mrisr_gemm", kernels=2 if splitk_ws is not None else 1,
             detail=(M, N, taps * (k1 + k2), act, res1 is not None))
     if part is not None:
         out._gn_part = (part, 4 if up2x else 1, M // 128)      # (partials, sub-pixel phases, 128-row blocks per phase)

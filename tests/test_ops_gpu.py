@@ -613,3 +613,45 @@ def test_gemm_lora_fused_saves_t_and_takes_f16(ops, f16):
     assert _rel(t[:, :16], t_ref[:, :16]) < 4e-3 and float(t[:, 16:].float().abs().max()) == 0.0
     ref = x.float() @ w_ext[:, :K].float().t() + t.float() @ w_ext[:, K:].float().t()
     assert _rel(out, ref) < 4e-3
+
+
+@pytest.mark.parametrize("B,H,C1,C2,N,act,f16", [(2, 8, 1280, 0, 1280, "none", False), (2, 16, 1280, 1280, 1280, "silu", False),
+                                                   (2, 8, 1280, 1280, 1280, "none", True), (1, 16, 1280, 0, 320, "relu", True),
+                                                   (4, 16, 1280, 1280, 1280, "none", False)])
+def test_conv3x3_split_k(ops, B, H, C1, C2, N, act, f16):
+    """Small-M deep-K convs (the 8x8 level and the concatenated-input convs of the 16x16 level at batch <= 4) take the split-K form: K slices on different CTA pairs, fp32
+    partial tiles, fixed-order reduce with bias / time-embedding row / activation / residual.  Same answer as the reference conv,
+    bit-identical run to run."""
+    from mri_diffusion_superresolution_b200 import _lib
+    from mri_diffusion_superresolution_b200.packing import pack_conv3x3
+    mk = _h16 if f16 else (lambda s, seed, scale=1.0: _bf(s, seed, scale))
+    M = B * H * H
+    assert _lib.load().mrisr_gemm_splitk_workspace_floats(M, N, C1, C2, 9, {"none": 0, "relu": 1, "silu": 2}[act], 0, 0) > 0
+    x1 = mk((B, H, H, C1), 91).cuda()
+    x2 = mk((B, H, H, C2), 92).cuda() if C2 else None
+    cin = C1 + C2
+    w = mk((N, cin, 3, 3), 93, 1.0 / math.sqrt(9 * cin)).cuda()
+    bias = _f32((N,), 94)
+    temb = _f32((B, N), 95)
+    res = mk((M, N), 96).cuda()
+    kw = dict(a2=x2, bias=bias, rowvec=temb, rowvec_stride=N, rows_per_batch=H * H, act={"none": ops.ACT_NONE, "relu": ops.ACT_RELU, "silu": ops.ACT_SILU}[act],
+              res1=res, conv=True, out_dtype=torch.float16 if f16 else torch.bfloat16)
+    out = ops.gemm(x1, pack_conv3x3(w), **kw)
+    xin = x1 if x2 is None else torch.cat([x1, x2], -1)
+    ref = F.conv2d(xin.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(B, H * H, N) + temb[:, None, :]
+    ref = {"none": lambda t: t, "relu": F.relu, "silu": F.silu}[act](ref).reshape(M, N) + res.float()
+    assert _rel(out, ref) < (1e-3 if f16 else 4e-3)
+    assert torch.equal(out, ops.gemm(x1, pack_conv3x3(w), **kw))
+
+
+def test_gemm_split_k_plain_and_ragged_store(ops):
+    """Plain small-M GEMM (154 rows x K = 10240) through split-K with an fp32 output and a partial n_store."""
+    from mri_diffusion_superresolution_b200 import _lib
+    M, N, K = 154, 1280, 10240
+    assert _lib.load().mrisr_gemm_splitk_workspace_floats(M, N, K, 0, 1, 0, 0, 0) > 0
+    a, w = _bf((M, K), 97), _bf((N, K), 98, 1.0 / math.sqrt(K))
+    ref = a.float() @ w.float().t()
+    out = ops.gemm(a, w, out_fp32=True)
+    assert out.dtype == torch.float32 and _rel(out, ref) < 1e-5
+    out2 = ops.gemm(a, w, n_store=1000)
+    assert tuple(out2.shape) == (M, 1000) and _rel(out2, ref[:, :1000]) < 4e-3
