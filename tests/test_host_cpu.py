@@ -228,6 +228,8 @@ def test_no_cpu_path_widened_rows():
         volume_to_slices(torch.zeros(4, 4, 4), 0.0, 1.0)
     with pytest.raises(RuntimeError):
         mnist.forward_pass(torch.zeros(1, 1, 28, 28), 3, torch.zeros(1, 1, 28, 28))
+    with pytest.raises(RuntimeError):
+        mnist.DiffusionSupResModel(mnist.init_params(0), device="cpu")
     vae = AutoencoderKLB200(VAEConfig(block_out_channels=(64, 128), layers_per_block=1), device="cpu")
     with pytest.raises(RuntimeError):
         vae.decode(torch.zeros(1, 4, 8, 8))                       # weights not loaded
@@ -283,3 +285,26 @@ def test_dgrad_filter_packing_matches_autograd():
     assert (got - x.grad).abs().max().item() < 1e-5
     wp = _dgrad3x3(w.float(), pad_cout_to=8)
     assert wp.shape == (ci, 9 * 8) and float(wp.view(ci, 9, 8)[:, :, co:].abs().max()) == 0.0
+
+
+def test_mnist_model_oracle_follows_the_notebook_skeleton():
+    """oracle/mnist_oracle.model_forward: the notebook's channel plan / skip wiring (:163-208) with the documented fill-ins --
+    shapes, the state-dict layout shared with the product, and that timestep, class label and the low-resolution channel all matter."""
+    from oracle import mnist_oracle as mo
+    from mri_diffusion_superresolution_b200 import mnist
+    shapes = mnist.param_shapes()
+    assert shapes["downs.3.conv1.weight"] == (1024, 512, 3, 3) and shapes["ups.0.conv1.weight"] == (512, 2048, 3, 3)     # cat(x, skip)
+    assert shapes["ups.3.transform.weight"] == (64, 64, 3, 3) and shapes["output.weight"] == (1, 64, 1, 1)
+    assert shapes["time_mlp.1.weight"] == (32, 32) and shapes["class_emb.weight"] == (10, 32)
+    params = mnist.init_params(seed=1)
+    assert sorted(params) == sorted(shapes) and all(tuple(params[k].shape) == shapes[k] for k in shapes)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 2, 28, 28, generator=g)
+    t, y = torch.tensor([10, 800]), torch.tensor([3, 5])
+    out = mo.model_forward(params, x, t, y)
+    assert tuple(out.shape) == (2, 1, 28, 28) and torch.isfinite(out).all() and 0.05 < float(out.std()) < 20
+    assert not torch.allclose(out, mo.model_forward(params, x, torch.tensor([11, 700]), y), atol=1e-4)
+    assert not torch.allclose(out, mo.model_forward(params, x, t, torch.tensor([4, 5])), atol=1e-4)
+    x2 = x.clone(); x2[:, 1] = 0
+    assert not torch.allclose(out, mo.model_forward(params, x2, t, y), atol=1e-4)
+    torch.testing.assert_close(mo.sinusoidal(torch.tensor([0, 5]))[0], torch.cat([torch.zeros(16), torch.ones(16)]))

@@ -376,3 +376,44 @@ def test_mnist_ddpm_sampling_loop_vs_oracle():
     sch.set_timesteps(1000)
     _, book = sch.step_table("ddpm")
     assert [b[0] for b in book] == list(range(999, -1, -1)) and [b[2] for b in book] == [True] * 999 + [False]    # bookkeeping exact
+
+
+def test_mnist_model_vs_oracle_and_short_sampling_chain():
+    """BASELINE config 1, the model: the notebook's DiffusionSupResModel skeleton (undefined pieces filled in as mnist.py documents)
+    on the tensor-core convs vs its fp32 restatement (oracle/mnist_oracle.py, unpinned), then a 25-step DDPM chain conditioned on
+    14x14 low-resolution digits through both."""
+    from oracle import mnist_oracle as mo
+    from mri_diffusion_superresolution_b200 import mnist
+    params = mnist.init_params(seed=3)
+    model = mnist.DiffusionSupResModel(params)
+    g = torch.Generator().manual_seed(9)
+    B = 3
+    x = torch.randn(B, 2, 28, 28, generator=g)
+    t = torch.tensor([999, 500, 3])
+    y = torch.tensor([7, 0, 9])
+    want = mo.model_forward(params, x, t, y)
+    got = model(x.cuda(), t.cuda(), y.cuda())
+    assert tuple(got.shape) == (B, 1, 28, 28) and got.dtype == torch.float32
+    print(f"mnist model eps rel-L2 {_rel(got, want):.2e}")
+    assert _rel(got, want) < REL_L2_BF16
+    # the class label and the timestep both reach the output
+    assert _rel(model(x.cuda(), t.cuda(), torch.tensor([1, 2, 3]).cuda()), want) > 5 * _rel(got, want)
+    assert _rel(model(x.cuda(), torch.tensor([10, 900, 400]).cuda(), y.cuda()), want) > 5 * _rel(got, want)
+    # 25-step ancestral chain (trailing spacing) with injected noise: CUDA model + fused step kernel vs fp32 model + fp64 updates
+    lr = torch.rand(2, 1, 14, 14, generator=g) * 2 - 1
+    yy = torch.tensor([4, 8])
+    steps = 25
+    noises = torch.randn(steps + 1, 2, 1, 28, 28, generator=g)
+    got = mnist.sample(model.eps_model(lr.cuda(), yy.cuda()), (2, 1, 28, 28), num_steps=steps, noises=noises.cuda())
+    up = torch.nn.functional.interpolate(lr, size=(28, 28), mode="bilinear", align_corners=False)
+    sch = mnist.make_scheduler()
+    sch.config.timestep_spacing = "trailing"
+    sch.set_timesteps(steps)
+    coef, book = sch.step_table("ddpm")
+    xo = noises[0].double()
+    for i, (tt, _, flag) in enumerate(book):
+        eps = mo.model_forward(params, torch.cat([xo.float(), up], 1), torch.full((2,), tt), yy).double()
+        c = [float(v) for v in coef[i]]
+        xo = c[0] * xo + c[1] * eps + (c[3] * noises[i + 1].double() if flag else 0.0)
+    print(f"mnist 25-step chain rel-L2 {_rel(got, xo.float()):.2e}")
+    assert torch.isfinite(got).all() and _rel(got, xo.float()) < 3e-2
