@@ -99,6 +99,12 @@ constexpr int kEpilogueThreads = 256;
 // kPair: a cluster of two CTAs on one TPC computes a 256 x BN tile with cta_group::2 MMAs; each CTA stages its own 128
 // rows of A and HALF of the W tile, so every SM pulls 16 KB + BN*64 B per k-chunk from L2 instead of 16 KB + BN*128 B
 // (the round-1 profile showed the single-CTA kernel bound by L2->SM operand delivery).
+// Staging buffers per epilogue warp.  A ring of 4 (more TMA stores in flight) measured no different from 2 on the store-heavy small-K
+// GEMMs (M = 131072, N = 960, K = 320: 130 us either way -- dbg bits 4 / 32 / 64 show the time is in the pack + st.shared + fence sequence,
+// not in the stores), and it costs a pipeline stage: 2.
+#ifndef MRISR_EPI_BUFS
+#define MRISR_EPI_BUFS 2
+#endif
 constexpr int kLoraN = 64;   // rows of the stacked LoRA A matrices == width of the K extension
 template <int BN, bool kPair, bool kLora = false>
 struct GemmCfg {
@@ -111,7 +117,8 @@ struct GemmCfg {
   static constexpr int kTBytes = kLora ? kBlockM * kLoraN * 2 : 0;   // T = x A^T rounded to bf16, as a 128 x 64 SW128 A tile
   static constexpr int kStageBytes = kABytes + kBBytes + kB2Bytes;
   static_assert(!kLora || (kBBytes % 1024 == 0 && kStageBytes % 1024 == 0), "swizzled tiles must stay 1024-byte aligned");
-  static constexpr int kEpiBytes = 8 * 4096;     // per-epilogue-warp: two 32x32 bf16 staging buffers (TMA store double buffer)
+  static constexpr int kEpiBufs = kPair ? MRISR_EPI_BUFS : 2;   // staging buffers per epilogue warp (the single-CTA A/B kernel keeps 2)
+  static constexpr int kEpiBytes = 8 * kEpiBufs * 2048;   // per-epilogue-warp: kEpiBufs 32x32 16-bit staging buffers (ring of TMA stores in flight)
   static constexpr int kBiasBytes = 8 * BN * 4;  // epilogue-staged bias, one slab per epilogue warp
   static constexpr int kBarBytes = 256;          // <= 2*8+4 mbarriers + the TMEM base slot + 6 statistics counters
   // GroupNorm-statistics staging: ring of 3 tiles x 4 lane-quarter warps x BN columns x (sum, sumsq).  Ring depth 3: the
@@ -235,7 +242,7 @@ __device__ __forceinline__ void gemm_chunk_col_stats(const uint8_t* buf, int lan
 // the warp's two 2 KB staging buffers in the TMA 64B-swizzle pattern (16-byte slot ^= (row >> 1) & 3: conflict-free
 // 128-bit writes) and stored by ONE cp.async.bulk.tensor issued by lane 0 -- ~4x fewer instructions per chunk than
 // transposing through shared memory and storing with per-row pointers, and rows >= M are clipped by the TMA unit.
-template <int BN, bool kGeglu, typename Release>
+template <int BN, bool kGeglu, int kEpiBufs, typename Release>
 __device__ __forceinline__ void gemm_epilogue_tma(const GemmKernelParams& p, const CUtensorMap* tm_out, uint32_t t_row, int m,
                                                   int n_blk, int half, const float* sbias, uint8_t* stage_buf,
                                                   uint32_t& buf_sel, Release release, const GemmStatCtx& st) {
@@ -298,9 +305,9 @@ __device__ __forceinline__ void gemm_epilogue_tma(const GemmKernelParams& p, con
         }
       }
       if (!(p.dbg & 4)) {
-        uint8_t* buf = stage_buf + (buf_sel & 1u) * 2048;
-        buf_sel ^= 1u;
-        if (lane_id == 0) bulk_wait_group_read<1>();  // the store that last read THIS buffer has drained it
+        uint8_t* buf = stage_buf + (buf_sel % kEpiBufs) * 2048;
+        ++buf_sel;
+        if (lane_id == 0) bulk_wait_group_read<kEpiBufs - 1>();  // the store that last read THIS buffer has drained it
         __syncwarp();
         uint8_t* dst = buf + lane_id * 64;
         if (p.f16_out) {
@@ -316,9 +323,9 @@ __device__ __forceinline__ void gemm_epilogue_tma(const GemmKernelParams& p, con
                 make_uint4(pack_bf16(f[8 * u], f[8 * u + 1]), pack_bf16(f[8 * u + 2], f[8 * u + 3]),
                            pack_bf16(f[8 * u + 4], f[8 * u + 5]), pack_bf16(f[8 * u + 6], f[8 * u + 7]));
         }
-        fence_proxy_async_smem();
+        if (!(p.dbg & 64)) fence_proxy_async_smem();
         __syncwarp();
-        if (lane_id == 0 && m_warp0 < p.M) {
+        if (lane_id == 0 && m_warp0 < p.M && !(p.dbg & 32)) {   // (dbg 32: stage but never store -- timing experiments)
           if (p.up2x) tma_store_4d(tm_out, smem_u32(buf), n_o0 + c * 32, up_x, up_y, up_b);
           else tma_store_2d(tm_out, smem_u32(buf), n_o0 + c * 32, m_warp0);
           bulk_commit_group();
@@ -714,7 +721,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     const int half = (warp - 4) >> 2;
     float* sbias = sbias_base + (warp - 4) * BN;
-    uint8_t* stage_buf = sepi_base + (warp - 4) * 4096;
+    uint8_t* stage_buf = sepi_base + (warp - 4) * (Cfg::kEpiBufs * 2048);
     uint32_t buf_sel = 0;
     uint32_t it = 0;
     grid_dep_wait();  // the previous kernel may still read the buffer this one overwrites
@@ -773,9 +780,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
       if (p.tma_store && (n_blk + 1) * out_cols <= p.n_store && (BN % 64 == 0 || p.act != ACT_GEGLU)) {
         if (p.act == ACT_GEGLU) {
           if constexpr (BN % 64 == 0)
-            gemm_epilogue_tma<BN, true>(p, &maps.out[0], t_row, m, n_blk, half, sbias, stage_buf, buf_sel, release, st);
+            gemm_epilogue_tma<BN, true, Cfg::kEpiBufs>(p, &maps.out[0], t_row, m, n_blk, half, sbias, stage_buf, buf_sel, release, st);
         } else {
-          gemm_epilogue_tma<BN, false>(p, &maps.out[ph], t_row, m, n_blk, half, sbias, stage_buf, buf_sel, release, st);
+          gemm_epilogue_tma<BN, false, Cfg::kEpiBufs>(p, &maps.out[ph], t_row, m, n_blk, half, sbias, stage_buf, buf_sel, release, st);
         }
       } else {
         gemm_epilogue_rows<BN>(p, t_row, m, n_blk, half, sbias, stage_buf, ksplit > 1 ? static_cast<long long>(tile - t2 * ksplit) * p.M : 0ll);
