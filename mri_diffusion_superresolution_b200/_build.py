@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmrisr_b200.so")
 SOURCES = ["mrisr_abi.cu"]
-DEPS = ["mrisr_abi.cu", "ptx.cuh", "gemm_tcgen05.cuh", "attention.cuh", "attention_tcgen05.cuh", "pointwise.cuh", "metrics.cuh",
+DEPS = ["mrisr_abi.cu", "ptx.cuh", "train.cuh", "gemm_tcgen05.cuh", "attention.cuh", "attention_tcgen05.cuh", "pointwise.cuh", "metrics.cuh",
         os.path.join("..", "..", "include", "mrisr_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--cudart", "shared"]

@@ -242,6 +242,13 @@ __device__ __forceinline__ void gemm_chunk_col_stats(const uint8_t* buf, int lan
 // the warp's two 2 KB staging buffers in the TMA 64B-swizzle pattern (16-byte slot ^= (row >> 1) & 3: conflict-free
 // 128-bit writes) and stored by ONE cp.async.bulk.tensor issued by lane 0 -- ~4x fewer instructions per chunk than
 // transposing through shared memory and storing with per-row pointers, and rows >= M are clipped by the TMA unit.
+#ifdef MRISR_GEMM_TIMELINE
+__device__ long long g_gtl[16];
+__device__ int g_gtl_n;
+#define GTLF(k) do { if (blockIdx.x == 0 && (threadIdx.x >> 5) == 9 && (threadIdx.x & 31) == 0 && g_gtl_n == 5) g_gtl[k] = clock64(); } while (0)
+#else
+#define GTLF(k) do { } while (0)
+#endif
 template <int BN, bool kGeglu, int kEpiBufs, typename Release>
 __device__ __forceinline__ void gemm_epilogue_tma(const GemmKernelParams& p, const CUtensorMap* tm_out, uint32_t t_row, int m,
                                                   int n_blk, int half, const float* sbias, uint8_t* stage_buf,
@@ -252,15 +259,37 @@ __device__ __forceinline__ void gemm_epilogue_tma(const GemmKernelParams& p, con
   const int lane_id = threadIdx.x & 31;
   const int c_begin = half == 0 ? 0 : kMaxC;
   const int nc = half == 0 ? kMaxC : kChunks - kMaxC;
-  uint32_t v[kMaxC][32];
-  uint32_t g[kGeglu ? kMaxC : 1][32];
+  // TMEM reads are a shared 64 B/clk port per SM (a 128 x 160 fp32 tile = 1280 clk for the 8 epilogue warps together).  On the
+  // store-heavy small-K GEMMs (5 k-chunks per tile) the epilogue, not the MMA, paces the tile loop: ~3800 clk per tile per warp
+  // (MRISR_GEMM_TIMELINE: ~130 clk load wait, then per chunk ~700 arithmetic, ~250 buffer wait, ~330 pack + st.shared, ~180 fence,
+  // ~500 store issue -- a latency chain of ~150-200 instructions per chunk on 2 warps per scheduler).  -DMRISR_EPI_PIPELINED runs the
+  // loads one chunk ahead of the arithmetic: M = 131072, N = 960, K = 320 128 -> 122 us, but the 50-step loop LOSES 0.9 %
+  // (19.83 -> 19.65 slices/s, same box, alternated): the deep-K convs want the accumulator stage handed back early.  Default: off.
+#ifndef MRISR_EPI_PIPELINED   // default: every load issued and awaited before any arithmetic, accumulator released at once
+  constexpr int kV = kMaxC;
+#define MRISR_EPI_SLOT(ci) (ci)
+  uint32_t v[kV][32];
+  uint32_t g[kGeglu ? kV : 1][32];
 #pragma unroll
   for (int ci = 0; ci < kMaxC; ++ci) {
     if (ci < nc) {
       tmem_ld_32x32(t_row + (c_begin + ci) * 32, v[ci]);
-      if (kGeglu) tmem_ld_32x32(t_row + kOutCols + (c_begin + ci) * 32, g[ci]);
+      if (kGeglu) tmem_ld_32x32(t_row + kOutCols + (c_begin + ci) * 32, g[kGeglu ? ci : 0]);
     }
   }
+  tmem_ld_wait();
+  release();
+#else
+#define MRISR_EPI_SLOT(ci) ((ci) & 1)
+  uint32_t v[2][32];
+  uint32_t g[kGeglu ? 2 : 1][32];
+  if (nc > 0) {
+    tmem_ld_32x32(t_row + c_begin * 32, v[0]);
+    if (kGeglu) tmem_ld_32x32(t_row + kOutCols + c_begin * 32, g[0]);
+  } else {
+    release();   // (a one-chunk tile: the second warp of the lane quarter has nothing to read)
+  }
+#endif
   const bool row_ok = m < p.M;
   const float* rv = nullptr;
   if (!kGeglu && p.rowvec != nullptr && row_ok)
@@ -277,20 +306,29 @@ __device__ __forceinline__ void gemm_epilogue_tma(const GemmKernelParams& p, con
     up_y = rem / p.W;
     up_x = rem - up_y * p.W;
   }
-  tmem_ld_wait();
-  release();
 #pragma unroll
   for (int ci = 0; ci < kMaxC; ++ci) {
     if (ci < nc) {
       const int c = c_begin + ci;
+      GTLF(ci * 6 + 0);
+#ifdef MRISR_EPI_PIPELINED
+      tmem_ld_wait();   // chunk ci is in registers
+      GTLF(ci * 6 + 1);
+      if (ci + 1 < nc) {   // next chunk in flight under this chunk's arithmetic
+        tmem_ld_32x32(t_row + (c + 1) * 32, v[(ci + 1) & 1]);
+        if (kGeglu) tmem_ld_32x32(t_row + kOutCols + (c + 1) * 32, g[kGeglu ? ((ci + 1) & 1) : 0]);
+      } else {
+        release();         // the whole accumulator has been read: hand the stage back to the MMA warp
+      }
+#endif
       float f[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[ci][j]);
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[MRISR_EPI_SLOT(ci)][j]);
       add_smem32(f, sbias + c * 32);
       if (kGeglu) {
         float gg[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) gg[j] = __uint_as_float(g[ci][j]);
+        for (int j = 0; j < 32; ++j) gg[j] = __uint_as_float(g[kGeglu ? MRISR_EPI_SLOT(ci) : 0][j]);
         add_smem32(gg, sbias + kOutCols + c * 32);
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] *= act_gelu_erf(gg[j]);
@@ -307,8 +345,10 @@ __device__ __forceinline__ void gemm_epilogue_tma(const GemmKernelParams& p, con
       if (!(p.dbg & 4)) {
         uint8_t* buf = stage_buf + (buf_sel % kEpiBufs) * 2048;
         ++buf_sel;
+        GTLF(ci * 6 + 2);
         if (lane_id == 0) bulk_wait_group_read<kEpiBufs - 1>();  // the store that last read THIS buffer has drained it
         __syncwarp();
+        GTLF(ci * 6 + 3);
         uint8_t* dst = buf + lane_id * 64;
         if (p.f16_out) {
 #pragma unroll
@@ -323,8 +363,10 @@ __device__ __forceinline__ void gemm_epilogue_tma(const GemmKernelParams& p, con
                 make_uint4(pack_bf16(f[8 * u], f[8 * u + 1]), pack_bf16(f[8 * u + 2], f[8 * u + 3]),
                            pack_bf16(f[8 * u + 4], f[8 * u + 5]), pack_bf16(f[8 * u + 6], f[8 * u + 7]));
         }
+        GTLF(ci * 6 + 4);
         if (!(p.dbg & 64)) fence_proxy_async_smem();
         __syncwarp();
+        GTLF(ci * 6 + 5);
         if (lane_id == 0 && m_warp0 < p.M && !(p.dbg & 32)) {   // (dbg 32: stage but never store -- timing experiments)
           if (p.up2x) tma_store_4d(tm_out, smem_u32(buf), n_o0 + c * 32, up_x, up_y, up_b);
           else tma_store_2d(tm_out, smem_u32(buf), n_o0 + c * 32, m_warp0);
@@ -650,7 +692,15 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
         const int rcount = res_count(t2 % p.n_tiles);
         const int kmain_t = ksplit > 1 ? min(kmain, (tile - t2 * ksplit + 1) * kper) - (tile - t2 * ksplit) * kper : kmain;   // this K slice
         const int kiters = kmain_t + p.res_mma * rcount;
+#ifdef MRISR_GEMM_TIMELINE
+        long long m0c = 0, m1c = 0, m2c = 0;
+        const bool mtl = blockIdx.x == 0 && it >= 4 && it < 8;
+        if (mtl) m0c = clock64();
+#endif
         mbar_wait(tempty_bar(as), aph ^ 1u);
+#ifdef MRISR_GEMM_TIMELINE
+        if (mtl) m1c = clock64();
+#endif
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         const uint32_t t_tmem = tmem_base + 2 * BN + as * kLoraN;   // kLora: T = x A^T accumulator of this stage
@@ -692,7 +742,13 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
           }
           __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
+#ifdef MRISR_GEMM_TIMELINE
+          if (mtl && ki == 0) m2c = clock64();
+#endif
         }
+#ifdef MRISR_GEMM_TIMELINE
+        (void)m0c; (void)m1c; (void)m2c;
+#endif
         if (kLora) {
           // K extension: A = the bf16 T tile the epilogue warps staged (both CTAs of a pair), B = the (s B) columns of this N tile
           mbar_wait(tT_ready(as), aph);
@@ -725,7 +781,15 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
     uint32_t buf_sel = 0;
     uint32_t it = 0;
     grid_dep_wait();  // the previous kernel may still read the buffer this one overwrites
+#ifdef MRISR_GEMM_TIMELINE
+    long long tl[4][4];
+    const bool tl_on = blockIdx.x == 0 && lane == 0 && (warp == 4 || warp == 9);
+#define GTL(k) do { if (tl_on && it >= 4 && it < 8) tl[it - 4][k] = clock64(); } while (0)
+#else
+#define GTL(k) do { } while (0)
+#endif
     for (int tile = worker; tile < total_tiles; tile += num_workers, ++it) {
+      GTL(0);
       const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
       const int t2 = ksplit > 1 ? tile / ksplit : tile;
       const int n_blk = t2 % p.n_tiles;
@@ -740,6 +804,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
       st.block = static_cast<long long>(ph) * p.part_phase_stride + m_tile * (kPair ? 2 : 1) + rank;
       __syncwarp();  // every lane finished reading the previous tile's slab
       gemm_stage_bias<BN>(p, sbias, n_blk, lane);
+      GTL(1);
       if (kLora) {
         // round this thread's row of T = x A^T (its 32 of the 64 columns) to bf16 into the SW128 A tile of the K extension
         mbar_wait(tT_full(as), aph);
@@ -771,6 +836,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
         if (kPair) mbar_arrive_leader(tT_ready(as)); else mbar_arrive(tT_ready(as));
       }
       mbar_wait(tfull_bar(as), aph);
+      GTL(2);
       tcgen05_fence_after();
       auto release = [&]() {
         tcgen05_fence_before();
@@ -788,7 +854,23 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
         gemm_epilogue_rows<BN>(p, t_row, m, n_blk, half, sbias, stage_buf, ksplit > 1 ? static_cast<long long>(tile - t2 * ksplit) * p.M : 0ll);
         release();
       }
+      GTL(3);
+#ifdef MRISR_GEMM_TIMELINE
+      if (blockIdx.x == 0 && warp == 9 && lane == 0) {
+        if (g_gtl_n == 5)
+          printf("GTLF warp 9 tile 5: c0: ldwait +%lld | arith +%lld | wait_read +%lld | pack+sts +%lld | fence +%lld || c1: start +%lld | ldwait +%lld | arith +%lld | wait_read +%lld | pack+sts +%lld | fence +%lld | end +%lld\n",
+                 g_gtl[1] - g_gtl[0], g_gtl[2] - g_gtl[1], g_gtl[3] - g_gtl[2], g_gtl[4] - g_gtl[3], g_gtl[5] - g_gtl[4], g_gtl[6] - g_gtl[5],
+                 g_gtl[7] - g_gtl[6], g_gtl[8] - g_gtl[7], g_gtl[9] - g_gtl[8], g_gtl[10] - g_gtl[9], g_gtl[11] - g_gtl[10], clock64() - g_gtl[11]);
+        g_gtl_n = g_gtl_n + 1;
+      }
+#endif
     }
+#ifdef MRISR_GEMM_TIMELINE
+    if (tl_on && it >= 8 && warp == 9)
+      for (int t = 0; t < 2; ++t)
+        printf("GTL epi warp %2d tile %d: start %8lld | bias +%5lld | tfull wait +%5lld | epilogue +%5lld | next start +%5lld\n", warp, t + 4, tl[t][0] % 100000000,
+               tl[t][1] - tl[t][0], tl[t][2] - tl[t][1], tl[t][3] - tl[t][2], t < 3 ? tl[t + 1][0] - tl[t][0] : 0ll);
+#endif
     if (lane == 0) bulk_wait_group_read<0>();  // staging buffers must outlive the last TMA store's reads
   }
 
