@@ -276,11 +276,18 @@ int mrisr_xty64(const void* X, int64_t ldx, int x_f16, const void* Y, int64_t ld
 /* Backward of mrisr_attention (flash-style, P is recomputed): q/k/v/o bf16 as in the forward call, dq / dk / dv half, d_o bf16
  * (d_o_f16 = 0: every streamed tile is a cp.async copy) or half (rounded to bf16 on load);
  * stats_ws >= mrisr_attention_backward_workspace(...) floats: row log-sum-exp and rowsum(dO*O) (recomputed here) and, when the
- * key count is small (cross attention), the fp32 partial dK / dV of the query-range splits.  d in {8,16,40,80,160}. */
+ * key count is small (cross attention), the fp32 partial dK / dV of the query-range splits.  d in {8,16,40,80,160}.
+ * have_lse != 0: the first batch*heads*nq floats of stats_ws already hold the row log-sum-exp written by mrisr_attention_lse
+ * in the forward pass, and the dQ kernel skips its recomputation sweep over the keys. */
 int64_t mrisr_attention_backward_workspace(int batch, int nq, int nk, int heads, int d);
+/* mrisr_attention (no K/V broadcast) that also writes lse[batch*heads*nq] = row log-sum-exp of the scaled scores, log2 domain -- only
+ * for the shapes that run on the tcgen05 kernels (mrisr_attention_exports_lse(d, nk, ldo) == 1); MRISR_E_UNSUPPORTED otherwise. */
+int mrisr_attention_exports_lse(int d, int nk, int64_t ldo);
+int mrisr_attention_lse(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
+                        float* lse, int batch, int nq, int nk, int heads, int d, void* stream);
 int mrisr_attention_backward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o, int64_t ldo,
                              const void* d_o, int64_t lddo, int d_o_f16, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
-                             float* stats_ws, int batch, int nq, int nk, int heads, int d, void* stream);
+                             float* stats_ws, int have_lse, int batch, int nq, int nk, int heads, int d, void* stream);
 /* One trainable tensor [rows, cols]: fp32 master p and AdamW moments m, v (dense); its gradient as a strided window
  * grad(i,j) = g[i*g_sr + j*g_sc] * g_scale of an mrisr_xty64 result; up to two packed 16-bit destinations that receive
  * p(i,j) * scale after the update (the forward GEMM's and the dgrad GEMM's operand), so no re-packing pass exists. */

@@ -97,7 +97,9 @@ PROTOTYPES = {
     "mrisr_xty64": (_I, [_P, _L, _I, _P, _L, _I, _I, _I, _F, _P, _P, _P]),
     "mrisr_gemm_splitk_workspace_floats": (_L, [_I, _I, _I, _I, _I, _I, _I, _I]),
     "mrisr_attention_backward_workspace": (_L, [_I, _I, _I, _I, _I]),
-    "mrisr_attention_backward": (_I, [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _I, _P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _P]),
+    "mrisr_attention_backward": (_I, [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _I, _P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "mrisr_attention_exports_lse": (_I, [_I, _I, _L]),
+    "mrisr_attention_lse": (_I, [_P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _I, _I, _P]),
     "mrisr_grad_sqnorm": (_I, [_P, _I, _F, _P, _P, _P]),
     "mrisr_adamw": (_I, [_P, _I, _P, _P, _F, _F, _F, _F, _P, _P]),
     "mrisr_slice_volume": (_I, [_P, _I, _I, _I, _I, _F, _F, _F, _P, _I, _I, _P]),

@@ -31,6 +31,8 @@ struct AttnTcArgs {
   int nq, nk, heads, batch;
   int kv_rows_per_batch;  // nk, or 0 when one context is shared by every batch element
   float scale_log2;       // log2(e) / sqrt(d)
+  float* lse;             // nullptr, or [batch * heads * nq]: the row log-sum-exp of the SCALED scores in the log2 domain (m + log2 l), kept by
+                          // the fine-tune step so the attention backward does not recompute it
   int lag_max;            // split kernel: from the third key tile on, decide the (lazy) rescale on the row maxima of tile j - 2 (no
                           // per-tile barrier between the two threads of a row); 0 = exchange the maxima of tile j itself
 };
@@ -373,6 +375,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_c
       tmem_ld_wait();
       if (row < a.nq) {
         const float inv = 1.f / l;
+        if (a.lse != nullptr) a.lse[(static_cast<long long>(b) * a.heads + head) * a.nq + row] = m_used + log2f(l);
         __nv_bfloat16* og = a.o + (static_cast<long long>(b) * a.nq + row) * a.ldo + head * D;
 #pragma unroll
         for (int c = 0; c < D / 8; ++c) {
@@ -717,6 +720,7 @@ attention_tcgen05_split_kernel(const __grid_constant__ CUtensorMap tmK, const __
       tmem_ld_wait();
       if (row < a.nq) {
         const float inv = 1.f / __uint_as_float(lt);
+        if (a.lse != nullptr && half == 0) a.lse[(static_cast<long long>(b) * a.heads + head) * a.nq + row] = m_used + log2f(__uint_as_float(lt));
         __nv_bfloat16* og = a.o + (static_cast<long long>(b) * a.nq + row) * a.ldo + head * D + half * HC;
 #pragma unroll
         for (int c = 0; c < HC / 8; ++c) {

@@ -236,7 +236,7 @@ int dispatch_attention_ctx(const mrisr::AttnArgs& a, cudaStream_t st) {
 // tcgen05 / TMEM attention (head dims 40, 80).  K and V are addressed through TMA maps over [rows, heads*d] views.
 template <int D>
 int launch_attention_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
-                        int64_t ldo, int batch, int nq, int nk, int heads, int kv_broadcast, cudaStream_t st) {
+                        int64_t ldo, int batch, int nq, int nk, int heads, int kv_broadcast, cudaStream_t st, float* lse = nullptr) {
   using Cfg = mrisr::AttnTcCfg<D>;
   if (int e = load_encode()) return e;
   CUtensorMap mk, mv;
@@ -259,6 +259,7 @@ int launch_attention_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, 
   a.scale_log2 = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(D)));
   static const int lag_max = getenv("MRISR_ATTN_LAGMAX") ? atoi(getenv("MRISR_ATTN_LAGMAX")) : 1;   // =0: per-tile maximum exchange (A/B runs)
   a.lag_max = lag_max;
+  a.lse = lse;
   dim3 grid((nq + mrisr::kAtcBQ - 1) / mrisr::kAtcBQ, heads, batch);
   if constexpr (D == 40) {
     // two threads per query row (16 softmax warps): see attention_tcgen05_split_kernel
@@ -370,17 +371,19 @@ void attention_backward_split(int batch, int nq, int nk, int heads, int* nsplit,
 long long attention_backward_dp(int d) { return (d + 15) / 16 * 16; }
 
 template <int D>
-int launch_attention_backward(const mrisr::AttnBwdArgs& a, cudaStream_t st) {
+int launch_attention_backward(const mrisr::AttnBwdArgs& a, bool have_lse, cudaStream_t st) {
   using Cfg = mrisr::AttnBwdCfg<D>;
   static bool configured = false;
   if (!configured) {
-    MRISR_CHECK_CUDA(cudaFuncSetAttribute(mrisr::attention_bwd_dq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    MRISR_CHECK_CUDA(cudaFuncSetAttribute(mrisr::attention_bwd_dq_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    MRISR_CHECK_CUDA(cudaFuncSetAttribute(mrisr::attention_bwd_dq_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     MRISR_CHECK_CUDA(cudaFuncSetAttribute(mrisr::attention_bwd_dkdv_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     MRISR_CHECK_CUDA(cudaFuncSetAttribute(mrisr::attention_bwd_dkdv_kernel<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     MRISR_CHECK_CUDA(cudaFuncSetAttribute(mrisr::attention_bwd_dkdv_kernel<D, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
-  launch_k(mrisr::attention_bwd_dq_kernel<D>, dim3((a.nq + 63) / 64, a.heads, a.batch), dim3(mrisr::kAbThreads), Cfg::kSmemBytes, st, a);
+  if (have_lse) launch_k(mrisr::attention_bwd_dq_kernel<D, true>, dim3((a.nq + 63) / 64, a.heads, a.batch), dim3(mrisr::kAbThreads), Cfg::kSmemBytes, st, a);
+  else launch_k(mrisr::attention_bwd_dq_kernel<D, false>, dim3((a.nq + 63) / 64, a.heads, a.batch), dim3(mrisr::kAbThreads), Cfg::kSmemBytes, st, a);
   MRISR_CHECK_CUDA(cudaGetLastError());
   const dim3 gk((a.nk + 63) / 64 * a.nsplit, a.heads, a.batch);
   if (D > 80) {   // the dK and dV accumulators do not fit the register file together: two sweeps
@@ -963,6 +966,24 @@ int mrisr_gemm(const mrisr_gemm_args* g, void* stream) {
   return pair ? dispatch_gemm<true>(BN, maps, p, st) : dispatch_gemm<false>(BN, maps, p, st);
 }
 
+// the shapes whose forward pass runs on the tcgen05 kernels (which can hand the row log-sum-exp to the backward pass)
+static bool attention_takes_tc(int d, int nk, int64_t ldo) { return use_tc_attention() && (d == 40 || d == 80) && nk >= 128 && ldo % 8 == 0; }
+
+int mrisr_attention_exports_lse(int d, int nk, int64_t ldo) { return attention_takes_tc(d, nk, ldo) ? 1 : 0; }
+
+int mrisr_attention_lse(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
+                        float* lse, int batch, int nq, int nk, int heads, int d, void* stream) {
+  MRISR_ONE_DEVICE();
+  MRISR_REQUIRE(q && k && v && o && lse, "attention_lse: null pointer");
+  MRISR_REQUIRE(batch > 0 && nq > 0 && nk > 0 && heads > 0, "attention_lse: bad sizes");
+  MRISR_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o), "attention_lse: misaligned pointer");
+  MRISR_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0, "attention_lse: row strides must be multiples of 8");
+  if (!attention_takes_tc(d, nk, ldo)) return fail(MRISR_E_UNSUPPORTED, "attention_lse: this shape does not run on the tcgen05 kernels (mrisr_attention_exports_lse)");
+  cudaStream_t st = as_stream(stream);
+  if (d == 40) return launch_attention_tc<40>(q, ldq, k, ldk, v, ldv, o, ldo, batch, nq, nk, heads, 0, st, lse);
+  return launch_attention_tc<80>(q, ldq, k, ldk, v, ldv, o, ldo, batch, nq, nk, heads, 0, st, lse);
+}
+
 int mrisr_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
                     int batch, int nq, int nk, int heads, int d, int kv_broadcast, void* stream) {
   MRISR_ONE_DEVICE();
@@ -979,7 +1000,7 @@ int mrisr_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   a.scale_log2 = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(d)));
   cudaStream_t st = as_stream(stream);
   // tensor-core (tcgen05) path: needs 16-byte aligned, 16-byte-pitched K / V views for TMA and 16-byte aligned O rows
-  if (use_tc_attention() && (d == 40 || d == 80) && nk >= 128 && ldo % 8 == 0) {
+  if (attention_takes_tc(d, nk, ldo)) {
     if (d == 40) return launch_attention_tc<40>(q, ldq, k, ldk, v, ldv, o, ldo, batch, nq, nk, heads, kv_broadcast, st);
     return launch_attention_tc<80>(q, ldq, k, ldk, v, ldv, o, ldo, batch, nq, nk, heads, kv_broadcast, st);
   }
@@ -1347,7 +1368,7 @@ int64_t mrisr_attention_backward_workspace(int batch, int nq, int nk, int heads,
 
 int mrisr_attention_backward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o, int64_t ldo,
                              const void* d_o, int64_t lddo, int d_o_f16, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
-                             float* stats_ws, int batch, int nq, int nk, int heads, int d, void* stream) {
+                             float* stats_ws, int have_lse, int batch, int nq, int nk, int heads, int d, void* stream) {
   MRISR_ONE_DEVICE();
   MRISR_REQUIRE(q && k && v && o && d_o && dq && dk && dv && stats_ws, "attention_backward: null pointer");
   MRISR_REQUIRE(batch > 0 && nq > 0 && nk > 0 && heads > 0, "attention_backward: bad sizes");
@@ -1370,11 +1391,11 @@ int mrisr_attention_backward(const void* q, int64_t ldq, const void* k, int64_t 
   a.scale_log2 = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(d)));
   cudaStream_t st = as_stream(stream);
   switch (d) {
-    case 8: return launch_attention_backward<8>(a, st);
-    case 16: return launch_attention_backward<16>(a, st);
-    case 40: return launch_attention_backward<40>(a, st);
-    case 80: return launch_attention_backward<80>(a, st);
-    case 160: return launch_attention_backward<160>(a, st);
+    case 8: return launch_attention_backward<8>(a, have_lse != 0, st);
+    case 16: return launch_attention_backward<16>(a, have_lse != 0, st);
+    case 40: return launch_attention_backward<40>(a, have_lse != 0, st);
+    case 80: return launch_attention_backward<80>(a, have_lse != 0, st);
+    case 160: return launch_attention_backward<160>(a, have_lse != 0, st);
     default: return fail(MRISR_E_UNSUPPORTED, "attention_backward: head dim %d unsupported (8, 16, 40, 80, 160)", d);
   }
 }

@@ -712,7 +712,8 @@ __device__ __forceinline__ void ab_mma_pn(float (&out)[AttnBwdCfg<D>::DP / 8][4]
   }
 }
 
-template <int D>
+// kHaveLse: a.lse already holds the forward pass's row log-sum-exp (mrisr_attention_lse): pass 1 is skipped
+template <int D, bool kHaveLse>
 __global__ void __launch_bounds__(kAbThreads, D <= 40 ? 4 : 1) attention_bwd_dq_kernel(AttnBwdArgs a) {
   grid_dep_launch();
   grid_dep_wait();   // launched with programmatic dependent launch: inputs are the predecessor's output
@@ -732,7 +733,12 @@ __global__ void __launch_bounds__(kAbThreads, D <= 40 ? 4 : 1) attention_bwd_dq_
   const __nv_bfloat16* kbase = a.k + krow0 * a.ldk;
   const __nv_bfloat16* vbase = a.v + krow0 * a.ldv;
   const int ktiles = (a.nk + 63) / 64;
-  ab_load_tile_async<D>(sK, kbase, a.ldk, 0, a.nk, h * D);   // first key tile of pass 1, in flight under the Q / dO loads
+  if (kHaveLse) {   // first K / V pair of pass 2 (its buffer: see below), in flight under the Q / dO loads
+    ab_load_tile_async<D>(sK + (ktiles % NB) * Cfg::kTileElems, kbase, a.ldk, 0, a.nk, h * D);
+    ab_load_tile_async<D>(sV + (ktiles % NB) * Cfg::kTileElems, vbase, a.ldv, 0, a.nk, h * D);
+  } else {
+    ab_load_tile_async<D>(sK, kbase, a.ldk, 0, a.nk, h * D);   // first key tile of pass 1
+  }
   ab_cp_commit();
   ab_load_tile<D, false>(sQ, a.q + qrow0 * a.ldq, a.ldq, q0, a.nq, h * D);
   if (a.d_o_f16) ab_load_tile<D, true>(sdO, static_cast<const uint16_t*>(a.d_o) + qrow0 * a.lddo, a.lddo, q0, a.nq, h * D);
@@ -754,7 +760,7 @@ __global__ void __launch_bounds__(kAbThreads, D <= 40 ? 4 : 1) attention_bwd_dq_
   const int r0 = warp * 16;
   // ---- pass 1: log2-domain log-sum-exp of the two rows this thread owns (g, g + 8)
   float mx[2] = {-INFINITY, -INFINITY}, sm[2] = {0.f, 0.f};
-  for (int kt = 0; kt < ktiles; ++kt) {
+  for (int kt = 0; kt < (kHaveLse ? 0 : ktiles); ++kt) {
     ab_cp_wait_all();
     __syncthreads();   // tile kt has landed; every warp is past tile kt - 1, so the other buffer is free
     const __nv_bfloat16* cK = sK + (kt % NB) * Cfg::kTileElems;
@@ -806,10 +812,14 @@ __global__ void __launch_bounds__(kAbThreads, D <= 40 ? 4 : 1) attention_bwd_dq_
   float lse[2], dsv[2];
 #pragma unroll
   for (int rrow = 0; rrow < 2; ++rrow) {
-    lse[rrow] = mx[rrow] + log2f(sm[rrow]);
-    dsv[rrow] = sDs[r0 + g + 8 * rrow];
     const int qi = q0 + r0 + g + 8 * rrow;
-    if (t == 0 && qi < a.nq) a.lse[stat0 + qi] = lse[rrow];
+    if (kHaveLse) {
+      lse[rrow] = qi < a.nq ? a.lse[stat0 + qi] : 0.f;
+    } else {
+      lse[rrow] = mx[rrow] + log2f(sm[rrow]);
+      if (t == 0 && qi < a.nq) a.lse[stat0 + qi] = lse[rrow];
+    }
+    dsv[rrow] = sDs[r0 + g + 8 * rrow];
   }
   // ---- pass 2: dQ.  Tile i of this pass lives in buffer (ktiles + i) % NB (the pass-1 loop left tile 0 in flight there).
   float dq[Cfg::DP / 8][4];

@@ -304,7 +304,8 @@ class LoRAFineTuner:
         h_a = ops.gemm(g0.view(M, Cc), a.w_in, bias=a.b_in, out_dtype=F16)
         y1 = ops.layernorm(h_a, a.ln1[0], a.ln1[1], 1e-5)
         qkv, t1 = self._lora_fwd(y1, d["qkv"])
-        o1 = ops.attention(qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:], B, heads)
+        # (the tcgen05 forward kernels also hand back the rows' log-sum-exp: the backward's dQ kernel then skips its recomputation sweep)
+        o1, lse1 = ops.attention_with_lse(qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:], B, heads)
         h_b, t2 = self._lora_fwd(o1, d["o1"], bias=a.b_o1, res1=h_a, out_dtype=F16)
         y2 = ops.layernorm(h_b, a.ln2[0], a.ln2[1], 1e-5)
         q2, t3 = self._lora_fwd(y2, d["q2"])
@@ -316,7 +317,7 @@ class LoRAFineTuner:
         f = ops.geglu_forward(pre)
         h_d = ops.gemm(f, a.w_ff2, bias=a.b_ff2, res1=h_c, out_dtype=F16)
         out = ops.gemm(h_d, a.w_out, bias=a.b_out, res1=x.view(M, Cc), res2=extra_res, out_dtype=F16).view(B, H, W, Cc)
-        return out, (a, x, h_a, y1, t1, qkv, o1, t2, h_b, y2, t3, q2, ehs2, t4, kv, o2, t5, h_c, pre, h_d)
+        return out, (a, x, h_a, y1, t1, qkv, o1, t2, h_b, y2, t3, q2, ehs2, t4, kv, o2, t5, h_c, pre, h_d, lse1)
 
     def _lora_bwd(self, g: _Group, dy: Tensor, x: Tensor, t: Tensor, need_dx: bool = True, out_dtype=F16) -> Optional[Tensor]:
         """y = [x | t] [W | sB]^T with t = x A^T.  dx = [dy | u] [W^T | A^T]^T, u = dy (sB); accumulates nothing: the weight
@@ -336,7 +337,7 @@ class LoRAFineTuner:
         return ops.gemm(dy, g.wd_ext, a2=u, out_dtype=out_dtype)
 
     def _transformer_bwd(self, ctx, dout: Tensor) -> Tensor:
-        a, x, h_a, y1, t1, qkv, o1, t2, h_b, y2, t3, q2, ehs2, t4, kv, o2, t5, h_c, pre, h_d = ctx
+        a, x, h_a, y1, t1, qkv, o1, t2, h_b, y2, t3, q2, ehs2, t4, kv, o2, t5, h_c, pre, h_d, lse1 = ctx
         c = self.cfg
         B, H, W, Cc = x.shape
         M = B * H * W
@@ -361,7 +362,7 @@ class LoRAFineTuner:
         d_o1 = self._lora_bwd(d["o1"], d_hb, o1, t2, out_dtype=torch.bfloat16)
         d_qkv = torch.empty((M, 3 * Cc), device=self.dev, dtype=F16)
         ops.attention_backward(qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:], o1, d_o1, B, heads,
-                               d_qkv[:, :Cc], d_qkv[:, Cc:2 * Cc], d_qkv[:, 2 * Cc:])
+                               d_qkv[:, :Cc], d_qkv[:, Cc:2 * Cc], d_qkv[:, 2 * Cc:], lse=lse1)
         d_y1 = self._lora_bwd(d["qkv"], d_qkv, y1, t1)
         d_ha = ops.layernorm_backward(h_a, d_y1, a.ln1[0], 1e-5, dres=d_hb)
         if os.environ.get("MRISR_FT_DEBUG"):

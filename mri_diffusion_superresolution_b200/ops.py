@@ -241,6 +241,25 @@ def attention(q: Tensor, k: Tensor, v: Tensor, batch: int, heads: int, kv_broadc
     return o
 
 
+def attention_with_lse(q: Tensor, k: Tensor, v: Tensor, batch: int, heads: int) -> Tuple[Tensor, Optional[Tensor]]:
+    """``attention`` for the fine-tune forward pass: also returns the backward pass's statistics workspace with the rows' log-sum-exp
+    (log2 domain of the scaled scores) already in its first ``batch*heads*nq`` floats -- when the shape runs on the tcgen05 kernels,
+    else ``None`` (``attention_backward`` then recomputes it)."""
+    lib = _lib.load()
+    for n, t in (("q", q), ("k", k), ("v", v)):
+        _cuda(t, f"attention.{n}", torch.bfloat16)
+    c = q.shape[1]
+    d = c // heads
+    nq, nk = q.shape[0] // batch, k.shape[0] // batch
+    if not lib.mrisr_attention_exports_lse(d, nk, c):
+        return attention(q, k, v, batch, heads), None
+    o = torch.empty((q.shape[0], c), device=q.device, dtype=torch.bfloat16)
+    lse = torch.empty((lib.mrisr_attention_backward_workspace(batch, nq, nk, heads, d),), device=q.device, dtype=torch.float32)
+    _lib.check(lib.mrisr_attention_lse(q.data_ptr(), _rows(q, "q"), k.data_ptr(), _rows(k, "k"), v.data_ptr(), _rows(v, "v"),
+                                       o.data_ptr(), c, lse.data_ptr(), batch, nq, nk, heads, d, _stream(q)), "mrisr_attention_lse")
+    return o, lse
+
+
 def groupnorm(x1: Tensor, gamma: Tensor, beta: Tensor, groups: int, eps: float, silu: bool,
               x2: Optional[Tensor] = None) -> Tensor:
     """GroupNorm(+SiLU) of the channel concat [x1 | x2]; x*: NHWC ``[B, H, W, c]`` (channel-slice views allowed).
@@ -642,7 +661,7 @@ def xty64(x64: Tensor, y: Tensor, out: Tensor, scale: float = 1.0) -> Tensor:
 
 
 def attention_backward(q: Tensor, k: Tensor, v: Tensor, o: Tensor, d_o: Tensor, batch: int, heads: int,
-                       dq: Tensor, dk: Tensor, dv: Tensor) -> None:
+                       dq: Tensor, dk: Tensor, dv: Tensor, lse: Optional[Tensor] = None) -> None:
     """Backward of ``attention`` (no K/V broadcast): q/k/v/o bf16 (column-slice views allowed), d_o bfloat16 (the fast path: every
     streamed tile is an asynchronous copy) or float16 (rounded to bf16 on load); writes the float16 views dq / dk / dv (e.g. the three
     column ranges of one ``[M, 3C]`` buffer)."""
@@ -657,12 +676,19 @@ def attention_backward(q: Tensor, k: Tensor, v: Tensor, o: Tensor, d_o: Tensor, 
     c = q.shape[1]
     d = c // heads
     nq, nk = q.shape[0] // batch, k.shape[0] // batch
-    ws = torch.empty((lib.mrisr_attention_backward_workspace(batch, nq, nk, heads, d),), device=q.device, dtype=torch.float32)
+    nws = lib.mrisr_attention_backward_workspace(batch, nq, nk, heads, d)
+    if lse is not None:   # the workspace attention_with_lse returned (log-sum-exp in place): the dQ kernel skips its recomputation sweep
+        _cuda(lse, "attention_backward.lse", torch.float32)
+        if lse.numel() < nws or not lse.is_contiguous():
+            raise ValueError("attention_backward: lse must be the workspace returned by attention_with_lse")
+        ws = lse
+    else:
+        ws = torch.empty((nws,), device=q.device, dtype=torch.float32)
     _lib.check(lib.mrisr_attention_backward(q.data_ptr(), _rows(q, "q"), k.data_ptr(), _rows(k, "k"), v.data_ptr(), _rows(v, "v"),
                                             o.data_ptr(), _rows(o, "o"), d_o.data_ptr(), _rows(d_o, "d_o"), int(d_o.dtype == torch.float16),
                                             dq.data_ptr(), _rows(dq, "dq"),
-                                            dk.data_ptr(), _rows(dk, "dk"), dv.data_ptr(), _rows(dv, "dv"), ws.data_ptr(), batch, nq, nk,
-                                            heads, d, _stream(q)), "mrisr_attention_backward", kernels=2)
+                                            dk.data_ptr(), _rows(dk, "dk"), dv.data_ptr(), _rows(dv, "dv"), ws.data_ptr(), int(lse is not None),
+                                            batch, nq, nk, heads, d, _stream(q)), "mrisr_attention_backward", kernels=2)
 
 
 def scale_(x: Tensor, factor: float) -> Tensor:

@@ -104,6 +104,15 @@ def test_attention_backward(ops, B, heads, d, nq, nk, do_dtype):
     assert _rel(dq, merge(qr.grad, nq)) < 8e-3
     assert _rel(dkv[:, :C], merge(kr.grad, nk)) < 8e-3
     assert _rel(dkv[:, C:], merge(vr.grad, nk)) < 8e-3
+    # the forward pass's own log-sum-exp (tcgen05 shapes only) instead of the dQ kernel's recomputation sweep: same gradients
+    o2, stats = ops.attention_with_lse(q.cuda(), k.cuda(), v.cuda(), B, heads)
+    assert torch.equal(o2, o) and (stats is not None) == (d in (40, 80) and nk >= 128)
+    if stats is not None:
+        ref_lse = torch.logsumexp(torch.einsum("bhqd,bhkd->bhqk", split(q, nq), split(k, nk)) / math.sqrt(d), -1) / math.log(2.0)
+        assert _rel(stats[: B * heads * nq].view(B, heads, nq), ref_lse) < 2e-3
+        dq2, dkv2 = torch.empty_like(dq), torch.empty_like(dkv)
+        ops.attention_backward(q.cuda(), k.cuda(), v.cuda(), o, d_o.cuda(), B, heads, dq2, dkv2[:, :C], dkv2[:, C:], lse=stats)
+        assert _rel(dq2, merge(qr.grad, nq)) < 8e-3 and _rel(dkv2[:, :C], merge(kr.grad, nk)) < 8e-3 and _rel(dkv2[:, C:], merge(vr.grad, nk)) < 8e-3
 
 
 def test_xty64_and_spatial_helpers(ops):
