@@ -261,8 +261,8 @@ __device__ __forceinline__ void gemm_epilogue_tma(const GemmKernelParams& p, con
   const int nc = half == 0 ? kMaxC : kChunks - kMaxC;
   // TMEM reads are a shared 64 B/clk port per SM (a 128 x 160 fp32 tile = 1280 clk for the 8 epilogue warps together).  On the
   // store-heavy small-K GEMMs (5 k-chunks per tile) the epilogue, not the MMA, paces the tile loop: ~3800 clk per tile per warp
-  // (MRISR_GEMM_TIMELINE: ~130 clk load wait, then per chunk ~700 arithmetic, ~250 buffer wait, ~330 pack + st.shared, ~180 fence,
-  // ~500 store issue -- a latency chain of ~150-200 instructions per chunk on 2 warps per scheduler).  -DMRISR_EPI_PIPELINED runs the
+  // (MRISR_GEMM_TIMELINE; dbg bits: of 128 us on M = 131072, N = 960, K = 320 the arithmetic + staging is 33, the fence 8, the store
+  // issue 13 -- a latency chain of ~150-200 instructions per chunk on 2 warps per scheduler).  -DMRISR_EPI_PIPELINED runs the
   // loads one chunk ahead of the arithmetic: M = 131072, N = 960, K = 320 128 -> 122 us, but the 50-step loop LOSES 0.9 %
   // (19.83 -> 19.65 slices/s, same box, alternated): the deep-K convs want the accumulator stage handed back early.  Default: off.
 #ifndef MRISR_EPI_PIPELINED   // default: every load issued and awaited before any arithmetic, accumulator released at once
