@@ -217,6 +217,9 @@ __device__ __forceinline__ void gemm_stage_bias(const GemmKernelParams& p, float
 // ones / its own fragment, 16 HMMA per chunk: measured +17 us on a 171 us 3x3 conv, the legacy MMAs take tensor-pipe
 // cycles from the tcgen05 main loop; this form costs nothing measurable.)
 struct GemmStatCtx {
+#ifdef MRISR_GEMM_TIMELINE
+  mutable long long tl[18];
+#endif
   float2* slots;   // this tile's ring entry: [4 lane quarters][BN]
   int* counter;    // this tile's ring entry: arrivals of the lane-quarter warps, one counter per chunk half
   long long block; // 128-row block index in gn_part
@@ -243,9 +246,8 @@ __device__ __forceinline__ void gemm_chunk_col_stats(const uint8_t* buf, int lan
 // 128-bit writes) and stored by ONE cp.async.bulk.tensor issued by lane 0 -- ~4x fewer instructions per chunk than
 // transposing through shared memory and storing with per-row pointers, and rows >= M are clipped by the TMA unit.
 #ifdef MRISR_GEMM_TIMELINE
-__device__ long long g_gtl[16];
-__device__ int g_gtl_n;
-#define GTLF(k) do { if (blockIdx.x == 0 && (threadIdx.x >> 5) == 9 && (threadIdx.x & 31) == 0 && g_gtl_n == 5) g_gtl[k] = clock64(); } while (0)
+// per-chunk stamps of the TMA-store epilogue, kept in registers (st.tl, compile-time indices) and printed by the caller
+#define GTLF(k) do { if ((k) < 18) st.tl[(k)] = clock64(); } while (0)
 #else
 #define GTLF(k) do { } while (0)
 #endif
@@ -277,8 +279,10 @@ __device__ __forceinline__ void gemm_epilogue_tma(const GemmKernelParams& p, con
       if (kGeglu) tmem_ld_32x32(t_row + kOutCols + (c_begin + ci) * 32, g[kGeglu ? ci : 0]);
     }
   }
+  GTLF(16);
   tmem_ld_wait();
   release();
+  GTLF(17);
 #else
 #define MRISR_EPI_SLOT(ci) ((ci) & 1)
   uint32_t v[2][32];
@@ -320,6 +324,8 @@ __device__ __forceinline__ void gemm_epilogue_tma(const GemmKernelParams& p, con
       } else {
         release();         // the whole accumulator has been read: hand the stage back to the MMA warp
       }
+#else
+      GTLF(ci * 6 + 1);
 #endif
       float f[32];
 #pragma unroll
@@ -856,13 +862,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
       }
       GTL(3);
 #ifdef MRISR_GEMM_TIMELINE
-      if (blockIdx.x == 0 && warp == 9 && lane == 0) {
-        if (g_gtl_n == 5)
-          printf("GTLF warp 9 tile 5: c0: ldwait +%lld | arith +%lld | wait_read +%lld | pack+sts +%lld | fence +%lld || c1: start +%lld | ldwait +%lld | arith +%lld | wait_read +%lld | pack+sts +%lld | fence +%lld | end +%lld\n",
-                 g_gtl[1] - g_gtl[0], g_gtl[2] - g_gtl[1], g_gtl[3] - g_gtl[2], g_gtl[4] - g_gtl[3], g_gtl[5] - g_gtl[4], g_gtl[6] - g_gtl[5],
-                 g_gtl[7] - g_gtl[6], g_gtl[8] - g_gtl[7], g_gtl[9] - g_gtl[8], g_gtl[10] - g_gtl[9], g_gtl[11] - g_gtl[10], clock64() - g_gtl[11]);
-        g_gtl_n = g_gtl_n + 1;
-      }
+      if (blockIdx.x == 0 && warp == 9 && lane == 0 && it == 5)
+        printf("GTLF warp 9 tile 5 (registers): tmem wait+release +%lld | setup +%lld | c0: ldwait +%lld | arith +%lld | wait_read +%lld | pack+sts +%lld | fence+sync +%lld || issue -> c1 start +%lld | ldwait +%lld | arith +%lld | wait_read +%lld | pack+sts +%lld | fence+sync +%lld | issue+return +%lld\n",
+               st.tl[17] - st.tl[16], st.tl[0] - st.tl[17], st.tl[1] - st.tl[0], st.tl[2] - st.tl[1], st.tl[3] - st.tl[2], st.tl[4] - st.tl[3], st.tl[5] - st.tl[4], st.tl[6] - st.tl[5],
+               st.tl[7] - st.tl[6], st.tl[8] - st.tl[7], st.tl[9] - st.tl[8], st.tl[10] - st.tl[9], st.tl[11] - st.tl[10], clock64() - st.tl[11]);
 #endif
     }
 #ifdef MRISR_GEMM_TIMELINE
