@@ -180,6 +180,7 @@ class LoRAFineTuner:
         self.lr_dev = torch.zeros(1, device=dev, dtype=torch.float32)
         self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
         self._graph = None
+        self._graph2 = None
         self._gkey = None
         self.kernel_launches_per_step = 0
         # write the packed 16-bit destinations once from the masters (also fills the dgrad operands' LoRA parts)
@@ -502,15 +503,19 @@ class LoRAFineTuner:
         self.lr_dev.fill_(float(lr))
         return self._optimizer_step_device()
 
-    def _optimizer_step_device(self) -> Tensor:
+    def _allreduce_gradients(self) -> None:
+        """Data-parallel fine-tuning: every rank ran its own micro-batch; ONE all-reduce of the flat LoRA gradient buffer (the 64-row
+        X^T Y results of all 80 projection groups: 41.5 MB for SD-1.5) over NCCL / NVLink; the frozen UNet needs no communication."""
+        import torch.distributed as dist
+        dist.all_reduce(self.gbuf, op=dist.ReduceOp.SUM)
+
+    def _optimizer_step_device(self, reduce: bool = True) -> Tensor:
         lib = _lib.load()
         if self.ddp:
-            # data-parallel fine-tuning: every rank ran its own micro-batch; ONE all-reduce of the flat LoRA gradient buffer
-            # (the 64-row X^T Y results of all 80 projection groups: 41.5 MB for SD-1.5) over NCCL / NVLink, averaged; the frozen UNet
-            # needs no communication at all
-            import torch.distributed as dist
-            dist.all_reduce(self.gbuf, op=dist.ReduceOp.SUM)
-            ops.scale_(self.gbuf, 1.0 / dist.get_world_size())
+            if reduce:
+                self._allreduce_gradients()
+            flat = self.gbuf.view(-1)
+            ops.sched_step(flat, flat, self._dp_coef, out=flat)       # average: gbuf *= 1 / world_size (axpy kernel, c1 = 1 / N)
         st = torch.cuda.current_stream(self.dev).cuda_stream
         _lib.check(lib.mrisr_grad_sqnorm(self.desc_dev.data_ptr(), len(self._descs), float(self.max_norm), self.norm_ws.data_ptr(),
                                          self.clip.data_ptr(), st), "mrisr_grad_sqnorm", kernels=2)
@@ -527,6 +532,7 @@ class LoRAFineTuner:
         if not dist.is_initialized():
             raise RuntimeError("enable_data_parallel: torch.distributed is not initialised")
         self.ddp = dist.get_world_size() > 1
+        self._dp_coef = torch.tensor([1.0 / dist.get_world_size(), 0.0, 0.0, 0.0], device=self.dev, dtype=torch.float32)
         self._graph = None
 
     @property
@@ -540,7 +546,7 @@ class LoRAFineTuner:
         ``use_cuda_graph``: the ~1.3 k kernel launches of a step (forward, loss, backward, clip, AdamW) are captured once per input
         shape and replayed -- at the reference's batch of 2 the eager step is bound by launch overhead, not by the GPU."""
         feats = down_intrablock_additional_residuals
-        if not use_cuda_graph or self.ddp:       # (the NCCL all-reduce is issued by torch between the two halves of the step)
+        if not use_cuda_graph:
             loss, _ = self.forward_backward(hr_latents, lr_latents, timesteps, noise, encoder_hidden_states, feats)
             return loss, self.optimizer_step(lr).clone()
         ins = [hr_latents.float(), lr_latents.float(), timesteps.to(torch.int64).reshape(-1), noise.float(), encoder_hidden_states.float()]
@@ -561,14 +567,26 @@ class LoRAFineTuner:
             torch.cuda.current_stream(self.dev).wait_stream(side)
             g = torch.cuda.CUDAGraph()
             n0 = _lib.LAUNCHES[0]
+            # data-parallel: TWO graphs (forward + backward | average + clip + AdamW) with torch's NCCL all-reduce of the flat gradient
+            # buffer issued between their replays
+            self._graph2 = None
             with torch.cuda.graph(g):
                 self._g_loss, _ = self.forward_backward(*self._static[:5], sfe)
-                self._optimizer_step_device()
+                if not self.ddp:
+                    self._optimizer_step_device()
+            if self.ddp:
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2, pool=g.pool()):
+                    self._optimizer_step_device(reduce=False)
+                self._graph2 = g2
             self.kernel_launches_per_step = _lib.LAUNCHES[0] - n0
             self._graph, self._gkey = g, key
         for dst, src in zip(self._static, ins):
             dst.copy_(src, non_blocking=True)
         self.lr_dev.fill_(float(lr))
         self._graph.replay()
+        if self._graph2 is not None:
+            self._allreduce_gradients()
+            self._graph2.replay()
         self.unet._ehs_key = None
         return self._g_loss.clone(), self.clip.clone()

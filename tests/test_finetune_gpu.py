@@ -191,7 +191,7 @@ def _batch(kw, B, seed, with_feats):
     g = torch.Generator().manual_seed(seed)
     s, ch = kw["sample_size"], kw["block_out_channels"]
     hr, lr, noise = (torch.randn(B, 4, s, s, generator=g) * 0.8 for _ in range(3))
-    t = torch.tensor([700, 40][:B] if B <= 2 else [700, 40, 333][:B])
+    t = torch.tensor([700, 40, 333, 910][:B])
     ehs = torch.randn(B, 77, kw["cross_attention_dim"], generator=g)
     feats = [torch.randn(B, c, s >> i, s >> i, generator=g) * 0.5 for i, c in enumerate(ch)] if with_feats else None
     return hr, lr, t, noise, ehs, feats
@@ -288,3 +288,62 @@ def test_flat_gradient_buffer_and_scale(ops):
     assert torch.equal(ft.gbuf, before * 0.5)
     g1 = ft.lora_grads()
     assert all(torch.equal(g1[k], g0[k] * 0.5) for k in g0)
+
+
+def _ddp_worker(rank, world, port, use_graph, q):
+    """One data-parallel rank (both ranks share cuda:0; gloo carries the CUDA gradient buffer): two steps on this rank's micro-batch."""
+    import torch.distributed as dist
+    try:
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+        _, _, _, ft = _setup(SMALL)
+        ft.enable_data_parallel()
+        hr, lr, t, noise, ehs, feats = _batch(SMALL, 4, 11, True)
+        sl = slice(2 * rank, 2 * rank + 2)
+        cu = lambda v: v[sl].cuda()
+        norms = []
+        for _ in range(2):
+            loss, info = ft.step(cu(hr), cu(lr), cu(t), cu(noise), cu(ehs), lr=1e-3, down_intrablock_additional_residuals=[cu(f) for f in feats],
+                                 use_cuda_graph=use_graph)
+            norms.append(float(info[0].item()))
+        torch.cuda.synchronize()
+        sd = {k: v.float().cpu().numpy() for k, v in ft.lora_state_dict().items()}      # (numpy: pickled by value through the queue)
+        q.put((rank, True, sd, norms))
+        dist.destroy_process_group()
+    except Exception as e:   # surface the failure in the parent
+        q.put((rank, False, repr(e), []))
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_data_parallel_two_ranks_match_single_process_on_the_joint_batch(use_graph):
+    """DDP semantics for the LoRA matrices: two ranks with micro-batches of 2 (gradients averaged by one all-reduce of the flat buffer;
+    with CUDA graphs: forward + backward and clip + AdamW replayed as two graphs around the all-reduce) end two steps with identical
+    LoRA matrices, equal to one process stepping on the joint batch of 4 (mean loss => mean of the per-rank gradients)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30500 + (os.getpid() % 2000) + int(use_graph)
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, use_graph, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=300) for _ in range(2)), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] for r in res), [r[2] for r in res if not r[1]]
+    sd0, sd1 = ({k: torch.from_numpy(v) for k, v in r[2].items()} for r in res)
+    assert sorted(sd0) == sorted(sd1) and all(torch.equal(sd0[k], sd1[k]) for k in sd0)          # replicas stay bit-identical
+    assert res[0][3] == res[1][3]                                                                # ... and see the same averaged gradient
+    _, _, _, ft = _setup(SMALL)
+    init = {k: v.float().cpu() for k, v in ft.lora_state_dict().items()}
+    hr, lr, t, noise, ehs, feats = _batch(SMALL, 4, 11, True)
+    ref_norms = []
+    for _ in range(2):
+        _, info = ft.step(hr.cuda(), lr.cuda(), t.cuda(), noise.cuda(), ehs.cuda(), lr=1e-3, down_intrablock_additional_residuals=[f.cuda() for f in feats],
+                          use_cuda_graph=False)
+        ref_norms.append(float(info[0].item()))
+    # the global gradient norm of the averaged per-rank gradients == that of the joint batch (first step: identical weights)
+    assert abs(res[0][3][0] - ref_norms[0]) < 1e-2 * ref_norms[0] and abs(res[0][3][1] - ref_norms[1]) < 5e-2 * ref_norms[1]
+    ref = {k: v.float().cpu() for k, v in ft.lora_state_dict().items()}
+    # and the weights moved the same way: AdamW's first updates are +-lr per element, so compare the update DIRECTIONS
+    num = sum(float(((sd0[k] - init[k]) * (ref[k] - init[k])).sum()) for k in ref)
+    den = math.sqrt(sum(float(((sd0[k] - init[k]) ** 2).sum()) for k in ref) * sum(float(((ref[k] - init[k]) ** 2).sum()) for k in ref))
+    assert den > 0 and num / den > 0.98
