@@ -92,11 +92,14 @@ int mrisr_groupnorm(const void* x1, int64_t ld1, int c1, const void* x2, int64_t
  * statistics pass, no grid barrier.  part1 / part2: fp32 pairs (sum, sum of squares) per 128-row block and channel as
  * written by mrisr_gemm for x1 / x2: element [(ph * phase_stride + b * (hw_part / 128) + j) * ldp + c] with ldp counted in
  * PAIRS; n_phases = 4 / hw_part = hw / 4 / phase_stride = blocks per phase for outputs of a taps == 4 (up2x) GEMM,
- * otherwise n_phases = 1, hw_part = hw.  hw_part % 128 == 0. */
+ * otherwise n_phases = 1, hw_part = hw.  hw_part % 128 == 0.
+ * workspace: NULL, or 2 * batch * groups floats (8-byte aligned) for the two-kernel variant (MRISR_GN_FINALIZE=1: the block partials are
+ * folded once per batch element into (mean, rstd) pairs by a small kernel; measured slower than the default, where every normalise CTA
+ * folds them in a prologue that overlaps its first loads). */
 int mrisr_groupnorm_apply_stats(const void* x1, int64_t ld1, int c1, const float* part1, int64_t ldp1, int n_phases1, int64_t phase_stride1,
                                 const void* x2, int64_t ld2, int c2, const float* part2, int64_t ldp2, int n_phases2, int64_t phase_stride2,
                                 int batch, int hw, int groups, const float* gamma, const float* beta, float eps, int silu,
-                                void* out, int f16_flags, void* stream);
+                                void* out, float* workspace, int f16_flags, void* stream);
 
 /* LayerNorm over the last dim: bf16 (or, in_f16 != 0, IEEE half) [rows, C] (row stride ldx) -> bf16 [rows, C] (row stride ldo).
  * C % 8 == 0, C <= 2048. */

@@ -66,7 +66,7 @@ PROTOTYPES = {
     "mrisr_sinusoidal_embedding": (_I, [_P, _P, _I, _I, _I, _P]),
     "mrisr_groupnorm_workspace_floats": (_L, [_I, _I]),
     "mrisr_groupnorm": (_I, [_P, _L, _I, _P, _L, _I, _I, _I, _I, _P, _P, _F, _I, _P, _P, _I, _P]),
-    "mrisr_groupnorm_apply_stats": (_I, [_P, _L, _I, _P, _L, _I, _L, _P, _L, _I, _P, _L, _I, _L, _I, _I, _I, _P, _P, _F, _I, _P, _I, _P]),
+    "mrisr_groupnorm_apply_stats": (_I, [_P, _L, _I, _P, _L, _I, _L, _P, _L, _I, _P, _L, _I, _L, _I, _I, _I, _P, _P, _F, _I, _P, _P, _I, _P]),
     "mrisr_layernorm": (_I, [_P, _L, _P, _P, _F, _P, _L, _I, _I, _I, _P]),
     "mrisr_gemm": (_I, [C.POINTER(GemmArgs), _P]),
     "mrisr_gemm_block_n": (_I, [_I, _I]),

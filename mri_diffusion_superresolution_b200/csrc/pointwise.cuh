@@ -397,9 +397,57 @@ struct GnPartArgs {
   int nph[2];
   int nblk[2];
 };
+// One CTA per batch element: block partials of the producing GEMM(s) -> per-channel sums (fixed order) -> the 32 group statistics
+// (fp64 where the cancellation is) -> mr[b][g] = (mean, rstd).  A few microseconds, launch-bound; it replaces the same reduction
+// repeated by every slab CTA of the normalise kernel (up to 16 per element, all before their first store).
+__global__ void __launch_bounds__(256) groupnorm_finalize_part_kernel(GnArgs a, GnPartArgs q, float eps, float2* __restrict__ mr) {
+  grid_dep_launch();
+  grid_dep_wait();
+  extern __shared__ __align__(16) float gnf_sh[];   // [sum[C] | sumsq[C]]
+  const int C = a.c1 + a.c2, cpg = C / a.groups;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int c = tid; c < C; c += 256) {
+    const bool s0 = c < a.c1;
+    const int cc = s0 ? c : c - a.c1;
+    const float2* qpart = s0 ? q.part[0] : q.part[1];
+    const long long qldp = s0 ? q.ldp[0] : q.ldp[1], qps = s0 ? q.pstride[0] : q.pstride[1];
+    const int qnblk = s0 ? q.nblk[0] : q.nblk[1], qnph = s0 ? q.nph[0] : q.nph[1];
+    float su = 0.f, sq = 0.f;
+    for (int ph = 0; ph < qnph; ++ph) {
+      const float2* base = qpart + (ph * qps + static_cast<long long>(b) * qnblk) * qldp + cc;
+      int j = 0;
+      for (; j + 4 <= qnblk; j += 4) {   // four independent L2 loads in flight
+        const float2 v0 = __ldg(base + j * qldp), v1 = __ldg(base + (j + 1) * qldp), v2 = __ldg(base + (j + 2) * qldp), v3 = __ldg(base + (j + 3) * qldp);
+        su += (v0.x + v1.x) + (v2.x + v3.x);
+        sq += (v0.y + v1.y) + (v2.y + v3.y);
+      }
+      for (; j < qnblk; ++j) { const float2 v = __ldg(base + j * qldp); su += v.x; sq += v.y; }
+    }
+    gnf_sh[c] = su;
+    gnf_sh[C + c] = sq;
+  }
+  __syncthreads();
+  const int lane = tid & 31, warp = tid >> 5;
+  for (int g = warp; g < a.groups; g += 8) {
+    double su = 0.0, sq = 0.0;
+    for (int i = lane; i < cpg; i += 32) { su += gnf_sh[g * cpg + i]; sq += gnf_sh[C + g * cpg + i]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { su += __shfl_xor_sync(0xffffffffu, su, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
+    if (lane == 0) {
+      const double mean = su * a.inv_n;
+      double var = sq * a.inv_n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      mr[static_cast<long long>(b) * a.groups + g] = make_float2(static_cast<float>(mean), rsqrtf(static_cast<float>(var) + eps));
+    }
+  }
+}
+
+// kFinal: the group statistics were already folded by groupnorm_finalize_part_kernel (mr[b][g] = (mean, rstd)): the prologue is one
+// 256-byte read instead of every slab CTA re-adding its element's hw / 128 x C block partials.
+template <bool kFinal>
 __global__ void __launch_bounds__(512, 2)   // <= 64 registers: four 240..256-thread CTAs per SM (the first version held 95 and ran two)
 groupnorm_apply_cpart_kernel(GnArgs a, GnPartArgs q, const float* __restrict__ gamma, const float* __restrict__ beta,
-                             float eps, int silu, __nv_bfloat16* __restrict__ out) {
+                             float eps, int silu, __nv_bfloat16* __restrict__ out, const float2* __restrict__ mr) {
   grid_dep_launch();
   grid_dep_wait();
   extern __shared__ __align__(16) float gn_sh[];   // [R][sum[C] | sumsq[C]] block partials added per thread row, then scale[C], shift[C]
@@ -423,7 +471,13 @@ groupnorm_apply_cpart_kernel(GnArgs a, GnPartArgs q, const float* __restrict__ g
   // (B) block partials of this batch element, no integer divisions: thread (vx, ry) owns the 8 channels of its vector and adds
   // the 128-row blocks j = ry, ry + R, ... (four 16-byte L2 loads per block, eight in flight), then the R rows are added per channel
   float* s_aff = gn_sh + R * 2 * C;
-  {
+  if constexpr (kFinal) {
+    if (tid < a.groups) {
+      const float2 v = __ldg(mr + static_cast<long long>(b) * a.groups + tid);
+      s_mean[tid] = v.x;
+      s_rstd[tid] = v.y;
+    }
+  } else {
     const int nv1 = a.c1 >> 3;
     const bool s0 = vx < nv1;
     const int cv = s0 ? vx : vx - nv1;
@@ -455,7 +509,7 @@ groupnorm_apply_cpart_kernel(GnArgs a, GnPartArgs q, const float* __restrict__ g
   }
   __syncthreads();
   // (C) group statistics: one (full) warp per group at a time, lanes over the group's R x cpg partial entries, fp64 from here
-  {
+  if constexpr (!kFinal) {
     const int lane = tid & 31, warp = tid >> 5, nfull = nthr >> 5;
     const int cnt = R * cpg;
     if (warp < nfull) {

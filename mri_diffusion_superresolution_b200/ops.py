@@ -34,6 +34,7 @@ def _launch(cls: str, work: float, t: Tensor, code_fn, what: str, kernels: int =
     e1.record(st)
     PROFILE.append((cls, float(work), e0, e1, detail))
 _GN_SMALL_MAXHW = int(os.environ.get("MRISR_GN_SMALL_MAXHW", "256"))    # tuning runs
+_GN_FINALIZE = os.environ.get("MRISR_GN_FINALIZE") == "1"     # A/B runs: fold the block partials in a separate small kernel (measured slower)
 _NO_GN_STATS = bool(os.environ.get("MRISR_NO_GN_STATS"))     # A/B runs: GroupNorm computes its own statistics (two kernels)
 _DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 _H16 = (torch.bfloat16, torch.float16)     # 16-bit activation formats: bf16 everywhere, IEEE half for the residual stream
@@ -285,13 +286,14 @@ def groupnorm(x1: Tensor, gamma: Tensor, beta: Tensor, groups: int, eps: float, 
     work = 4.0 * B * hw * C                                 # algorithmic bytes: one 2-byte read + one 2-byte write per element
     if fused:
         pt2, nph2, ps2 = p2 if p2 is not None else (None, 1, 0)
+        mr = torch.empty((2 * B * groups,), device=x1.device, dtype=torch.float32) if _GN_FINALIZE else None   # (mean, rstd) per (image, group)
         _launch("groupnorm", work, x1,
                 lambda: lib.mrisr_groupnorm_apply_stats(
                     x1.data_ptr(), x1.stride(2), c1, p1[0].data_ptr(), p1[0].shape[1], p1[1], p1[2],
                     _ptr(x2), ld2, c2, _ptr(pt2), (pt2.shape[1] if pt2 is not None else 0), nph2, ps2,
                     B, hw, groups, _cuda(gamma, "gamma", torch.float32).data_ptr(),
-                    _cuda(beta, "beta", torch.float32).data_ptr(), float(eps), int(silu), out.data_ptr(), f16, _stream(x1)),
-                "mrisr_groupnorm_apply_stats")
+                    _cuda(beta, "beta", torch.float32).data_ptr(), float(eps), int(silu), out.data_ptr(), _ptr(mr), f16, _stream(x1)),
+                "mrisr_groupnorm_apply_stats", kernels=2 if mr is not None else 1)
         return out
     ws = torch.empty((lib.mrisr_groupnorm_workspace_floats(B, groups),), device=x1.device, dtype=torch.float32)
     _launch("groupnorm", work, x1,
