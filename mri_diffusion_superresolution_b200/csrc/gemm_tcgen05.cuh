@@ -261,7 +261,8 @@ __device__ __forceinline__ void gemm_epilogue_tma(const GemmKernelParams& p, con
   const int lane_id = threadIdx.x & 31;
   const int c_begin = half == 0 ? 0 : kMaxC;
   const int nc = half == 0 ? kMaxC : kChunks - kMaxC;
-  // TMEM reads are a shared 64 B/clk port per SM (a 128 x 160 fp32 tile = 1280 clk for the 8 epilogue warps together).  On the
+  // TMEM reads are NOT the limit here: measured 450 B/clk/SM with one reading warp per lane quarter, ~670 with two (8 warps), ~36 clk
+  // per 4 KB tcgen05.ld incl. its wait (scripts/micro/tmem_ld_bench.cu, profiles/r2_tmem_ld_bench.txt): a 128 x 160 fp32 tile is ~125 clk.  On the
   // store-heavy small-K GEMMs (5 k-chunks per tile) the epilogue, not the MMA, paces the tile loop: ~3800 clk per tile per warp
   // (MRISR_GEMM_TIMELINE; dbg bits: of 128 us on M = 131072, N = 960, K = 320 the arithmetic + staging is 33, the fence 8, the store
   // issue 13 -- a latency chain of ~150-200 instructions per chunk on 2 warps per scheduler).  -DMRISR_EPI_PIPELINED runs the
