@@ -95,6 +95,14 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kGemmThreads = 384;  // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: epilogue (2 per TMEM lane quarter)
 constexpr int kEpilogueThreads = 256;
+// kEW (epilogue warps, 8 or 12): the store-heavy small-K GEMMs (5-10 k-chunks per tile) are paced by the epilogue's dependent
+// chain per 32-column chunk, not by the MMAs (profiles/r2_summary.md pass 10).  Twelve warps = three per TMEM lane quarter cut the
+// chunks a warp walks per 160-column tile from 3 to 2; they cost two staging-buffer sets and register room (144 instead of 216 per
+// epilogue thread), so the deep-K convs and the GEGLU tiles (two accumulator halves per chunk) keep eight.  Measured: M = 131072, K = 320:
+// N = 960 116 -> 87 us, N = 1280 151 -> 116 us; no gain at N = 320 (bound by its DRAM streams) and 0-9 % slower from K = 640 up; the
+// power-capped sampling loop is unchanged (the five QKV projections it speeds up draw the saved time back as clock), so the host keeps it
+// opt-in (MRISR_GEMM_EW12, mrisr_abi.cu).
+constexpr int gemm_threads(int ew) { return (4 + ew) * 32; }
 
 // kPair: a cluster of two CTAs on one TPC computes a 256 x BN tile with cta_group::2 MMAs; each CTA stages its own 128
 // rows of A and HALF of the W tile, so every SM pulls 16 KB + BN*64 B per k-chunk from L2 instead of 16 KB + BN*128 B
@@ -106,8 +114,10 @@ constexpr int kEpilogueThreads = 256;
 #define MRISR_EPI_BUFS 2
 #endif
 constexpr int kLoraN = 64;   // rows of the stacked LoRA A matrices == width of the K extension
-template <int BN, bool kPair, bool kLora = false>
+template <int BN, bool kPair, bool kLora = false, int kEW = 8>
 struct GemmCfg {
+  static_assert(kEW == 8 || kEW == 12, "epilogue warps: 2 or 3 per TMEM lane quarter");
+  static constexpr int kParts = kEW / 4;   // warps per lane quarter == column ranges a tile's chunks are dealt into
   static constexpr int kTileM = kPair ? 2 * kBlockM : kBlockM;
   static constexpr int kBRows = kPair ? BN / 2 : BN;
   static constexpr int kABytes = kBlockM * kBlockK * 2;
@@ -118,9 +128,9 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes + kB2Bytes;
   static_assert(!kLora || (kBBytes % 1024 == 0 && kStageBytes % 1024 == 0), "swizzled tiles must stay 1024-byte aligned");
   static constexpr int kEpiBufs = kPair ? MRISR_EPI_BUFS : 2;   // staging buffers per epilogue warp (the single-CTA A/B kernel keeps 2)
-  static constexpr int kEpiBytes = 8 * kEpiBufs * 2048;   // per-epilogue-warp: kEpiBufs 32x32 16-bit staging buffers (ring of TMA stores in flight)
-  static constexpr int kBiasBytes = 8 * BN * 4;  // epilogue-staged bias, one slab per epilogue warp
-  static constexpr int kBarBytes = 256;          // <= 2*8+4 mbarriers + the TMEM base slot + 6 statistics counters
+  static constexpr int kEpiBytes = kEW * kEpiBufs * 2048;   // per-epilogue-warp: kEpiBufs 32x32 16-bit staging buffers (ring of TMA stores in flight)
+  static constexpr int kBiasBytes = kEW * BN * 4;  // epilogue-staged bias, one slab per epilogue warp
+  static constexpr int kBarBytes = 256;          // <= 2*8+4 mbarriers + the TMEM base slot + kStatRing x kParts statistics counters (5 slots) + 4 LoRA mbarriers
   // GroupNorm-statistics staging: ring of 3 tiles x 4 lane-quarter warps x BN columns x (sum, sumsq).  Ring depth 3: the
   // accumulator hand-back happens BEFORE the epilogue arithmetic, so epilogue warps of one CTA can be two tiles apart.
   static constexpr int kStatRing = 3;
@@ -251,16 +261,18 @@ __device__ __forceinline__ void gemm_chunk_col_stats(const uint8_t* buf, int lan
 #else
 #define GTLF(k) do { } while (0)
 #endif
-template <int BN, bool kGeglu, int kEpiBufs, typename Release>
+template <int BN, bool kGeglu, int kEpiBufs, int kParts, typename Release>
 __device__ __forceinline__ void gemm_epilogue_tma(const GemmKernelParams& p, const CUtensorMap* tm_out, uint32_t t_row, int m,
                                                   int n_blk, int half, const float* sbias, uint8_t* stage_buf,
                                                   uint32_t& buf_sel, Release release, const GemmStatCtx& st) {
   constexpr int kOutCols = kGeglu ? BN / 2 : BN;
   constexpr int kChunks = kOutCols / 32;
-  constexpr int kMaxC = (kChunks + 1) / 2;
+  // the tile's chunks are dealt to the kParts warps of a lane quarter (`half` = 0 .. kParts - 1) in contiguous, balanced ranges
+  constexpr int kBaseC = kChunks / kParts, kRemC = kChunks % kParts;
+  constexpr int kMaxC = kBaseC + (kRemC > 0 ? 1 : 0);
   const int lane_id = threadIdx.x & 31;
-  const int c_begin = half == 0 ? 0 : kMaxC;
-  const int nc = half == 0 ? kMaxC : kChunks - kMaxC;
+  const int c_begin = half * kBaseC + (half < kRemC ? half : kRemC);
+  const int nc = kBaseC + (half < kRemC ? 1 : 0);
   // TMEM reads are NOT the limit here: measured 450 B/clk/SM with one reading warp per lane quarter, ~670 with two (8 warps), ~36 clk
   // per 4 KB tcgen05.ld incl. its wait (scripts/micro/tmem_ld_bench.cu, profiles/r2_tmem_ld_bench.txt): a 128 x 160 fp32 tile is ~125 clk.  On the
   // store-heavy small-K GEMMs (5 k-chunks per tile) the epilogue, not the MMA, paces the tile loop: ~3800 clk per tile per warp
@@ -269,21 +281,28 @@ __device__ __forceinline__ void gemm_epilogue_tma(const GemmKernelParams& p, con
   // loads one chunk ahead of the arithmetic: M = 131072, N = 960, K = 320 128 -> 122 us, but the 50-step loop LOSES 0.9 %
   // (19.83 -> 19.65 slices/s, same box, alternated): the deep-K convs want the accumulator stage handed back early.  Default: off.
 #ifndef MRISR_EPI_PIPELINED   // default: every load issued and awaited before any arithmetic, accumulator released at once
-  constexpr int kV = kMaxC;
-#define MRISR_EPI_SLOT(ci) (ci)
+  // kSeq (three warps per lane quarter, 144 registers each): one chunk in registers at a time -- load, wait, process; the stage is
+  // handed back after the warp's LAST load.  (A tcgen05.ld and its wait cost ~36 clk: profiles/r2_tmem_ld_bench.txt.)
+  constexpr bool kSeq = kParts > 2 && !kGeglu;
+  constexpr int kV = kSeq ? 1 : kMaxC;
+#define MRISR_EPI_SLOT(ci) (kSeq ? 0 : (ci))
   uint32_t v[kV][32];
   uint32_t g[kGeglu ? kV : 1][32];
+  if constexpr (!kSeq) {
 #pragma unroll
-  for (int ci = 0; ci < kMaxC; ++ci) {
-    if (ci < nc) {
-      tmem_ld_32x32(t_row + (c_begin + ci) * 32, v[ci]);
-      if (kGeglu) tmem_ld_32x32(t_row + kOutCols + (c_begin + ci) * 32, g[kGeglu ? ci : 0]);
+    for (int ci = 0; ci < kMaxC; ++ci) {
+      if (ci < nc) {
+        tmem_ld_32x32(t_row + (c_begin + ci) * 32, v[ci]);
+        if (kGeglu) tmem_ld_32x32(t_row + kOutCols + (c_begin + ci) * 32, g[kGeglu ? ci : 0]);
+      }
     }
+    GTLF(16);
+    tmem_ld_wait();
+    release();
+    GTLF(17);
+  } else {
+    if (nc == 0) release();   // (a tile with fewer chunks than warps per lane quarter)
   }
-  GTLF(16);
-  tmem_ld_wait();
-  release();
-  GTLF(17);
 #else
 #define MRISR_EPI_SLOT(ci) ((ci) & 1)
   uint32_t v[2][32];
@@ -326,6 +345,11 @@ __device__ __forceinline__ void gemm_epilogue_tma(const GemmKernelParams& p, con
         release();         // the whole accumulator has been read: hand the stage back to the MMA warp
       }
 #else
+      if constexpr (kSeq) {
+        tmem_ld_32x32(t_row + c * 32, v[0]);
+        tmem_ld_wait();
+        if (ci == nc - 1) release();
+      }
       GTLF(ci * 6 + 1);
 #endif
       float f[32];
@@ -413,14 +437,15 @@ __device__ __forceinline__ void gemm_epilogue_tma(const GemmKernelParams& p, con
 // a swizzled shared-memory transpose (8 rows x 64 contiguous bytes per store instruction).
 template <int BN>
 __device__ __forceinline__ void gemm_epilogue_rows(const GemmKernelParams& p, uint32_t t_row, int m, int n_blk, int half,
-                                                   const float* sbias, uint8_t* stage_buf, long long row_off = 0) {
+                                                   const float* sbias, uint8_t* stage_buf, long long row_off = 0, int parts = 2) {
   const int lane_id = threadIdx.x & 31;
   const bool row_ok = m < p.M;
   const bool geglu = p.act == ACT_GEGLU;
   const int out_cols = geglu ? BN / 2 : BN;
   const int nchunks = out_cols / 32;
-  const int c_begin = half == 0 ? 0 : (nchunks + 1) / 2;
-  const int c_end = half == 0 ? (nchunks + 1) / 2 : nchunks;
+  const int base_c = nchunks / parts, rem_c = nchunks % parts;   // (parts == 2: first half gets the odd chunk, as before)
+  const int c_begin = half * base_c + min(half, rem_c);
+  const int c_end = c_begin + base_c + (half < rem_c ? 1 : 0);
   if (c_begin >= c_end || (p.dbg & 16)) return;
   const int n_w0 = n_blk * BN;        // first weight row of this tile
   const int n_o0 = n_blk * out_cols;  // first output column of this tile
@@ -515,10 +540,12 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmKernelParams& p, ui
 // Persistent kernel: grid = #SMs (pairs: clusters of 2).  Pair protocol: both CTAs' TMA loads complete on the LEADER's
 // full barrier; the leader's commits are multicast to both CTAs' empty / accumulator-full barriers; both CTAs' epilogue
 // warps arrive on the leader's accumulator-empty barrier.
-template <int BN, bool kPair, bool kLora = false>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int BN, bool kPair, bool kLora = false, int kEW = 8>
+__global__ void __launch_bounds__(gemm_threads(kEW), 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParams p) {
-  using Cfg = GemmCfg<BN, kPair, kLora>;
+  using Cfg = GemmCfg<BN, kPair, kLora, kEW>;
+  constexpr int kParts = Cfg::kParts;
+  constexpr int kEpiThreads = kEW * 32;
   constexpr int kStages = Cfg::kStages;
   constexpr int kTileM = Cfg::kTileM;
   extern __shared__ uint8_t smem_raw[];
@@ -530,9 +557,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
   float* sbias_base = reinterpret_cast<float*>(sepi_base + Cfg::kEpiBytes);
   float2* sstat_base = reinterpret_cast<float2*>(sepi_base + Cfg::kEpiBytes + Cfg::kBiasBytes);   // [ring][4][BN]
   const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes + Cfg::kTBytes + Cfg::kEpiBytes + Cfg::kBiasBytes + Cfg::kStatBytes;
-  auto tT_full = [&](int s) { return bar_base + 8u * (2 * kStages + 8 + s); };    // kLora: T accumulator complete (MMA -> epilogue)
-  auto tT_ready = [&](int s) { return bar_base + 8u * (2 * kStages + 10 + s); };  // kLora: bf16 T tile staged (epilogue -> MMA)
-  int* scnt_base = reinterpret_cast<int*>(sepi_base + Cfg::kEpiBytes + Cfg::kBiasBytes + Cfg::kStatBytes + 8 * (2 * kStages + 5));   // [ring][2]
+  auto tT_full = [&](int s) { return bar_base + 8u * (2 * kStages + 10 + s); };   // kLora: T accumulator complete (MMA -> epilogue)
+  auto tT_ready = [&](int s) { return bar_base + 8u * (2 * kStages + 12 + s); };  // kLora: bf16 T tile staged (epilogue -> MMA)
+  static_assert(8 * (2 * kStages + 14) <= Cfg::kBarBytes && Cfg::kStatRing * kParts * 4 <= 5 * 8, "barrier / counter slots");
+  int* scnt_base = reinterpret_cast<int*>(sepi_base + Cfg::kEpiBytes + Cfg::kBiasBytes + Cfg::kStatBytes + 8 * (2 * kStages + 5));   // [ring][kParts], slots +5 .. +9
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
@@ -570,13 +598,13 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), (kPair ? 2 : 1) * kEpilogueThreads);
+      mbar_init(tempty_bar(s), (kPair ? 2 : 1) * kEpiThreads);
       if (kLora) {
         mbar_init(tT_full(s), 1);
-        mbar_init(tT_ready(s), (kPair ? 2 : 1) * kEpilogueThreads);
+        mbar_init(tT_ready(s), (kPair ? 2 : 1) * kEpiThreads);
       }
     }
-    for (int s = 0; s < 2 * Cfg::kStatRing; ++s) scnt_base[s] = 0;
+    for (int s = 0; s < kParts * Cfg::kStatRing; ++s) scnt_base[s] = 0;
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -779,10 +807,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
   } else if (warp < 4) {
     reg_dealloc<72>();
   } else {
-    reg_alloc<216>();
+    if constexpr (kEW == 8) reg_alloc<216>(); else reg_alloc<144>();   // pool: 4 x 72 + kEW x R <= 2048 per lane
     // ===================== epilogue (every CTA drains its own 128 TMEM lanes) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may read
-    const int half = (warp - 4) >> 2;
+    const int half = (warp - 4) >> 2;   // which of the lane quarter's kParts warps this is (0 .. kParts - 1)
     float* sbias = sbias_base + (warp - 4) * BN;
     uint8_t* stage_buf = sepi_base + (warp - 4) * (Cfg::kEpiBufs * 2048);
     uint32_t buf_sel = 0;
@@ -807,7 +835,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
       GemmStatCtx st;
       st.slots = p.gn_part != nullptr ? sstat_base + (it % Cfg::kStatRing) * 4 * BN : nullptr;
-      st.counter = scnt_base + (it % Cfg::kStatRing) * 2;
+      st.counter = scnt_base + (it % Cfg::kStatRing) * kParts;
       st.block = static_cast<long long>(ph) * p.part_phase_stride + m_tile * (kPair ? 2 : 1) + rank;
       __syncwarp();  // every lane finished reading the previous tile's slab
       gemm_stage_bias<BN>(p, sbias, n_blk, lane);
@@ -816,7 +844,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
         // round this thread's row of T = x A^T (its 32 of the 64 columns) to bf16 into the SW128 A tile of the K extension
         mbar_wait(tT_full(as), aph);
         tcgen05_fence_after();
-        if (half * 32 < p.lora_n) {   // (columns >= lora_n of the accumulator were never written and are never read back by the MMA)
+        if (half < 2 && half * 32 < p.lora_n) {   // (a third warp of the lane quarter has no T columns: it only arrives; columns >= lora_n of the accumulator were never written and are never read back by the MMA)
           uint32_t tv[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 2 * BN + as * kLoraN + half * 32, tv);
           tmem_ld_wait();
@@ -833,7 +861,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
             *reinterpret_cast<uint4*>(trow + (((half * 4 + u) ^ (r & 7)) << 4)) = pk;
             if (tg != nullptr) reinterpret_cast<uint4*>(tg)[u] = pk;
           }
-        } else if (p.lora_t_out != nullptr && n_blk == 0 && m < p.M) {   // unused columns of the saved copy: zeros
+        } else if (half < 2 && p.lora_t_out != nullptr && n_blk == 0 && m < p.M) {   // unused columns of the saved copy: zeros
           uint4* tg = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.lora_t_out) + static_cast<long long>(m) * kLoraN + half * 32);
 #pragma unroll
           for (int u = 0; u < 4; ++u) tg[u] = make_uint4(0u, 0u, 0u, 0u);
@@ -852,13 +880,13 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmMaps maps, const GemmKernelParam
       const int out_cols = p.act == ACT_GEGLU ? BN / 2 : BN;
       if (p.tma_store && (n_blk + 1) * out_cols <= p.n_store && (BN % 64 == 0 || p.act != ACT_GEGLU)) {
         if (p.act == ACT_GEGLU) {
-          if constexpr (BN % 64 == 0)
-            gemm_epilogue_tma<BN, true, Cfg::kEpiBufs>(p, &maps.out[0], t_row, m, n_blk, half, sbias, stage_buf, buf_sel, release, st);
+          if constexpr (BN % 64 == 0 && kEW == 8)   // (the host never sends a GEGLU GEMM to the 12-warp kernel: two accumulator halves per chunk need the registers)
+            gemm_epilogue_tma<BN, true, Cfg::kEpiBufs, kParts>(p, &maps.out[0], t_row, m, n_blk, half, sbias, stage_buf, buf_sel, release, st);
         } else {
-          gemm_epilogue_tma<BN, false, Cfg::kEpiBufs>(p, &maps.out[ph], t_row, m, n_blk, half, sbias, stage_buf, buf_sel, release, st);
+          gemm_epilogue_tma<BN, false, Cfg::kEpiBufs, kParts>(p, &maps.out[ph], t_row, m, n_blk, half, sbias, stage_buf, buf_sel, release, st);
         }
       } else {
-        gemm_epilogue_rows<BN>(p, t_row, m, n_blk, half, sbias, stage_buf, ksplit > 1 ? static_cast<long long>(tile - t2 * ksplit) * p.M : 0ll);
+        gemm_epilogue_rows<BN>(p, t_row, m, n_blk, half, sbias, stage_buf, ksplit > 1 ? static_cast<long long>(tile - t2 * ksplit) * p.M : 0ll, kParts);
         release();
       }
       GTL(3);

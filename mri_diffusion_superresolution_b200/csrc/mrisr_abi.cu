@@ -142,12 +142,16 @@ struct IdentityTile {
 __device__ const IdentityTile g_identity_tile = IdentityTile(0x3F80);    // bf16 1.0
 __device__ const IdentityTile g_identity_tile_h = IdentityTile(0x3C00);  // IEEE half 1.0 (fp16 residual-stream operands)
 
-template <int BN, bool kPair, bool kLora = false>
+#ifndef MRISR_GEMM_EW12_DEFAULT
+#define MRISR_GEMM_EW12_DEFAULT 0   // off: the isolated GEMMs gain up to 25 % at K = 320, N >= 640 (profiles/r2_gemm_ew12_ab.txt; threshold 6 takes exactly
+                                    // those), but the power-capped 50-step loop does not move (19.846 vs 19.842 / 19.847 vs 19.81 slices/s, same box, alternated)
+#endif
+template <int BN, bool kPair, bool kLora = false, int kEW = 8>
 int launch_gemm(const mrisr::GemmMaps& maps, const mrisr::GemmKernelParams& p, cudaStream_t st) {
-  using Cfg = mrisr::GemmCfg<BN, kPair, kLora>;
+  using Cfg = mrisr::GemmCfg<BN, kPair, kLora, kEW>;
   static bool configured = false;
   if (!configured) {
-    MRISR_CHECK_CUDA(cudaFuncSetAttribute(mrisr::gemm_tcgen05_kernel<BN, kPair, kLora>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MRISR_CHECK_CUDA(cudaFuncSetAttribute(mrisr::gemm_tcgen05_kernel<BN, kPair, kLora, kEW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           Cfg::kSmemBytes));
     configured = true;
   }
@@ -156,7 +160,7 @@ int launch_gemm(const mrisr::GemmMaps& maps, const mrisr::GemmKernelParams& p, c
   const int workers = tiles < max_workers ? tiles : max_workers;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(kPair ? 2 * workers : workers);
-  cfg.blockDim = dim3(mrisr::kGemmThreads);
+  cfg.blockDim = dim3(mrisr::gemm_threads(kEW));
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
@@ -168,16 +172,38 @@ int launch_gemm(const mrisr::GemmMaps& maps, const mrisr::GemmKernelParams& p, c
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl() ? 2 : 1;
-  MRISR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mrisr::gemm_tcgen05_kernel<BN, kPair, kLora>, maps, p));
+  MRISR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mrisr::gemm_tcgen05_kernel<BN, kPair, kLora, kEW>, maps, p));
   return 0;
+}
+
+// Twelve epilogue warps (three per TMEM lane quarter) for the store-heavy small-K GEMMs whose tile loop is paced by the epilogue
+// (gemm_tcgen05.cuh, kEW): CTA-pair kernel, no GEGLU / LoRA / split-K, N >= 640 (at N = 320 the GEMM is bound by its DRAM streams,
+// not by the epilogue: no gain measured), at most `kmax` k-chunks per tile (main + residual operands).  Measured at M = 131072, K = 320:
+// N = 960 116 -> 87 us, N = 1280 151 -> 116 us, N = 640 77 -> 73 us; K >= 640: 0-9 % slower, hence the default threshold of 6.
+// MRISR_GEMM_EW12=<kmax> sets the threshold (0 = never).
+static int ew12_max_kchunks() {
+  static const int v = [] {
+    const char* e = getenv("MRISR_GEMM_EW12");
+    return e != nullptr ? atoi(e) : MRISR_GEMM_EW12_DEFAULT;
+  }();
+  return v;
+}
+static bool takes_ew12(const mrisr::GemmKernelParams& p, int BN) {
+  // (only tiles that leave through the TMA-store epilogue: the generic row epilogue is compiled for 216 registers and spills at 144)
+  if (p.act == mrisr::ACT_GEGLU || p.ksplit > 1 || p.up2x || !p.tma_store || p.n_store != p.N || p.N % BN != 0) return false;
+  const int res_chunks = p.res_mma > 0 ? p.res_mma * ((BN + 63) / 64 + 1) : 0;
+  return p.N >= 640 && p.taps * (p.kc1 + p.kc2) + res_chunks <= ew12_max_kchunks();
 }
 
 template <bool kPair>
 int dispatch_gemm(int BN, const mrisr::GemmMaps& maps, const mrisr::GemmKernelParams& p, cudaStream_t st) {
   switch (BN) {
-    case 256: return launch_gemm<256, kPair>(maps, p, st);
-    case 192: return launch_gemm<192, kPair>(maps, p, st);
-    case 160: return launch_gemm<160, kPair>(maps, p, st);
+    case 256: if (kPair && takes_ew12(p, 256)) return launch_gemm<256, true, false, 12>(maps, p, st);
+              return launch_gemm<256, kPair>(maps, p, st);
+    case 192: if (kPair && takes_ew12(p, 192)) return launch_gemm<192, true, false, 12>(maps, p, st);
+              return launch_gemm<192, kPair>(maps, p, st);
+    case 160: if (kPair && takes_ew12(p, 160)) return launch_gemm<160, true, false, 12>(maps, p, st);
+              return launch_gemm<160, kPair>(maps, p, st);
     case 128: return launch_gemm<128, kPair>(maps, p, st);
     default: return launch_gemm<64, kPair>(maps, p, st);
   }

@@ -655,3 +655,24 @@ def test_gemm_split_k_plain_and_ragged_store(ops):
     assert out.dtype == torch.float32 and _rel(out, ref) < 1e-5
     out2 = ops.gemm(a, w, n_store=1000)
     assert tuple(out2.shape) == (M, 1000) and _rel(out2, ref[:, :1000]) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------ 12-epilogue-warp GEMM (opt-in)
+def test_gemm_twelve_epilogue_warps_subprocess():
+    """The opt-in kernel variant with three epilogue warps per TMEM lane quarter (MRISR_GEMM_EW12, read once per process, hence
+    the subprocess): tiles of 160 / 192 / 256 columns, with and without a residual operand, ragged M, against a torch fp32 product
+    (scripts/gemm_ew12_ab.py prints the relative L2 error per shape); tolerance = the bf16 output rounding, 4e-3."""
+    import os
+    import re
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MRISR_GEMM_EW12="24")
+    shapes = ["4096,640,320", "4096,960,320", "8192,1280,320,res", "2048,1280,1280", "1000,640,320", "512,320,320,res"]
+    res = subprocess.run([sys.executable, os.path.join(root, "scripts", "gemm_ew12_ab.py"), *shapes], env=env, capture_output=True,
+                         text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    errs = [float(x) for x in re.findall(r"rel-L2 vs fp32 ([0-9.e+-]+)", res.stdout)]
+    assert len(errs) == len(shapes), res.stdout
+    assert max(errs) <= 4e-3, res.stdout
