@@ -3,6 +3,7 @@ bit-exact against the oracle, weight re-layouts are exact, the product refuses C
 sharding works under a 2-rank gloo group."""
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -308,3 +309,24 @@ def test_mnist_model_oracle_follows_the_notebook_skeleton():
     x2 = x.clone(); x2[:, 1] = 0
     assert not torch.allclose(out, mo.model_forward(params, x2, t, y), atol=1e-4)
     torch.testing.assert_close(mo.sinusoidal(torch.tensor([0, 5]))[0], torch.cat([torch.zeros(16), torch.ones(16)]))
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the same metric / unit as our arm,
+    `impl`, a `cpu_baseline` describing the run and a zero-copy `e2e`; it drives the oracle's restatement of the reference loop
+    (src/adapters/res_srdiff.py:58-96) and launches nothing on a GPU."""
+    import json
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "slices/s" and line["higher_is_better"] is True
+    assert line["metric"].startswith("MRI slices/sec") and line["config"]["workload"] == "sd15_unet_lora16_t2iadapter_512px_50step"
+    assert line["value"] > 0 and abs(line["ms_per_step"] * line["value"] - 1000.0) < 1e-6 * 1000.0
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "reference loop" in cb["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0
