@@ -330,3 +330,23 @@ def test_reference_arm_prints_the_contract_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "reference loop" in cb["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["gpu_launches"] == 0
+
+
+def test_roofline_traffic_file_follows_from_the_committed_ncu_launch_list(tmp_path):
+    """`bench.py` takes `roofline.traffic` from profiles/r2_traffic_b32.json; that file must be exactly what
+    scripts/traffic_from_ncu.py derives from the committed ncu launch list (nothing hand-edited, nothing hard-coded)."""
+    import json
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "traffic.json"
+    res = subprocess.run([sys.executable, os.path.join(root, "scripts", "traffic_from_ncu.py"),
+                          os.path.join("profiles", "r2_launches_step_b32.csv"), "661e0b5", str(out)], capture_output=True, text=True, cwd=root)
+    assert res.returncode == 0, res.stderr
+    got = json.load(open(out))
+    want = json.load(open(os.path.join(root, "profiles", "r2_traffic_b32.json")))
+    assert got["batch"] == want["batch"] == 32 and set(got["classes"]) == set(want["classes"])
+    for k, v in want["classes"].items():
+        assert got["classes"][k]["launches"] == v["launches"]
+        assert abs(got["classes"][k]["dram_bytes"] - v["dram_bytes"]) <= 1e-9 * max(1.0, v["dram_bytes"])
+    assert want["classes"]["gemm"]["launches"] > 150 and want["classes"]["attn_self_d40"]["launches"] == 5
