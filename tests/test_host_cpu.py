@@ -350,3 +350,31 @@ def test_roofline_traffic_file_follows_from_the_committed_ncu_launch_list(tmp_pa
         assert got["classes"][k]["launches"] == v["launches"]
         assert abs(got["classes"][k]["dram_bytes"] - v["dram_bytes"]) <= 1e-9 * max(1.0, v["dram_bytes"])
     assert want["classes"]["gemm"]["launches"] > 150 and want["classes"]["attn_self_d40"]["launches"] == 5
+
+
+def test_committed_bench_lines_are_self_consistent():
+    """Every headline line kept under profiles/ must follow from its own numbers: whole-step TFLOP/s = slices/s x algorithmic
+    TFLOP per slice / GPUs, its fraction = that / the sustained peak, each roofline class's frac = achieved / peak, and
+    ms_per_step x value = slices per step."""
+    import json
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    n = 0
+    for raw in open(os.path.join(root, "profiles", "r2_bench_lines.jsonl")):
+        raw = raw.strip()
+        if not raw.startswith("{"):
+            continue
+        d = json.loads(raw)
+        if d.get("config", {}).get("workload", "").startswith("sd15_unet_lora16") and "finetune" not in d["config"]["workload"] and "whole_step" in d:
+            ws = d["whole_step"]
+            want = d["value"] * ws["algorithmic_tflop_per_slice"] / d["n_gpus"]
+            assert abs(ws["achieved_tflops_per_gpu"] - want) <= 1e-6 * want
+            assert abs(ws["frac_of_sustained_peak"] - want / 1407.6) <= 2e-3    # (MEASURED_PEAKS.json: 1407.6 sustained bf16 TFLOP/s)
+            slices_per_step = d["config"]["global_batch"]
+            assert abs(d["ms_per_step"] * d["value"] / 1e3 - slices_per_step) <= 1e-6 * slices_per_step
+            n += 1
+        roof = d.get("roofline")
+        for c in ([roof] + list(roof.get("classes", []))) if isinstance(roof, dict) else []:
+            if c.get("achieved") and c.get("peak"):
+                assert abs(c["frac"] - c["achieved"] / c["peak"]) <= 1e-9 + 1e-6 * c["frac"]
+    assert n >= 3
